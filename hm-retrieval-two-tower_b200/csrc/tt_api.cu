@@ -1,0 +1,261 @@
+// tt_api.cu -- library plumbing and the small element-wise entry points of tt.h.
+#include <stdarg.h>
+
+#include "tt_common.cuh"
+
+namespace tt {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+// ---- kernels ----------------------------------------------------------------------------------
+__global__ void fill_kernel(float* __restrict__ p, float v, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+__global__ void log_kernel(const float* __restrict__ p, float* __restrict__ out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = logf(p[i]);
+}
+
+__global__ void logq_apply_kernel(const float* __restrict__ L, int ldl, const float* __restrict__ bias, int Bq, int Bc,
+                                  float* __restrict__ Z, int ldz) {
+    int64_t total = (int64_t)Bq * Bc;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int r = (int)(i / Bc), c = (int)(i % Bc);
+        float b = bias ? bias[c] : 0.0f;
+        Z[(int64_t)r * ldz + c] = __fsub_rn(L[(int64_t)r * ldl + c], b);
+    }
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int64_t rows,
+                                  int cols) {
+    int64_t total = rows * cols;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int64_t r = i / cols;
+        int c = (int)(i % cols);
+        dst[r * ldd + c] = tf32_rn(src[r * lds + c]);
+    }
+}
+
+// ResourceApplyAdagradV2: acc += g*g; w -= (g*lr)/(sqrt(acc)+eps).  Every op individually rounded
+// (no FMA contraction) so the result is bit-identical to the numpy oracle.
+__global__ void dense_adagrad_kernel(float* __restrict__ w, float* __restrict__ acc, const float* __restrict__ g, int64_t n,
+                                     float lr, float eps) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float gi = g[i];
+        float a = __fadd_rn(acc[i], __fmul_rn(gi, gi));
+        acc[i] = a;
+        w[i] = __fsub_rn(w[i], __fdiv_rn(__fmul_rn(gi, lr), __fadd_rn(__fsqrt_rn(a), eps)));
+    }
+}
+
+// ResourceApplyAdam: m += (g-m)(1-b1); v += (g*g-v)(1-b2); w -= (m*lr_t)/(sqrt(v)+eps)
+__global__ void dense_adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                                  const float* __restrict__ g, int64_t n, float lr_t, float omb1, float omb2, float eps) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float gi = g[i];
+        float mi = __fadd_rn(m[i], __fmul_rn(__fsub_rn(gi, m[i]), omb1));
+        float vi = __fadd_rn(v[i], __fmul_rn(__fsub_rn(__fmul_rn(gi, gi), v[i]), omb2));
+        m[i] = mi;
+        v[i] = vi;
+        w[i] = __fsub_rn(w[i], __fdiv_rn(__fmul_rn(mi, lr_t), __fadd_rn(__fsqrt_rn(vi), eps)));
+    }
+}
+
+// hits[t] += #{(b, j<ks[t]) : cand[b][j] == true[b]} -- integer, exact; one block-level reduction and
+// a single integer atomicAdd per (block, k) (integer adds commute, so the result is deterministic).
+struct KsArg {
+    int32_t ks[TT_MAX_KS];
+};
+
+__global__ void recall_hits_kernel(const int32_t* __restrict__ cand, int k_stride, const int32_t* __restrict__ truth, int nq,
+                                   KsArg ks, int nk, int32_t* __restrict__ hits) {
+    __shared__ int32_t s_hits[TT_MAX_KS];
+    if (threadIdx.x < TT_MAX_KS) s_hits[threadIdx.x] = 0;
+    __syncthreads();
+    int32_t local[TT_MAX_KS];
+#pragma unroll
+    for (int t = 0; t < TT_MAX_KS; ++t) local[t] = 0;
+    // one warp per query row; lanes stride over the k_stride candidates
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int b = warp; b < nq; b += nwarps) {
+        int32_t t_id = truth[b];
+        for (int j = lane; j < k_stride; j += 32) {
+            if (cand[(int64_t)b * k_stride + j] == t_id) {
+#pragma unroll
+                for (int t = 0; t < TT_MAX_KS; ++t)
+                    if (t < nk && j < ks.ks[t]) local[t]++;
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < TT_MAX_KS; ++t) {
+        if (t < nk) {
+            int32_t v = local[t];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && v) atomicAdd(&s_hits[t], v);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < nk && s_hits[threadIdx.x]) atomicAdd(&hits[threadIdx.x], s_hits[threadIdx.x]);
+}
+
+// max_j ||corpus_j||_2 : per-row norm, block max, then atomicMax on the float bit pattern (all >= 0)
+__global__ void corpus_max_norm_kernel(const float* __restrict__ C, int ldc, int64_t n, int E, float* __restrict__ out) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float best = 0.0f;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        float s = 0.0f;
+        for (int k = lane; k < E; k += 32) {
+            float v = C[r * ldc + k];
+            s = fmaf(v, v, s);
+        }
+        s = warp_sum(s);
+        best = fmaxf(best, sqrtf(s));
+    }
+    best = warp_max(best);
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(best));
+}
+
+static inline int grid_for(int64_t n, int block) {
+    int64_t g = ceil_div(n, block);
+    int64_t cap = (int64_t)sm_count() * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" {
+
+int tt_version(void) { return 100; }
+
+const char* tt_last_error(void) { return tt::g_err; }
+
+int tt_device_supports_tc(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}
+
+int tt_fill_f32(float* p, float value, int64_t n, void* stream) {
+    TT_REQUIRE(p != nullptr || n == 0, "tt_fill_f32: null pointer");
+    if (n == 0) return TT_OK;
+    fill_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(p, value, n);
+    TT_LAUNCH_OK("fill_kernel");
+    return TT_OK;
+}
+
+int tt_log_f32(const float* p, float* out, int64_t n, void* stream) {
+    TT_REQUIRE((p && out) || n == 0, "tt_log_f32: null pointer");
+    if (n == 0) return TT_OK;
+    log_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(p, out, n);
+    TT_LAUNCH_OK("log_kernel");
+    return TT_OK;
+}
+
+int tt_logq_apply(const float* logits, int ldl, const float* col_bias, int Bq, int Bc, float* Z, int ldz, void* stream) {
+    TT_REQUIRE(logits && Z, "tt_logq_apply: null pointer");
+    TT_REQUIRE(Bq >= 0 && Bc >= 0 && ldl >= Bc && ldz >= Bc, "tt_logq_apply: bad shape");
+    if ((int64_t)Bq * Bc == 0) return TT_OK;
+    logq_apply_kernel<<<grid_for((int64_t)Bq * Bc, 256), 256, 0, as_stream(stream)>>>(logits, ldl, col_bias, Bq, Bc, Z, ldz);
+    TT_LAUNCH_OK("logq_apply_kernel");
+    return TT_OK;
+}
+
+int tt_round_tf32(const float* src, int lds, float* dst, int ldd, int64_t rows, int cols, void* stream) {
+    TT_REQUIRE(src && dst, "tt_round_tf32: null pointer");
+    TT_REQUIRE(rows >= 0 && cols >= 0 && lds >= cols && ldd >= cols, "tt_round_tf32: bad shape");
+    if (rows * cols == 0) return TT_OK;
+    round_tf32_kernel<<<grid_for(rows * cols, 256), 256, 0, as_stream(stream)>>>(src, lds, dst, ldd, rows, cols);
+    TT_LAUNCH_OK("round_tf32_kernel");
+    return TT_OK;
+}
+
+int tt_dense_adagrad(float* w, float* acc, const float* g, int64_t n, float lr, float eps, void* stream) {
+    TT_REQUIRE((w && acc && g) || n == 0, "tt_dense_adagrad: null pointer");
+    if (n == 0) return TT_OK;
+    dense_adagrad_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, acc, g, n, lr, eps);
+    TT_LAUNCH_OK("dense_adagrad_kernel");
+    return TT_OK;
+}
+
+int tt_dense_adam(float* w, float* m, float* v, const float* g, int64_t n, float lr_t, float beta1, float beta2, float eps,
+                  void* stream) {
+    TT_REQUIRE((w && m && v && g) || n == 0, "tt_dense_adam: null pointer");
+    if (n == 0) return TT_OK;
+    dense_adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, m, v, g, n, lr_t, 1.0f - beta1, 1.0f - beta2, eps);
+    TT_LAUNCH_OK("dense_adam_kernel");
+    return TT_OK;
+}
+
+int tt_recall_hits(const int32_t* cand, int k_stride, const int32_t* true_idx, int nq, const int32_t* ks, int nk,
+                   int32_t* hits, void* stream) {
+    TT_REQUIRE(cand && true_idx && ks && hits, "tt_recall_hits: null pointer");
+    TT_REQUIRE(nk >= 1 && nk <= TT_MAX_KS, "tt_recall_hits: nk must be in [1,%d]", TT_MAX_KS);
+    TT_REQUIRE(nq >= 0 && k_stride >= 1, "tt_recall_hits: bad shape");
+    if (nq == 0) return TT_OK;
+    KsArg a;
+    for (int t = 0; t < TT_MAX_KS; ++t) a.ks[t] = t < nk ? ks[t] : 0;
+    int block = 256;
+    int grid = (int)ceil_div((int64_t)nq * 32, block);
+    int cap = sm_count() * 4;
+    if (grid > cap) grid = cap;
+    recall_hits_kernel<<<grid, block, 0, as_stream(stream)>>>(cand, k_stride, true_idx, nq, a, nk, hits);
+    TT_LAUNCH_OK("recall_hits_kernel");
+    return TT_OK;
+}
+
+int tt_corpus_max_norm(const float* corpus, int ldc, int64_t n, int E, float* out, void* stream) {
+    TT_REQUIRE(corpus && out, "tt_corpus_max_norm: null pointer");
+    TT_REQUIRE(n >= 0 && E >= 1 && ldc >= E, "tt_corpus_max_norm: bad shape");
+    TT_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), as_stream(stream)));
+    if (n == 0) return TT_OK;
+    int block = 256;
+    int grid = (int)ceil_div(n * 32, block);
+    int cap = sm_count() * 8;
+    if (grid > cap) grid = cap;
+    corpus_max_norm_kernel<<<grid, block, 0, as_stream(stream)>>>(corpus, ldc, n, E, out);
+    TT_LAUNCH_OK("corpus_max_norm_kernel");
+    return TT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// tt_common.cuh -- shared helpers for libtt.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "tt.h"
+
+namespace tt {
+
+void set_error(const char* fmt, ...);
+
+#define TT_REQUIRE(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            tt::set_error(__VA_ARGS__);       \
+            return TT_ERR_ARG;                \
+        }                                     \
+    } while (0)
+
+#define TT_CUDA_OK(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            tt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return TT_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+// after a kernel launch: surfaces launch-configuration errors without synchronising
+#define TT_LAUNCH_OK(name)                                                                    \
+    do {                                                                                      \
+        cudaError_t _e = cudaPeekAtLastError();                                               \
+        if (_e != cudaSuccess) {                                                              \
+            tt::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));           \
+            (void)cudaGetLastError();                                                         \
+            return TT_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();
+
+// carve a caller-provided workspace
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(reinterpret_cast<char*>(p)) {}
+    template <typename T>
+    T* take(size_t n) {
+        off = align_up(off, 256);
+        T* r = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return r;
+    }
+};
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// strict ordering of the tf.math.top_k contract: higher score first, then lower index
+__device__ __forceinline__ bool ranks_before(float sa, int32_t ia, float sb, int32_t ib) {
+    return (sa > sb) || (sa == sb && ia < ib);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace tt

@@ -1,0 +1,96 @@
+// tt_softmax.cu -- C-ABI dispatch for the in-batch sampled softmax (tt.h).
+#include "tt_common.cuh"
+
+namespace tt {
+// tt_softmax_simt.cu
+int softmax_fwd_simt(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse,
+                     float* loss, float* rowloss, cudaStream_t st);
+int softmax_bwd_pass_simt(const float* R, int ldr, const float* T, int ldt, const float* rowv, const float* colv, int nR, int nT, int E,
+                          int d, float* G, int ldg, cudaStream_t st);
+int logits_simt(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, float* Z, int ldz,
+                cudaStream_t st);
+// tt_softmax_tc.cu
+bool softmax_tc_supported(int ldq, int ldc, int E, const void* Q, const void* C);
+int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse,
+                   float* loss, float* rowloss, cudaStream_t st);
+int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const float* rowv, const float* colv, int nR, int nT, int E,
+                        int d, float* G, int ldg, cudaStream_t st);
+
+static int pick_impl(int impl, int ldq, int ldc, int E, const void* Q, const void* C, const char* who) {
+    if (impl == TT_IMPL_SIMT) return TT_IMPL_SIMT;
+    bool ok = softmax_tc_supported(ldq, ldc, E, Q, C);
+    if (impl == TT_IMPL_TC) {
+        if (!ok) {
+            set_error("%s: TT_IMPL_TC needs an sm_100 device, E in {32,64,128}, 16-byte aligned rows (ld %% 4 == 0)", who);
+            return TT_ERR_UNSUPPORTED;
+        }
+        return TT_IMPL_TC;
+    }
+    return ok ? TT_IMPL_TC : TT_IMPL_SIMT;
+}
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" {
+
+size_t tt_softmax_workspace_bytes(int Bq, int Bc, int E) {
+    (void)E;
+    size_t rows = (size_t)(Bq > Bc ? Bq : Bc);
+    return align_up(rows * sizeof(float), 256) + 512;
+}
+
+int tt_inbatch_softmax_fwd(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, int Bq, int Bc, int E,
+                           int diag_offset, float* lse, float* loss, void* ws, size_t ws_bytes, int impl, void* stream) {
+    TT_REQUIRE(Q && C && lse && loss, "tt_inbatch_softmax_fwd: null pointer");
+    TT_REQUIRE(Bq >= 0 && Bc >= 0 && E >= 1 && ldq >= E && ldc >= E, "tt_inbatch_softmax_fwd: bad shape");
+    TT_REQUIRE(diag_offset >= 0 && (Bq == 0 || diag_offset + Bq <= Bc), "tt_inbatch_softmax_fwd: positives (row i -> column i+%d) fall outside Bc=%d", diag_offset, Bc);
+    TT_REQUIRE(ws && ws_bytes >= tt_softmax_workspace_bytes(Bq, Bc, E), "tt_inbatch_softmax_fwd: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    if (Bq == 0) {
+        TT_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), st));
+        return TT_OK;
+    }
+    int use = pick_impl(impl, ldq, ldc, E, Q, C, "tt_inbatch_softmax_fwd");
+    if (use < 0) return use;
+    float* rowloss = reinterpret_cast<float*>(ws);
+    if (use == TT_IMPL_TC) return softmax_fwd_tc(Q, ldq, C, ldc, col_bias, Bq, Bc, E, diag_offset, lse, loss, rowloss, st);
+    return softmax_fwd_simt(Q, ldq, C, ldc, col_bias, Bq, Bc, E, diag_offset, lse, loss, rowloss, st);
+}
+
+int tt_inbatch_softmax_bwd(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, const float* lse, int Bq, int Bc,
+                           int E, int diag_offset, float* dQ, int lddq, float* dC, int lddc, void* ws, size_t ws_bytes, int impl,
+                           void* stream) {
+    (void)ws;
+    (void)ws_bytes;
+    TT_REQUIRE(Q && C && lse && dQ && dC, "tt_inbatch_softmax_bwd: null pointer");
+    TT_REQUIRE(Bq >= 0 && Bc >= 0 && E >= 1 && ldq >= E && ldc >= E && lddq >= E && lddc >= E, "tt_inbatch_softmax_bwd: bad shape");
+    TT_REQUIRE(diag_offset >= 0 && (Bq == 0 || diag_offset + Bq <= Bc), "tt_inbatch_softmax_bwd: bad diag_offset");
+    cudaStream_t st = as_stream(stream);
+    int use = pick_impl(impl, ldq, ldc, E, Q, C, "tt_inbatch_softmax_bwd");
+    if (use < 0) return use;
+    if (Bq == 0) {
+        if (Bc > 0) TT_CUDA_OK(cudaMemset2DAsync(dC, sizeof(float) * lddc, 0, sizeof(float) * E, Bc, st));
+        return TT_OK;
+    }
+    int rc;
+    if (use == TT_IMPL_TC) {
+        rc = softmax_bwd_pass_tc(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, dQ, lddq, st);
+        if (rc) return rc;
+        return softmax_bwd_pass_tc(C, ldc, Q, ldq, col_bias, lse, Bc, Bq, E, -diag_offset, dC, lddc, st);
+    }
+    rc = softmax_bwd_pass_simt(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, dQ, lddq, st);
+    if (rc) return rc;
+    return softmax_bwd_pass_simt(C, ldc, Q, ldq, col_bias, lse, Bc, Bq, E, -diag_offset, dC, lddc, st);
+}
+
+int tt_logits(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, int Bq, int Bc, int E, float* Z, int ldz,
+              int impl, void* stream) {
+    (void)impl;  // the materialised matrix is an API/test convenience: always the exact path
+    TT_REQUIRE(Q && C && Z, "tt_logits: null pointer");
+    TT_REQUIRE(Bq >= 0 && Bc >= 0 && E >= 1 && ldq >= E && ldc >= E && ldz >= Bc, "tt_logits: bad shape");
+    if (Bq == 0 || Bc == 0) return TT_OK;
+    return logits_simt(Q, ldq, C, ldc, col_bias, Bq, Bc, E, Z, ldz, as_stream(stream));
+}
+
+}  // extern "C"

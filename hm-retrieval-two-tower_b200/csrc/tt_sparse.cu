@@ -1,0 +1,372 @@
+// tt_sparse.cu -- deterministic sparse embedding-gradient update.
+//
+// Replaces (reference file:line): two_tower_model.py:124 (optimizer.minimize) for the Embedding
+// tables of input_layer.py:37-40, i.e. tf-keras 2.16 legacy OptimizerV2:
+//   IndexedSlices (duplicates not merged) -> _deduplicate_indexed_slices (Unique + UnsortedSegmentSum)
+//   -> ResourceSparseApplyAdagradV2 / Adam._resource_apply_sparse          (optimizer_factory.py:15-18)
+//
+// Determinism: no floating-point atomics anywhere.  (id, position) pairs are ordered by a stable LSD
+// radix sort (8-bit digits, only as many passes as the table's row count needs); each run of equal
+// ids is then summed by ONE warp in ascending position order and the row is written once.
+// The summation order equals oracle/two_tower_oracle.py:dedup_indexed_slices, so the updated rows are
+// bit-identical to the oracle given identical gradients.
+#include "tt_common.cuh"
+
+namespace tt {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kItems = 8;                          // keys per thread
+constexpr int kTile = kSortThreads * kItems;       // 2048 keys per CTA
+constexpr int kRadix = 256;
+
+struct JobArr {
+    tt_sparse_job j[TT_MAX_JOBS];
+    int n;
+};
+
+struct SortPlan {  // per-job workspace pointers
+    uint32_t* keys[2];
+    int32_t* vals[2];
+    uint32_t* hist;  // [kRadix][ntiles]
+    int32_t n;       // elements
+    int32_t ntiles;
+    int32_t npass;
+};
+struct PlanArr {
+    SortPlan p[TT_MAX_JOBS];
+    int n;
+};
+
+static int passes_for_rows(int rows) {
+    int bits = 1;
+    while (bits < 31 && (1ll << bits) < (long long)rows) ++bits;
+    return (bits + 7) / 8;
+}
+
+__device__ __forceinline__ uint32_t load_key(const tt_sparse_job& job, int i) {
+    int src = i / job.n_per_src, r = i - src * job.n_per_src;
+    int id = __ldg(job.ids[src] + r);
+    if ((unsigned)id >= (unsigned)job.rows) id = 0;  // out-of-range -> OOV row, as in the forward gather
+    return (uint32_t)id;
+}
+
+// ---- pass kernels (blockIdx.y = job, blockIdx.x = tile) ---------------------------------------------
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans,
+                                                                 int pass) {
+    const SortPlan& pl = plans.p[blockIdx.y];
+    if (pass >= pl.npass || (int)blockIdx.x >= pl.ntiles) return;
+    __shared__ uint32_t s_hist[kRadix];
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * kTile;
+    const uint32_t* kin = pl.keys[pass & 1];
+    const int shift = pass * 8;
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+        int i = base + it * kSortThreads + threadIdx.x;
+        if (i < pl.n) {
+            uint32_t key = pass == 0 ? load_key(jobs.j[blockIdx.y], i) : kin[i];
+            atomicAdd(&s_hist[(key >> shift) & 0xff], 1u);  // integer: order-independent
+        }
+    }
+    __syncthreads();
+    pl.hist[(size_t)threadIdx.x * pl.ntiles + blockIdx.x] = s_hist[threadIdx.x];
+}
+
+// exclusive scan of hist viewed as one array of kRadix*ntiles entries (digit-major): one CTA per job
+__global__ void __launch_bounds__(1024) sort_scan_kernel(const __grid_constant__ PlanArr plans, int pass) {
+    const SortPlan& pl = plans.p[blockIdx.x];
+    if (pass >= pl.npass) return;
+    __shared__ uint32_t s_part[1024];
+    const int total = kRadix * pl.ntiles;
+    const int per = (total + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(total, b + per);
+    uint32_t sum = 0;
+    for (int i = b; i < e; ++i) sum += pl.hist[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int o = 1; o < 1024; o <<= 1) {
+        uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = threadIdx.x ? s_part[threadIdx.x - 1] : 0u;
+    for (int i = b; i < e; ++i) {
+        uint32_t c = pl.hist[i];
+        pl.hist[i] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans,
+                                                                    int pass) {
+    const SortPlan& pl = plans.p[blockIdx.y];
+    if (pass >= pl.npass || (int)blockIdx.x >= pl.ntiles) return;
+    __shared__ uint32_t s_wcount[kSortWarps][kRadix];
+    for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&s_wcount[0][0])[i] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int base = blockIdx.x * kTile + warp * (kTile / kSortWarps);  // each warp owns 256 consecutive keys
+    const uint32_t* kin = pl.keys[pass & 1];
+    const int32_t* vin = pl.vals[pass & 1];
+    uint32_t* kout = pl.keys[(pass + 1) & 1];
+    int32_t* vout = pl.vals[(pass + 1) & 1];
+    const int shift = pass * 8;
+    uint32_t key[kItems];
+    int32_t val[kItems];
+    uint32_t rank[kItems];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+        int i = base + it * 32 + lane;
+        bool ok = i < pl.n;
+        key[it] = 0;
+        val[it] = 0;
+        if (ok) {
+            if (pass == 0) { key[it] = load_key(jobs.j[blockIdx.y], i); val[it] = i; }
+            else { key[it] = kin[i]; val[it] = vin[i]; }
+        }
+        uint32_t digit = ok ? ((key[it] >> shift) & 0xff) : 0xffffffffu;  // invalid lanes group together
+        uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (ok && lane == leader) old = s_wcount[warp][digit];
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[it] = old + __popc(peers & lt);
+        if (ok && lane == leader) s_wcount[warp][digit] = old + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over warps, plus the global base of (digit, tile)
+    {
+        const int d = threadIdx.x;  // kSortThreads == kRadix
+        uint32_t run = pl.hist[(size_t)d * pl.ntiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            uint32_t c = s_wcount[w][d];
+            s_wcount[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+        int i = base + it * 32 + lane;
+        if (i < pl.n) {
+            uint32_t pos = s_wcount[warp][(key[it] >> shift) & 0xff] + rank[it];
+            kout[pos] = key[it];
+            vout[pos] = val[it];
+        }
+    }
+}
+
+// ---- segmented reduce + row update: one warp per run of equal ids --------------------------------------
+__device__ __forceinline__ const float* grad_row(const tt_sparse_job& job, int pos) {
+    int src = pos / job.n_per_src, r = pos - src * job.n_per_src;
+    return job.grad[src] + (int64_t)r * job.grad_ld[src];
+}
+
+enum { kModeAdagrad = 0, kModeAdamMoments = 1 };
+
+template <int kMode>
+__global__ void __launch_bounds__(256) sparse_apply_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans, float lr,
+                                                           float eps, float omb1, float omb2) {
+    const SortPlan& pl = plans.p[blockIdx.y];
+    const tt_sparse_job& job = jobs.j[blockIdx.y];
+    const uint32_t* ks = pl.keys[pl.npass & 1];
+    const int32_t* vs = pl.vals[pl.npass & 1];
+    const int lane = threadIdx.x & 31;
+    const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int e = job.e;
+    for (int i = warp0; i < pl.n; i += nwarps) {
+        const uint32_t id = ks[i];
+        if (i > 0 && ks[i - 1] == id) continue;  // not the head of its run
+        // run length: 32 keys at a time
+        int len = 1;
+        for (;;) {
+            int j = i + len + lane;
+            bool same = j < pl.n && ks[j] == id;
+            uint32_t m = __ballot_sync(0xffffffffu, same);
+            if (m == 0xffffffffu) { len += 32; continue; }
+            len += __ffs(~m) - 1;
+            break;
+        }
+        for (int c = lane; c < e; c += 32) {
+            // ascending-position sequential sum (sort is stable), loads batched 4 deep for latency
+            float g = 0.f;
+            int j = 0;
+            for (; j + 4 <= len; j += 4) {
+                float g0 = __ldg(grad_row(job, vs[i + j]) + c);
+                float g1 = __ldg(grad_row(job, vs[i + j + 1]) + c);
+                float g2 = __ldg(grad_row(job, vs[i + j + 2]) + c);
+                float g3 = __ldg(grad_row(job, vs[i + j + 3]) + c);
+                g = __fadd_rn(g, g0);
+                g = __fadd_rn(g, g1);
+                g = __fadd_rn(g, g2);
+                g = __fadd_rn(g, g3);
+            }
+            for (; j < len; ++j) g = __fadd_rn(g, __ldg(grad_row(job, vs[i + j]) + c));
+            const int64_t o = (int64_t)id * e + c;
+            if (kMode == kModeAdagrad) {
+                float a = __fadd_rn(job.slot0[o], __fmul_rn(g, g));
+                job.slot0[o] = a;
+                job.table[o] = __fsub_rn(job.table[o], __fdiv_rn(__fmul_rn(g, lr), __fadd_rn(__fsqrt_rn(a), eps)));
+            } else {  // Adam: scatter-add into the already decayed moments
+                job.slot0[o] = __fadd_rn(job.slot0[o], __fmul_rn(g, omb1));
+                job.slot1[o] = __fadd_rn(job.slot1[o], __fmul_rn(__fmul_rn(g, g), omb2));
+            }
+        }
+    }
+}
+
+// Adam whole-table sweeps (legacy Adam is not lazy): phase 0: m *= b1, v *= b2; phase 1: w -= (m*lr_t)/(sqrt(v)+eps)
+__global__ void __launch_bounds__(256) adam_sweep_kernel(const __grid_constant__ JobArr jobs, int phase, float b1, float b2, float lr_t,
+                                                         float eps) {
+    const tt_sparse_job& job = jobs.j[blockIdx.y];
+    const int64_t total = (int64_t)job.rows * job.e;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+        if (phase == 0) {
+            job.slot0[i] = __fmul_rn(job.slot0[i], b1);
+            job.slot1[i] = __fmul_rn(job.slot1[i], b2);
+        } else {
+            job.table[i] = __fsub_rn(job.table[i], __fdiv_rn(__fmul_rn(job.slot0[i], lr_t), __fadd_rn(__fsqrt_rn(job.slot1[i]), eps)));
+        }
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------
+static size_t per_job_bytes(int max_n) {
+    size_t n = (size_t)(max_n > 0 ? max_n : 1);
+    size_t ntiles = (n + kTile - 1) / kTile;
+    return 4 * align_up(n * 4, 256) + align_up(ntiles * kRadix * 4, 256);
+}
+
+static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, JobArr* ja, PlanArr* pa, int* max_tiles,
+                      int* max_pass, const char* who) {
+    TT_REQUIRE(jobs != nullptr && njobs >= 1 && njobs <= TT_MAX_JOBS, "%s: njobs must be in [1,%d]", who, TT_MAX_JOBS);
+    memset(ja, 0, sizeof(*ja));
+    memset(pa, 0, sizeof(*pa));
+    ja->n = pa->n = njobs;
+    int max_n = 0;
+    for (int j = 0; j < njobs; ++j) {
+        const tt_sparse_job& jb = jobs[j];
+        TT_REQUIRE(jb.table && jb.slot0 && jb.rows >= 1 && jb.e >= 1, "%s: job %d malformed", who, j);
+        TT_REQUIRE(jb.nsrc >= 1 && jb.nsrc <= TT_MAX_SRC && jb.n_per_src >= 0, "%s: job %d nsrc/n_per_src out of range", who, j);
+        TT_REQUIRE((int64_t)jb.nsrc * jb.n_per_src < (1ll << 31), "%s: job %d too many rows", who, j);
+        for (int s = 0; s < jb.nsrc; ++s) TT_REQUIRE(jb.n_per_src == 0 || (jb.ids[s] && jb.grad[s] && jb.grad_ld[s] >= jb.e), "%s: job %d source %d malformed", who, j, s);
+        ja->j[j] = jb;
+        int n = jb.nsrc * jb.n_per_src;
+        if (n > max_n) max_n = n;
+    }
+    size_t per = per_job_bytes(max_n);
+    TT_REQUIRE(ws != nullptr && ws_bytes >= per * (size_t)njobs, "%s: workspace too small (%zu < %zu)", who, ws_bytes, per * (size_t)njobs);
+    *max_tiles = 0;
+    *max_pass = 0;
+    for (int j = 0; j < njobs; ++j) {
+        char* base = reinterpret_cast<char*>(ws) + per * (size_t)j;
+        size_t seg = align_up((size_t)(max_n > 0 ? max_n : 1) * 4, 256);
+        SortPlan& p = pa->p[j];
+        p.keys[0] = reinterpret_cast<uint32_t*>(base);
+        p.keys[1] = reinterpret_cast<uint32_t*>(base + seg);
+        p.vals[0] = reinterpret_cast<int32_t*>(base + 2 * seg);
+        p.vals[1] = reinterpret_cast<int32_t*>(base + 3 * seg);
+        p.hist = reinterpret_cast<uint32_t*>(base + 4 * seg);
+        p.n = jobs[j].nsrc * jobs[j].n_per_src;
+        p.ntiles = (int)ceil_div(p.n, kTile);
+        p.npass = passes_for_rows(jobs[j].rows);
+        if (p.ntiles > *max_tiles) *max_tiles = p.ntiles;
+        if (p.npass > *max_pass) *max_pass = p.npass;
+    }
+    return TT_OK;
+}
+
+static int apply_grid(const PlanArr& pa) {
+    int max_n = 0;
+    for (int j = 0; j < pa.n; ++j) max_n = pa.p[j].n > max_n ? pa.p[j].n : max_n;
+    int64_t g = ceil_div((int64_t)max_n, 256 / 32);
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" {
+
+size_t tt_sparse_workspace_bytes(int njobs, int max_n) {
+    if (njobs < 1) njobs = 1;
+    return per_job_bytes(max_n) * (size_t)njobs + 256;
+}
+
+int tt_sparse_sort(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, void* stream) {
+    JobArr ja;
+    PlanArr pa;
+    int max_tiles = 0, max_pass = 0;
+    int rc = make_plans(jobs, njobs, ws, ws_bytes, &ja, &pa, &max_tiles, &max_pass, "tt_sparse_sort");
+    if (rc) return rc;
+    if (max_tiles == 0) return TT_OK;
+    cudaStream_t st = as_stream(stream);
+    for (int pass = 0; pass < max_pass; ++pass) {
+        dim3 grid((unsigned)max_tiles, (unsigned)njobs);
+        sort_hist_kernel<<<grid, kSortThreads, 0, st>>>(ja, pa, pass);
+        TT_LAUNCH_OK("sort_hist_kernel");
+        sort_scan_kernel<<<(unsigned)njobs, 1024, 0, st>>>(pa, pass);
+        TT_LAUNCH_OK("sort_scan_kernel");
+        sort_scatter_kernel<<<grid, kSortThreads, 0, st>>>(ja, pa, pass);
+        TT_LAUNCH_OK("sort_scatter_kernel");
+    }
+    return TT_OK;
+}
+
+int tt_sparse_adagrad(const tt_sparse_job* jobs, int njobs, float lr, float eps, void* ws, size_t ws_bytes, void* stream) {
+    JobArr ja;
+    PlanArr pa;
+    int max_tiles = 0, max_pass = 0;
+    int rc = make_plans(jobs, njobs, ws, ws_bytes, &ja, &pa, &max_tiles, &max_pass, "tt_sparse_adagrad");
+    if (rc) return rc;
+    if (max_tiles == 0) return TT_OK;
+    dim3 grid((unsigned)apply_grid(pa), (unsigned)njobs);
+    sparse_apply_kernel<kModeAdagrad><<<grid, 256, 0, as_stream(stream)>>>(ja, pa, lr, eps, 0.f, 0.f);
+    TT_LAUNCH_OK("sparse_apply_kernel<adagrad>");
+    return TT_OK;
+}
+
+int tt_sparse_adam(const tt_sparse_job* jobs, int njobs, float lr_t, float beta1, float beta2, float eps, void* ws, size_t ws_bytes,
+                   void* stream) {
+    JobArr ja;
+    PlanArr pa;
+    int max_tiles = 0, max_pass = 0;
+    int rc = make_plans(jobs, njobs, ws, ws_bytes, &ja, &pa, &max_tiles, &max_pass, "tt_sparse_adam");
+    if (rc) return rc;
+    for (int j = 0; j < njobs; ++j) TT_REQUIRE(jobs[j].slot1 != nullptr, "tt_sparse_adam: job %d has no second moment", j);
+    cudaStream_t st = as_stream(stream);
+    int64_t max_elems = 0;
+    for (int j = 0; j < njobs; ++j) {
+        int64_t t = (int64_t)jobs[j].rows * jobs[j].e;
+        if (t > max_elems) max_elems = t;
+    }
+    int64_t sg = ceil_div(max_elems, 256 * 4);
+    int64_t cap = (int64_t)sm_count() * 8;
+    if (sg > cap) sg = cap;
+    if (sg < 1) sg = 1;
+    dim3 sweep((unsigned)sg, (unsigned)njobs);
+    adam_sweep_kernel<<<sweep, 256, 0, st>>>(ja, 0, beta1, beta2, lr_t, eps);
+    TT_LAUNCH_OK("adam_sweep_kernel<decay>");
+    if (max_tiles > 0) {
+        dim3 grid((unsigned)apply_grid(pa), (unsigned)njobs);
+        sparse_apply_kernel<kModeAdamMoments><<<grid, 256, 0, st>>>(ja, pa, 0.f, eps, 1.0f - beta1, 1.0f - beta2);
+        TT_LAUNCH_OK("sparse_apply_kernel<adam>");
+    }
+    adam_sweep_kernel<<<sweep, 256, 0, st>>>(ja, 1, beta1, beta2, lr_t, eps);
+    TT_LAUNCH_OK("adam_sweep_kernel<update>");
+    return TT_OK;
+}
+
+}  // extern "C"

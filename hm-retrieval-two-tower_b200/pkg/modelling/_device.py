@@ -1,0 +1,144 @@
+"""
+Host<->device plumbing shared by the pkg.modelling classes: vocabulary lookup (the StringLookup half of
+reference input_layer.py:33-36, done on the host because strings never reach the GPU), staging of a
+batch into device buffers, and a tiny parameter store that keeps all Dense weights of a model in one
+flat buffer (one optimizer launch, one all-reduce).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional, Sequence
+
+import numpy as np
+
+from pkg import _native as N
+
+
+def _as_str(v) -> str:
+    return v.decode() if isinstance(v, (bytes, np.bytes_)) else str(v)
+
+
+class Vocab:
+    """StringLookup(num_oov_indices=1, vocabulary=vocab): OOV -> 0, vocab[i] -> i + 1."""
+
+    def __init__(self, vocab):
+        self.size = len(vocab)
+        self._range = hasattr(vocab, "n") and vocab.__class__.__name__ == "_RangeVocab"
+        self._table: Optional[Dict[str, int]] = None
+        self._vocab = vocab
+
+    @property
+    def rows(self) -> int:
+        return self.size + 1
+
+    def _dict(self) -> Dict[str, int]:
+        if self._table is None:
+            t: Dict[str, int] = {}
+            for i, v in enumerate(self._vocab):
+                t.setdefault(_as_str(v), i + 1)
+            self._table = t
+        return self._table
+
+    def encode(self, values) -> np.ndarray:
+        """Any array of str / bytes / objects -> int32 row ids, shape (n,)."""
+        flat = np.asarray(values).reshape(-1)
+        if self._range:
+            out = np.zeros(flat.shape[0], dtype=np.int32)
+            for n, v in enumerate(flat):
+                s = _as_str(v)
+                if s.isdigit() and str(int(s)) == s and 1 <= int(s) <= self.size:
+                    out[n] = int(s)
+            return out
+        table = self._dict()
+        return np.fromiter((table.get(_as_str(v), 0) for v in flat), dtype=np.int32, count=flat.shape[0])
+
+    def token(self, row: int) -> str:
+        return "[UNK]" if row == 0 else _as_str(self._vocab[row - 1])
+
+
+def is_string_like(a) -> bool:
+    if isinstance(a, np.ndarray):
+        return a.dtype.kind in ("U", "S", "O")
+    if isinstance(a, (list, tuple)):
+        return len(a) > 0 and isinstance(np.asarray(a).reshape(-1)[0], (str, bytes, np.str_, np.bytes_))
+    return False
+
+
+def batch_size_of(x) -> int:
+    shp = getattr(x, "shape", None)
+    if shp is None:
+        return len(x)
+    return int(shp[0]) if len(shp) else 1
+
+
+def stage_ids(value, vocab: Vocab, out):
+    """Fill the int32 device buffer ``out`` (B,) with row ids for one categorical feature.
+    Accepts: strings (host lookup), integer numpy arrays / torch tensors (already row ids)."""
+    torch = N.require_cuda()
+    if isinstance(value, torch.Tensor):
+        out.copy_(value.reshape(-1), non_blocking=True)
+        return
+    if is_string_like(value):
+        ids = vocab.encode(value)
+    else:
+        ids = np.ascontiguousarray(np.asarray(value).reshape(-1), dtype=np.int32)
+    out.copy_(torch.from_numpy(ids), non_blocking=True)
+
+
+def stage_floats(value, out):
+    torch = N.require_cuda()
+    if isinstance(value, torch.Tensor):
+        out.copy_(value.reshape(-1), non_blocking=True)
+        return
+    out.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(value).reshape(-1), dtype=np.float32)), non_blocking=True)
+
+
+class ParamStore:
+    """Flat fp32 buffers for Dense kernels/biases: ``params`` and ``grads`` share one layout."""
+
+    def __init__(self, capacity: int):
+        torch = N.require_cuda()
+        self.capacity = int(max(capacity, 1))
+        self.params = torch.zeros(self.capacity, dtype=torch.float32, device="cuda")
+        self.grads = torch.zeros(self.capacity, dtype=torch.float32, device="cuda")
+        self.used = 0
+
+    def alloc(self, shape: Sequence[int]):
+        n = int(np.prod(shape))
+        start = (self.used + 3) // 4 * 4  # keep every tensor 16-byte aligned
+        if start + n > self.capacity:
+            raise RuntimeError("ParamStore overflow")
+        self.used = start + n
+        return self.params[start:start + n].view(*shape), self.grads[start:start + n].view(*shape)
+
+    @staticmethod
+    def padded(n: int) -> int:
+        return (n + 3) // 4 * 4
+
+
+_SEED = [1234]
+
+
+def set_seed(seed: int) -> None:
+    """Seed for parameter initialisation (the reference relies on TF's global seed)."""
+    _SEED[0] = int(seed)
+
+
+def next_generator():
+    torch = N.require_cuda()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(_SEED[0])
+    _SEED[0] += 1
+    return g
+
+
+def feature_array(entries: Iterable[dict]):
+    """Build a ctypes array of tt_feature from dicts {table, src, rows, e, col} (device pointers)."""
+    entries = list(entries)
+    arr = (N.TTFeature * len(entries))()
+    for i, d in enumerate(entries):
+        arr[i].table = d["table"]
+        arr[i].src = d["src"]
+        arr[i].rows = d["rows"]
+        arr[i].e = d["e"]
+        arr[i].col = d["col"]
+    return arr

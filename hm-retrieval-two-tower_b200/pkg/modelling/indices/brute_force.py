@@ -1,0 +1,123 @@
+"""
+BruteForceIndex: keep (ids, candidate embeddings), answer the top-k ids per query
+(reference pkg/modelling/indices/brute_force.py:7-114).
+
+call = query_model(x) -> scores = q.C^T -> top_k (sorted descending, LOWER index first on ties) -> ids.
+Scoring and selection are one fused CUDA path (tt_index_topk): the (B x N) score matrix is never written
+to HBM.  Indices and scores are bit-identical to the oracle's canonical fp32 evaluation.  The final
+index -> identifier gather stays on the host (identifiers are strings in the reference, :83).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional, Tuple
+
+import numpy as np
+
+from pkg import _native as N
+from pkg.modelling.models.abstract_keras_model import AbstractKerasModel, TensorSpec
+
+
+def _to_device_f32(a):
+    torch = N.require_cuda()
+    if isinstance(a, torch.Tensor):
+        return a.to(device="cuda", dtype=torch.float32)
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).cuda()
+
+
+class BruteForceIndex(AbstractKerasModel):
+    def __init__(self, k: int, query_model, id_candidate_pairs: Iterable, shard: Optional[Tuple[int, int]] = None):
+        """``id_candidate_pairs`` yields (ids (n,), embeddings (n, E)) batches.  ``shard=(rank, world)`` keeps only
+        this rank's contiguous slice of rows (see pkg.modelling.distributed.ShardedBruteForceIndex)."""
+        super().__init__()
+        self.k = int(k)
+        self.query_model = query_model
+        self.impl = N.TT_IMPL_AUTO
+        self._shard = shard
+        self._index(id_candidate_pairs)
+        self._ws = None
+        self._pos_of = None
+        self.initialise_model()
+
+    def _index(self, id_candidate_pairs: Iterable) -> None:
+        torch = N.require_cuda()
+        identifiers, candidates = self.get_id_embeddings_from_dataset(id_candidate_pairs)
+        n_total = candidates.shape[0]
+        self.idx_base = 0
+        if self._shard is not None:
+            rank, world = self._shard
+            per = (n_total + world - 1) // world
+            lo, hi = min(n_total, rank * per), min(n_total, (rank + 1) * per)
+            self.idx_base = lo
+            candidates = candidates[lo:hi]
+        self.n_total = n_total
+        self._identifiers = identifiers                       # all ids (host), position == global row index
+        self._candidates = candidates.contiguous()            # (N_local, E) fp32, non-trainable
+        if self.k > n_total:
+            raise ValueError(f"k={self.k} exceeds the number of candidates ({n_total})")
+
+    @staticmethod
+    def get_id_embeddings_from_dataset(candidates: Iterable):
+        """Concatenate an iterable of (ids, embeddings) -> (ids (N,), embeddings (N, E) on the device)."""
+        torch = N.require_cuda()
+        ids, embs = [], []
+        for identifiers, embeddings in candidates:
+            if isinstance(identifiers, torch.Tensor):
+                identifiers = identifiers.detach().cpu().numpy()
+            ids.append(np.asarray(identifiers).reshape(-1))
+            e = _to_device_f32(embeddings)
+            embs.append(e.reshape(-1, e.shape[-1]))
+        if not embs:
+            raise ValueError("id_candidate_pairs is empty")
+        return np.concatenate(ids, axis=0), torch.cat(embs, dim=0)
+
+    # ---- query paths -----------------------------------------------------------------------------------
+    def _embed_queries(self, queries):
+        torch = N.require_cuda()
+        out = self.query_model(queries)
+        return _to_device_f32(out).contiguous()
+
+    def search(self, query_embeddings, k: Optional[int] = None):
+        """(B, E) device embeddings -> (scores (B,k) fp32, GLOBAL row indices (B,k) int32), both on the device."""
+        torch = N.require_cuda()
+        lib = N.load()
+        k = int(k or self.k)
+        q = query_embeddings
+        nq, e = q.shape
+        n = self._candidates.shape[0]
+        scores = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        idx = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+        if n == 0 or nq == 0:
+            scores.fill_(float("-inf"))
+            idx.fill_(-1)
+            return scores, idx
+        need = int(lib.tt_index_workspace_bytes(nq, n, e, k, self.impl))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+        N.check(lib.tt_index_topk(q.data_ptr(), q.stride(0), self._candidates.data_ptr(), self._candidates.stride(0), nq, n, e, k,
+                                  self.idx_base, scores.data_ptr(), idx.data_ptr(), self._ws.data_ptr(), self._ws.numel(), self.impl,
+                                  N.stream_ptr()), "tt_index_topk")
+        return scores, idx
+
+    def query_indices(self, queries, k: Optional[int] = None):
+        return self.search(self._embed_queries(queries), k)
+
+    def call(self, queries, training: bool = False):
+        """{query feature: (B,1)} -> (B, k) array of candidate identifiers."""
+        _, idx = self.query_indices(queries)
+        return self._identifiers[idx.cpu().numpy()]
+
+    def positions_of(self, ids) -> np.ndarray:
+        """Global row index of each identifier (-1 when absent); used by IndexRecall's device path."""
+        flat = np.asarray(ids).reshape(-1)
+        if self._pos_of is None:
+            self._pos_of = {}
+            for i, v in enumerate(self._identifiers):
+                self._pos_of.setdefault(v.decode() if isinstance(v, bytes) else str(v), i)
+        return np.fromiter((self._pos_of.get(v.decode() if isinstance(v, bytes) else str(v), -1) for v in flat), dtype=np.int32,
+                           count=flat.shape[0])
+
+    def get_input_signature(self) -> Dict[str, TensorSpec]:
+        return self.query_model.get_input_signature()
+
+    def state_arrays(self) -> Dict[str, np.ndarray]:
+        return {"identifiers": np.asarray(self._identifiers).astype(str), "candidates": self._candidates.detach().cpu().numpy()}

@@ -1,0 +1,113 @@
+"""
+InputLayer: embed every string feature and concatenate, numeric features first, each group in schema
+order (reference pkg/modelling/layers/input_layer.py:16-69).
+
+Per string feature the reference builds StringLookup(num_oov_indices=1) -> Embedding(len(vocab)+1, e)
+-> Reshape.  Here the lookup is a host dictionary (strings never reach the GPU; integer inputs are taken
+as row ids directly), the tables live in HBM as (V+1, e) fp32 row-major, and gather + concat is one CUDA
+kernel (tt_gather_concat) -- or is fused into the first Dense layer by Tower (tt_input_dense_fwd).
+As in the reference, the table dict is keyed by feature *name*: two features with the same name share
+the table built last and are both concatenated (input_layer.py:30-43).
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+
+from pkg import _native as N
+from pkg.modelling import _device as D
+from pkg.schema.dtypes import DType
+from pkg.schema.features import Feature
+
+
+class EmbeddingTable:
+    """Embedding(len(vocab)+1, e) with tf-keras' default RandomUniform(-0.05, 0.05) initialiser."""
+
+    def __init__(self, feature: Feature):
+        torch = N.require_cuda()
+        if feature.vocab is None:
+            raise ValueError(f"feature {feature.name} has no vocabulary; build the schema first")
+        if not feature.embedding_size:
+            raise ValueError(f"string feature {feature.name} needs an embedding_size")
+        self.name = feature.name
+        self.vocab = D.Vocab(feature.vocab)
+        self.e = int(feature.embedding_size)
+        self.rows = self.vocab.rows
+        self.weight = torch.empty((self.rows, self.e), dtype=torch.float32, device="cuda")
+        self.weight.uniform_(-0.05, 0.05, generator=D.next_generator())
+
+
+class InputLayer:
+    def __init__(self, features: List[Feature]):
+        self.numerical_features = [f for f in features if f.dtype != DType.string]
+        self.categorical_features = [f for f in features if f.dtype == DType.string]
+        if len(features) > N.TT_MAX_FEATURES:
+            raise ValueError(f"at most {N.TT_MAX_FEATURES} features per tower")
+        self._init_embedding_layers()
+        # column layout of the concatenated output
+        self.blocks = []  # (feature, table or None, first column, width)
+        col = 0
+        for f in self.numerical_features:
+            self.blocks.append((f, None, col, 1))
+            col += 1
+        for f in self.categorical_features:
+            t = self.embedding_layers[f.name]
+            self.blocks.append((f, t, col, t.e))
+            col += t.e
+        self.output_dim = col
+        self.ld = D.ParamStore.padded(col)
+
+    def _init_embedding_layers(self) -> None:
+        self.embedding_layers: Dict[str, EmbeddingTable] = {}
+        for f in self.categorical_features:
+            self.embedding_layers[f.name] = EmbeddingTable(f)
+
+    # ---- staging / descriptors -------------------------------------------------------------------
+    def new_buffers(self, batch: int):
+        """Device buffers for one batch: int32 ids per string feature *occurrence*, fp32 per numeric."""
+        torch = N.require_cuda()
+        bufs = []
+        for f, t, _, _ in self.blocks:
+            dt = torch.float32 if t is None else torch.int32
+            bufs.append(torch.zeros(batch, dtype=dt, device="cuda"))
+        return bufs
+
+    def stage(self, x: Dict[str, object], bufs) -> None:
+        for (f, t, _, _), buf in zip(self.blocks, bufs):
+            if f.name not in x:
+                raise KeyError(f"input is missing feature {f.name!r}")
+            if t is None:
+                D.stage_floats(x[f.name], buf)
+            else:
+                D.stage_ids(x[f.name], t.vocab, buf)
+
+    def descriptors(self, bufs):
+        return D.feature_array(
+            {"table": None if t is None else t.weight.data_ptr(), "src": buf.data_ptr(), "rows": 0 if t is None else t.rows,
+             "e": w, "col": c}
+            for (f, t, c, w), buf in zip(self.blocks, bufs))
+
+    def batch_size(self, x: Dict[str, object]) -> int:
+        return D.batch_size_of(x[self.blocks[0][0].name])
+
+    def call(self, x: Dict[str, object]):
+        """{name: (B,1) strings | row ids | floats} -> (B, D) fp32 device tensor."""
+        torch = N.require_cuda()
+        lib = N.load()
+        batch = self.batch_size(x)
+        bufs = self.new_buffers(batch)
+        self.stage(x, bufs)
+        out = torch.empty((batch, self.ld), dtype=torch.float32, device="cuda")
+        feats = self.descriptors(bufs)
+        N.check(lib.tt_gather_concat(feats, len(self.blocks), batch, self.output_dim, out.data_ptr(), self.ld, N.stream_ptr()),
+                "tt_gather_concat")
+        return out[:, :self.output_dim]
+
+    __call__ = call
+
+    def tables(self) -> Dict[str, EmbeddingTable]:
+        return self.embedding_layers
+
+    def state_arrays(self, prefix: str = "") -> Dict[str, np.ndarray]:
+        return {f"{prefix}embedding/{n}": t.weight.detach().cpu().numpy() for n, t in self.embedding_layers.items()}

@@ -1,0 +1,354 @@
+"""
+TwoTowerModel: two Towers, dot-product logits, in-batch sampled softmax with optional logQ correction
+(reference pkg/modelling/models/two_tower_model.py:13-205).
+
+train_step (reference :94-130) = tape -> logQ -> labels=eye(B) -> CE(from_logits, SUM) -> minimize.
+Here it is a fixed sequence of CUDA launches on pre-allocated buffers (optionally one CUDA graph):
+
+    side stream : radix-sort (id, position) of every embedding feature           tt_sparse_sort
+    main stream : gather + Dense per tower (fp32, + TF32 copy of Q and C)          tt_input_dense_fwd / tt_dense_fwd
+                  ln p(candidate) per column                                       tt_gather_concat on the ln-p row table
+                  S = Q.C^T, Z = S - ln p, LSE, loss   (S never leaves the SM)     tt_inbatch_softmax_fwd
+                  dQ = dZ.C, dC = dZ^T.Q               (S recomputed per tile)     tt_inbatch_softmax_bwd
+                  Dense backward per tower (dW, db, dX)                            tt_dense_bwd
+                  [data parallel: all-reduce dense grads, all-gather (ids, dX)]    torch.distributed / NCCL
+                  Adagrad | Adam on the flat Dense buffer                          tt_dense_adagrad | tt_dense_adam
+                  join side stream; de-duplicated row update of every table        tt_sparse_adagrad | tt_sparse_adam
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from pkg import _native as N
+from pkg.modelling import _device as D
+from pkg.modelling.layers.logq_correction import LogQCorrection
+from pkg.modelling.losses import CategoricalCrossentropy
+from pkg.modelling.models.abstract_keras_model import AbstractKerasModel, TensorSpec
+from pkg.modelling.models.tower import Tower
+from pkg.modelling.optimizer_factory import Adagrad, Adam
+from pkg.schema.features import Feature
+from pkg.schema.schema import Schema
+
+logger = logging.getLogger(__name__)
+
+
+class _StepWorkspace:
+    """Everything one train step of batch size B touches, allocated once."""
+
+    def __init__(self, model: "TwoTowerModel", batch: int):
+        torch = N.require_cuda()
+        lib = N.load()
+        self.batch = batch
+        self.q = model.query_tower.workspace(batch)
+        self.c = model.candidate_tower.workspace(batch)
+        e = model.joint_embedding_size
+        f32 = dict(dtype=torch.float32, device="cuda")
+        self.col_bias = torch.zeros(batch, **f32) if model.logq_correction else None
+        self.col_prob = torch.ones(batch, **f32) if model.logq_correction else None
+        self.lse = torch.zeros(batch, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.dq = torch.zeros((batch, e), **f32)
+        self.dc = torch.zeros((batch, e), **f32)
+        self.sm_ws = torch.empty(int(lib.tt_softmax_workspace_bytes(batch, batch, e)), dtype=torch.uint8, device="cuda")
+        self.bias_feat = None
+        if model.logq_correction:
+            cid_buf = None
+            for (f, t, _, _), buf in zip(model.candidate_tower.input_layer.blocks, self.c.bufs):
+                if f.name == model.candidate_id_col and t is not None:
+                    cid_buf = buf
+            self.cid_buf = cid_buf
+            self.bias_feat = D.feature_array([{"table": model._logq_rows.data_ptr(), "src": cid_buf.data_ptr(),
+                                               "rows": model._logq_rows.shape[0], "e": 1, "col": 0}])
+        self.graph = None
+        self.side = torch.cuda.Stream()
+        self.jobs = None
+        self.sp_ws = None
+        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+
+class TwoTowerModel(AbstractKerasModel):
+    def __init__(self, query_features: List[Feature], candidate_features: List[Feature], candidate_id_col: str,
+                 joint_embedding_size: int, query_tower_units: Optional[List[int]] = None,
+                 candidate_tower_units: Optional[List[int]] = None, candidate_prob_lookup: Optional[Dict[str, float]] = None):
+        super().__init__()
+        self.query_features = query_features
+        self.candidate_features = candidate_features
+        if candidate_id_col not in [f.name for f in candidate_features]:
+            raise ValueError(f"candidate_id_col {candidate_id_col} not a candidate feature")
+        self.candidate_id_col = candidate_id_col
+        self.joint_embedding_size = int(joint_embedding_size)
+        torch = N.require_cuda()
+
+        def dense_count(feats, units):
+            dim = 0
+            last_e = {}
+            for f in feats:
+                if f.embedding_size and f.dtype.value == "string":
+                    last_e[f.name] = int(f.embedding_size)
+            for f in feats:
+                dim += last_e[f.name] if f.dtype.value == "string" else 1
+            return Tower.dense_param_count(dim, Tower.layer_sizes(units, joint_embedding_size))
+
+        self._store = D.ParamStore(dense_count(query_features, query_tower_units) +
+                                   dense_count(candidate_features, candidate_tower_units))
+        self.query_tower = Tower(query_features, joint_embedding_size, query_tower_units, _store=self._store)
+        self.candidate_tower = Tower(candidate_features, joint_embedding_size, candidate_tower_units, _store=self._store)
+        if candidate_prob_lookup:
+            self.logq_correction = LogQCorrection(candidate_prob_lookup)
+            table = self.candidate_tower.input_layer.embedding_layers[candidate_id_col]
+            rows_p = self.logq_correction.row_log_probabilities(table.vocab)  # probabilities per row
+            self._logq_rows = torch.log(torch.from_numpy(rows_p).cuda())     # fp32 ln, as logq_correction.py:69
+        else:
+            self.logq_correction = None
+            self._logq_rows = None
+        self.optimizer = None
+        self.loss_fn = None
+        self.impl = N.TT_IMPL_AUTO           # contraction implementation for the B x B softmax
+        self.use_cuda_graph = os.environ.get("TT_CUDA_GRAPH", "0") == "1"
+        self.dist = None                     # set by pkg.modelling.distributed.DataParallel
+        self._steps: Dict[int, _StepWorkspace] = {}
+        self._opt_state = None
+        self._loss_sum = 0.0
+        self._loss_count = 0
+        self.initialise_model()
+
+    # ---- inference-style call ------------------------------------------------------------------------
+    def call(self, x, training: bool = True):
+        """(B x B) score of query i with candidate j -- materialised, for API parity (reference :65-92).
+        No logQ correction here; train_step applies it (fused) exactly as the reference does."""
+        torch = N.require_cuda()
+        lib = N.load()
+        qf = {f.name: x[f.name] for f in self.query_features}
+        cf = {f.name: x[f.name] for f in self.candidate_features}
+        q = self.query_tower(qf)
+        c = self.candidate_tower(cf)
+        e = self.joint_embedding_size
+        out = torch.empty((q.shape[0], c.shape[0]), dtype=torch.float32, device="cuda")
+        N.check(lib.tt_logits(q.data_ptr(), e, c.data_ptr(), e, None, q.shape[0], c.shape[0], e, out.data_ptr(), c.shape[0],
+                              N.TT_IMPL_SIMT, N.stream_ptr()), "tt_logits")
+        return out
+
+    # ---- training ----------------------------------------------------------------------------------
+    def compile(self, loss=None, optimizer=None, **_ignored) -> None:
+        if loss is not None:
+            if not isinstance(loss, CategoricalCrossentropy):
+                raise NotImplementedError("loss must be pkg.modelling.losses.CategoricalCrossentropy(from_logits=True, reduction=SUM)")
+            loss.validate()
+        if optimizer is None or not isinstance(optimizer, (Adagrad, Adam)):
+            raise ValueError("optimizer must come from OptimizerFactory.get_optimizer ('adagrad' or 'adam')")
+        self.loss_fn = loss
+        self.optimizer = optimizer
+        self._build_optimizer_state()
+
+    def _tables(self):
+        out = []
+        for tower in (self.query_tower, self.candidate_tower):
+            for name, t in tower.input_layer.embedding_layers.items():
+                out.append((tower, name, t))
+        return out
+
+    def _build_optimizer_state(self) -> None:
+        torch = N.require_cuda()
+        opt = self.optimizer
+        init = opt.slot_init()
+        self._opt_state = {
+            "dense": [torch.full_like(self._store.params, v) for v in init],
+            "tables": {id(t): [torch.full_like(t.weight, v) for v in init] for _, _, t in self._tables()},
+        }
+
+    def _step_ws(self, batch: int) -> _StepWorkspace:
+        sw = self._steps.get(batch)
+        if sw is None:
+            if len(self._steps) >= 4:
+                self._steps.pop(next(iter(self._steps)))
+            sw = self._steps[batch] = _StepWorkspace(self, batch)
+            self._build_jobs(sw)
+        return sw
+
+    def _build_jobs(self, sw: _StepWorkspace) -> None:
+        """Sparse-optimizer job list: one job per embedding table, one source per feature using it
+        (or, data-parallel, per all-gathered block)."""
+        torch = N.require_cuda()
+        lib = N.load()
+        srcs = []
+        for tower, tws in ((self.query_tower, sw.q), (self.candidate_tower, sw.c)):
+            for name, (table, lst) in tower.sparse_sources(tws).items():
+                srcs.append((table, lst))
+        if self.dist is not None:
+            srcs = self.dist.wrap_sparse_sources(self, sw, srcs)
+        if len(srcs) > N.TT_MAX_JOBS:
+            raise ValueError(f"at most {N.TT_MAX_JOBS} embedding tables per model")
+        jobs = (N.TTSparseJob * len(srcs))()
+        max_n = 0
+        for j, (table, lst) in enumerate(srcs):
+            if len(lst) > N.TT_MAX_SRC:
+                raise ValueError(f"table {table.name}: more than {N.TT_MAX_SRC} features share it")
+            slots = self._opt_state["tables"][id(table)]
+            jobs[j].table = table.weight.data_ptr()
+            jobs[j].slot0 = slots[0].data_ptr()
+            jobs[j].slot1 = slots[1].data_ptr() if len(slots) > 1 else None
+            jobs[j].rows, jobs[j].e, jobs[j].nsrc = table.rows, table.e, len(lst)
+            n_per = lst[0][0].numel()
+            jobs[j].n_per_src = n_per
+            for s, (ids, gptr, gld) in enumerate(lst):
+                jobs[j].ids[s] = ids.data_ptr()
+                jobs[j].grad[s] = gptr
+                jobs[j].grad_ld[s] = gld
+            max_n = max(max_n, n_per * len(lst))
+        sw.jobs, sw.njobs = jobs, len(srcs)
+        sw.sp_ws = torch.empty(int(lib.tt_sparse_workspace_bytes(len(srcs), max_n)), dtype=torch.uint8, device="cuda")
+
+    def _stage(self, sw: _StepWorkspace, data) -> None:
+        qf = {f.name: data[f.name] for f in self.query_features}
+        cf = {f.name: data[f.name] for f in self.candidate_features}
+        self.query_tower.input_layer.stage(qf, sw.q.bufs)
+        self.candidate_tower.input_layer.stage(cf, sw.c.bufs)
+        if self.logq_correction is not None and D.is_string_like(data[self.candidate_id_col]):
+            # exact reference semantics for string ids: probability looked up by the STRING (an id outside
+            # the vocabulary may still have a sampling probability); ln taken on the device below
+            torch = N.require_cuda()
+            p = self.logq_correction.probabilities(data[self.candidate_id_col])
+            sw.col_prob.copy_(torch.from_numpy(p), non_blocking=True)
+            sw.bias_from_strings = True
+        else:
+            sw.bias_from_strings = False
+
+    def _launch_step(self, sw: _StepWorkspace) -> None:
+        torch = N.require_cuda()
+        lib = N.load()
+        opt = self.optimizer
+        b, e = sw.batch, self.joint_embedding_size
+        main = torch.cuda.current_stream()
+        # fork: the id sort depends on the inputs only
+        sw.side.wait_stream(main)
+        with torch.cuda.stream(sw.side):
+            if self.dist is not None:
+                self.dist.gather_ids(self, sw)
+            N.check(lib.tt_sparse_sort(sw.jobs, sw.njobs, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), N.stream_ptr()), "tt_sparse_sort")
+        st = N.stream_ptr()
+        q, q32 = self.query_tower.forward_ws(sw.q)
+        c, c32 = self.candidate_tower.forward_ws(sw.c)
+        bias = None
+        if self.logq_correction is not None:
+            if sw.bias_from_strings:
+                N.check(lib.tt_log_f32(sw.col_prob.data_ptr(), sw.col_bias.data_ptr(), b, st), "tt_log_f32")
+            else:
+                N.check(lib.tt_gather_concat(sw.bias_feat, 1, b, 1, sw.col_bias.data_ptr(), 1, st), "tt_gather_concat(logq)")
+            bias = sw.col_bias.data_ptr()
+        use_tc = self.impl != N.TT_IMPL_SIMT and self._tc_ok()
+        qa, ca = (q32, c32) if use_tc else (q, c)
+        impl = N.TT_IMPL_TC if use_tc else N.TT_IMPL_SIMT
+        N.check(lib.tt_inbatch_softmax_fwd(qa.data_ptr(), e, ca.data_ptr(), e, bias, b, b, e, 0, sw.lse.data_ptr(),
+                                           sw.loss.data_ptr(), sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st), "tt_inbatch_softmax_fwd")
+        N.check(lib.tt_inbatch_softmax_bwd(qa.data_ptr(), e, ca.data_ptr(), e, bias, sw.lse.data_ptr(), b, b, e, 0,
+                                           sw.dq.data_ptr(), e, sw.dc.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st),
+                "tt_inbatch_softmax_bwd")
+        self.query_tower.backward_ws(sw.q, sw.dq)
+        self.candidate_tower.backward_ws(sw.c, sw.dc)
+        if self.dist is not None:
+            self.dist.reduce_dense_and_gather_rows(self, sw)
+        n_dense = self._store.used
+        if n_dense:
+            ds = self._opt_state["dense"]
+            if isinstance(opt, Adagrad):
+                N.check(lib.tt_dense_adagrad(self._store.params.data_ptr(), ds[0].data_ptr(), self._store.grads.data_ptr(), n_dense,
+                                             opt.learning_rate, opt.epsilon, st), "tt_dense_adagrad")
+            else:
+                N.check(lib.tt_dense_adam(self._store.params.data_ptr(), ds[0].data_ptr(), ds[1].data_ptr(),
+                                          self._store.grads.data_ptr(), n_dense, sw.lr_t, opt.beta_1, opt.beta_2, opt.epsilon, st),
+                        "tt_dense_adam")
+        main.wait_stream(sw.side)  # join
+        if isinstance(opt, Adagrad):
+            N.check(lib.tt_sparse_adagrad(sw.jobs, sw.njobs, opt.learning_rate, opt.epsilon, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), st),
+                    "tt_sparse_adagrad")
+        else:
+            N.check(lib.tt_sparse_adam(sw.jobs, sw.njobs, sw.lr_t, opt.beta_1, opt.beta_2, opt.epsilon, sw.sp_ws.data_ptr(),
+                                       sw.sp_ws.numel(), st), "tt_sparse_adam")
+
+    def _tc_ok(self) -> bool:
+        return bool(N.load().tt_device_supports_tc()) and self.joint_embedding_size in (32, 64, 128)
+
+    def train_step(self, data) -> Dict[str, object]:
+        """One optimisation step on a batch {feature name: (B,1) column}.  Returns {"loss": 0-d device
+        tensor holding this batch's SUM loss} (``float()`` it to synchronise)."""
+        if self.optimizer is None:
+            raise RuntimeError("call compile(loss=..., optimizer=...) before training")
+        torch = N.require_cuda()
+        batch = D.batch_size_of(data[self.candidate_id_col])
+        sw = self._step_ws(batch)
+        self._stage(sw, data)
+        self.optimizer.iterations += 1
+        graph_ok = self.use_cuda_graph and not isinstance(self.optimizer, Adam) and not sw.bias_from_strings and self.dist is None
+        if isinstance(self.optimizer, Adam):
+            sw.lr_t = self.optimizer.lr_t(self.optimizer.iterations)
+        if graph_ok:
+            if sw.graph is None:
+                self._launch_step(sw)  # eager warm-up (sets kernel attributes), also a real step
+                torch.cuda.current_stream().synchronize()
+                sw.graph = "pending"
+            elif sw.graph == "pending":
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_step(sw)
+                sw.graph = g
+                g.replay()
+            else:
+                sw.graph.replay()
+        else:
+            self._launch_step(sw)
+        return {"loss": sw.loss[0]}
+
+    def fit(self, ds, epochs: int = 1, callbacks=None, verbose: int = 1):
+        """Minimal Keras-like loop: ``ds`` is any iterable of batches (re-iterable for epochs > 1)."""
+        history = {"loss": []}
+        for epoch in range(epochs):
+            total, steps, last = None, 0, None
+            for batch in ds:
+                last = self.train_step(batch)["loss"]
+                total = last.clone() if total is None else total + last
+                steps += 1
+            mean = float(total) / steps if steps else float("nan")
+            history["loss"].append(mean)
+            if verbose:
+                logger.info(f"epoch {epoch + 1}/{epochs}: {steps} steps, mean batch-sum loss {mean:.6f}")
+            for cb in callbacks or []:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, {"loss": mean})
+        return history
+
+    # ---- factory / signature / save ------------------------------------------------------------------
+    @classmethod
+    def create_from_schema(cls, schema: Schema, candidate_id_col: str) -> "TwoTowerModel":
+        return TwoTowerModel(
+            query_features=schema.query_features,
+            candidate_features=schema.candidate_features,
+            candidate_id_col=candidate_id_col,
+            joint_embedding_size=schema.model_config.joint_embedding_size,
+            query_tower_units=schema.model_config.query_tower_units,
+            candidate_tower_units=schema.model_config.candidate_tower_units,
+            candidate_prob_lookup=schema.training_config.candidate_prob_lookup,
+        )
+
+    def get_input_signature(self) -> Dict[str, TensorSpec]:
+        return {f.name: TensorSpec((None, 1), f.dtype, f.name) for f in self.candidate_features + self.query_features}
+
+    def state_arrays(self) -> Dict[str, np.ndarray]:
+        arrs = self.query_tower.state_arrays("query_tower/")
+        arrs.update(self.candidate_tower.state_arrays("candidate_tower/"))
+        return arrs
+
+    def save(self, model_path: str) -> None:
+        """two_tower/, query_tower/, candidate_tower/ next to ``model_path`` (reference :176-205), each holding
+        variables.npz instead of a SavedModel."""
+        base = os.path.dirname(model_path)
+        os.makedirs(base or ".", exist_ok=True)
+        for sub, arrs in (("two_tower", self.state_arrays()), ("query_tower", self.query_tower.state_arrays()),
+                          ("candidate_tower", self.candidate_tower.state_arrays())):
+            path = os.path.join(base, sub)
+            logging.info(f"Saving {sub} at path: {path}")
+            os.makedirs(path, exist_ok=True)
+            np.savez(os.path.join(path, "variables.npz"), **arrs)

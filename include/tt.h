@@ -1,0 +1,173 @@
+/*
+ * tt.h -- C ABI of libtt.so: the B200 (sm_100a) implementation of the two-tower hot path.
+ *
+ * The reference (SelvinSelbaraju/hm-retrieval-two-tower) has no FFI / operator layer of its own: its
+ * hot path is ~15 TensorFlow op call sites inside pkg/modelling.  Each entry
+ * point below replaces one group of those call sites; the reference file:line it stands in for is
+ * given per function.  The Python classes in hm-retrieval-two-tower_b200/pkg/modelling bind these
+ * with ctypes (INTEGRATION.md shows the binding a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; tt_last_error() gives a thread-local message;
+ *   - all tensor arguments are BORROWED raw device pointers (caller-owned; never freed or retained);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation,
+ *     no cudaMalloc in any call; scratch comes from the caller via *_workspace_bytes();
+ *   - matrices are row-major fp32 with an explicit leading dimension in ELEMENTS;
+ *   - row ids are int32 with 0 = OOV (StringLookup(num_oov_indices=1), input_layer.py:33-36);
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU the calls fail with TT_ERR_CUDA.
+ */
+#ifndef TT_H_
+#define TT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_OK 0
+#define TT_ERR_ARG (-1)
+#define TT_ERR_CUDA (-2)
+#define TT_ERR_WORKSPACE (-3)
+#define TT_ERR_UNSUPPORTED (-4)
+
+#define TT_MAX_FEATURES 16   /* features per tower */
+#define TT_MAX_SRC 4         /* gradient sources that may share one table (same-named features) */
+#define TT_MAX_JOBS 32       /* tables updated by one sparse-optimizer call */
+#define TT_MAX_KS 8
+
+/* which implementation of a contraction to run */
+#define TT_IMPL_AUTO 0
+#define TT_IMPL_SIMT 1   /* exact fp32 FMA on CUDA cores, canonical k-ascending order */
+#define TT_IMPL_TC 2     /* tcgen05 tensor cores (TF32 operands, fp32 accumulate in TMEM), TMA-fed */
+
+int tt_version(void);
+const char* tt_last_error(void);
+/* 1 when the current device is compute capability 10.x and the tcgen05 kernels can launch. */
+int tt_device_supports_tc(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * InputLayer (pkg/modelling/layers/input_layer.py:45-69): one column block per feature.
+ * Numeric feature: table == NULL, src = float[B], e = 1.  Categorical: src = int32 ids[B].
+ * Ids outside [0, rows) are treated as OOV (row 0).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tt_feature {
+    const float* table; /* (rows, e) row-major fp32, or NULL for a numeric feature */
+    const void* src;    /* int32 ids[B] (categorical) or float[B] (numeric) */
+    int32_t rows;
+    int32_t e;
+    int32_t col;        /* first output column of this block */
+    int32_t _pad;
+} tt_feature;
+
+/* X[b, col_f : col_f+e_f] = table_f[ids_f[b]]  (or the numeric value); columns [D, ldx) are zeroed.
+ * Replaces LookupTableFind->ResourceGather->Reshape->ConcatV2 (input_layer.py:37-41,61-68). */
+int tt_gather_concat(const tt_feature* feats, int nfeat, int B, int D, float* X, int ldx, void* stream);
+
+/* Y = relu?(X.W + b).  X (B,K) ld ldx; W (K,N) row-major (Keras kernel layout); b (N) or NULL.
+ * Optional Y_tf32: a copy of Y rounded to TF32 (round-to-nearest) for the tensor-core logits kernels.
+ * Replaces MatMul+BiasAdd+Relu of tf.keras.layers.Dense (tower.py:41-49,72-75).  Canonical
+ * k-ascending fmaf accumulation (bit-exact against oracle/tt_oracle.c:tto_dense_fmaf). */
+int tt_dense_fwd(const float* X, int ldx, const float* W, const float* b, float* Y, int ldy, float* Y_tf32,
+                 int B, int K, int N, int relu, void* stream);
+
+/* Fused InputLayer + first Dense: gathers the A operand straight from the embedding tables.
+ * If X_out != NULL the concatenated input is also written (needed by tt_dense_bwd for dW). */
+int tt_input_dense_fwd(const tt_feature* feats, int nfeat, int D, const float* W, const float* b, float* X_out,
+                       int ldx, float* Y, int ldy, float* Y_tf32, int B, int N, int relu, void* stream);
+
+/* Backward of Y = relu(X.W + b) given dY (autodiff of tower.py:72-75):
+ *   dpre = dY * (Y > 0);  dW = X^T.dpre;  db = sum_b dpre;  dX = dpre.W^T (skipped when dX == NULL).
+ * dW/db are reduced over the batch in a fixed chunk order (deterministic).  */
+size_t tt_dense_bwd_workspace_bytes(int B, int K, int N);
+int tt_dense_bwd(const float* X, int ldx, const float* W, const float* Y, int ldy, const float* dY, int lddy,
+                 float* dX, int lddx, float* dW, float* db, int B, int K, int N, int relu, void* ws,
+                 size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * In-batch sampled softmax (two_tower_model.py:90-92,110-124; logq_correction.py:66-71;
+ * runner.py:78-83):   S = Q.C^T ; Z = S - col_bias[None,:] ; labels = eye (row i <-> column
+ * i + diag_offset) ; loss = sum_i (logsumexp_j Z_ij - Z_i,i+off) ; dZ = softmax_row(Z) - eye.
+ * Q (Bq,E), C (Bc,E); col_bias = ln p(candidate j) (NULL = no logQ correction).  S is never
+ * written to HBM.  Bc != Bq with diag_offset serves all-gathered negatives.
+ * ---------------------------------------------------------------------------------------------- */
+size_t tt_softmax_workspace_bytes(int Bq, int Bc, int E);
+int tt_inbatch_softmax_fwd(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, int Bq, int Bc,
+                           int E, int diag_offset, float* lse, float* loss, void* ws, size_t ws_bytes, int impl,
+                           void* stream);
+/* dQ = dZ.C (Bq,E);  dC = dZ^T.Q (Bc,E).  Recomputes S tile by tile from Q, C and lse. */
+int tt_inbatch_softmax_bwd(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, const float* lse,
+                           int Bq, int Bc, int E, int diag_offset, float* dQ, int lddq, float* dC, int lddc,
+                           void* ws, size_t ws_bytes, int impl, void* stream);
+/* Materialised Z (Bq,Bc) for TwoTowerModel.call / LogQCorrection parity tests only. */
+int tt_logits(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, int Bq, int Bc, int E,
+              float* Z, int ldz, int impl, void* stream);
+/* Z = logits - col_bias[None,:]   (LogQCorrection.__call__ on a materialised matrix). */
+int tt_logq_apply(const float* logits, int ldl, const float* col_bias, int Bq, int Bc, float* Z, int ldz, void* stream);
+/* out[i] = ln(p[i])  (fp32 log, logq_correction.py:69). */
+int tt_log_f32(const float* p, float* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizers (optimizer_factory.py:15-18 -> tf-keras 2.16 legacy Adagrad / Adam).
+ * Sparse path: duplicate ids are summed FIRST (OptimizerV2._deduplicate_indexed_slices), in
+ * ascending position order (deterministic, no floating-point atomics), then the update touches
+ * each unique row once.
+ * ---------------------------------------------------------------------------------------------- */
+int tt_dense_adagrad(float* w, float* acc, const float* g, int64_t n, float lr, float eps, void* stream);
+int tt_dense_adam(float* w, float* m, float* v, const float* g, int64_t n, float lr_t, float beta1, float beta2,
+                  float eps, void* stream);
+int tt_fill_f32(float* p, float value, int64_t n, void* stream);
+
+typedef struct tt_sparse_job {
+    float* table;  /* (rows, e) */
+    float* slot0;  /* Adagrad accumulator, or Adam m */
+    float* slot1;  /* Adam v (unused for Adagrad) */
+    int32_t rows;
+    int32_t e;
+    int32_t nsrc;  /* number of (ids, grad) sources feeding this table */
+    int32_t n_per_src; /* rows per source (the batch size) */
+    const int32_t* ids[TT_MAX_SRC];
+    const float* grad[TT_MAX_SRC]; /* first column of this feature's slice of dX */
+    int32_t grad_ld[TT_MAX_SRC];
+} tt_sparse_job;
+
+size_t tt_sparse_workspace_bytes(int njobs, int max_n);
+/* Stable LSD radix sort of (id, position) for every job; depends on ids only, so it can run on a
+ * side stream concurrently with forward/backward. */
+int tt_sparse_sort(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, void* stream);
+int tt_sparse_adagrad(const tt_sparse_job* jobs, int njobs, float lr, float eps, void* ws, size_t ws_bytes,
+                      void* stream);
+/* Non-lazy legacy Adam: whole-table decay + update every step. `touched` is a
+ * per-job bitmap workspace inside ws. */
+int tt_sparse_adam(const tt_sparse_job* jobs, int njobs, float lr_t, float beta1, float beta2, float eps, void* ws,
+                   size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Brute-force index (pkg/modelling/indices/brute_force.py:75-83): scores = Q.corpus^T, top_k
+ * sorted descending with the LOWER index first on equal scores, int32 indices (+ idx_base for a
+ * row-sharded corpus).  The (nq, n) score matrix never reaches HBM.
+ * Scores returned are the canonical fp32 values (k-ascending fmaf), bit-exact against the oracle.
+ * ---------------------------------------------------------------------------------------------- */
+size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl);
+int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, int nq, int64_t n, int E, int K,
+                  int64_t idx_base, float* out_scores, int32_t* out_idx, void* ws, size_t ws_bytes, int impl,
+                  void* stream);
+/* max_j ||corpus_j||_2 (used by the tensor-core filter's error bound); result is one float. */
+int tt_corpus_max_norm(const float* corpus, int ldc, int64_t n, int E, float* out, void* stream);
+/* Round-to-nearest TF32 copy of a matrix (operand preparation for TT_IMPL_TC). */
+int tt_round_tf32(const float* src, int lds, float* dst, int ldd, int64_t rows, int cols, void* stream);
+
+/* K-way merge of per-shard results laid out (G, nq, K) by (score desc, idx asc) -> (nq, K). */
+int tt_topk_merge(const float* scores, const int32_t* idx, int G, int nq, int K, float* out_scores,
+                  int32_t* out_idx, void* stream);
+
+/* hits[t] += sum_{b, j < ks[t]} [true_idx[b] == cand[b, j]]   (index_recall.py:54-58; int32 exact).
+ * cand is (nq, k_stride) int32; hits is int32[nk] on the device and is accumulated into. */
+int tt_recall_hits(const int32_t* cand, int k_stride, const int32_t* true_idx, int nq, const int32_t* ks, int nk,
+                   int32_t* hits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_H_ */
