@@ -1,0 +1,452 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the two-tower hot path (BASELINE.json: "train examples/s; index
+queries/s (top-100, 105k items) at 1/2/4/8 B200").
+
+    python bench.py --gpus 1 --steps K --warmup W                       (ours)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                                (CPU arm: the oracle port on host cores)
+
+Workload (configs[1], "c2"): H&M-shaped synthetic data -- 1 371 980 customers, 105 542 articles (Zipf), side
+features age (f32), product_type (131 -> e16), colour (50 -> e8); id embeddings and joint dim 64, no hidden
+layers, logQ-corrected in-batch softmax, Adagrad lr 0.05, batch 8192 per GPU (weak scaling).
+One "step" = one TwoTowerModel.train_step on one batch.  `value` = examples/s with the batch ids already
+resident in HBM; `e2e` = the same through the public API from pinned host buffers, loss read back each step.
+The index half of the metric is reported in the same JSON line under "index".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "hm-retrieval-two-tower_b200")
+for _p in (ROOT, PKG_DIR):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+V_CUSTOMERS, V_ARTICLES, V_PTYPE, V_COLOUR = 1_371_980, 105_542, 131, 50
+E_ID, E_PTYPE, E_COLOUR, JOINT = 64, 16, 8, 64
+INDEX_K, INDEX_BQ = 100, 2048
+METRIC = "train examples/s; index queries/s (top-100, 105k items) at 1/2/4/8 B200"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops_burst": p["bf16_tflops"], "tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic data (seeded; pre-encoded row ids, 0 = OOV)
+# ---------------------------------------------------------------------------------------------------
+def zipf_articles(rng, n):
+    # Zipf(s ~ 1.0) over {1..V_ARTICLES} by inverse-CDF on the harmonic weights
+    w = 1.0 / np.arange(1, V_ARTICLES + 1, dtype=np.float64)
+    cdf = np.cumsum(w / w.sum())
+    return (np.searchsorted(cdf, rng.random(n), side="left") + 1).clip(1, V_ARTICLES).astype(np.int32)
+
+
+def article_probs():
+    w = 1.0 / np.arange(1, V_ARTICLES + 1, dtype=np.float64)
+    return (w / w.sum()).astype(np.float32)
+
+
+def make_batch(rng, b):
+    art = zipf_articles(rng, b)
+    return {
+        "age": (np.clip(rng.normal(36, 14, size=b), 16, 99) / 100.0).astype(np.float32).reshape(b, 1),
+        "customer_id": rng.integers(1, V_CUSTOMERS + 1, size=(b, 1)).astype(np.int32),
+        "article_id": art.reshape(b, 1),
+        "product_type_name": (art % V_PTYPE + 1).astype(np.int32).reshape(b, 1),   # functionally dependent on the article
+        "colour_group_name": (art % V_COLOUR + 1).astype(np.int32).reshape(b, 1),
+    }
+
+
+BYTES_PER_EXAMPLE_H2D = 4 * 5
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port with all host threads
+# ---------------------------------------------------------------------------------------------------
+def build_cpu_model(seed=0):
+    import torch
+    from oracle.torch_cpu_port import CpuTwoTower
+
+    logp = torch.zeros(V_ARTICLES + 1)
+    logp[1:] = torch.from_numpy(np.log(article_probs()))
+    return CpuTwoTower(q_cat=[(V_CUSTOMERS + 1, E_ID)], q_num=1,
+                       c_cat=[(V_ARTICLES + 1, E_ID), (V_PTYPE + 1, E_PTYPE), (V_COLOUR + 1, E_COLOUR)], c_num=0, joint=JOINT,
+                       log_p_rows=logp, lr=0.05, seed=seed)
+
+
+def cpu_train_rate(batch, warmup, steps, seed=1):
+    """examples/s of the torch-CPU port on `steps` batches of the same workload."""
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = build_cpu_model()
+    rng = np.random.default_rng(seed)
+    batches = []
+    for _ in range(4):
+        b = make_batch(rng, batch)
+        batches.append(([torch.from_numpy(b["customer_id"].reshape(-1).astype(np.int64))], [torch.from_numpy(b["age"].reshape(-1))],
+                        [torch.from_numpy(b[k].reshape(-1).astype(np.int64)) for k in ("article_id", "product_type_name", "colour_group_name")], []))
+    it = [0]
+
+    def step():
+        q_ids, q_nums, c_ids, c_nums = batches[it[0] % len(batches)]
+        it[0] += 1
+        model.train_step(q_ids, q_nums, c_ids, c_nums)
+
+    from oracle.torch_cpu_port import time_fn
+
+    sec = time_fn(step, warmup, steps)
+    return batch / sec, sec, cores
+
+
+def cpu_index_rate(bq, warmup, steps, seed=2):
+    import torch
+    from oracle.torch_cpu_port import cpu_index_topk, time_fn
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(seed)
+    corpus = torch.from_numpy((np.abs(rng.standard_normal((V_ARTICLES, JOINT))) * 0.1).astype(np.float32))
+    q = torch.from_numpy(np.maximum(rng.standard_normal((bq, JOINT)) * 0.3, 0).astype(np.float32))
+    sec = time_fn(lambda: cpu_index_topk(q, corpus, INDEX_K), warmup, steps)
+    return bq / sec, sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    rate, sec, cores = cpu_train_rate(args.batch, warmup, steps)
+    irate, isec, _ = cpu_index_rate(INDEX_BQ, 1, 3)
+    sample = f"{steps} train steps of batch {args.batch} (same synthetic workload), torch-CPU port, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "examples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c2: H&M-shaped two-tower dim 64 + side features, batch %d, logQ in-batch softmax, Adagrad" % args.batch,
+                   "note": "reference TF is not installable here; this is the oracle restatement run with torch-CPU ops"},
+        "cpu_baseline": {"value": rate, "unit": "examples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "index": {"value": irate, "unit": "queries/s", "ms_per_batch": isec * 1e3,
+                  "config": f"N={V_ARTICLES}, E={JOINT}, K={INDEX_K}, Bq={INDEX_BQ}, torch-CPU matmul+topk, {cores} threads"},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def build_gpu_model():
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+    from pkg.schema import dtypes as tt
+    from pkg.schema.features import Feature, FeatureFamily
+
+    set_seed(1234)
+    qf = [Feature("age", tt.float32, FeatureFamily.QUERY), Feature("customer_id", tt.string, FeatureFamily.QUERY, embedding_size=E_ID)]
+    cf = [Feature("article_id", tt.string, FeatureFamily.CANDIDATE, embedding_size=E_ID),
+          Feature("product_type_name", tt.string, FeatureFamily.CANDIDATE, embedding_size=E_PTYPE),
+          Feature("colour_group_name", tt.string, FeatureFamily.CANDIDATE, embedding_size=E_COLOUR)]
+    qf[1].set_vocab_size(V_CUSTOMERS); cf[0].set_vocab_size(V_ARTICLES); cf[1].set_vocab_size(V_PTYPE); cf[2].set_vocab_size(V_COLOUR)
+    probs = article_probs()
+    lookup = {str(i + 1): float(p) for i, p in enumerate(probs)}
+    model = TwoTowerModel(qf, cf, "article_id", JOINT, candidate_prob_lookup=lookup)
+    model.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))
+    return model
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from pkg import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = N.load()
+    pk = peaks()
+    B, K, W = args.batch, max(args.steps, 1), max(args.warmup, 3)
+    model = build_gpu_model()
+    if args.simt:
+        model.impl = N.TT_IMPL_SIMT
+    if world > 1:
+        from pkg.modelling.distributed import DataParallel
+
+        DataParallel(model)
+    model.use_cuda_graph = (not args.no_graph) and world == 1
+    rng = np.random.default_rng(1000 + rank)
+    pool = 8
+    host_batches = [make_batch(rng, B) for _ in range(pool)]
+    dev_batches = [{k: torch.from_numpy(v).cuda() for k, v in hb.items()} for hb in host_batches]
+    pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in hb.items()} for hb in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # launches per step (eager, before any graph capture decision matters)
+    c0 = lib.tt_launch_count()
+    model.train_step(dev_batches[0])
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.tt_launch_count() - c0)
+
+    for i in range(W):
+        model.train_step(dev_batches[i % pool])
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record()
+        for i in range(K):
+            model.train_step(dev_batches[i % pool])
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    ms_per_step = ms / K
+    value = world * B / (ms_per_step * 1e-3)
+    clocks = clk.summary()
+
+    # end-to-end through the public API: pinned host ids -> H2D -> step -> loss D2H, every step
+    for i in range(3):
+        float(model.train_step(pinned[i % pool])["loss"])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        loss = float(model.train_step(pinned[i % pool])["loss"])
+    barrier()
+    e2e_sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_sec], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t)
+    e2e = world * B * K / e2e_sec
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if model._tc_ok() and model.impl != N.TT_IMPL_SIMT else "f32",
+        "data": "synthetic",
+        "config": {"workload": "c2: H&M-shaped two-tower (1.37M customers, 105k articles), id emb + joint dim 64, side features age/product_type/colour, "
+                               f"batch {B}/GPU, logQ in-batch softmax, Adagrad lr 0.05",
+                   "parallelism": f"dp{world}" if world > 1 else "single", "cuda_graph": bool(model.use_cuda_graph),
+                   "l2": "inputs larger than L2: tables + Adagrad accumulators 0.76 GB, random rows each step; no explicit flush",
+                   "last_loss": loss},
+        "e2e": {"value": e2e, "unit": "examples/s", "h2d_bytes_per_step": B * BYTES_PER_EXAMPLE_H2D, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches_per_step * K, "clocks": clocks,
+    }
+
+    if rank == 0:
+        line["roofline"] = softmax_roofline(model, B, pk, lib)
+    if world == 1:
+        line["index"] = index_bench(model, pk, lib, K)
+        if not args.no_cpu:
+            rate, sec, cores = cpu_train_rate(B, 2, args.cpu_steps)
+            line["cpu_baseline"] = {"value": rate, "unit": "examples/s", "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_steps} train steps of batch {B} of the same workload (torch-CPU oracle port, {cores} threads, {sec * 1e3:.1f} ms/step)"}
+            irate, isec, _ = cpu_index_rate(INDEX_BQ, 1, 3)
+            line["index"]["cpu_baseline"] = {"value": irate, "unit": "queries/s", "cores": cores, "kind": "port",
+                                             "sample": f"3 batches of {INDEX_BQ} queries, torch-CPU matmul+topk ({isec * 1e3:.0f} ms/batch)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def softmax_roofline(model, B, pk, lib):
+    """Dominant kernel group: in-batch softmax fwd + bwd (6.B^2.E algorithmic flop), timed alone with CUDA events."""
+    import torch
+
+    from pkg import _native as N
+
+    sw = model._step_ws(B)
+    e = model.joint_embedding_size
+    use_tc = model.impl != N.TT_IMPL_SIMT and model._tc_ok()
+    q, c = (sw.q.out_tf32, sw.c.out_tf32) if use_tc else (sw.q.acts[-1], sw.c.acts[-1])
+    impl = N.TT_IMPL_TC if use_tc else N.TT_IMPL_SIMT
+    bias = sw.col_bias.data_ptr() if sw.col_bias is not None else None
+    st = N.stream_ptr()
+
+    def once():
+        N.check(lib.tt_inbatch_softmax_fwd(q.data_ptr(), e, c.data_ptr(), e, bias, B, B, e, 0, sw.lse.data_ptr(), sw.loss.data_ptr(),
+                                           sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st))
+        N.check(lib.tt_inbatch_softmax_bwd(q.data_ptr(), e, c.data_ptr(), e, bias, sw.lse.data_ptr(), B, B, e, 0, sw.dq.data_ptr(), e,
+                                           sw.dc.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st))
+
+    for _ in range(3):
+        once()
+    torch.cuda.synchronize()
+    n = 10
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(n):
+        once()
+    ev1.record()
+    torch.cuda.synchronize()
+    sec = ev0.elapsed_time(ev1) * 1e-3 / n
+    flops = 6.0 * B * B * e
+    achieved = flops / sec / 1e12
+    return {"bound": "tensor", "kernel": "in-batch softmax fwd+bwd (%s)" % ("tcgen05 tf32" if use_tc else "fp32 CUDA cores"),
+            "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_burst"], "traffic": None,
+            "ms": sec * 1e3, "algorithmic_flop": flops, "peak_source": pk["source"] + ", dense bf16 burst (kernel timed alone)"}
+
+
+def index_bench(model, pk, lib, steps):
+    """Index half of the metric: N=105 542 candidate-tower outputs, E=64, top-100, 2048 queries per batch."""
+    import torch
+
+    from pkg import _native as N
+    from pkg.modelling.indices.brute_force import BruteForceIndex
+
+    art = np.arange(1, V_ARTICLES + 1, dtype=np.int32)
+    pairs = []
+    for lo in range(0, V_ARTICLES, 10000):   # candidate_batch_size = 10000 (training_config.py:36)
+        a = art[lo:lo + 10000]
+        x = {"article_id": a.reshape(-1, 1), "product_type_name": (a % V_PTYPE + 1).reshape(-1, 1), "colour_group_name": (a % V_COLOUR + 1).reshape(-1, 1)}
+        pairs.append((a, model.candidate_tower(x)))
+    index = BruteForceIndex(INDEX_K, model.query_tower, pairs)
+    index.impl = model.impl
+    rng = np.random.default_rng(77)
+    pool = 4
+    hq = [{"age": rng.random((INDEX_BQ, 1)).astype(np.float32), "customer_id": rng.integers(1, V_CUSTOMERS + 1, size=(INDEX_BQ, 1)).astype(np.int32)}
+          for _ in range(pool)]
+    dq = [{k: torch.from_numpy(v).cuda() for k, v in h.items()} for h in hq]
+    pq = [{k: torch.from_numpy(v).pin_memory() for k, v in h.items()} for h in hq]
+    n = max(steps, 5)
+    c0 = lib.tt_launch_count()
+    for i in range(3):
+        index.query_indices(dq[i % pool])
+    torch.cuda.synchronize()
+    per_call = int((lib.tt_launch_count() - c0) // 3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(n):
+        index.query_indices(dq[i % pool])
+    ev1.record()
+    torch.cuda.synchronize()
+    sec = ev0.elapsed_time(ev1) * 1e-3 / n
+    # scoring + selection alone (embeddings resident): the dominant kernel group of the index path
+    qe = index._embed_queries(dq[0])
+    for _ in range(2):
+        index.search(qe)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(n):
+        index.search(qe)
+    ev1.record()
+    torch.cuda.synchronize()
+    ksec = ev0.elapsed_time(ev1) * 1e-3 / n
+    t0 = time.perf_counter()
+    for i in range(n):
+        ids = index(pq[i % pool])          # host ids in, (Bq, K) identifiers out on the host
+    e2e_sec = (time.perf_counter() - t0) / n
+    flops = 2.0 * INDEX_BQ * V_ARTICLES * JOINT
+    ach = flops / ksec / 1e12
+    return {"metric": "index queries/s (top-100, 105k items)", "value": INDEX_BQ / sec, "unit": "queries/s", "ms_per_batch": sec * 1e3,
+            "e2e": {"value": INDEX_BQ / e2e_sec, "unit": "queries/s", "h2d_bytes_per_step": INDEX_BQ * 8, "d2h_bytes_per_step": INDEX_BQ * INDEX_K * 4},
+            "config": f"N={V_ARTICLES} candidate-tower rows, E={JOINT}, K={INDEX_K}, Bq={INDEX_BQ}; corpus 27 MB is L2-resident (stated)",
+            "gpu_launches_per_batch": per_call,
+            "roofline": {"bound": "tensor", "kernel": "index scoring + top-K", "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                         "frac": ach / pk["tflops_burst"], "traffic": None, "ms": ksec * 1e3, "algorithmic_flop": flops},
+            "sample_ids": [str(x) for x in ids[0, :3]]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--simt", action="store_true", help="force the exact fp32 CUDA-core contraction path")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

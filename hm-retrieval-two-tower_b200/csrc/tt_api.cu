@@ -1,6 +1,8 @@
 // tt_api.cu -- library plumbing and the small element-wise entry points of tt.h.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "tt_common.cuh"
 
 namespace tt {
@@ -13,6 +15,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
     static int cached = 0;
@@ -168,6 +173,8 @@ extern "C" {
 int tt_version(void) { return 100; }
 
 const char* tt_last_error(void) { return tt::g_err; }
+
+int64_t tt_launch_count(void) { return tt::g_launches.load(); }
 
 int tt_device_supports_tc(void) {
     int dev = 0, major = 0;

@@ -10,6 +10,7 @@
 namespace tt {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define TT_REQUIRE(cond, ...)                 \
     do {                                      \
@@ -37,6 +38,7 @@ void set_error(const char* fmt, ...);
             (void)cudaGetLastError();                                                         \
             return TT_ERR_CUDA;                                                               \
         }                                                                                     \
+        tt::count_launch();                                                                   \
     } while (0)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

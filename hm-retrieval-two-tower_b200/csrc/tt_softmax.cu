@@ -32,7 +32,17 @@ static int pick_impl(int impl, int ldq, int ldc, int E, const void* Q, const voi
 
 using namespace tt;
 
+namespace tt {
+bool index_tc_supported(int ldq, int ldc, int E, int K, int64_t n, const void* Q, const void* C);
+}
+
 extern "C" {
+
+int tt_tc_available(int kind, int E) {
+    if (kind == 0) return softmax_tc_supported(E, E, E, nullptr, nullptr) ? 1 : 0;
+    if (kind == 1) return index_tc_supported(E, E, E, 100, 1 << 20, nullptr, nullptr) ? 1 : 0;
+    return 0;
+}
 
 size_t tt_softmax_workspace_bytes(int Bq, int Bc, int E) {
     (void)E;

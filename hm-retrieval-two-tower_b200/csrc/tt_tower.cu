@@ -284,6 +284,7 @@ using namespace tt;
 extern "C" {
 
 int tt_gather_concat(const tt_feature* feats, int nfeat, int B, int D, float* X, int ldx, void* stream) {
+    if (B == 0) return TT_OK;
     int rc = check_feats(feats, nfeat, D, "tt_gather_concat");
     if (rc) return rc;
     TT_REQUIRE(X != nullptr && B >= 0 && ldx >= D && ldx <= kMaxGatherCols, "tt_gather_concat: bad output shape");
@@ -333,6 +334,7 @@ int tt_dense_fwd(const float* X, int ldx, const float* W, const float* b, float*
 
 int tt_input_dense_fwd(const tt_feature* feats, int nfeat, int D, const float* W, const float* b, float* X_out, int ldx, float* Y,
                        int ldy, float* Y_tf32, int B, int N, int relu, void* stream) {
+    if (B == 0) return TT_OK;
     int rc = check_feats(feats, nfeat, D, "tt_input_dense_fwd");
     if (rc) return rc;
     TT_REQUIRE(W && Y, "tt_input_dense_fwd: null pointer");

@@ -37,6 +37,8 @@ SIGNATURES = {
     "tt_version": (c_int, []),
     "tt_last_error": (ctypes.c_char_p, []),
     "tt_device_supports_tc": (c_int, []),
+    "tt_launch_count": (c_int64, []),
+    "tt_tc_available": (c_int, [c_int, c_int]),
     "tt_gather_concat": (c_int, [ctypes.POINTER(TTFeature), c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "tt_dense_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p]),

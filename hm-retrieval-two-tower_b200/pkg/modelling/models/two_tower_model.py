@@ -270,7 +270,7 @@ class TwoTowerModel(AbstractKerasModel):
                                        sw.sp_ws.numel(), st), "tt_sparse_adam")
 
     def _tc_ok(self) -> bool:
-        return bool(N.load().tt_device_supports_tc()) and self.joint_embedding_size in (32, 64, 128)
+        return bool(N.load().tt_tc_available(0, self.joint_embedding_size))
 
     def train_step(self, data) -> Dict[str, object]:
         """One optimisation step on a batch {feature name: (B,1) column}.  Returns {"loss": 0-d device

@@ -46,6 +46,11 @@ int tt_version(void);
 const char* tt_last_error(void);
 /* 1 when the current device is compute capability 10.x and the tcgen05 kernels can launch. */
 int tt_device_supports_tc(void);
+/* 1 when TT_IMPL_AUTO resolves to the tensor-core kernels for the in-batch softmax (kind 0) or the index
+ * (kind 1) at joint dimension E on the current device; callers use it to pick the TF32-rounded operands. */
+int tt_tc_available(int kind, int E);
+/* Number of kernels this library has launched (or captured into a CUDA graph) in this process so far. */
+int64_t tt_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * InputLayer (pkg/modelling/layers/input_layer.py:45-69): one column block per feature.

@@ -1,0 +1,294 @@
+"""The reference-facing Python API (pkg.modelling) on the GPU, checked against the oracle, the reference's
+own fixtures and the KAT vectors."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import two_tower_oracle as O  # noqa: E402
+from pkg.schema import dtypes as tt  # noqa: E402
+from pkg.schema.features import Feature, FeatureFamily  # noqa: E402
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _set(t, a):
+    import torch
+
+    t.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda())
+
+
+def _kat_model(a, lib):
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+    from pkg.modelling.losses import CategoricalCrossentropy, Reduction
+
+    qf = [Feature("q", tt.string, FeatureFamily.QUERY, embedding_size=2, vocab=["1", "2", "3"])]
+    cf = [Feature("c", tt.string, FeatureFamily.CANDIDATE, embedding_size=2, vocab=["1", "2"])]
+    p = a["p_row"]
+    m = TwoTowerModel(qf, cf, "c", 2, candidate_prob_lookup={"1": p[1], "2": p[2]})
+    _set(m.query_tower.input_layer.embedding_layers["q"].weight, a["Tq"])
+    _set(m.candidate_tower.input_layer.embedding_layers["c"].weight, a["Tc"])
+    _set(m.query_tower.kernels[0], a["Wq"]); _set(m.query_tower.biases[0], a["bq"])
+    _set(m.candidate_tower.kernels[0], a["Wc"]); _set(m.candidate_tower.biases[0], a["bc"])
+    m.compile(loss=CategoricalCrossentropy(from_logits=True, reduction=Reduction.SUM),
+              optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": a["lr"]}))
+    return m
+
+
+@pytest.mark.parametrize("encoded", [False, True])
+def test_kat_a_train_step_through_the_api(lib, golden, encoded):
+    _, kat = golden
+    a = kat["A"]
+    m = _kat_model(a, lib)
+    if encoded:   # pre-encoded row ids (fast path) -- same result as strings
+        data = {"q": np.array(a["query_ids"], np.int32).reshape(-1, 1), "c": np.array(a["candidate_ids"], np.int32).reshape(-1, 1)}
+    else:
+        data = {"q": np.array([[str(i)] for i in a["query_ids"]], dtype=object),
+                "c": np.array([[str(i)] for i in a["candidate_ids"]], dtype=object)}
+    logits = _np(m(data))
+    np.testing.assert_allclose(logits, a["S"], atol=1e-7)                       # call(): raw Q.C^T, no logQ (:65-92)
+    out = m.train_step(data)
+    assert abs(float(out["loss"]) - a["loss"]) < 1e-5
+    np.testing.assert_allclose(_np(m.candidate_tower.input_layer.embedding_layers["c"].weight), a["Tc_after"], atol=1e-6)
+    np.testing.assert_allclose(_np(m.query_tower.input_layer.embedding_layers["q"].weight), a["Tq_after"], atol=1e-6)
+    np.testing.assert_allclose(_np(m.query_tower.kernels[0]), a["Wq_after"], atol=1e-6)
+    np.testing.assert_allclose(_np(m.query_tower.biases[0]), a["bq_after"], atol=1e-6)
+    np.testing.assert_allclose(_np(m.candidate_tower.kernels[0]), a["Wc_after"], atol=1e-6)
+    np.testing.assert_allclose(_np(m.candidate_tower.biases[0]), a["bc_after"], atol=1e-6)
+    np.testing.assert_allclose(_np(m._opt_state["tables"][id(m.candidate_tower.input_layer.embedding_layers["c"])][0]),
+                               a["acc_c_after"], atol=1e-6)
+
+
+def test_constructor_errors(lib):
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+
+    qf = [Feature("q", tt.string, FeatureFamily.QUERY, embedding_size=2, vocab=["1"])]
+    cf = [Feature("c", tt.string, FeatureFamily.CANDIDATE, embedding_size=2, vocab=["1"])]
+    with pytest.raises(ValueError):
+        TwoTowerModel(qf, cf, "nope", 2)                                         # two_tower_model.py:47-50
+    m = TwoTowerModel(qf, cf, "c", 2)
+    with pytest.raises(RuntimeError):
+        m.train_step({"q": np.array([["1"]]), "c": np.array([["1"]])})
+    assert set(m.get_input_signature()) == {"q", "c"}
+    assert m.get_input_signature()["q"].shape == (None, 1)
+
+
+def test_logq_layer_reference_fixture(lib, golden):
+    from pkg.modelling.layers.logq_correction import LogQCorrection
+
+    fix, _ = golden
+    g = fix["logq"]
+    layer = LogQCorrection(g["candidate_prob_lookup"])
+    out = layer(np.array(g["logits"], np.float32), np.array(g["candidate_ids"]).reshape(3, 1))
+    np.testing.assert_allclose(_np(out), np.array(g["expected"]), rtol=0, atol=5e-7)   # tests/test_layers.py:26-39
+    same = layer(np.array(g["logits"], np.float32), np.array(["zz", "zz", "zz"]).reshape(3, 1))
+    np.testing.assert_allclose(_np(same), np.array(g["logits"]), atol=0)        # unknown ids: ln(1) = 0
+
+
+class _MockEmbeddingModel:
+    """The reference test's fake query tower (tests/test_indices.py:8-60): StringLookup + row gather."""
+
+    def __init__(self, vocab, table):
+        from pkg.modelling._device import Vocab
+
+        self.vocab, self.table = Vocab(vocab), np.asarray(table, np.float32)
+
+    def __call__(self, x):
+        return self.table[self.vocab.encode(x["id"])]
+
+    def get_input_signature(self):
+        from pkg.modelling.models.abstract_keras_model import TensorSpec
+
+        return {"id": TensorSpec((None, 1), tt.string, "id")}
+
+
+def test_brute_force_index_reference_fixture(lib, golden):
+    from pkg.modelling.indices.brute_force import BruteForceIndex
+    from pkg.modelling.metrics.index_recall import IndexRecall
+
+    fix, _ = golden
+    g = fix["brute_force"]
+    qm = _MockEmbeddingModel(g["query_vocab"], g["query_table"])
+    pairs = [(np.array([i]), np.array([e], np.float32)) for i, e in zip(g["candidate_ids"], g["candidate_embeddings"])]  # batch(1)
+    index = BruteForceIndex(g["k"], qm, pairs)
+    inputs = {"id": np.array(g["queries"], dtype=object).reshape(5, 1)}
+    assert index(inputs).tolist() == g["expected"]                               # tests/test_indices.py:105-132
+    assert index._candidates.shape == (5, 2) and index._identifiers.shape == (5,)
+    # recall over that index: true ids chosen so that hits@1 = 3, hits@2 = 4
+    metric = IndexRecall(index, ks=[1, 2])
+    truth = np.array(["candidate_1", "candidate_4", "candidate_5", "candidate_9", "candidate_1"], dtype=object).reshape(5, 1)
+    metric(inputs, truth)
+    assert metric.hits[1] == 3 and metric.hits[2] == 4 and metric.metric[2] == np.float64(0.8)
+    with pytest.raises(ValueError):
+        BruteForceIndex(6, qm, pairs)
+
+
+def _c2_features(vq, vc):
+    qf = [Feature("age", tt.float32, FeatureFamily.QUERY),
+          Feature("customer_id", tt.string, FeatureFamily.QUERY, embedding_size=64)]
+    cf = [Feature("article_id", tt.string, FeatureFamily.CANDIDATE, embedding_size=64),
+          Feature("product_type_name", tt.string, FeatureFamily.CANDIDATE, embedding_size=16),
+          Feature("colour_group_name", tt.string, FeatureFamily.CANDIDATE, embedding_size=8)]
+    qf[1].set_vocab_size(vq); cf[0].set_vocab_size(vc); cf[1].set_vocab_size(131); cf[2].set_vocab_size(50)
+    return qf, cf
+
+
+def _oracle_twin(m):
+    def tower(t):
+        feats = [O.OracleFeature(f.name, f.dtype == tt.string, f.embedding_size) for f in t.features]
+        tables = {n: _np(e.weight).copy() for n, e in t.input_layer.embedding_layers.items()}
+        dense = [(_np(w).copy(), _np(b).copy()) for w, b in zip(t.kernels, t.biases)]
+        return O.OracleTower(feats, tables, dense)
+    return tower(m.query_tower), tower(m.candidate_tower)
+
+
+def _batch(rng, B, vq, vc):
+    art = np.minimum(rng.zipf(1.2, size=B), vc).astype(np.int32)            # duplicates in the batch
+    return {"age": rng.random((B, 1)).astype(np.float32), "customer_id": rng.integers(0, vq + 1, size=(B, 1)).astype(np.int32),
+            "article_id": art.reshape(B, 1), "product_type_name": (art % 131 + 1).reshape(B, 1).astype(np.int32),
+            "colour_group_name": (art % 50 + 1).reshape(B, 1).astype(np.int32)}
+
+
+@pytest.mark.parametrize("hidden", [None, [96]])
+@pytest.mark.parametrize("impl", [1])
+def test_train_step_matches_oracle_c2_shape(lib, hidden, impl):
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+
+    set_seed(99)
+    vq, vc, B = 5000, 800, 777
+    qf, cf = _c2_features(vq, vc)
+    rng = np.random.default_rng(21)
+    probs = {str(i + 1): float(p) for i, p in enumerate(rng.dirichlet(np.ones(vc)))}
+    m = TwoTowerModel(qf, cf, "article_id", 64, hidden, hidden, candidate_prob_lookup=probs)
+    m.impl = impl
+    m.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))
+    qt, ct = _oracle_twin(m)
+    data = _batch(rng, B, vq, vc)
+    p_rows = np.ones(vc + 1, np.float32); p_rows[1:] = [np.float32(probs[str(i + 1)]) for i in range(vc)]
+    col_p = p_rows[data["article_id"].reshape(-1)]
+    ids_q = {"customer_id": data["customer_id"]}; ids_c = {k: data[k] for k in ("article_id", "product_type_name", "colour_group_name")}
+    g = O.train_step_grads(qt, ct, ids_q, {"age": data["age"]}, ids_c, {}, col_p)
+    logits = _np(m(data))
+    # north star: logits within 1e-3 relative (fp32 exact path: bit-level agreement up to fp64-vs-fp32 accumulation)
+    np.testing.assert_allclose(logits, g.logits + np.log(col_p)[None, :], rtol=1e-5, atol=1e-6)
+    out = m.train_step(data)
+    assert abs(float(out["loss"]) - g.loss) <= 1e-5 * abs(g.loss)
+    # apply the oracle's optimizer and compare every parameter
+    for tower, ot, dg, sl in ((m.query_tower, qt, g.dense_q, g.tables_q), (m.candidate_tower, ct, g.dense_c, g.tables_c)):
+        for i, (w, b) in enumerate(ot.dense):
+            aw, ab = np.full_like(w, 0.1), np.full_like(b, 0.1)
+            O.adagrad_dense(w, aw, dg[i][0], 0.05); O.adagrad_dense(b, ab, dg[i][1], 0.05)
+            # Adagrad's first step moves each weight by ~lr*sign(g): compare the update, not the weight
+            np.testing.assert_allclose(_np(tower.kernels[i]), w, rtol=0, atol=2e-4)
+            np.testing.assert_allclose(_np(tower.biases[i]), b, rtol=0, atol=2e-4)
+        for name, s in sl.items():
+            t = ot.tables[name]; acc = np.full_like(t, 0.1)
+            O.adagrad_sparse(t, acc, s, 0.05)
+            got = _np(tower.input_layer.embedding_layers[name].weight)
+            np.testing.assert_allclose(got, t, rtol=0, atol=2e-4)
+            untouched = np.setdiff1d(np.arange(t.shape[0]), s.indices)
+            assert np.array_equal(got[untouched], t[untouched])                # only touched rows move
+
+
+def test_training_is_deterministic_and_graph_equals_eager(lib):
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+
+    def run(graph):
+        set_seed(5)
+        qf, cf = _c2_features(3000, 500)
+        m = TwoTowerModel(qf, cf, "article_id", 64, candidate_prob_lookup={str(i + 1): 1.0 / 500 for i in range(500)})
+        m.use_cuda_graph = graph
+        m.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))
+        rng = np.random.default_rng(1)
+        losses = []
+        for _ in range(5):
+            losses.append(float(m.train_step(_batch(rng, 512, 3000, 500))["loss"]))
+        state = m.state_arrays()
+        return losses, state
+
+    l1, s1 = run(False)
+    l2, s2 = run(False)
+    l3, s3 = run(True)
+    assert l1 == l2 and all(np.array_equal(s1[k], s2[k]) for k in s1)          # run-to-run bit-identical
+    assert l1 == l3 and all(np.array_equal(s1[k], s3[k]) for k in s1)          # CUDA-graph replay == eager
+    assert l1[-1] < l1[0]                                                        # and it learns
+
+
+def test_fit_accepts_ragged_final_batch_and_save(lib, tmp_path):
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+
+    qf, cf = _c2_features(1000, 300)
+    m = TwoTowerModel(qf, cf, "article_id", 32)
+    m.compile(optimizer=OptimizerFactory.get_optimizer("adam", {"learning_rate": 0.001}))
+    rng = np.random.default_rng(2)
+    ds = [_batch(rng, b, 1000, 300) for b in (256, 256, 100)]                    # drop_remainder=False (tfrecord_dataset.py:97)
+    h = m.fit(ds, epochs=2, verbose=0)
+    assert len(h["loss"]) == 2 and np.isfinite(h["loss"]).all() and h["loss"][1] < h["loss"][0]
+    m.save(str(tmp_path / "model") + "/")
+    for sub in ("two_tower", "query_tower", "candidate_tower"):                  # two_tower_model.py:176-205
+        assert (tmp_path / sub / "variables.npz").exists()
+
+
+def test_adam_train_step_matches_oracle(lib):
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+
+    set_seed(7)
+    qf, cf = _c2_features(400, 120)
+    m = TwoTowerModel(qf, cf, "article_id", 32)
+    m.compile(optimizer=OptimizerFactory.get_optimizer("adam", {"learning_rate": 0.01}))
+    qt, ct = _oracle_twin(m)
+    rng = np.random.default_rng(3)
+    data = _batch(rng, 200, 400, 120)
+    g = O.train_step_grads(qt, ct, {"customer_id": data["customer_id"]}, {"age": data["age"]},
+                           {k: data[k] for k in ("article_id", "product_type_name", "colour_group_name")}, {}, None)
+    m.train_step(data)
+    t = ct.tables["article_id"]; mm = np.zeros_like(t); vv = np.zeros_like(t)
+    O.adam_sparse(t, mm, vv, g.tables_c["article_id"], 0.01, 1)
+    got = _np(m.candidate_tower.input_layer.embedding_layers["article_id"].weight)
+    np.testing.assert_allclose(got, t, rtol=0, atol=5e-4)   # first Adam step is ~lr*sign(g); sign flips only where |g|~0
+    w, b = ct.dense[0]; mw = np.zeros_like(w); vw = np.zeros_like(w)
+    O.adam_dense(w, mw, vw, g.dense_c[0][0], 0.01, 1)
+    np.testing.assert_allclose(_np(m.candidate_tower.kernels[0]), w, rtol=0, atol=5e-4)
+
+
+def test_index_over_trained_towers_recall_at_12_bit_exact(lib):
+    """C2-style eval: candidate tower -> BruteForceIndex -> Recall@12, indices bit-exact vs the oracle."""
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.indices.brute_force import BruteForceIndex
+    from pkg.modelling.metrics.index_recall import IndexRecall
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+
+    set_seed(11)
+    vq, vc = 2000, 3000
+    qf, cf = _c2_features(vq, vc)
+    m = TwoTowerModel(qf, cf, "article_id", 64)
+    art = np.arange(1, vc + 1, dtype=np.int32)
+    pairs = []
+    for lo in range(0, vc, 1000):                                                # candidate_batch_size
+        a = art[lo:lo + 1000]
+        x = {"article_id": a.reshape(-1, 1), "product_type_name": (a % 131 + 1).reshape(-1, 1), "colour_group_name": (a % 50 + 1).reshape(-1, 1)}
+        pairs.append((a, m.candidate_tower(x)))
+    index = BruteForceIndex(12, m.query_tower, pairs)
+    index.impl = 1
+    rng = np.random.default_rng(4)
+    B = 300
+    queries = {"age": rng.random((B, 1)).astype(np.float32), "customer_id": rng.integers(0, vq + 1, size=(B, 1)).astype(np.int32)}
+    truth = rng.integers(1, vc + 1, size=(B, 1)).astype(np.int32)
+    got = index(queries)
+    q_emb = _np(m.query_tower(queries)); c_emb = _np(index._candidates)
+    _, want = O.index_topk(q_emb, c_emb, 12)
+    assert np.array_equal(got, art[want])
+    metric = IndexRecall(index, [1, 12])
+    metric(queries, truth)
+    rec = O.RecallOracle([1, 12]); rec.update(truth, art[want])
+    assert metric.hits[12] == rec.hits[12] and metric.metric[12] == rec.metric[12]

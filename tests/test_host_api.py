@@ -1,0 +1,113 @@
+"""Host-side mirror of the reference API: validation, vocabulary, StaticIndex + IndexRecall (CPU only)."""
+import numpy as np
+import pytest
+
+from pkg.modelling.indices.static_index import StaticIndex
+from pkg.modelling.metrics.index_recall import IndexRecall
+from pkg.modelling.optimizer_factory import Adagrad, Adam, OptimizerFactory
+from pkg.modelling._device import Vocab
+from pkg.schema import dtypes as tt
+from pkg.schema.features import Feature, FeatureFamily
+from pkg.schema.model_config import ModelConfig
+from pkg.schema.schema import Schema
+from pkg.schema.training_config import TrainingConfig
+
+
+def test_feature_validation_matches_reference_errors():
+    with pytest.raises(TypeError):
+        Feature("x", "int64", FeatureFamily.QUERY)                       # features.py:55-58
+    with pytest.raises(ValueError):
+        Feature("x", tt.string, "query")                                 # features.py:61-65
+    with pytest.raises(TypeError):
+        Feature("x", tt.float32, FeatureFamily.QUERY, embedding_size=4)  # features.py:69-72
+    with pytest.raises(TypeError):
+        Feature("x", tt.string, FeatureFamily.QUERY, max_vocab_size="3")  # features.py:77-80
+    f = Feature("age", tt.float32, FeatureFamily.QUERY, vocab=["a"])
+    assert f.vocab is None and f.is_built
+    g = Feature("id", tt.string, FeatureFamily.CANDIDATE, embedding_size=8)
+    assert not g.is_built
+
+
+def test_vocab_from_dataframe_is_value_counts_order():
+    import pandas as pd
+
+    df = pd.DataFrame({"id": ["b", "a", "b", "c", "b", "a"]})
+    f = Feature("id", tt.string, FeatureFamily.CANDIDATE, embedding_size=4, max_vocab_size=2)
+    f.set_vocab_from_dataframe(df)
+    assert list(f.vocab) == ["b", "a"]                                   # features.py:119-127
+    with pytest.raises(ValueError):
+        Feature("zz", tt.string, FeatureFamily.CANDIDATE, embedding_size=4).set_vocab_from_dataframe(df)
+
+
+def test_string_lookup_semantics():
+    v = Vocab(["query_1", "query_2", "query_3"])
+    ids = v.encode(np.array([["query_1"], [b"query_3"], ["query_4"]], dtype=object))
+    assert ids.tolist() == [1, 3, 0] and ids.dtype == np.int32 and v.rows == 4
+
+
+def test_schema_split_and_pickle_roundtrip(tmp_path):
+    feats = [Feature("customer_id", tt.string, FeatureFamily.QUERY, 8, vocab=["1"]),
+             Feature("article_id", tt.string, FeatureFamily.CANDIDATE, 8, vocab=["2"])]
+    s = Schema(feats, TrainingConfig(512, 2048, "adagrad", {"learning_rate": 0.05}), ModelConfig(128, [10, 100]))
+    assert [f.name for f in s.query_features] == ["customer_id"]
+    assert s.training_config.candidate_batch_size == 10000 and s.training_config.epochs == 1
+    s.set_candidate_prob_lookup({"2": 0.5})
+    p = tmp_path / "d" / "schema.pkl"
+    s.save(str(p))
+    s2 = Schema.load_from_filepath(str(p))
+    assert s2.training_config.candidate_prob_lookup == {"2": 0.5} and s2.model_config.ks == [10, 100]
+
+
+def test_optimizer_factory_contract():
+    with pytest.raises(ValueError):
+        OptimizerFactory.get_optimizer("sgd", {"learning_rate": 0.1})     # optimizer_factory.py:43-48
+    with pytest.raises(ValueError):
+        OptimizerFactory.get_optimizer("adam", {})                        # optimizer_factory.py:49-53
+    a = OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05})
+    assert isinstance(a, Adagrad) and a.initial_accumulator_value == 0.1 and a.epsilon == 1e-7
+    m = OptimizerFactory.get_optimizer("adam", {"learning_rate": 0.001})
+    assert isinstance(m, Adam) and abs(m.lr_t(1) - 0.001 * (1 - 0.999) ** 0.5 / (1 - 0.9)) < 1e-12
+
+
+def test_recall_with_static_index_reference_fixture(golden):
+    fix, _ = golden
+    g = fix["recall"]
+    feats = [Feature("query_id", tt.string, FeatureFamily.QUERY, embedding_size=2)]
+    index = StaticIndex(k=g["static_k"], input_features=feats,
+                        candidates=np.array([s.encode() for s in g["static_candidates"]], dtype=object).reshape(1, -1))
+    metric = IndexRecall(index, ks=g["ks"])
+    q = np.array(g["query_ids"], dtype=object).reshape(-1, 1)
+    t = np.array([s.encode() for s in g["true_candidate_ids"]], dtype=object).reshape(-1, 1)
+    for i in range(0, 5, g["batch_size"]):
+        out = metric({"query_id": q[i:i + 2]}, t[i:i + 2])
+    for k, v in g["expected"].items():
+        assert metric.metric[int(k)] == np.float64(v) and isinstance(out[int(k)], np.float64)
+    assert index({"query_id": q[:3]}).shape == (3, 5)                     # tile(candidates[:, :k], (B, 1))
+    assert set(index.get_input_signature()) == {"query_id"}
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from pkg._native import TTError
+    from pkg.modelling.models.tower import Tower
+
+    with pytest.raises(TTError):
+        Tower([Feature("a", tt.string, FeatureFamily.QUERY, 4, vocab=["x"])], 8)
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    import re
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hm-retrieval-two-tower_b200")
+    bad = []
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(d, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|tt_oracle\.h|libtt_oracle", src, flags=re.M):
+                    bad.append(f)
+    assert not bad, f"product files reference the oracle: {bad}"
