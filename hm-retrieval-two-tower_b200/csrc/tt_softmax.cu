@@ -12,9 +12,11 @@ int logits_simt(const float* Q, int ldq, const float* C, int ldc, const float* b
 // tt_softmax_tc.cu
 bool softmax_tc_supported(int ldq, int ldc, int E, const void* Q, const void* C);
 int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse,
-                   float* loss, float* rowloss, cudaStream_t st);
+                   float* loss, float* ws, cudaStream_t st);
 int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const float* rowv, const float* colv, int nR, int nT, int E,
-                        int d, float* G, int ldg, cudaStream_t st);
+                        int d, float* G, int ldg, float* ws, cudaStream_t st);
+int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, float* Z, int ldz, cudaStream_t st);
+size_t softmax_tc_workspace_bytes(int Bq, int Bc, int E);
 
 static int pick_impl(int impl, int ldq, int ldc, int E, const void* Q, const void* C, const char* who) {
     if (impl == TT_IMPL_SIMT) return TT_IMPL_SIMT;
@@ -45,9 +47,10 @@ int tt_tc_available(int kind, int E) {
 }
 
 size_t tt_softmax_workspace_bytes(int Bq, int Bc, int E) {
-    (void)E;
     size_t rows = (size_t)(Bq > Bc ? Bq : Bc);
-    return align_up(rows * sizeof(float), 256) + 512;
+    size_t simt = align_up(rows * sizeof(float), 256) + 512;
+    size_t tcb = (E == 32 || E == 64 || E == 128) ? softmax_tc_workspace_bytes(Bq, Bc, E) : 0;
+    return simt > tcb ? simt : tcb;
 }
 
 int tt_inbatch_softmax_fwd(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, int Bq, int Bc, int E,
@@ -64,16 +67,15 @@ int tt_inbatch_softmax_fwd(const float* Q, int ldq, const float* C, int ldc, con
     int use = pick_impl(impl, ldq, ldc, E, Q, C, "tt_inbatch_softmax_fwd");
     if (use < 0) return use;
     float* rowloss = reinterpret_cast<float*>(ws);
-    if (use == TT_IMPL_TC) return softmax_fwd_tc(Q, ldq, C, ldc, col_bias, Bq, Bc, E, diag_offset, lse, loss, rowloss, st);
+    if (use == TT_IMPL_TC) return softmax_fwd_tc(Q, ldq, C, ldc, col_bias, Bq, Bc, E, diag_offset, lse, loss, rowloss, st);  // rowloss == ws base
     return softmax_fwd_simt(Q, ldq, C, ldc, col_bias, Bq, Bc, E, diag_offset, lse, loss, rowloss, st);
 }
 
 int tt_inbatch_softmax_bwd(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, const float* lse, int Bq, int Bc,
                            int E, int diag_offset, float* dQ, int lddq, float* dC, int lddc, void* ws, size_t ws_bytes, int impl,
                            void* stream) {
-    (void)ws;
-    (void)ws_bytes;
     TT_REQUIRE(Q && C && lse && dQ && dC, "tt_inbatch_softmax_bwd: null pointer");
+    TT_REQUIRE(ws && ws_bytes >= tt_softmax_workspace_bytes(Bq, Bc, E), "tt_inbatch_softmax_bwd: workspace too small");
     TT_REQUIRE(Bq >= 0 && Bc >= 0 && E >= 1 && ldq >= E && ldc >= E && lddq >= E && lddc >= E, "tt_inbatch_softmax_bwd: bad shape");
     TT_REQUIRE(diag_offset >= 0 && (Bq == 0 || diag_offset + Bq <= Bc), "tt_inbatch_softmax_bwd: bad diag_offset");
     cudaStream_t st = as_stream(stream);
@@ -85,9 +87,10 @@ int tt_inbatch_softmax_bwd(const float* Q, int ldq, const float* C, int ldc, con
     }
     int rc;
     if (use == TT_IMPL_TC) {
-        rc = softmax_bwd_pass_tc(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, dQ, lddq, st);
+        float* wsf = reinterpret_cast<float*>(ws);
+        rc = softmax_bwd_pass_tc(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, dQ, lddq, wsf, st);
         if (rc) return rc;
-        return softmax_bwd_pass_tc(C, ldc, Q, ldq, col_bias, lse, Bc, Bq, E, -diag_offset, dC, lddc, st);
+        return softmax_bwd_pass_tc(C, ldc, Q, ldq, col_bias, lse, Bc, Bq, E, -diag_offset, dC, lddc, wsf, st);
     }
     rc = softmax_bwd_pass_simt(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, dQ, lddq, st);
     if (rc) return rc;
@@ -96,10 +99,15 @@ int tt_inbatch_softmax_bwd(const float* Q, int ldq, const float* C, int ldc, con
 
 int tt_logits(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, int Bq, int Bc, int E, float* Z, int ldz,
               int impl, void* stream) {
-    (void)impl;  // the materialised matrix is an API/test convenience: always the exact path
+    // the materialised matrix is an API/test convenience: exact path unless TT_IMPL_TC is asked for explicitly
     TT_REQUIRE(Q && C && Z, "tt_logits: null pointer");
     TT_REQUIRE(Bq >= 0 && Bc >= 0 && E >= 1 && ldq >= E && ldc >= E && ldz >= Bc, "tt_logits: bad shape");
     if (Bq == 0 || Bc == 0) return TT_OK;
+    if (impl == TT_IMPL_TC) {
+        int use = pick_impl(impl, ldq, ldc, E, Q, C, "tt_logits");
+        if (use < 0) return use;
+        return logits_tc(Q, ldq, C, ldc, col_bias, Bq, Bc, E, Z, ldz, as_stream(stream));
+    }
     return logits_simt(Q, ldq, C, ldc, col_bias, Bq, Bc, E, Z, ldz, as_stream(stream));
 }
 

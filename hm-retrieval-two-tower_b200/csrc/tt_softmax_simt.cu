@@ -191,6 +191,12 @@ __global__ void __launch_bounds__(256) logits_simt_kernel(const float* __restric
     }
 }
 
+int sum_rows_launch(const float* v, int n, float* out, cudaStream_t st) {
+    sum_rows_kernel<<<1, 1024, 0, st>>>(v, n, out);
+    TT_LAUNCH_OK("sum_rows_kernel");
+    return TT_OK;
+}
+
 // ---- host-side entry points used by the dispatchers in tt_softmax.cu -------------------------------
 int softmax_fwd_simt(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse,
                      float* loss, float* rowloss, cudaStream_t st) {

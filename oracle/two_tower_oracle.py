@@ -327,8 +327,9 @@ def adam_dense(w, m, v, g, lr, step, b1=0.9, b2=0.999, eps=KERAS_EPS):
     w -= lr_t*m/(sqrt(v)+eps)."""
     g = g.astype(np.float32)
     a = adam_lr_t(lr, step, b1, b2)
-    m += (g - m) * np.float32(1.0 - b1)
-    v += (g * g - v) * np.float32(1.0 - b2)
+    # tf-keras forms (1 - beta) from the fp32 hyper-parameter tensors: fp32 subtraction, not float64
+    m += (g - m) * (np.float32(1.0) - np.float32(b1))
+    v += (g * g - v) * (np.float32(1.0) - np.float32(b2))
     w -= (m * a) / (np.sqrt(v) + np.float32(eps))
 
 
@@ -338,9 +339,9 @@ def adam_sparse(table, m, v, s: IndexedSlices, lr, step, b1=0.9, b2=0.999, eps=K
     d = dedup_indexed_slices(s)
     a = adam_lr_t(lr, step, b1, b2)
     m *= np.float32(b1)
-    m[d.indices] += d.values * np.float32(1.0 - b1)
+    m[d.indices] += d.values * (np.float32(1.0) - np.float32(b1))
     v *= np.float32(b2)
-    v[d.indices] += (d.values * d.values) * np.float32(1.0 - b2)
+    v[d.indices] += (d.values * d.values) * (np.float32(1.0) - np.float32(b2))
     table -= (m * a) / (np.sqrt(v) + np.float32(eps))
 
 

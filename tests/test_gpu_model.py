@@ -233,8 +233,8 @@ def test_fit_accepts_ragged_final_batch_and_save(lib, tmp_path):
     h = m.fit(ds, epochs=2, verbose=0)
     assert len(h["loss"]) == 2 and np.isfinite(h["loss"]).all() and h["loss"][1] < h["loss"][0]
     m.save(str(tmp_path / "model") + "/")
-    for sub in ("two_tower", "query_tower", "candidate_tower"):                  # two_tower_model.py:176-205
-        assert (tmp_path / sub / "variables.npz").exists()
+    for sub in ("two_tower", "query_tower", "candidate_tower"):                  # two_tower_model.py:176-205: dirname(model_path)/<sub>
+        assert (tmp_path / "model" / sub / "variables.npz").exists()
 
 
 def test_adam_train_step_matches_oracle(lib):

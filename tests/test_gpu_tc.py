@@ -1,0 +1,162 @@
+"""tcgen05 / TMA / TMEM kernels against the oracle.  Operands are TF32-rounded first (tt_round_tf32), so the
+tensor-core products are exact and only the fp32 accumulation order differs from the float64 oracle:
+logits agree to ~1e-6 relative; the north-star bound (1e-3 relative for loss and logits) is asserted with
+the tolerance written next to each check."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import two_tower_oracle as O  # noqa: E402
+
+TC = 2
+
+
+@pytest.fixture(scope="module")
+def T(lib):
+    import torch
+
+    if not lib.tt_tc_available(0, 64):
+        pytest.skip("tensor-core path unavailable on this device")
+    return torch
+
+
+def dev(T, a):
+    return T.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def stream():
+    from pkg import _native as N
+
+    return N.stream_ptr()
+
+
+def round_tf32(lib, T, a):
+    from pkg import _native as N
+
+    src = dev(T, a)
+    dst = T.empty_like(src)
+    N.check(lib.tt_round_tf32(src.data_ptr(), a.shape[1], dst.data_ptr(), a.shape[1], a.shape[0], a.shape[1], stream()))
+    return dst
+
+
+@pytest.mark.parametrize("Bq,Bc,E", [(128, 128, 64), (1, 1, 32), (300, 200, 32), (257, 1000, 128), (1024, 2100, 64), (130, 64, 64)])
+def test_logits_tc_matches_float64(lib, T, Bq, Bc, E):
+    from pkg import _native as N
+
+    rng = np.random.default_rng(1)
+    q = rng.standard_normal((Bq, E)).astype(np.float32)
+    c = rng.standard_normal((Bc, E)).astype(np.float32)
+    bias = rng.standard_normal(Bc).astype(np.float32)
+    dq, dc, db = round_tf32(lib, T, q), round_tf32(lib, T, c), dev(T, bias)
+    qr, cr = dq.cpu().numpy(), dc.cpu().numpy()
+    assert np.all((qr.view(np.uint32) & 0x1FFF) == 0)
+    want = O.logits_qct(qr, cr).astype(np.float64) - bias[None, :]
+    z = T.full((Bq, Bc), 777.0, dtype=T.float32, device="cuda")
+    N.check(lib.tt_logits(dq.data_ptr(), E, dc.data_ptr(), E, db.data_ptr(), Bq, Bc, E, z.data_ptr(), Bc, TC, stream()))
+    got = z.cpu().numpy()
+    # exact TF32 products, fp32 accumulation of <= 128 terms: 1e-5 of the row scale
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-5 * (np.abs(want).max() + 1.0))
+
+
+def test_logits_tc_dyadic_bit_exact(lib, T):
+    from pkg import _native as N
+
+    rng = np.random.default_rng(2)
+    q = (rng.integers(-16, 17, size=(200, 64)) / 16.0).astype(np.float32)      # exactly representable in TF32
+    c = (rng.integers(-16, 17, size=(333, 64)) / 16.0).astype(np.float32)
+    dq, dc = dev(T, q), dev(T, c)
+    z = T.empty((200, 333), dtype=T.float32, device="cuda")
+    N.check(lib.tt_logits(dq.data_ptr(), 64, dc.data_ptr(), 64, None, 200, 333, 64, z.data_ptr(), 333, TC, stream()))
+    assert np.array_equal(z.cpu().numpy(), O.logits_qct(q, c, canonical=True))  # every path is exact on this grid
+
+
+@pytest.mark.parametrize("Bq,Bc,E,off,bias", [(128, 128, 64, 0, True), (1000, 1000, 64, 0, True), (257, 257, 32, 0, True),
+                                              (130, 390, 64, 130, True), (300, 300, 128, 0, False), (2048, 2048, 64, 0, True),
+                                              (3, 3, 32, 0, True)])
+def test_softmax_fwd_bwd_tc(lib, T, Bq, Bc, E, off, bias):
+    from pkg import _native as N
+
+    rng = np.random.default_rng(5)
+    q = np.maximum(rng.standard_normal((Bq, E)) * 0.3, 0).astype(np.float32)
+    c = np.maximum(rng.standard_normal((Bc, E)) * 0.3, 0).astype(np.float32)
+    p = (rng.random(Bc) * 0.01 + 1e-5).astype(np.float32) if bias else None
+    dq_, dc_ = round_tf32(lib, T, q), round_tf32(lib, T, c)
+    qr, cr = dq_.cpu().numpy(), dc_.cpu().numpy()
+    s = O.logits_qct(qr, cr)
+    z = O.logq_correction(s, p) if bias else s
+    loss, lse, dz = O.ce_sum_from_logits(z, diag_offset=off)
+    want_dq, want_dc = dz @ cr.astype(np.float64), dz.T @ qr.astype(np.float64)
+    dbias = T.log(dev(T, p)) if bias else None
+    bp = dbias.data_ptr() if bias else None
+    d_lse = T.empty(Bq, dtype=T.float32, device="cuda"); d_loss = T.zeros(1, dtype=T.float32, device="cuda")
+    ws = T.empty(int(lib.tt_softmax_workspace_bytes(Bq, Bc, E)), dtype=T.uint8, device="cuda")
+    N.check(lib.tt_inbatch_softmax_fwd(dq_.data_ptr(), E, dc_.data_ptr(), E, bp, Bq, Bc, E, off, d_lse.data_ptr(), d_loss.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), TC, stream()))
+    # north star: loss within 1e-3 relative; measured agreement is ~1e-6, assert 1e-5
+    assert abs(float(d_loss) - loss) <= 1e-5 * abs(loss) + 1e-5
+    np.testing.assert_allclose(d_lse.cpu().numpy(), lse, rtol=1e-5, atol=1e-5)
+    gq = T.full((Bq, E), 9.0, dtype=T.float32, device="cuda"); gc = T.full((Bc, E), 9.0, dtype=T.float32, device="cuda")
+    N.check(lib.tt_inbatch_softmax_bwd(dq_.data_ptr(), E, dc_.data_ptr(), E, bp, d_lse.data_ptr(), Bq, Bc, E, off, gq.data_ptr(), E,
+                                       gc.data_ptr(), E, ws.data_ptr(), ws.numel(), TC, stream()))
+    # dZ is rounded to TF32 (2^-11 relative per element) before the second MMA: 1e-3 of the gradient scale
+    np.testing.assert_allclose(gq.cpu().numpy(), want_dq, rtol=0, atol=1e-3 * (np.abs(want_dq).max() + 1e-6))
+    np.testing.assert_allclose(gc.cpu().numpy(), want_dc, rtol=0, atol=1e-3 * (np.abs(want_dc).max() + 1e-6))
+    # deterministic: fixed-order split reduction, no atomics
+    gq2 = T.empty_like(gq); gc2 = T.empty_like(gc)
+    N.check(lib.tt_inbatch_softmax_bwd(dq_.data_ptr(), E, dc_.data_ptr(), E, bp, d_lse.data_ptr(), Bq, Bc, E, off, gq2.data_ptr(), E,
+                                       gc2.data_ptr(), E, ws.data_ptr(), ws.numel(), TC, stream()))
+    assert T.equal(gq, gq2) and T.equal(gc, gc2)
+
+
+def test_tc_and_exact_paths_agree_on_raw_fp32_operands(lib, T):
+    """Un-rounded fp32 operands: the tensor core truncates/rounds them to TF32 itself; the north-star bound
+    (logits within 1e-3 relative of the fp32 reference) must still hold."""
+    from pkg import _native as N
+
+    rng = np.random.default_rng(6)
+    Bq = Bc = 512; E = 64
+    q = np.maximum(rng.standard_normal((Bq, E)) * 0.3, 0).astype(np.float32)
+    c = np.maximum(rng.standard_normal((Bc, E)) * 0.3, 0).astype(np.float32)
+    dq_, dc_ = dev(T, q), dev(T, c)
+    z_tc = T.empty((Bq, Bc), dtype=T.float32, device="cuda"); z_ex = T.empty_like(z_tc)
+    N.check(lib.tt_logits(dq_.data_ptr(), E, dc_.data_ptr(), E, None, Bq, Bc, E, z_tc.data_ptr(), Bc, TC, stream()))
+    N.check(lib.tt_logits(dq_.data_ptr(), E, dc_.data_ptr(), E, None, Bq, Bc, E, z_ex.data_ptr(), Bc, 1, stream()))
+    a, b = z_tc.cpu().numpy(), z_ex.cpu().numpy()
+    rel = np.abs(a - b).max() / np.abs(b).max()
+    assert rel < 1e-3, rel
+
+
+def test_model_train_step_tc_within_north_star(lib, T):
+    from pkg import _native as N
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+    from pkg.schema import dtypes as tt
+    from pkg.schema.features import Feature, FeatureFamily
+
+    def build(impl):
+        set_seed(3)
+        qf = [Feature("age", tt.float32, FeatureFamily.QUERY), Feature("customer_id", tt.string, FeatureFamily.QUERY, embedding_size=64)]
+        cf = [Feature("article_id", tt.string, FeatureFamily.CANDIDATE, embedding_size=64)]
+        qf[1].set_vocab_size(4000); cf[0].set_vocab_size(900)
+        m = TwoTowerModel(qf, cf, "article_id", 64, candidate_prob_lookup={str(i + 1): 1.0 / 900 for i in range(900)})
+        m.impl = impl
+        m.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))
+        return m
+
+    rng = np.random.default_rng(9)
+    B = 1500
+    batches = [{"age": rng.random((B, 1)).astype(np.float32), "customer_id": rng.integers(0, 4001, size=(B, 1)).astype(np.int32),
+                "article_id": np.minimum(rng.zipf(1.2, size=(B, 1)), 900).astype(np.int32)} for _ in range(4)]
+    exact, tc = build(N.TT_IMPL_SIMT), build(N.TT_IMPL_AUTO)
+    assert tc._tc_ok()
+    for b in batches:
+        le, lt = float(exact.train_step(b)["loss"]), float(tc.train_step(b)["loss"])
+        assert abs(le - lt) <= 1e-3 * abs(le), (le, lt)                   # north star: loss within 1e-3 relative
+    we = exact.candidate_tower.input_layer.embedding_layers["article_id"].weight
+    wt = tc.candidate_tower.input_layer.embedding_layers["article_id"].weight
+    # trajectories stay together over 4 steps (Adagrad's early steps are ~lr*sign(g), so isolated elements whose
+    # gradient is ~0 may differ by a few 1e-2; the bulk must agree)
+    assert float((we - wt).abs().mean()) < 5e-4
+    assert float(((we - wt).abs() > 1e-2).float().mean()) < 1e-3

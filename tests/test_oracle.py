@@ -157,4 +157,4 @@ def test_merge_topk_is_independent_of_sharding():
 def test_adam_sparse_is_not_lazy():
     t = np.ones((4, 2), np.float32); m = np.full((4, 2), 0.5, np.float32); v = np.full((4, 2), 0.25, np.float32)
     O.adam_sparse(t, m, v, O.IndexedSlices(np.array([2]), np.array([[1.0, -1.0]], np.float32)), lr=0.1, step=1)
-    assert np.all(t[0] != 1.0) and np.all(m[0] == np.float32(0.45))   # untouched rows still decay and move
+    assert np.all(t[0] != 1.0) and np.all(m[0] == np.float32(0.5) * np.float32(0.9))   # untouched rows still decay and move
