@@ -17,6 +17,7 @@ int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const 
                         int d, float* G, int ldg, float* ws, cudaStream_t st);
 int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, float* Z, int ldz, cudaStream_t st);
 size_t softmax_tc_workspace_bytes(int Bq, int Bc, int E);
+void debug_tc(void* trace, int max_splits);
 
 static int pick_impl(int impl, int ldq, int ldc, int E, const void* Q, const void* C, const char* who) {
     if (impl == TT_IMPL_SIMT) return TT_IMPL_SIMT;
@@ -39,6 +40,11 @@ bool index_tc_supported(int ldq, int ldc, int E, int K, int64_t n, const void* Q
 }
 
 extern "C" {
+
+int tt_debug_tc(void* trace, int max_splits) {
+    debug_tc(trace, max_splits);
+    return TT_OK;
+}
 
 int tt_tc_available(int kind, int E) {
     if (kind == 0) return softmax_tc_supported(E, E, E, nullptr, nullptr) ? 1 : 0;

@@ -77,6 +77,18 @@ __global__ void bwd_reduce_kernel(const float* __restrict__ part, int splits, in
     G[r * ldg + c] = s;
 }
 
+// out[i] = colv[i] * log2(e) for i < n (0 when colv is null), zero padding up to n_pad
+__global__ void scale_pad_kernel(const float* __restrict__ colv, int n, float* __restrict__ out, int n_pad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) out[i] = (i < n && colv) ? colv[i] * kLog2e : 0.f;
+}
+
+static int launch_scale_pad(const float* colv, int n, float* out, int n_pad, cudaStream_t st) {
+    scale_pad_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, st>>>(colv, n, out, n_pad);
+    TT_LAUNCH_OK("scale_pad_kernel");
+    return TT_OK;
+}
+
 // out (cols x ldo) = in (rows x cols)^T, 32x32 shared-memory tiles, coalesced both ways
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int ld, int rows, int cols, float* __restrict__ out, int ldo) {
     __shared__ float tile[32][33];
@@ -103,13 +115,17 @@ static int launch_rowpanel(const CUtensorMap& tmR, const CUtensorMap& tmT, const
         attr_done = true;
     }
     dim3 grid((unsigned)m_tiles, (unsigned)splits);
-    rowpanel_kernel<MODE, E, BN><<<grid, 192, Cfg::kSmemBytes, st>>>(tmR, tmT, tmTt, p);
+    rowpanel_kernel<MODE, E, BN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmR, tmT, tmTt, p);
     TT_LAUNCH_OK(name);
     return TT_OK;
 }
 
 constexpr int kFwdBN = 128;
-constexpr int kMaxSplits = 16;
+constexpr int kMaxSplits = 16;   // column splits per launch; the forward keeps 2 partials per split (one per warp half)
+
+// debug knobs (tt_debug_tc): timeline buffer and a cap on the column splits
+static unsigned long long* g_trace = nullptr;
+static int g_max_splits = kMaxSplits;
 static inline int bwd_bn(int E) { return E <= 64 ? 64 : 32; }  // shared-memory budget (see RowPanelCfg)
 
 struct Plan {
@@ -119,7 +135,7 @@ static Plan plan_for(int nR, int nT, int bn) {
     Plan pl;
     pl.m_tiles = (int)ceil_div(nR, 128);
     pl.n_tiles = (int)ceil_div(nT, bn);
-    choose_splits(pl.m_tiles, pl.n_tiles, 2, kMaxSplits, &pl.splits, &pl.tps);
+    choose_splits(pl.m_tiles, pl.n_tiles, 2, g_max_splits, &pl.splits, &pl.tps);
     return pl;
 }
 
@@ -127,12 +143,12 @@ static inline size_t tt_ld(int n) { return align_up((size_t)n, 4); }
 
 static size_t bwd_pass_floats(int nR, int nT, int E) {
     Plan pl = plan_for(nR, nT, bwd_bn(E));
-    return align_up((size_t)pl.splits * nR * E, 64) + (size_t)E * tt_ld(nT) + 64;
+    return align_up((size_t)pl.splits * nR * E, 64) + align_up((size_t)E * tt_ld(nT), 64) + (size_t)nT + 512;
 }
 
 size_t softmax_tc_workspace(int Bq, int Bc, int E) {
     size_t rows = (size_t)(Bq > Bc ? Bq : Bc);
-    size_t fwd = (2 * (size_t)kMaxSplits + 2) * align_up(rows * sizeof(float), 256);
+    size_t fwd = (4 * (size_t)kMaxSplits + 4) * align_up(rows * sizeof(float), 256) + 2048;
     size_t a = bwd_pass_floats(Bq, Bc, E) * sizeof(float), b = bwd_pass_floats(Bc, Bq, E) * sizeof(float);
     size_t bwd = a > b ? a : b;
     return (fwd > bwd ? fwd : bwd) + 1024;
@@ -169,19 +185,22 @@ int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float
     size_t rows = (size_t)(Bq > Bc ? Bq : Bc);
     size_t seg = align_up(rows * sizeof(float), 256) / sizeof(float);
     float* m2 = ws;
-    float* l = ws + (size_t)kMaxSplits * seg;
-    float* zd = ws + 2 * (size_t)kMaxSplits * seg;
+    float* l = ws + 2 * (size_t)kMaxSplits * seg;
+    float* zd = ws + 4 * (size_t)kMaxSplits * seg;
     float* rowloss = zd + seg;
+    float* c2 = rowloss + seg;
+    rc = launch_scale_pad(bias, Bc, c2, pl.n_tiles * kFwdBN, st);
+    if (rc) return rc;
     RowPanelParams p{};
-    p.nR = Bq; p.nT = Bc; p.n_tiles = pl.n_tiles; p.tiles_per_split = pl.tps; p.rowv = nullptr; p.colv = bias; p.d = off;
-    p.out0 = m2; p.out1 = l; p.out2 = zd; p.ld_out = 0;
+    p.nR = Bq; p.nT = Bc; p.n_tiles = pl.n_tiles; p.tiles_per_split = pl.tps; p.rowv = nullptr; p.colv2 = c2; p.d = off;
+    p.out0 = m2; p.out1 = l; p.out2 = zd; p.ld_out = 0; p.trace = g_trace;
     switch (E) {
         case 32: rc = launch_rowpanel<kFwd, 32, kFwdBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<fwd,32>"); break;
         case 64: rc = launch_rowpanel<kFwd, 64, kFwdBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<fwd,64>"); break;
         default: rc = launch_rowpanel<kFwd, 128, kFwdBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<fwd,128>"); break;
     }
     if (rc) return rc;
-    fwd_combine_kernel<<<(unsigned)ceil_div(Bq, 256), 256, 0, st>>>(m2, l, zd, pl.splits, Bq, lse, rowloss);
+    fwd_combine_kernel<<<(unsigned)ceil_div(Bq, 256), 256, 0, st>>>(m2, l, zd, pl.splits * 2 /* kHalves for BN=128 */, Bq, lse, rowloss);
     TT_LAUNCH_OK("fwd_combine_kernel");
     return sum_rows_launch(rowloss, Bq, loss, st);
 }
@@ -194,7 +213,10 @@ int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const 
     float* part = ws;
     float* Tt = ws + align_up((size_t)pl.splits * nR * E, 64);
     const int ldtt = (int)tt_ld(nT);
+    float* c2 = Tt + align_up((size_t)E * ldtt, 64);
     {
+        int rc0 = launch_scale_pad(colv, nT, c2, pl.n_tiles * bn, st);
+        if (rc0) return rc0;
         dim3 grid((unsigned)ceil_div(nT, 32), (unsigned)ceil_div(E, 32));
         transpose_kernel<<<grid, 256, 0, st>>>(T, ldt, nT, E, Tt, ldtt);
         TT_LAUNCH_OK("transpose_kernel");
@@ -207,8 +229,8 @@ int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const 
     rc = make_tmap_2d(&tmTt, Tt, E, nT, ldtt, E);
     if (rc) return rc;
     RowPanelParams p{};
-    p.nR = nR; p.nT = nT; p.n_tiles = pl.n_tiles; p.tiles_per_split = pl.tps; p.rowv = rowv; p.colv = colv; p.d = d;
-    p.out0 = part; p.out1 = nullptr; p.out2 = nullptr; p.ld_out = 0;
+    p.nR = nR; p.nT = nT; p.n_tiles = pl.n_tiles; p.tiles_per_split = pl.tps; p.rowv = rowv; p.colv2 = c2; p.d = d;
+    p.out0 = part; p.out1 = nullptr; p.out2 = nullptr; p.ld_out = 0; p.trace = g_trace;
     switch (E) {
         case 32: rc = launch_rowpanel<kBwd, 32, 64>(tmR, tmT, tmTt, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<bwd,32>"); break;
         case 64: rc = launch_rowpanel<kBwd, 64, 64>(tmR, tmT, tmTt, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<bwd,64>"); break;
@@ -228,8 +250,20 @@ int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bia
     if (rc) return rc;
     rc = make_tmap_2d(&tmC, C, Bc, E, ldc, kFwdBN);
     if (rc) return rc;
+    // test / API-convenience path: the scaled column term lives in a lazily grown static buffer
+    static float* c2 = nullptr;
+    static size_t c2_cap = 0;
+    size_t need = (size_t)pl.n_tiles * kFwdBN;
+    if (need > c2_cap) {
+        if (c2) cudaFree(c2);
+        TT_CUDA_OK(cudaMalloc(&c2, need * sizeof(float)));
+        c2_cap = need;
+    }
+    rc = launch_scale_pad(bias, Bc, c2, (int)need, st);
+    if (rc) return rc;
     RowPanelParams p{};
-    p.nR = Bq; p.nT = Bc; p.n_tiles = pl.n_tiles; p.tiles_per_split = pl.tps; p.colv = bias; p.out0 = Z; p.ld_out = ldz;
+    p.nR = Bq; p.nT = Bc; p.n_tiles = pl.n_tiles; p.tiles_per_split = pl.tps; p.colv2 = c2; p.out0 = Z; p.ld_out = ldz;
+    p.d = -(1 << 30);
     switch (E) {
         case 32: return launch_rowpanel<kLogits, 32, kFwdBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<logits,32>");
         case 64: return launch_rowpanel<kLogits, 64, kFwdBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<logits,64>");
@@ -238,5 +272,10 @@ int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bia
 }
 
 size_t softmax_tc_workspace_bytes(int Bq, int Bc, int E) { return tc::softmax_tc_workspace(Bq, Bc, E); }
+
+void debug_tc(void* trace, int max_splits) {
+    tc::g_trace = reinterpret_cast<unsigned long long*>(trace);
+    tc::g_max_splits = (max_splits >= 1 && max_splits <= tc::kMaxSplits) ? max_splits : tc::kMaxSplits;
+}
 
 }  // namespace tt

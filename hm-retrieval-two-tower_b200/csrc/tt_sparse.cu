@@ -29,6 +29,8 @@ struct SortPlan {  // per-job workspace pointers
     uint32_t* keys[2];
     int32_t* vals[2];
     uint32_t* hist;  // [kRadix][ntiles]
+    float* partL;    // [nblocks][e] piece sums of runs continuing from an earlier block
+    float* partR;    // [nblocks][e] piece sums of runs that begin in the block and continue
     int32_t n;       // elements
     int32_t ntiles;
     int32_t npass;
@@ -171,55 +173,97 @@ __device__ __forceinline__ const float* grad_row(const tt_sparse_job& job, int p
 
 enum { kModeAdagrad = 0, kModeAdamMoments = 1 };
 
-template <int kMode>
-__global__ void __launch_bounds__(256) sparse_apply_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans, float lr,
-                                                           float eps, float omb1, float omb2) {
+// The stably sorted (id, position) array is cut into blocks of 32 entries; one warp owns one block.
+// A run of equal ids is summed piecewise: each block sums its piece in ascending position order
+// (sequential fp32 adds), and pieces are added in block order.  Runs that stay inside one block (the
+// common case) are applied immediately; a run crossing block boundaries leaves per-block partial sums
+// (partL: the piece that continues a run begun in an earlier block; partR: the piece of a run that begins
+// here and continues) which phase B adds up from the run's head block.  The order depends only on the
+// sorted array, so the result is deterministic and equals oracle/two_tower_oracle.py:dedup_indexed_slices.
+__device__ __forceinline__ void apply_row(const tt_sparse_job& job, int kMode, uint32_t id, int c, float g, float lr, float eps, float omb1,
+                                          float omb2) {
+    const int64_t o = (int64_t)id * job.e + c;
+    if (kMode == kModeAdagrad) {
+        float a = __fadd_rn(job.slot0[o], __fmul_rn(g, g));
+        job.slot0[o] = a;
+        job.table[o] = __fsub_rn(job.table[o], __fdiv_rn(__fmul_rn(g, lr), __fadd_rn(__fsqrt_rn(a), eps)));
+    } else {  // Adam: scatter-add into the already decayed moments
+        job.slot0[o] = __fadd_rn(job.slot0[o], __fmul_rn(g, omb1));
+        job.slot1[o] = __fadd_rn(job.slot1[o], __fmul_rn(__fmul_rn(g, g), omb2));
+    }
+}
+
+// phase A: grid (ceil(max_blocks / 8), njobs), 8 warps per CTA, one warp per block of 32 sorted entries
+__global__ void __launch_bounds__(256) sparse_block_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans, int kMode,
+                                                           float lr, float eps, float omb1, float omb2) {
     const SortPlan& pl = plans.p[blockIdx.y];
     const tt_sparse_job& job = jobs.j[blockIdx.y];
     const uint32_t* ks = pl.keys[pl.npass & 1];
     const int32_t* vs = pl.vals[pl.npass & 1];
     const int lane = threadIdx.x & 31;
-    const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nblk = (pl.n + 31) >> 5;
+    if (b >= nblk) return;
+    const int base = b << 5;
+    const int cnt = min(32, pl.n - base);
+    const uint32_t key = lane < cnt ? ks[base + lane] : 0xffffffffu;
+    const int pos = lane < cnt ? vs[base + lane] : 0;
+    const uint32_t kprev_lane = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool cont_in = base > 0 && ks[base - 1] == __shfl_sync(0xffffffffu, key, 0);           // first run began earlier
+    const uint32_t last_key = __shfl_sync(0xffffffffu, key, cnt - 1);
+    const bool cont_out = base + 32 < pl.n && cnt == 32 && ks[base + 32] == last_key;            // last run goes on
+    const bool head = lane < cnt && (lane == 0 || key != kprev_lane);
+    uint32_t heads = __ballot_sync(0xffffffffu, head);
     const int e = job.e;
-    for (int i = warp0; i < pl.n; i += nwarps) {
-        const uint32_t id = ks[i];
-        if (i > 0 && ks[i - 1] == id) continue;  // not the head of its run
-        // run length: 32 keys at a time
-        int len = 1;
-        for (;;) {
-            int j = i + len + lane;
-            bool same = j < pl.n && ks[j] == id;
-            uint32_t m = __ballot_sync(0xffffffffu, same);
-            if (m == 0xffffffffu) { len += 32; continue; }
-            len += __ffs(~m) - 1;
-            break;
-        }
+    float* partL = pl.partL + (int64_t)b * e;
+    float* partR = pl.partR + (int64_t)b * e;
+    while (heads) {
+        const int s = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const int en = heads ? (__ffs(heads) - 1) : cnt;
+        const uint32_t id = __shfl_sync(0xffffffffu, key, s);
+        const bool is_first = (s == 0), is_last = (en == cnt);
         for (int c = lane; c < e; c += 32) {
-            // ascending-position sequential sum (sort is stable), loads batched 4 deep for latency
             float g = 0.f;
-            int j = 0;
-            for (; j + 4 <= len; j += 4) {
-                float g0 = __ldg(grad_row(job, vs[i + j]) + c);
-                float g1 = __ldg(grad_row(job, vs[i + j + 1]) + c);
-                float g2 = __ldg(grad_row(job, vs[i + j + 2]) + c);
-                float g3 = __ldg(grad_row(job, vs[i + j + 3]) + c);
-                g = __fadd_rn(g, g0);
-                g = __fadd_rn(g, g1);
-                g = __fadd_rn(g, g2);
-                g = __fadd_rn(g, g3);
+            int j = s;
+            for (; j + 4 <= en; j += 4) {
+                const float g0 = __ldg(grad_row(job, __shfl_sync(0xffffffffu, pos, j)) + c);
+                const float g1 = __ldg(grad_row(job, __shfl_sync(0xffffffffu, pos, j + 1)) + c);
+                const float g2 = __ldg(grad_row(job, __shfl_sync(0xffffffffu, pos, j + 2)) + c);
+                const float g3 = __ldg(grad_row(job, __shfl_sync(0xffffffffu, pos, j + 3)) + c);
+                g = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(g, g0), g1), g2), g3);
             }
-            for (; j < len; ++j) g = __fadd_rn(g, __ldg(grad_row(job, vs[i + j]) + c));
-            const int64_t o = (int64_t)id * e + c;
-            if (kMode == kModeAdagrad) {
-                float a = __fadd_rn(job.slot0[o], __fmul_rn(g, g));
-                job.slot0[o] = a;
-                job.table[o] = __fsub_rn(job.table[o], __fdiv_rn(__fmul_rn(g, lr), __fadd_rn(__fsqrt_rn(a), eps)));
-            } else {  // Adam: scatter-add into the already decayed moments
-                job.slot0[o] = __fadd_rn(job.slot0[o], __fmul_rn(g, omb1));
-                job.slot1[o] = __fadd_rn(job.slot1[o], __fmul_rn(__fmul_rn(g, g), omb2));
-            }
+            for (; j < en; ++j) g = __fadd_rn(g, __ldg(grad_row(job, __shfl_sync(0xffffffffu, pos, j)) + c));
+            if (is_first && cont_in) partL[c] = g;                         // continuation piece (may also continue further)
+            else if (is_last && cont_out) partR[c] = g;                    // run begins here and continues
+            else apply_row(job, kMode, id, c, g, lr, eps, omb1, omb2);      // run lives entirely in this block
         }
+    }
+}
+
+// phase B: the head block of every boundary-crossing run adds the pieces in block order and applies the update
+__global__ void __launch_bounds__(256) sparse_combine_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans, int kMode,
+                                                             float lr, float eps, float omb1, float omb2) {
+    const SortPlan& pl = plans.p[blockIdx.y];
+    const tt_sparse_job& job = jobs.j[blockIdx.y];
+    const uint32_t* ks = pl.keys[pl.npass & 1];
+    const int lane = threadIdx.x & 31;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nblk = (pl.n + 31) >> 5;
+    if (b >= nblk) return;
+    const int base = b << 5;
+    if (base + 32 >= pl.n) return;                       // last block: nothing can continue
+    const uint32_t id = ks[base + 31];
+    if (ks[base + 32] != id) return;                     // last run does not continue
+    if (ks[base] == id && base > 0 && ks[base - 1] == id) return;   // whole block is a middle piece: the head block owns it
+    // this block holds the head of the run (either mid-block, or at lane 0 with a different predecessor)
+    const int e = job.e;
+    int last = b + 1;                                    // last block touched by the run
+    while ((last + 1) * 32 < pl.n && ks[(last + 1) * 32] == id) ++last;
+    for (int c = lane; c < e; c += 32) {
+        float g = pl.partR[(int64_t)b * e + c];
+        for (int nb = b + 1; nb <= last; ++nb) g = __fadd_rn(g, pl.partL[(int64_t)nb * e + c]);
+        apply_row(job, kMode, id, c, g, lr, eps, omb1, omb2);
     }
 }
 
@@ -240,10 +284,14 @@ __global__ void __launch_bounds__(256) adam_sweep_kernel(const __grid_constant__
 }
 
 // ---- host ---------------------------------------------------------------------------------------------
-static size_t per_job_bytes(int max_n) {
+static size_t part_bytes(int max_n, int max_e) {
+    size_t n = (size_t)(max_n > 0 ? max_n : 1);
+    return align_up(((n + 31) / 32) * (size_t)(max_e > 0 ? max_e : 1) * sizeof(float), 256);
+}
+static size_t per_job_bytes(int max_n, int max_e) {
     size_t n = (size_t)(max_n > 0 ? max_n : 1);
     size_t ntiles = (n + kTile - 1) / kTile;
-    return 4 * align_up(n * 4, 256) + align_up(ntiles * kRadix * 4, 256);
+    return 4 * align_up(n * 4, 256) + align_up(ntiles * kRadix * 4, 256) + 2 * part_bytes(max_n, max_e);
 }
 
 static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, JobArr* ja, PlanArr* pa, int* max_tiles,
@@ -252,9 +300,10 @@ static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_
     memset(ja, 0, sizeof(*ja));
     memset(pa, 0, sizeof(*pa));
     ja->n = pa->n = njobs;
-    int max_n = 0;
+    int max_n = 0, max_e = 0;
     for (int j = 0; j < njobs; ++j) {
         const tt_sparse_job& jb = jobs[j];
+        if (jb.e > max_e) max_e = jb.e;
         TT_REQUIRE(jb.table && jb.slot0 && jb.rows >= 1 && jb.e >= 1, "%s: job %d malformed", who, j);
         TT_REQUIRE(jb.nsrc >= 1 && jb.nsrc <= TT_MAX_SRC && jb.n_per_src >= 0, "%s: job %d nsrc/n_per_src out of range", who, j);
         TT_REQUIRE((int64_t)jb.nsrc * jb.n_per_src < (1ll << 31), "%s: job %d too many rows", who, j);
@@ -263,7 +312,7 @@ static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_
         int n = jb.nsrc * jb.n_per_src;
         if (n > max_n) max_n = n;
     }
-    size_t per = per_job_bytes(max_n);
+    size_t per = per_job_bytes(max_n, max_e);
     TT_REQUIRE(ws != nullptr && ws_bytes >= per * (size_t)njobs, "%s: workspace too small (%zu < %zu)", who, ws_bytes, per * (size_t)njobs);
     *max_tiles = 0;
     *max_pass = 0;
@@ -276,6 +325,9 @@ static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_
         p.vals[0] = reinterpret_cast<int32_t*>(base + 2 * seg);
         p.vals[1] = reinterpret_cast<int32_t*>(base + 3 * seg);
         p.hist = reinterpret_cast<uint32_t*>(base + 4 * seg);
+        size_t hist_bytes = align_up((size_t)ceil_div(max_n > 0 ? max_n : 1, kTile) * kRadix * 4, 256);
+        p.partL = reinterpret_cast<float*>(base + 4 * seg + hist_bytes);
+        p.partR = reinterpret_cast<float*>(base + 4 * seg + hist_bytes + part_bytes(max_n, max_e));
         p.n = jobs[j].nsrc * jobs[j].n_per_src;
         p.ntiles = (int)ceil_div(p.n, kTile);
         p.npass = passes_for_rows(jobs[j].rows);
@@ -285,13 +337,20 @@ static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_
     return TT_OK;
 }
 
-static int apply_grid(const PlanArr& pa) {
+static int apply_grid(const PlanArr& pa) {   // one warp per block of 32 sorted entries, 8 warps per CTA
     int max_n = 0;
     for (int j = 0; j < pa.n; ++j) max_n = pa.p[j].n > max_n ? pa.p[j].n : max_n;
-    int64_t g = ceil_div((int64_t)max_n, 256 / 32);
-    int64_t cap = (int64_t)sm_count() * 16;
-    if (g > cap) g = cap;
+    int64_t g = ceil_div(ceil_div((int64_t)max_n, 32), 8);
     return (int)(g < 1 ? 1 : g);
+}
+
+static int launch_apply(const JobArr& ja, const PlanArr& pa, int njobs, int mode, float lr, float eps, float omb1, float omb2, cudaStream_t st) {
+    dim3 grid((unsigned)apply_grid(pa), (unsigned)njobs);
+    sparse_block_kernel<<<grid, 256, 0, st>>>(ja, pa, mode, lr, eps, omb1, omb2);
+    TT_LAUNCH_OK("sparse_block_kernel");
+    sparse_combine_kernel<<<grid, 256, 0, st>>>(ja, pa, mode, lr, eps, omb1, omb2);
+    TT_LAUNCH_OK("sparse_combine_kernel");
+    return TT_OK;
 }
 
 }  // namespace tt
@@ -300,9 +359,9 @@ using namespace tt;
 
 extern "C" {
 
-size_t tt_sparse_workspace_bytes(int njobs, int max_n) {
+size_t tt_sparse_workspace_bytes(int njobs, int max_n, int max_e) {
     if (njobs < 1) njobs = 1;
-    return per_job_bytes(max_n) * (size_t)njobs + 256;
+    return per_job_bytes(max_n, max_e) * (size_t)njobs + 256;
 }
 
 int tt_sparse_sort(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, void* stream) {
@@ -332,10 +391,7 @@ int tt_sparse_adagrad(const tt_sparse_job* jobs, int njobs, float lr, float eps,
     int rc = make_plans(jobs, njobs, ws, ws_bytes, &ja, &pa, &max_tiles, &max_pass, "tt_sparse_adagrad");
     if (rc) return rc;
     if (max_tiles == 0) return TT_OK;
-    dim3 grid((unsigned)apply_grid(pa), (unsigned)njobs);
-    sparse_apply_kernel<kModeAdagrad><<<grid, 256, 0, as_stream(stream)>>>(ja, pa, lr, eps, 0.f, 0.f);
-    TT_LAUNCH_OK("sparse_apply_kernel<adagrad>");
-    return TT_OK;
+    return launch_apply(ja, pa, njobs, kModeAdagrad, lr, eps, 0.f, 0.f, as_stream(stream));
 }
 
 int tt_sparse_adam(const tt_sparse_job* jobs, int njobs, float lr_t, float beta1, float beta2, float eps, void* ws, size_t ws_bytes,
@@ -360,9 +416,8 @@ int tt_sparse_adam(const tt_sparse_job* jobs, int njobs, float lr_t, float beta1
     adam_sweep_kernel<<<sweep, 256, 0, st>>>(ja, 0, beta1, beta2, lr_t, eps);
     TT_LAUNCH_OK("adam_sweep_kernel<decay>");
     if (max_tiles > 0) {
-        dim3 grid((unsigned)apply_grid(pa), (unsigned)njobs);
-        sparse_apply_kernel<kModeAdamMoments><<<grid, 256, 0, st>>>(ja, pa, 0.f, eps, 1.0f - beta1, 1.0f - beta2);
-        TT_LAUNCH_OK("sparse_apply_kernel<adam>");
+        rc = launch_apply(ja, pa, njobs, kModeAdamMoments, 0.f, eps, 1.0f - beta1, 1.0f - beta2, st);
+        if (rc) return rc;
     }
     adam_sweep_kernel<<<sweep, 256, 0, st>>>(ja, 1, beta1, beta2, lr_t, eps);
     TT_LAUNCH_OK("adam_sweep_kernel<update>");

@@ -6,7 +6,8 @@
 // through a TMA/mbarrier ring.  S is double-buffered in TMEM so the tensor core works on tile j+1 while
 // the epilogue warps consume tile j; S never goes to HBM.  Warp roles (192 threads):
 //   warp 0: TMA producer (one elected lane)      warp 1: MMA issuer (one elected lane), TMEM owner
-//   warps 2-5: epilogue, one TMEM lane (= one R row) per thread
+//   warps 2-9: epilogue; thread = one TMEM lane (= one R row); the two warps that share a lane quarter split
+//              the columns of every tile between them (two warps per scheduler hide each other's latencies)
 // Modes (compile-time):
 //   kFwd    online log-sum-exp per row (+ diagonal logit)                -> partial (m2, l, zdiag) per split
 //   kBwd    P = exp(S - rowv - colv) - [col == row + d], written TF32 to swizzled smem as the A operand of a
@@ -15,6 +16,10 @@
 //           MMA is a K-major tile of T^T (E x BN) loaded by TMA from a transposed copy of T.
 //   kLogits Z = S - colv written out (tests / TwoTowerModel.call)
 //   kIndex  max over each group of 32 consecutive columns                 -> group maxima (filter stage)
+//
+// The per-column term arrives pre-scaled (colv2 = colv * log2 e, zero padded to whole tiles) and is staged
+// into shared memory by a 1-D bulk copy on the tile's barrier; the epilogue works in the log2 domain with
+// ex2.approx, and takes a check-free fast path for tiles that are fully in range and off the diagonal.
 #pragma once
 #include <math_constants.h>
 
@@ -29,46 +34,165 @@ struct RowPanelParams {
     int nR, nT;
     int n_tiles;          // ceil(nT / BN)
     int tiles_per_split;  // tiles handled by one blockIdx.y
-    const float* rowv;    // kBwd: per-R-row term (lse or ln p)
-    const float* colv;    // per-T-row term (ln p or lse); may be null
+    const float* rowv;    // kBwd: per-R-row term (lse or ln p), natural units
+    const float* colv2;   // per-T-row term * log2(e), padded with zeros to n_tiles*BN entries (never null)
     int d;                // diagonal: column == row + d
     float* out0;          // kFwd: m2 [split][nR] | kBwd: G partial [split][nR][E] | kLogits: Z | kIndex: gmax [nR][ld_out]
     float* out1;          // kFwd: l  [split][nR]
-    float* out2;          // kFwd: zdiag [nR] (written by the split that owns the diagonal column)
+    float* out2;          // kFwd: zdiag [nR] (natural units; written by the split that owns the diagonal column)
     int ld_out;           // kLogits: ldz | kIndex: row stride of gmax (groups)
+    unsigned long long* trace;  // optional debug timeline: [cta][16] globaltimer stamps (ns); null in production
 };
 
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TT_TRACE(slot)                                                                                        \
+    do {                                                                                                      \
+        if (p.trace) p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime();          \
+    } while (0)
+
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ void bulk_copy_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// explicit shared-space accesses (a generic pointer would compile to slower generic LD/ST)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// round-to-nearest (ties away from zero) to TF32 on the integer pipe: same result as cvt.rna.tf32.f32 for finite
+// inputs, without occupying the transcendental/conversion unit the exponentials need
+__device__ __forceinline__ float tf32_rn_int(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+// issue only (no wait): 32 lanes x 32 columns
+__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int MODE, int E, int BN>
 struct RowPanelCfg {
     static constexpr int kSlabs = E / 32;                       // 128-byte K slabs per operand row
-    static constexpr int kStages = (MODE == kBwd) ? 3 : 2;      // T ring depth
     static constexpr int kRBytes = kSlabs * 128 * 128;
+    static constexpr int kFit = (232448 - 6 * 1024 - kRBytes) / (kSlabs * BN * 128);   // T tiles that fit beside the R panel
+    static constexpr int kStages = (MODE == kBwd) ? 3 : (kFit >= 4 ? 4 : (kFit >= 3 ? 3 : 2));   // T ring depth
     static constexpr int kT1Bytes = kSlabs * BN * 128;                       // T tile, K-major over E  (first MMA)
     static constexpr int kT2Bytes = (MODE == kBwd) ? (BN / 32) * E * 128 : 0;  // T^T tile, K-major over BN (second MMA)
     static constexpr int kTBytes = kT1Bytes + kT2Bytes;
     static constexpr int kPSlabs = BN / 32;
     static constexpr int kPBytes = (MODE == kBwd) ? kPSlabs * 128 * 128 : 0;
     static constexpr int kPBufs = (MODE == kBwd) ? 2 : 0;
+    static constexpr int kC2Bytes = BN * 4;                                  // staged column term per stage
+    static constexpr int kHalves = (BN / 32 >= 2) ? 2 : 1;                   // epilogue warps per TMEM lane quarter
+    static constexpr int kEpiWarps = 4 * kHalves;
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;
     static constexpr int kTmemCols = (MODE == kBwd) ? (2 * BN + E <= 256 ? 256 : 512) : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
-    static constexpr int kSmemBytes = kRBytes + kStages * kTBytes + kPBufs * kPBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+    static constexpr int kSmemBytes = kRBytes + kStages * kTBytes + kPBufs * kPBytes + 4 * 1024 /*c2 stages*/ + 1024 /*barriers*/ + 1024 /*align*/;
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
     static_assert(E == 32 || E == 64 || E == 128, "E must be 32, 64 or 128");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 up to 256");
     static_assert(MODE != kBwd || 2 * BN + E <= 512, "TMEM budget");
+    static_assert(kC2Bytes <= 1024, "c2 stage");
 };
 
 struct RowPanelBars {
     uint64_t r_full;
-    uint64_t t_full[3], t_empty[3];
+    uint64_t t_full[4], t_empty[4];
     uint64_t s_full[2], s_empty[2];
     uint64_t p_full[2], p_empty[2];
     uint64_t g_full;
     uint32_t tmem_base;
 };
 
+// ---- per-chunk epilogue bodies (32 columns of one row), check-free when FAST ---------------------------
+template <bool FAST>
+__device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], uint32_t c2s, int nb, int row, int nT, int d, float& m2, float& l, float& zd,
+                                          bool& has_diag) {
+    float z[32];
+    float cm0 = -CUDART_INF_F, cm1 = -CUDART_INF_F;
+#pragma unroll
+    for (int g4 = 0; g4 < 8; ++g4) {
+        const float4 cc = lds128(c2s + g4 * 16);
+        const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int i = g4 * 4 + t;
+            float zz = fmaf(__uint_as_float(r[i]), kLog2e, -cv[t]);
+            if (!FAST) {
+                const int n = nb + i;
+                if (n >= nT) zz = -CUDART_INF_F;
+                else if (n == row + d) { zd = zz * kLn2; has_diag = true; }
+            }
+            z[i] = zz;
+            if (t & 1) cm1 = fmaxf(cm1, zz); else cm0 = fmaxf(cm0, zz);
+        }
+    }
+    const float cmax = fmaxf(cm0, cm1);
+    if (FAST || cmax > -CUDART_INF_F) {
+        const float mn = fmaxf(m2, cmax);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            s0 += ex2_approx(z[i] - mn); s1 += ex2_approx(z[i + 1] - mn);
+            s2 += ex2_approx(z[i + 2] - mn); s3 += ex2_approx(z[i + 3] - mn);
+        }
+        l = l * ex2_approx(m2 - mn) + ((s0 + s1) + (s2 + s3));
+        m2 = mn;
+    }
+}
+
+template <bool FAST>
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t c2s, int nb, int row, int row_l, int nT, int nR, int d, float r2,
+                                          uint32_t prow) {
+#pragma unroll
+    for (int g4 = 0; g4 < 8; ++g4) {
+        const float4 cc = lds128(c2s + g4 * 16);
+        const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
+        float o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int i = g4 * 4 + t;
+            float pv = ex2_approx(fmaf(__uint_as_float(r[i]), kLog2e, -r2) - cv[t]);
+            if (!FAST) {
+                const int n = nb + i;
+                if (n >= nT || row >= nR) pv = 0.f;
+                else if (n == row + d) pv -= 1.0f;
+            }
+            o[t] = tf32_rn_int(pv);
+        }
+        sts128(prow + ((g4 ^ (row_l & 7)) << 4), o[0], o[1], o[2], o[3]);
+    }
+}
+
 template <int MODE, int E, int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(64 + 32 * 4 * ((BN / 32 >= 2) ? 2 : 1), 1)
 rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmTt,
                 const RowPanelParams p) {
     using Cfg = RowPanelCfg<MODE, E, BN>;
@@ -77,22 +201,24 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
     unsigned char* sR = smem;
     unsigned char* sT = sR + Cfg::kRBytes;
     unsigned char* sP = sT + Cfg::kStages * Cfg::kTBytes;
-    RowPanelBars* bars = reinterpret_cast<RowPanelBars*>(sP + Cfg::kPBufs * Cfg::kPBytes);
+    unsigned char* sC2 = sP + Cfg::kPBufs * Cfg::kPBytes;       // kStages x 1 KB
+    RowPanelBars* bars = reinterpret_cast<RowPanelBars*>(sC2 + 4 * 1024);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * 128;
     const int tile_begin = blockIdx.y * p.tiles_per_split;
     const int my_tiles = min(p.tiles_per_split, p.n_tiles - tile_begin);
+    if (threadIdx.x == 0) TT_TRACE(0);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmR);
         prefetch_tmap(&tmT);
         if (MODE == kBwd) prefetch_tmap(&tmTt);
         mbar_init(&bars->r_full, 1);
-        for (int i = 0; i < 3; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], MODE == kBwd ? 1 : 1 + Cfg::kEpiWarps); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 4);
-            mbar_init(&bars->p_full[i], 4); mbar_init(&bars->p_empty[i], 1);
+            mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], Cfg::kEpiWarps);
+            mbar_init(&bars->p_full[i], Cfg::kEpiWarps); mbar_init(&bars->p_empty[i], 1);
         }
         mbar_init(&bars->g_full, 1);
         fence_barrier_init();
@@ -102,6 +228,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
+    if (threadIdx.x == 0) TT_TRACE(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -111,14 +238,15 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
             for (int it = 0; it < my_tiles; ++it) {
                 const int stage = it % Cfg::kStages;
                 const uint32_t ph = (it / Cfg::kStages) & 1;
+                const int n0 = (tile_begin + it) * BN;
                 mbar_wait(&bars->t_empty[stage], ph ^ 1);
-                mbar_arrive_expect_tx(&bars->t_full[stage], Cfg::kTBytes);
+                mbar_arrive_expect_tx(&bars->t_full[stage], Cfg::kTBytes + Cfg::kC2Bytes);
                 unsigned char* dst = sT + stage * Cfg::kTBytes;
-                for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(dst + s * BN * 128, &tmT, &bars->t_full[stage], s * 32, (tile_begin + it) * BN);
-                if constexpr (MODE == kBwd) {
-                    for (int s = 0; s < BN / 32; ++s)
-                        tma_load_2d(dst + Cfg::kT1Bytes + s * E * 128, &tmTt, &bars->t_full[stage], (tile_begin + it) * BN + s * 32, 0);
+                for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(dst + s * BN * 128, &tmT, &bars->t_full[stage], s * 32, n0);
+                if (MODE == kBwd) {
+                    for (int s = 0; s < BN / 32; ++s) tma_load_2d(dst + Cfg::kT1Bytes + s * E * 128, &tmTt, &bars->t_full[stage], n0 + s * 32, 0);
                 }
+                bulk_copy_1d(sC2 + stage * 1024, p.colv2 + n0, Cfg::kC2Bytes, &bars->t_full[stage]);
             }
         }
     } else if (warp == 1) {
@@ -143,12 +271,14 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                     uint64_t bd = make_smem_desc(sT_a + stage * Cfg::kTBytes + offT, 16, 1024);
                     mma_tf32(tmem + acc * BN, ad, bd, idesc1, k > 0 ? 1u : 0u);
                 }
-                if (MODE != kBwd) mma_commit(&bars->t_empty[stage]);  // T tile is free once S is computed
+                // non-bwd: the stage is released by this commit (T tile consumed) AND by the 4 epilogue warps (c2 consumed)
+                if (MODE != kBwd) mma_commit(&bars->t_empty[stage]);
                 mma_commit(&bars->s_full[acc]);
             }
             __syncwarp();
         };
         mbar_wait(&bars->r_full, 0);
+        if (lane == 0) TT_TRACE(2);
         if constexpr (MODE != kBwd) {
             for (int it = 0; it < my_tiles; ++it) issue_g1(it);
         } else {
@@ -167,7 +297,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                         uint64_t bd = make_smem_desc(sT_a + stage * Cfg::kTBytes + Cfg::kT1Bytes + (kk >> 2) * E * 128 + (kk & 3) * 32, 16, 1024);
                         mma_tf32(tmem + 2 * BN, ad, bd, idesc2, (it > 0 || kk > 0) ? 1u : 0u);
                     }
-                    mma_commit(&bars->t_empty[stage]);
+                    mma_commit(&bars->t_empty[stage]);  // T, T^T and c2 of this stage are all consumed by now
                     mma_commit(&bars->p_empty[pb]);
                 }
                 __syncwarp();
@@ -176,89 +306,85 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
             __syncwarp();
         }
     } else {
-        // ===================== epilogue warps (2..5) =====================
+        // ===================== epilogue warps (2..) =====================
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // which share of each tile's columns this warp handles
         const int row_l = q * 32 + lane;              // row within the panel == TMEM lane
         const int row = m0 + row_l;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const int wrow0 = m0 + q * 32;                // first row of this warp
         float m2 = -CUDART_INF_F, l = 0.f, zd = 0.f;
         bool has_diag = false;
-        float rv = 0.f;
-        if (MODE == kBwd) rv = (row < p.nR && p.rowv) ? __ldg(p.rowv + row) : 0.f;
+        float r2 = 0.f;
+        if (MODE == kBwd) r2 = (row < p.nR && p.rowv) ? __ldg(p.rowv + row) * kLog2e : 0.f;
+        constexpr int NC = BN / 32;
+        constexpr int NCW = NC / Cfg::kHalves;        // 32-column chunks per warp per tile
+        const int c_first = half * NCW;
         for (int it = 0; it < my_tiles; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
+            const int stage = it % Cfg::kStages;
             const int n0 = (tile_begin + it) * BN;
+            const int pb = it & 1;
+            // warp-uniform: tile fully in range and no diagonal element of this warp's rows inside it
+            const bool fast = (n0 + BN <= p.nT) && (wrow0 + 32 <= p.nR) && (wrow0 + p.d + 32 <= n0 || wrow0 + p.d >= n0 + BN);
             mbar_wait(&bars->s_full[acc], aph);
             tc_fence_after();
-            const int pb = it & 1;
+            mbar_wait(&bars->t_full[stage], (it / Cfg::kStages) & 1);   // completed long ago; acquires the staged column term
+            if (threadIdx.x == 64 && it < 6) TT_TRACE(3 + 2 * it);
             if (MODE == kBwd) mbar_wait(&bars->p_empty[pb], ((it >> 1) & 1) ^ 1);
-            float gm[BN / 32];
+            const float4* c2v = reinterpret_cast<const float4*>(sC2 + stage * 1024);
+            const uint32_t c2s = smem_u32(sC2 + stage * 1024);
+            uint32_t rbuf[2][32];
+            float gm[NCW];
+            tmem_ld_32x32_issue(tmem + lane_addr + acc * BN + c_first * 32, rbuf[0]);
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-                float v[32];
-                tmem_ld_32x32(tmem + lane_addr + acc * BN + c * 32, v);
+            for (int cl = 0; cl < NCW; ++cl) {
+                const int c = c_first + cl;
+                tmem_ld_wait();
+                if (cl + 1 < NCW) tmem_ld_32x32_issue(tmem + lane_addr + acc * BN + (c + 1) * 32, rbuf[(cl + 1) & 1]);
+                uint32_t(&r)[32] = rbuf[cl & 1];
                 const int nb = n0 + c * 32;
                 if constexpr (MODE == kFwd) {
-                    float cmax = -CUDART_INF_F;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int n = nb + i;
-                        float z = -CUDART_INF_F;
-                        if (n < p.nT) {
-                            z = v[i] - (p.colv ? __ldg(p.colv + n) : 0.f);
-                            if (n == row + p.d) { zd = z; has_diag = true; }
-                            z *= kLog2e;
-                        }
-                        v[i] = z;
-                        cmax = fmaxf(cmax, z);
-                    }
-                    if (cmax > -CUDART_INF_F) {
-                        const float mn = fmaxf(m2, cmax);
-                        float sum = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) sum += exp2f(v[i] - mn);
-                        l = l * exp2f(m2 - mn) + sum;
-                        m2 = mn;
-                    }
+                    if (fast) fwd_chunk<true>(r, c2s + c * 128, nb, row, p.nT, p.d, m2, l, zd, has_diag);
+                    else fwd_chunk<false>(r, c2s + c * 128, nb, row, p.nT, p.d, m2, l, zd, has_diag);
                 } else if constexpr (MODE == kBwd) {
-                    unsigned char* prow = sP + pb * Cfg::kPBytes + c * 128 * 128 + row_l * 128;
-#pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        float o[4];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int i = g4 * 4 + t;
-                            const int n = nb + i;
-                            float pv = 0.f;
-                            if (n < p.nT && row < p.nR) {
-                                const float cv = p.colv ? __ldg(p.colv + n) : 0.f;
-                                pv = exp2f((v[i] - rv - cv) * kLog2e);
-                                if (n == row + p.d) pv -= 1.0f;
-                            }
-                            o[t] = tf32_rn(pv);
-                        }
-                        *reinterpret_cast<float4*>(prow + ((g4 ^ (row_l & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
-                    }
+                    const uint32_t prow = smem_u32(sP + pb * Cfg::kPBytes + c * 128 * 128 + row_l * 128);
+                    if (fast) bwd_chunk<true>(r, c2s + c * 128, nb, row, row_l, p.nT, p.nR, p.d, r2, prow);
+                    else bwd_chunk<false>(r, c2s + c * 128, nb, row, row_l, p.nT, p.nR, p.d, r2, prow);
                 } else if constexpr (MODE == kLogits) {
                     if (row < p.nR) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int n = nb + i;
-                            if (n < p.nT) p.out0[(int64_t)row * p.ld_out + n] = v[i] - (p.colv ? __ldg(p.colv + n) : 0.f);
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            const float4 cc = c2v[c * 8 + g4];
+                            const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const int n = nb + g4 * 4 + t;
+                                if (n < p.nT) p.out0[(int64_t)row * p.ld_out + n] = __uint_as_float(r[g4 * 4 + t]) - cv[t] * kLn2;
+                            }
                         }
                     }
                 } else {  // kIndex
                     float mx = -CUDART_INF_F;
+                    if (fast || nb + 32 <= p.nT) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (nb + i < p.nT) ? v[i] : -CUDART_INF_F);
-                    gm[c] = mx;
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (nb + i < p.nT) ? __uint_as_float(r[i]) : -CUDART_INF_F);
+                    }
+                    gm[cl] = mx;
                 }
             }
             // this S buffer may be overwritten by the MMA of tile it+2
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->s_empty[acc]);
+            if (lane == 0) {
+                mbar_arrive(&bars->s_empty[acc]);
+                if (MODE != kBwd) mbar_arrive(&bars->t_empty[stage]);   // c2 of this stage consumed
+            }
+            if (threadIdx.x == 64 && it < 6) TT_TRACE(4 + 2 * it);
             if constexpr (MODE == kBwd) {
                 fence_proxy_async_smem();   // P stores (generic proxy) -> visible to the tensor core (async proxy)
                 __syncwarp();
@@ -266,16 +392,17 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
             }
             if constexpr (MODE == kIndex) {
                 if (row < p.nR) {
-                    float* dst = p.out0 + (int64_t)row * p.ld_out + (int64_t)(tile_begin + it) * (BN / 32);
+                    float* dst = p.out0 + (int64_t)row * p.ld_out + (int64_t)(tile_begin + it) * NC + c_first;
 #pragma unroll
-                    for (int c = 0; c < BN / 32; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(gm[c], gm[c + 1], gm[c + 2], gm[c + 3]);
+                    for (int c = 0; c < NCW; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(gm[c], gm[c + 1], gm[c + 2], gm[c + 3]);
                 }
             }
         }
         if constexpr (MODE == kFwd) {
             if (row < p.nR) {
-                p.out0[(int64_t)blockIdx.y * p.nR + row] = m2;
-                p.out1[(int64_t)blockIdx.y * p.nR + row] = l;
+                // one partial per (column split, warp half): the combine kernel merges gridDim.y * kHalves of them
+                p.out0[((int64_t)blockIdx.y * Cfg::kHalves + half) * p.nR + row] = m2;
+                p.out1[((int64_t)blockIdx.y * Cfg::kHalves + half) * p.nR + row] = l;
                 if (has_diag) p.out2[row] = zd;
             }
         }
@@ -283,7 +410,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
             mbar_wait(&bars->g_full, 0);
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < E / 32; ++c) {
+            for (int c = half; c < E / 32; c += Cfg::kHalves) {
                 float v[32];
                 tmem_ld_32x32(tmem + lane_addr + 2 * BN + c * 32, v);
                 if (row < p.nR) {
@@ -296,6 +423,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) TT_TRACE(15);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem, Cfg::kTmemCols);
@@ -314,8 +442,8 @@ inline void choose_splits(int m_tiles, int n_tiles, int min_tiles_per_split, int
         if (real != s) continue;
         int64_t ctas = (int64_t)m_tiles * s;
         int64_t waves = (ctas + sms - 1) / sms;
-        // work per CTA is tps tiles; time ~ waves * tps; ideal ~ m_tiles * n_tiles / sms
-        double eff = ((double)m_tiles * n_tiles / sms) / ((double)waves * tps);
+        // per-CTA cost ~ tps tiles + ~2 tiles of fixed prologue; ideal ~ m_tiles * n_tiles / sms
+        double eff = ((double)m_tiles * n_tiles / sms) / ((double)waves * (tps + 2.0));
         if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
     }
     *splits = best;

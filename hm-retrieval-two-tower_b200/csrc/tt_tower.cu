@@ -255,7 +255,7 @@ __global__ void dense_bwd_reduce_kernel(const float* __restrict__ partial, int n
 static int dw_chunks(int B, int K, int N, int* chunk_rows) {
     int64_t tiles = ceil_div(K + 1, BM) * ceil_div(N, BN);
     int64_t want = ceil_div(2 * (int64_t)sm_count(), tiles);
-    int64_t maxc = ceil_div(B, 256);
+    int64_t maxc = ceil_div(B, 128);
     int64_t nchunk = want < maxc ? want : maxc;
     if (nchunk < 1) nchunk = 1;
     int64_t rows = ceil_div(ceil_div(B, nchunk), BK) * BK;

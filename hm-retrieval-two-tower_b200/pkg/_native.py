@@ -39,6 +39,7 @@ SIGNATURES = {
     "tt_device_supports_tc": (c_int, []),
     "tt_launch_count": (c_int64, []),
     "tt_tc_available": (c_int, [c_int, c_int]),
+    "tt_debug_tc": (c_int, [c_void_p, c_int]),
     "tt_gather_concat": (c_int, [ctypes.POINTER(TTFeature), c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "tt_dense_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p]),
@@ -60,7 +61,7 @@ SIGNATURES = {
     "tt_dense_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                               c_void_p]),
     "tt_fill_f32": (c_int, [c_void_p, c_float, c_int64, c_void_p]),
-    "tt_sparse_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "tt_sparse_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "tt_sparse_sort": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_void_p, c_size_t, c_void_p]),
     "tt_sparse_adagrad": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "tt_sparse_adam": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_float, c_float, c_float, c_float, c_void_p, c_size_t,

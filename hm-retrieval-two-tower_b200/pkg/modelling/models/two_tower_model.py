@@ -200,7 +200,8 @@ class TwoTowerModel(AbstractKerasModel):
                 jobs[j].grad_ld[s] = gld
             max_n = max(max_n, n_per * len(lst))
         sw.jobs, sw.njobs = jobs, len(srcs)
-        sw.sp_ws = torch.empty(int(lib.tt_sparse_workspace_bytes(len(srcs), max_n)), dtype=torch.uint8, device="cuda")
+        max_e = max(t.e for t, _ in srcs)
+        sw.sp_ws = torch.empty(int(lib.tt_sparse_workspace_bytes(len(srcs), max_n, max_e)), dtype=torch.uint8, device="cuda")
 
     def _stage(self, sw: _StepWorkspace, data) -> None:
         qf = {f.name: data[f.name] for f in self.query_features}

@@ -49,6 +49,9 @@ int tt_device_supports_tc(void);
 /* 1 when TT_IMPL_AUTO resolves to the tensor-core kernels for the in-batch softmax (kind 0) or the index
  * (kind 1) at joint dimension E on the current device; callers use it to pick the TF32-rounded operands. */
 int tt_tc_available(int kind, int E);
+/* Debug/profiling knobs of the tensor-core kernels: `trace` (device, u64[ctas][16], or NULL) receives
+ * globaltimer stamps of subsequent launches; `max_splits` caps the column splits (0 = default). */
+int tt_debug_tc(void* trace, int max_splits);
 /* Number of kernels this library has launched (or captured into a CUDA graph) in this process so far. */
 int64_t tt_launch_count(void);
 
@@ -137,7 +140,7 @@ typedef struct tt_sparse_job {
     int32_t grad_ld[TT_MAX_SRC];
 } tt_sparse_job;
 
-size_t tt_sparse_workspace_bytes(int njobs, int max_n);
+size_t tt_sparse_workspace_bytes(int njobs, int max_n, int max_e);
 /* Stable LSD radix sort of (id, position) for every job; depends on ids only, so it can run on a
  * side stream concurrently with forward/backward. */
 int tt_sparse_sort(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, void* stream);

@@ -289,14 +289,34 @@ ADAGRAD_INIT_ACC = np.float32(0.1)
 KERAS_EPS = np.float32(1e-7)
 
 
-def dedup_indexed_slices(s: IndexedSlices) -> IndexedSlices:
-    """OptimizerV2._deduplicate_indexed_slices: Unique + UnsortedSegmentSum.  The summation order is
-    fixed here to ascending position in fp32 (sequential adds), which is what the CUDA kernel does;
-    unique ids are returned in ascending id order (order does not affect the update)."""
+DEDUP_BLOCK = 32
+
+
+def dedup_indexed_slices(s: IndexedSlices, block: int = DEDUP_BLOCK) -> IndexedSlices:
+    """OptimizerV2._deduplicate_indexed_slices: Unique + UnsortedSegmentSum.  TensorFlow leaves the
+    summation order of duplicates unspecified; the canonical fp32 order fixed here (and implemented by
+    tt_sparse.cu) is: stable-sort the (id, position) pairs by id; cut the sorted array into blocks of
+    ``block`` entries; within a block, sum a run of equal ids sequentially in ascending position; add the
+    per-block pieces of a run in block order.  Runs shorter than a block that do not straddle a block
+    boundary -- the common case -- are plain sequential sums.  Unique ids come back in ascending order."""
     idx = np.asarray(s.indices, dtype=np.int64)
-    uniq, inv = np.unique(idx, return_inverse=True)
-    out = np.zeros((uniq.shape[0], s.values.shape[1]), dtype=np.float32)
-    np.add.at(out, inv, s.values.astype(np.float32))  # unbuffered, position order, fp32
+    vals = s.values.astype(np.float32)
+    order = np.argsort(idx, kind="stable")
+    sid = idx[order]
+    uniq, starts = np.unique(sid, return_index=True)
+    ends = np.append(starts[1:], sid.shape[0])
+    out = np.zeros((uniq.shape[0], vals.shape[1]), dtype=np.float32)
+    for u, (a, b) in enumerate(zip(starts, ends)):
+        total = None
+        lo = a
+        while lo < b:
+            hi = min(b, (lo // block + 1) * block)
+            piece = np.zeros(vals.shape[1], dtype=np.float32)
+            for j in range(lo, hi):                      # sequential fp32 adds, ascending position
+                piece = piece + vals[order[j]]
+            total = piece if total is None else total + piece
+            lo = hi
+        out[u] = total
     return IndexedSlices(uniq, out)
 
 

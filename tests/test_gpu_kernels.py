@@ -261,7 +261,7 @@ def test_sparse_adagrad_bit_exact_and_deterministic(lib, T, B):
     rng = np.random.default_rng(7)
     specs = [(1_000_003, 32, 1), (105_543, 64, 1), (132, 16, 2), (51, 8, 1), (70_000, 3, 1)]
     jobs, keep, host = _sparse_jobs(N, T, specs, B, rng)
-    ws = T.empty(int(lib.tt_sparse_workspace_bytes(len(specs), 2 * B)), dtype=T.uint8, device="cuda")
+    ws = T.empty(int(lib.tt_sparse_workspace_bytes(len(specs), 2 * B, max(s[1] for s in specs))), dtype=T.uint8, device="cuda")
     N.check(lib.tt_sparse_sort(jobs, len(specs), ws.data_ptr(), ws.numel(), stream()))
     N.check(lib.tt_sparse_adagrad(jobs, len(specs), 0.05, 1e-7, ws.data_ptr(), ws.numel(), stream()))
     T.cuda.synchronize()
@@ -278,7 +278,7 @@ def test_sparse_adam_matches_oracle(lib, T):
     specs = [(5000, 16, 1), (300, 8, 2)]
     B = 700
     jobs, keep, host = _sparse_jobs(N, T, specs, B, rng, adam=True)
-    ws = T.empty(int(lib.tt_sparse_workspace_bytes(len(specs), 2 * B)), dtype=T.uint8, device="cuda")
+    ws = T.empty(int(lib.tt_sparse_workspace_bytes(len(specs), 2 * B, max(s[1] for s in specs))), dtype=T.uint8, device="cuda")
     lr_t = float(O.adam_lr_t(0.001, 3))
     N.check(lib.tt_sparse_sort(jobs, len(specs), ws.data_ptr(), ws.numel(), stream()))
     N.check(lib.tt_sparse_adam(jobs, len(specs), lr_t, 0.9, 0.999, 1e-7, ws.data_ptr(), ws.numel(), stream()))

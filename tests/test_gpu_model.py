@@ -245,6 +245,7 @@ def test_adam_train_step_matches_oracle(lib):
     set_seed(7)
     qf, cf = _c2_features(400, 120)
     m = TwoTowerModel(qf, cf, "article_id", 32)
+    m.impl = 1   # exact fp32 contraction: Adam's first step is ~lr*sign(g), so TF32 noise would flip signs where g ~ 0
     m.compile(optimizer=OptimizerFactory.get_optimizer("adam", {"learning_rate": 0.01}))
     qt, ct = _oracle_twin(m)
     rng = np.random.default_rng(3)
