@@ -172,6 +172,7 @@ __device__ __forceinline__ const float* grad_row(const tt_sparse_job& job, int p
 }
 
 enum { kModeAdagrad = 0, kModeAdamMoments = 1 };
+constexpr int kMaxColsPerLane = 8;   // embedding widths up to 256
 
 // The stably sorted (id, position) array is cut into blocks of 32 entries; one warp owns one block.
 // A run of equal ids is summed piecewise: each block sums its piece in ascending position order
@@ -217,26 +218,48 @@ __global__ void __launch_bounds__(256) sparse_block_kernel(const __grid_constant
     const int e = job.e;
     float* partL = pl.partL + (int64_t)b * e;
     float* partR = pl.partR + (int64_t)b * e;
+    const int nc = (e + 31) >> 5;                        // columns per lane (e <= 32 * kMaxColsPerLane)
     while (heads) {
         const int s = __ffs(heads) - 1;
         heads &= heads - 1;
         const int en = heads ? (__ffs(heads) - 1) : cnt;
         const uint32_t id = __shfl_sync(0xffffffffu, key, s);
         const bool is_first = (s == 0), is_last = (en == cnt);
-        for (int c = lane; c < e; c += 32) {
-            float g = 0.f;
-            int j = s;
-            for (; j + 4 <= en; j += 4) {
-                const float g0 = __ldg(grad_row(job, __shfl_sync(0xffffffffu, pos, j)) + c);
-                const float g1 = __ldg(grad_row(job, __shfl_sync(0xffffffffu, pos, j + 1)) + c);
-                const float g2 = __ldg(grad_row(job, __shfl_sync(0xffffffffu, pos, j + 2)) + c);
-                const float g3 = __ldg(grad_row(job, __shfl_sync(0xffffffffu, pos, j + 3)) + c);
-                g = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(g, g0), g1), g2), g3);
+        float g[kMaxColsPerLane];
+#pragma unroll
+        for (int ci = 0; ci < kMaxColsPerLane; ++ci) g[ci] = 0.f;
+        // every lane takes part in the position broadcasts; the column loops are predicated per lane
+        int j = s;
+        for (; j + 4 <= en; j += 4) {
+            const float* r0 = grad_row(job, __shfl_sync(0xffffffffu, pos, j));
+            const float* r1 = grad_row(job, __shfl_sync(0xffffffffu, pos, j + 1));
+            const float* r2 = grad_row(job, __shfl_sync(0xffffffffu, pos, j + 2));
+            const float* r3 = grad_row(job, __shfl_sync(0xffffffffu, pos, j + 3));
+#pragma unroll
+            for (int ci = 0; ci < kMaxColsPerLane; ++ci) {
+                const int c = lane + 32 * ci;
+                if (ci < nc && c < e) {
+                    const float g0 = __ldg(r0 + c), g1 = __ldg(r1 + c), g2 = __ldg(r2 + c), g3 = __ldg(r3 + c);
+                    g[ci] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(g[ci], g0), g1), g2), g3);
+                }
             }
-            for (; j < en; ++j) g = __fadd_rn(g, __ldg(grad_row(job, __shfl_sync(0xffffffffu, pos, j)) + c));
-            if (is_first && cont_in) partL[c] = g;                         // continuation piece (may also continue further)
-            else if (is_last && cont_out) partR[c] = g;                    // run begins here and continues
-            else apply_row(job, kMode, id, c, g, lr, eps, omb1, omb2);      // run lives entirely in this block
+        }
+        for (; j < en; ++j) {
+            const float* r0 = grad_row(job, __shfl_sync(0xffffffffu, pos, j));
+#pragma unroll
+            for (int ci = 0; ci < kMaxColsPerLane; ++ci) {
+                const int c = lane + 32 * ci;
+                if (ci < nc && c < e) g[ci] = __fadd_rn(g[ci], __ldg(r0 + c));
+            }
+        }
+#pragma unroll
+        for (int ci = 0; ci < kMaxColsPerLane; ++ci) {
+            const int c = lane + 32 * ci;
+            if (ci < nc && c < e) {
+                if (is_first && cont_in) partL[c] = g[ci];                       // continuation piece (may also continue further)
+                else if (is_last && cont_out) partR[c] = g[ci];                  // run begins here and continues
+                else apply_row(job, kMode, id, c, g[ci], lr, eps, omb1, omb2);    // run lives entirely in this block
+            }
         }
     }
 }
@@ -305,6 +328,7 @@ static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_
         const tt_sparse_job& jb = jobs[j];
         if (jb.e > max_e) max_e = jb.e;
         TT_REQUIRE(jb.table && jb.slot0 && jb.rows >= 1 && jb.e >= 1, "%s: job %d malformed", who, j);
+        TT_REQUIRE(jb.e <= 32 * kMaxColsPerLane, "%s: job %d embedding width %d exceeds %d", who, j, jb.e, 32 * kMaxColsPerLane);
         TT_REQUIRE(jb.nsrc >= 1 && jb.nsrc <= TT_MAX_SRC && jb.n_per_src >= 0, "%s: job %d nsrc/n_per_src out of range", who, j);
         TT_REQUIRE((int64_t)jb.nsrc * jb.n_per_src < (1ll << 31), "%s: job %d too many rows", who, j);
         for (int s = 0; s < jb.nsrc; ++s) TT_REQUIRE(jb.n_per_src == 0 || (jb.ids[s] && jb.grad[s] && jb.grad_ld[s] >= jb.e), "%s: job %d source %d malformed", who, j, s);
