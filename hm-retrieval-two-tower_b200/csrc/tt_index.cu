@@ -64,10 +64,15 @@ struct IndexSmem {
 template <int BQ, int CAP>
 __global__ void __launch_bounds__(256) index_exact_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ C, int ldc, int nq,
                                                           int64_t n, int E, int K, int64_t per_split, float* __restrict__ ps,
-                                                          int32_t* __restrict__ pi) {
+                                                          int32_t* __restrict__ pi, const int32_t* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IndexSmem<BQ, CAP>& sm = *reinterpret_cast<IndexSmem<BQ, CAP>*>(smem_raw);
     const int q0 = blockIdx.x * BQ;
+    if (flags) {   // fallback mode: only query tiles holding a flagged query do any work
+        int mine = 0;
+        for (int q = threadIdx.x; q < BQ; q += 256) mine |= (q0 + q < nq) ? flags[q0 + q] : 0;
+        if (!__syncthreads_or(mine)) return;
+    }
     const int64_t c_begin = (int64_t)blockIdx.y * per_split;
     const int64_t c_end = min(n, c_begin + per_split);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -124,7 +129,9 @@ __global__ void __launch_bounds__(256) index_exact_kernel(const float* __restric
 
 // block-wide bitonic sort of P pairs in shared memory, then write the best K (idx padded -> -1)
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ s_in, const int32_t* __restrict__ i_in, int G, int nq, int K,
-                                                         int P, int64_t idx_add, float* __restrict__ s_out, int32_t* __restrict__ i_out) {
+                                                         int P, int64_t idx_add, float* __restrict__ s_out, int32_t* __restrict__ i_out,
+                                                         const int32_t* __restrict__ flags) {
+    if (flags && !flags[blockIdx.x]) return;   // fallback mode: leave the rows the filter path already produced
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s = reinterpret_cast<float*>(smem_raw);
     int32_t* id = reinterpret_cast<int32_t*>(s + P);
@@ -199,7 +206,7 @@ static int plan_exact(int nq, int64_t n, int K, ExactPlan* pl) {
 }
 
 int merge_launch(const float* s_in, const int32_t* i_in, int G, int nq, int K, int64_t idx_add, float* s_out, int32_t* i_out,
-                 cudaStream_t st) {
+                 cudaStream_t st, const int32_t* flags = nullptr) {
     int P = next_pow2(G * K);
     if (P < 2) P = 2;
     if (P > 16384) { set_error("tt_topk_merge: G*K=%d exceeds 16384", G * K); return TT_ERR_UNSUPPORTED; }
@@ -209,7 +216,7 @@ int merge_launch(const float* s_in, const int32_t* i_in, int G, int nq, int K, i
         TT_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
         attr_set = true;
     }
-    topk_merge_kernel<<<(unsigned)nq, 256, smem, st>>>(s_in, i_in, G, nq, K, P, idx_add, s_out, i_out);
+    topk_merge_kernel<<<(unsigned)nq, 256, smem, st>>>(s_in, i_in, G, nq, K, P, idx_add, s_out, i_out, flags);
     TT_LAUNCH_OK("topk_merge_kernel");
     return TT_OK;
 }
@@ -221,7 +228,7 @@ size_t index_exact_workspace(int nq, int64_t n, int K) {
 }
 
 int index_exact(const float* Q, int ldq, const float* C, int ldc, int nq, int64_t n, int E, int K, int64_t idx_base, float* out_s,
-                int32_t* out_i, void* ws, size_t ws_bytes, cudaStream_t st) {
+                int32_t* out_i, void* ws, size_t ws_bytes, cudaStream_t st, const int32_t* flags) {
     ExactPlan pl;
     int rc = plan_exact(nq, n, K, &pl);
     if (rc) return rc;
@@ -233,21 +240,21 @@ int index_exact(const float* Q, int ldq, const float* C, int ldc, int nq, int64_
     if (pl.bq == 64) {
         static bool set64 = false;
         if (!set64) { TT_CUDA_OK(cudaFuncSetAttribute(index_exact_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IndexSmem<64, 256>))); set64 = true; }
-        index_exact_kernel<64, 256><<<grid, 256, pl.smem, st>>>(Q, ldq, C, ldc, nq, n, E, K, pl.per_split, ps, pi);
+        index_exact_kernel<64, 256><<<grid, 256, pl.smem, st>>>(Q, ldq, C, ldc, nq, n, E, K, pl.per_split, ps, pi, flags);
     } else {
         static bool set8 = false;
         if (!set8) { TT_CUDA_OK(cudaFuncSetAttribute(index_exact_kernel<8, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IndexSmem<8, 2048>))); set8 = true; }
-        index_exact_kernel<8, 2048><<<grid, 256, pl.smem, st>>>(Q, ldq, C, ldc, nq, n, E, K, pl.per_split, ps, pi);
+        index_exact_kernel<8, 2048><<<grid, 256, pl.smem, st>>>(Q, ldq, C, ldc, nq, n, E, K, pl.per_split, ps, pi, flags);
     }
     TT_LAUNCH_OK("index_exact_kernel");
-    return merge_launch(ps, pi, pl.nsplit, nq, K, idx_base, out_s, out_i, st);
+    return merge_launch(ps, pi, pl.nsplit, nq, K, idx_base, out_s, out_i, st, flags);
 }
 
 // tt_index_tc.cu
 bool index_tc_supported(int ldq, int ldc, int E, int K, int64_t n, const void* Q, const void* C);
-size_t index_tc_workspace(int nq, int64_t n, int E, int K);
-int index_tc(const float* Q, int ldq, const float* C, int ldc, int nq, int64_t n, int E, int K, int64_t idx_base, float* out_s,
-             int32_t* out_i, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t index_tc_workspace(int nq, int64_t n, int E, int K, bool need_corpus_copy);
+int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32, const float* cmax, int nq, int64_t n, int E, int K,
+             int64_t idx_base, float* out_s, int32_t* out_i, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace tt
 
@@ -255,15 +262,16 @@ using namespace tt;
 
 extern "C" {
 
-size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl) {
+size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl, int have_corpus_tf32) {
     if (nq <= 0 || n <= 0 || K <= 0) return 256;
     size_t a = index_exact_workspace(nq, n, K);
-    size_t b = (impl == TT_IMPL_SIMT) ? 0 : index_tc_workspace(nq, n, E, K);
-    return (a > b ? a : b) + 256;
+    size_t b = (impl == TT_IMPL_SIMT) ? 0 : index_tc_workspace(nq, n, E, K, !have_corpus_tf32);
+    return a + b + 256;   // the filter path keeps the exact path's scratch for its (rare) fallback
 }
 
-int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, int nq, int64_t n, int E, int K, int64_t idx_base,
-                  float* out_scores, int32_t* out_idx, void* ws, size_t ws_bytes, int impl, void* stream) {
+int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const float* corpus_tf32, const float* corpus_max_norm, int nq,
+                  int64_t n, int E, int K, int64_t idx_base, float* out_scores, int32_t* out_idx, void* ws, size_t ws_bytes, int impl,
+                  void* stream) {
     TT_REQUIRE(Q && corpus && out_scores && out_idx, "tt_index_topk: null pointer");
     TT_REQUIRE(nq >= 0 && n >= 1 && E >= 1 && K >= 1 && ldq >= E && ldc >= E, "tt_index_topk: bad shape");
     TT_REQUIRE(idx_base >= 0 && idx_base + n < 2147483647ll - 64, "tt_index_topk: indices must fit int32");
@@ -275,8 +283,8 @@ int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, int nq,
         return TT_ERR_UNSUPPORTED;
     }
     if (impl == TT_IMPL_TC || (impl == TT_IMPL_AUTO && tc_ok))
-        return index_tc(Q, ldq, corpus, ldc, nq, n, E, K, idx_base, out_scores, out_idx, ws, ws_bytes, st);
-    return index_exact(Q, ldq, corpus, ldc, nq, n, E, K, idx_base, out_scores, out_idx, ws, ws_bytes, st);
+        return index_tc(Q, ldq, corpus, ldc, corpus_tf32, corpus_max_norm, nq, n, E, K, idx_base, out_scores, out_idx, ws, ws_bytes, st);
+    return index_exact(Q, ldq, corpus, ldc, nq, n, E, K, idx_base, out_scores, out_idx, ws, ws_bytes, st, nullptr);
 }
 
 int tt_topk_merge(const float* scores, const int32_t* idx, int G, int nq, int K, float* out_scores, int32_t* out_idx, void* stream) {

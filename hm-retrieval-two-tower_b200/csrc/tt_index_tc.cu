@@ -1,7 +1,352 @@
-// placeholder until the tcgen05 kernels land
-#include "tt_common.cuh"
+// tt_index_tc.cu -- brute-force index on the tensor cores with EXACT results.
+//
+// Replaces (reference file:line): brute_force.py:75-78 (scores = Q.C^T) and :81 (top_k, sorted, lower index
+// first on ties).  The (nq x n) score matrix never reaches HBM, and the returned (score, index) pairs are the
+// canonical fp32 values -- bit-identical to the exact path and to oracle/tt_oracle.c -- although the
+// heavy lifting runs in TF32 on tcgen05:
+//
+//   1. rowpanel_kernel<kIndex>   TF32 scores a_ij; only the maximum of every group of 32 consecutive corpus
+//                                rows is kept (n/32 floats per query).
+//   2. select_threshold_kernel   tau = K-th largest group maximum of the query (radix select);
+//                                thr = tau - 2*eps_q with eps_q >= |a_ij - s_ij| for every j.
+//   3. rowpanel_kernel<kCollect> same TF32 contraction; every j with a_ij >= thr is appended to the query's
+//                                candidate list (~K entries).
+//   4. rescore_topk_kernel       exact canonical fp32 score of each candidate, then exact top-K.
+//   5. a query whose list overflowed is redone by the exact CUDA-core kernel (tt_index.cu), on the device.
+//
+// Why it is exact: K groups have a maximum >= tau, so K corpus rows have exact score >= tau - eps; hence
+// the exact K-th best score s_K >= tau - eps, every true top-K row has s >= s_K, i.e. a >= tau - 2 eps = thr,
+// and is therefore collected; step 4 orders the collected rows by the exact (score desc, index asc) rule.
+// eps_q = 2^-9 * ||q||_2 * max_j ||c_j||_2 bounds TF32 operand rounding (2^-11 each, Cauchy-Schwarz) plus the
+// fp32 accumulation error of both evaluations with a 2x margin.
+#include "tt_tc_rowpanel.cuh"
+
 namespace tt {
-bool index_tc_supported(int, int, int, int, int64_t, const void*, const void*) { return false; }
-size_t index_tc_workspace(int, int64_t, int, int) { return 0; }
-int index_tc(const float*, int, const float*, int, int, int64_t, int, int, int64_t, float*, int32_t*, void*, size_t, cudaStream_t) { set_error("tc path not built"); return TT_ERR_UNSUPPORTED; }
+
+// tt_index.cu
+size_t index_exact_workspace(int nq, int64_t n, int K);
+int index_exact(const float* Q, int ldq, const float* C, int ldc, int nq, int64_t n, int E, int K, int64_t idx_base, float* out_s,
+                int32_t* out_i, void* ws, size_t ws_bytes, cudaStream_t st, const int32_t* flags);
+// tt_softmax_tc.cu
+bool softmax_tc_supported(int ldq, int ldc, int E, const void* Q, const void* C);
+
+namespace tc {
+
+constexpr int kGroup = 32;
+static inline int idx_bn(int E) { return E <= 64 ? 256 : 128; }   // shared-memory budget of the T ring
+constexpr float kEpsCoef = 1.0f / 512.0f;   // 2^-9
+static int g_cap_override = 0;              // tests: force tiny candidate lists to exercise the fallback
+
+static inline int cand_cap(int K) { return g_cap_override > 0 ? g_cap_override : 4 * K + 512; }
+static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+__device__ __forceinline__ uint32_t ordered_key(float f) {   // monotone float -> uint
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(b);
+}
+
+// Q32 = tf32_rn(Q); eps[q] = kEpsCoef * ||q|| * cmax.  One warp per query row.
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ Q, int ldq, int nq, int E, const float* __restrict__ cmax,
+                                                           float* __restrict__ Q32, float* __restrict__ eps) {
+    const int lane = threadIdx.x & 31;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    float s = 0.f;
+    for (int k = lane; k < E; k += 32) {
+        float v = Q[(int64_t)q * ldq + k];
+        Q32[(int64_t)q * E + k] = tf32_rn(v);
+        s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) eps[q] = kEpsCoef * sqrtf(s) * cmax[0] * 1.0001f + 1e-30f;
+}
+
+// One CTA per query: tau = K-th largest of gmax[q][0..ngroups) by 4-pass MSB radix select; thr = tau - 2 eps.
+__global__ void __launch_bounds__(256) select_threshold_kernel(const float* __restrict__ gmax, int ld, int ngroups, int K,
+                                                               const float* __restrict__ eps, float* __restrict__ thr, int32_t* __restrict__ cnt,
+                                                               int32_t* __restrict__ flags) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_remaining;
+    const int q = blockIdx.x;
+    const float* row = gmax + (int64_t)q * ld;
+    if (threadIdx.x == 0) { cnt[q] = 0; flags[q] = 0; }
+    if (ngroups < K) {   // fewer groups than K: everything is a candidate (the list will overflow unless n is tiny)
+        if (threadIdx.x == 0) thr[q] = -CUDART_INF_F;
+        return;
+    }
+    constexpr int kCache = 16;                         // values cached in registers when the row is short
+    uint32_t cache[kCache];
+    const bool cached = ngroups <= kCache * 256;
+    if (cached) {
+#pragma unroll
+        for (int i = 0; i < kCache; ++i) {
+            int g = threadIdx.x + i * 256;
+            cache[i] = g < ngroups ? ordered_key(row[g]) : 0u;   // key 0 sorts below every real value
+        }
+    }
+    uint32_t prefix = 0, mask = 0, remaining = (uint32_t)K;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        if (cached) {
+#pragma unroll
+            for (int i = 0; i < kCache; ++i) {
+                int g = threadIdx.x + i * 256;
+                if (g < ngroups && (cache[i] & mask) == prefix) atomicAdd(&hist[(cache[i] >> shift) & 255], 1u);
+            }
+        } else {
+            for (int g = threadIdx.x; g < ngroups; g += 256) {
+                uint32_t k = ordered_key(row[g]);
+                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t cum = 0;
+            int b = 255;
+            for (; b > 0; --b) {
+                if (cum + hist[b] >= remaining) break;
+                cum += hist[b];
+            }
+            s_prefix = prefix | ((uint32_t)b << shift);
+            s_remaining = remaining - cum;
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        remaining = s_remaining;
+        mask |= 255u << shift;
+    }
+    if (threadIdx.x == 0) thr[q] = key_to_float(prefix) - 2.0f * eps[q];
+}
+
+// One CTA per query: exact canonical score of every collected candidate, then exact top-K (bitonic sort in smem).
+__global__ void __launch_bounds__(256) rescore_topk_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ C, int ldc, int E, int K,
+                                                           const int32_t* __restrict__ cand, const int32_t* __restrict__ cnt, int cap, int P,
+                                                           int64_t idx_base, float* __restrict__ out_s, int32_t* __restrict__ out_i,
+                                                           int32_t* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sq = reinterpret_cast<float*>(smem_raw);          // E
+    float* ss = sq + 128;                                      // P scores
+    int32_t* si = reinterpret_cast<int32_t*>(ss + P);          // P indices
+    const int q = blockIdx.x;
+    const int m = cnt[q];
+    if (m > cap) {   // overflow: hand the query to the exact fallback
+        if (threadIdx.x == 0) flags[q] = 1;
+        return;
+    }
+    for (int k = threadIdx.x; k < E; k += 256) sq[k] = Q[(int64_t)q * ldq + k];
+    __syncthreads();
+    for (int t = threadIdx.x; t < P; t += 256) {
+        float s = -CUDART_INF_F;
+        int32_t id = 0x7fffffff;
+        if (t < m) {
+            id = cand[(int64_t)q * cap + t];
+            const float4* row = reinterpret_cast<const float4*>(C + (int64_t)id * ldc);
+            float acc = 0.f;
+            for (int k4 = 0; k4 < E / 4; ++k4) {   // canonical order: k ascending, one fmaf per term
+                const float4 c = __ldg(row + k4);
+                acc = fmaf(sq[4 * k4], c.x, acc);
+                acc = fmaf(sq[4 * k4 + 1], c.y, acc);
+                acc = fmaf(sq[4 * k4 + 2], c.z, acc);
+                acc = fmaf(sq[4 * k4 + 3], c.w, acc);
+            }
+            s = acc;
+        }
+        ss[t] = s;
+        si[t] = id;
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < P / 2; t += 256) {
+                int i = 2 * t - (t & (j - 1));
+                int p = i + j;
+                bool up = ((i & k) == 0);
+                float a = ss[i], b = ss[p];
+                int32_t ia = si[i], ib = si[p];
+                bool swap = up ? ranks_before(b, ib, a, ia) : ranks_before(a, ia, b, ib);
+                if (swap) { ss[i] = b; ss[p] = a; si[i] = ib; si[p] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < K; t += 256) {
+        const bool pad = si[t] == 0x7fffffff;
+        out_s[(int64_t)q * K + t] = pad ? -CUDART_INF_F : ss[t];
+        out_i[(int64_t)q * K + t] = pad ? -1 : (int32_t)(si[t] + idx_base);
+    }
+}
+
+__global__ void round_rows_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int64_t rows, int E) {
+    int64_t total = rows * E;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+        int64_t r = i / E;
+        int c = (int)(i % E);
+        dst[i] = tf32_rn(src[r * lds + c]);
+    }
+}
+
+__global__ void max_norm_kernel(const float* __restrict__ C, int ldc, int64_t n, int E, float* __restrict__ out) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float best = 0.f;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        float s = 0.f;
+        for (int k = lane; k < E; k += 32) { float v = C[r * ldc + k]; s = fmaf(v, v, s); }
+        s = warp_sum(s);
+        best = fmaxf(best, sqrtf(s));
+    }
+    best = warp_max(best);
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(best));
+}
+
+template <int MODE, int E>
+static int launch_idx(const CUtensorMap& tmQ, const CUtensorMap& tmC, const RowPanelParams& p, int m_tiles, int splits, cudaStream_t st,
+                      const char* name) {
+    constexpr int BN = (E <= 64) ? 256 : 128;
+    using Cfg = RowPanelCfg<MODE, E, BN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        TT_CUDA_OK(cudaFuncSetAttribute(rowpanel_kernel<MODE, E, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)m_tiles, (unsigned)splits);
+    rowpanel_kernel<MODE, E, BN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmQ, tmC, tmC, p);
+    TT_LAUNCH_OK(name);
+    return TT_OK;
+}
+
+template <int MODE>
+static int launch_idx_e(int E, const CUtensorMap& tmQ, const CUtensorMap& tmC, const RowPanelParams& p, int m_tiles, int splits, cudaStream_t st,
+                        const char* name) {
+    switch (E) {
+        case 32: return launch_idx<MODE, 32>(tmQ, tmC, p, m_tiles, splits, st, name);
+        case 64: return launch_idx<MODE, 64>(tmQ, tmC, p, m_tiles, splits, st, name);
+        default: return launch_idx<MODE, 128>(tmQ, tmC, p, m_tiles, splits, st, name);
+    }
+}
+
+struct IdxLayout {
+    size_t q32, eps, thr, gmax, cnt, flags, cand, c32, cmax, exact, total;
+    int ngroups, n_tiles, cap;
+};
+
+static IdxLayout layout(int nq, int64_t n, int E, int K, bool need_corpus_copy) {
+    IdxLayout L;
+    L.n_tiles = (int)ceil_div(n, idx_bn(E));
+    L.ngroups = L.n_tiles * (idx_bn(E) / kGroup);
+    L.cap = cand_cap(K);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    L.q32 = take((size_t)nq * E * 4);
+    L.eps = take((size_t)nq * 4);
+    L.thr = take((size_t)nq * 4);
+    L.gmax = take((size_t)nq * L.ngroups * 4);
+    L.cnt = take((size_t)nq * 4);
+    L.flags = take((size_t)nq * 4);
+    L.cand = take((size_t)nq * L.cap * 4);
+    L.c32 = take(need_corpus_copy ? (size_t)n * E * 4 : 0);
+    L.cmax = take(256);
+    L.exact = off;
+    L.total = off;
+    return L;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+bool index_tc_supported(int ldq, int ldc, int E, int K, int64_t n, const void* Q, const void* C) {
+    if (!softmax_tc_supported(ldq, ldc, E, Q, C)) return false;
+    if (K < 1 || K > 1024) return false;
+    if (n < 4096) return false;                                   // tiny corpora: the exact kernel is already fast
+    if (ceil_div(n, kGroup) < 4 * (int64_t)K) return false;      // the group filter needs many more groups than K
+    return true;
+}
+
+size_t index_tc_workspace(int nq, int64_t n, int E, int K, bool need_corpus_copy) {
+    if (!(E == 32 || E == 64 || E == 128)) return 0;
+    return layout(nq, n, E, K, need_corpus_copy).total + 512;
+}
+
+void debug_index_cap(int cap) { tc::g_cap_override = cap; }
+
+int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_in, const float* cmax_in, int nq, int64_t n, int E, int K,
+             int64_t idx_base, float* out_s, int32_t* out_i, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const bool need_copy = (C32_in == nullptr);
+    IdxLayout L = layout(nq, n, E, K, need_copy);
+    const size_t exact_bytes = index_exact_workspace(nq, n, K);
+    TT_REQUIRE(ws && ws_bytes >= L.total + exact_bytes, "tt_index_topk: workspace too small (%zu < %zu)", ws_bytes, L.total + exact_bytes);
+    char* base = reinterpret_cast<char*>(ws);
+    float* q32 = reinterpret_cast<float*>(base + L.q32);
+    float* eps = reinterpret_cast<float*>(base + L.eps);
+    float* thr = reinterpret_cast<float*>(base + L.thr);
+    float* gmax = reinterpret_cast<float*>(base + L.gmax);
+    int32_t* cnt = reinterpret_cast<int32_t*>(base + L.cnt);
+    int32_t* flags = reinterpret_cast<int32_t*>(base + L.flags);
+    int32_t* cand = reinterpret_cast<int32_t*>(base + L.cand);
+    float* cmax = reinterpret_cast<float*>(base + L.cmax);
+    const float* c32 = C32_in;
+    if (need_copy) {
+        float* dst = reinterpret_cast<float*>(base + L.c32);
+        int64_t total = n * E;
+        int64_t g = ceil_div(total, 256 * 4);
+        int64_t cap = (int64_t)sm_count() * 16;
+        round_rows_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(C, ldc, dst, n, E);
+        TT_LAUNCH_OK("round_rows_kernel");
+        c32 = dst;
+    }
+    const float* cm = cmax_in;
+    if (!cm) {
+        TT_CUDA_OK(cudaMemsetAsync(cmax, 0, sizeof(float), st));
+        int64_t g = ceil_div(n * 32, 256);
+        int64_t cap = (int64_t)sm_count() * 8;
+        max_norm_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(C, ldc, n, E, cmax);
+        TT_LAUNCH_OK("max_norm_kernel");
+        cm = cmax;
+    }
+    prep_queries_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, st>>>(Q, ldq, nq, E, cm, q32, eps);
+    TT_LAUNCH_OK("prep_queries_kernel");
+
+    CUtensorMap tmQ, tmC;
+    int rc = make_tmap_2d(&tmQ, q32, nq, E, E, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmC, c32, n, E, need_copy ? E : ldc, idx_bn(E));
+    if (rc) return rc;
+    const int m_tiles = (int)ceil_div(nq, 128);
+    int splits = 1, tps = L.n_tiles;
+    choose_splits(m_tiles, L.n_tiles, 2, 64, &splits, &tps);
+    RowPanelParams p{};
+    p.nR = nq; p.nT = (int)n; p.n_tiles = L.n_tiles; p.tiles_per_split = tps; p.rowv = nullptr; p.colv2 = nullptr; p.d = -(1 << 30);
+    p.out0 = gmax; p.out1 = nullptr; p.out2 = nullptr; p.ld_out = L.ngroups; p.trace = nullptr;
+    rc = launch_idx_e<kIndex>(E, tmQ, tmC, p, m_tiles, splits, st, "rowpanel_kernel<index>");
+    if (rc) return rc;
+    select_threshold_kernel<<<(unsigned)nq, 256, 0, st>>>(gmax, L.ngroups, (int)ceil_div(n, kGroup), K, eps, thr, cnt, flags);
+    TT_LAUNCH_OK("select_threshold_kernel");
+    p.rowv = thr;
+    p.out0 = reinterpret_cast<float*>(cand);
+    p.out1 = reinterpret_cast<float*>(cnt);
+    p.ld_out = L.cap;
+    rc = launch_idx_e<kCollect>(E, tmQ, tmC, p, m_tiles, splits, st, "rowpanel_kernel<collect>");
+    if (rc) return rc;
+    const int P = next_pow2(L.cap < 2 ? 2 : L.cap);
+    const size_t smem = 128 * 4 + (size_t)P * 8;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        TT_CUDA_OK(cudaFuncSetAttribute(rescore_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    rescore_topk_kernel<<<(unsigned)nq, 256, smem, st>>>(Q, ldq, C, ldc, E, K, cand, cnt, L.cap, P, idx_base, out_s, out_i, flags);
+    TT_LAUNCH_OK("rescore_topk_kernel");
+    // queries whose candidate list overflowed: exact CUDA-core path, decided on the device (no host sync)
+    return index_exact(Q, ldq, C, ldc, nq, n, E, K, idx_base, out_s, out_i, base + L.exact, exact_bytes, st, flags);
+}
+
+}  // namespace tt

@@ -18,6 +18,7 @@ int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const 
 int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, float* Z, int ldz, cudaStream_t st);
 size_t softmax_tc_workspace_bytes(int Bq, int Bc, int E);
 void debug_tc(void* trace, int max_splits);
+void debug_index_cap(int cap);
 
 static int pick_impl(int impl, int ldq, int ldc, int E, const void* Q, const void* C, const char* who) {
     if (impl == TT_IMPL_SIMT) return TT_IMPL_SIMT;
@@ -43,6 +44,11 @@ extern "C" {
 
 int tt_debug_tc(void* trace, int max_splits) {
     debug_tc(trace, max_splits);
+    return TT_OK;
+}
+
+int tt_debug_index_cap(int cap) {
+    debug_index_cap(cap);
     return TT_OK;
 }
 

@@ -15,7 +15,9 @@
 //           swizzle (128B_BASE32B) than the K-major tile of the first MMA, so the B operand of the second
 //           MMA is a K-major tile of T^T (E x BN) loaded by TMA from a transposed copy of T.
 //   kLogits Z = S - colv written out (tests / TwoTowerModel.call)
-//   kIndex  max over each group of 32 consecutive columns                 -> group maxima (filter stage)
+//   kIndex  max over each group of 32 consecutive columns                 -> group maxima (filter stage 1)
+//   kCollect every column whose score reaches the row's threshold is appended to the row's candidate list
+//           (filter stage 2; the list is rescored exactly afterwards, so its order does not matter)
 //
 // The per-column term arrives pre-scaled (colv2 = colv * log2 e, zero padded to whole tiles) and is staged
 // into shared memory by a 1-D bulk copy on the tile's barrier; the epilogue works in the log2 domain with
@@ -28,19 +30,20 @@
 namespace tt {
 namespace tc {
 
-enum RowPanelMode { kFwd = 0, kBwd = 1, kLogits = 2, kIndex = 3 };
+enum RowPanelMode { kFwd = 0, kBwd = 1, kLogits = 2, kIndex = 3, kCollect = 4 };
 
 struct RowPanelParams {
     int nR, nT;
     int n_tiles;          // ceil(nT / BN)
     int tiles_per_split;  // tiles handled by one blockIdx.y
-    const float* rowv;    // kBwd: per-R-row term (lse or ln p), natural units
+    const float* rowv;    // kBwd: per-R-row term (lse or ln p), natural units | kCollect: per-row score threshold
     const float* colv2;   // per-T-row term * log2(e), padded with zeros to n_tiles*BN entries (never null)
     int d;                // diagonal: column == row + d
     float* out0;          // kFwd: m2 [split][nR] | kBwd: G partial [split][nR][E] | kLogits: Z | kIndex: gmax [nR][ld_out]
-    float* out1;          // kFwd: l  [split][nR]
+                          // kCollect: (int32*) candidate column lists [nR][ld_out]
+    float* out1;          // kFwd: l  [split][nR] | kCollect: (int32*) list lengths [nR] (may exceed ld_out: overflow)
     float* out2;          // kFwd: zdiag [nR] (natural units; written by the split that owns the diagonal column)
-    int ld_out;           // kLogits: ldz | kIndex: row stride of gmax (groups)
+    int ld_out;           // kLogits: ldz | kIndex: row stride of gmax (groups) | kCollect: list capacity
     unsigned long long* trace;  // optional debug timeline: [cta][16] globaltimer stamps (ns); null in production
 };
 
@@ -109,7 +112,8 @@ struct RowPanelCfg {
     static constexpr int kPSlabs = BN / 32;
     static constexpr int kPBytes = (MODE == kBwd) ? kPSlabs * 128 * 128 : 0;
     static constexpr int kPBufs = (MODE == kBwd) ? 2 : 0;
-    static constexpr int kC2Bytes = BN * 4;                                  // staged column term per stage
+    static constexpr bool kUsesC2 = (MODE == kFwd || MODE == kBwd || MODE == kLogits);
+    static constexpr int kC2Bytes = kUsesC2 ? BN * 4 : 0;                    // staged column term per stage
     static constexpr int kHalves = (BN / 32 >= 2) ? 2 : 1;                   // epilogue warps per TMEM lane quarter
     static constexpr int kEpiWarps = 4 * kHalves;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
@@ -246,7 +250,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                 if (MODE == kBwd) {
                     for (int s = 0; s < BN / 32; ++s) tma_load_2d(dst + Cfg::kT1Bytes + s * E * 128, &tmTt, &bars->t_full[stage], n0 + s * 32, 0);
                 }
-                bulk_copy_1d(sC2 + stage * 1024, p.colv2 + n0, Cfg::kC2Bytes, &bars->t_full[stage]);
+                if (Cfg::kUsesC2) bulk_copy_1d(sC2 + stage * 1024, p.colv2 + n0, Cfg::kC2Bytes, &bars->t_full[stage]);
             }
         }
     } else if (warp == 1) {
@@ -317,6 +321,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         bool has_diag = false;
         float r2 = 0.f;
         if (MODE == kBwd) r2 = (row < p.nR && p.rowv) ? __ldg(p.rowv + row) * kLog2e : 0.f;
+        if (MODE == kCollect) r2 = (row < p.nR) ? __ldg(p.rowv + row) : CUDART_INF_F;   // threshold (natural units)
         constexpr int NC = BN / 32;
         constexpr int NCW = NC / Cfg::kHalves;        // 32-column chunks per warp per tile
         const int c_first = half * NCW;
@@ -365,6 +370,21 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                             }
                         }
                     }
+                } else if constexpr (MODE == kCollect) {
+                    float mx = -CUDART_INF_F;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    if (mx >= r2) {   // rare: some column of this chunk reaches the row's threshold
+                        int32_t* lists = reinterpret_cast<int32_t*>(p.out0);
+                        int32_t* lens = reinterpret_cast<int32_t*>(p.out1);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (__uint_as_float(r[i]) >= r2 && nb + i < p.nT) {
+                                const int slot = atomicAdd(lens + row, 1);
+                                if (slot < p.ld_out) lists[(int64_t)row * p.ld_out + slot] = nb + i;
+                            }
+                        }
+                    }
                 } else {  // kIndex
                     float mx = -CUDART_INF_F;
                     if (fast || nb + 32 <= p.nT) {
@@ -393,8 +413,13 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
             if constexpr (MODE == kIndex) {
                 if (row < p.nR) {
                     float* dst = p.out0 + (int64_t)row * p.ld_out + (int64_t)(tile_begin + it) * NC + c_first;
+                    if constexpr (NCW % 4 == 0) {
 #pragma unroll
-                    for (int c = 0; c < NCW; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(gm[c], gm[c + 1], gm[c + 2], gm[c + 3]);
+                        for (int c = 0; c < NCW; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(gm[c], gm[c + 1], gm[c + 2], gm[c + 3]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NCW; ++c) dst[c] = gm[c];
+                    }
                 }
             }
         }

@@ -40,6 +40,7 @@ SIGNATURES = {
     "tt_launch_count": (c_int64, []),
     "tt_tc_available": (c_int, [c_int, c_int]),
     "tt_debug_tc": (c_int, [c_void_p, c_int]),
+    "tt_debug_index_cap": (c_int, [c_int]),
     "tt_gather_concat": (c_int, [ctypes.POINTER(TTFeature), c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "tt_dense_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p]),
@@ -66,9 +67,9 @@ SIGNATURES = {
     "tt_sparse_adagrad": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "tt_sparse_adam": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_float, c_float, c_float, c_float, c_void_p, c_size_t,
                                c_void_p]),
-    "tt_index_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int, c_int]),
-    "tt_index_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p,
-                              c_void_p, c_size_t, c_int, c_void_p]),
+    "tt_index_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int, c_int, c_int]),
+    "tt_index_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int64,
+                              c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "tt_corpus_max_norm": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "tt_round_tf32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "tt_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -52,6 +52,17 @@ class BruteForceIndex(AbstractKerasModel):
         self.n_total = n_total
         self._identifiers = identifiers                       # all ids (host), position == global row index
         self._candidates = candidates.contiguous()            # (N_local, E) fp32, non-trainable
+        # operand preparation for the tensor-core filter, done once at build time: TF32-rounded copy of the
+        # corpus and the largest row norm (error bound of the filter); the exact fp32 rows stay authoritative
+        lib = N.load()
+        n_loc, e = self._candidates.shape
+        self._candidates_tf32, self._max_norm = None, None
+        if n_loc > 0 and lib.tt_tc_available(1, e):
+            self._candidates_tf32 = torch.empty_like(self._candidates)
+            self._max_norm = torch.zeros(1, dtype=torch.float32, device="cuda")
+            st = N.stream_ptr()
+            N.check(lib.tt_round_tf32(self._candidates.data_ptr(), e, self._candidates_tf32.data_ptr(), e, n_loc, e, st), "tt_round_tf32")
+            N.check(lib.tt_corpus_max_norm(self._candidates.data_ptr(), e, n_loc, e, self._max_norm.data_ptr(), st), "tt_corpus_max_norm")
         if self.k > n_total:
             raise ValueError(f"k={self.k} exceeds the number of candidates ({n_total})")
 
@@ -90,12 +101,14 @@ class BruteForceIndex(AbstractKerasModel):
             scores.fill_(float("-inf"))
             idx.fill_(-1)
             return scores, idx
-        need = int(lib.tt_index_workspace_bytes(nq, n, e, k, self.impl))
+        have32 = self._candidates_tf32 is not None
+        need = int(lib.tt_index_workspace_bytes(nq, n, e, k, self.impl, 1 if have32 else 0))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
-        N.check(lib.tt_index_topk(q.data_ptr(), q.stride(0), self._candidates.data_ptr(), self._candidates.stride(0), nq, n, e, k,
-                                  self.idx_base, scores.data_ptr(), idx.data_ptr(), self._ws.data_ptr(), self._ws.numel(), self.impl,
-                                  N.stream_ptr()), "tt_index_topk")
+        N.check(lib.tt_index_topk(q.data_ptr(), q.stride(0), self._candidates.data_ptr(), self._candidates.stride(0),
+                                  self._candidates_tf32.data_ptr() if have32 else None, self._max_norm.data_ptr() if have32 else None,
+                                  nq, n, e, k, self.idx_base, scores.data_ptr(), idx.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                  self.impl, N.stream_ptr()), "tt_index_topk")
         return scores, idx
 
     def query_indices(self, queries, k: Optional[int] = None):

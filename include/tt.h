@@ -52,6 +52,9 @@ int tt_tc_available(int kind, int E);
 /* Debug/profiling knobs of the tensor-core kernels: `trace` (device, u64[ctas][16], or NULL) receives
  * globaltimer stamps of subsequent launches; `max_splits` caps the column splits (0 = default). */
 int tt_debug_tc(void* trace, int max_splits);
+/* Test knob: cap the candidate lists of the tensor-core index filter (0 = default 4K+512) to force the
+ * on-device exact fallback. */
+int tt_debug_index_cap(int cap);
 /* Number of kernels this library has launched (or captured into a CUDA graph) in this process so far. */
 int64_t tt_launch_count(void);
 
@@ -157,10 +160,13 @@ int tt_sparse_adam(const tt_sparse_job* jobs, int njobs, float lr_t, float beta1
  * row-sharded corpus).  The (nq, n) score matrix never reaches HBM.
  * Scores returned are the canonical fp32 values (k-ascending fmaf), bit-exact against the oracle.
  * ---------------------------------------------------------------------------------------------- */
-size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl);
-int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, int nq, int64_t n, int E, int K,
-                  int64_t idx_base, float* out_scores, int32_t* out_idx, void* ws, size_t ws_bytes, int impl,
-                  void* stream);
+/* corpus_tf32 (optional, same ld as corpus): round-to-nearest TF32 copy of the corpus kept by the caller
+ * (tt_round_tf32 at index-build time); corpus_max_norm (optional): device float from tt_corpus_max_norm.
+ * When NULL they are recomputed into the workspace on every call (pass have_corpus_tf32 = 0 when sizing). */
+size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl, int have_corpus_tf32);
+int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const float* corpus_tf32,
+                  const float* corpus_max_norm, int nq, int64_t n, int E, int K, int64_t idx_base, float* out_scores,
+                  int32_t* out_idx, void* ws, size_t ws_bytes, int impl, void* stream);
 /* max_j ||corpus_j||_2 (used by the tensor-core filter's error bound); result is one float. */
 int tt_corpus_max_norm(const float* corpus, int ldc, int64_t n, int E, float* out, void* stream);
 /* Round-to-nearest TF32 copy of a matrix (operand preparation for TT_IMPL_TC). */

@@ -317,9 +317,9 @@ def _index_call(lib, T, q, c, K, idx_base=0, impl=1):
     dq, dc = dev(T, q), dev(T, c)
     nq, n, E = q.shape[0], c.shape[0], q.shape[1]
     s = T.empty((nq, K), dtype=T.float32, device="cuda"); i = T.empty((nq, K), dtype=T.int32, device="cuda")
-    ws = T.empty(int(lib.tt_index_workspace_bytes(nq, n, E, K, impl)), dtype=T.uint8, device="cuda")
-    N.check(lib.tt_index_topk(dq.data_ptr(), E, dc.data_ptr(), E, nq, n, E, K, idx_base, s.data_ptr(), i.data_ptr(), ws.data_ptr(),
-                              ws.numel(), impl, stream()))
+    ws = T.empty(int(lib.tt_index_workspace_bytes(nq, n, E, K, impl, 0)), dtype=T.uint8, device="cuda")
+    N.check(lib.tt_index_topk(dq.data_ptr(), E, dc.data_ptr(), E, None, None, nq, n, E, K, idx_base, s.data_ptr(), i.data_ptr(),
+                              ws.data_ptr(), ws.numel(), impl, stream()))
     return s.cpu().numpy(), i.cpu().numpy()
 
 

@@ -160,3 +160,86 @@ def test_model_train_step_tc_within_north_star(lib, T):
     # gradient is ~0 may differ by a few 1e-2; the bulk must agree)
     assert float((we - wt).abs().mean()) < 5e-4
     assert float(((we - wt).abs() > 1e-2).float().mean()) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------
+# index: tensor-core filter + exact rescoring must return exactly what the canonical fp32 oracle returns
+# ---------------------------------------------------------------------------------------------------
+def _index_tc(lib, T, q, c, K, idx_base=0, prepared=False):
+    from pkg import _native as N
+
+    dq, dc = dev(T, q), dev(T, c)
+    nq, n, E = q.shape[0], c.shape[0], q.shape[1]
+    c32 = mx = None
+    if prepared:   # what BruteForceIndex does once at build time
+        c32 = T.empty_like(dc); mx = T.zeros(1, dtype=T.float32, device="cuda")
+        N.check(lib.tt_round_tf32(dc.data_ptr(), E, c32.data_ptr(), E, n, E, stream()))
+        N.check(lib.tt_corpus_max_norm(dc.data_ptr(), E, n, E, mx.data_ptr(), stream()))
+    s = T.empty((nq, K), dtype=T.float32, device="cuda"); i = T.empty((nq, K), dtype=T.int32, device="cuda")
+    ws = T.empty(int(lib.tt_index_workspace_bytes(nq, n, E, K, TC, 1 if prepared else 0)), dtype=T.uint8, device="cuda")
+    N.check(lib.tt_index_topk(dq.data_ptr(), E, dc.data_ptr(), E, c32.data_ptr() if prepared else None, mx.data_ptr() if prepared else None,
+                              nq, n, E, K, idx_base, s.data_ptr(), i.data_ptr(), ws.data_ptr(), ws.numel(), TC, stream()))
+    return s.cpu().numpy(), i.cpu().numpy()
+
+
+@pytest.mark.parametrize("nq,n,E,K,prepared", [(70, 20_000, 64, 100, False), (2048, 105_542, 64, 100, True), (5, 8000, 32, 12, True),
+                                               (300, 40_000, 128, 100, False), (129, 50_001, 64, 1, True), (64, 140_000, 64, 1000, True)])
+def test_index_tc_bit_exact(lib, T, nq, n, E, K, prepared):
+    rng = np.random.default_rng(10)
+    q = np.maximum(rng.standard_normal((nq, E)) * 0.3, 0).astype(np.float32)      # tower outputs are non-negative
+    c = (np.abs(rng.standard_normal((n, E))) * 0.1).astype(np.float32)
+    want_s, want_i = O.index_topk(q, c, K, idx_base=7)
+    s, i = _index_tc(lib, T, q, c, K, idx_base=7, prepared=prepared)
+    assert np.array_equal(i, want_i.astype(np.int32))                              # indices bit-exact
+    assert np.array_equal(s, want_s)                                               # scores are the canonical fp32 values
+
+
+def test_index_tc_signed_embeddings_and_many_exact_ties(lib, T):
+    rng = np.random.default_rng(11)
+    # signed values (BruteForceIndex accepts any query model) on a coarse dyadic grid: thousands of exactly equal
+    # scores, so the (score desc, index asc) rule decides most of the top-100
+    q = (rng.integers(-4, 5, size=(40, 32)) / 4.0).astype(np.float32)
+    c = (rng.integers(-2, 3, size=(30_000, 32)) / 2.0).astype(np.float32)
+    want_s, want_i = O.index_topk(q, c, 100)
+    s, i = _index_tc(lib, T, q, c, 100)
+    assert np.array_equal(i, want_i.astype(np.int32)) and np.array_equal(s, want_s)
+
+
+def test_index_tc_overflow_falls_back_to_exact_on_device(lib, T):
+    rng = np.random.default_rng(12)
+    q = np.maximum(rng.standard_normal((200, 64)) * 0.3, 0).astype(np.float32)
+    c = (np.abs(rng.standard_normal((20_000, 64))) * 0.1).astype(np.float32)
+    want_s, want_i = O.index_topk(q, c, 100)
+    lib.tt_debug_index_cap(64)          # candidate lists of 64 < K: every query overflows
+    try:
+        s, i = _index_tc(lib, T, q, c, 100)
+    finally:
+        lib.tt_debug_index_cap(0)
+    assert np.array_equal(i, want_i.astype(np.int32)) and np.array_equal(s, want_s)
+
+
+def test_brute_force_index_uses_tc_and_matches_exact(lib, T):
+    from pkg import _native as N
+    from pkg.modelling.indices.brute_force import BruteForceIndex
+
+    rng = np.random.default_rng(13)
+    n, E = 50_000, 64
+    c = (np.abs(rng.standard_normal((n, E))) * 0.1).astype(np.float32)
+    table = np.maximum(rng.standard_normal((500, E)) * 0.3, 0).astype(np.float32)
+
+    class QM:
+        def __call__(self, x):
+            return table[np.asarray(x["id"]).reshape(-1)]
+
+        def get_input_signature(self):
+            return {}
+
+    ids = np.arange(n, dtype=np.int32)
+    index = BruteForceIndex(100, QM(), [(ids[:30_000], c[:30_000]), (ids[30_000:], c[30_000:])])
+    assert index._candidates_tf32 is not None
+    x = {"id": rng.integers(0, 500, size=(333, 1)).astype(np.int32)}
+    got = index(x)
+    index.impl = N.TT_IMPL_SIMT
+    assert np.array_equal(got, index(x))
+    _, want = O.index_topk(table[x["id"].reshape(-1)], c, 100)
+    assert np.array_equal(got, ids[want])
