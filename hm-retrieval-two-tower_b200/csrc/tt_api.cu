@@ -137,25 +137,6 @@ __global__ void recall_hits_kernel(const int32_t* __restrict__ cand, int k_strid
     if (threadIdx.x < nk && s_hits[threadIdx.x]) atomicAdd(&hits[threadIdx.x], s_hits[threadIdx.x]);
 }
 
-// max_j ||corpus_j||_2 : per-row norm, block max, then atomicMax on the float bit pattern (all >= 0)
-__global__ void corpus_max_norm_kernel(const float* __restrict__ C, int ldc, int64_t n, int E, float* __restrict__ out) {
-    int lane = threadIdx.x & 31;
-    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float best = 0.0f;
-    for (int64_t r = warp; r < n; r += nwarps) {
-        float s = 0.0f;
-        for (int k = lane; k < E; k += 32) {
-            float v = C[r * ldc + k];
-            s = fmaf(v, v, s);
-        }
-        s = warp_sum(s);
-        best = fmaxf(best, sqrtf(s));
-    }
-    best = warp_max(best);
-    if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(best));
-}
-
 static inline int grid_for(int64_t n, int block) {
     int64_t g = ceil_div(n, block);
     int64_t cap = (int64_t)sm_count() * 8;
@@ -248,20 +229,6 @@ int tt_recall_hits(const int32_t* cand, int k_stride, const int32_t* true_idx, i
     if (grid > cap) grid = cap;
     recall_hits_kernel<<<grid, block, 0, as_stream(stream)>>>(cand, k_stride, true_idx, nq, a, nk, hits);
     TT_LAUNCH_OK("recall_hits_kernel");
-    return TT_OK;
-}
-
-int tt_corpus_max_norm(const float* corpus, int ldc, int64_t n, int E, float* out, void* stream) {
-    TT_REQUIRE(corpus && out, "tt_corpus_max_norm: null pointer");
-    TT_REQUIRE(n >= 0 && E >= 1 && ldc >= E, "tt_corpus_max_norm: bad shape");
-    TT_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), as_stream(stream)));
-    if (n == 0) return TT_OK;
-    int block = 256;
-    int grid = (int)ceil_div(n * 32, block);
-    int cap = sm_count() * 8;
-    if (grid > cap) grid = cap;
-    corpus_max_norm_kernel<<<grid, block, 0, as_stream(stream)>>>(corpus, ldc, n, E, out);
-    TT_LAUNCH_OK("corpus_max_norm_kernel");
     return TT_OK;
 }
 

@@ -253,8 +253,9 @@ int index_exact(const float* Q, int ldq, const float* C, int ldc, int nq, int64_
 // tt_index_tc.cu
 bool index_tc_supported(int ldq, int ldc, int E, int K, int64_t n, const void* Q, const void* C);
 size_t index_tc_workspace(int nq, int64_t n, int E, int K, bool need_corpus_copy);
-int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32, const float* cmax, int nq, int64_t n, int E, int K,
+int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32, const float* norms, int nq, int64_t n, int E, int K,
              int64_t idx_base, float* out_s, int32_t* out_i, void* ws, size_t ws_bytes, cudaStream_t st);
+namespace tc { int launch_prepare(const float* C, int ldc, int64_t n, int E, float* C32p, float* norms, int64_t n_pad, cudaStream_t st); }
 
 }  // namespace tt
 
@@ -262,14 +263,20 @@ using namespace tt;
 
 extern "C" {
 
-size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl, int have_corpus_tf32) {
+size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl, int have_corpus_prepared) {
     if (nq <= 0 || n <= 0 || K <= 0) return 256;
     size_t a = index_exact_workspace(nq, n, K);
-    size_t b = (impl == TT_IMPL_SIMT) ? 0 : index_tc_workspace(nq, n, E, K, !have_corpus_tf32);
+    size_t b = (impl == TT_IMPL_SIMT) ? 0 : index_tc_workspace(nq, n, E, K, !have_corpus_prepared);
     return a + b + 256;   // the filter path keeps the exact path's scratch for its (rare) fallback
 }
 
-int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const float* corpus_tf32, const float* corpus_max_norm, int nq,
+int tt_index_prepare(const float* corpus, int ldc, int64_t n, int E, float* corpus_prepared, float* corpus_norms, void* stream) {
+    TT_REQUIRE(corpus && corpus_prepared && corpus_norms, "tt_index_prepare: null pointer");
+    TT_REQUIRE(n >= 0 && E >= 1 && ldc >= E, "tt_index_prepare: bad shape");
+    return tc::launch_prepare(corpus, ldc, n, E, corpus_prepared, corpus_norms, (int64_t)TT_INDEX_NORM_PAD(n), as_stream(stream));
+}
+
+int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const float* corpus_prepared, const float* corpus_norms, int nq,
                   int64_t n, int E, int K, int64_t idx_base, float* out_scores, int32_t* out_idx, void* ws, size_t ws_bytes, int impl,
                   void* stream) {
     TT_REQUIRE(Q && corpus && out_scores && out_idx, "tt_index_topk: null pointer");
@@ -283,7 +290,7 @@ int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const f
         return TT_ERR_UNSUPPORTED;
     }
     if (impl == TT_IMPL_TC || (impl == TT_IMPL_AUTO && tc_ok))
-        return index_tc(Q, ldq, corpus, ldc, corpus_tf32, corpus_max_norm, nq, n, E, K, idx_base, out_scores, out_idx, ws, ws_bytes, st);
+        return index_tc(Q, ldq, corpus, ldc, corpus_prepared, corpus_norms, nq, n, E, K, idx_base, out_scores, out_idx, ws, ws_bytes, st);
     return index_exact(Q, ldq, corpus, ldc, nq, n, E, K, idx_base, out_scores, out_idx, ws, ws_bytes, st, nullptr);
 }
 

@@ -5,20 +5,19 @@
 // canonical fp32 values -- bit-identical to the exact path and to oracle/tt_oracle.c -- although the
 // heavy lifting runs in TF32 on tcgen05:
 //
-//   1. rowpanel_kernel<kIndex>   TF32 scores a_ij; only the maximum of every group of 32 consecutive corpus
-//                                rows is kept (n/32 floats per query).
-//   2. select_threshold_kernel   tau = K-th largest group maximum of the query (radix select);
-//                                thr = tau - 2*eps_q with eps_q >= |a_ij - s_ij| for every j.
-//   3. rowpanel_kernel<kCollect> same TF32 contraction; every j with a_ij >= thr is appended to the query's
-//                                candidate list (~K entries).
+//   1. rowpanel_kernel<kIndex>   TF32 scores a_ij with the error bound eps_ij = kappa_i*||c_j||, kappa_i = 2^-9*||q_i||;
+//                                only max_j (a_ij - eps_ij) over every group of 32 consecutive corpus rows is
+//                                kept (n/32 floats per query).
+//   2. select_threshold_kernel   lambda_i = K-th largest group value of the query (radix select).
+//   3. rowpanel_kernel<kCollect> same TF32 contraction; every j with a_ij + eps_ij >= lambda_i is appended to
+//                                the query's candidate list (~K entries).
 //   4. rescore_topk_kernel       exact canonical fp32 score of each candidate, then exact top-K.
 //   5. a query whose list overflowed is redone by the exact CUDA-core kernel (tt_index.cu), on the device.
 //
-// Why it is exact: K groups have a maximum >= tau, so K corpus rows have exact score >= tau - eps; hence
-// the exact K-th best score s_K >= tau - eps, every true top-K row has s >= s_K, i.e. a >= tau - 2 eps = thr,
-// and is therefore collected; step 4 orders the collected rows by the exact (score desc, index asc) rule.
-// eps_q = 2^-9 * ||q||_2 * max_j ||c_j||_2 bounds TF32 operand rounding (2^-11 each, Cauchy-Schwarz) plus the
-// fp32 accumulation error of both evaluations with a 2x margin.
+// Why it is exact: |a_ij - s_ij| <= eps_ij (TF32 operand rounding 2^-11 each and Cauchy-Schwarz, plus the fp32
+// accumulation error of both evaluations, with a 2x margin).  K groups hold a row with s >= a - eps >= lambda,
+// so the exact K-th best score s_K >= lambda; every true top-K row has s >= s_K, hence a + eps >= lambda, and is
+// collected; step 4 orders the collected rows by the exact (score desc, index asc) rule.
 #include "tt_tc_rowpanel.cuh"
 
 namespace tt {
@@ -49,9 +48,38 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
     return __uint_as_float(b);
 }
 
-// Q32 = tf32_rn(Q); eps[q] = kEpsCoef * ||q|| * cmax.  One warp per query row.
-__global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ Q, int ldq, int nq, int E, const float* __restrict__ cmax,
-                                                           float* __restrict__ Q32, float* __restrict__ eps) {
+// The filter's group statistics assume the best rows are spread over many groups of 32.  Vocabularies are
+// ordered by frequency (features.py:119-127), so popular -- and, once trained, high-scoring -- candidates sit
+// next to each other; the prepared copy therefore stores the corpus under the fixed affine permutation
+// pos = (orig * A) mod n, orig = (pos * Ainv) mod n, with A ~ 0.618 n coprime to n (a low-discrepancy spread of
+// any run of consecutive rows).  Candidate lists hold permuted positions; rescoring maps them back.
+struct Perm {
+    unsigned long long n, a, a_inv;
+};
+static unsigned long long gcd_u64(unsigned long long x, unsigned long long y) { while (y) { unsigned long long t = x % y; x = y; y = t; } return x; }
+static Perm make_perm(int64_t n) {
+    Perm pm;
+    pm.n = (unsigned long long)n;
+    if (n <= 2) { pm.a = 1; pm.a_inv = 1; return pm; }
+    unsigned long long a = (unsigned long long)((double)n * 0.6180339887498949) | 1ull;
+    while (a >= pm.n || gcd_u64(a, pm.n) != 1) { a += 2; if (a >= pm.n) a = 1; }
+    // modular inverse by the extended Euclid algorithm (signed 128-bit free: values stay below n < 2^31)
+    long long t = 0, nt = 1, r = (long long)pm.n, nr = (long long)a;
+    while (nr != 0) {
+        long long qq = r / nr;
+        long long tmp = t - qq * nt; t = nt; nt = tmp;
+        tmp = r - qq * nr; r = nr; nr = tmp;
+    }
+    if (t < 0) t += (long long)pm.n;
+    pm.a = a;
+    pm.a_inv = (unsigned long long)t;
+    return pm;
+}
+__device__ __forceinline__ int64_t perm_orig(const Perm& pm, int64_t pos) { return (int64_t)(((unsigned long long)pos * pm.a_inv) % pm.n); }
+
+// Q32 = tf32_rn(Q); kappa[q] = kEpsCoef * ||q||.  One warp per query row.
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ Q, int ldq, int nq, int E, float* __restrict__ Q32,
+                                                           float* __restrict__ eps) {
     const int lane = threadIdx.x & 31;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq) return;
@@ -62,13 +90,12 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
         s = fmaf(v, v, s);
     }
     s = warp_sum(s);
-    if (lane == 0) eps[q] = kEpsCoef * sqrtf(s) * cmax[0] * 1.0001f + 1e-30f;
+    if (lane == 0) eps[q] = kEpsCoef * sqrtf(s) * 1.0001f + 1e-30f;
 }
 
-// One CTA per query: tau = K-th largest of gmax[q][0..ngroups) by 4-pass MSB radix select; thr = tau - 2 eps.
+// One CTA per query: lambda = K-th largest of gmax[q][0..ngroups) by a 4-pass MSB radix select.
 __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __restrict__ gmax, int ld, int ngroups, int K,
-                                                               const float* __restrict__ eps, float* __restrict__ thr, int32_t* __restrict__ cnt,
-                                                               int32_t* __restrict__ flags) {
+                                                               float* __restrict__ thr, int32_t* __restrict__ cnt, int32_t* __restrict__ flags) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_remaining;
     const int q = blockIdx.x;
@@ -106,28 +133,43 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __re
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t cum = 0;
-            int b = 255;
-            for (; b > 0; --b) {
-                if (cum + hist[b] >= remaining) break;
-                cum += hist[b];
+        if (threadIdx.x < 32) {   // warp 0: find the bin holding the `remaining`-th largest key (suffix scan over 256 bins)
+            const int lane = threadIdx.x;
+            uint32_t c[8], tot = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; tot += c[i]; }
+            uint32_t above = 0;   // keys in bins of higher lanes
+            uint32_t run = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_down_sync(0xffffffffu, run, o);
+                if (lane + o < 32) run += v;
             }
-            s_prefix = prefix | ((uint32_t)b << shift);
-            s_remaining = remaining - cum;
+            above = run - tot;    // run = inclusive suffix sum over lanes >= lane
+            const bool mine = above < remaining && remaining <= above + tot;
+            if (mine) {
+                uint32_t cum = above;
+                int b = 7;
+                for (; b > 0; --b) {
+                    if (cum + c[b] >= remaining) break;
+                    cum += c[b];
+                }
+                s_prefix = prefix | ((uint32_t)(lane * 8 + b) << shift);
+                s_remaining = remaining - cum;
+            }
         }
         __syncthreads();
         prefix = s_prefix;
         remaining = s_remaining;
         mask |= 255u << shift;
     }
-    if (threadIdx.x == 0) thr[q] = key_to_float(prefix) - 2.0f * eps[q];
+    if (threadIdx.x == 0) thr[q] = key_to_float(prefix);
 }
 
 // One CTA per query: exact canonical score of every collected candidate, then exact top-K (bitonic sort in smem).
 __global__ void __launch_bounds__(256) rescore_topk_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ C, int ldc, int E, int K,
                                                            const int32_t* __restrict__ cand, const int32_t* __restrict__ cnt, int cap, int P,
-                                                           int64_t idx_base, float* __restrict__ out_s, int32_t* __restrict__ out_i,
+                                                           Perm pm, int64_t idx_base, float* __restrict__ out_s, int32_t* __restrict__ out_i,
                                                            int32_t* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sq = reinterpret_cast<float*>(smem_raw);          // E
@@ -145,7 +187,7 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(const float* __restri
         float s = -CUDART_INF_F;
         int32_t id = 0x7fffffff;
         if (t < m) {
-            id = cand[(int64_t)q * cap + t];
+            id = (int32_t)perm_orig(pm, cand[(int64_t)q * cap + t]);   // permuted position -> original corpus row
             const float4* row = reinterpret_cast<const float4*>(C + (int64_t)id * ldc);
             float acc = 0.f;
             for (int k4 = 0; k4 < E / 4; ++k4) {   // canonical order: k ascending, one fmaf per term
@@ -182,29 +224,33 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(const float* __restri
     }
 }
 
-__global__ void round_rows_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int64_t rows, int E) {
-    int64_t total = rows * E;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-        int64_t r = i / E;
-        int c = (int)(i % E);
-        dst[i] = tf32_rn(src[r * lds + c]);
-    }
-}
-
-__global__ void max_norm_kernel(const float* __restrict__ C, int ldc, int64_t n, int E, float* __restrict__ out) {
+// C32p[pos][:] = tf32_rn(C[orig(pos)][:]); norms[pos] = ||C[orig(pos)]|| (rounded up a hair); norms[n..n_pad) = 0.
+__global__ void __launch_bounds__(256) prepare_corpus_kernel(const float* __restrict__ C, int ldc, int64_t n, int E, Perm pm,
+                                                             float* __restrict__ C32p, float* __restrict__ norms, int64_t n_pad) {
     int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float best = 0.f;
-    for (int64_t r = warp; r < n; r += nwarps) {
+    for (int64_t pos = warp; pos < n_pad; pos += nwarps) {
         float s = 0.f;
-        for (int k = lane; k < E; k += 32) { float v = C[r * ldc + k]; s = fmaf(v, v, s); }
+        if (pos < n) {
+            const int64_t o = perm_orig(pm, pos);
+            for (int k = lane; k < E; k += 32) {
+                float v = C[o * ldc + k];
+                C32p[pos * E + k] = tf32_rn(v);
+                s = fmaf(v, v, s);
+            }
+        }
         s = warp_sum(s);
-        best = fmaxf(best, sqrtf(s));
+        if (lane == 0) norms[pos] = pos < n ? sqrtf(s) * 1.0001f : 0.f;
     }
-    best = warp_max(best);
-    if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(best));
+}
+
+int launch_prepare(const float* C, int ldc, int64_t n, int E, float* C32p, float* norms, int64_t n_pad, cudaStream_t st) {
+    int64_t g = ceil_div(n_pad * 32, 256);
+    int64_t cap = (int64_t)sm_count() * 16;
+    prepare_corpus_kernel<<<(unsigned)(g > cap ? cap : (g < 1 ? 1 : g)), 256, 0, st>>>(C, ldc, n, E, make_perm(n), C32p, norms, n_pad);
+    TT_LAUNCH_OK("prepare_corpus_kernel");
+    return TT_OK;
 }
 
 template <int MODE, int E>
@@ -234,7 +280,7 @@ static int launch_idx_e(int E, const CUtensorMap& tmQ, const CUtensorMap& tmC, c
 }
 
 struct IdxLayout {
-    size_t q32, eps, thr, gmax, cnt, flags, cand, c32, cmax, exact, total;
+    size_t q32, eps, thr, gmax, cnt, flags, cand, c32, norms, exact, total;
     int ngroups, n_tiles, cap;
 };
 
@@ -253,7 +299,7 @@ static IdxLayout layout(int nq, int64_t n, int E, int K, bool need_corpus_copy) 
     L.flags = take((size_t)nq * 4);
     L.cand = take((size_t)nq * L.cap * 4);
     L.c32 = take(need_corpus_copy ? (size_t)n * E * 4 : 0);
-    L.cmax = take(256);
+    L.norms = take(need_corpus_copy ? ((size_t)L.n_tiles * idx_bn(E) + 256) * 4 : 0);
     L.exact = off;
     L.total = off;
     return L;
@@ -278,8 +324,10 @@ size_t index_tc_workspace(int nq, int64_t n, int E, int K, bool need_corpus_copy
 
 void debug_index_cap(int cap) { tc::g_cap_override = cap; }
 
-int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_in, const float* cmax_in, int nq, int64_t n, int E, int K,
+int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_in, const float* norms_in, int nq, int64_t n, int E, int K,
              int64_t idx_base, float* out_s, int32_t* out_i, void* ws, size_t ws_bytes, cudaStream_t st) {
+    TT_REQUIRE((C32_in == nullptr) == (norms_in == nullptr), "tt_index_topk: corpus_prepared and corpus_norms must be given together");
+    TT_REQUIRE(C32_in == nullptr || (reinterpret_cast<uintptr_t>(C32_in) & 15) == 0, "tt_index_topk: corpus_prepared must be 16-byte aligned");
     const bool need_copy = (C32_in == nullptr);
     IdxLayout L = layout(nq, n, E, K, need_copy);
     const size_t exact_bytes = index_exact_workspace(nq, n, K);
@@ -292,45 +340,34 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
     int32_t* cnt = reinterpret_cast<int32_t*>(base + L.cnt);
     int32_t* flags = reinterpret_cast<int32_t*>(base + L.flags);
     int32_t* cand = reinterpret_cast<int32_t*>(base + L.cand);
-    float* cmax = reinterpret_cast<float*>(base + L.cmax);
     const float* c32 = C32_in;
+    const float* norms = norms_in;
     if (need_copy) {
         float* dst = reinterpret_cast<float*>(base + L.c32);
-        int64_t total = n * E;
-        int64_t g = ceil_div(total, 256 * 4);
-        int64_t cap = (int64_t)sm_count() * 16;
-        round_rows_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(C, ldc, dst, n, E);
-        TT_LAUNCH_OK("round_rows_kernel");
+        float* nd = reinterpret_cast<float*>(base + L.norms);
+        int rcn = launch_prepare(C, ldc, n, E, dst, nd, (int64_t)L.n_tiles * idx_bn(E), st);
+        if (rcn) return rcn;
         c32 = dst;
+        norms = nd;
     }
-    const float* cm = cmax_in;
-    if (!cm) {
-        TT_CUDA_OK(cudaMemsetAsync(cmax, 0, sizeof(float), st));
-        int64_t g = ceil_div(n * 32, 256);
-        int64_t cap = (int64_t)sm_count() * 8;
-        max_norm_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(C, ldc, n, E, cmax);
-        TT_LAUNCH_OK("max_norm_kernel");
-        cm = cmax;
-    }
-    prep_queries_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, st>>>(Q, ldq, nq, E, cm, q32, eps);
+    prep_queries_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, st>>>(Q, ldq, nq, E, q32, eps);
     TT_LAUNCH_OK("prep_queries_kernel");
 
     CUtensorMap tmQ, tmC;
     int rc = make_tmap_2d(&tmQ, q32, nq, E, E, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmC, c32, n, E, need_copy ? E : ldc, idx_bn(E));
+    rc = make_tmap_2d(&tmC, c32, n, E, E, idx_bn(E));   // the prepared copy is dense (ld = E)
     if (rc) return rc;
     const int m_tiles = (int)ceil_div(nq, 128);
     int splits = 1, tps = L.n_tiles;
     choose_splits(m_tiles, L.n_tiles, 2, 64, &splits, &tps);
     RowPanelParams p{};
-    p.nR = nq; p.nT = (int)n; p.n_tiles = L.n_tiles; p.tiles_per_split = tps; p.rowv = nullptr; p.colv2 = nullptr; p.d = -(1 << 30);
+    p.nR = nq; p.nT = (int)n; p.n_tiles = L.n_tiles; p.tiles_per_split = tps; p.rowv = eps; p.rowv2 = thr; p.colv2 = norms; p.d = -(1 << 30);
     p.out0 = gmax; p.out1 = nullptr; p.out2 = nullptr; p.ld_out = L.ngroups; p.trace = nullptr;
     rc = launch_idx_e<kIndex>(E, tmQ, tmC, p, m_tiles, splits, st, "rowpanel_kernel<index>");
     if (rc) return rc;
-    select_threshold_kernel<<<(unsigned)nq, 256, 0, st>>>(gmax, L.ngroups, (int)ceil_div(n, kGroup), K, eps, thr, cnt, flags);
+    select_threshold_kernel<<<(unsigned)nq, 256, 0, st>>>(gmax, L.ngroups, (int)ceil_div(n, kGroup), K, thr, cnt, flags);
     TT_LAUNCH_OK("select_threshold_kernel");
-    p.rowv = thr;
     p.out0 = reinterpret_cast<float*>(cand);
     p.out1 = reinterpret_cast<float*>(cnt);
     p.ld_out = L.cap;
@@ -343,7 +380,7 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
         TT_CUDA_OK(cudaFuncSetAttribute(rescore_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    rescore_topk_kernel<<<(unsigned)nq, 256, smem, st>>>(Q, ldq, C, ldc, E, K, cand, cnt, L.cap, P, idx_base, out_s, out_i, flags);
+    rescore_topk_kernel<<<(unsigned)nq, 256, smem, st>>>(Q, ldq, C, ldc, E, K, cand, cnt, L.cap, P, make_perm(n), idx_base, out_s, out_i, flags);
     TT_LAUNCH_OK("rescore_topk_kernel");
     // queries whose candidate list overflowed: exact CUDA-core path, decided on the device (no host sync)
     return index_exact(Q, ldq, C, ldc, nq, n, E, K, idx_base, out_s, out_i, base + L.exact, exact_bytes, st, flags);

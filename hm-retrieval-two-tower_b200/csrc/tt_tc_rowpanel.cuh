@@ -36,7 +36,8 @@ struct RowPanelParams {
     int nR, nT;
     int n_tiles;          // ceil(nT / BN)
     int tiles_per_split;  // tiles handled by one blockIdx.y
-    const float* rowv;    // kBwd: per-R-row term (lse or ln p), natural units | kCollect: per-row score threshold
+    const float* rowv;    // kBwd: per-R-row term (lse or ln p), natural units | kIndex/kCollect: kappa_q = c*||q||
+    const float* rowv2;   // kCollect: per-row threshold lambda_q
     const float* colv2;   // per-T-row term * log2(e), padded with zeros to n_tiles*BN entries (never null)
     int d;                // diagonal: column == row + d
     float* out0;          // kFwd: m2 [split][nR] | kBwd: G partial [split][nR][E] | kLogits: Z | kIndex: gmax [nR][ld_out]
@@ -112,8 +113,8 @@ struct RowPanelCfg {
     static constexpr int kPSlabs = BN / 32;
     static constexpr int kPBytes = (MODE == kBwd) ? kPSlabs * 128 * 128 : 0;
     static constexpr int kPBufs = (MODE == kBwd) ? 2 : 0;
-    static constexpr bool kUsesC2 = (MODE == kFwd || MODE == kBwd || MODE == kLogits);
-    static constexpr int kC2Bytes = kUsesC2 ? BN * 4 : 0;                    // staged column term per stage
+    static constexpr bool kUsesC2 = true;                                    // every mode stages a per-column vector
+    static constexpr int kC2Bytes = BN * 4;                                  // (softmax: colv*log2e, index: row norms)
     static constexpr int kHalves = (BN / 32 >= 2) ? 2 : 1;                   // epilogue warps per TMEM lane quarter
     static constexpr int kEpiWarps = 4 * kHalves;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
@@ -321,7 +322,9 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         bool has_diag = false;
         float r2 = 0.f;
         if (MODE == kBwd) r2 = (row < p.nR && p.rowv) ? __ldg(p.rowv + row) * kLog2e : 0.f;
-        if (MODE == kCollect) r2 = (row < p.nR) ? __ldg(p.rowv + row) : CUDART_INF_F;   // threshold (natural units)
+        float r3 = CUDART_INF_F;
+        if (MODE == kIndex || MODE == kCollect) r2 = (row < p.nR) ? __ldg(p.rowv + row) : 0.f;      // kappa_q
+        if (MODE == kCollect) r3 = (row < p.nR) ? __ldg(p.rowv2 + row) : CUDART_INF_F;              // lambda_q
         constexpr int NC = BN / 32;
         constexpr int NCW = NC / Cfg::kHalves;        // 32-column chunks per warp per tile
         const int c_first = half * NCW;
@@ -371,28 +374,47 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                         }
                     }
                 } else if constexpr (MODE == kCollect) {
+                    // upper bounds U_j = a_j + kappa_q*||c_j|| >= s_j; collect every j with U_j >= lambda_q
+                    float u[32];
                     float mx = -CUDART_INF_F;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                    if (mx >= r2) {   // rare: some column of this chunk reaches the row's threshold
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 cc = lds128(c2s + c * 128 + g4 * 16);
+                        u[g4 * 4] = fmaf(r2, cc.x, __uint_as_float(r[g4 * 4]));
+                        u[g4 * 4 + 1] = fmaf(r2, cc.y, __uint_as_float(r[g4 * 4 + 1]));
+                        u[g4 * 4 + 2] = fmaf(r2, cc.z, __uint_as_float(r[g4 * 4 + 2]));
+                        u[g4 * 4 + 3] = fmaf(r2, cc.w, __uint_as_float(r[g4 * 4 + 3]));
+                        mx = fmaxf(fmaxf(mx, fmaxf(u[g4 * 4], u[g4 * 4 + 1])), fmaxf(u[g4 * 4 + 2], u[g4 * 4 + 3]));
+                    }
+                    if (mx >= r3) {   // rare: some column of this chunk reaches the row's threshold
                         int32_t* lists = reinterpret_cast<int32_t*>(p.out0);
                         int32_t* lens = reinterpret_cast<int32_t*>(p.out1);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            if (__uint_as_float(r[i]) >= r2 && nb + i < p.nT) {
+                            if (u[i] >= r3 && nb + i < p.nT) {
                                 const int slot = atomicAdd(lens + row, 1);
                                 if (slot < p.ld_out) lists[(int64_t)row * p.ld_out + slot] = nb + i;
                             }
                         }
                     }
-                } else {  // kIndex
+                } else {  // kIndex: group maximum of the lower bounds L_j = a_j - kappa_q*||c_j|| <= s_j
                     float mx = -CUDART_INF_F;
-                    if (fast || nb + 32 <= p.nT) {
+                    const bool whole = fast || nb + 32 <= p.nT;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (nb + i < p.nT) ? __uint_as_float(r[i]) : -CUDART_INF_F);
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 cc = lds128(c2s + c * 128 + g4 * 16);
+                        float l0 = fmaf(-r2, cc.x, __uint_as_float(r[g4 * 4]));
+                        float l1 = fmaf(-r2, cc.y, __uint_as_float(r[g4 * 4 + 1]));
+                        float l2 = fmaf(-r2, cc.z, __uint_as_float(r[g4 * 4 + 2]));
+                        float l3 = fmaf(-r2, cc.w, __uint_as_float(r[g4 * 4 + 3]));
+                        if (!whole) {
+                            const int n = nb + g4 * 4;
+                            if (n >= p.nT) l0 = -CUDART_INF_F;
+                            if (n + 1 >= p.nT) l1 = -CUDART_INF_F;
+                            if (n + 2 >= p.nT) l2 = -CUDART_INF_F;
+                            if (n + 3 >= p.nT) l3 = -CUDART_INF_F;
+                        }
+                        mx = fmaxf(fmaxf(mx, fmaxf(l0, l1)), fmaxf(l2, l3));
                     }
                     gm[cl] = mx;
                 }

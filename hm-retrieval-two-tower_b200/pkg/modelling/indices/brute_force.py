@@ -52,17 +52,17 @@ class BruteForceIndex(AbstractKerasModel):
         self.n_total = n_total
         self._identifiers = identifiers                       # all ids (host), position == global row index
         self._candidates = candidates.contiguous()            # (N_local, E) fp32, non-trainable
-        # operand preparation for the tensor-core filter, done once at build time: TF32-rounded copy of the
-        # corpus and the largest row norm (error bound of the filter); the exact fp32 rows stay authoritative
+        # operand preparation for the tensor-core filter, done once at build time: permuted TF32-rounded copy of
+        # the corpus and the row norms (error bound of the filter); the exact fp32 rows stay authoritative
         lib = N.load()
         n_loc, e = self._candidates.shape
         self._candidates_tf32, self._max_norm = None, None
         if n_loc > 0 and lib.tt_tc_available(1, e):
             self._candidates_tf32 = torch.empty_like(self._candidates)
-            self._max_norm = torch.zeros(1, dtype=torch.float32, device="cuda")
-            st = N.stream_ptr()
-            N.check(lib.tt_round_tf32(self._candidates.data_ptr(), e, self._candidates_tf32.data_ptr(), e, n_loc, e, st), "tt_round_tf32")
-            N.check(lib.tt_corpus_max_norm(self._candidates.data_ptr(), e, n_loc, e, self._max_norm.data_ptr(), st), "tt_corpus_max_norm")
+            n_pad = ((n_loc + 255) // 256 + 1) * 256             # TT_INDEX_NORM_PAD
+            self._max_norm = torch.zeros(n_pad, dtype=torch.float32, device="cuda")   # per-row norms, zero padded
+            N.check(lib.tt_index_prepare(self._candidates.data_ptr(), e, n_loc, e, self._candidates_tf32.data_ptr(),
+                                         self._max_norm.data_ptr(), N.stream_ptr()), "tt_index_prepare")
         if self.k > n_total:
             raise ValueError(f"k={self.k} exceeds the number of candidates ({n_total})")
 

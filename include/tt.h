@@ -160,15 +160,20 @@ int tt_sparse_adam(const tt_sparse_job* jobs, int njobs, float lr_t, float beta1
  * row-sharded corpus).  The (nq, n) score matrix never reaches HBM.
  * Scores returned are the canonical fp32 values (k-ascending fmaf), bit-exact against the oracle.
  * ---------------------------------------------------------------------------------------------- */
-/* corpus_tf32 (optional, same ld as corpus): round-to-nearest TF32 copy of the corpus kept by the caller
- * (tt_round_tf32 at index-build time); corpus_max_norm (optional): device float from tt_corpus_max_norm.
- * When NULL they are recomputed into the workspace on every call (pass have_corpus_tf32 = 0 when sizing). */
-size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl, int have_corpus_tf32);
-int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const float* corpus_tf32,
-                  const float* corpus_max_norm, int nq, int64_t n, int E, int K, int64_t idx_base, float* out_scores,
+/* Operand preparation for the tensor-core filter, done once at index-build time (tt_index_prepare) and passed
+ * to every query call:
+ *   corpus_prepared  (n, E) dense: TF32-rounded rows stored under a fixed pseudo-random permutation (so that
+ *                    neighbouring -- e.g. equally popular -- rows do not share a filter group);
+ *   corpus_norms     ||row||_2 in the same order, zero padded to TT_INDEX_NORM_PAD(n) floats.
+ * Pass both or neither; when NULL they are rebuilt in the workspace on every call (size the workspace with
+ * have_corpus_prepared = 0).  The exact fp32 `corpus` stays authoritative: results never depend on the copy. */
+#define TT_INDEX_NORM_PAD(n) ((((n) + 255) / 256 + 1) * 256)
+int tt_index_prepare(const float* corpus, int ldc, int64_t n, int E, float* corpus_prepared, float* corpus_norms,
+                     void* stream);
+size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl, int have_corpus_prepared);
+int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const float* corpus_prepared,
+                  const float* corpus_norms, int nq, int64_t n, int E, int K, int64_t idx_base, float* out_scores,
                   int32_t* out_idx, void* ws, size_t ws_bytes, int impl, void* stream);
-/* max_j ||corpus_j||_2 (used by the tensor-core filter's error bound); result is one float. */
-int tt_corpus_max_norm(const float* corpus, int ldc, int64_t n, int E, float* out, void* stream);
 /* Round-to-nearest TF32 copy of a matrix (operand preparation for TT_IMPL_TC). */
 int tt_round_tf32(const float* src, int lds, float* dst, int ldd, int64_t rows, int cols, void* stream);
 

@@ -172,9 +172,9 @@ def _index_tc(lib, T, q, c, K, idx_base=0, prepared=False):
     nq, n, E = q.shape[0], c.shape[0], q.shape[1]
     c32 = mx = None
     if prepared:   # what BruteForceIndex does once at build time
-        c32 = T.empty_like(dc); mx = T.zeros(1, dtype=T.float32, device="cuda")
-        N.check(lib.tt_round_tf32(dc.data_ptr(), E, c32.data_ptr(), E, n, E, stream()))
-        N.check(lib.tt_corpus_max_norm(dc.data_ptr(), E, n, E, mx.data_ptr(), stream()))
+        n_pad = ((n + 255) // 256 + 1) * 256
+        c32 = T.empty_like(dc); mx = T.full((n_pad,), 9.0, dtype=T.float32, device="cuda")
+        N.check(lib.tt_index_prepare(dc.data_ptr(), E, n, E, c32.data_ptr(), mx.data_ptr(), stream()))
     s = T.empty((nq, K), dtype=T.float32, device="cuda"); i = T.empty((nq, K), dtype=T.int32, device="cuda")
     ws = T.empty(int(lib.tt_index_workspace_bytes(nq, n, E, K, TC, 1 if prepared else 0)), dtype=T.uint8, device="cuda")
     N.check(lib.tt_index_topk(dq.data_ptr(), E, dc.data_ptr(), E, c32.data_ptr() if prepared else None, mx.data_ptr() if prepared else None,
