@@ -317,8 +317,8 @@ def run_ours(args):
 
     if rank == 0:
         line["roofline"] = softmax_roofline(model, B, pk, lib)
+    line["index"] = index_bench(model, pk, lib, K, world)      # every rank takes part (row-sharded corpus when N > 1)
     if world == 1:
-        line["index"] = index_bench(model, pk, lib, K)
         if not args.no_cpu:
             rate, sec, cores = cpu_train_rate(B, 2, args.cpu_steps)
             line["cpu_baseline"] = {"value": rate, "unit": "examples/s", "cores": cores, "kind": "port",
@@ -370,12 +370,14 @@ def softmax_roofline(model, B, pk, lib):
             "ms": sec * 1e3, "algorithmic_flop": flops, "peak_source": pk["source"] + ", dense bf16 burst (kernel timed alone)"}
 
 
-def index_bench(model, pk, lib, steps):
-    """Index half of the metric: N=105 542 candidate-tower outputs, E=64, top-100, 2048 queries per batch."""
+def index_bench(model, pk, lib, steps, world=1):
+    """Index half of the metric: N=105 542 candidate-tower outputs, E=64, top-100, 2048 queries per batch.
+    With N > 1 ranks the corpus is sharded row-wise and per-shard top-K lists are all-gathered and merged."""
     import torch
 
     from pkg import _native as N
     from pkg.modelling.indices.brute_force import BruteForceIndex
+    from pkg.modelling.distributed import make_sharded_index
 
     art = np.arange(1, V_ARTICLES + 1, dtype=np.int32)
     pairs = []
@@ -383,7 +385,7 @@ def index_bench(model, pk, lib, steps):
         a = art[lo:lo + 10000]
         x = {"article_id": a.reshape(-1, 1), "product_type_name": (a % V_PTYPE + 1).reshape(-1, 1), "colour_group_name": (a % V_COLOUR + 1).reshape(-1, 1)}
         pairs.append((a, model.candidate_tower(x)))
-    index = BruteForceIndex(INDEX_K, model.query_tower, pairs)
+    index = make_sharded_index(INDEX_K, model.query_tower, pairs) if world > 1 else BruteForceIndex(INDEX_K, model.query_tower, pairs)
     index.impl = model.impl
     rng = np.random.default_rng(77)
     pool = 4
@@ -423,7 +425,8 @@ def index_bench(model, pk, lib, steps):
     ach = flops / ksec / 1e12
     return {"metric": "index queries/s (top-100, 105k items)", "value": INDEX_BQ / sec, "unit": "queries/s", "ms_per_batch": sec * 1e3,
             "e2e": {"value": INDEX_BQ / e2e_sec, "unit": "queries/s", "h2d_bytes_per_step": INDEX_BQ * 8, "d2h_bytes_per_step": INDEX_BQ * INDEX_K * 4},
-            "config": f"N={V_ARTICLES} candidate-tower rows, E={JOINT}, K={INDEX_K}, Bq={INDEX_BQ}; corpus 27 MB is L2-resident (stated)",
+            "config": f"N={V_ARTICLES} candidate-tower rows, E={JOINT}, K={INDEX_K}, Bq={INDEX_BQ}; corpus 27 MB is L2-resident (stated); "
+                      + (f"row-sharded over {world} GPUs, NCCL all-gather + on-device merge" if world > 1 else "single shard"),
             "gpu_launches_per_batch": per_call,
             "roofline": {"bound": "tensor", "kernel": "index scoring + top-K", "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
                          "frac": ach / pk["tflops_burst"], "traffic": None, "ms": ksec * 1e3, "algorithmic_flop": flops},

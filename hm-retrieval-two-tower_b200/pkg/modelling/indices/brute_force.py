@@ -100,6 +100,10 @@ class BruteForceIndex(AbstractKerasModel):
         if n == 0 or nq == 0:
             scores.fill_(float("-inf"))
             idx.fill_(-1)
+            if getattr(self, "_world", 1) > 1 and nq > 0:
+                from pkg.modelling.distributed import merge_shard_results
+
+                scores, idx = merge_shard_results(scores, idx, k, getattr(self, "_group", None))
             return scores, idx
         have32 = self._candidates_tf32 is not None
         need = int(lib.tt_index_workspace_bytes(nq, n, e, k, self.impl, 1 if have32 else 0))
@@ -109,6 +113,10 @@ class BruteForceIndex(AbstractKerasModel):
                                   self._candidates_tf32.data_ptr() if have32 else None, self._max_norm.data_ptr() if have32 else None,
                                   nq, n, e, k, self.idx_base, scores.data_ptr(), idx.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                                   self.impl, N.stream_ptr()), "tt_index_topk")
+        if getattr(self, "_world", 1) > 1:   # row-sharded corpus: merge the per-shard lists (identical on every rank)
+            from pkg.modelling.distributed import merge_shard_results
+
+            scores, idx = merge_shard_results(scores, idx, k, getattr(self, "_group", None))
         return scores, idx
 
     def query_indices(self, queries, k: Optional[int] = None):

@@ -175,11 +175,12 @@ class TwoTowerModel(AbstractKerasModel):
         torch = N.require_cuda()
         lib = N.load()
         srcs = []
-        for tower, tws in ((self.query_tower, sw.q), (self.candidate_tower, sw.c)):
-            for name, (table, lst) in tower.sparse_sources(tws).items():
-                srcs.append((table, lst))
-        if self.dist is not None:
-            srcs = self.dist.wrap_sparse_sources(self, sw, srcs)
+        if self.dist is not None:   # data parallel: sources are the all-gathered (ids, gradient rows) of every rank
+            srcs = self.dist.build_sparse_sources(self, sw)
+        else:
+            for tower, tws in ((self.query_tower, sw.q), (self.candidate_tower, sw.c)):
+                for name, (table, lst) in tower.sparse_sources(tws).items():
+                    srcs.append((table, lst))
         if len(srcs) > N.TT_MAX_JOBS:
             raise ValueError(f"at most {N.TT_MAX_JOBS} embedding tables per model")
         jobs = (N.TTSparseJob * len(srcs))()

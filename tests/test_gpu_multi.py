@@ -1,0 +1,125 @@
+"""2-GPU NCCL tests of data-parallel training and the sharded index (skipped with fewer than 2 GPUs)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _features():
+    from pkg.schema import dtypes as tt
+    from pkg.schema.features import Feature, FeatureFamily
+
+    qf = [Feature("age", tt.float32, FeatureFamily.QUERY), Feature("customer_id", tt.string, FeatureFamily.QUERY, embedding_size=32)]
+    cf = [Feature("article_id", tt.string, FeatureFamily.CANDIDATE, embedding_size=32),
+          Feature("colour_group_name", tt.string, FeatureFamily.CANDIDATE, embedding_size=8)]
+    qf[1].set_vocab_size(600); cf[0].set_vocab_size(300); cf[1].set_vocab_size(50)
+    return qf, cf
+
+
+def _batch(rng, b):
+    art = np.minimum(rng.zipf(1.3, size=b), 300).astype(np.int32)
+    return {"age": rng.random((b, 1)).astype(np.float32), "customer_id": rng.integers(0, 601, size=(b, 1)).astype(np.int32),
+            "article_id": art.reshape(b, 1), "colour_group_name": (art % 50 + 1).reshape(b, 1).astype(np.int32)}
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "hm-retrieval-two-tower_b200"))
+    import torch
+    import torch.distributed as dist
+
+    from pkg import _native as N
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.distributed import DataParallel, make_sharded_index
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        set_seed(17)
+        qf, cf = _features()
+        model = TwoTowerModel(qf, cf, "article_id", 32, candidate_prob_lookup={str(i + 1): 1.0 / 300 for i in range(300)})
+        model.impl = N.TT_IMPL_SIMT
+        model.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))
+        before = {k: v.copy() for k, v in model.state_arrays().items()}
+        DataParallel(model)
+        rng = np.random.default_rng(100)
+        batches = [_batch(rng, 96) for _ in range(world)]
+        loss = float(model.train_step(batches[rank])["loss"])
+        after = model.state_arrays()
+        # sharded index over the (now trained) candidate tower
+        art = np.arange(1, 301, dtype=np.int32)
+        emb = model.candidate_tower({"article_id": art.reshape(-1, 1), "colour_group_name": (art % 50 + 1).reshape(-1, 1)})
+        index = make_sharded_index(10, model.query_tower, [(art, emb)])
+        q = {"age": np.linspace(0, 1, 40, dtype=np.float32).reshape(-1, 1), "customer_id": np.arange(40, dtype=np.int32).reshape(-1, 1)}
+        ids = index(q)
+        q_emb = model.query_tower(q).cpu().numpy()
+        np.savez(out, loss=loss, ids=ids, q_emb=q_emb, c_emb=emb.cpu().numpy(), **{"before/" + k: v for k, v in before.items()},
+                 **{"after/" + k: v for k, v in after.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_data_parallel_step_and_sharded_index_on_two_gpus(tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from oracle import two_tower_oracle as O
+
+    world, port = 2, _free_port()
+    outs = [str(tmp_path / f"r{r}.npz") for r in range(world)]
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_worker, args=(r, world, port, outs[r])) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(280)
+        assert p.exitcode == 0
+    res = [np.load(o) for o in outs]
+    keys = [k for k in res[0].files if k.startswith("after/")]
+    for k in keys:                                     # replicas stay bit-identical
+        assert np.array_equal(res[0][k], res[1][k]), k
+    assert np.array_equal(res[0]["ids"], res[1]["ids"])
+    # oracle: G batches at the same weights, gradients summed, one Adagrad apply
+    b = {k[len("before/"):]: res[0][k] for k in res[0].files if k.startswith("before/")}
+    qt = O.OracleTower([O.OracleFeature("age", False), O.OracleFeature("customer_id", True, 32)],
+                       {"customer_id": b["query_tower/embedding/customer_id"].copy()},
+                       [(b["query_tower/dense_0/kernel"].copy(), b["query_tower/dense_0/bias"].copy())])
+    ct = O.OracleTower([O.OracleFeature("article_id", True, 32), O.OracleFeature("colour_group_name", True, 8)],
+                       {"article_id": b["candidate_tower/embedding/article_id"].copy(), "colour_group_name": b["candidate_tower/embedding/colour_group_name"].copy()},
+                       [(b["candidate_tower/dense_0/kernel"].copy(), b["candidate_tower/dense_0/bias"].copy())])
+    rng = np.random.default_rng(100)
+    batches = [_batch(rng, 96) for _ in range(world)]
+    p_rows = np.ones(301, np.float32); p_rows[1:] = np.float32(1.0 / 300)
+    gs = [O.train_step_grads(qt, ct, {"customer_id": bt["customer_id"]}, {"age": bt["age"]},
+                             {"article_id": bt["article_id"], "colour_group_name": bt["colour_group_name"]}, {},
+                             p_rows[bt["article_id"].reshape(-1)]) for bt in batches]
+    for r in range(world):
+        assert abs(float(res[r]["loss"]) - gs[r].loss) <= 1e-5 * abs(gs[r].loss)
+    dw = sum(g.dense_c[0][0] for g in gs); w = ct.dense[0][0].copy(); aw = np.full_like(w, 0.1)
+    O.adagrad_dense(w, aw, dw, 0.05)
+    np.testing.assert_allclose(res[0]["after/candidate_tower/dense_0/kernel"], w, rtol=0, atol=2e-4)
+    ids = np.concatenate([g.tables_c["article_id"].indices for g in gs]); rows = np.concatenate([g.tables_c["article_id"].values for g in gs])
+    t = ct.tables["article_id"].copy(); acc = np.full_like(t, 0.1)
+    O.adagrad_sparse(t, acc, O.IndexedSlices(ids, rows), 0.05)
+    np.testing.assert_allclose(res[0]["after/candidate_tower/embedding/article_id"], t, rtol=0, atol=2e-4)
+    # sharded index == unsharded oracle, bit-exact ids
+    _, want = O.index_topk(res[0]["q_emb"], res[0]["c_emb"], 10)
+    assert np.array_equal(res[0]["ids"], np.arange(1, 301, dtype=np.int32)[want])
