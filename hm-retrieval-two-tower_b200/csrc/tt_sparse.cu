@@ -194,6 +194,84 @@ __device__ __forceinline__ void apply_row(const tt_sparse_job& job, int kMode, u
     }
 }
 
+// Body of phase A for one block, NC columns per lane, RB runs in flight.  The loads of a batch of RB runs
+// (first gradient row of each run plus the table / slot values their update will need) are issued together so a
+// block of 32 distinct ids costs ~32/RB memory round trips instead of 64.
+template <int NC, int RB>
+__device__ __forceinline__ void block_body(const tt_sparse_job& job, int kMode, uint32_t key, int pos, uint32_t heads, int cnt, bool cont_in,
+                                           bool cont_out, float* __restrict__ partL, float* __restrict__ partR, int lane, float lr, float eps,
+                                           float omb1, float omb2) {
+    const int e = job.e;
+    while (heads) {
+        int s[RB], en[RB];
+        uint32_t id[RB];
+        int nb = 0;
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            s[u] = 0; en[u] = 0; id[u] = 0;
+            if (heads) {
+                s[u] = __ffs(heads) - 1;
+                heads &= heads - 1;
+                en[u] = heads ? (__ffs(heads) - 1) : cnt;
+                nb = u + 1;
+            }
+            id[u] = __shfl_sync(0xffffffffu, key, s[u]);
+        }
+        float g[RB][NC], a[RB][NC], w[RB][NC];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const float* r0 = grad_row(job, __shfl_sync(0xffffffffu, pos, s[u]));
+#pragma unroll
+            for (int ci = 0; ci < NC; ++ci) {
+                const int c = lane + 32 * ci;
+                g[u][ci] = 0.f; a[u][ci] = 0.f; w[u][ci] = 0.f;
+                if (u < nb && c < e) {
+                    const int64_t o = (int64_t)id[u] * e + c;
+                    g[u][ci] = __ldg(r0 + c);
+                    a[u][ci] = job.slot0[o];
+                    w[u][ci] = (kMode == kModeAdagrad) ? job.table[o] : job.slot1[o];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            for (int j = s[u] + 1; j < en[u]; ++j) {   // duplicates of the id inside this block: sequential, position order
+                const float* r0 = grad_row(job, __shfl_sync(0xffffffffu, pos, j));
+#pragma unroll
+                for (int ci = 0; ci < NC; ++ci) {
+                    const int c = lane + 32 * ci;
+                    if (c < e) g[u][ci] = __fadd_rn(g[u][ci], __ldg(r0 + c));
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            if (u >= nb) continue;
+            const bool to_l = (s[u] == 0) && cont_in;
+            const bool to_r = (en[u] == cnt) && cont_out && !to_l;
+#pragma unroll
+            for (int ci = 0; ci < NC; ++ci) {
+                const int c = lane + 32 * ci;
+                if (c >= e) continue;
+                const float gv = g[u][ci];
+                if (to_l) partL[c] = gv;          // continuation piece (may also continue further)
+                else if (to_r) partR[c] = gv;     // run begins here and continues
+                else {                            // run lives entirely in this block: apply with the prefetched state
+                    const int64_t o = (int64_t)id[u] * e + c;
+                    if (kMode == kModeAdagrad) {
+                        const float an = __fadd_rn(a[u][ci], __fmul_rn(gv, gv));
+                        job.slot0[o] = an;
+                        job.table[o] = __fsub_rn(w[u][ci], __fdiv_rn(__fmul_rn(gv, lr), __fadd_rn(__fsqrt_rn(an), eps)));
+                    } else {
+                        job.slot0[o] = __fadd_rn(a[u][ci], __fmul_rn(gv, omb1));
+                        job.slot1[o] = __fadd_rn(w[u][ci], __fmul_rn(__fmul_rn(gv, gv), omb2));
+                    }
+                }
+            }
+        }
+    }
+}
+
 // phase A: grid (ceil(max_blocks / 8), njobs), 8 warps per CTA, one warp per block of 32 sorted entries
 __global__ void __launch_bounds__(256) sparse_block_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans, int kMode,
                                                            float lr, float eps, float omb1, float omb2) {
@@ -214,54 +292,15 @@ __global__ void __launch_bounds__(256) sparse_block_kernel(const __grid_constant
     const uint32_t last_key = __shfl_sync(0xffffffffu, key, cnt - 1);
     const bool cont_out = base + 32 < pl.n && cnt == 32 && ks[base + 32] == last_key;            // last run goes on
     const bool head = lane < cnt && (lane == 0 || key != kprev_lane);
-    uint32_t heads = __ballot_sync(0xffffffffu, head);
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
     const int e = job.e;
     float* partL = pl.partL + (int64_t)b * e;
     float* partR = pl.partR + (int64_t)b * e;
-    const int nc = (e + 31) >> 5;                        // columns per lane (e <= 32 * kMaxColsPerLane)
-    while (heads) {
-        const int s = __ffs(heads) - 1;
-        heads &= heads - 1;
-        const int en = heads ? (__ffs(heads) - 1) : cnt;
-        const uint32_t id = __shfl_sync(0xffffffffu, key, s);
-        const bool is_first = (s == 0), is_last = (en == cnt);
-        float g[kMaxColsPerLane];
-#pragma unroll
-        for (int ci = 0; ci < kMaxColsPerLane; ++ci) g[ci] = 0.f;
-        // every lane takes part in the position broadcasts; the column loops are predicated per lane
-        int j = s;
-        for (; j + 4 <= en; j += 4) {
-            const float* r0 = grad_row(job, __shfl_sync(0xffffffffu, pos, j));
-            const float* r1 = grad_row(job, __shfl_sync(0xffffffffu, pos, j + 1));
-            const float* r2 = grad_row(job, __shfl_sync(0xffffffffu, pos, j + 2));
-            const float* r3 = grad_row(job, __shfl_sync(0xffffffffu, pos, j + 3));
-#pragma unroll
-            for (int ci = 0; ci < kMaxColsPerLane; ++ci) {
-                const int c = lane + 32 * ci;
-                if (ci < nc && c < e) {
-                    const float g0 = __ldg(r0 + c), g1 = __ldg(r1 + c), g2 = __ldg(r2 + c), g3 = __ldg(r3 + c);
-                    g[ci] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(g[ci], g0), g1), g2), g3);
-                }
-            }
-        }
-        for (; j < en; ++j) {
-            const float* r0 = grad_row(job, __shfl_sync(0xffffffffu, pos, j));
-#pragma unroll
-            for (int ci = 0; ci < kMaxColsPerLane; ++ci) {
-                const int c = lane + 32 * ci;
-                if (ci < nc && c < e) g[ci] = __fadd_rn(g[ci], __ldg(r0 + c));
-            }
-        }
-#pragma unroll
-        for (int ci = 0; ci < kMaxColsPerLane; ++ci) {
-            const int c = lane + 32 * ci;
-            if (ci < nc && c < e) {
-                if (is_first && cont_in) partL[c] = g[ci];                       // continuation piece (may also continue further)
-                else if (is_last && cont_out) partR[c] = g[ci];                  // run begins here and continues
-                else apply_row(job, kMode, id, c, g[ci], lr, eps, omb1, omb2);    // run lives entirely in this block
-            }
-        }
-    }
+    const int nc = (e + 31) >> 5;
+    if (nc <= 1) block_body<1, 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2);
+    else if (nc <= 2) block_body<2, 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2);
+    else if (nc <= 4) block_body<4, 2>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2);
+    else block_body<8, 1>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2);
 }
 
 // phase B: the head block of every boundary-crossing run adds the pieces in block order and applies the update
