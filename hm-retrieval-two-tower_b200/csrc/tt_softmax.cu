@@ -109,6 +109,31 @@ int tt_inbatch_softmax_bwd(const float* Q, int ldq, const float* C, int ldc, con
     return softmax_bwd_pass_simt(C, ldc, Q, ldq, col_bias, lse, Bc, Bq, E, -diag_offset, dC, lddc, st);
 }
 
+/* one half of the backward: which = 0 -> dQ (G is (Bq,E)), which = 1 -> dC (G is (Bc,E)).  The halves are
+ * independent; with separate workspaces they may run concurrently on two streams. */
+int tt_inbatch_softmax_bwd_one(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, const float* lse, int Bq, int Bc,
+                               int E, int diag_offset, int which, float* G, int ldg, void* ws, size_t ws_bytes, int impl, void* stream) {
+    TT_REQUIRE(Q && C && lse && G, "tt_inbatch_softmax_bwd_one: null pointer");
+    TT_REQUIRE(Bq >= 0 && Bc >= 0 && E >= 1 && ldq >= E && ldc >= E && ldg >= E, "tt_inbatch_softmax_bwd_one: bad shape");
+    TT_REQUIRE(which == 0 || which == 1, "tt_inbatch_softmax_bwd_one: which must be 0 (dQ) or 1 (dC)");
+    TT_REQUIRE(diag_offset >= 0 && (Bq == 0 || diag_offset + Bq <= Bc), "tt_inbatch_softmax_bwd_one: bad diag_offset");
+    TT_REQUIRE(ws && ws_bytes >= tt_softmax_workspace_bytes(Bq, Bc, E), "tt_inbatch_softmax_bwd_one: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    int use = pick_impl(impl, ldq, ldc, E, Q, C, "tt_inbatch_softmax_bwd_one");
+    if (use < 0) return use;
+    if (Bq == 0) {
+        if (which == 1 && Bc > 0) TT_CUDA_OK(cudaMemset2DAsync(G, sizeof(float) * ldg, 0, sizeof(float) * E, Bc, st));
+        return TT_OK;
+    }
+    float* wsf = reinterpret_cast<float*>(ws);
+    if (use == TT_IMPL_TC) {
+        return which == 0 ? softmax_bwd_pass_tc(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, G, ldg, wsf, st)
+                          : softmax_bwd_pass_tc(C, ldc, Q, ldq, col_bias, lse, Bc, Bq, E, -diag_offset, G, ldg, wsf, st);
+    }
+    return which == 0 ? softmax_bwd_pass_simt(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, G, ldg, st)
+                      : softmax_bwd_pass_simt(C, ldc, Q, ldq, col_bias, lse, Bc, Bq, E, -diag_offset, G, ldg, st);
+}
+
 int tt_logits(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, int Bq, int Bc, int E, float* Z, int ldz,
               int impl, void* stream) {
     // the materialised matrix is an API/test convenience: exact path unless TT_IMPL_TC is asked for explicitly

@@ -246,7 +246,8 @@ __global__ void dense_bwd_reduce_kernel(const float* __restrict__ partial, int n
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= total) return;
     float s = 0.f;
-    for (int z = 0; z < nchunk; ++z) s = __fadd_rn(s, partial[(int64_t)z * total + i]);
+#pragma unroll 16
+    for (int z = 0; z < nchunk; ++z) s = __fadd_rn(s, __ldg(partial + (int64_t)z * total + i));   // loads are independent: keep 16 in flight
     int k = (int)(i / N), n = (int)(i % N);
     if (k < K) dW[(int64_t)k * N + n] = s;
     else if (db) db[n] = s;
@@ -276,6 +277,19 @@ static int check_feats(const tt_feature* feats, int nfeat, int D, const char* wh
     }
     return TT_OK;
 }
+
+// tt_tower_panel.cu: shared-memory resident variants for K <= 256 / N <= 256
+bool panel_fwd_ok(int K, int N);
+bool panel_bwd_ok(int K, int N);
+int panel_dense_fwd(const float* X, int ldx, const float* W, const float* b, float* Y, int ldy, float* Y32, int B, int K, int N, int relu,
+                    cudaStream_t st);
+int panel_input_dense_fwd(const tt_feature* feats, int nfeat, int D, const float* W, const float* b, float* Xout, int ldx, float* Y, int ldy,
+                          float* Y32, int B, int N, int relu, cudaStream_t st);
+size_t panel_bwd_workspace(int B, int K, int N);
+int panel_dense_bwd_dx(const float* W, const float* Y, int ldy, const float* dY, int lddy, float* dX, int lddx, int B, int K, int N, int relu,
+                       cudaStream_t st);
+int panel_dense_bwd_dw(const float* X, int ldx, const float* Y, int ldy, const float* dY, int lddy, float* partial, int B, int K, int N, int relu,
+                       int* nchunk_out, cudaStream_t st);
 
 }  // namespace tt
 
@@ -324,6 +338,7 @@ int tt_dense_fwd(const float* X, int ldx, const float* W, const float* b, float*
     TT_REQUIRE(X && W && Y, "tt_dense_fwd: null pointer");
     TT_REQUIRE(B >= 0 && K >= 1 && N >= 1 && ldx >= K && ldy >= N, "tt_dense_fwd: bad shape");
     if (B == 0) return TT_OK;
+    if (panel_fwd_ok(K, N)) return panel_dense_fwd(X, ldx, W, b, Y, ldy, Y_tf32, B, K, N, relu, as_stream(stream));
     FeatArr fa;
     memset(&fa, 0, sizeof(fa));
     dim3 grid((unsigned)ceil_div(B, BM), (unsigned)ceil_div(N, BN));
@@ -340,6 +355,7 @@ int tt_input_dense_fwd(const tt_feature* feats, int nfeat, int D, const float* W
     TT_REQUIRE(W && Y, "tt_input_dense_fwd: null pointer");
     TT_REQUIRE(B >= 0 && N >= 1 && ldy >= N && (X_out == nullptr || ldx >= D), "tt_input_dense_fwd: bad shape");
     if (B == 0) return TT_OK;
+    if (panel_fwd_ok(D, N)) return panel_input_dense_fwd(feats, nfeat, D, W, b, X_out, ldx, Y, ldy, Y_tf32, B, N, relu, as_stream(stream));
     FeatArr fa;
     memset(&fa, 0, sizeof(fa));
     fa.n = nfeat;
@@ -354,7 +370,9 @@ size_t tt_dense_bwd_workspace_bytes(int B, int K, int N) {
     if (B <= 0 || K <= 0 || N <= 0) return 256;
     int rows = 0;
     int nchunk = dw_chunks(B, K, N, &rows);
-    return align_up((size_t)nchunk * (size_t)(K + 1) * (size_t)N * sizeof(float), 256) + 256;
+    size_t generic = align_up((size_t)nchunk * (size_t)(K + 1) * (size_t)N * sizeof(float), 256) + 256;
+    size_t panel = panel_bwd_ok(K, N) ? panel_bwd_workspace(B, K, N) : 0;
+    return generic > panel ? generic : panel;
 }
 
 int tt_dense_bwd(const float* X, int ldx, const float* W, const float* Y, int ldy, const float* dY, int lddy, float* dX, int lddx,
@@ -366,6 +384,20 @@ int tt_dense_bwd(const float* X, int ldx, const float* W, const float* Y, int ld
     if (B == 0) {
         TT_CUDA_OK(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)K * N, st));
         if (db) TT_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
+        return TT_OK;
+    }
+    if (panel_bwd_ok(K, N)) {
+        if (dX) {
+            int rc = panel_dense_bwd_dx(W, Y, ldy, dY, lddy, dX, lddx, B, K, N, relu, st);
+            if (rc) return rc;
+        }
+        float* partial = reinterpret_cast<float*>(ws);
+        int nchunk = 0;
+        int rc = panel_dense_bwd_dw(X, ldx, Y, ldy, dY, lddy, partial, B, K, N, relu, &nchunk, st);
+        if (rc) return rc;
+        int64_t total = (int64_t)(K + 1) * N;
+        dense_bwd_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(partial, nchunk, K, N, dW, db);
+        TT_LAUNCH_OK("dense_bwd_reduce_kernel");
         return TT_OK;
     }
     DPre dp{dY, Y, lddy, ldy, B, N, relu};

@@ -1,0 +1,310 @@
+// tt_tower_panel.cu -- tower Dense kernels for the common case where a whole reduction extent fits in shared
+// memory (K <= 256 inputs, N <= 256 units): both operands are staged once per CTA, the inner loop touches only
+// shared memory, and the embedding gather writes straight into the staged A operand.
+//
+// Same arithmetic contract as tt_tower.cu (reference: input_layer.py:37-41,61-68; tower.py:41-49,72-75):
+// forward accumulates k-ascending with one fmaf per term (bit-identical to oracle/tt_oracle.c:tto_dense_fmaf);
+// dW/db are summed over fixed 64-row chunks and then over chunks in order (deterministic).
+#include "tt_common.cuh"
+
+namespace tt {
+
+struct FeatArr {   // same layout as in tt_tower.cu
+    tt_feature f[TT_MAX_FEATURES];
+    int n;
+};
+
+constexpr int PT = 64;        // tile edge
+constexpr int PS = PT + 4;    // padded shared-memory row (floats): float4-aligned, spreads banks
+constexpr int kPanelMaxK = 256;
+
+// ---- forward: Y = relu?(X.W + b), X either dense or gathered from the embedding tables ----------------------
+// grid (ceil(B/64), ceil(N/64)), 256 threads, dynamic smem = 2 * K * PS floats (+ ids for the gather)
+template <bool kGather>
+__global__ void __launch_bounds__(256) dense_fwd_panel_kernel(const __grid_constant__ FeatArr fa, const float* __restrict__ X, int ldx,
+                                                              const float* __restrict__ W, const float* __restrict__ bias,
+                                                              float* __restrict__ Xout, float* __restrict__ Y, int ldy,
+                                                              float* __restrict__ Ytf32, int B, int K, int N, int relu) {
+    extern __shared__ __align__(16) float sm[];
+    float* XsT = sm;                 // [K][PS]  XsT[k][r]
+    float* Ws = sm + (size_t)K * PS;  // [K][PS]  Ws[k][n]
+    const int m0 = blockIdx.x * PT, n0 = blockIdx.y * PT;
+    const int tid = threadIdx.x;
+    // All staging loops are flat and free of loop-carried dependences, so each thread keeps many independent
+    // global loads in flight (these kernels are latency-bound: one CTA per SM, one staging phase per CTA).
+#pragma unroll 8
+    for (int idx = tid; idx < K * PT; idx += 256) {   // W tile, coalesced along n
+        const int k = idx >> 6, n = idx & 63;
+        Ws[k * PS + n] = (n0 + n < N) ? __ldg(W + (int64_t)k * N + n0 + n) : 0.f;
+    }
+    if constexpr (kGather) {
+        __shared__ int32_t s_ids[PT * TT_MAX_FEATURES];
+        __shared__ uint8_t s_feat[kPanelMaxK];
+        __shared__ uint16_t s_off[kPanelMaxK];
+        for (int c = tid; c < K; c += 256) {
+            uint8_t ff = 255;
+            uint16_t oo = 0;
+            for (int f = 0; f < fa.n; ++f)
+                if (c >= fa.f[f].col && c < fa.f[f].col + fa.f[f].e) { ff = (uint8_t)f; oo = (uint16_t)(c - fa.f[f].col); }
+            s_feat[c] = ff;
+            s_off[c] = oo;
+        }
+        for (int i = tid; i < PT * fa.n; i += 256) {
+            const int r = i / fa.n, f = i - r * fa.n;
+            int id = 0;
+            if (m0 + r < B && fa.f[f].table != nullptr) {
+                id = __ldg(reinterpret_cast<const int32_t*>(fa.f[f].src) + m0 + r);
+                if ((unsigned)id >= (unsigned)fa.f[f].rows) id = 0;
+            }
+            s_ids[r * TT_MAX_FEATURES + f] = id;
+        }
+        __syncthreads();
+        const bool write_x = (Xout != nullptr) && blockIdx.y == 0;
+#pragma unroll 8
+        for (int idx = tid; idx < PT * K; idx += 256) {   // consecutive threads -> consecutive columns of one row
+            const int r = idx / K, k = idx - r * K;
+            const int row = m0 + r;
+            const int f = s_feat[k];
+            float v = 0.f;
+            if (row < B && f != 255) {
+                const tt_feature& ft = fa.f[f];
+                v = (ft.table == nullptr) ? __ldg(reinterpret_cast<const float*>(ft.src) + row)
+                                          : __ldg(ft.table + (int64_t)s_ids[r * TT_MAX_FEATURES + f] * ft.e + s_off[k]);
+            }
+            XsT[k * PS + r] = v;
+            if (write_x && row < B) Xout[(int64_t)row * ldx + k] = v;
+        }
+        if (write_x) {
+            const int padc = ldx - K;
+            for (int idx = tid; idx < PT * padc; idx += 256) {   // zero the padding columns
+                const int r = idx / padc, c = K + idx - r * padc;
+                if (m0 + r < B) Xout[(int64_t)(m0 + r) * ldx + c] = 0.f;
+            }
+        }
+    } else {
+#pragma unroll 8
+        for (int idx = tid; idx < PT * K; idx += 256) {
+            const int r = idx / K, k = idx - r * K;
+            XsT[k * PS + r] = (m0 + r < B) ? __ldg(X + (int64_t)(m0 + r) * ldx + k) : 0.f;
+        }
+    }
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4] = {};
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float4 a4 = *reinterpret_cast<const float4*>(XsT + k * PS + ty * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(Ws + k * PS + tx * 4);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= B) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float y = acc[i][j];
+            if (bias) y = __fadd_rn(y, __ldg(bias + n));
+            if (relu && !(y > 0.f)) y = 0.f;
+            Y[(int64_t)m * ldy + n] = y;
+            if (Ytf32) Ytf32[(int64_t)m * ldy + n] = tf32_rn(y);
+        }
+    }
+}
+
+// ---- backward dX = dpre.W^T  (reduction over N <= 256) ----------------------------------------------------------
+// grid (ceil(B/64), ceil(K/64)); smem: DsT[N][PS] (dpre^T tile) + WsT[N][PS] (WsT[n][kk] = W[k0+kk][n])
+__global__ void __launch_bounds__(256) dense_bwd_dx_panel_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Yv, int ldy,
+                                                                 const float* __restrict__ W, float* __restrict__ dX, int lddx, int B, int K,
+                                                                 int N, int relu) {
+    extern __shared__ __align__(16) float sm[];
+    float* DsT = sm;
+    float* WsT = sm + (size_t)N * PS;
+    const int m0 = blockIdx.x * PT, k0 = blockIdx.y * PT;
+    const int tid = threadIdx.x;
+#pragma unroll 8
+    for (int idx = tid; idx < PT * N; idx += 256) {
+        const int r = idx / N, n = idx - r * N;
+        const int row = m0 + r;
+        float g = 0.f;
+        if (row < B) {
+            g = __ldg(dY + (int64_t)row * lddy + n);
+            if (relu && !(__ldg(Yv + (int64_t)row * ldy + n) > 0.f)) g = 0.f;
+        }
+        DsT[n * PS + r] = g;
+    }
+#pragma unroll 8
+    for (int idx = tid; idx < PT * N; idx += 256) {
+        const int kk = idx / N, n = idx - kk * N;
+        WsT[n * PS + kk] = (k0 + kk < K) ? __ldg(W + (int64_t)(k0 + kk) * N + n) : 0.f;
+    }
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4] = {};
+#pragma unroll 4
+    for (int n = 0; n < N; ++n) {
+        const float4 a4 = *reinterpret_cast<const float4*>(DsT + n * PS + ty * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(WsT + n * PS + tx * 4);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= B) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k < K) dX[(int64_t)m * lddx + k] = acc[i][j];
+        }
+    }
+}
+
+// ---- backward dW / db: partial[chunk][k][n] = sum_{b in chunk} X[b][k] * dpre[b][n]; row k == K is the bias gradient --
+// grid (nchunk, ceil((K+1)/96), ceil(N/64)); a chunk is `rows` batch rows processed 64 at a time.
+// thread (ty 0..15, tx 0..15): rows k0 + ty + 16*i (i < 6), cols n0 + 4*tx .. +3.
+constexpr int kDwRows = 96;
+__global__ void __launch_bounds__(256) dense_bwd_dw_panel_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int lddy,
+                                                                 const float* __restrict__ Yv, int ldy, float* __restrict__ partial, int B,
+                                                                 int K, int N, int rows, int relu) {
+    __shared__ __align__(16) float Xs[PT][kDwRows + 1];
+    __shared__ __align__(16) float Ds[PT][PS];
+    const int b_begin = blockIdx.x * rows, b_end = min(B, b_begin + rows);
+    const int k0 = blockIdx.y * kDwRows, n0 = blockIdx.z * PT;
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[6][4] = {};
+    for (int bb = b_begin; bb < b_end; bb += PT) {
+#pragma unroll 8
+        for (int idx = tid; idx < PT * kDwRows; idx += 256) {
+            const int r = idx / kDwRows, kk = idx - r * kDwRows;
+            const int row = bb + r, k = k0 + kk;
+            float v = 0.f;
+            if (row < b_end) v = k < K ? __ldg(X + (int64_t)row * ldx + k) : (k == K ? 1.0f : 0.f);
+            Xs[r][kk] = v;
+        }
+#pragma unroll 8
+        for (int idx = tid; idx < PT * PT; idx += 256) {
+            const int r = idx >> 6, n = idx & 63;
+            const int row = bb + r;
+            float g = 0.f;
+            if (row < b_end && n0 + n < N) {
+                g = __ldg(dY + (int64_t)row * lddy + n0 + n);
+                if (relu && !(__ldg(Yv + (int64_t)row * ldy + n0 + n) > 0.f)) g = 0.f;
+            }
+            Ds[r][n] = g;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < PT; ++r) {
+            const float4 d4 = *reinterpret_cast<const float4*>(&Ds[r][tx * 4]);
+            const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const float a = Xs[r][ty + 16 * i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a, d[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+    float* out = partial + (int64_t)blockIdx.x * (K + 1) * N;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int k = k0 + ty + 16 * i;
+        if (k > K) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N) out[(int64_t)k * N + n] = acc[i][j];
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+bool panel_fwd_ok(int K, int N) { return K >= 1 && K <= kPanelMaxK && N >= 1; }
+bool panel_bwd_ok(int K, int N) { return K >= 1 && K <= 1024 && N >= 1 && N <= kPanelMaxK; }
+
+template <bool G>
+static int launch_fwd(const FeatArr& fa, const float* X, int ldx, const float* W, const float* b, float* Xout, float* Y, int ldy, float* Y32, int B,
+                      int K, int N, int relu, cudaStream_t st) {
+    const size_t smem = 2 * (size_t)K * PS * sizeof(float);
+    static bool set = false;   // static + dynamic shared memory can exceed 48 KB even for small K: always opt in
+    if (!set) {
+        TT_CUDA_OK(cudaFuncSetAttribute(dense_fwd_panel_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kPanelMaxK * PS * sizeof(float))));
+        set = true;
+    }
+    dim3 grid((unsigned)ceil_div(B, PT), (unsigned)ceil_div(N, PT));
+    dense_fwd_panel_kernel<G><<<grid, 256, smem, st>>>(fa, X, ldx, W, b, Xout, Y, ldy, Y32, B, K, N, relu);
+    TT_LAUNCH_OK("dense_fwd_panel_kernel");
+    return TT_OK;
+}
+
+int panel_dense_fwd(const float* X, int ldx, const float* W, const float* b, float* Y, int ldy, float* Y32, int B, int K, int N, int relu,
+                    cudaStream_t st) {
+    FeatArr fa;
+    memset(&fa, 0, sizeof(fa));
+    return launch_fwd<false>(fa, X, ldx, W, b, nullptr, Y, ldy, Y32, B, K, N, relu, st);
+}
+
+int panel_input_dense_fwd(const tt_feature* feats, int nfeat, int D, const float* W, const float* b, float* Xout, int ldx, float* Y, int ldy,
+                          float* Y32, int B, int N, int relu, cudaStream_t st) {
+    FeatArr fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.n = nfeat;
+    for (int f = 0; f < nfeat; ++f) fa.f[f] = feats[f];
+    return launch_fwd<true>(fa, nullptr, ldx, W, b, Xout, Y, ldy, Y32, B, D, N, relu, st);
+}
+
+static int dw_plan(int B, int* rows) {   // batch rows per CTA: a multiple of 64, about two waves of CTAs overall
+    int64_t want = 2 * (int64_t)sm_count();
+    int64_t r = ceil_div(ceil_div(B, want), PT) * PT;
+    if (r < PT) r = PT;
+    *rows = (int)r;
+    return (int)ceil_div(B, r);
+}
+
+size_t panel_bwd_workspace(int B, int K, int N) {
+    int rows = 0;
+    int nchunk = dw_plan(B, &rows);
+    return align_up((size_t)nchunk * (K + 1) * N * sizeof(float), 256) + 256;
+}
+
+int panel_dense_bwd_dx(const float* W, const float* Y, int ldy, const float* dY, int lddy, float* dX, int lddx, int B, int K, int N, int relu,
+                       cudaStream_t st) {
+    const size_t smem = 2 * (size_t)N * PS * sizeof(float);
+    static bool set = false;
+    if (!set) {
+        TT_CUDA_OK(cudaFuncSetAttribute(dense_bwd_dx_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kPanelMaxK * PS * sizeof(float))));
+        set = true;
+    }
+    dim3 grid((unsigned)ceil_div(B, PT), (unsigned)ceil_div(K, PT));
+    dense_bwd_dx_panel_kernel<<<grid, 256, smem, st>>>(dY, lddy, Y, ldy, W, dX, lddx, B, K, N, relu);
+    TT_LAUNCH_OK("dense_bwd_dx_panel_kernel");
+    return TT_OK;
+}
+
+// returns the number of chunks written to `partial` ([chunk][K+1][N])
+int panel_dense_bwd_dw(const float* X, int ldx, const float* Y, int ldy, const float* dY, int lddy, float* partial, int B, int K, int N, int relu,
+                       int* nchunk_out, cudaStream_t st) {
+    int rows = 0;
+    int nchunk = dw_plan(B, &rows);
+    dim3 grid((unsigned)nchunk, (unsigned)ceil_div(K + 1, kDwRows), (unsigned)ceil_div(N, PT));
+    dense_bwd_dw_panel_kernel<<<grid, 256, 0, st>>>(X, ldx, dY, lddy, Y, ldy, partial, B, K, N, rows, relu);
+    TT_LAUNCH_OK("dense_bwd_dw_panel_kernel");
+    *nchunk_out = nchunk;
+    return TT_OK;
+}
+
+}  // namespace tt

@@ -54,6 +54,7 @@ class _StepWorkspace:
         self.dq = torch.zeros((batch, e), **f32)
         self.dc = torch.zeros((batch, e), **f32)
         self.sm_ws = torch.empty(int(lib.tt_softmax_workspace_bytes(batch, batch, e)), dtype=torch.uint8, device="cuda")
+        self.sm_ws2 = torch.empty_like(self.sm_ws)    # the candidate-side half of the backward runs concurrently
         self.bias_feat = None
         if model.logq_correction:
             cid_buf = None
@@ -65,6 +66,7 @@ class _StepWorkspace:
                                                "rows": model._logq_rows.shape[0], "e": 1, "col": 0}])
         self.graph = None
         self.side = torch.cuda.Stream()
+        self.cand = torch.cuda.Stream()               # candidate tower / dC pass, concurrent with the query side
         self.jobs = None
         self.sp_ws = None
         self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
@@ -232,25 +234,36 @@ class TwoTowerModel(AbstractKerasModel):
                 self.dist.gather_ids(self, sw)
             N.check(lib.tt_sparse_sort(sw.jobs, sw.njobs, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), N.stream_ptr()), "tt_sparse_sort")
         st = N.stream_ptr()
+        # the two towers are independent until the logits: candidate side on its own stream
+        sw.cand.wait_stream(main)
         q, q32 = self.query_tower.forward_ws(sw.q)
-        c, c32 = self.candidate_tower.forward_ws(sw.c)
         bias = None
-        if self.logq_correction is not None:
-            if sw.bias_from_strings:
-                N.check(lib.tt_log_f32(sw.col_prob.data_ptr(), sw.col_bias.data_ptr(), b, st), "tt_log_f32")
-            else:
-                N.check(lib.tt_gather_concat(sw.bias_feat, 1, b, 1, sw.col_bias.data_ptr(), 1, st), "tt_gather_concat(logq)")
-            bias = sw.col_bias.data_ptr()
+        with torch.cuda.stream(sw.cand):
+            stc = N.stream_ptr()
+            c, c32 = self.candidate_tower.forward_ws(sw.c)
+            if self.logq_correction is not None:
+                if sw.bias_from_strings:
+                    N.check(lib.tt_log_f32(sw.col_prob.data_ptr(), sw.col_bias.data_ptr(), b, stc), "tt_log_f32")
+                else:
+                    N.check(lib.tt_gather_concat(sw.bias_feat, 1, b, 1, sw.col_bias.data_ptr(), 1, stc), "tt_gather_concat(logq)")
+                bias = sw.col_bias.data_ptr()
+        main.wait_stream(sw.cand)
         use_tc = self.impl != N.TT_IMPL_SIMT and self._tc_ok()
         qa, ca = (q32, c32) if use_tc else (q, c)
         impl = N.TT_IMPL_TC if use_tc else N.TT_IMPL_SIMT
         N.check(lib.tt_inbatch_softmax_fwd(qa.data_ptr(), e, ca.data_ptr(), e, bias, b, b, e, 0, sw.lse.data_ptr(),
                                            sw.loss.data_ptr(), sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st), "tt_inbatch_softmax_fwd")
-        N.check(lib.tt_inbatch_softmax_bwd(qa.data_ptr(), e, ca.data_ptr(), e, bias, sw.lse.data_ptr(), b, b, e, 0,
-                                           sw.dq.data_ptr(), e, sw.dc.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st),
-                "tt_inbatch_softmax_bwd")
+        # backward: dQ -> query tower on the main stream, dC -> candidate tower on the candidate stream
+        sw.cand.wait_stream(main)
+        N.check(lib.tt_inbatch_softmax_bwd_one(qa.data_ptr(), e, ca.data_ptr(), e, bias, sw.lse.data_ptr(), b, b, e, 0, 0,
+                                               sw.dq.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st), "tt_inbatch_softmax_bwd_one(dQ)")
         self.query_tower.backward_ws(sw.q, sw.dq)
-        self.candidate_tower.backward_ws(sw.c, sw.dc)
+        with torch.cuda.stream(sw.cand):
+            N.check(lib.tt_inbatch_softmax_bwd_one(qa.data_ptr(), e, ca.data_ptr(), e, bias, sw.lse.data_ptr(), b, b, e, 0, 1,
+                                                   sw.dc.data_ptr(), e, sw.sm_ws2.data_ptr(), sw.sm_ws2.numel(), impl, N.stream_ptr()),
+                    "tt_inbatch_softmax_bwd_one(dC)")
+            self.candidate_tower.backward_ws(sw.c, sw.dc)
+        main.wait_stream(sw.cand)
         if self.dist is not None:
             self.dist.reduce_dense_and_gather_rows(self, sw)
         n_dense = self._store.used

@@ -111,6 +111,11 @@ int tt_inbatch_softmax_fwd(const float* Q, int ldq, const float* C, int ldc, con
 int tt_inbatch_softmax_bwd(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, const float* lse,
                            int Bq, int Bc, int E, int diag_offset, float* dQ, int lddq, float* dC, int lddc,
                            void* ws, size_t ws_bytes, int impl, void* stream);
+/* One half of the backward (which = 0: dQ into G (Bq,E); which = 1: dC into G (Bc,E)).  The halves are
+ * independent: given separate workspaces they may run concurrently on two streams. */
+int tt_inbatch_softmax_bwd_one(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, const float* lse,
+                               int Bq, int Bc, int E, int diag_offset, int which, float* G, int ldg, void* ws,
+                               size_t ws_bytes, int impl, void* stream);
 /* Materialised Z (Bq,Bc) for TwoTowerModel.call / LogQCorrection parity tests only. */
 int tt_logits(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, int Bq, int Bc, int E,
               float* Z, int ldz, int impl, void* stream);
