@@ -273,7 +273,7 @@ size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl, int h
 int tt_index_prepare(const float* corpus, int ldc, int64_t n, int E, float* corpus_prepared, float* corpus_norms, void* stream) {
     TT_REQUIRE(corpus && corpus_prepared && corpus_norms, "tt_index_prepare: null pointer");
     TT_REQUIRE(n >= 0 && E >= 1 && ldc >= E, "tt_index_prepare: bad shape");
-    return tc::launch_prepare(corpus, ldc, n, E, corpus_prepared, corpus_norms, (int64_t)TT_INDEX_NORM_PAD(n), as_stream(stream));
+    return tc::launch_prepare(corpus, ldc, n, E, corpus_prepared, corpus_norms, (int64_t)TT_INDEX_ROWS_PAD(n), as_stream(stream));
 }
 
 int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const float* corpus_prepared, const float* corpus_norms, int nq,

@@ -181,6 +181,12 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(const float* __restri
         if (threadIdx.x == 0) flags[q] = 1;
         return;
     }
+    {   // sort only as many slots as this query needs (typically ~K, far below the list capacity)
+        int need = m > K ? m : K;
+        int pq = 2;
+        while (pq < need) pq <<= 1;
+        P = pq < P ? pq : P;
+    }
     for (int k = threadIdx.x; k < E; k += 256) sq[k] = Q[(int64_t)q * ldq + k];
     __syncthreads();
     for (int t = threadIdx.x; t < P; t += 256) {
@@ -245,11 +251,24 @@ __global__ void __launch_bounds__(256) prepare_corpus_kernel(const float* __rest
     }
 }
 
+// gn[c] = max over the 32 rows of chunk c of norms[] (norms is zero beyond n)
+__global__ void chunk_max_kernel(const float* __restrict__ norms, int64_t nchunks, float* __restrict__ gn) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    float m = 0.f;
+    for (int i = 0; i < 32; ++i) m = fmaxf(m, norms[c * 32 + i]);
+    gn[c] = m;
+}
+
+// norms buffer layout: [n_pad per-row norms][n_pad/32 per-chunk maxima]
 int launch_prepare(const float* C, int ldc, int64_t n, int E, float* C32p, float* norms, int64_t n_pad, cudaStream_t st) {
     int64_t g = ceil_div(n_pad * 32, 256);
     int64_t cap = (int64_t)sm_count() * 16;
     prepare_corpus_kernel<<<(unsigned)(g > cap ? cap : (g < 1 ? 1 : g)), 256, 0, st>>>(C, ldc, n, E, make_perm(n), C32p, norms, n_pad);
     TT_LAUNCH_OK("prepare_corpus_kernel");
+    const int64_t nchunks = n_pad / 32;
+    chunk_max_kernel<<<(unsigned)ceil_div(nchunks, 256), 256, 0, st>>>(norms, nchunks, norms + n_pad);
+    TT_LAUNCH_OK("chunk_max_kernel");
     return TT_OK;
 }
 
@@ -299,7 +318,7 @@ static IdxLayout layout(int nq, int64_t n, int E, int K, bool need_corpus_copy) 
     L.flags = take((size_t)nq * 4);
     L.cand = take((size_t)nq * L.cap * 4);
     L.c32 = take(need_corpus_copy ? (size_t)n * E * 4 : 0);
-    L.norms = take(need_corpus_copy ? ((size_t)L.n_tiles * idx_bn(E) + 256) * 4 : 0);
+    L.norms = take(need_corpus_copy ? (size_t)TT_INDEX_NORM_PAD(n) * 4 : 0);
     L.exact = off;
     L.total = off;
     return L;
@@ -345,7 +364,7 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
     if (need_copy) {
         float* dst = reinterpret_cast<float*>(base + L.c32);
         float* nd = reinterpret_cast<float*>(base + L.norms);
-        int rcn = launch_prepare(C, ldc, n, E, dst, nd, (int64_t)L.n_tiles * idx_bn(E), st);
+        int rcn = launch_prepare(C, ldc, n, E, dst, nd, (int64_t)TT_INDEX_ROWS_PAD(n), st);
         if (rcn) return rcn;
         c32 = dst;
         norms = nd;
@@ -362,7 +381,7 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
     int splits = 1, tps = L.n_tiles;
     choose_splits(m_tiles, L.n_tiles, 2, 64, &splits, &tps);
     RowPanelParams p{};
-    p.nR = nq; p.nT = (int)n; p.n_tiles = L.n_tiles; p.tiles_per_split = tps; p.rowv = eps; p.rowv2 = thr; p.colv2 = norms; p.d = -(1 << 30);
+    p.nR = nq; p.nT = (int)n; p.n_tiles = L.n_tiles; p.tiles_per_split = tps; p.rowv = eps; p.rowv2 = thr; p.colv2 = norms; p.gnorm = norms + TT_INDEX_ROWS_PAD(n); p.d = -(1 << 30);
     p.out0 = gmax; p.out1 = nullptr; p.out2 = nullptr; p.ld_out = L.ngroups; p.trace = nullptr;
     rc = launch_idx_e<kIndex>(E, tmQ, tmC, p, m_tiles, splits, st, "rowpanel_kernel<index>");
     if (rc) return rc;

@@ -38,6 +38,7 @@ struct RowPanelParams {
     int tiles_per_split;  // tiles handled by one blockIdx.y
     const float* rowv;    // kBwd: per-R-row term (lse or ln p), natural units | kIndex/kCollect: kappa_q = c*||q||
     const float* rowv2;   // kCollect: per-row threshold lambda_q
+    const float* gnorm;   // kIndex/kCollect: max ||c_j|| over each chunk of 32 columns (colv2 holds the per-column norms)
     const float* colv2;   // per-T-row term * log2(e), padded with zeros to n_tiles*BN entries (never null)
     int d;                // diagonal: column == row + d
     float* out0;          // kFwd: m2 [split][nR] | kBwd: G partial [split][nR][E] | kLogits: Z | kIndex: gmax [nR][ld_out]
@@ -113,13 +114,16 @@ struct RowPanelCfg {
     static constexpr int kPSlabs = BN / 32;
     static constexpr int kPBytes = (MODE == kBwd) ? kPSlabs * 128 * 128 : 0;
     static constexpr int kPBufs = (MODE == kBwd) ? 2 : 0;
-    static constexpr bool kUsesC2 = true;                                    // every mode stages a per-column vector
-    static constexpr int kC2Bytes = BN * 4;                                  // (softmax: colv*log2e, index: row norms)
+    static constexpr bool kUsesC2 = (MODE != kIndex);   // staged per-column vector (softmax: colv*log2e; kCollect: row norms)
+    static constexpr int kC2Bytes = kUsesC2 ? BN * 4 : 0;
     static constexpr int kHalves = (BN / 32 >= 2) ? 2 : 1;                   // epilogue warps per TMEM lane quarter
     static constexpr int kEpiWarps = 4 * kHalves;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
     static constexpr int kTmemCols = (MODE == kBwd) ? (2 * BN + E <= 256 ? 256 : 512) : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
-    static constexpr int kSmemBytes = kRBytes + kStages * kTBytes + kPBufs * kPBytes + 4 * 1024 /*c2 stages*/ + 1024 /*barriers*/ + 1024 /*align*/;
+    static constexpr int kListCap = 47;                                      // kCollect: per-row candidate slots staged in smem
+    static constexpr int kListBytes = (MODE == kCollect) ? 128 * (kListCap + 1) * 4 : 0;
+    static constexpr int kSmemBytes = kRBytes + kStages * kTBytes + kPBufs * kPBytes + 4 * 1024 /*c2 stages*/ + 1024 /*barriers*/ + kListBytes +
+                                      1024 /*align*/;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
     static_assert(E == 32 || E == 64 || E == 128, "E must be 32, 64 or 128");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 up to 256");
@@ -208,6 +212,10 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
     unsigned char* sP = sT + Cfg::kStages * Cfg::kTBytes;
     unsigned char* sC2 = sP + Cfg::kPBufs * Cfg::kPBytes;       // kStages x 1 KB
     RowPanelBars* bars = reinterpret_cast<RowPanelBars*>(sC2 + 4 * 1024);
+    int32_t* sList = reinterpret_cast<int32_t*>(sC2 + 4 * 1024 + 1024);   // kCollect: [128][kListCap + 1], slot 0 = count
+    if (MODE == kCollect) {
+        for (int r = threadIdx.x; r < 128; r += blockDim.x) sList[r * (Cfg::kListCap + 1)] = 0;
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * 128;
@@ -220,7 +228,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         prefetch_tmap(&tmT);
         if (MODE == kBwd) prefetch_tmap(&tmTt);
         mbar_init(&bars->r_full, 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], MODE == kBwd ? 1 : 1 + Cfg::kEpiWarps); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], (MODE == kBwd || !Cfg::kUsesC2) ? 1 : 1 + Cfg::kEpiWarps); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], Cfg::kEpiWarps);
             mbar_init(&bars->p_full[i], Cfg::kEpiWarps); mbar_init(&bars->p_empty[i], 1);
@@ -338,7 +346,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
             const bool fast = (n0 + BN <= p.nT) && (wrow0 + 32 <= p.nR) && (wrow0 + p.d + 32 <= n0 || wrow0 + p.d >= n0 + BN);
             mbar_wait(&bars->s_full[acc], aph);
             tc_fence_after();
-            mbar_wait(&bars->t_full[stage], (it / Cfg::kStages) & 1);   // completed long ago; acquires the staged column term
+            if (Cfg::kUsesC2) mbar_wait(&bars->t_full[stage], (it / Cfg::kStages) & 1);   // completed long ago; acquires the staged column term
             if (threadIdx.x == 64 && it < 6) TT_TRACE(3 + 2 * it);
             if (MODE == kBwd) mbar_wait(&bars->p_empty[pb], ((it >> 1) & 1) ^ 1);
             const float4* c2v = reinterpret_cast<const float4*>(sC2 + stage * 1024);
@@ -374,48 +382,55 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                         }
                     }
                 } else if constexpr (MODE == kCollect) {
-                    // upper bounds U_j = a_j + kappa_q*||c_j|| >= s_j; collect every j with U_j >= lambda_q
-                    float u[32];
+                    // upper bounds U_j = a_j + kappa*||c_j|| >= s_j; collect every j with U_j >= lambda.  Pre-filter with
+                    // the chunk's largest norm (one FFMA per chunk), descend through quad maxima only on a hit.
+                    const float thr_c = fmaf(-r2, __ldg(p.gnorm + (nb >> 5)), r3);   // lambda - kappa * max_j ||c_j||
+                    float m4[8];
                     float mx = -CUDART_INF_F;
 #pragma unroll
                     for (int g4 = 0; g4 < 8; ++g4) {
-                        const float4 cc = lds128(c2s + c * 128 + g4 * 16);
-                        u[g4 * 4] = fmaf(r2, cc.x, __uint_as_float(r[g4 * 4]));
-                        u[g4 * 4 + 1] = fmaf(r2, cc.y, __uint_as_float(r[g4 * 4 + 1]));
-                        u[g4 * 4 + 2] = fmaf(r2, cc.z, __uint_as_float(r[g4 * 4 + 2]));
-                        u[g4 * 4 + 3] = fmaf(r2, cc.w, __uint_as_float(r[g4 * 4 + 3]));
-                        mx = fmaxf(fmaxf(mx, fmaxf(u[g4 * 4], u[g4 * 4 + 1])), fmaxf(u[g4 * 4 + 2], u[g4 * 4 + 3]));
+                        m4[g4] = fmaxf(fmaxf(__uint_as_float(r[g4 * 4]), __uint_as_float(r[g4 * 4 + 1])),
+                                       fmaxf(__uint_as_float(r[g4 * 4 + 2]), __uint_as_float(r[g4 * 4 + 3])));
+                        mx = fmaxf(mx, m4[g4]);
                     }
-                    if (mx >= r3) {   // rare: some column of this chunk reaches the row's threshold
+                    if (mx >= thr_c) {   // about one hit per warp-chunk
                         int32_t* lists = reinterpret_cast<int32_t*>(p.out0);
                         int32_t* lens = reinterpret_cast<int32_t*>(p.out1);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (u[i] >= r3 && nb + i < p.nT) {
-                                const int slot = atomicAdd(lens + row, 1);
-                                if (slot < p.ld_out) lists[(int64_t)row * p.ld_out + slot] = nb + i;
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            if (m4[g4] >= thr_c) {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const int n = nb + g4 * 4 + t;
+                                    const float a = __uint_as_float(r[g4 * 4 + t]);
+                                    float nrm;   // staged row norm: a global load here would put ~L2 latency on every hit
+                                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(nrm) : "r"(c2s + (c * 32 + g4 * 4 + t) * 4));
+                                    if (a >= thr_c && n < p.nT && fmaf(r2, nrm, a) >= r3) {
+                                        // stage in shared memory (a returning global atomic per hit would cost ~1 us of latency)
+                                        int32_t* mine = sList + row_l * (Cfg::kListCap + 1);
+                                        const int ls = atomicAdd(mine, 1);
+                                        if (ls < Cfg::kListCap) mine[1 + ls] = n;
+                                        else {   // staged list full: rare direct push
+                                            const int slot = atomicAdd(lens + row, 1);
+                                            if (slot < p.ld_out) lists[(int64_t)row * p.ld_out + slot] = n;
+                                        }
+                                    }
+                                }
                             }
                         }
                     }
-                } else {  // kIndex: group maximum of the lower bounds L_j = a_j - kappa_q*||c_j|| <= s_j
+                } else {  // kIndex: per chunk, max_j a_j - kappa * max_j ||c_j||  <=  max_j (a_j - kappa*||c_j||)  <=  max_j s_j
                     float mx = -CUDART_INF_F;
-                    const bool whole = fast || nb + 32 <= p.nT;
+                    if (fast || nb + 32 <= p.nT) {
 #pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        const float4 cc = lds128(c2s + c * 128 + g4 * 16);
-                        float l0 = fmaf(-r2, cc.x, __uint_as_float(r[g4 * 4]));
-                        float l1 = fmaf(-r2, cc.y, __uint_as_float(r[g4 * 4 + 1]));
-                        float l2 = fmaf(-r2, cc.z, __uint_as_float(r[g4 * 4 + 2]));
-                        float l3 = fmaf(-r2, cc.w, __uint_as_float(r[g4 * 4 + 3]));
-                        if (!whole) {
-                            const int n = nb + g4 * 4;
-                            if (n >= p.nT) l0 = -CUDART_INF_F;
-                            if (n + 1 >= p.nT) l1 = -CUDART_INF_F;
-                            if (n + 2 >= p.nT) l2 = -CUDART_INF_F;
-                            if (n + 3 >= p.nT) l3 = -CUDART_INF_F;
-                        }
-                        mx = fmaxf(fmaxf(mx, fmaxf(l0, l1)), fmaxf(l2, l3));
+                        for (int i = 0; i < 32; i += 4)
+                            mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
+                                                 fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]))));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (nb + i < p.nT) ? __uint_as_float(r[i]) : -CUDART_INF_F);
                     }
+                    mx = fmaf(-r2, __ldg(p.gnorm + (nb >> 5)), mx);
                     gm[cl] = mx;
                 }
             }
@@ -424,7 +439,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&bars->s_empty[acc]);
-                if (MODE != kBwd) mbar_arrive(&bars->t_empty[stage]);   // c2 of this stage consumed
+                if (MODE != kBwd && Cfg::kUsesC2) mbar_arrive(&bars->t_empty[stage]);   // c2 of this stage consumed
             }
             if (threadIdx.x == 64 && it < 6) TT_TRACE(4 + 2 * it);
             if constexpr (MODE == kBwd) {
@@ -442,6 +457,21 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
 #pragma unroll
                         for (int c = 0; c < NCW; ++c) dst[c] = gm[c];
                     }
+                }
+            }
+        }
+        if constexpr (MODE == kCollect) {
+            // both halves of every row are done: flush the staged candidates with ONE global atomic per row
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * Cfg::kEpiWarps) : "memory");
+            if (half == 0 && row < p.nR) {
+                int32_t* lists = reinterpret_cast<int32_t*>(p.out0);
+                int32_t* lens = reinterpret_cast<int32_t*>(p.out1);
+                const int32_t* mine = sList + row_l * (Cfg::kListCap + 1);
+                const int m = min(mine[0], Cfg::kListCap);
+                if (m > 0) {
+                    const int base = atomicAdd(lens + row, m);
+                    for (int t = 0; t < m; ++t)
+                        if (base + t < p.ld_out) lists[(int64_t)row * p.ld_out + base + t] = mine[1 + t];
                 }
             }
         }

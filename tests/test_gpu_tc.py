@@ -172,7 +172,8 @@ def _index_tc(lib, T, q, c, K, idx_base=0, prepared=False):
     nq, n, E = q.shape[0], c.shape[0], q.shape[1]
     c32 = mx = None
     if prepared:   # what BruteForceIndex does once at build time
-        n_pad = ((n + 255) // 256 + 1) * 256
+        rows_pad = ((n + 255) // 256 + 1) * 256
+        n_pad = rows_pad + rows_pad // 32                      # TT_INDEX_NORM_PAD
         c32 = T.empty_like(dc); mx = T.full((n_pad,), 9.0, dtype=T.float32, device="cuda")
         N.check(lib.tt_index_prepare(dc.data_ptr(), E, n, E, c32.data_ptr(), mx.data_ptr(), stream()))
     s = T.empty((nq, K), dtype=T.float32, device="cuda"); i = T.empty((nq, K), dtype=T.int32, device="cuda")
