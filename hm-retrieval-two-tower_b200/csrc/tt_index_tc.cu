@@ -9,10 +9,11 @@
 //                                only max_j (a_ij - eps_ij) over every group of 32 consecutive corpus rows is
 //                                kept (n/32 floats per query).
 //   2. select_threshold_kernel   lambda_i = K-th largest group value of the query (radix select).
-//   3. rowpanel_kernel<kCollect> same TF32 contraction; every j with a_ij + eps_ij >= lambda_i is appended to
-//                                the query's candidate list (~K entries).
-//   4. rescore_topk_kernel       exact canonical fp32 score of each candidate, then exact top-K.
-//   5. a query whose list overflowed is redone by the exact CUDA-core kernel (tt_index.cu), on the device.
+//   3. rowpanel_kernel<kCollect> same TF32 contraction; every chunk of 32 columns whose maximum can reach lambda_i
+//                                (~1.25 K chunks per query) is dumped whole into the query's hit queue.
+//   4. collect_rescore_kernel    per column: a_ij + eps_ij >= lambda_i -> exact canonical fp32 score from the
+//                                authoritative corpus -> drop s < lambda_i -> exact top-K by (score desc, index asc).
+//   5. a query whose queue or list overflowed is redone by the exact CUDA-core kernel (tt_index.cu), on the device.
 //
 // Why it is exact: |a_ij - s_ij| <= eps_ij (TF32 operand rounding 2^-11 each and Cauchy-Schwarz, plus the fp32
 // accumulation error of both evaluations, with a 2x margin).  K groups hold a row with s >= a - eps >= lambda,
@@ -95,12 +96,12 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
 
 // One CTA per query: lambda = K-th largest of gmax[q][0..ngroups) by a 4-pass MSB radix select.
 __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __restrict__ gmax, int ld, int ngroups, int K,
-                                                               float* __restrict__ thr, int32_t* __restrict__ cnt, int32_t* __restrict__ flags) {
+                                                               float* __restrict__ thr, int32_t* __restrict__ flags) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_remaining;
     const int q = blockIdx.x;
     const float* row = gmax + (int64_t)q * ld;
-    if (threadIdx.x == 0) { cnt[q] = 0; flags[q] = 0; }
+    if (threadIdx.x == 0) flags[q] = 0;
     if (ngroups < K) {   // fewer groups than K: everything is a candidate (the list will overflow unless n is tiny)
         if (threadIdx.x == 0) thr[q] = -CUDART_INF_F;
         return;
@@ -166,64 +167,111 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __re
     if (threadIdx.x == 0) thr[q] = key_to_float(prefix);
 }
 
-// One CTA per query: exact canonical score of every collected candidate, then exact top-K (bitonic sort in smem).
-__global__ void __launch_bounds__(256) rescore_topk_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ C, int ldc, int E, int K,
-                                                           const int32_t* __restrict__ cand, const int32_t* __restrict__ cnt, int cap, int P,
-                                                           Perm pm, int64_t idx_base, float* __restrict__ out_s, int32_t* __restrict__ out_i,
-                                                           int32_t* __restrict__ flags) {
+// One CTA per query.  Walks the query's hit queue (chunks of 32 TF32 scores dumped by rowpanel_kernel<kCollect>), keeps every
+// column with a_j + kappa*||c_j|| >= lambda, computes its exact canonical fp32 score from the authoritative corpus, drops
+// rows with s < lambda (the exact K-th best score is >= lambda, see the file header), and sorts the survivors by
+// (score desc, index asc).  Overflow anywhere hands the query to the exact fallback.
+__global__ void __launch_bounds__(256) collect_rescore_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ C, int ldc, int E,
+                                                              int K, int64_t n, const float* __restrict__ queue, const int32_t* __restrict__ segcnt,
+                                                              int nseg, int cap_seg, const float* __restrict__ norms,
+                                                              const float* __restrict__ eps, const float* __restrict__ thr, int cap, int P, Perm pm,
+                                                              int64_t idx_base, float* __restrict__ out_s, int32_t* __restrict__ out_i,
+                                                              int32_t* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sq = reinterpret_cast<float*>(smem_raw);          // E
+    float* sq = reinterpret_cast<float*>(smem_raw);          // 128 floats: the query row
     float* ss = sq + 128;                                      // P scores
     int32_t* si = reinterpret_cast<int32_t*>(ss + P);          // P indices
+    int32_t* spos = si + P;                                    // cap permuted positions (first-stage list)
+    __shared__ int s_off[257];                                 // exclusive prefix of the segment counts
+    __shared__ int s_n1, s_n2, s_over;
     const int q = blockIdx.x;
-    const int m = cnt[q];
-    if (m > cap) {   // overflow: hand the query to the exact fallback
-        if (threadIdx.x == 0) flags[q] = 1;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_n1 = 0; s_n2 = 0; s_over = 0; }
+    // segment counts -> prefix (nseg <= 256)
+    int c = 0;
+    if (tid < nseg) {
+        c = segcnt[(int64_t)q * nseg + tid];
+        if (c > cap_seg) { c = cap_seg; s_over = 1; }   // benign race: every writer stores 1
+    }
+    s_off[tid + 1] = c;
+    if (tid == 0) s_off[0] = 0;
+    for (int k = tid; k < E; k += 256) sq[k] = Q[(int64_t)q * ldq + k];
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int s = 0; s < nseg; ++s) { run += s_off[s + 1]; s_off[s + 1] = run; }
+    }
+    __syncthreads();
+    if (s_over) {
+        if (tid == 0) flags[q] = 1;
         return;
     }
-    {   // sort only as many slots as this query needs (typically ~K, far below the list capacity)
-        int need = m > K ? m : K;
-        int pq = 2;
-        while (pq < need) pq <<= 1;
-        P = pq < P ? pq : P;
-    }
-    for (int k = threadIdx.x; k < E; k += 256) sq[k] = Q[(int64_t)q * ldq + k];
-    __syncthreads();
-    for (int t = threadIdx.x; t < P; t += 256) {
-        float s = -CUDART_INF_F;
-        int32_t id = 0x7fffffff;
-        if (t < m) {
-            id = (int32_t)perm_orig(pm, cand[(int64_t)q * cap + t]);   // permuted position -> original corpus row
-            const float4* row = reinterpret_cast<const float4*>(C + (int64_t)id * ldc);
-            float acc = 0.f;
-            for (int k4 = 0; k4 < E / 4; ++k4) {   // canonical order: k ascending, one fmaf per term
-                const float4 c = __ldg(row + k4);
-                acc = fmaf(sq[4 * k4], c.x, acc);
-                acc = fmaf(sq[4 * k4 + 1], c.y, acc);
-                acc = fmaf(sq[4 * k4 + 2], c.z, acc);
-                acc = fmaf(sq[4 * k4 + 3], c.w, acc);
-            }
-            s = acc;
+    const int total = s_off[nseg];
+    const float kappa = eps[q], lambda = thr[q];
+    const float* qbase = queue + (int64_t)q * nseg * cap_seg * kHitWords;
+    // stage 1: per-column upper-bound test over every dumped chunk (a warp reads one entry's 32 scores at a time)
+    for (int w = tid >> 5; w < total; w += 8) {
+        int lo = 0, hi = nseg;                    // segment of entry w: largest s with s_off[s] <= w
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_off[mid] <= w) lo = mid; else hi = mid; }
+        const float* ent = qbase + ((int64_t)lo * cap_seg + (w - s_off[lo])) * kHitWords;
+        const int nb = __float_as_int(ent[0]);
+        const int col = nb + (tid & 31);
+        const float a = ent[4 + (tid & 31)];
+        if (col < n && fmaf(kappa, norms[col], a) >= lambda) {
+            const int slot = atomicAdd(&s_n1, 1);
+            if (slot < cap) spos[slot] = col;
         }
-        ss[t] = s;
-        si[t] = id;
     }
     __syncthreads();
-    for (int k = 2; k <= P; k <<= 1) {
+    const int m1 = s_n1;
+    if (m1 > cap) {
+        if (tid == 0) flags[q] = 1;
+        return;
+    }
+    // stage 2: exact canonical score (k ascending, one fmaf per term), exact prune against lambda
+    for (int t = tid; t < m1; t += 256) {
+        const int32_t id = (int32_t)perm_orig(pm, spos[t]);   // permuted position -> original corpus row
+        const float4* row = reinterpret_cast<const float4*>(C + (int64_t)id * ldc);
+        float acc = 0.f;
+        for (int k8 = 0; k8 < E / 8; ++k8) {
+            const float4 c0 = __ldg(row + 2 * k8), c1 = __ldg(row + 2 * k8 + 1);
+            acc = fmaf(sq[8 * k8], c0.x, acc);
+            acc = fmaf(sq[8 * k8 + 1], c0.y, acc);
+            acc = fmaf(sq[8 * k8 + 2], c0.z, acc);
+            acc = fmaf(sq[8 * k8 + 3], c0.w, acc);
+            acc = fmaf(sq[8 * k8 + 4], c1.x, acc);
+            acc = fmaf(sq[8 * k8 + 5], c1.y, acc);
+            acc = fmaf(sq[8 * k8 + 6], c1.z, acc);
+            acc = fmaf(sq[8 * k8 + 7], c1.w, acc);
+        }
+        if (acc >= lambda) {
+            const int slot = atomicAdd(&s_n2, 1);
+            ss[slot] = acc;
+            si[slot] = id;
+        }
+    }
+    __syncthreads();
+    const int m2 = s_n2;
+    int need = m2 > K ? m2 : K, Ps = 2;
+    while (Ps < need) Ps <<= 1;
+    Ps = Ps < P ? Ps : P;
+    for (int t = m2 + tid; t < Ps; t += 256) { ss[t] = -CUDART_INF_F; si[t] = 0x7fffffff; }
+    __syncthreads();
+    for (int k = 2; k <= Ps; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < P / 2; t += 256) {
+            for (int t = tid; t < Ps / 2; t += 256) {
                 int i = 2 * t - (t & (j - 1));
-                int p = i + j;
+                int p2 = i + j;
                 bool up = ((i & k) == 0);
-                float a = ss[i], b = ss[p];
-                int32_t ia = si[i], ib = si[p];
+                float a = ss[i], b = ss[p2];
+                int32_t ia = si[i], ib = si[p2];
                 bool swap = up ? ranks_before(b, ib, a, ia) : ranks_before(a, ia, b, ib);
-                if (swap) { ss[i] = b; ss[p] = a; si[i] = ib; si[p] = ia; }
+                if (swap) { ss[i] = b; ss[p2] = a; si[i] = ib; si[p2] = ia; }
             }
             __syncthreads();
         }
     }
-    for (int t = threadIdx.x; t < K; t += 256) {
+    for (int t = tid; t < K; t += 256) {
         const bool pad = si[t] == 0x7fffffff;
         out_s[(int64_t)q * K + t] = pad ? -CUDART_INF_F : ss[t];
         out_i[(int64_t)q * K + t] = pad ? -1 : (int32_t)(si[t] + idx_base);
@@ -299,8 +347,9 @@ static int launch_idx_e(int E, const CUtensorMap& tmQ, const CUtensorMap& tmC, c
 }
 
 struct IdxLayout {
-    size_t q32, eps, thr, gmax, cnt, flags, cand, c32, norms, exact, total;
+    size_t q32, eps, thr, gmax, cnt, flags, queue, c32, norms, exact, total;
     int ngroups, n_tiles, cap;
+    int m_tiles, splits, tps, nseg, cap_seg;
 };
 
 static IdxLayout layout(int nq, int64_t n, int E, int K, bool need_corpus_copy) {
@@ -308,15 +357,21 @@ static IdxLayout layout(int nq, int64_t n, int E, int K, bool need_corpus_copy) 
     L.n_tiles = (int)ceil_div(n, idx_bn(E));
     L.ngroups = L.n_tiles * (idx_bn(E) / kGroup);
     L.cap = cand_cap(K);
+    L.m_tiles = (int)ceil_div(nq, 128);
+    choose_splits(L.m_tiles, L.n_tiles, 2, 64, &L.splits, &L.tps);
+    L.nseg = L.splits * (idx_bn(E) / 32 >= 2 ? 2 : 1);   // RowPanelCfg::kHalves
+    // hit-queue segment of one (row, split, half): ~1.25 K / nseg qualifying chunks are expected; generous slack because an
+    // overflow costs a trip through the exact CUDA-core fallback
+    L.cap_seg = g_cap_override > 0 ? 1 + g_cap_override / L.nseg : (int)ceil_div(2 * K, L.nseg) + 16;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     L.q32 = take((size_t)nq * E * 4);
     L.eps = take((size_t)nq * 4);
     L.thr = take((size_t)nq * 4);
     L.gmax = take((size_t)nq * L.ngroups * 4);
-    L.cnt = take((size_t)nq * 4);
+    L.cnt = take((size_t)nq * L.nseg * 4);
     L.flags = take((size_t)nq * 4);
-    L.cand = take((size_t)nq * L.cap * 4);
+    L.queue = take((size_t)nq * L.nseg * L.cap_seg * kHitWords * 4);
     L.c32 = take(need_corpus_copy ? (size_t)n * E * 4 : 0);
     L.norms = take(need_corpus_copy ? (size_t)TT_INDEX_NORM_PAD(n) * 4 : 0);
     L.exact = off;
@@ -358,7 +413,7 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
     float* gmax = reinterpret_cast<float*>(base + L.gmax);
     int32_t* cnt = reinterpret_cast<int32_t*>(base + L.cnt);
     int32_t* flags = reinterpret_cast<int32_t*>(base + L.flags);
-    int32_t* cand = reinterpret_cast<int32_t*>(base + L.cand);
+    float* queue = reinterpret_cast<float*>(base + L.queue);
     const float* c32 = C32_in;
     const float* norms = norms_in;
     if (need_copy) {
@@ -377,30 +432,30 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
     if (rc) return rc;
     rc = make_tmap_2d(&tmC, c32, n, E, E, idx_bn(E));   // the prepared copy is dense (ld = E)
     if (rc) return rc;
-    const int m_tiles = (int)ceil_div(nq, 128);
-    int splits = 1, tps = L.n_tiles;
-    choose_splits(m_tiles, L.n_tiles, 2, 64, &splits, &tps);
+    const int m_tiles = L.m_tiles, splits = L.splits, tps = L.tps;
+    TT_REQUIRE(L.nseg <= 256, "tt_index_topk: too many column splits");
     RowPanelParams p{};
     p.nR = nq; p.nT = (int)n; p.n_tiles = L.n_tiles; p.tiles_per_split = tps; p.rowv = eps; p.rowv2 = thr; p.colv2 = norms; p.gnorm = norms + TT_INDEX_ROWS_PAD(n); p.d = -(1 << 30);
     p.out0 = gmax; p.out1 = nullptr; p.out2 = nullptr; p.ld_out = L.ngroups; p.trace = nullptr;
     rc = launch_idx_e<kIndex>(E, tmQ, tmC, p, m_tiles, splits, st, "rowpanel_kernel<index>");
     if (rc) return rc;
-    select_threshold_kernel<<<(unsigned)nq, 256, 0, st>>>(gmax, L.ngroups, (int)ceil_div(n, kGroup), K, thr, cnt, flags);
+    select_threshold_kernel<<<(unsigned)nq, 256, 0, st>>>(gmax, L.ngroups, (int)ceil_div(n, kGroup), K, thr, flags);
     TT_LAUNCH_OK("select_threshold_kernel");
-    p.out0 = reinterpret_cast<float*>(cand);
+    p.out0 = queue;
     p.out1 = reinterpret_cast<float*>(cnt);
-    p.ld_out = L.cap;
+    p.ld_out = L.cap_seg;
     rc = launch_idx_e<kCollect>(E, tmQ, tmC, p, m_tiles, splits, st, "rowpanel_kernel<collect>");
     if (rc) return rc;
     const int P = next_pow2(L.cap < 2 ? 2 : L.cap);
-    const size_t smem = 128 * 4 + (size_t)P * 8;
+    const size_t smem = 128 * 4 + (size_t)P * 8 + (size_t)L.cap * 4;
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
-        TT_CUDA_OK(cudaFuncSetAttribute(rescore_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TT_CUDA_OK(cudaFuncSetAttribute(collect_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    rescore_topk_kernel<<<(unsigned)nq, 256, smem, st>>>(Q, ldq, C, ldc, E, K, cand, cnt, L.cap, P, make_perm(n), idx_base, out_s, out_i, flags);
-    TT_LAUNCH_OK("rescore_topk_kernel");
+    collect_rescore_kernel<<<(unsigned)nq, 256, smem, st>>>(Q, ldq, C, ldc, E, K, n, queue, cnt, L.nseg, L.cap_seg, norms, eps, thr, L.cap, P,
+                                                            make_perm(n), idx_base, out_s, out_i, flags);
+    TT_LAUNCH_OK("collect_rescore_kernel");
     // queries whose candidate list overflowed: exact CUDA-core path, decided on the device (no host sync)
     return index_exact(Q, ldq, C, ldc, nq, n, E, K, idx_base, out_s, out_i, base + L.exact, exact_bytes, st, flags);
 }

@@ -16,8 +16,8 @@
 //           MMA is a K-major tile of T^T (E x BN) loaded by TMA from a transposed copy of T.
 //   kLogits Z = S - colv written out (tests / TwoTowerModel.call)
 //   kIndex  max over each group of 32 consecutive columns                 -> group maxima (filter stage 1)
-//   kCollect every column whose score reaches the row's threshold is appended to the row's candidate list
-//           (filter stage 2; the list is rescored exactly afterwards, so its order does not matter)
+//   kCollect every 32-column chunk that can hold a column reaching the row's threshold is dumped (32 TF32 scores)
+//           into the row's hit queue (filter stage 2; the queue is tested per column and rescored exactly afterwards)
 //
 // The per-column term arrives pre-scaled (colv2 = colv * log2 e, zero padded to whole tiles) and is staged
 // into shared memory by a 1-D bulk copy on the tile's barrier; the epilogue works in the log2 domain with
@@ -42,10 +42,10 @@ struct RowPanelParams {
     const float* colv2;   // per-T-row term * log2(e), padded with zeros to n_tiles*BN entries (never null)
     int d;                // diagonal: column == row + d
     float* out0;          // kFwd: m2 [split][nR] | kBwd: G partial [split][nR][E] | kLogits: Z | kIndex: gmax [nR][ld_out]
-                          // kCollect: (int32*) candidate column lists [nR][ld_out]
-    float* out1;          // kFwd: l  [split][nR] | kCollect: (int32*) list lengths [nR] (may exceed ld_out: overflow)
+                          // kCollect: hit queue [nR][splits*halves][ld_out][kHitWords]
+    float* out1;          // kFwd: l  [split][nR] | kCollect: (int32*) hits per segment [nR][splits*halves] (may exceed ld_out: overflow)
     float* out2;          // kFwd: zdiag [nR] (natural units; written by the split that owns the diagonal column)
-    int ld_out;           // kLogits: ldz | kIndex: row stride of gmax (groups) | kCollect: list capacity
+    int ld_out;           // kLogits: ldz | kIndex: row stride of gmax (groups) | kCollect: entries per queue segment
     unsigned long long* trace;  // optional debug timeline: [cta][16] globaltimer stamps (ns); null in production
 };
 
@@ -59,6 +59,7 @@ __device__ __forceinline__ unsigned long long gtime() {
         if (p.trace) p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime();          \
     } while (0)
 
+constexpr int kHitWords = 36;   // hit-queue entry: {first column, 3 pad words, 32 TF32 scores} = 144 bytes
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -87,6 +88,24 @@ __device__ __forceinline__ void sts128(uint32_t saddr, float a, float b, float c
 // inputs, without occupying the transcendental/conversion unit the exponentials need
 __device__ __forceinline__ float tf32_rn_int(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
+// 3-input maximum (one FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// maximum of the 32 accumulator words of one chunk: 16 FMNMX3
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32]) {
+    float m0 = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
+    float m1 = fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3]));
+#pragma unroll
+    for (int i = 4; i < 32; i += 4) {
+        m0 = fmax3(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        m1 = fmax3(m1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+    }
+    return fmaxf(m0, m1);
+}
+
 // issue only (no wait): 32 lanes x 32 columns
 __device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -114,16 +133,13 @@ struct RowPanelCfg {
     static constexpr int kPSlabs = BN / 32;
     static constexpr int kPBytes = (MODE == kBwd) ? kPSlabs * 128 * 128 : 0;
     static constexpr int kPBufs = (MODE == kBwd) ? 2 : 0;
-    static constexpr bool kUsesC2 = (MODE != kIndex);   // staged per-column vector (softmax: colv*log2e; kCollect: row norms)
+    static constexpr bool kUsesC2 = (MODE != kIndex && MODE != kCollect);   // staged per-column vector (softmax: colv * log2 e)
     static constexpr int kC2Bytes = kUsesC2 ? BN * 4 : 0;
     static constexpr int kHalves = (BN / 32 >= 2) ? 2 : 1;                   // epilogue warps per TMEM lane quarter
     static constexpr int kEpiWarps = 4 * kHalves;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
     static constexpr int kTmemCols = (MODE == kBwd) ? (2 * BN + E <= 256 ? 256 : 512) : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
-    static constexpr int kListCap = 47;                                      // kCollect: per-row candidate slots staged in smem
-    static constexpr int kListBytes = (MODE == kCollect) ? 128 * (kListCap + 1) * 4 : 0;
-    static constexpr int kSmemBytes = kRBytes + kStages * kTBytes + kPBufs * kPBytes + 4 * 1024 /*c2 stages*/ + 1024 /*barriers*/ + kListBytes +
-                                      1024 /*align*/;
+    static constexpr int kSmemBytes = kRBytes + kStages * kTBytes + kPBufs * kPBytes + 4 * 1024 /*c2 stages*/ + 1024 /*barriers*/ + 1024 /*align*/;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
     static_assert(E == 32 || E == 64 || E == 128, "E must be 32, 64 or 128");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 up to 256");
@@ -212,10 +228,6 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
     unsigned char* sP = sT + Cfg::kStages * Cfg::kTBytes;
     unsigned char* sC2 = sP + Cfg::kPBufs * Cfg::kPBytes;       // kStages x 1 KB
     RowPanelBars* bars = reinterpret_cast<RowPanelBars*>(sC2 + 4 * 1024);
-    int32_t* sList = reinterpret_cast<int32_t*>(sC2 + 4 * 1024 + 1024);   // kCollect: [128][kListCap + 1], slot 0 = count
-    if (MODE == kCollect) {
-        for (int r = threadIdx.x; r < 128; r += blockDim.x) sList[r * (Cfg::kListCap + 1)] = 0;
-    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * 128;
@@ -335,6 +347,11 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         if (MODE == kCollect) r3 = (row < p.nR) ? __ldg(p.rowv2 + row) : CUDART_INF_F;              // lambda_q
         constexpr int NC = BN / 32;
         constexpr int NCW = NC / Cfg::kHalves;        // 32-column chunks per warp per tile
+        // kCollect: this lane's private segment of the hit queue
+        const int nseg = gridDim.y * Cfg::kHalves;
+        const int seg = blockIdx.y * Cfg::kHalves + half;
+        float* qseg = (MODE == kCollect && row < p.nR) ? p.out0 + ((int64_t)row * nseg + seg) * p.ld_out * kHitWords : nullptr;
+        int n_hit = 0;                                // rows beyond nR have lambda = +inf and never record
         const int c_first = half * NCW;
         for (int it = 0; it < my_tiles; ++it) {
             const int acc = it & 1;
@@ -382,50 +399,26 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                         }
                     }
                 } else if constexpr (MODE == kCollect) {
-                    // upper bounds U_j = a_j + kappa*||c_j|| >= s_j; collect every j with U_j >= lambda.  Pre-filter with
-                    // the chunk's largest norm (one FFMA per chunk), descend through quad maxima only on a hit.
-                    const float thr_c = fmaf(-r2, __ldg(p.gnorm + (nb >> 5)), r3);   // lambda - kappa * max_j ||c_j||
-                    float m4[8];
-                    float mx = -CUDART_INF_F;
+                    // A chunk can hold a column with a_j + kappa*||c_j|| >= lambda only if max_j a_j >= lambda - kappa*max_j||c_j||.
+                    // The (rare, ~K per row) qualifying chunks are dumped whole -- 32 TF32 scores + the chunk's first column --
+                    // into this (row, split, half) segment of the hit queue; collect_rescore_kernel does the per-column test.
+                    // No atomics: the segment belongs to this lane alone, so the queue order is deterministic.
+                    const float thr_c = fmaf(-r2, __ldg(p.gnorm + (nb >> 5)), r3);
+                    if (chunk_max(r) >= thr_c) {
+                        if (n_hit < p.ld_out) {
+                            float4* dst = reinterpret_cast<float4*>(qseg + (int64_t)n_hit * kHitWords);
+                            dst[0] = make_float4(__int_as_float(nb), 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        m4[g4] = fmaxf(fmaxf(__uint_as_float(r[g4 * 4]), __uint_as_float(r[g4 * 4 + 1])),
-                                       fmaxf(__uint_as_float(r[g4 * 4 + 2]), __uint_as_float(r[g4 * 4 + 3])));
-                        mx = fmaxf(mx, m4[g4]);
-                    }
-                    if (mx >= thr_c) {   // about one hit per warp-chunk
-                        int32_t* lists = reinterpret_cast<int32_t*>(p.out0);
-                        int32_t* lens = reinterpret_cast<int32_t*>(p.out1);
-#pragma unroll
-                        for (int g4 = 0; g4 < 8; ++g4) {
-                            if (m4[g4] >= thr_c) {
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    const int n = nb + g4 * 4 + t;
-                                    const float a = __uint_as_float(r[g4 * 4 + t]);
-                                    float nrm;   // staged row norm: a global load here would put ~L2 latency on every hit
-                                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(nrm) : "r"(c2s + (c * 32 + g4 * 4 + t) * 4));
-                                    if (a >= thr_c && n < p.nT && fmaf(r2, nrm, a) >= r3) {
-                                        // stage in shared memory (a returning global atomic per hit would cost ~1 us of latency)
-                                        int32_t* mine = sList + row_l * (Cfg::kListCap + 1);
-                                        const int ls = atomicAdd(mine, 1);
-                                        if (ls < Cfg::kListCap) mine[1 + ls] = n;
-                                        else {   // staged list full: rare direct push
-                                            const int slot = atomicAdd(lens + row, 1);
-                                            if (slot < p.ld_out) lists[(int64_t)row * p.ld_out + slot] = n;
-                                        }
-                                    }
-                                }
-                            }
+                            for (int g4 = 0; g4 < 8; ++g4)
+                                dst[1 + g4] = make_float4(__uint_as_float(r[g4 * 4]), __uint_as_float(r[g4 * 4 + 1]), __uint_as_float(r[g4 * 4 + 2]),
+                                                          __uint_as_float(r[g4 * 4 + 3]));
                         }
+                        ++n_hit;
                     }
                 } else {  // kIndex: per chunk, max_j a_j - kappa * max_j ||c_j||  <=  max_j (a_j - kappa*||c_j||)  <=  max_j s_j
                     float mx = -CUDART_INF_F;
                     if (fast || nb + 32 <= p.nT) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
-                                                 fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]))));
+                        mx = chunk_max(r);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (nb + i < p.nT) ? __uint_as_float(r[i]) : -CUDART_INF_F);
@@ -461,19 +454,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
             }
         }
         if constexpr (MODE == kCollect) {
-            // both halves of every row are done: flush the staged candidates with ONE global atomic per row
-            asm volatile("bar.sync 1, %0;" ::"r"(32 * Cfg::kEpiWarps) : "memory");
-            if (half == 0 && row < p.nR) {
-                int32_t* lists = reinterpret_cast<int32_t*>(p.out0);
-                int32_t* lens = reinterpret_cast<int32_t*>(p.out1);
-                const int32_t* mine = sList + row_l * (Cfg::kListCap + 1);
-                const int m = min(mine[0], Cfg::kListCap);
-                if (m > 0) {
-                    const int base = atomicAdd(lens + row, m);
-                    for (int t = 0; t < m; ++t)
-                        if (base + t < p.ld_out) lists[(int64_t)row * p.ld_out + base + t] = mine[1 + t];
-                }
-            }
+            if (row < p.nR) reinterpret_cast<int32_t*>(p.out1)[(int64_t)row * nseg + seg] = n_hit;   // may exceed the capacity: overflow
         }
         if constexpr (MODE == kFwd) {
             if (row < p.nR) {
