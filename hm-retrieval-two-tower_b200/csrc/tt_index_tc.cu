@@ -94,12 +94,17 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
     if (lane == 0) eps[q] = kEpsCoef * sqrtf(s) * 1.0001f + 1e-30f;
 }
 
-// One CTA per query: lambda = K-th largest of gmax[q][0..ngroups) by a 4-pass MSB radix select.
+// One CTA per query: lambda = a lower bound, tight to 16 significant bits, of the K-th largest of gmax[q][0..ngroups).
+// Any lambda <= the K-th largest group value keeps the filter exact (a smaller lambda only admits more candidates), so
+// the radix select skips the bits every key shares (group maxima of one query differ only from about the 9th bit on:
+// without the skip nearly all keys land in one histogram bin and the shared-memory atomics serialise) and stops after
+// two 8-bit digits, returning the lower edge of the bin that holds the K-th largest key.
 __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __restrict__ gmax, int ld, int ngroups, int K,
                                                                float* __restrict__ thr, int32_t* __restrict__ flags) {
     __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_prefix, s_remaining;
+    __shared__ uint32_t s_prefix, s_remaining, s_red[16];
     const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* row = gmax + (int64_t)q * ld;
     if (threadIdx.x == 0) flags[q] = 0;
     if (ngroups < K) {   // fewer groups than K: everything is a candidate (the list will overflow unless n is tiny)
@@ -109,33 +114,58 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __re
     constexpr int kCache = 16;                         // values cached in registers when the row is short
     uint32_t cache[kCache];
     const bool cached = ngroups <= kCache * 256;
+    uint32_t kmax = 0u, kmin = 0xFFFFFFFFu;
     if (cached) {
 #pragma unroll
         for (int i = 0; i < kCache; ++i) {
             int g = threadIdx.x + i * 256;
-            cache[i] = g < ngroups ? ordered_key(row[g]) : 0u;   // key 0 sorts below every real value
+            cache[i] = g < ngroups ? ordered_key(row[g]) : 0u;
+            if (g < ngroups) { kmax = max(kmax, cache[i]); kmin = min(kmin, cache[i]); }
+        }
+    } else {
+        for (int g = threadIdx.x; g < ngroups; g += 256) {
+            uint32_t k = ordered_key(row[g]);
+            kmax = max(kmax, k); kmin = min(kmin, k);
         }
     }
-    uint32_t prefix = 0, mask = 0, remaining = (uint32_t)K;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    }
+    if (lane == 0) { s_red[warp] = kmax; s_red[8 + warp] = kmin; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { kmax = max(kmax, s_red[w]); kmin = min(kmin, s_red[8 + w]); }
+    const uint32_t diff = kmax ^ kmin;
+    if (diff == 0u) {   // every group has the same value
+        if (threadIdx.x == 0) thr[q] = key_to_float(kmax);
+        return;
+    }
+    const int common = __clz(diff);                    // leading bits shared by every key
+    uint32_t mask = common ? (0xFFFFFFFFu << (32 - common)) : 0u;
+    uint32_t prefix = kmax & mask, remaining = (uint32_t)K;
+    int shift = 32 - common;
+    for (int pass = 0; pass < 2 && shift > 0; ++pass) {
+        const int bits = shift < 8 ? shift : 8;
+        shift -= bits;
+        const uint32_t dmask = (1u << bits) - 1u;
         hist[threadIdx.x] = 0;
         __syncthreads();
         if (cached) {
 #pragma unroll
             for (int i = 0; i < kCache; ++i) {
                 int g = threadIdx.x + i * 256;
-                if (g < ngroups && (cache[i] & mask) == prefix) atomicAdd(&hist[(cache[i] >> shift) & 255], 1u);
+                if (g < ngroups && (cache[i] & mask) == prefix) atomicAdd(&hist[(cache[i] >> shift) & dmask], 1u);
             }
         } else {
             for (int g = threadIdx.x; g < ngroups; g += 256) {
                 uint32_t k = ordered_key(row[g]);
-                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1u);
+                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & dmask], 1u);
             }
         }
         __syncthreads();
         if (threadIdx.x < 32) {   // warp 0: find the bin holding the `remaining`-th largest key (suffix scan over 256 bins)
-            const int lane = threadIdx.x;
             uint32_t c[8], tot = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; tot += c[i]; }
@@ -162,17 +192,21 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __re
         __syncthreads();
         prefix = s_prefix;
         remaining = s_remaining;
-        mask |= 255u << shift;
+        mask |= dmask << shift;
     }
-    if (threadIdx.x == 0) thr[q] = key_to_float(prefix);
+    if (threadIdx.x == 0) {
+        float v = key_to_float(prefix);                // unresolved low bits are zero: the lower edge of the bin
+        thr[q] = (v == v) ? v : -CUDART_INF_F;
+    }
 }
 
 // One CTA per query.  Walks the query's hit queue (chunks of 32 TF32 scores dumped by rowpanel_kernel<kCollect>), keeps every
 // column with a_j + kappa*||c_j|| >= lambda, computes its exact canonical fp32 score from the authoritative corpus, drops
 // rows with s < lambda (the exact K-th best score is >= lambda, see the file header), and sorts the survivors by
 // (score desc, index asc).  Overflow anywhere hands the query to the exact fallback.
-__global__ void __launch_bounds__(256) collect_rescore_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ C, int ldc, int E,
-                                                              int K, int64_t n, const float* __restrict__ queue, const int32_t* __restrict__ segcnt,
+template <int E>
+__global__ void __launch_bounds__(256) collect_rescore_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ C, int ldc, int K,
+                                                              int64_t n, const float* __restrict__ queue, const int32_t* __restrict__ segcnt,
                                                               int nseg, int cap_seg, const float* __restrict__ norms,
                                                               const float* __restrict__ eps, const float* __restrict__ thr, int cap, int P, Perm pm,
                                                               int64_t idx_base, float* __restrict__ out_s, int32_t* __restrict__ out_i,
@@ -182,44 +216,41 @@ __global__ void __launch_bounds__(256) collect_rescore_kernel(const float* __res
     float* ss = sq + 128;                                      // P scores
     int32_t* si = reinterpret_cast<int32_t*>(ss + P);          // P indices
     int32_t* spos = si + P;                                    // cap permuted positions (first-stage list)
-    __shared__ int s_off[257];                                 // exclusive prefix of the segment counts
-    __shared__ int s_n1, s_n2, s_over;
+    __shared__ int s_n1, s_n2;
     const int q = blockIdx.x;
-    const int tid = threadIdx.x;
-    if (tid == 0) { s_n1 = 0; s_n2 = 0; s_over = 0; }
-    // segment counts -> prefix (nseg <= 256)
-    int c = 0;
-    if (tid < nseg) {
-        c = segcnt[(int64_t)q * nseg + tid];
-        if (c > cap_seg) { c = cap_seg; s_over = 1; }   // benign race: every writer stores 1
-    }
-    s_off[tid + 1] = c;
-    if (tid == 0) s_off[0] = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_n1 = 0; s_n2 = 0; }
+    const int my_cnt = tid < nseg ? segcnt[(int64_t)q * nseg + tid] : 0;
     for (int k = tid; k < E; k += 256) sq[k] = Q[(int64_t)q * ldq + k];
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int s = 0; s < nseg; ++s) { run += s_off[s + 1]; s_off[s + 1] = run; }
-    }
-    __syncthreads();
-    if (s_over) {
+    if (__syncthreads_or(my_cnt > cap_seg)) {   // a queue segment overflowed
         if (tid == 0) flags[q] = 1;
         return;
     }
-    const int total = s_off[nseg];
     const float kappa = eps[q], lambda = thr[q];
     const float* qbase = queue + (int64_t)q * nseg * cap_seg * kHitWords;
-    // stage 1: per-column upper-bound test over every dumped chunk (a warp reads one entry's 32 scores at a time)
-    for (int w = tid >> 5; w < total; w += 8) {
-        int lo = 0, hi = nseg;                    // segment of entry w: largest s with s_off[s] <= w
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_off[mid] <= w) lo = mid; else hi = mid; }
-        const float* ent = qbase + ((int64_t)lo * cap_seg + (w - s_off[lo])) * kHitWords;
-        const int nb = __float_as_int(ent[0]);
-        const int col = nb + (tid & 31);
-        const float a = ent[4 + (tid & 31)];
-        if (col < n && fmaf(kappa, norms[col], a) >= lambda) {
-            const int slot = atomicAdd(&s_n1, 1);
-            if (slot < cap) spos[slot] = col;
+    // stage 1: per-column upper-bound test; a warp takes whole segments, four entries in flight
+    for (int s = warp; s < nseg; s += 8) {
+        const int cnt = __shfl_sync(0xffffffffu, segcnt[(int64_t)q * nseg + s], 0);
+        const float* sb = qbase + (int64_t)s * cap_seg * kHitWords;
+        for (int e0 = 0; e0 < cnt; e0 += 4) {
+            float a[4];
+            int nb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = min(e0 + u, cnt - 1);
+                nb[u] = __float_as_int(__ldg(sb + e * kHitWords));
+                a[u] = __ldg(sb + e * kHitWords + 4 + lane);
+            }
+            float nr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nr[u] = (nb[u] + lane < n) ? __ldg(norms + nb[u] + lane) : -CUDART_INF_F;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (e0 + u < cnt && fmaf(kappa, nr[u], a[u]) >= lambda) {   // -inf norm: column beyond the corpus
+                    const int slot = atomicAdd(&s_n1, 1);
+                    if (slot < cap) spos[slot] = nb[u] + lane;
+                }
+            }
         }
     }
     __syncthreads();
@@ -232,17 +263,17 @@ __global__ void __launch_bounds__(256) collect_rescore_kernel(const float* __res
     for (int t = tid; t < m1; t += 256) {
         const int32_t id = (int32_t)perm_orig(pm, spos[t]);   // permuted position -> original corpus row
         const float4* row = reinterpret_cast<const float4*>(C + (int64_t)id * ldc);
+        float4 cv[E / 4];
+#pragma unroll
+        for (int k4 = 0; k4 < E / 4; ++k4) cv[k4] = __ldg(row + k4);
         float acc = 0.f;
-        for (int k8 = 0; k8 < E / 8; ++k8) {
-            const float4 c0 = __ldg(row + 2 * k8), c1 = __ldg(row + 2 * k8 + 1);
-            acc = fmaf(sq[8 * k8], c0.x, acc);
-            acc = fmaf(sq[8 * k8 + 1], c0.y, acc);
-            acc = fmaf(sq[8 * k8 + 2], c0.z, acc);
-            acc = fmaf(sq[8 * k8 + 3], c0.w, acc);
-            acc = fmaf(sq[8 * k8 + 4], c1.x, acc);
-            acc = fmaf(sq[8 * k8 + 5], c1.y, acc);
-            acc = fmaf(sq[8 * k8 + 6], c1.z, acc);
-            acc = fmaf(sq[8 * k8 + 7], c1.w, acc);
+#pragma unroll
+        for (int k4 = 0; k4 < E / 4; ++k4) {
+            const float4 qv = *reinterpret_cast<const float4*>(sq + 4 * k4);
+            acc = fmaf(qv.x, cv[k4].x, acc);
+            acc = fmaf(qv.y, cv[k4].y, acc);
+            acc = fmaf(qv.z, cv[k4].z, acc);
+            acc = fmaf(qv.w, cv[k4].w, acc);
         }
         if (acc >= lambda) {
             const int slot = atomicAdd(&s_n2, 1);
@@ -448,13 +479,14 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
     if (rc) return rc;
     const int P = next_pow2(L.cap < 2 ? 2 : L.cap);
     const size_t smem = 128 * 4 + (size_t)P * 8 + (size_t)L.cap * 4;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        TT_CUDA_OK(cudaFuncSetAttribute(collect_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
-    collect_rescore_kernel<<<(unsigned)nq, 256, smem, st>>>(Q, ldq, C, ldc, E, K, n, queue, cnt, L.nseg, L.cap_seg, norms, eps, thr, L.cap, P,
-                                                            make_perm(n), idx_base, out_s, out_i, flags);
+    auto launch_rescore = [&](auto kern) -> int {
+        if (smem > 48 * 1024) TT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)nq, 256, smem, st>>>(Q, ldq, C, ldc, K, n, queue, cnt, L.nseg, L.cap_seg, norms, eps, thr, L.cap, P, make_perm(n), idx_base,
+                                             out_s, out_i, flags);
+        return TT_OK;
+    };
+    rc = E == 32 ? launch_rescore(collect_rescore_kernel<32>) : E == 64 ? launch_rescore(collect_rescore_kernel<64>) : launch_rescore(collect_rescore_kernel<128>);
+    if (rc) return rc;
     TT_LAUNCH_OK("collect_rescore_kernel");
     // queries whose candidate list overflowed: exact CUDA-core path, decided on the device (no host sync)
     return index_exact(Q, ldq, C, ldc, nq, n, E, K, idx_base, out_s, out_i, base + L.exact, exact_bytes, st, flags);

@@ -361,6 +361,20 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
             const int pb = it & 1;
             // warp-uniform: tile fully in range and no diagonal element of this warp's rows inside it
             const bool fast = (n0 + BN <= p.nT) && (wrow0 + 32 <= p.nR) && (wrow0 + p.d + 32 <= n0 || wrow0 + p.d >= n0 + BN);
+            float gn[NCW];                            // kIndex/kCollect: chunk norm maxima, fetched before the wait on the accumulator
+            if constexpr (MODE == kIndex || MODE == kCollect) {
+                const float* src = p.gnorm + (n0 >> 5) + c_first;
+                if constexpr (NCW % 4 == 0) {
+#pragma unroll
+                    for (int c4 = 0; c4 < NCW; c4 += 4) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(src + c4));
+                        gn[c4] = v.x; gn[c4 + 1] = v.y; gn[c4 + 2] = v.z; gn[c4 + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c1 = 0; c1 < NCW; ++c1) gn[c1] = __ldg(src + c1);
+                }
+            }
             mbar_wait(&bars->s_full[acc], aph);
             tc_fence_after();
             if (Cfg::kUsesC2) mbar_wait(&bars->t_full[stage], (it / Cfg::kStages) & 1);   // completed long ago; acquires the staged column term
@@ -403,7 +417,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                     // The (rare, ~K per row) qualifying chunks are dumped whole -- 32 TF32 scores + the chunk's first column --
                     // into this (row, split, half) segment of the hit queue; collect_rescore_kernel does the per-column test.
                     // No atomics: the segment belongs to this lane alone, so the queue order is deterministic.
-                    const float thr_c = fmaf(-r2, __ldg(p.gnorm + (nb >> 5)), r3);
+                    const float thr_c = fmaf(-r2, gn[cl], r3);
                     if (chunk_max(r) >= thr_c) {
                         if (n_hit < p.ld_out) {
                             float4* dst = reinterpret_cast<float4*>(qseg + (int64_t)n_hit * kHitWords);
@@ -423,8 +437,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
 #pragma unroll
                         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (nb + i < p.nT) ? __uint_as_float(r[i]) : -CUDART_INF_F);
                     }
-                    mx = fmaf(-r2, __ldg(p.gnorm + (nb >> 5)), mx);
-                    gm[cl] = mx;
+                    gm[cl] = fmaf(-r2, gn[cl], mx);
                 }
             }
             // this S buffer may be overwritten by the MMA of tile it+2
