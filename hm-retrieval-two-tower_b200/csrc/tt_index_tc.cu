@@ -6,19 +6,21 @@
 // heavy lifting runs in TF32 on tcgen05:
 //
 //   1. rowpanel_kernel<kIndex>   TF32 scores a_ij with the error bound eps_ij = kappa_i*||c_j||, kappa_i = 2^-9*||q_i||;
-//                                only max_j (a_ij - eps_ij) over every group of 32 consecutive corpus rows is
-//                                kept (n/32 floats per query).
-//   2. select_threshold_kernel   lambda_i = K-th largest group value of the query (radix select).
+//                                only a lower bound of the best score of every group of consecutive corpus rows
+//                                (128 rows; 32 for small corpora) is kept: max_j a_ij - kappa_i * max_j ||c_j||.
+//   2. select_threshold_kernel   lambda_i = (a lower bound, tight to 16 bits, of) the K-th largest group value.
 //   3. rowpanel_kernel<kCollect> same TF32 contraction; every chunk of 32 columns whose maximum can reach lambda_i
-//                                (~1.25 K chunks per query) is dumped whole into the query's hit queue.
-//   4. collect_rescore_kernel    per column: a_ij + eps_ij >= lambda_i -> exact canonical fp32 score from the
-//                                authoritative corpus -> drop s < lambda_i -> exact top-K by (score desc, index asc).
-//   5. a query whose queue or list overflowed is redone by the exact CUDA-core kernel (tt_index.cu), on the device.
+//                                (~1.25 K chunks per query) is appended whole to the dumping warp's hit log.
+//   4. column_test_kernel        per logged column: a_ij >= lambda_i - kappa_i * max_chunk ||c|| -> the query's list.
+//   5. exact_score_kernel        exact canonical fp32 score of every listed column from the authoritative corpus; rows
+//                                with s < lambda_i are dropped.
+//   6. sort_topk_kernel          exact top-K by (score desc, index asc).
+//   7. a query whose log or list overflowed is redone by the exact CUDA-core kernel (tt_index.cu), on the device.
 //
 // Why it is exact: |a_ij - s_ij| <= eps_ij (TF32 operand rounding 2^-11 each and Cauchy-Schwarz, plus the fp32
 // accumulation error of both evaluations, with a 2x margin).  K groups hold a row with s >= a - eps >= lambda,
 // so the exact K-th best score s_K >= lambda; every true top-K row has s >= s_K, hence a + eps >= lambda, and is
-// collected; step 4 orders the collected rows by the exact (score desc, index asc) rule.
+// listed; steps 5-6 order the listed rows by the exact (score desc, index asc) rule.
 #include "tt_tc_rowpanel.cuh"
 
 namespace tt {
@@ -32,13 +34,16 @@ bool softmax_tc_supported(int ldq, int ldc, int E, const void* Q, const void* C)
 
 namespace tc {
 
-constexpr int kGroup = 32;
 static inline int idx_bn(int E) { return E <= 64 ? 256 : 128; }   // shared-memory budget of the T ring
+static inline int idx_halves(int E) { return idx_bn(E) / 32 >= 2 ? 2 : 1; }   // RowPanelCfg::kHalves
 constexpr float kEpsCoef = 1.0f / 512.0f;   // 2^-9
 static int g_cap_override = 0;              // tests: force tiny candidate lists to exercise the fallback
 
-static inline int cand_cap(int K) { return g_cap_override > 0 ? g_cap_override : 4 * K + 512; }
-static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+static inline int cand_cap(int K) {   // listed columns per query (a power of two: it is also the largest sort size)
+    int c = 128;
+    while (c < K + K / 2 + 32) c <<= 1;
+    return c < 1024 ? c : 1024;
+}
 
 __device__ __forceinline__ uint32_t ordered_key(float f) {   // monotone float -> uint
     uint32_t b = __float_as_uint(f);
@@ -96,35 +101,37 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
 
 // One CTA per query: lambda = a lower bound, tight to 16 significant bits, of the K-th largest of gmax[q][0..ngroups).
 // Any lambda <= the K-th largest group value keeps the filter exact (a smaller lambda only admits more candidates), so
-// the radix select skips the bits every key shares (group maxima of one query differ only from about the 9th bit on:
+// the radix select skips the bits every key shares (group values of one query differ only from about the 9th bit on:
 // without the skip nearly all keys land in one histogram bin and the shared-memory atomics serialise) and stops after
 // two 8-bit digits, returning the lower edge of the bin that holds the K-th largest key.
-__global__ void __launch_bounds__(256) select_threshold_kernel(const float* __restrict__ gmax, int ld, int ngroups, int K,
-                                                               float* __restrict__ thr, int32_t* __restrict__ flags) {
+constexpr int kSelectThreads = 128;
+constexpr int kSelectCache = 8;                        // keys held in registers per thread (rows up to 1024 groups; longer rows are re-read)
+__global__ void __launch_bounds__(kSelectThreads) select_threshold_kernel(const float* __restrict__ gmax, int ld, int ngroups, int K,
+                                                                          float* __restrict__ thr, int32_t* __restrict__ flags,
+                                                                          int32_t* __restrict__ cand_cnt) {
     __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_prefix, s_remaining, s_red[16];
+    __shared__ uint32_t s_prefix, s_remaining, s_red[2 * kSelectThreads / 32];
     const int q = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* row = gmax + (int64_t)q * ld;
-    if (threadIdx.x == 0) flags[q] = 0;
+    if (tid == 0) { flags[q] = 0; cand_cnt[q] = 0; }
     if (ngroups < K) {   // fewer groups than K: everything is a candidate (the list will overflow unless n is tiny)
-        if (threadIdx.x == 0) thr[q] = -CUDART_INF_F;
+        if (tid == 0) thr[q] = -CUDART_INF_F;
         return;
     }
-    constexpr int kCache = 16;                         // values cached in registers when the row is short
-    uint32_t cache[kCache];
-    const bool cached = ngroups <= kCache * 256;
+    uint32_t cache[kSelectCache];
+    const bool cached = ngroups <= kSelectCache * kSelectThreads;
     uint32_t kmax = 0u, kmin = 0xFFFFFFFFu;
     if (cached) {
 #pragma unroll
-        for (int i = 0; i < kCache; ++i) {
-            int g = threadIdx.x + i * 256;
-            cache[i] = g < ngroups ? ordered_key(row[g]) : 0u;
+        for (int i = 0; i < kSelectCache; ++i) {
+            const int g = tid + i * kSelectThreads;
+            cache[i] = g < ngroups ? ordered_key(__ldg(row + g)) : 0u;
             if (g < ngroups) { kmax = max(kmax, cache[i]); kmin = min(kmin, cache[i]); }
         }
     } else {
-        for (int g = threadIdx.x; g < ngroups; g += 256) {
-            uint32_t k = ordered_key(row[g]);
+        for (int g = tid; g < ngroups; g += kSelectThreads) {
+            const uint32_t k = ordered_key(__ldg(row + g));
             kmax = max(kmax, k); kmin = min(kmin, k);
         }
     }
@@ -133,13 +140,13 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __re
         kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
         kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
     }
-    if (lane == 0) { s_red[warp] = kmax; s_red[8 + warp] = kmin; }
+    if (lane == 0) { s_red[warp] = kmax; s_red[kSelectThreads / 32 + warp] = kmin; }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { kmax = max(kmax, s_red[w]); kmin = min(kmin, s_red[8 + w]); }
+    for (int w = 0; w < kSelectThreads / 32; ++w) { kmax = max(kmax, s_red[w]); kmin = min(kmin, s_red[kSelectThreads / 32 + w]); }
     const uint32_t diff = kmax ^ kmin;
     if (diff == 0u) {   // every group has the same value
-        if (threadIdx.x == 0) thr[q] = key_to_float(kmax);
+        if (tid == 0) thr[q] = key_to_float(kmax);
         return;
     }
     const int common = __clz(diff);                    // leading bits shared by every key
@@ -150,35 +157,33 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __re
         const int bits = shift < 8 ? shift : 8;
         shift -= bits;
         const uint32_t dmask = (1u << bits) - 1u;
-        hist[threadIdx.x] = 0;
+        hist[tid] = 0; hist[tid + kSelectThreads] = 0;
         __syncthreads();
         if (cached) {
 #pragma unroll
-            for (int i = 0; i < kCache; ++i) {
-                int g = threadIdx.x + i * 256;
+            for (int i = 0; i < kSelectCache; ++i) {
+                const int g = tid + i * kSelectThreads;
                 if (g < ngroups && (cache[i] & mask) == prefix) atomicAdd(&hist[(cache[i] >> shift) & dmask], 1u);
             }
         } else {
-            for (int g = threadIdx.x; g < ngroups; g += 256) {
-                uint32_t k = ordered_key(row[g]);
+            for (int g = tid; g < ngroups; g += kSelectThreads) {
+                const uint32_t k = ordered_key(__ldg(row + g));
                 if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & dmask], 1u);
             }
         }
         __syncthreads();
-        if (threadIdx.x < 32) {   // warp 0: find the bin holding the `remaining`-th largest key (suffix scan over 256 bins)
+        if (tid < 32) {   // warp 0: find the bin holding the `remaining`-th largest key (suffix scan over 256 bins)
             uint32_t c[8], tot = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; tot += c[i]; }
-            uint32_t above = 0;   // keys in bins of higher lanes
             uint32_t run = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t v = __shfl_down_sync(0xffffffffu, run, o);
                 if (lane + o < 32) run += v;
             }
-            above = run - tot;    // run = inclusive suffix sum over lanes >= lane
-            const bool mine = above < remaining && remaining <= above + tot;
-            if (mine) {
+            const uint32_t above = run - tot;    // keys in bins of higher lanes (run = inclusive suffix sum over lanes >= lane)
+            if (above < remaining && remaining <= above + tot) {
                 uint32_t cum = above;
                 int b = 7;
                 for (; b > 0; --b) {
@@ -194,124 +199,188 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const float* __re
         remaining = s_remaining;
         mask |= dmask << shift;
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         float v = key_to_float(prefix);                // unresolved low bits are zero: the lower edge of the bin
         thr[q] = (v == v) ? v : -CUDART_INF_F;
     }
 }
 
-// One CTA per query.  Walks the query's hit queue (chunks of 32 TF32 scores dumped by rowpanel_kernel<kCollect>), keeps every
-// column with a_j + kappa*||c_j|| >= lambda, computes its exact canonical fp32 score from the authoritative corpus, drops
-// rows with s < lambda (the exact K-th best score is >= lambda, see the file header), and sorts the survivors by
-// (score desc, index asc).  Overflow anywhere hands the query to the exact fallback.
-template <int E>
-__global__ void __launch_bounds__(256) collect_rescore_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ C, int ldc, int K,
-                                                              int64_t n, const float* __restrict__ queue, const int32_t* __restrict__ segcnt,
-                                                              int nseg, int cap_seg, const float* __restrict__ norms,
-                                                              const float* __restrict__ eps, const float* __restrict__ thr, int cap, int P, Perm pm,
-                                                              int64_t idx_base, float* __restrict__ out_s, int32_t* __restrict__ out_i,
-                                                              int32_t* __restrict__ flags) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sq = reinterpret_cast<float*>(smem_raw);          // 128 floats: the query row
-    float* ss = sq + 128;                                      // P scores
-    int32_t* si = reinterpret_cast<int32_t*>(ss + P);          // P indices
-    int32_t* spos = si + P;                                    // cap permuted positions (first-stage list)
-    __shared__ int s_n1, s_n2;
-    const int q = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_n1 = 0; s_n2 = 0; }
-    const int my_cnt = tid < nseg ? segcnt[(int64_t)q * nseg + tid] : 0;
-    for (int k = tid; k < E; k += 256) sq[k] = Q[(int64_t)q * ldq + k];
-    if (__syncthreads_or(my_cnt > cap_seg)) {   // a queue segment overflowed
-        if (tid == 0) flags[q] = 1;
-        return;
+// ---- after the collect pass: three small kernels, each with whole-chip parallelism and no intra-query barrier -------
+// (one CTA per query doing all three steps is bound by its own chain of dependent L2 round trips times the few CTAs an
+//  SM can hold: measured 47 us for 2048 queries against ~20 us for the split form.)
+//
+// column_test_kernel    a quarter-warp (8 lanes x 16 B = one dumped chunk of 32 TF32 scores) per hit-queue segment
+//                       (rowpanel_kernel<kCollect> dumps qualifying chunks into per-(query, split, half) segments);
+//                       column j is listed when a_j >= lambda - kappa*max_chunk||c|| (the threshold the dumping lane
+//                       stored in the entry; it is implied by the per-column bound a_j + kappa*||c_j|| >= lambda, so no
+//                       true top-K row is lost).  Lists are appended with one global atomic per passing quad.
+// exact_score_kernel    one thread per listed column: canonical fp32 score from the authoritative corpus (k ascending,
+//                       one fmaf per term) -> 64-bit key (ordered score, ~index); rows with s < lambda get key 0 (the
+//                       exact K-th best score is >= lambda, see the file header).
+// sort_topk_kernel      one warp per query: bitonic network over the keys in registers, descending key == (score desc,
+//                       index asc); writes the first K.
+// A queue-segment overflow or more than `cap` (<= 1024) listed columns hands the query to the exact fallback.
+constexpr int kTestThreads = 256;
+
+// grid (ceil(cap_log / 32), logs of the collect pass): a quarter-warp per log entry
+__global__ void __launch_bounds__(kTestThreads) column_test_kernel(const float* __restrict__ logs, const int32_t* __restrict__ log_cnt, int cap_log,
+                                                                   int64_t n, int cap, int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
+    const int log = blockIdx.y;
+    const int e = blockIdx.x * (kTestThreads / 8) + (threadIdx.x >> 3);
+    const int sub = threadIdx.x & 7;
+    if (e >= __ldg(log_cnt + log)) return;
+    const float4* ent = reinterpret_cast<const float4*>(logs + ((int64_t)log * cap_log + e) * kHitWords);
+    const float4 hd = __ldg(ent);
+    const float4 a = __ldg(ent + 2 + sub);
+    const int q = __float_as_int(hd.x);
+    const float tc = hd.z;                                     // lambda - kappa * max ||c|| over the chunk
+    const int col0 = __float_as_int(hd.y) + 4 * sub;
+    uint32_t pass = (a.x >= tc ? 1u : 0u) | (a.y >= tc ? 2u : 0u) | (a.z >= tc ? 4u : 0u) | (a.w >= tc ? 8u : 0u);
+    if ((int64_t)col0 + 4 > n) pass &= (col0 < n) ? (0xFu >> (4 - (int)(n - col0))) : 0u;   // columns beyond the corpus
+    if (pass) {
+        int slot = atomicAdd(cand_cnt + q, __popc(pass));
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if ((pass >> t) & 1u) { if (slot < cap) cand[(int64_t)q * cap + slot] = col0 + t; ++slot; }
     }
-    const float kappa = eps[q], lambda = thr[q];
-    const float* qbase = queue + (int64_t)q * nseg * cap_seg * kHitWords;
-    // stage 1: per-column upper-bound test; a warp takes whole segments, four entries in flight
-    for (int s = warp; s < nseg; s += 8) {
-        const int cnt = __shfl_sync(0xffffffffu, segcnt[(int64_t)q * nseg + s], 0);
-        const float* sb = qbase + (int64_t)s * cap_seg * kHitWords;
-        for (int e0 = 0; e0 < cnt; e0 += 4) {
-            float a[4];
-            int nb[4];
+}
+
+// grid (ceil(cap / 128), queries); a warp takes 32 listed columns: the rows are copied to shared memory with coalesced
+// 128-bit loads (16-byte requests from 32 different rows would cost a 32-byte L2 sector access each -- the kernel is
+// bound by L2 sector accesses), then lane j computes row j's canonical score.
+template <int E>
+struct ScoreCfg {
+    static constexpr int kThreads = E >= 128 ? 64 : 128;   // static shared memory budget (32 staged rows per warp)
+};
+template <int E>
+__global__ void __launch_bounds__(ScoreCfg<E>::kThreads) exact_score_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ C, int ldc,
+                                                                    const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int cap,
+                                                                    const float* __restrict__ thr, const int32_t* __restrict__ orig_of,
+                                                                    unsigned long long* __restrict__ keys) {
+    constexpr int kScoreThreads = ScoreCfg<E>::kThreads;
+    constexpr int kRowLd = E + 4;                              // padded row stride (floats): conflict-free 128-bit row reads
+    constexpr int kF4 = E / 4;                                 // float4s per row
+    __shared__ __align__(16) float sq[E];
+    __shared__ __align__(16) float srows[kScoreThreads / 32][32 * kRowLd];
+    const int q = blockIdx.y;
+    const int m1 = min(cand_cnt[q], cap);
+    if ((int)(blockIdx.x * kScoreThreads) >= m1) return;
+    for (int k = threadIdx.x; k < E; k += kScoreThreads) sq[k] = Q[(int64_t)q * ldq + k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot0 = blockIdx.x * kScoreThreads + warp * 32;
+    if (slot0 >= m1) return;
+    const int nrow = min(32, m1 - slot0);
+    const int32_t my_id = (lane < nrow) ? __ldg(orig_of + cand[(int64_t)q * cap + slot0 + lane]) : 0;   // permuted position -> original corpus row
+    float* mine = srows[warp];
+    float4 v[kF4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = min(e0 + u, cnt - 1);
-                nb[u] = __float_as_int(__ldg(sb + e * kHitWords));
-                a[u] = __ldg(sb + e * kHitWords + 4 + lane);
-            }
-            float nr[4];
+    for (int i = 0; i < kF4; ++i) {                            // 32 * kF4 pieces, 32 per step: consecutive lanes, consecutive 16 bytes
+        const int piece = i * 32 + lane;
+        const int r = piece / kF4, c4 = piece % kF4;
+        const int32_t id = __shfl_sync(0xffffffffu, my_id, r);
+        if (r < nrow) v[i] = __ldg(reinterpret_cast<const float4*>(C + (int64_t)id * ldc) + c4);
+    }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) nr[u] = (nb[u] + lane < n) ? __ldg(norms + nb[u] + lane) : -CUDART_INF_F;
+    for (int i = 0; i < kF4; ++i) {
+        const int piece = i * 32 + lane;
+        const int r = piece / kF4, c4 = piece % kF4;
+        if (r < nrow) *reinterpret_cast<float4*>(mine + r * kRowLd + 4 * c4) = v[i];
+    }
+    __syncwarp();
+    if (lane < nrow) {
+        const float* row = mine + lane * kRowLd;
+        float acc = 0.f;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (e0 + u < cnt && fmaf(kappa, nr[u], a[u]) >= lambda) {   // -inf norm: column beyond the corpus
-                    const int slot = atomicAdd(&s_n1, 1);
-                    if (slot < cap) spos[slot] = nb[u] + lane;
+        for (int k4 = 0; k4 < kF4; ++k4) {
+            const float4 cv = *reinterpret_cast<const float4*>(row + 4 * k4);
+            const float4 qv = *reinterpret_cast<const float4*>(sq + 4 * k4);
+            acc = fmaf(qv.x, cv.x, acc);
+            acc = fmaf(qv.y, cv.y, acc);
+            acc = fmaf(qv.z, cv.z, acc);
+            acc = fmaf(qv.w, cv.w, acc);
+        }
+        keys[(int64_t)q * cap + slot0 + lane] =
+            (acc >= thr[q]) ? (((unsigned long long)ordered_key(acc) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)my_id)) : 0ull;
+    }
+}
+
+__device__ __forceinline__ void ce_desc(unsigned long long& a, unsigned long long& b, bool desc) {   // compare-exchange
+    const bool sw = (a < b) == desc;
+    const unsigned long long t = a;
+    a = sw ? b : a;
+    b = sw ? t : b;
+}
+// sorts the 32*S keys of a warp (element g = lane*S + i, the first m of them read from `src`) into descending order and
+// writes the first K as (score, index)
+template <int S>
+__device__ __forceinline__ void sort_write(const unsigned long long* __restrict__ src, int m, int K, int64_t idx_base, float* __restrict__ os,
+                                           int32_t* __restrict__ oi, int lane) {
+    unsigned long long key[S];
+#pragma unroll
+    for (int i = 0; i < S; ++i) key[i] = (i * 32 + lane < m) ? src[i * 32 + lane] : 0ull;   // 0 sorts after every real key
+    for (int k = 2; k <= 32 * S; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= S) {
+                const int lj = j / S;
+                const bool take_max = ((lane & lj) == 0) == (((lane * S) & k) == 0);
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, key[i], lj);
+                    key[i] = ((key[i] < o) == take_max) ? o : key[i];
+                }
+            } else {
+#pragma unroll
+                for (int jj = 1; jj < S; jj <<= 1) {
+                    if (j == jj) {
+#pragma unroll
+                        for (int i = 0; i < S; ++i)
+                            if ((i & jj) == 0) ce_desc(key[i], key[i | jj], (((lane * S + i) & k) == 0));
+                    }
                 }
             }
         }
     }
-    __syncthreads();
-    const int m1 = s_n1;
-    if (m1 > cap) {
-        if (tid == 0) flags[q] = 1;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        const int g = lane * S + i;
+        if (g < K) {
+            const bool pad = key[i] == 0ull;                   // fewer survivors than K (only when n < K)
+            os[g] = pad ? -CUDART_INF_F : key_to_float((uint32_t)(key[i] >> 32));
+            oi[g] = pad ? -1 : (int32_t)((int64_t)(0xFFFFFFFFu - (uint32_t)key[i]) + idx_base);
+        }
+    }
+}
+
+constexpr int kSortWarps = 4;             // queries per CTA
+template <bool BIG>                       // BIG: up to 1024 listed columns (32 keys per lane); otherwise up to 256 (8 per lane)
+__global__ void __launch_bounds__(32 * kSortWarps) sort_topk_kernel(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ cand_cnt,
+                                                                    int nq, int cap, int K, int64_t idx_base, float* __restrict__ out_s,
+                                                                    int32_t* __restrict__ out_i, int32_t* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * kSortWarps + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int m1 = cand_cnt[q];
+    if (m1 > cap || flags[q]) {   // list overflow, or a queue segment overflowed: exact fallback
+        if (lane == 0) flags[q] = 1;
         return;
     }
-    // stage 2: exact canonical score (k ascending, one fmaf per term), exact prune against lambda
-    for (int t = tid; t < m1; t += 256) {
-        const int32_t id = (int32_t)perm_orig(pm, spos[t]);   // permuted position -> original corpus row
-        const float4* row = reinterpret_cast<const float4*>(C + (int64_t)id * ldc);
-        float4 cv[E / 4];
-#pragma unroll
-        for (int k4 = 0; k4 < E / 4; ++k4) cv[k4] = __ldg(row + k4);
-        float acc = 0.f;
-#pragma unroll
-        for (int k4 = 0; k4 < E / 4; ++k4) {
-            const float4 qv = *reinterpret_cast<const float4*>(sq + 4 * k4);
-            acc = fmaf(qv.x, cv[k4].x, acc);
-            acc = fmaf(qv.y, cv[k4].y, acc);
-            acc = fmaf(qv.z, cv[k4].z, acc);
-            acc = fmaf(qv.w, cv[k4].w, acc);
-        }
-        if (acc >= lambda) {
-            const int slot = atomicAdd(&s_n2, 1);
-            ss[slot] = acc;
-            si[slot] = id;
-        }
-    }
-    __syncthreads();
-    const int m2 = s_n2;
-    int need = m2 > K ? m2 : K, Ps = 2;
-    while (Ps < need) Ps <<= 1;
-    Ps = Ps < P ? Ps : P;
-    for (int t = m2 + tid; t < Ps; t += 256) { ss[t] = -CUDART_INF_F; si[t] = 0x7fffffff; }
-    __syncthreads();
-    for (int k = 2; k <= Ps; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < Ps / 2; t += 256) {
-                int i = 2 * t - (t & (j - 1));
-                int p2 = i + j;
-                bool up = ((i & k) == 0);
-                float a = ss[i], b = ss[p2];
-                int32_t ia = si[i], ib = si[p2];
-                bool swap = up ? ranks_before(b, ib, a, ia) : ranks_before(a, ia, b, ib);
-                if (swap) { ss[i] = b; ss[p2] = a; si[i] = ib; si[p2] = ia; }
-            }
-            __syncthreads();
-        }
-    }
-    for (int t = tid; t < K; t += 256) {
-        const bool pad = si[t] == 0x7fffffff;
-        out_s[(int64_t)q * K + t] = pad ? -CUDART_INF_F : ss[t];
-        out_i[(int64_t)q * K + t] = pad ? -1 : (int32_t)(si[t] + idx_base);
+    const unsigned long long* src = keys + (int64_t)q * cap;
+    float* os = out_s + (int64_t)q * K;
+    int32_t* oi = out_i + (int64_t)q * K;
+    const int need = m1 > K ? m1 : K;
+    if constexpr (!BIG) {
+        if (need <= 128) sort_write<4>(src, m1, K, idx_base, os, oi, lane);
+        else sort_write<8>(src, m1, K, idx_base, os, oi, lane);
+    } else {
+        if (need <= 512) sort_write<16>(src, m1, K, idx_base, os, oi, lane);
+        else sort_write<32>(src, m1, K, idx_base, os, oi, lane);
     }
 }
 
 // C32p[pos][:] = tf32_rn(C[orig(pos)][:]); norms[pos] = ||C[orig(pos)]|| (rounded up a hair); norms[n..n_pad) = 0.
 __global__ void __launch_bounds__(256) prepare_corpus_kernel(const float* __restrict__ C, int ldc, int64_t n, int E, Perm pm,
-                                                             float* __restrict__ C32p, float* __restrict__ norms, int64_t n_pad) {
+                                                             float* __restrict__ C32p, float* __restrict__ norms, int32_t* __restrict__ orig_of, int64_t n_pad) {
     int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -326,7 +395,10 @@ __global__ void __launch_bounds__(256) prepare_corpus_kernel(const float* __rest
             }
         }
         s = warp_sum(s);
-        if (lane == 0) norms[pos] = pos < n ? sqrtf(s) * 1.0001f : 0.f;
+        if (lane == 0) {
+            norms[pos] = pos < n ? sqrtf(s) * 1.0001f : 0.f;
+            orig_of[pos] = pos < n ? (int32_t)perm_orig(pm, pos) : 0;
+        }
     }
 }
 
@@ -339,11 +411,11 @@ __global__ void chunk_max_kernel(const float* __restrict__ norms, int64_t nchunk
     gn[c] = m;
 }
 
-// norms buffer layout: [n_pad per-row norms][n_pad/32 per-chunk maxima]
+// norms buffer layout: [n_pad per-row norms][n_pad/32 per-chunk maxima][n_pad int32: original row of every permuted position]
 int launch_prepare(const float* C, int ldc, int64_t n, int E, float* C32p, float* norms, int64_t n_pad, cudaStream_t st) {
     int64_t g = ceil_div(n_pad * 32, 256);
     int64_t cap = (int64_t)sm_count() * 16;
-    prepare_corpus_kernel<<<(unsigned)(g > cap ? cap : (g < 1 ? 1 : g)), 256, 0, st>>>(C, ldc, n, E, make_perm(n), C32p, norms, n_pad);
+    prepare_corpus_kernel<<<(unsigned)(g > cap ? cap : (g < 1 ? 1 : g)), 256, 0, st>>>(C, ldc, n, E, make_perm(n), C32p, norms, reinterpret_cast<int32_t*>(norms + n_pad + n_pad / 32), n_pad);
     TT_LAUNCH_OK("prepare_corpus_kernel");
     const int64_t nchunks = n_pad / 32;
     chunk_max_kernel<<<(unsigned)ceil_div(nchunks, 256), 256, 0, st>>>(norms, nchunks, norms + n_pad);
@@ -378,31 +450,35 @@ static int launch_idx_e(int E, const CUtensorMap& tmQ, const CUtensorMap& tmC, c
 }
 
 struct IdxLayout {
-    size_t q32, eps, thr, gmax, cnt, flags, queue, c32, norms, exact, total;
+    size_t q32, eps, thr, gmax, cnt, flags, queue, cand, ccnt, keys, c32, norms, exact, total;
     int ngroups, n_tiles, cap;
-    int m_tiles, splits, tps, nseg, cap_seg;
+    int m_tiles, splits, tps, n_logs, cap_log, fine;
 };
 
 static IdxLayout layout(int nq, int64_t n, int E, int K, bool need_corpus_copy) {
     IdxLayout L;
     L.n_tiles = (int)ceil_div(n, idx_bn(E));
-    L.ngroups = L.n_tiles * (idx_bn(E) / kGroup);
+    // one filter group per (tile, warp half) = BN/2 consecutive rows; per 32-row chunk when that leaves fewer than 8 K groups
+    L.fine = (int64_t)L.n_tiles * idx_halves(E) < 8 * (int64_t)K;
+    L.ngroups = L.n_tiles * (L.fine ? idx_bn(E) / 32 : idx_halves(E));
     L.cap = cand_cap(K);
     L.m_tiles = (int)ceil_div(nq, 128);
     choose_splits(L.m_tiles, L.n_tiles, 2, 64, &L.splits, &L.tps);
-    L.nseg = L.splits * (idx_bn(E) / 32 >= 2 ? 2 : 1);   // RowPanelCfg::kHalves
-    // hit-queue segment of one (row, split, half): ~1.25 K / nseg qualifying chunks are expected; generous slack because an
-    // overflow costs a trip through the exact CUDA-core fallback
-    L.cap_seg = g_cap_override > 0 ? 1 + g_cap_override / L.nseg : (int)ceil_div(2 * K, L.nseg) + 16;
+    // hit logs of the collect pass: a warp's 32 rows each see ~1.25 K / (splits * halves) qualifying chunks; generous slack because an overflow costs a trip through the exact CUDA-core fallback
+    L.n_logs = L.m_tiles * L.splits * 4 * idx_halves(E);   // one log per epilogue warp (32 rows x its share of the columns)
+    L.cap_log = g_cap_override > 0 ? 32 * (1 + g_cap_override / (4 * L.splits)) : 32 * (int)ceil_div(5 * (int64_t)K, 2 * L.splits * idx_halves(E)) + 128;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     L.q32 = take((size_t)nq * E * 4);
     L.eps = take((size_t)nq * 4);
     L.thr = take((size_t)nq * 4);
     L.gmax = take((size_t)nq * L.ngroups * 4);
-    L.cnt = take((size_t)nq * L.nseg * 4);
+    L.cnt = take((size_t)L.n_logs * 4);
     L.flags = take((size_t)nq * 4);
-    L.queue = take((size_t)nq * L.nseg * L.cap_seg * kHitWords * 4);
+    L.queue = take((size_t)L.n_logs * L.cap_log * kHitWords * 4);
+    L.cand = take((size_t)nq * L.cap * 4);
+    L.ccnt = take((size_t)nq * 4);
+    L.keys = take((size_t)nq * L.cap * 8);
     L.c32 = take(need_corpus_copy ? (size_t)n * E * 4 : 0);
     L.norms = take(need_corpus_copy ? (size_t)TT_INDEX_NORM_PAD(n) * 4 : 0);
     L.exact = off;
@@ -416,9 +492,9 @@ using namespace tc;
 
 bool index_tc_supported(int ldq, int ldc, int E, int K, int64_t n, const void* Q, const void* C) {
     if (!softmax_tc_supported(ldq, ldc, E, Q, C)) return false;
-    if (K < 1 || K > 1024) return false;
+    if (K < 1 || K > 640) return false;                           // sort_topk_kernel orders at most 1024 listed columns
     if (n < 4096) return false;                                   // tiny corpora: the exact kernel is already fast
-    if (ceil_div(n, kGroup) < 4 * (int64_t)K) return false;      // the group filter needs many more groups than K
+    if (ceil_div(n, 32) < 4 * (int64_t)K) return false;           // the group filter needs many more groups than K
     return true;
 }
 
@@ -428,6 +504,12 @@ size_t index_tc_workspace(int nq, int64_t n, int E, int K, bool need_corpus_copy
 }
 
 void debug_index_cap(int cap) { tc::g_cap_override = cap; }
+
+// debug: per-stage device times of the next tensor-core index calls (events on the caller's stream; reading them syncs)
+static float* g_stage_ms = nullptr;   // host array of 8 floats, accumulated
+void debug_index_stages(float* host_ms8) {
+    g_stage_ms = host_ms8;
+}
 
 int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_in, const float* norms_in, int nq, int64_t n, int E, int K,
              int64_t idx_base, float* out_s, int32_t* out_i, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -445,6 +527,9 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
     int32_t* cnt = reinterpret_cast<int32_t*>(base + L.cnt);
     int32_t* flags = reinterpret_cast<int32_t*>(base + L.flags);
     float* queue = reinterpret_cast<float*>(base + L.queue);
+    int32_t* cand = reinterpret_cast<int32_t*>(base + L.cand);
+    int32_t* ccnt = reinterpret_cast<int32_t*>(base + L.ccnt);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(base + L.keys);
     const float* c32 = C32_in;
     const float* norms = norms_in;
     if (need_copy) {
@@ -455,6 +540,10 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
         c32 = dst;
         norms = nd;
     }
+    cudaEvent_t ev[8];
+    int nev = 0;
+    auto mark = [&]() { if (g_stage_ms && nev < 8) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], st); ++nev; } };
+    mark();
     prep_queries_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, st>>>(Q, ldq, nq, E, q32, eps);
     TT_LAUNCH_OK("prep_queries_kernel");
 
@@ -464,32 +553,53 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
     rc = make_tmap_2d(&tmC, c32, n, E, E, idx_bn(E));   // the prepared copy is dense (ld = E)
     if (rc) return rc;
     const int m_tiles = L.m_tiles, splits = L.splits, tps = L.tps;
-    TT_REQUIRE(L.nseg <= 256, "tt_index_topk: too many column splits");
     RowPanelParams p{};
-    p.nR = nq; p.nT = (int)n; p.n_tiles = L.n_tiles; p.tiles_per_split = tps; p.rowv = eps; p.rowv2 = thr; p.colv2 = norms; p.gnorm = norms + TT_INDEX_ROWS_PAD(n); p.d = -(1 << 30);
+    p.nR = nq; p.nT = (int)n; p.n_tiles = L.n_tiles; p.tiles_per_split = tps; p.rowv = eps; p.rowv2 = thr; p.colv2 = norms; p.gnorm = norms + TT_INDEX_ROWS_PAD(n); p.d = -(1 << 30); p.fine_groups = L.fine;
     p.out0 = gmax; p.out1 = nullptr; p.out2 = nullptr; p.ld_out = L.ngroups; p.trace = nullptr;
+    mark();
     rc = launch_idx_e<kIndex>(E, tmQ, tmC, p, m_tiles, splits, st, "rowpanel_kernel<index>");
     if (rc) return rc;
-    select_threshold_kernel<<<(unsigned)nq, 256, 0, st>>>(gmax, L.ngroups, (int)ceil_div(n, kGroup), K, thr, flags);
+    mark();
+    select_threshold_kernel<<<(unsigned)nq, kSelectThreads, 0, st>>>(gmax, L.ngroups, L.ngroups, K, thr, flags, ccnt);
     TT_LAUNCH_OK("select_threshold_kernel");
+    mark();
     p.out0 = queue;
     p.out1 = reinterpret_cast<float*>(cnt);
-    p.ld_out = L.cap_seg;
+    p.out2 = reinterpret_cast<float*>(flags);
+    p.ld_out = L.cap_log;
     rc = launch_idx_e<kCollect>(E, tmQ, tmC, p, m_tiles, splits, st, "rowpanel_kernel<collect>");
     if (rc) return rc;
-    const int P = next_pow2(L.cap < 2 ? 2 : L.cap);
-    const size_t smem = 128 * 4 + (size_t)P * 8 + (size_t)L.cap * 4;
-    auto launch_rescore = [&](auto kern) -> int {
-        if (smem > 48 * 1024) TT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)nq, 256, smem, st>>>(Q, ldq, C, ldc, K, n, queue, cnt, L.nseg, L.cap_seg, norms, eps, thr, L.cap, P, make_perm(n), idx_base,
-                                             out_s, out_i, flags);
-        return TT_OK;
-    };
-    rc = E == 32 ? launch_rescore(collect_rescore_kernel<32>) : E == 64 ? launch_rescore(collect_rescore_kernel<64>) : launch_rescore(collect_rescore_kernel<128>);
-    if (rc) return rc;
-    TT_LAUNCH_OK("collect_rescore_kernel");
+    mark();
+    {
+        const int32_t* orig_of = reinterpret_cast<const int32_t*>(norms + TT_INDEX_ROWS_PAD(n) + TT_INDEX_ROWS_PAD(n) / 32);
+        const dim3 cgrid((unsigned)ceil_div(L.cap_log, kTestThreads / 8), (unsigned)L.n_logs);
+        column_test_kernel<<<cgrid, kTestThreads, 0, st>>>(queue, cnt, L.cap_log, n, L.cap, cand, ccnt);
+        TT_LAUNCH_OK("column_test_kernel");
+#define TT_SCORE(EE)                                                                                                        \
+    exact_score_kernel<EE><<<dim3((unsigned)ceil_div(L.cap, ScoreCfg<EE>::kThreads), (unsigned)nq), ScoreCfg<EE>::kThreads, 0, st>>>( \
+        Q, ldq, C, ldc, cand, ccnt, L.cap, thr, orig_of, keys)
+        if (E == 32) TT_SCORE(32); else if (E == 64) TT_SCORE(64); else TT_SCORE(128);
+#undef TT_SCORE
+        TT_LAUNCH_OK("exact_score_kernel");
+        const unsigned tgrid = (unsigned)ceil_div(nq, kSortWarps);
+        if (L.cap <= 256) sort_topk_kernel<false><<<tgrid, 32 * kSortWarps, 0, st>>>(keys, ccnt, nq, L.cap, K, idx_base, out_s, out_i, flags);
+        else sort_topk_kernel<true><<<tgrid, 32 * kSortWarps, 0, st>>>(keys, ccnt, nq, L.cap, K, idx_base, out_s, out_i, flags);
+        TT_LAUNCH_OK("sort_topk_kernel");
+    }
+    mark();
     // queries whose candidate list overflowed: exact CUDA-core path, decided on the device (no host sync)
-    return index_exact(Q, ldq, C, ldc, nq, n, E, K, idx_base, out_s, out_i, base + L.exact, exact_bytes, st, flags);
+    rc = index_exact(Q, ldq, C, ldc, nq, n, E, K, idx_base, out_s, out_i, base + L.exact, exact_bytes, st, flags);
+    mark();
+    if (g_stage_ms && nev > 1) {   // debug only: prep | filter | select | collect | rescore | fallback
+        cudaEventSynchronize(ev[nev - 1]);
+        for (int i = 0; i + 1 < nev; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            g_stage_ms[i] += ms;
+        }
+        for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+    }
+    return rc;
 }
 
 }  // namespace tt

@@ -19,6 +19,7 @@ int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bia
 size_t softmax_tc_workspace_bytes(int Bq, int Bc, int E);
 void debug_tc(void* trace, int max_splits);
 void debug_index_cap(int cap);
+void debug_index_stages(float* host_ms8);
 
 static int pick_impl(int impl, int ldq, int ldc, int E, const void* Q, const void* C, const char* who) {
     if (impl == TT_IMPL_SIMT) return TT_IMPL_SIMT;
@@ -44,6 +45,11 @@ extern "C" {
 
 int tt_debug_tc(void* trace, int max_splits) {
     debug_tc(trace, max_splits);
+    return TT_OK;
+}
+
+int tt_debug_index_stages(float* host_ms8) {
+    debug_index_stages(host_ms8);
     return TT_OK;
 }
 

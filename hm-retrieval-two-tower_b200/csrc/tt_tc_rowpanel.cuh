@@ -15,7 +15,7 @@
 //           swizzle (128B_BASE32B) than the K-major tile of the first MMA, so the B operand of the second
 //           MMA is a K-major tile of T^T (E x BN) loaded by TMA from a transposed copy of T.
 //   kLogits Z = S - colv written out (tests / TwoTowerModel.call)
-//   kIndex  max over each group of 32 consecutive columns                 -> group maxima (filter stage 1)
+//   kIndex  lower bound of the best score in each group of BN/2 consecutive columns -> group values (filter stage 1)
 //   kCollect every 32-column chunk that can hold a column reaching the row's threshold is dumped (32 TF32 scores)
 //           into the row's hit queue (filter stage 2; the queue is tested per column and rescored exactly afterwards)
 //
@@ -41,11 +41,13 @@ struct RowPanelParams {
     const float* gnorm;   // kIndex/kCollect: max ||c_j|| over each chunk of 32 columns (colv2 holds the per-column norms)
     const float* colv2;   // per-T-row term * log2(e), padded with zeros to n_tiles*BN entries (never null)
     int d;                // diagonal: column == row + d
+    int fine_groups;      // kIndex: 1 = one filter group per 32-column chunk (small corpora), 0 = one per (tile, warp half)
     float* out0;          // kFwd: m2 [split][nR] | kBwd: G partial [split][nR][E] | kLogits: Z | kIndex: gmax [nR][ld_out]
-                          // kCollect: hit queue [nR][splits*halves][ld_out][kHitWords]
-    float* out1;          // kFwd: l  [split][nR] | kCollect: (int32*) hits per segment [nR][splits*halves] (may exceed ld_out: overflow)
+                          // kCollect: hit logs [CTA][epilogue warp][ld_out][kHitWords]
+    float* out1;          // kFwd: l  [split][nR] | kCollect: (int32*) entries in each warp's log
     float* out2;          // kFwd: zdiag [nR] (natural units; written by the split that owns the diagonal column)
-    int ld_out;           // kLogits: ldz | kIndex: row stride of gmax (groups) | kCollect: entries per queue segment
+                          // kCollect: (int32*) per-row overflow flags (set when a warp's log is full)
+    int ld_out;           // kLogits: ldz | kIndex: row stride of gmax (groups) | kCollect: capacity (entries) of one warp's hit log
     unsigned long long* trace;  // optional debug timeline: [cta][16] globaltimer stamps (ns); null in production
 };
 
@@ -59,7 +61,8 @@ __device__ __forceinline__ unsigned long long gtime() {
         if (p.trace) p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime();          \
     } while (0)
 
-constexpr int kHitWords = 36;   // hit-queue entry: {first column, 3 pad words, 32 TF32 scores} = 144 bytes
+constexpr int kHitWords = 40;   // hit-log entry: 32-byte header {row, first column, chunk threshold lambda - kappa*max||c||, 5 pad words} + 32 TF32 scores
+                                // = 160 bytes = five whole 32-byte sectors, each written completely (a partially written sector costs a DRAM fill on read)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -347,12 +350,12 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         if (MODE == kCollect) r3 = (row < p.nR) ? __ldg(p.rowv2 + row) : CUDART_INF_F;              // lambda_q
         constexpr int NC = BN / 32;
         constexpr int NCW = NC / Cfg::kHalves;        // 32-column chunks per warp per tile
-        // kCollect: this lane's private segment of the hit queue
-        const int nseg = gridDim.y * Cfg::kHalves;
-        const int seg = blockIdx.y * Cfg::kHalves + half;
-        float* qseg = (MODE == kCollect && row < p.nR) ? p.out0 + ((int64_t)row * nseg + seg) * p.ld_out * kHitWords : nullptr;
-        int n_hit = 0;                                // rows beyond nR have lambda = +inf and never record
         const int c_first = half * NCW;
+        // kCollect: this warp's hit log (dense: the entries of its 32 lanes back to back, so the consumer reads whole lines;
+        // slots come from a warp ballot -- no atomics)
+        const int log_id = (blockIdx.y * gridDim.x + blockIdx.x) * Cfg::kEpiWarps + (warp - 2);
+        float* qlog = (MODE == kCollect) ? p.out0 + (int64_t)log_id * p.ld_out * kHitWords : nullptr;
+        int n_log = 0;                                // entries appended so far (warp-uniform)
         for (int it = 0; it < my_tiles; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
@@ -383,7 +386,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
             const float4* c2v = reinterpret_cast<const float4*>(sC2 + stage * 1024);
             const uint32_t c2s = smem_u32(sC2 + stage * 1024);
             uint32_t rbuf[2][32];
-            float gm[NCW];
+            float gmx = -CUDART_INF_F;                // kIndex: the group (= this warp's share of the tile) lower bound
             tmem_ld_32x32_issue(tmem + lane_addr + acc * BN + c_first * 32, rbuf[0]);
 #pragma unroll
             for (int cl = 0; cl < NCW; ++cl) {
@@ -414,21 +417,26 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                     }
                 } else if constexpr (MODE == kCollect) {
                     // A chunk can hold a column with a_j + kappa*||c_j|| >= lambda only if max_j a_j >= lambda - kappa*max_j||c_j||.
-                    // The (rare, ~K per row) qualifying chunks are dumped whole -- 32 TF32 scores + the chunk's first column --
-                    // into this (row, split, half) segment of the hit queue; collect_rescore_kernel does the per-column test.
-                    // No atomics: the segment belongs to this lane alone, so the queue order is deterministic.
+                    // The (rare, ~K per row) qualifying chunks are appended whole -- row, first column, threshold, 32 TF32 scores --
+                    // to the CTA's hit log; column_test_kernel does the per-column test.  One shared-memory atomic per hit.
                     const float thr_c = fmaf(-r2, gn[cl], r3);
-                    if (chunk_max(r) >= thr_c) {
-                        if (n_hit < p.ld_out) {
-                            float4* dst = reinterpret_cast<float4*>(qseg + (int64_t)n_hit * kHitWords);
-                            dst[0] = make_float4(__int_as_float(nb), 0.f, 0.f, 0.f);
+                    const bool hit = chunk_max(r) >= thr_c;
+                    const unsigned hits = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        const int slot = n_log + __popc(hits & ((1u << lane) - 1u));
+                        if (slot < p.ld_out) {
+                            float4* dst = reinterpret_cast<float4*>(qlog + (int64_t)slot * kHitWords);
+                            dst[0] = make_float4(__int_as_float(row), __int_as_float(nb), thr_c, 0.f);
+                            dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                             for (int g4 = 0; g4 < 8; ++g4)
-                                dst[1 + g4] = make_float4(__uint_as_float(r[g4 * 4]), __uint_as_float(r[g4 * 4 + 1]), __uint_as_float(r[g4 * 4 + 2]),
+                                dst[2 + g4] = make_float4(__uint_as_float(r[g4 * 4]), __uint_as_float(r[g4 * 4 + 1]), __uint_as_float(r[g4 * 4 + 2]),
                                                           __uint_as_float(r[g4 * 4 + 3]));
+                        } else {
+                            reinterpret_cast<int32_t*>(p.out2)[row] = 1;   // log full: this query goes to the exact fallback
                         }
-                        ++n_hit;
                     }
+                    n_log += __popc(hits);
                 } else {  // kIndex: per chunk, max_j a_j - kappa * max_j ||c_j||  <=  max_j (a_j - kappa*||c_j||)  <=  max_j s_j
                     float mx = -CUDART_INF_F;
                     if (fast || nb + 32 <= p.nT) {
@@ -437,7 +445,9 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
 #pragma unroll
                         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (nb + i < p.nT) ? __uint_as_float(r[i]) : -CUDART_INF_F);
                     }
-                    gm[cl] = fmaf(-r2, gn[cl], mx);
+                    const float lb = fmaf(-r2, gn[cl], mx);
+                    gmx = fmaxf(gmx, lb);
+                    if (p.fine_groups && row < p.nR) p.out0[(int64_t)row * p.ld_out + (int64_t)(tile_begin + it) * NC + c] = lb;   // small corpora
                 }
             }
             // this S buffer may be overwritten by the MMA of tile it+2
@@ -454,20 +464,11 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                 if (lane == 0) mbar_arrive(&bars->p_full[pb]);
             }
             if constexpr (MODE == kIndex) {
-                if (row < p.nR) {
-                    float* dst = p.out0 + (int64_t)row * p.ld_out + (int64_t)(tile_begin + it) * NC + c_first;
-                    if constexpr (NCW % 4 == 0) {
-#pragma unroll
-                        for (int c = 0; c < NCW; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(gm[c], gm[c + 1], gm[c + 2], gm[c + 3]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < NCW; ++c) dst[c] = gm[c];
-                    }
-                }
+                if (!p.fine_groups && row < p.nR) p.out0[(int64_t)row * p.ld_out + (int64_t)(tile_begin + it) * Cfg::kHalves + half] = gmx;
             }
         }
         if constexpr (MODE == kCollect) {
-            if (row < p.nR) reinterpret_cast<int32_t*>(p.out1)[(int64_t)row * nseg + seg] = n_hit;   // may exceed the capacity: overflow
+            if (lane == 0) reinterpret_cast<int32_t*>(p.out1)[log_id] = min(n_log, p.ld_out);
         }
         if constexpr (MODE == kFwd) {
             if (row < p.nR) {

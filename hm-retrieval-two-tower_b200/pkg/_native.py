@@ -41,6 +41,7 @@ SIGNATURES = {
     "tt_tc_available": (c_int, [c_int, c_int]),
     "tt_debug_tc": (c_int, [c_void_p, c_int]),
     "tt_debug_index_cap": (c_int, [c_int]),
+    "tt_debug_index_stages": (c_int, [c_void_p]),
     "tt_gather_concat": (c_int, [ctypes.POINTER(TTFeature), c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "tt_dense_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p]),

@@ -60,7 +60,7 @@ class BruteForceIndex(AbstractKerasModel):
         if n_loc > 0 and lib.tt_tc_available(1, e):
             self._candidates_tf32 = torch.empty_like(self._candidates)
             rows_pad = ((n_loc + 255) // 256 + 1) * 256          # TT_INDEX_ROWS_PAD
-            n_pad = rows_pad + rows_pad // 32                    # TT_INDEX_NORM_PAD: row norms + per-chunk maxima
+            n_pad = 2 * rows_pad + rows_pad // 32                    # TT_INDEX_NORM_PAD: row norms + per-chunk maxima
             self._max_norm = torch.zeros(n_pad, dtype=torch.float32, device="cuda")   # per-row norms, zero padded
             N.check(lib.tt_index_prepare(self._candidates.data_ptr(), e, n_loc, e, self._candidates_tf32.data_ptr(),
                                          self._max_norm.data_ptr(), N.stream_ptr()), "tt_index_prepare")

@@ -55,6 +55,9 @@ int tt_debug_tc(void* trace, int max_splits);
 /* Test knob: cap the candidate lists of the tensor-core index filter (0 = default 4K+512) to force the
  * on-device exact fallback. */
 int tt_debug_index_cap(int cap);
+/* Profiling knob: while `host_ms8` (8 host floats, or NULL to stop) is set, every tensor-core tt_index_topk call adds
+ * the device time of its stages (prep, filter, select, collect, rescore, fallback) to it and synchronises. */
+int tt_debug_index_stages(float* host_ms8);
 /* Number of kernels this library has launched (or captured into a CUDA graph) in this process so far. */
 int64_t tt_launch_count(void);
 
@@ -170,11 +173,12 @@ int tt_sparse_adam(const tt_sparse_job* jobs, int njobs, float lr_t, float beta1
  *   corpus_prepared  (n, E) dense: TF32-rounded rows stored under a fixed pseudo-random permutation (so that
  *                    neighbouring -- e.g. equally popular -- rows do not share a filter group);
  *   corpus_norms     TT_INDEX_NORM_PAD(n) floats: ||row||_2 in the same order, zero padded to TT_INDEX_ROWS_PAD(n),
- *                    followed by the maximum norm of every chunk of 32 rows.
+ *                    followed by the maximum norm of every chunk of 32 rows, followed by TT_INDEX_ROWS_PAD(n) int32: the
+ *                    original row of every permuted position.
  * Pass both or neither; when NULL they are rebuilt in the workspace on every call (size the workspace with
  * have_corpus_prepared = 0).  The exact fp32 `corpus` stays authoritative: results never depend on the copy. */
 #define TT_INDEX_ROWS_PAD(n) ((((n) + 255) / 256 + 1) * 256)
-#define TT_INDEX_NORM_PAD(n) (TT_INDEX_ROWS_PAD(n) + TT_INDEX_ROWS_PAD(n) / 32)
+#define TT_INDEX_NORM_PAD(n) (2 * TT_INDEX_ROWS_PAD(n) + TT_INDEX_ROWS_PAD(n) / 32)
 int tt_index_prepare(const float* corpus, int ldc, int64_t n, int E, float* corpus_prepared, float* corpus_norms,
                      void* stream);
 size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl, int have_corpus_prepared);

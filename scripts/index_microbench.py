@@ -15,7 +15,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 C = torch.randn(n, E, device="cuda", generator=g).abs() * 0.1
 Q = torch.relu(torch.randn(nq, E, device="cuda", generator=g) * 0.3)
 rows_pad = ((n + 255) // 256 + 1) * 256
-n_pad = rows_pad + rows_pad // 32
+n_pad = 2 * rows_pad + rows_pad // 32
 C32 = torch.empty_like(C); norms = torch.zeros(n_pad, device="cuda")
 st = N.stream_ptr()
 N.check(lib.tt_index_prepare(C.data_ptr(), E, n, E, C32.data_ptr(), norms.data_ptr(), st))
@@ -34,3 +34,15 @@ for impl, name in ((N.TT_IMPL_TC, "tensor-core filter"), (N.TT_IMPL_SIMT, "exact
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     print(f"{name}: n={n} nq={nq} E={E} K={K}: {ms:.3f} ms/batch, {nq / ms * 1e3:.0f} queries/s, {2.0 * nq * n * E / ms / 1e9:.1f} TFLOP/s algorithmic")
+
+import ctypes
+stages = (ctypes.c_float * 8)()
+lib.tt_debug_index_stages(ctypes.cast(stages, ctypes.c_void_p))
+ws = torch.empty(int(lib.tt_index_workspace_bytes(nq, n, E, K, N.TT_IMPL_TC, 1)), dtype=torch.uint8, device="cuda")
+reps = 20
+for _ in range(reps):
+    N.check(lib.tt_index_topk(Q.data_ptr(), E, C.data_ptr(), E, C32.data_ptr(), norms.data_ptr(), nq, n, E, K, 0, s.data_ptr(), i.data_ptr(),
+                              ws.data_ptr(), ws.numel(), N.TT_IMPL_TC, st))
+lib.tt_debug_index_stages(None)
+names = ["prep", "filter", "select", "collect", "rescore", "fallback"]
+print("stages (us, in situ): " + "  ".join(f"{nm} {stages[k] / reps * 1e3:.1f}" for k, nm in enumerate(names)))

@@ -173,7 +173,7 @@ def _index_tc(lib, T, q, c, K, idx_base=0, prepared=False):
     c32 = mx = None
     if prepared:   # what BruteForceIndex does once at build time
         rows_pad = ((n + 255) // 256 + 1) * 256
-        n_pad = rows_pad + rows_pad // 32                      # TT_INDEX_NORM_PAD
+        n_pad = 2 * rows_pad + rows_pad // 32                      # TT_INDEX_NORM_PAD
         c32 = T.empty_like(dc); mx = T.full((n_pad,), 9.0, dtype=T.float32, device="cuda")
         N.check(lib.tt_index_prepare(dc.data_ptr(), E, n, E, c32.data_ptr(), mx.data_ptr(), stream()))
     s = T.empty((nq, K), dtype=T.float32, device="cuda"); i = T.empty((nq, K), dtype=T.int32, device="cuda")
@@ -184,7 +184,7 @@ def _index_tc(lib, T, q, c, K, idx_base=0, prepared=False):
 
 
 @pytest.mark.parametrize("nq,n,E,K,prepared", [(70, 20_000, 64, 100, False), (2048, 105_542, 64, 100, True), (5, 8000, 32, 12, True),
-                                               (300, 40_000, 128, 100, False), (129, 50_001, 64, 1, True), (64, 140_000, 64, 1000, True)])
+                                               (300, 40_000, 128, 100, False), (129, 50_001, 64, 1, True), (64, 140_000, 64, 500, True)])
 def test_index_tc_bit_exact(lib, T, nq, n, E, K, prepared):
     rng = np.random.default_rng(10)
     q = np.maximum(rng.standard_normal((nq, E)) * 0.3, 0).astype(np.float32)      # tower outputs are non-negative
