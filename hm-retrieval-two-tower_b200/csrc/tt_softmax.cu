@@ -15,6 +15,8 @@ int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float
                    float* loss, float* ws, cudaStream_t st);
 int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const float* rowv, const float* colv, int nR, int nT, int E,
                         int d, float* G, int ldg, float* ws, cudaStream_t st);
+int softmax_bwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E, int off, int which,
+                   float* G0, int ldg0, float* G1, int ldg1, float* ws, cudaStream_t st);
 int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, float* Z, int ldz, cudaStream_t st);
 size_t softmax_tc_workspace_bytes(int Bq, int Bc, int E);
 void debug_tc(void* trace, int max_splits);
@@ -106,9 +108,7 @@ int tt_inbatch_softmax_bwd(const float* Q, int ldq, const float* C, int ldc, con
     int rc;
     if (use == TT_IMPL_TC) {
         float* wsf = reinterpret_cast<float*>(ws);
-        rc = softmax_bwd_pass_tc(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, dQ, lddq, wsf, st);
-        if (rc) return rc;
-        return softmax_bwd_pass_tc(C, ldc, Q, ldq, col_bias, lse, Bc, Bq, E, -diag_offset, dC, lddc, wsf, st);
+        return softmax_bwd_tc(Q, ldq, C, ldc, col_bias, lse, Bq, Bc, E, diag_offset, 2, dQ, lddq, dC, lddc, wsf, st);
     }
     rc = softmax_bwd_pass_simt(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, dQ, lddq, st);
     if (rc) return rc;
@@ -133,8 +133,7 @@ int tt_inbatch_softmax_bwd_one(const float* Q, int ldq, const float* C, int ldc,
     }
     float* wsf = reinterpret_cast<float*>(ws);
     if (use == TT_IMPL_TC) {
-        return which == 0 ? softmax_bwd_pass_tc(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, G, ldg, wsf, st)
-                          : softmax_bwd_pass_tc(C, ldc, Q, ldq, col_bias, lse, Bc, Bq, E, -diag_offset, G, ldg, wsf, st);
+        return softmax_bwd_tc(Q, ldq, C, ldc, col_bias, lse, Bq, Bc, E, diag_offset, which, G, ldg, nullptr, 0, wsf, st);
     }
     return which == 0 ? softmax_bwd_pass_simt(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, G, ldg, st)
                       : softmax_bwd_pass_simt(C, ldc, Q, ldq, col_bias, lse, Bc, Bq, E, -diag_offset, G, ldg, st);

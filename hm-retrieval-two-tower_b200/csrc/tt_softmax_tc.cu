@@ -5,12 +5,16 @@
 // Operands are expected TF32-rounded (tt_round_tf32 / the Y_tf32 output of tt_dense_fwd); products are
 // exact in fp32 and accumulate in fp32 in TMEM, so logits agree with the fp32 reference to ~2^-11 relative.
 //
-//   forward : one rowpanel_kernel<kFwd> over (row panels x column splits) + a tiny combine kernel
-//   backward: rowpanel_kernel<kBwd> twice (rows = queries -> dQ; rows = candidates -> dC), each followed by
-//             a fixed-order reduction of the per-split partial sums (deterministic, no atomics).  The
-//             second MMA of the backward kernel reads a K-major tile of T^T, so each pass first writes a
-//             transposed copy of its streamed operand into the workspace.
+//   forward : scale/pad of the column term, ONE persistent streamk_kernel<kFwd> (tt_tc_streamk.cuh: every SM walks an
+//             equal share of the (row panel, column tile) units), a combine kernel (per-row partials -> lse, row loss)
+//             and the fixed-order loss sum
+//   backward: one prep kernel (transposed copies of both operands for the second MMA's K-major B tiles; scaled column
+//             terms), ONE persistent streamk_kernel<kBwd> covering the dQ and the dC pass, one fixed-order reduction of
+//             the per-(panel, CTA) partial blocks (deterministic, no atomics)
+#include <cuda_fp16.h>
+
 #include "tt_tc_rowpanel.cuh"
+#include "tt_tc_streamk.cuh"
 
 namespace tt {
 
@@ -45,6 +49,23 @@ int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int cols, in
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d ld=%d box_rows=%d", (int)r, (long long)rows, cols, ld, box_rows);
+        return TT_ERR_CUDA;
+    }
+    return TT_OK;
+}
+
+// 2-D fp16 row-major matrix; box = 64 columns (128 B, one swizzle span) x box_rows rows; SWIZZLE_128B; OOB reads as zero
+int make_tmap_2d_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return TT_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(fp16) failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r, (long long)rows, (long long)cols, (long long)ld, box_rows);
         return TT_ERR_CUDA;
     }
     return TT_OK;
@@ -146,12 +167,177 @@ static size_t bwd_pass_floats(int nR, int nT, int E) {
     return align_up((size_t)pl.splits * nR * E, 64) + align_up((size_t)E * tt_ld(nT), 64) + (size_t)nT + 512;
 }
 
+
+
+// ---- stream-K host side ---------------------------------------------------------------------------------
+struct SkPlan {
+    int grid;       // CTAs
+    int units;
+    int slots[2];   // partial slots per panel (max number of CTAs that share a panel), per pass
+};
+static int sk_slots(int unit0, int m_tiles, int n_tiles, int units, int G) {
+    int mx = 1;
+    for (int pnl = 0; pnl < m_tiles; ++pnl) {
+        const int first = unit0 + pnl * n_tiles;
+        const int s = sk_owner(first + n_tiles - 1, units, G) - sk_owner(first, units, G) + 1;
+        mx = s > mx ? s : mx;
+    }
+    return mx;
+}
+static SkPlan sk_plan(int n_pass, const int* m_tiles, const int* n_tiles) {
+    SkPlan pl{};
+    pl.units = 0;
+    int unit0[2] = {0, 0};
+    for (int i = 0; i < n_pass; ++i) { unit0[i] = pl.units; pl.units += m_tiles[i] * n_tiles[i]; }
+    const int sms = sm_count();
+    pl.grid = pl.units < sms ? (pl.units > 0 ? pl.units : 1) : sms;
+    for (int i = 0; i < n_pass; ++i) pl.slots[i] = sk_slots(unit0[i], m_tiles[i], n_tiles[i], pl.units, pl.grid);
+    return pl;
+}
+
+template <int MODE, int E, int BN>
+static int launch_streamk(const SkMaps& maps, const SkParams& p, int grid, cudaStream_t st, const char* name) {
+    using Cfg = SkCfg<MODE, E, BN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        TT_CUDA_OK(cudaFuncSetAttribute(streamk_kernel<MODE, E, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_done = true;
+    }
+    streamk_kernel<MODE, E, BN><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
+    TT_LAUNCH_OK(name);
+    return TT_OK;
+}
+
+// per-row merge of the forward partials, slot order then warp-half order
+__global__ void fwd_combine_sk_kernel(const float* __restrict__ m2, const float* __restrict__ l, const float* __restrict__ zd, int nR, int n_tiles,
+                                      int units, int G, int halves, float* __restrict__ lse, float* __restrict__ rowloss) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nR) return;
+    const int first = (r >> 7) * n_tiles;
+    const int parts = (sk_owner(first + n_tiles - 1, units, G) - sk_owner(first, units, G) + 1) * halves;
+    float M = -CUDART_INF_F;
+    for (int s = 0; s < parts; ++s) M = fmaxf(M, m2[(int64_t)s * nR + r]);
+    float L = 0.f;
+    for (int s = 0; s < parts; ++s) {
+        float ms = m2[(int64_t)s * nR + r];
+        if (ms > -CUDART_INF_F) L += l[(int64_t)s * nR + r] * exp2f(ms - M);
+    }
+    float v = (M + log2f(L)) * 0.6931471805599453f;
+    lse[r] = v;
+    rowloss[r] = v - zd[r];
+}
+
+struct SkSide {   // one backward pass
+    const float* R; int ldr;
+    const float* T; int ldt;
+    const float* rowv; const float* colv;
+    int nR, nT, d;
+    float* G; int ldg;
+};
+struct PrepSide {
+    const float* T; int ldt, nT;
+    __half* Tt; int ldtt;   // fp16 transposed copy (E x ldtt)
+    const float* colv; float* c2; int n_pad;
+    int tblocks_x, tblocks;   // 32x32 transpose tiles: per row of tiles, total
+    int cblocks;              // scale/pad blocks of 256
+};
+struct PrepArgs { PrepSide s[2]; int n; int E; };
+// one launch: transposed fp16 copies of the streamed operands (B tiles of the second MMA) + scaled, padded column
+// terms, for every pass
+__global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
+    __shared__ float tile[32][33];
+    int b = blockIdx.x;
+    for (int i = 0; i < a.n; ++i) {
+        const PrepSide& sd = a.s[i];
+        if (b < sd.tblocks) {
+            const int r0 = (b % sd.tblocks_x) * 32, c0 = (b / sd.tblocks_x) * 32;
+            const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+            for (int k = ty; k < 32; k += 8) {
+                int r = r0 + k, c = c0 + tx;
+                tile[k][tx] = (r < sd.nT && c < a.E) ? sd.T[(int64_t)r * sd.ldt + c] : 0.f;
+            }
+            __syncthreads();
+            for (int k = ty; k < 32; k += 8) {
+                int c = c0 + k, r = r0 + tx;
+                if (c < a.E && r < sd.nT) sd.Tt[(int64_t)c * sd.ldtt + r] = __float2half_rn(tile[tx][k]);
+            }
+            return;
+        }
+        b -= sd.tblocks;
+        if (b < sd.cblocks) {
+            const int j = b * 256 + threadIdx.x;
+            if (j < sd.n_pad) sd.c2[j] = (j < sd.nT && sd.colv) ? sd.colv[j] * kLog2e : 0.f;
+            return;
+        }
+        b -= sd.cblocks;
+    }
+}
+
+struct RedSide { const float* part; float* G; int ldg, nR, n_tiles, unit0; };
+struct RedArgs { RedSide s[2]; int n, E, units, grid; };
+// G[r][:] = sum over the panel's CTA slots, in slot order (one thread per float4)
+__global__ void __launch_bounds__(256) bwd_reduce_sk_kernel(const RedArgs a) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int e4 = a.E >> 2;
+    for (int k = 0; k < a.n; ++k) {
+        const RedSide& sd = a.s[k];
+        const int64_t cnt = (int64_t)sd.nR * e4;
+        if (i < cnt) {
+            const int r = (int)(i / e4), c4 = (int)(i % e4);
+            const int first = sd.unit0 + (r >> 7) * sd.n_tiles;
+            const int slots = sk_owner(first + sd.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int z = 0; z < slots; ++z) {
+                const float4 v = *reinterpret_cast<const float4*>(sd.part + ((int64_t)z * sd.nR + r) * a.E + 4 * c4);
+                acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+            }
+            float* dst = sd.G + (int64_t)r * sd.ldg + 4 * c4;
+            dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w;
+            return;
+        }
+        i -= cnt;
+    }
+}
+
+static inline int sk_bwd_bn(int E) { return E <= 64 ? 128 : 64; }   // shared-memory budget (SkCfg)
+static inline size_t sk_ldtt(int n) { return align_up((size_t)n, 8); }   // fp16 row stride: 16-byte multiples
+
+static size_t bwd_sk_floats(int n_sides, const int* nR, const int* nT, int E) {
+    const int bn = sk_bwd_bn(E);
+    int mt[2], nt[2];
+    for (int i = 0; i < n_sides; ++i) { mt[i] = (int)ceil_div(nR[i], 128); nt[i] = (int)ceil_div(nT[i], bn); }
+    SkPlan pl = sk_plan(n_sides, mt, nt);
+    size_t f = 0;
+    for (int i = 0; i < n_sides; ++i) {
+        f += align_up((size_t)pl.slots[i] * nR[i] * E, 64);          // partial blocks
+        f += align_up((size_t)E * sk_ldtt(nT[i]) / 2, 64);           // T^T (fp16)
+        f += align_up((size_t)nt[i] * bn, 64);                       // scaled column term
+    }
+    return f + 512;
+}
+
 size_t softmax_tc_workspace(int Bq, int Bc, int E) {
     size_t rows = (size_t)(Bq > Bc ? Bq : Bc);
-    size_t fwd = (4 * (size_t)kMaxSplits + 4) * align_up(rows * sizeof(float), 256) + 2048;
+    // forward: m2, l partials (slots x 2 halves) + zdiag + rowloss + scaled column term
+    int mt = (int)ceil_div(Bq, 128), nt = (int)ceil_div(Bc, kFwdBN);
+    SkPlan pf = sk_plan(1, &mt, &nt);
+    size_t seg = align_up(rows * sizeof(float), 256);
+    size_t fwd = (4 * (size_t)pf.slots[0] + 2) * seg + align_up(((size_t)nt * kFwdBN + 64) * sizeof(float), 256) + 2048;
+    // backward: both passes at once, or one pass alone (tt_inbatch_softmax_bwd_one)
+    int nR[2] = {Bq, Bc}, nT[2] = {Bc, Bq};
+    size_t both = bwd_sk_floats(2, nR, nT, E) * sizeof(float);
+    int nRq[1] = {Bq}, nTq[1] = {Bc}, nRc[1] = {Bc}, nTc[1] = {Bq};
+    size_t one_q = bwd_sk_floats(1, nRq, nTq, E) * sizeof(float), one_c = bwd_sk_floats(1, nRc, nTc, E) * sizeof(float);
+    size_t bwd = both > one_q ? both : one_q;
+    bwd = bwd > one_c ? bwd : one_c;
+    // the split-launch kernels (debug / legacy path)
     size_t a = bwd_pass_floats(Bq, Bc, E) * sizeof(float), b = bwd_pass_floats(Bc, Bq, E) * sizeof(float);
-    size_t bwd = a > b ? a : b;
-    return (fwd > bwd ? fwd : bwd) + 1024;
+    size_t legacy_fwd = (4 * (size_t)kMaxSplits + 4) * align_up(rows * sizeof(float), 256) + 2048;
+    size_t m = fwd > bwd ? fwd : bwd;
+    m = m > a ? m : a;
+    m = m > b ? m : b;
+    m = m > legacy_fwd ? m : legacy_fwd;
+    return m + 1024;
 }
 
 }  // namespace tc
@@ -176,33 +362,103 @@ bool softmax_tc_supported(int ldq, int ldc, int E, const void* Q, const void* C)
 
 int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
                    float* ws, cudaStream_t st) {
-    Plan pl = plan_for(Bq, Bc, kFwdBN);
-    CUtensorMap tmQ, tmC;
-    int rc = make_tmap_2d(&tmQ, Q, Bq, E, ldq, 128);
+    int mt = (int)ceil_div(Bq, 128), nt = (int)ceil_div(Bc, kFwdBN);
+    SkPlan pl = sk_plan(1, &mt, &nt);
+    SkMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc = make_tmap_2d(&maps.r[0], Q, Bq, E, ldq, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmC, C, Bc, E, ldc, kFwdBN);
+    rc = make_tmap_2d(&maps.t[0], C, Bc, E, ldc, kFwdBN);
     if (rc) return rc;
     size_t rows = (size_t)(Bq > Bc ? Bq : Bc);
     size_t seg = align_up(rows * sizeof(float), 256) / sizeof(float);
-    float* m2 = ws;
-    float* l = ws + 2 * (size_t)kMaxSplits * seg;
-    float* zd = ws + 4 * (size_t)kMaxSplits * seg;
-    float* rowloss = zd + seg;
-    float* c2 = rowloss + seg;
-    rc = launch_scale_pad(bias, Bc, c2, pl.n_tiles * kFwdBN, st);
+    float* rowloss = ws;                                   // (the SIMT path keeps its row losses at the workspace base too)
+    float* zd = rowloss + seg;
+    float* m2 = zd + seg;
+    float* l = m2 + 2 * (size_t)pl.slots[0] * seg;
+    float* c2 = l + 2 * (size_t)pl.slots[0] * seg;
+    rc = launch_scale_pad(bias, Bc, c2, nt * kFwdBN, st);
     if (rc) return rc;
-    RowPanelParams p{};
-    p.nR = Bq; p.nT = Bc; p.n_tiles = pl.n_tiles; p.tiles_per_split = pl.tps; p.rowv = nullptr; p.colv2 = c2; p.d = off;
-    p.out0 = m2; p.out1 = l; p.out2 = zd; p.ld_out = 0; p.trace = g_trace;
+    SkParams p{};
+    p.n_pass = 1; p.units = pl.units;
+    SkPass& ps = p.pass[0];
+    ps.nR = Bq; ps.nT = Bc; ps.m_tiles = mt; ps.n_tiles = nt; ps.d = off; ps.unit0 = 0; ps.rowv = nullptr; ps.colv2 = c2;
+    ps.out0 = m2; ps.out1 = l; ps.out2 = zd;
     switch (E) {
-        case 32: rc = launch_rowpanel<kFwd, 32, kFwdBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<fwd,32>"); break;
-        case 64: rc = launch_rowpanel<kFwd, 64, kFwdBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<fwd,64>"); break;
-        default: rc = launch_rowpanel<kFwd, 128, kFwdBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<fwd,128>"); break;
+        case 32: rc = launch_streamk<kFwd, 32, kFwdBN>(maps, p, pl.grid, st, "streamk_kernel<fwd,32>"); break;
+        case 64: rc = launch_streamk<kFwd, 64, kFwdBN>(maps, p, pl.grid, st, "streamk_kernel<fwd,64>"); break;
+        default: rc = launch_streamk<kFwd, 128, kFwdBN>(maps, p, pl.grid, st, "streamk_kernel<fwd,128>"); break;
     }
     if (rc) return rc;
-    fwd_combine_kernel<<<(unsigned)ceil_div(Bq, 256), 256, 0, st>>>(m2, l, zd, pl.splits * 2 /* kHalves for BN=128 */, Bq, lse, rowloss);
-    TT_LAUNCH_OK("fwd_combine_kernel");
+    fwd_combine_sk_kernel<<<(unsigned)ceil_div(Bq, 256), 256, 0, st>>>(m2, l, zd, Bq, nt, pl.units, pl.grid, 2 /* kHalves for BN=128 */, lse, rowloss);
+    TT_LAUNCH_OK("fwd_combine_sk_kernel");
     return sum_rows_launch(rowloss, Bq, loss, st);
+}
+
+// one launch for `n` backward passes (dQ and dC, or one of them)
+int softmax_bwd_sk(const SkSide* sides, int n, int E, float* ws, cudaStream_t st) {
+    const int bn = sk_bwd_bn(E);
+    int mt[2] = {0, 0}, nt[2] = {0, 0};
+    for (int i = 0; i < n; ++i) { mt[i] = (int)ceil_div(sides[i].nR, 128); nt[i] = (int)ceil_div(sides[i].nT, bn); }
+    SkPlan pl = sk_plan(n, mt, nt);
+    SkMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    SkParams p{};
+    p.n_pass = n; p.units = pl.units;
+    PrepArgs pa{};
+    pa.n = n; pa.E = E;
+    RedArgs ra{};
+    ra.n = n; ra.E = E; ra.units = pl.units; ra.grid = pl.grid;
+    float* cur = ws;
+    int unit0 = 0, prep_blocks = 0;
+    int64_t red_items = 0;
+    for (int i = 0; i < n; ++i) {
+        const SkSide& sd = sides[i];
+        float* part = cur; cur += align_up((size_t)pl.slots[i] * sd.nR * E, 64);
+        __half* Tt = reinterpret_cast<__half*>(cur); const int ldtt = (int)sk_ldtt(sd.nT); cur += align_up((size_t)E * ldtt / 2, 64);
+        float* c2 = cur; cur += align_up((size_t)nt[i] * bn, 64);
+        int rc = make_tmap_2d(&maps.r[i], sd.R, sd.nR, E, sd.ldr, 128);
+        if (rc) return rc;
+        rc = make_tmap_2d(&maps.t[i], sd.T, sd.nT, E, sd.ldt, bn);
+        if (rc) return rc;
+        rc = make_tmap_2d_f16(&maps.tt[i], Tt, E, sd.nT, ldtt, E);
+        if (rc) return rc;
+        SkPass& ps = p.pass[i];
+        ps.nR = sd.nR; ps.nT = sd.nT; ps.m_tiles = mt[i]; ps.n_tiles = nt[i]; ps.d = sd.d; ps.unit0 = unit0; ps.rowv = sd.rowv; ps.colv2 = c2;
+        ps.out0 = part; ps.out1 = nullptr; ps.out2 = nullptr;
+        PrepSide& pp = pa.s[i];
+        pp.T = sd.T; pp.ldt = sd.ldt; pp.nT = sd.nT; pp.Tt = Tt; pp.ldtt = ldtt; pp.colv = sd.colv; pp.c2 = c2; pp.n_pad = nt[i] * bn;
+        pp.tblocks_x = (int)ceil_div(sd.nT, 32); pp.tblocks = pp.tblocks_x * (int)ceil_div(E, 32); pp.cblocks = (int)ceil_div(pp.n_pad, 256);
+        prep_blocks += pp.tblocks + pp.cblocks;
+        RedSide& rs = ra.s[i];
+        rs.part = part; rs.G = sd.G; rs.ldg = sd.ldg; rs.nR = sd.nR; rs.n_tiles = nt[i]; rs.unit0 = unit0;
+        red_items += (int64_t)sd.nR * (E / 4);
+        unit0 += mt[i] * nt[i];
+    }
+    if (pl.units == 0) return TT_OK;
+    bwd_prep_kernel<<<(unsigned)prep_blocks, 256, 0, st>>>(pa);
+    TT_LAUNCH_OK("bwd_prep_kernel");
+    int rc;
+    switch (E) {
+        case 32: rc = launch_streamk<kBwd, 32, 128>(maps, p, pl.grid, st, "streamk_kernel<bwd,32>"); break;
+        case 64: rc = launch_streamk<kBwd, 64, 128>(maps, p, pl.grid, st, "streamk_kernel<bwd,64>"); break;
+        default: rc = launch_streamk<kBwd, 128, 64>(maps, p, pl.grid, st, "streamk_kernel<bwd,128>"); break;
+    }
+    if (rc) return rc;
+    bwd_reduce_sk_kernel<<<(unsigned)ceil_div(red_items, 256), 256, 0, st>>>(ra);
+    TT_LAUNCH_OK("bwd_reduce_sk_kernel");
+    return TT_OK;
+}
+
+// (Q, C) backward: which = 0 dQ only, 1 dC only, 2 both (G0 = dQ, G1 = dC)
+int softmax_bwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E, int off, int which,
+                   float* G0, int ldg0, float* G1, int ldg1, float* ws, cudaStream_t st) {
+    SkSide sides[2];
+    int n = 0;
+    if (which == 0 || which == 2) sides[n++] = SkSide{Q, ldq, C, ldc, lse, bias, Bq, Bc, off, G0, ldg0};
+    if (which == 1) sides[n++] = SkSide{C, ldc, Q, ldq, bias, lse, Bc, Bq, -off, G0, ldg0};
+    if (which == 2) sides[n++] = SkSide{C, ldc, Q, ldq, bias, lse, Bc, Bq, -off, G1, ldg1};
+    return softmax_bwd_sk(sides, n, E, ws, st);
 }
 
 int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const float* rowv, const float* colv, int nR, int nT, int E, int d,

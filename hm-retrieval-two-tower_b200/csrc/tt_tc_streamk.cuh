@@ -1,0 +1,401 @@
+// tt_tc_streamk.cuh -- persistent ("stream-K") form of the logits-shaped softmax kernels.
+//
+// The in-batch softmax is a grid of work units, one per (128-row panel of the resident operand R, BN-row tile of the
+// streamed operand T):  S(128 x BN) = R_panel . T_tile^T on tcgen05 (kind::tf32, fp32 accumulators in TMEM), consumed by
+// the epilogue warps straight from TMEM.  rowpanel_kernel (tt_tc_rowpanel.cuh) launches one CTA per (panel, column
+// split); with 64 panels that fills 128 of the 148 SMs and the backward runs as two such launches.  Here ONE launch of
+// (at most) one CTA per SM walks a contiguous range of the unit list -- all panels of the dQ pass followed by all panels
+// of the dC pass -- so every SM gets the same number of units (+-1).  A CTA whose range crosses a panel boundary
+// switches panels in flight: the producer reloads R once the last MMA that reads it has completed, the MMA warp flips
+// to the second G accumulator, the epilogue warps flush the finished panel (per-row log-sum-exp partials forward, the
+// 128 x E gradient block backward) into a per-(panel, CTA slot) partial buffer.  A panel is covered by consecutive CTAs;
+// its partials are merged in slot order by a small kernel (fixed order: deterministic, no atomics).
+//
+//   kFwd  z = s*log2e - colv2_j; online max / sum 2^(z - max) per row; diagonal logit          (tt_inbatch_softmax_fwd)
+//   kBwd  P = 2^(z - rowv_i*log2e) - [j == i + d] -> fp16 -> swizzled smem = A operand of the 2nd MMA (kind::f16)
+//         G(128 x E) += P . T_tile; the B operand is a K-major fp16 tile of T^T (TMA from a transposed fp16 copy)
+//                                                                                                (tt_inbatch_softmax_bwd)
+#pragma once
+#include "tt_tc_rowpanel.cuh"
+
+namespace tt {
+namespace tc {
+
+struct SkPass {
+    int nR, nT;          // rows of the resident operand / of the streamed operand
+    int m_tiles, n_tiles;
+    int d;               // diagonal: column == row + d
+    int unit0;           // first work unit of this pass
+    const float* rowv;   // kBwd: per-R-row term (lse or ln p), natural units; may be null (zero)
+    const float* colv2;  // per-T-row term * log2(e), zero padded to n_tiles*BN entries (never null)
+    float* out0;         // kFwd: m2 [slot][half][nR] | kBwd: G partial [slot][nR][E]
+    float* out1;         // kFwd: l  [slot][half][nR]
+    float* out2;         // kFwd: zdiag [nR] (natural units)
+};
+struct SkParams {
+    SkPass pass[2];
+    int n_pass;
+    int units;           // work units of all passes
+};
+struct SkMaps {
+    CUtensorMap r[2], t[2], tt[2];   // per pass: R panels (box 128 rows), T tiles (box BN rows), T^T tiles (box E rows)
+};
+
+// CTA b of G owns units [sk_begin(b), sk_begin(b + 1)); sk_owner inverts it
+__host__ __device__ inline int sk_begin(int b, int units, int G) { return (int)(((long long)b * units) / G); }
+__host__ __device__ inline int sk_owner(int u, int units, int G) { return (int)((((long long)u + 1) * G + units - 1) / units) - 1; }
+
+struct SkCursor {   // position in the unit list
+    int pass, panel, tile;
+    __device__ __forceinline__ void init(const SkParams& p, int u) {
+        pass = (p.n_pass > 1 && u >= p.pass[1].unit0) ? 1 : 0;
+        const int local = u - p.pass[pass].unit0;
+        panel = local / p.pass[pass].n_tiles;
+        tile = local - panel * p.pass[pass].n_tiles;
+    }
+    __device__ __forceinline__ void next(const SkParams& p) {
+        if (++tile == p.pass[pass].n_tiles) {
+            tile = 0;
+            if (++panel == p.pass[pass].m_tiles) { panel = 0; ++pass; }
+        }
+    }
+};
+
+template <int MODE, int E, int BN>
+struct SkCfg {
+    static constexpr int kSlabs = E / 32;                               // 128-byte K slabs per fp32/TF32 operand row
+    static constexpr int kRBytes = kSlabs * 128 * 128;                  // R panel (TF32, K-major over E)
+    static constexpr int kT1Bytes = kSlabs * BN * 128;                  // T tile (TF32, K-major over E): first MMA
+    static constexpr int kT2Bytes = (MODE == kBwd) ? (BN / 64) * E * 128 : 0;     // T^T tile (fp16, K-major over BN): second MMA
+    static constexpr int kTBytes = kT1Bytes + kT2Bytes;
+    static constexpr int kPBytes = (MODE == kBwd) ? (BN / 64) * 128 * 128 : 0;    // P tile (fp16, K-major over BN)
+    static constexpr int kPBufs = (MODE == kBwd) ? 2 : 0;
+    static constexpr int kC2Bytes = BN * 4;
+    static constexpr int kFixed = kRBytes + kPBufs * kPBytes + 4 * 1024 /*c2 stages*/ + 1024 /*barriers*/ + 1024 /*align*/;
+    static constexpr int kFit = (232448 - kFixed) / kTBytes;
+    static constexpr int kStages = kFit >= 4 ? 4 : kFit;                // T ring depth
+    static constexpr int kSmemBytes = kFixed + kStages * kTBytes;
+    static constexpr int kHalves = (BN / 32 >= 2) ? 2 : 1;              // epilogue warps per TMEM lane quarter
+    static constexpr int kEpiWarps = 4 * kHalves;
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;
+    static constexpr int kTmemNeed = (MODE == kBwd) ? 2 * BN + 2 * E : 2 * BN;
+    static constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512);
+    static_assert(kStages >= 2, "shared memory budget");
+    static_assert(kTmemNeed <= 512, "TMEM budget");
+    static_assert(MODE == kFwd || MODE == kBwd, "stream-K kernel: forward or backward");
+    static_assert(MODE != kBwd || BN % 64 == 0, "backward: BN must be a multiple of 64 (fp16 slabs of 64 columns)");
+    static_assert(E == 32 || E == 64 || E == 128, "E must be 32, 64 or 128");
+};
+
+// instruction descriptor for kind::f16 with fp16 operands, fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4)                       // c_format  = F32
+           | (0u << 7)                     // a_format  = F16
+           | (0u << 10)                    // b_format  = F16
+           | (static_cast<uint32_t>(N >> 3) << 17)
+           | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {   // round-to-nearest-even, lo in the low half
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// backward epilogue body: 32 columns of one row -> P = 2^(z - r2) - [diag] as fp16 into the swizzled A tile of the second MMA
+// (fp16 keeps the 11 significant bits TF32 would; P lies in [-1, 1], values below 6e-5 lose relative precision only)
+template <bool FAST>
+__device__ __forceinline__ void bwd_chunk_h(const uint32_t (&r)[32], uint32_t c2s, int nb, int row, int row_l, int nT, int nR, int d, float r2,
+                                            uint32_t prow, int half_of_slab) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {            // 16-byte pieces of 8 columns
+        float pv[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float4 cc = lds128(c2s + (j * 2 + h) * 16);
+            const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = j * 8 + h * 4 + t;
+                float v = ex2_approx(fmaf(__uint_as_float(r[i]), kLog2e, -r2) - cv[t]);
+                if (!FAST) {
+                    const int n = nb + i;
+                    if (n >= nT || row >= nR) v = 0.f;
+                    else if (n == row + d) v -= 1.0f;
+                }
+                pv[h * 4 + t] = v;
+            }
+        }
+        const uint32_t w0 = pack_f16x2(pv[0], pv[1]), w1 = pack_f16x2(pv[2], pv[3]), w2 = pack_f16x2(pv[4], pv[5]), w3 = pack_f16x2(pv[6], pv[7]);
+        const uint32_t piece = static_cast<uint32_t>(half_of_slab * 4 + j);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((piece ^ (row_l & 7)) << 4)), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+    }
+}
+
+struct SkBars {
+    uint64_t r_full, r_empty;
+    uint64_t t_full[4], t_empty[4];
+    uint64_t s_full[2], s_empty[2];
+    uint64_t p_full[2], p_empty[2];
+    uint64_t g_full[2], g_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int MODE, int E, int BN>
+__global__ void __launch_bounds__(SkCfg<MODE, E, BN>::kThreads, 1)
+streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkParams p) {
+    using Cfg = SkCfg<MODE, E, BN>;
+    using Sk = SkCfg<MODE, E, BN>;
+    const int u_begin = sk_begin(blockIdx.x, p.units, gridDim.x), u_end = sk_begin(blockIdx.x + 1, p.units, gridDim.x);
+    const int my_units = u_end - u_begin;
+    if (my_units <= 0) return;   // (uniform) more CTAs than work units
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    unsigned char* sR = smem;
+    unsigned char* sT = sR + Cfg::kRBytes;
+    unsigned char* sP = sT + Cfg::kStages * Cfg::kTBytes;
+    unsigned char* sC2 = sP + Cfg::kPBufs * Cfg::kPBytes;       // kStages x 1 KB
+    SkBars* bars = reinterpret_cast<SkBars*>(sC2 + 4 * 1024);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            if (i < p.n_pass) {
+                prefetch_tmap(&maps.r[i]);
+                prefetch_tmap(&maps.t[i]);
+                if (MODE == kBwd) prefetch_tmap(&maps.tt[i]);
+            }
+        }
+        mbar_init(&bars->r_full, 1);
+        mbar_init(&bars->r_empty, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], MODE == kBwd ? 1 : 1 + Cfg::kEpiWarps); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], Cfg::kEpiWarps);
+            mbar_init(&bars->p_full[i], Cfg::kEpiWarps); mbar_init(&bars->p_empty[i], 1);
+            mbar_init(&bars->g_full[i], 1); mbar_init(&bars->g_empty[i], Cfg::kEpiWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, Sk::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            SkCursor c;
+            c.init(p, u_begin);
+            int k = 0;   // panels loaded so far
+            for (int it = 0; it < my_units; ++it, c.next(p)) {
+                const SkPass& ps = p.pass[c.pass];
+                if (it == 0 || c.tile == 0) {   // a new panel: R may be overwritten once the last MMA reading it has completed
+                    mbar_wait(&bars->r_empty, (k & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bars->r_full, Cfg::kRBytes);
+                    for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(sR + s * 128 * 128, &maps.r[c.pass], &bars->r_full, s * 32, c.panel * 128);
+                    ++k;
+                }
+                const int stage = it % Cfg::kStages;
+                const uint32_t ph = (it / Cfg::kStages) & 1;
+                const int n0 = c.tile * BN;
+                mbar_wait(&bars->t_empty[stage], ph ^ 1);
+                mbar_arrive_expect_tx(&bars->t_full[stage], Cfg::kTBytes + Cfg::kC2Bytes);
+                unsigned char* dst = sT + stage * Cfg::kTBytes;
+                for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(dst + s * BN * 128, &maps.t[c.pass], &bars->t_full[stage], s * 32, n0);
+                if (MODE == kBwd) {
+                    for (int s = 0; s < BN / 64; ++s)   // fp16 T^T: boxes of 64 columns (128 bytes) x E rows
+                        tma_load_2d(dst + Cfg::kT1Bytes + s * E * 128, &maps.tt[c.pass], &bars->t_full[stage], n0 + s * 64, 0);
+                }
+                bulk_copy_1d(sC2 + stage * 1024, ps.colv2 + n0, Cfg::kC2Bytes, &bars->t_full[stage]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc1 = make_idesc_tf32(128, BN, false, false);
+        constexpr uint32_t idesc2 = make_idesc_f16(128, E);
+        const uint32_t sR_a = smem_u32(sR), sT_a = smem_u32(sT), sP_a = smem_u32(sP);
+        SkCursor c1;   // unit whose first MMA is issued next
+        c1.init(p, u_begin);
+        int k1 = -1;   // panel sequence number of c1's unit
+        auto issue_g1 = [&](int it) {
+            const bool panel_start = (it == 0 || c1.tile == 0);
+            const bool panel_end = (it == my_units - 1 || c1.tile == p.pass[c1.pass].n_tiles - 1);
+            if (panel_start) {
+                ++k1;
+                mbar_wait(&bars->r_full, k1 & 1);
+            }
+            const int stage = it % Cfg::kStages;
+            const uint32_t tph = (it / Cfg::kStages) & 1;
+            const int acc = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(&bars->t_full[stage], tph);
+            mbar_wait(&bars->s_empty[acc], aph ^ 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < E / 8; ++k) {
+                    const uint32_t off = (k >> 2) * 128 * 128 + (k & 3) * 32;
+                    const uint32_t offT = (k >> 2) * BN * 128 + (k & 3) * 32;
+                    uint64_t ad = make_smem_desc(sR_a + off, 16, 1024);
+                    uint64_t bd = make_smem_desc(sT_a + stage * Cfg::kTBytes + offT, 16, 1024);
+                    mma_tf32(tmem + acc * BN, ad, bd, idesc1, k > 0 ? 1u : 0u);
+                }
+                if (MODE != kBwd) mma_commit(&bars->t_empty[stage]);   // T tile consumed (the epilogue releases the staged column term)
+                mma_commit(&bars->s_full[acc]);
+                if (panel_end) mma_commit(&bars->r_empty);             // the last MMA that reads this R panel
+            }
+            __syncwarp();
+            c1.next(p);
+        };
+        if constexpr (MODE != kBwd) {
+            for (int it = 0; it < my_units; ++it) issue_g1(it);
+        } else {
+            SkCursor c2;   // unit whose second MMA is issued next
+            c2.init(p, u_begin);
+            int k2 = -1;
+            issue_g1(0);
+            for (int it = 0; it < my_units; ++it, c2.next(p)) {
+                if (it + 1 < my_units) issue_g1(it + 1);  // keep the tensor core busy while the epilogue builds P(it)
+                const bool panel_start = (it == 0 || c2.tile == 0);
+                const bool panel_end = (it == my_units - 1 || c2.tile == p.pass[c2.pass].n_tiles - 1);
+                if (panel_start) {
+                    ++k2;
+                    mbar_wait(&bars->g_empty[k2 & 1], ((k2 >> 1) & 1) ^ 1);   // the epilogue has drained this G buffer
+                }
+                const int gb = k2 & 1;
+                const int stage = it % Cfg::kStages;
+                const int pb = it & 1;
+                const uint32_t pph = (it >> 1) & 1;
+                mbar_wait(&bars->p_full[pb], pph);
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int kk = 0; kk < BN / 16; ++kk) {   // fp16: 16 columns (32 bytes) per MMA, 64 per swizzle slab
+                        uint64_t ad = make_smem_desc(sP_a + pb * Cfg::kPBytes + (kk >> 2) * 128 * 128 + (kk & 3) * 32, 16, 1024);
+                        uint64_t bd = make_smem_desc(sT_a + stage * Cfg::kTBytes + Cfg::kT1Bytes + (kk >> 2) * E * 128 + (kk & 3) * 32, 16, 1024);
+                        mma_f16(tmem + 2 * BN + gb * E, ad, bd, idesc2, (!panel_start || kk > 0) ? 1u : 0u);
+                    }
+                    mma_commit(&bars->t_empty[stage]);  // T, T^T and c2 of this stage are all consumed by now
+                    mma_commit(&bars->p_empty[pb]);
+                    if (panel_end) mma_commit(&bars->g_full[gb]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== epilogue warps (2..) =====================
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // which share of each tile's columns this warp handles
+        const int row_l = q * 32 + lane;              // row within the panel == TMEM lane
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        constexpr int NC = BN / 32;
+        constexpr int NCW = NC / Cfg::kHalves;        // 32-column chunks per warp per tile
+        const int c_first = half * NCW;
+        SkCursor c;
+        c.init(p, u_begin);
+        int k = -1;                                   // panel sequence number
+        int row = 0, slot = 0;
+        float m2 = -CUDART_INF_F, l = 0.f, zd = 0.f, r2 = 0.f;
+        bool has_diag = false;
+        for (int it = 0; it < my_units; ++it, c.next(p)) {
+            const SkPass& ps = p.pass[c.pass];
+            const bool panel_start = (it == 0 || c.tile == 0);
+            const bool panel_end = (it == my_units - 1 || c.tile == ps.n_tiles - 1);
+            if (panel_start) {
+                ++k;
+                row = c.panel * 128 + row_l;
+                slot = blockIdx.x - sk_owner(ps.unit0 + c.panel * ps.n_tiles, p.units, gridDim.x);
+                m2 = -CUDART_INF_F; l = 0.f; zd = 0.f; has_diag = false;
+                if (MODE == kBwd) r2 = (row < ps.nR && ps.rowv) ? __ldg(ps.rowv + row) * kLog2e : 0.f;
+            }
+            const int wrow0 = c.panel * 128 + q * 32;     // first row of this warp
+            const int acc = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int stage = it % Cfg::kStages;
+            const int n0 = c.tile * BN;
+            const int pb = it & 1;
+            // warp-uniform: tile fully in range and no diagonal element of this warp's rows inside it
+            const bool fast = (n0 + BN <= ps.nT) && (wrow0 + 32 <= ps.nR) && (wrow0 + ps.d + 32 <= n0 || wrow0 + ps.d >= n0 + BN);
+            mbar_wait(&bars->s_full[acc], aph);
+            tc_fence_after();
+            mbar_wait(&bars->t_full[stage], (it / Cfg::kStages) & 1);   // completed long ago; acquires the staged column term
+            if (MODE == kBwd) mbar_wait(&bars->p_empty[pb], ((it >> 1) & 1) ^ 1);
+            const uint32_t c2s = smem_u32(sC2 + stage * 1024);
+            uint32_t rbuf[2][32];
+            tmem_ld_32x32_issue(tmem + lane_addr + acc * BN + c_first * 32, rbuf[0]);
+#pragma unroll
+            for (int cl = 0; cl < NCW; ++cl) {
+                const int cc = c_first + cl;
+                tmem_ld_wait();
+                if (cl + 1 < NCW) tmem_ld_32x32_issue(tmem + lane_addr + acc * BN + (cc + 1) * 32, rbuf[(cl + 1) & 1]);
+                uint32_t(&r)[32] = rbuf[cl & 1];
+                const int nb = n0 + cc * 32;
+                if constexpr (MODE == kFwd) {
+                    if (fast) fwd_chunk<true>(r, c2s + cc * 128, nb, row, ps.nT, ps.d, m2, l, zd, has_diag);
+                    else fwd_chunk<false>(r, c2s + cc * 128, nb, row, ps.nT, ps.d, m2, l, zd, has_diag);
+                } else {
+                    const uint32_t prow = smem_u32(sP + pb * Cfg::kPBytes + (cc >> 1) * 128 * 128 + row_l * 128);
+                    if (fast) bwd_chunk_h<true>(r, c2s + cc * 128, nb, row, row_l, ps.nT, ps.nR, ps.d, r2, prow, cc & 1);
+                    else bwd_chunk_h<false>(r, c2s + cc * 128, nb, row, row_l, ps.nT, ps.nR, ps.d, r2, prow, cc & 1);
+                }
+            }
+            // this S buffer may be overwritten by the MMA of unit it+2
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&bars->s_empty[acc]);
+                if (MODE != kBwd) mbar_arrive(&bars->t_empty[stage]);   // c2 of this stage consumed
+            }
+            if constexpr (MODE == kBwd) {
+                fence_proxy_async_smem();   // P stores (generic proxy) -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->p_full[pb]);
+            }
+            if (panel_end) {
+                if constexpr (MODE == kFwd) {
+                    if (row < ps.nR) {
+                        // one partial per (CTA slot of the panel, warp half): the combine kernel merges them in slot order
+                        ps.out0[((int64_t)slot * Cfg::kHalves + half) * ps.nR + row] = m2;
+                        ps.out1[((int64_t)slot * Cfg::kHalves + half) * ps.nR + row] = l;
+                        if (has_diag) ps.out2[row] = zd;
+                    }
+                } else {
+                    const int gb = k & 1;
+                    mbar_wait(&bars->g_full[gb], (k >> 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int cg = half; cg < E / 32; cg += Cfg::kHalves) {
+                        float v[32];
+                        tmem_ld_32x32(tmem + lane_addr + 2 * BN + gb * E + cg * 32, v);
+                        if (row < ps.nR) {
+                            float4* dst = reinterpret_cast<float4*>(ps.out0 + ((int64_t)slot * ps.nR + row) * E + cg * 32);
+#pragma unroll
+                            for (int g4 = 0; g4 < 8; ++g4) dst[g4] = make_float4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->g_empty[gb]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, Sk::kTmemCols);
+    }
+}
+
+}  // namespace tc
+}  // namespace tt

@@ -253,15 +253,13 @@ class TwoTowerModel(AbstractKerasModel):
         impl = N.TT_IMPL_TC if use_tc else N.TT_IMPL_SIMT
         N.check(lib.tt_inbatch_softmax_fwd(qa.data_ptr(), e, ca.data_ptr(), e, bias, b, b, e, 0, sw.lse.data_ptr(),
                                            sw.loss.data_ptr(), sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st), "tt_inbatch_softmax_fwd")
-        # backward: dQ -> query tower on the main stream, dC -> candidate tower on the candidate stream
+        # backward: ONE persistent launch covers the dQ and the dC pass; then dQ -> query tower on the main stream,
+        # dC -> candidate tower on the candidate stream
+        N.check(lib.tt_inbatch_softmax_bwd(qa.data_ptr(), e, ca.data_ptr(), e, bias, sw.lse.data_ptr(), b, b, e, 0, sw.dq.data_ptr(), e,
+                                           sw.dc.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st), "tt_inbatch_softmax_bwd")
         sw.cand.wait_stream(main)
-        N.check(lib.tt_inbatch_softmax_bwd_one(qa.data_ptr(), e, ca.data_ptr(), e, bias, sw.lse.data_ptr(), b, b, e, 0, 0,
-                                               sw.dq.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st), "tt_inbatch_softmax_bwd_one(dQ)")
         self.query_tower.backward_ws(sw.q, sw.dq)
         with torch.cuda.stream(sw.cand):
-            N.check(lib.tt_inbatch_softmax_bwd_one(qa.data_ptr(), e, ca.data_ptr(), e, bias, sw.lse.data_ptr(), b, b, e, 0, 1,
-                                                   sw.dc.data_ptr(), e, sw.sm_ws2.data_ptr(), sw.sm_ws2.numel(), impl, N.stream_ptr()),
-                    "tt_inbatch_softmax_bwd_one(dC)")
             self.candidate_tower.backward_ws(sw.c, sw.dc)
         main.wait_stream(sw.cand)
         if self.dist is not None:
