@@ -141,7 +141,9 @@ static int launch_rowpanel(const CUtensorMap& tmR, const CUtensorMap& tmT, const
     return TT_OK;
 }
 
-constexpr int kFwdBN = 128;
+constexpr int kFwdBN = 256;     // forward tile width: the per-unit costs of the producer and MMA lanes amortise over 2x the columns
+constexpr int kLogitsBN = 128;  // rowpanel_kernel<kLogits>
+constexpr int kFwdHalves = 4;    // SkCfg<kFwd, E, 128>::kHalves
 constexpr int kMaxSplits = 16;   // column splits per launch; the forward keeps 2 partials per split (one per warp half)
 
 // debug knobs (tt_debug_tc): timeline buffer and a cap on the column splits
@@ -195,15 +197,15 @@ static SkPlan sk_plan(int n_pass, const int* m_tiles, const int* n_tiles) {
     return pl;
 }
 
-template <int MODE, int E, int BN>
+template <int MODE, int E, int BN, bool H>
 static int launch_streamk(const SkMaps& maps, const SkParams& p, int grid, cudaStream_t st, const char* name) {
-    using Cfg = SkCfg<MODE, E, BN>;
+    using Cfg = SkCfg<MODE, E, BN, H>;
     static bool attr_done = false;
     if (!attr_done) {
-        TT_CUDA_OK(cudaFuncSetAttribute(streamk_kernel<MODE, E, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        TT_CUDA_OK(cudaFuncSetAttribute(streamk_kernel<MODE, E, BN, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_done = true;
     }
-    streamk_kernel<MODE, E, BN><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
+    streamk_kernel<MODE, E, BN, H><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
     TT_LAUNCH_OK(name);
     return TT_OK;
 }
@@ -234,43 +236,55 @@ struct SkSide {   // one backward pass
     int nR, nT, d;
     float* G; int ldg;
 };
-struct PrepSide {
-    const float* T; int ldt, nT;
-    __half* Tt; int ldtt;   // fp16 transposed copy (E x ldtt)
-    const float* colv; float* c2; int n_pad;
-    int tblocks_x, tblocks;   // 32x32 transpose tiles: per row of tiles, total
+struct PrepItem {   // one matrix X (n x E, leading dimension ld) and/or one per-row vector of it
+    const float* X; int ld, n;
+    __half* Xh;               // fp16 row-major copy (n x E, dense), or null
+    __half* Xt; int ldtt;     // fp16 transposed copy (E x ldtt), or null
+    const float* colv; float* c2; int n_pad;   // c2[j] = colv[j] * log2 e, zero padded to n_pad (c2 null: skip)
+    int tblocks_x, tblocks;   // 32x32 tiles: per row of tiles, total (0 when no copy is wanted)
     int cblocks;              // scale/pad blocks of 256
 };
-struct PrepArgs { PrepSide s[2]; int n; int E; };
-// one launch: transposed fp16 copies of the streamed operands (B tiles of the second MMA) + scaled, padded column
-// terms, for every pass
-__global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
+struct PrepArgs { PrepItem s[3]; int n; int E; };
+// one launch: fp16 copies (row-major: operands of the first MMA; transposed: B tiles of the second MMA) and scaled,
+// padded column terms, for every pass
+__global__ void __launch_bounds__(256) sk_prep_kernel(const PrepArgs a) {
     __shared__ float tile[32][33];
     int b = blockIdx.x;
     for (int i = 0; i < a.n; ++i) {
-        const PrepSide& sd = a.s[i];
+        const PrepItem& sd = a.s[i];
         if (b < sd.tblocks) {
             const int r0 = (b % sd.tblocks_x) * 32, c0 = (b / sd.tblocks_x) * 32;
             const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
             for (int k = ty; k < 32; k += 8) {
-                int r = r0 + k, c = c0 + tx;
-                tile[k][tx] = (r < sd.nT && c < a.E) ? sd.T[(int64_t)r * sd.ldt + c] : 0.f;
+                const int r = r0 + k, c = c0 + tx;
+                const float v = (r < sd.n && c < a.E) ? sd.X[(int64_t)r * sd.ld + c] : 0.f;
+                tile[k][tx] = v;
+                if (sd.Xh && r < sd.n && c < a.E) sd.Xh[(int64_t)r * a.E + c] = __float2half_rn(v);
             }
-            __syncthreads();
-            for (int k = ty; k < 32; k += 8) {
-                int c = c0 + k, r = r0 + tx;
-                if (c < a.E && r < sd.nT) sd.Tt[(int64_t)c * sd.ldtt + r] = __float2half_rn(tile[tx][k]);
+            if (sd.Xt) {
+                __syncthreads();
+                for (int k = ty; k < 32; k += 8) {
+                    const int c = c0 + k, r = r0 + tx;
+                    if (c < a.E && r < sd.n) sd.Xt[(int64_t)c * sd.ldtt + r] = __float2half_rn(tile[tx][k]);
+                }
             }
             return;
         }
         b -= sd.tblocks;
         if (b < sd.cblocks) {
             const int j = b * 256 + threadIdx.x;
-            if (j < sd.n_pad) sd.c2[j] = (j < sd.nT && sd.colv) ? sd.colv[j] * kLog2e : 0.f;
+            if (j < sd.n_pad) sd.c2[j] = (j < sd.n && sd.colv) ? sd.colv[j] * kLog2e : 0.f;
             return;
         }
         b -= sd.cblocks;
     }
+}
+static int prep_item(PrepItem& it, const float* X, int ld, int n, int E, __half* Xh, __half* Xt, int ldtt, const float* colv, float* c2, int n_pad) {
+    it.X = X; it.ld = ld; it.n = n; it.Xh = Xh; it.Xt = Xt; it.ldtt = ldtt; it.colv = colv; it.c2 = c2; it.n_pad = n_pad;
+    it.tblocks_x = (int)ceil_div(n, 32);
+    it.tblocks = (Xh || Xt) ? it.tblocks_x * (int)ceil_div(E, 32) : 0;
+    it.cblocks = c2 ? (int)ceil_div(n_pad, 256) : 0;
+    return it.tblocks + it.cblocks;
 }
 
 struct RedSide { const float* part; float* G; int ldg, nR, n_tiles, unit0; };
@@ -311,6 +325,8 @@ static size_t bwd_sk_floats(int n_sides, const int* nR, const int* nT, int E) {
     for (int i = 0; i < n_sides; ++i) {
         f += align_up((size_t)pl.slots[i] * nR[i] * E, 64);          // partial blocks
         f += align_up((size_t)E * sk_ldtt(nT[i]) / 2, 64);           // T^T (fp16)
+        f += align_up((size_t)nT[i] * E / 2, 64);                    // T (fp16 row-major)
+        f += align_up((size_t)nR[i] * E / 2, 64);                    // R (fp16 row-major; shared with the other pass when both run)
         f += align_up((size_t)nt[i] * bn, 64);                       // scaled column term
     }
     return f + 512;
@@ -322,7 +338,8 @@ size_t softmax_tc_workspace(int Bq, int Bc, int E) {
     int mt = (int)ceil_div(Bq, 128), nt = (int)ceil_div(Bc, kFwdBN);
     SkPlan pf = sk_plan(1, &mt, &nt);
     size_t seg = align_up(rows * sizeof(float), 256);
-    size_t fwd = (4 * (size_t)pf.slots[0] + 2) * seg + align_up(((size_t)nt * kFwdBN + 64) * sizeof(float), 256) + 2048;
+    size_t fwd = (2 * kFwdHalves * (size_t)pf.slots[0] + 2) * seg + align_up(((size_t)nt * kFwdBN + 64) * sizeof(float), 256) +
+                 align_up((size_t)Bq * E * 2, 256) + align_up((size_t)Bc * E * 2, 256) + 2048;
     // backward: both passes at once, or one pass alone (tt_inbatch_softmax_bwd_one)
     int nR[2] = {Bq, Bc}, nT[2] = {Bc, Bq};
     size_t both = bwd_sk_floats(2, nR, nT, E) * sizeof(float);
@@ -375,22 +392,36 @@ int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float
     float* rowloss = ws;                                   // (the SIMT path keeps its row losses at the workspace base too)
     float* zd = rowloss + seg;
     float* m2 = zd + seg;
-    float* l = m2 + 2 * (size_t)pl.slots[0] * seg;
-    float* c2 = l + 2 * (size_t)pl.slots[0] * seg;
-    rc = launch_scale_pad(bias, Bc, c2, nt * kFwdBN, st);
-    if (rc) return rc;
+    float* l = m2 + kFwdHalves * (size_t)pl.slots[0] * seg;
+    float* c2 = l + kFwdHalves * (size_t)pl.slots[0] * seg;
+    const bool h16 = E >= 64;                              // fp16 operand tiles (see SkCfg)
+    __half* Qh = reinterpret_cast<__half*>(c2 + align_up((size_t)nt * kFwdBN + 64, 64));
+    __half* Ch = Qh + align_up((size_t)Bq * E, 128);
+    PrepArgs pa{};
+    pa.E = E;
+    int blocks = 0;
+    blocks += prep_item(pa.s[pa.n++], C, ldc, Bc, E, h16 ? Ch : nullptr, nullptr, 0, bias, c2, nt * kFwdBN);
+    if (h16) blocks += prep_item(pa.s[pa.n++], Q, ldq, Bq, E, Qh, nullptr, 0, nullptr, nullptr, 0);
+    sk_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(pa);
+    TT_LAUNCH_OK("sk_prep_kernel");
+    if (h16) {
+        rc = make_tmap_2d_f16(&maps.r[0], Qh, Bq, E, E, 128);
+        if (rc) return rc;
+        rc = make_tmap_2d_f16(&maps.t[0], Ch, Bc, E, E, kFwdBN);
+        if (rc) return rc;
+    }
     SkParams p{};
-    p.n_pass = 1; p.units = pl.units;
+    p.n_pass = 1; p.units = pl.units; p.trace = g_trace;
     SkPass& ps = p.pass[0];
     ps.nR = Bq; ps.nT = Bc; ps.m_tiles = mt; ps.n_tiles = nt; ps.d = off; ps.unit0 = 0; ps.rowv = nullptr; ps.colv2 = c2;
     ps.out0 = m2; ps.out1 = l; ps.out2 = zd;
     switch (E) {
-        case 32: rc = launch_streamk<kFwd, 32, kFwdBN>(maps, p, pl.grid, st, "streamk_kernel<fwd,32>"); break;
-        case 64: rc = launch_streamk<kFwd, 64, kFwdBN>(maps, p, pl.grid, st, "streamk_kernel<fwd,64>"); break;
-        default: rc = launch_streamk<kFwd, 128, kFwdBN>(maps, p, pl.grid, st, "streamk_kernel<fwd,128>"); break;
+        case 32: rc = launch_streamk<kFwd, 32, kFwdBN, false>(maps, p, pl.grid, st, "streamk_kernel<fwd,32>"); break;
+        case 64: rc = launch_streamk<kFwd, 64, kFwdBN, true>(maps, p, pl.grid, st, "streamk_kernel<fwd,64>"); break;
+        default: rc = launch_streamk<kFwd, 128, kFwdBN, true>(maps, p, pl.grid, st, "streamk_kernel<fwd,128>"); break;
     }
     if (rc) return rc;
-    fwd_combine_sk_kernel<<<(unsigned)ceil_div(Bq, 256), 256, 0, st>>>(m2, l, zd, Bq, nt, pl.units, pl.grid, 2 /* kHalves for BN=128 */, lse, rowloss);
+    fwd_combine_sk_kernel<<<(unsigned)ceil_div(Bq, 256), 256, 0, st>>>(m2, l, zd, Bq, nt, pl.units, pl.grid, kFwdHalves, lse, rowloss);
     TT_LAUNCH_OK("fwd_combine_sk_kernel");
     return sum_rows_launch(rowloss, Bq, loss, st);
 }
@@ -404,45 +435,65 @@ int softmax_bwd_sk(const SkSide* sides, int n, int E, float* ws, cudaStream_t st
     SkMaps maps;
     memset(&maps, 0, sizeof(maps));
     SkParams p{};
-    p.n_pass = n; p.units = pl.units;
+    p.n_pass = n; p.units = pl.units; p.trace = g_trace;
     PrepArgs pa{};
-    pa.n = n; pa.E = E;
+    pa.E = E;
     RedArgs ra{};
     ra.n = n; ra.E = E; ra.units = pl.units; ra.grid = pl.grid;
+    const bool h16 = E >= 64;                              // fp16 operand tiles for the first MMA too (see SkCfg)
     float* cur = ws;
     int unit0 = 0, prep_blocks = 0;
     int64_t red_items = 0;
+    __half* Th[2] = {nullptr, nullptr};                    // fp16 row-major copy of each side's streamed operand
+    float* part[2]; __half* Tt[2]; float* c2[2]; int ldtt[2];
     for (int i = 0; i < n; ++i) {
         const SkSide& sd = sides[i];
-        float* part = cur; cur += align_up((size_t)pl.slots[i] * sd.nR * E, 64);
-        __half* Tt = reinterpret_cast<__half*>(cur); const int ldtt = (int)sk_ldtt(sd.nT); cur += align_up((size_t)E * ldtt / 2, 64);
-        float* c2 = cur; cur += align_up((size_t)nt[i] * bn, 64);
-        int rc = make_tmap_2d(&maps.r[i], sd.R, sd.nR, E, sd.ldr, 128);
+        part[i] = cur; cur += align_up((size_t)pl.slots[i] * sd.nR * E, 64);
+        Tt[i] = reinterpret_cast<__half*>(cur); ldtt[i] = (int)sk_ldtt(sd.nT); cur += align_up((size_t)E * ldtt[i] / 2, 64);
+        c2[i] = cur; cur += align_up((size_t)nt[i] * bn, 64);
+        if (h16) { Th[i] = reinterpret_cast<__half*>(cur); cur += align_up((size_t)sd.nT * E / 2, 64); }
+        prep_blocks += prep_item(pa.s[pa.n++], sd.T, sd.ldt, sd.nT, E, Th[i], Tt[i], ldtt[i], sd.colv, c2[i], nt[i] * bn);
+    }
+    // the resident operand of a pass is the streamed operand of the other one; a pass running alone converts its own
+    __half* Rh[2] = {nullptr, nullptr};
+    if (h16) {
+        if (n == 2) { Rh[0] = Th[1]; Rh[1] = Th[0]; }
+        else {
+            Rh[0] = reinterpret_cast<__half*>(cur); cur += align_up((size_t)sides[0].nR * E / 2, 64);
+            prep_blocks += prep_item(pa.s[pa.n++], sides[0].R, sides[0].ldr, sides[0].nR, E, Rh[0], nullptr, 0, nullptr, nullptr, 0);
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        const SkSide& sd = sides[i];
+        int rc;
+        if (h16) {
+            rc = make_tmap_2d_f16(&maps.r[i], Rh[i], sd.nR, E, E, 128);
+            if (rc) return rc;
+            rc = make_tmap_2d_f16(&maps.t[i], Th[i], sd.nT, E, E, bn);
+        } else {
+            rc = make_tmap_2d(&maps.r[i], sd.R, sd.nR, E, sd.ldr, 128);
+            if (rc) return rc;
+            rc = make_tmap_2d(&maps.t[i], sd.T, sd.nT, E, sd.ldt, bn);
+        }
         if (rc) return rc;
-        rc = make_tmap_2d(&maps.t[i], sd.T, sd.nT, E, sd.ldt, bn);
-        if (rc) return rc;
-        rc = make_tmap_2d_f16(&maps.tt[i], Tt, E, sd.nT, ldtt, E);
+        rc = make_tmap_2d_f16(&maps.tt[i], Tt[i], E, sd.nT, ldtt[i], E);
         if (rc) return rc;
         SkPass& ps = p.pass[i];
-        ps.nR = sd.nR; ps.nT = sd.nT; ps.m_tiles = mt[i]; ps.n_tiles = nt[i]; ps.d = sd.d; ps.unit0 = unit0; ps.rowv = sd.rowv; ps.colv2 = c2;
-        ps.out0 = part; ps.out1 = nullptr; ps.out2 = nullptr;
-        PrepSide& pp = pa.s[i];
-        pp.T = sd.T; pp.ldt = sd.ldt; pp.nT = sd.nT; pp.Tt = Tt; pp.ldtt = ldtt; pp.colv = sd.colv; pp.c2 = c2; pp.n_pad = nt[i] * bn;
-        pp.tblocks_x = (int)ceil_div(sd.nT, 32); pp.tblocks = pp.tblocks_x * (int)ceil_div(E, 32); pp.cblocks = (int)ceil_div(pp.n_pad, 256);
-        prep_blocks += pp.tblocks + pp.cblocks;
+        ps.nR = sd.nR; ps.nT = sd.nT; ps.m_tiles = mt[i]; ps.n_tiles = nt[i]; ps.d = sd.d; ps.unit0 = unit0; ps.rowv = sd.rowv; ps.colv2 = c2[i];
+        ps.out0 = part[i]; ps.out1 = nullptr; ps.out2 = nullptr;
         RedSide& rs = ra.s[i];
-        rs.part = part; rs.G = sd.G; rs.ldg = sd.ldg; rs.nR = sd.nR; rs.n_tiles = nt[i]; rs.unit0 = unit0;
+        rs.part = part[i]; rs.G = sd.G; rs.ldg = sd.ldg; rs.nR = sd.nR; rs.n_tiles = nt[i]; rs.unit0 = unit0;
         red_items += (int64_t)sd.nR * (E / 4);
         unit0 += mt[i] * nt[i];
     }
     if (pl.units == 0) return TT_OK;
-    bwd_prep_kernel<<<(unsigned)prep_blocks, 256, 0, st>>>(pa);
-    TT_LAUNCH_OK("bwd_prep_kernel");
+    sk_prep_kernel<<<(unsigned)prep_blocks, 256, 0, st>>>(pa);
+    TT_LAUNCH_OK("sk_prep_kernel");
     int rc;
     switch (E) {
-        case 32: rc = launch_streamk<kBwd, 32, 128>(maps, p, pl.grid, st, "streamk_kernel<bwd,32>"); break;
-        case 64: rc = launch_streamk<kBwd, 64, 128>(maps, p, pl.grid, st, "streamk_kernel<bwd,64>"); break;
-        default: rc = launch_streamk<kBwd, 128, 64>(maps, p, pl.grid, st, "streamk_kernel<bwd,128>"); break;
+        case 32: rc = launch_streamk<kBwd, 32, 128, false>(maps, p, pl.grid, st, "streamk_kernel<bwd,32>"); break;
+        case 64: rc = launch_streamk<kBwd, 64, 128, true>(maps, p, pl.grid, st, "streamk_kernel<bwd,64>"); break;
+        default: rc = launch_streamk<kBwd, 128, 64, true>(maps, p, pl.grid, st, "streamk_kernel<bwd,128>"); break;
     }
     if (rc) return rc;
     bwd_reduce_sk_kernel<<<(unsigned)ceil_div(red_items, 256), 256, 0, st>>>(ra);
@@ -500,16 +551,16 @@ int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const 
 }
 
 int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, float* Z, int ldz, cudaStream_t st) {
-    Plan pl = plan_for(Bq, Bc, kFwdBN);
+    Plan pl = plan_for(Bq, Bc, kLogitsBN);
     CUtensorMap tmQ, tmC;
     int rc = make_tmap_2d(&tmQ, Q, Bq, E, ldq, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmC, C, Bc, E, ldc, kFwdBN);
+    rc = make_tmap_2d(&tmC, C, Bc, E, ldc, kLogitsBN);
     if (rc) return rc;
     // test / API-convenience path: the scaled column term lives in a lazily grown static buffer
     static float* c2 = nullptr;
     static size_t c2_cap = 0;
-    size_t need = (size_t)pl.n_tiles * kFwdBN;
+    size_t need = (size_t)pl.n_tiles * kLogitsBN;
     if (need > c2_cap) {
         if (c2) cudaFree(c2);
         TT_CUDA_OK(cudaMalloc(&c2, need * sizeof(float)));
@@ -521,9 +572,9 @@ int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bia
     p.nR = Bq; p.nT = Bc; p.n_tiles = pl.n_tiles; p.tiles_per_split = pl.tps; p.colv2 = c2; p.out0 = Z; p.ld_out = ldz;
     p.d = -(1 << 30);
     switch (E) {
-        case 32: return launch_rowpanel<kLogits, 32, kFwdBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<logits,32>");
-        case 64: return launch_rowpanel<kLogits, 64, kFwdBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<logits,64>");
-        default: return launch_rowpanel<kLogits, 128, kFwdBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<logits,128>");
+        case 32: return launch_rowpanel<kLogits, 32, kLogitsBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<logits,32>");
+        case 64: return launch_rowpanel<kLogits, 64, kLogitsBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<logits,64>");
+        default: return launch_rowpanel<kLogits, 128, kLogitsBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<logits,128>");
     }
 }
 

@@ -18,6 +18,11 @@
 #pragma once
 #include "tt_tc_rowpanel.cuh"
 
+#define SK_TRACE(it, ev)                                                                                         \
+    do {                                                                                                     \
+        if (p.trace && (it) < 64) p.trace[((size_t)blockIdx.x * 64 + (it)) * 4 + (ev)] = gtime();             \
+    } while (0)
+
 namespace tt {
 namespace tc {
 
@@ -36,6 +41,7 @@ struct SkParams {
     SkPass pass[2];
     int n_pass;
     int units;           // work units of all passes
+    unsigned long long* trace;   // optional debug timeline [cta][64 units][4]: TMA issued, MMA issued, S seen by the epilogue, S released
 };
 struct SkMaps {
     CUtensorMap r[2], t[2], tt[2];   // per pass: R panels (box 128 rows), T tiles (box BN rows), T^T tiles (box E rows)
@@ -61,11 +67,17 @@ struct SkCursor {   // position in the unit list
     }
 };
 
-template <int MODE, int E, int BN>
+// H: the first MMA's operands are fp16 (kind::f16) instead of TF32-rounded fp32 (kind::tf32).  A TF32-rounded value inside
+// fp16's normal range [2^-14, 65504] converts exactly, so the logits are the same; the operand tiles are half the size, and the
+// kernels are bound by streaming those tiles from L2 (E >= 64 only: a 128-byte swizzle span holds 64 fp16).
+template <int MODE, int E, int BN, bool H>
 struct SkCfg {
-    static constexpr int kSlabs = E / 32;                               // 128-byte K slabs per fp32/TF32 operand row
-    static constexpr int kRBytes = kSlabs * 128 * 128;                  // R panel (TF32, K-major over E)
-    static constexpr int kT1Bytes = kSlabs * BN * 128;                  // T tile (TF32, K-major over E): first MMA
+    static constexpr int kSlabCols = H ? 64 : 32;                       // columns per 128-byte K slab of an operand row
+    static constexpr int kSlabs = E / kSlabCols;
+    static constexpr int kRBytes = kSlabs * 128 * 128;                  // R panel (K-major over E)
+    static constexpr int kT1Bytes = kSlabs * BN * 128;                  // T tile (K-major over E): first MMA
+    static constexpr int kMma1 = H ? E / 16 : E / 8;                    // first-MMA instructions per tile (32 bytes of K each)
+    static_assert(!H || E >= 64, "fp16 operands need E >= 64");
     static constexpr int kT2Bytes = (MODE == kBwd) ? (BN / 64) * E * 128 : 0;     // T^T tile (fp16, K-major over BN): second MMA
     static constexpr int kTBytes = kT1Bytes + kT2Bytes;
     static constexpr int kPBytes = (MODE == kBwd) ? (BN / 64) * 128 * 128 : 0;    // P tile (fp16, K-major over BN)
@@ -73,12 +85,17 @@ struct SkCfg {
     static constexpr int kC2Bytes = BN * 4;
     static constexpr int kFixed = kRBytes + kPBufs * kPBytes + 4 * 1024 /*c2 stages*/ + 1024 /*barriers*/ + 1024 /*align*/;
     static constexpr int kFit = (232448 - kFixed) / kTBytes;
-    static constexpr int kStages = kFit >= 4 ? 4 : kFit;                // T ring depth
+    static constexpr int kStages = kFit >= 8 ? 8 : kFit;                // T ring depth (TMA latency under load is several unit times)
+    static constexpr int kC2Slots = 4096 / kC2Bytes >= 8 ? 8 : 4096 / kC2Bytes;   // ring of staged column terms (its own barriers)
     static constexpr int kSmemBytes = kFixed + kStages * kTBytes;
-    static constexpr int kHalves = (BN / 32 >= 2) ? 2 : 1;              // epilogue warps per TMEM lane quarter
+    // epilogue warps per TMEM lane quarter: the forward runs 4 (one 32-column chunk each per tile: 4 warps per scheduler hide the
+    // dependent FMNMX / MUFU / FADD latencies better than 2 warps with two chunks each)
+    static constexpr int kHalves = (BN / 32 >= 4) ? 4 : ((BN / 32 >= 2) ? 2 : 1);
     static constexpr int kEpiWarps = 4 * kHalves;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
-    static constexpr int kTmemNeed = (MODE == kBwd) ? 2 * BN + 2 * E : 2 * BN;
+    // S accumulators in flight: the MMA -> epilogue -> MMA hand-over latency is amortised over kAcc units
+    static constexpr int kAcc = (MODE == kFwd) ? (4 * BN <= 512 ? 4 : 2) : ((3 * BN + 2 * E <= 512) ? 3 : 2);
+    static constexpr int kTmemNeed = (MODE == kBwd) ? kAcc * BN + 2 * E : kAcc * BN;
     static constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512);
     static_assert(kStages >= 2, "shared memory budget");
     static_assert(kTmemNeed <= 512, "TMEM budget");
@@ -108,6 +125,97 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {   // round-
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2: two lanes of the FMA pipe per issue slot) --------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// forward epilogue body for a chunk that is fully in range and off the diagonal: works on the NEGATED logits
+// zn = colv2 - s*log2e (one FFMA2 per two columns), running minimum with FMNMX3, 2^(min - zn) with one FFMA2 + two MUFU,
+// packed accumulation.  ~115 instructions per 32 columns against ~200 for the scalar form.
+__device__ __forceinline__ void fwd_chunk_packed(const uint32_t (&r)[32], uint32_t c2s, float& m2, float& l) {
+    f32x2 zn[16];
+    const f32x2 nl2e = pk2(-kLog2e, -kLog2e);
+#pragma unroll
+    for (int g4 = 0; g4 < 8; ++g4) {
+        const float4 cc = lds128(c2s + g4 * 16);
+        zn[2 * g4] = fma2(pk2(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1])), nl2e, pk2(cc.x, cc.y));
+        zn[2 * g4 + 1] = fma2(pk2(__uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])), nl2e, pk2(cc.z, cc.w));
+    }
+    float a0, a1, b0, b1;
+    upk2(zn[0], a0, a1);
+    upk2(zn[1], b0, b1);
+    float mn0 = fminf(a0, a1), mn1 = fminf(b0, b1);
+#pragma unroll
+    for (int i = 2; i < 16; i += 2) {
+        upk2(zn[i], a0, a1);
+        upk2(zn[i + 1], b0, b1);
+        mn0 = fmin3(mn0, a0, a1);
+        mn1 = fmin3(mn1, b0, b1);
+    }
+    const float mneg = fminf(-m2, fminf(mn0, mn1));   // minus the new running maximum
+    const f32x2 mone = pk2(-1.f, -1.f), mm = pk2(mneg, mneg);
+    f32x2 s0 = pk2(0.f, 0.f), s1 = s0;
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        upk2(fma2(zn[i], mone, mm), a0, a1);           // mneg - zn = z - max  (<= 0)
+        upk2(fma2(zn[i + 1], mone, mm), b0, b1);
+#if defined(TT_EXPERIMENT) && TT_EXPERIMENT == 1
+        s0 = add2(s0, pk2(a0, a1));
+        s1 = add2(s1, pk2(b0, b1));
+#else
+        s0 = add2(s0, pk2(ex2_approx(a0), ex2_approx(a1)));
+        s1 = add2(s1, pk2(ex2_approx(b0), ex2_approx(b1)));
+#endif
+    }
+    upk2(add2(s0, s1), a0, a1);
+    l = l * ex2_approx(m2 + mneg) + (a0 + a1);        // m2 - max_new; m2 = -inf gives 0
+    m2 = -mneg;
+}
+
+// backward epilogue body, fast path (chunk fully in range, off the diagonal): P = 2^(s*log2e - r2 - c2_j) as fp16.
+// One FFMA2 per two columns (r2 is folded into the addend), two MUFU, one F2FP pack; 4 x STS.128 per 32 columns.
+__device__ __forceinline__ void bwd_chunk_packed(const uint32_t (&r)[32], uint32_t c2s, int row_l, float r2, uint32_t prow, int half_of_slab) {
+    const f32x2 l2e = pk2(kLog2e, kLog2e), mone = pk2(-1.f, -1.f), nr2 = pk2(-r2, -r2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {            // 16-byte pieces of 8 columns
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float4 cc = lds128(c2s + (j * 2 + h) * 16);
+            const int i = j * 8 + h * 4;
+            // t = s*log2e - (c2 + r2):  addend = c2*(-1) + (-r2), then fma(s, log2e, addend)
+            const f32x2 ad0 = fma2(pk2(cc.x, cc.y), mone, nr2), ad1 = fma2(pk2(cc.z, cc.w), mone, nr2);
+            float a0, a1, b0, b1;
+            upk2(fma2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), l2e, ad0), a0, a1);
+            upk2(fma2(pk2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), l2e, ad1), b0, b1);
+            w[h * 2] = pack_f16x2(ex2_approx(a0), ex2_approx(a1));
+            w[h * 2 + 1] = pack_f16x2(ex2_approx(b0), ex2_approx(b1));
+        }
+        const uint32_t piece = static_cast<uint32_t>(half_of_slab * 4 + j);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((piece ^ (row_l & 7)) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+    }
 }
 
 // backward epilogue body: 32 columns of one row -> P = 2^(z - r2) - [diag] as fp16 into the swizzled A tile of the second MMA
@@ -142,18 +250,19 @@ __device__ __forceinline__ void bwd_chunk_h(const uint32_t (&r)[32], uint32_t c2
 
 struct SkBars {
     uint64_t r_full, r_empty;
-    uint64_t t_full[4], t_empty[4];
-    uint64_t s_full[2], s_empty[2];
+    uint64_t t_full[8], t_empty[8];
+    uint64_t c_full[8], c_empty[8];
+    uint64_t s_full[4], s_empty[4];
     uint64_t p_full[2], p_empty[2];
     uint64_t g_full[2], g_empty[2];
     uint32_t tmem_base;
 };
 
-template <int MODE, int E, int BN>
-__global__ void __launch_bounds__(SkCfg<MODE, E, BN>::kThreads, 1)
+template <int MODE, int E, int BN, bool H>
+__global__ void __launch_bounds__(SkCfg<MODE, E, BN, H>::kThreads, 1)
 streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkParams p) {
-    using Cfg = SkCfg<MODE, E, BN>;
-    using Sk = SkCfg<MODE, E, BN>;
+    using Cfg = SkCfg<MODE, E, BN, H>;
+    using Sk = SkCfg<MODE, E, BN, H>;
     const int u_begin = sk_begin(blockIdx.x, p.units, gridDim.x), u_end = sk_begin(blockIdx.x + 1, p.units, gridDim.x);
     const int my_units = u_end - u_begin;
     if (my_units <= 0) return;   // (uniform) more CTAs than work units
@@ -163,11 +272,15 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
     unsigned char* sR = smem;
     unsigned char* sT = sR + Cfg::kRBytes;
     unsigned char* sP = sT + Cfg::kStages * Cfg::kTBytes;
-    unsigned char* sC2 = sP + Cfg::kPBufs * Cfg::kPBytes;       // kStages x 1 KB
+    unsigned char* sC2 = sP + Cfg::kPBufs * Cfg::kPBytes;       // kC2Slots x kC2Bytes (4 KB)
     SkBars* bars = reinterpret_cast<SkBars*>(sC2 + 4 * 1024);
 
+    // roles: warps 0..kEpiWarps-1 epilogue, then the TMA producer, then the MMA issuer.  The two single-lane warps get the
+    // HIGHEST warp ids: the scheduler arbitrates highest-id-first, and behind 4 always-eligible epilogue warps per scheduler a
+    // low-id MMA warp was issuing one unit per ~0.9 us (measured) although every barrier it waits on had long completed.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0 && lane == 0) {
+    constexpr int kProducerWarp = Cfg::kEpiWarps, kMmaWarp = Cfg::kEpiWarps + 1;
+    if (warp == kProducerWarp && lane == 0) {
         for (int i = 0; i < 2; ++i) {
             if (i < p.n_pass) {
                 prefetch_tmap(&maps.r[i]);
@@ -177,21 +290,24 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
         }
         mbar_init(&bars->r_full, 1);
         mbar_init(&bars->r_empty, 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], MODE == kBwd ? 1 : 1 + Cfg::kEpiWarps); }
+        for (int i = 0; i < 8; ++i) {
+            mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 1);
+            mbar_init(&bars->c_full[i], 1); mbar_init(&bars->c_empty[i], Cfg::kEpiWarps);
+        }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], Cfg::kEpiWarps); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], Cfg::kEpiWarps);
             mbar_init(&bars->p_full[i], Cfg::kEpiWarps); mbar_init(&bars->p_empty[i], 1);
             mbar_init(&bars->g_full[i], 1); mbar_init(&bars->g_empty[i], Cfg::kEpiWarps);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, Sk::kTmemCols);
+    if (warp == kMmaWarp) tmem_alloc(&bars->tmem_base, Sk::kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    if (warp == 0) {
+    if (warp == kProducerWarp) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             SkCursor c;
@@ -202,26 +318,30 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
                 if (it == 0 || c.tile == 0) {   // a new panel: R may be overwritten once the last MMA reading it has completed
                     mbar_wait(&bars->r_empty, (k & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->r_full, Cfg::kRBytes);
-                    for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(sR + s * 128 * 128, &maps.r[c.pass], &bars->r_full, s * 32, c.panel * 128);
+                    for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(sR + s * 128 * 128, &maps.r[c.pass], &bars->r_full, s * Cfg::kSlabCols, c.panel * 128);
                     ++k;
                 }
                 const int stage = it % Cfg::kStages;
                 const uint32_t ph = (it / Cfg::kStages) & 1;
                 const int n0 = c.tile * BN;
+                const int cs = it % Cfg::kC2Slots;
+                mbar_wait(&bars->c_empty[cs], ((it / Cfg::kC2Slots) & 1) ^ 1);
+                mbar_arrive_expect_tx(&bars->c_full[cs], Cfg::kC2Bytes);
+                bulk_copy_1d(sC2 + cs * Cfg::kC2Bytes, ps.colv2 + n0, Cfg::kC2Bytes, &bars->c_full[cs]);
                 mbar_wait(&bars->t_empty[stage], ph ^ 1);
-                mbar_arrive_expect_tx(&bars->t_full[stage], Cfg::kTBytes + Cfg::kC2Bytes);
+                mbar_arrive_expect_tx(&bars->t_full[stage], Cfg::kTBytes);
                 unsigned char* dst = sT + stage * Cfg::kTBytes;
-                for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(dst + s * BN * 128, &maps.t[c.pass], &bars->t_full[stage], s * 32, n0);
+                for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(dst + s * BN * 128, &maps.t[c.pass], &bars->t_full[stage], s * Cfg::kSlabCols, n0);
                 if (MODE == kBwd) {
                     for (int s = 0; s < BN / 64; ++s)   // fp16 T^T: boxes of 64 columns (128 bytes) x E rows
                         tma_load_2d(dst + Cfg::kT1Bytes + s * E * 128, &maps.tt[c.pass], &bars->t_full[stage], n0 + s * 64, 0);
                 }
-                bulk_copy_1d(sC2 + stage * 1024, ps.colv2 + n0, Cfg::kC2Bytes, &bars->t_full[stage]);
+                SK_TRACE(it, 0);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc1 = make_idesc_tf32(128, BN, false, false);
+        constexpr uint32_t idesc1 = H ? make_idesc_f16(128, BN) : make_idesc_tf32(128, BN, false, false);
         constexpr uint32_t idesc2 = make_idesc_f16(128, E);
         const uint32_t sR_a = smem_u32(sR), sT_a = smem_u32(sT), sP_a = smem_u32(sP);
         SkCursor c1;   // unit whose first MMA is issued next
@@ -236,23 +356,25 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
             }
             const int stage = it % Cfg::kStages;
             const uint32_t tph = (it / Cfg::kStages) & 1;
-            const int acc = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
+            const int acc = it % Cfg::kAcc;
+            const uint32_t aph = (it / Cfg::kAcc) & 1;
             mbar_wait(&bars->t_full[stage], tph);
             mbar_wait(&bars->s_empty[acc], aph ^ 1);
             tc_fence_after();
             if (lane == 0) {
 #pragma unroll
-                for (int k = 0; k < E / 8; ++k) {
+                for (int k = 0; k < Cfg::kMma1; ++k) {
                     const uint32_t off = (k >> 2) * 128 * 128 + (k & 3) * 32;
                     const uint32_t offT = (k >> 2) * BN * 128 + (k & 3) * 32;
                     uint64_t ad = make_smem_desc(sR_a + off, 16, 1024);
                     uint64_t bd = make_smem_desc(sT_a + stage * Cfg::kTBytes + offT, 16, 1024);
-                    mma_tf32(tmem + acc * BN, ad, bd, idesc1, k > 0 ? 1u : 0u);
+                    if (H) mma_f16(tmem + acc * BN, ad, bd, idesc1, k > 0 ? 1u : 0u);
+                    else mma_tf32(tmem + acc * BN, ad, bd, idesc1, k > 0 ? 1u : 0u);
                 }
-                if (MODE != kBwd) mma_commit(&bars->t_empty[stage]);   // T tile consumed (the epilogue releases the staged column term)
+                if (MODE != kBwd) mma_commit(&bars->t_empty[stage]);   // T tile consumed
                 mma_commit(&bars->s_full[acc]);
                 if (panel_end) mma_commit(&bars->r_empty);             // the last MMA that reads this R panel
+                SK_TRACE(it, 1);
             }
             __syncwarp();
             c1.next(p);
@@ -283,9 +405,9 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
                     for (int kk = 0; kk < BN / 16; ++kk) {   // fp16: 16 columns (32 bytes) per MMA, 64 per swizzle slab
                         uint64_t ad = make_smem_desc(sP_a + pb * Cfg::kPBytes + (kk >> 2) * 128 * 128 + (kk & 3) * 32, 16, 1024);
                         uint64_t bd = make_smem_desc(sT_a + stage * Cfg::kTBytes + Cfg::kT1Bytes + (kk >> 2) * E * 128 + (kk & 3) * 32, 16, 1024);
-                        mma_f16(tmem + 2 * BN + gb * E, ad, bd, idesc2, (!panel_start || kk > 0) ? 1u : 0u);
+                        mma_f16(tmem + Cfg::kAcc * BN + gb * E, ad, bd, idesc2, (!panel_start || kk > 0) ? 1u : 0u);
                     }
-                    mma_commit(&bars->t_empty[stage]);  // T, T^T and c2 of this stage are all consumed by now
+                    mma_commit(&bars->t_empty[stage]);  // T and T^T of this stage are consumed by now
                     mma_commit(&bars->p_empty[pb]);
                     if (panel_end) mma_commit(&bars->g_full[gb]);
                 }
@@ -293,9 +415,9 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
             }
         }
     } else {
-        // ===================== epilogue warps (2..) =====================
+        // ===================== epilogue warps (0 .. kEpiWarps-1) =====================
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;             // which share of each tile's columns this warp handles
+        const int half = warp >> 2;                   // which share of each tile's columns this warp handles
         const int row_l = q * 32 + lane;              // row within the panel == TMEM lane
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         constexpr int NC = BN / 32;
@@ -319,8 +441,8 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
                 if (MODE == kBwd) r2 = (row < ps.nR && ps.rowv) ? __ldg(ps.rowv + row) * kLog2e : 0.f;
             }
             const int wrow0 = c.panel * 128 + q * 32;     // first row of this warp
-            const int acc = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
+            const int acc = it % Cfg::kAcc;
+            const uint32_t aph = (it / Cfg::kAcc) & 1;
             const int stage = it % Cfg::kStages;
             const int n0 = c.tile * BN;
             const int pb = it & 1;
@@ -328,9 +450,11 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
             const bool fast = (n0 + BN <= ps.nT) && (wrow0 + 32 <= ps.nR) && (wrow0 + ps.d + 32 <= n0 || wrow0 + ps.d >= n0 + BN);
             mbar_wait(&bars->s_full[acc], aph);
             tc_fence_after();
-            mbar_wait(&bars->t_full[stage], (it / Cfg::kStages) & 1);   // completed long ago; acquires the staged column term
+            if (threadIdx.x == 0) SK_TRACE(it, 2);
+            const int cs = it % Cfg::kC2Slots;
+            mbar_wait(&bars->c_full[cs], (it / Cfg::kC2Slots) & 1);     // the staged column term (landed long ago)
             if (MODE == kBwd) mbar_wait(&bars->p_empty[pb], ((it >> 1) & 1) ^ 1);
-            const uint32_t c2s = smem_u32(sC2 + stage * 1024);
+            const uint32_t c2s = smem_u32(sC2 + cs * Cfg::kC2Bytes);
             uint32_t rbuf[2][32];
             tmem_ld_32x32_issue(tmem + lane_addr + acc * BN + c_first * 32, rbuf[0]);
 #pragma unroll
@@ -341,11 +465,15 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
                 uint32_t(&r)[32] = rbuf[cl & 1];
                 const int nb = n0 + cc * 32;
                 if constexpr (MODE == kFwd) {
-                    if (fast) fwd_chunk<true>(r, c2s + cc * 128, nb, row, ps.nT, ps.d, m2, l, zd, has_diag);
+#if defined(TT_EXPERIMENT) && TT_EXPERIMENT == 2
+                    if (fast) { l += __uint_as_float(r[0]) + __uint_as_float(r[31]); }
+#else
+                    if (fast) fwd_chunk_packed(r, c2s + cc * 128, m2, l);
+#endif
                     else fwd_chunk<false>(r, c2s + cc * 128, nb, row, ps.nT, ps.d, m2, l, zd, has_diag);
                 } else {
                     const uint32_t prow = smem_u32(sP + pb * Cfg::kPBytes + (cc >> 1) * 128 * 128 + row_l * 128);
-                    if (fast) bwd_chunk_h<true>(r, c2s + cc * 128, nb, row, row_l, ps.nT, ps.nR, ps.d, r2, prow, cc & 1);
+                    if (fast) bwd_chunk_packed(r, c2s + cc * 128, row_l, r2, prow, cc & 1);
                     else bwd_chunk_h<false>(r, c2s + cc * 128, nb, row, row_l, ps.nT, ps.nR, ps.d, r2, prow, cc & 1);
                 }
             }
@@ -354,8 +482,9 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&bars->s_empty[acc]);
-                if (MODE != kBwd) mbar_arrive(&bars->t_empty[stage]);   // c2 of this stage consumed
+                mbar_arrive(&bars->c_empty[cs]);                        // staged column term consumed
             }
+            if (threadIdx.x == 0) SK_TRACE(it, 3);
             if constexpr (MODE == kBwd) {
                 fence_proxy_async_smem();   // P stores (generic proxy) -> visible to the tensor core (async proxy)
                 __syncwarp();
@@ -376,7 +505,7 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
 #pragma unroll
                     for (int cg = half; cg < E / 32; cg += Cfg::kHalves) {
                         float v[32];
-                        tmem_ld_32x32(tmem + lane_addr + 2 * BN + gb * E + cg * 32, v);
+                        tmem_ld_32x32(tmem + lane_addr + Cfg::kAcc * BN + gb * E + cg * 32, v);
                         if (row < ps.nR) {
                             float4* dst = reinterpret_cast<float4*>(ps.out0 + ((int64_t)slot * ps.nR + row) * E + cg * 32);
 #pragma unroll
@@ -391,7 +520,7 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
         }
     }
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem, Sk::kTmemCols);
     }

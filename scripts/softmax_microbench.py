@@ -57,34 +57,23 @@ def main():
     for cap in (1, 2, 4, 8, 16):
         lib.tt_debug_tc(None, cap)
         print(f"  max_splits={cap:2d}: fwd {time_ms(fwd):8.3f} ms   bwd(2 passes) {time_ms(bwd):8.3f} ms")
-    # timeline with splits capped at 2
-    cap = 2
-    nct = ((B + 127) // 128) * cap
-    trace = torch.zeros(nct * 16, dtype=torch.int64, device="cuda")
-    lib.tt_debug_tc(trace.data_ptr(), cap)
-    fwd()
-    torch.cuda.synchronize()
-    t = trace.cpu().numpy().reshape(nct, 16)
-    lib.tt_debug_tc(None, 0)
-    t0 = t[:, 0].min()
-    names = ["entry", "setup", "mma:R", "s_full0", "epi0", "s_full1", "epi1", "s_full2", "epi2", "s_full3", "epi3", "s_full4", "epi4", "s_full5", "epi5", "exit"]
-    print("fwd timeline (us since first CTA entry), first 3 CTAs and the last:")
-    for cta in (0, 1, 2, nct - 1):
-        print(f"  cta {cta:4d}: " + " ".join(f"{n}={(t[cta, i] - t0) / 1e3:.1f}" for i, n in enumerate(names) if t[cta, i]))
-    dur = (t[:, 15] - t[:, 0]) / 1e3
-    print(f"  CTA lifetime us: min {dur.min():.1f} median {np.median(dur):.1f} max {dur.max():.1f}; kernel span {(t[:, 15].max() - t0) / 1e3:.1f} us")
-    trace.zero_()
-    lib.tt_debug_tc(trace.data_ptr(), cap)
-    bwd()
-    torch.cuda.synchronize()
-    t = trace.cpu().numpy().reshape(nct, 16)
-    lib.tt_debug_tc(None, 0)
-    t0 = t[:, 0].min()
-    print("bwd (second pass) timeline:")
-    for cta in (0, 1, nct - 1):
-        print(f"  cta {cta:4d}: " + " ".join(f"{n}={(t[cta, i] - t0) / 1e3:.1f}" for i, n in enumerate(names) if t[cta, i]))
-    dur = (t[:, 15] - t[:, 0]) / 1e3
-    print(f"  CTA lifetime us: min {dur.min():.1f} median {np.median(dur):.1f} max {dur.max():.1f}; kernel span {(t[:, 15].max() - t0) / 1e3:.1f} us")
+    # stream-K timeline: [cta][64 units][4] = TMA issued, first MMA issued, S seen by an epilogue warp, S released
+    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+        trace = torch.zeros(148 * 64 * 4, dtype=torch.int64, device="cuda")
+        lib.tt_debug_tc(trace.data_ptr(), 0)
+        fn()
+        torch.cuda.synchronize()
+        lib.tt_debug_tc(None, 0)
+        t = trace.cpu().numpy().reshape(148, 64, 4)
+        for cta in (0, 73):
+            tt = t[cta]
+            n = int((tt[:, 3] > 0).sum())
+            if n == 0:
+                continue
+            t0 = tt[0, 0]
+            print(f"{name} cta {cta}: {n} traced units; us since the first TMA issue: unit: tma mma s_seen s_released")
+            for u in list(range(min(n, 14))) + ([n - 1] if n > 14 else []):
+                print(f"    {u:3d}: " + " ".join(f"{(tt[u, e] - t0) / 1e3:7.2f}" for e in range(4)))
 
 
 if __name__ == "__main__":
