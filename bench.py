@@ -304,7 +304,7 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if model._tc_ok() and model.impl != N.TT_IMPL_SIMT else "f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32/fp16 operands, fp32 accumulate" if model._tc_ok() and model.impl != N.TT_IMPL_SIMT else "f32",
         "data": "synthetic",
         "config": {"workload": "c2: H&M-shaped two-tower (1.37M customers, 105k articles), id emb + joint dim 64, side features age/product_type/colour, "
                                f"batch {B}/GPU, logQ in-batch softmax, Adagrad lr 0.05",
@@ -365,15 +365,20 @@ def softmax_roofline(model, B, pk, lib):
     sec = ev0.elapsed_time(ev1) * 1e-3 / n
     flops = 6.0 * B * B * e
     achieved = flops / sec / 1e12
-    return {"bound": "tensor", "kernel": "in-batch softmax fwd+bwd (%s)" % ("tcgen05 tf32" if use_tc else "fp32 CUDA cores"),
+    return {"bound": "tensor", "kernel": "in-batch softmax fwd+bwd (%s)" % ("tcgen05, fp16 operand tiles" if use_tc else "fp32 CUDA cores"),
             "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_burst"], "traffic": None,
             "ms": sec * 1e3, "algorithmic_flop": flops, "peak_source": pk["source"] + ", dense bf16 burst (kernel timed alone)"}
 
 
 def index_bench(model, pk, lib, steps, world=1):
     """Index half of the metric: N=105 542 candidate-tower outputs, E=64, top-100, 2048 queries per batch.
-    With N > 1 ranks the corpus is sharded row-wise and per-shard top-K lists are all-gathered and merged."""
+    N > 1 ranks, two sharding modes:
+      * headline `value`: the 27 MB corpus is replicated and the QUERIES are sharded (every rank answers its own
+        2048-query batches; no exchange on the data path) -- the natural layout when the corpus fits one GPU;
+      * `row_sharded`: the corpus is split row-wise, every rank scores all queries against its shard, the per-shard
+        top-K lists are all-gathered over NCCL and merged on the device (the layout the 10M / 100M-row configs need)."""
     import torch
+    import torch.distributed as dist
 
     from pkg import _native as N
     from pkg.modelling.indices.brute_force import BruteForceIndex
@@ -385,52 +390,82 @@ def index_bench(model, pk, lib, steps, world=1):
         a = art[lo:lo + 10000]
         x = {"article_id": a.reshape(-1, 1), "product_type_name": (a % V_PTYPE + 1).reshape(-1, 1), "colour_group_name": (a % V_COLOUR + 1).reshape(-1, 1)}
         pairs.append((a, model.candidate_tower(x)))
-    index = make_sharded_index(INDEX_K, model.query_tower, pairs) if world > 1 else BruteForceIndex(INDEX_K, model.query_tower, pairs)
-    index.impl = model.impl
-    rng = np.random.default_rng(77)
+    rank = int(os.environ.get("RANK", "0"))
+    rng = np.random.default_rng(77 + rank)
     pool = 4
     hq = [{"age": rng.random((INDEX_BQ, 1)).astype(np.float32), "customer_id": rng.integers(1, V_CUSTOMERS + 1, size=(INDEX_BQ, 1)).astype(np.int32)}
           for _ in range(pool)]
     dq = [{k: torch.from_numpy(v).cuda() for k, v in h.items()} for h in hq]
     pq = [{k: torch.from_numpy(v).pin_memory() for k, v in h.items()} for h in hq]
     n = max(steps, 5)
-    c0 = lib.tt_launch_count()
-    for i in range(3):
-        index.query_indices(dq[i % pool])
-    torch.cuda.synchronize()
-    per_call = int((lib.tt_launch_count() - c0) // 3)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(n):
-        index.query_indices(dq[i % pool])
-    ev1.record()
-    torch.cuda.synchronize()
-    sec = ev0.elapsed_time(ev1) * 1e-3 / n
-    # scoring + selection alone (embeddings resident): the dominant kernel group of the index path
-    qe = index._embed_queries(dq[0])
-    for _ in range(2):
-        index.search(qe)
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(n):
-        index.search(qe)
-    ev1.record()
-    torch.cuda.synchronize()
-    ksec = ev0.elapsed_time(ev1) * 1e-3 / n
-    t0 = time.perf_counter()
-    for i in range(n):
-        ids = index(pq[i % pool])          # host ids in, (Bq, K) identifiers out on the host
-    e2e_sec = (time.perf_counter() - t0) / n
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def measure(index):
+        c0 = lib.tt_launch_count()
+        for i in range(3):
+            index.query_indices(dq[i % pool])
+        torch.cuda.synchronize()
+        per_call = int((lib.tt_launch_count() - c0) // 3)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        for i in range(n):
+            index.query_indices(dq[i % pool])
+        ev1.record()
+        sync_all()
+        sec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3 / n)
+        # scoring + selection alone (embeddings resident): the dominant kernel group of the index path
+        qe = index._embed_queries(dq[0])
+        for _ in range(2):
+            index.search(qe)
+        sync_all()
+        ev0.record()
+        for _ in range(n):
+            index.search(qe)
+        ev1.record()
+        sync_all()
+        ksec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3 / n)
+        for i in range(3):                     # warm-up of the host-facing path (pinned result buffer, lazy kernel loads)
+            index(pq[i % pool])
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(n):
+            ids = index(pq[i % pool])          # host ids in, (Bq, K) identifiers out on the host
+        e2e_sec = max_over_ranks((time.perf_counter() - t0) / n)
+        return sec, ksec, e2e_sec, per_call, ids
+
+    replicated = BruteForceIndex(INDEX_K, model.query_tower, pairs)
+    replicated.impl = model.impl
+    sec, ksec, e2e_sec, per_call, ids = measure(replicated)
     flops = 2.0 * INDEX_BQ * V_ARTICLES * JOINT
     ach = flops / ksec / 1e12
-    return {"metric": "index queries/s (top-100, 105k items)", "value": INDEX_BQ / sec, "unit": "queries/s", "ms_per_batch": sec * 1e3,
-            "e2e": {"value": INDEX_BQ / e2e_sec, "unit": "queries/s", "h2d_bytes_per_step": INDEX_BQ * 8, "d2h_bytes_per_step": INDEX_BQ * INDEX_K * 4},
-            "config": f"N={V_ARTICLES} candidate-tower rows, E={JOINT}, K={INDEX_K}, Bq={INDEX_BQ}; corpus 27 MB is L2-resident (stated); "
-                      + (f"row-sharded over {world} GPUs, NCCL all-gather + on-device merge" if world > 1 else "single shard"),
-            "gpu_launches_per_batch": per_call,
-            "roofline": {"bound": "tensor", "kernel": "index scoring + top-K", "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
-                         "frac": ach / pk["tflops_burst"], "traffic": None, "ms": ksec * 1e3, "algorithmic_flop": flops},
-            "sample_ids": [str(x) for x in ids[0, :3]]}
+    out = {"metric": "index queries/s (top-100, 105k items)", "value": world * INDEX_BQ / sec, "unit": "queries/s", "ms_per_batch": sec * 1e3,
+           "e2e": {"value": world * INDEX_BQ / e2e_sec, "unit": "queries/s", "h2d_bytes_per_step": INDEX_BQ * 8, "d2h_bytes_per_step": INDEX_BQ * INDEX_K * 4},
+           "config": f"N={V_ARTICLES} candidate-tower rows, E={JOINT}, K={INDEX_K}, Bq={INDEX_BQ} per GPU; corpus 27 MB is L2-resident (stated); "
+                     + (f"corpus replicated, queries sharded over {world} GPUs (no data-path collective)" if world > 1 else "single shard"),
+           "gpu_launches_per_batch": per_call,
+           "roofline": {"bound": "tensor", "kernel": "index scoring + top-K (per GPU)", "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                        "frac": ach / pk["tflops_burst"], "traffic": None, "ms": ksec * 1e3, "algorithmic_flop": flops},
+           "sample_ids": [str(x) for x in ids[0, :3]]}
+    if world > 1:
+        sharded = make_sharded_index(INDEX_K, model.query_tower, pairs)
+        sharded.impl = model.impl
+        ssec, sksec, se2e, sper, _ = measure(sharded)
+        out["row_sharded"] = {"value": INDEX_BQ / ssec, "unit": "queries/s", "ms_per_batch": ssec * 1e3, "e2e": INDEX_BQ / se2e,
+                              "config": f"corpus row-sharded over {world} GPUs, every rank scores all {INDEX_BQ} queries, NCCL all-gather + on-device merge",
+                              "gpu_launches_per_batch": sper}
+    return out
 
 
 def main():

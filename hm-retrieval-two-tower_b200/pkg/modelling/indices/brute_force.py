@@ -51,6 +51,11 @@ class BruteForceIndex(AbstractKerasModel):
             candidates = candidates[lo:hi]
         self.n_total = n_total
         self._identifiers = identifiers                       # all ids (host), position == global row index
+        # numeric identifiers are also kept on the device: `call` then maps row indices to identifiers there and
+        # copies only the (B, k) result out (through a pinned buffer) instead of gathering on the host
+        self._identifiers_dev = (torch.from_numpy(np.ascontiguousarray(identifiers)).cuda()
+                                 if np.issubdtype(np.asarray(identifiers).dtype, np.integer) else None)
+        self._out_pinned = None
         self._candidates = candidates.contiguous()            # (N_local, E) fp32, non-trainable
         # operand preparation for the tensor-core filter, done once at build time: permuted TF32-rounded copy of
         # the corpus and the row norms (error bound of the filter); the exact fp32 rows stay authoritative
@@ -125,7 +130,15 @@ class BruteForceIndex(AbstractKerasModel):
 
     def call(self, queries, training: bool = False):
         """{query feature: (B,1)} -> (B, k) array of candidate identifiers."""
+        torch = N.require_cuda()
         _, idx = self.query_indices(queries)
+        if self._identifiers_dev is not None:
+            ids_dev = self._identifiers_dev[idx.long().clamp_(min=0)]
+            if self._out_pinned is None or self._out_pinned.shape != ids_dev.shape or self._out_pinned.dtype != ids_dev.dtype:
+                self._out_pinned = torch.empty(ids_dev.shape, dtype=ids_dev.dtype).pin_memory()
+            self._out_pinned.copy_(ids_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return self._out_pinned.numpy().copy()
         return self._identifiers[idx.cpu().numpy()]
 
     def positions_of(self, ids) -> np.ndarray:
