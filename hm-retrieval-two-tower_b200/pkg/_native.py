@@ -42,6 +42,19 @@ SIGNATURES = {
     "tt_debug_tc": (c_int, [c_void_p, c_int]),
     "tt_debug_index_cap": (c_int, [c_int]),
     "tt_debug_index_stages": (c_int, [c_void_p]),
+    # host-side helpers (csrc/tt_host.cu)
+    "tt_vocab_create": (c_void_p, [c_void_p, c_void_p, c_int64]),
+    "tt_vocab_destroy": (None, [c_void_p]),
+    "tt_vocab_size": (c_int64, [c_void_p]),
+    "tt_vocab_lookup": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int]),
+    "tt_vocab_lookup_fixed": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int]),
+    "tt_crc32c": (ctypes.c_uint32, [c_void_p, c_size_t]),
+    "tt_crc32c_portable": (ctypes.c_uint32, [c_void_p, c_size_t]),
+    "tt_crc32c_masked": (ctypes.c_uint32, [c_void_p, c_size_t]),
+    "tt_tfrecord_scan": (c_int64, [c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int64]),
+    "tt_tfrecord_frame": (c_int, [c_void_p, ctypes.c_uint64, c_void_p]),
+    "tt_example_parse": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, ctypes.POINTER(ctypes.c_char_p), c_void_p, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_int]),
     "tt_gather_concat": (c_int, [ctypes.POINTER(TTFeature), c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "tt_dense_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p]),

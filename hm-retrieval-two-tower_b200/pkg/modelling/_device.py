@@ -17,39 +17,76 @@ def _as_str(v) -> str:
     return v.decode() if isinstance(v, (bytes, np.bytes_)) else str(v)
 
 
+def _as_bytes_array(values) -> np.ndarray:
+    """Any array of str / bytes / objects -> contiguous numpy 'S<w>' array of shape (n,)."""
+    flat = np.asarray(values).reshape(-1)
+    if flat.dtype.kind == "S":
+        return np.ascontiguousarray(flat)
+    if flat.dtype.kind == "U":
+        try:
+            return np.ascontiguousarray(flat.astype("S"))          # ASCII fast path
+        except UnicodeEncodeError:
+            return np.ascontiguousarray(np.char.encode(flat, "utf-8"))
+    return np.ascontiguousarray(np.array([v if isinstance(v, (bytes, np.bytes_)) else str(v).encode() for v in flat], dtype="S"))
+
+
 class Vocab:
-    """StringLookup(num_oov_indices=1, vocabulary=vocab): OOV -> 0, vocab[i] -> i + 1."""
+    """StringLookup(num_oov_indices=1, vocabulary=vocab): OOV -> 0, vocab[i] -> i + 1.
+
+    Lookups of string batches run in libtt's open-addressing hash map (tt_vocab_lookup_fixed, multi-threaded): the
+    per-example Python dict lookup this replaces was the first host bottleneck once the kernels were fast."""
 
     def __init__(self, vocab):
         self.size = len(vocab)
         self._range = hasattr(vocab, "n") and vocab.__class__.__name__ == "_RangeVocab"
-        self._table: Optional[Dict[str, int]] = None
+        self._handle = None
         self._vocab = vocab
 
     @property
     def rows(self) -> int:
         return self.size + 1
 
-    def _dict(self) -> Dict[str, int]:
-        if self._table is None:
-            t: Dict[str, int] = {}
-            for i, v in enumerate(self._vocab):
-                t.setdefault(_as_str(v), i + 1)
-            self._table = t
-        return self._table
+    def _native(self):
+        if self._handle is None:
+            lib = N.load()
+            enc = [(_as_str(v)).encode() for v in self._vocab]
+            offsets = np.zeros(len(enc) + 1, dtype=np.int64)
+            np.cumsum([len(b) for b in enc], out=offsets[1:])
+            blob = b"".join(enc)
+            self._handle = lib.tt_vocab_create(blob, offsets.ctypes.data, len(enc))
+            if not self._handle:
+                raise N.TTError("tt_vocab_create failed: " + lib.tt_last_error().decode())
+        return self._handle
 
-    def encode(self, values) -> np.ndarray:
+    def __del__(self):
+        try:
+            if self._handle:
+                N.load().tt_vocab_destroy(self._handle)
+        except Exception:
+            pass
+
+    def __getstate__(self):          # the native handle does not pickle; it is rebuilt on demand
+        d = dict(self.__dict__)
+        d["_handle"] = None
+        return d
+
+    def encode(self, values, nthreads: int = 8) -> np.ndarray:
         """Any array of str / bytes / objects -> int32 row ids, shape (n,)."""
-        flat = np.asarray(values).reshape(-1)
-        if self._range:
-            out = np.zeros(flat.shape[0], dtype=np.int32)
-            for n, v in enumerate(flat):
-                s = _as_str(v)
-                if s.isdigit() and str(int(s)) == s and 1 <= int(s) <= self.size:
-                    out[n] = int(s)
+        cells = _as_bytes_array(values)
+        n = cells.shape[0]
+        out = np.zeros(n, dtype=np.int32)
+        if n == 0:
             return out
-        table = self._dict()
-        return np.fromiter((table.get(_as_str(v), 0) for v in flat), dtype=np.int32, count=flat.shape[0])
+        if self._range:   # synthetic vocabulary "1".."n": the row id is the integer itself when it is canonical and in range
+            for i, v in enumerate(cells):
+                s = v.decode()
+                if s.isdigit() and str(int(s)) == s and 1 <= int(s) <= self.size:
+                    out[i] = int(s)
+            return out
+        lib = N.load()
+        N.check(lib.tt_vocab_lookup_fixed(self._native(), cells.ctypes.data, n, cells.dtype.itemsize, out.ctypes.data, nthreads),
+                "tt_vocab_lookup_fixed")
+        return out
 
     def token(self, row: int) -> str:
         return "[UNK]" if row == 0 else _as_str(self._vocab[row - 1])

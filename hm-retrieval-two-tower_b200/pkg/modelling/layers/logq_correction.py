@@ -38,8 +38,10 @@ class LogQCorrection:
                 if k.isdigit() and 1 <= int(k) <= vocab.size:
                     p[int(k)] = v
         else:
-            for k, row in vocab._dict().items():
-                if k in self.lookup:
+            keys = list(self.lookup.keys())
+            rows = vocab.encode(np.array(keys, dtype=object)) if keys else []
+            for k, row in zip(keys, rows):
+                if row > 0:                      # ids with a probability but outside the vocabulary share the OOV row (ln 1 = 0)
                     p[row] = self.lookup[k]
         return p
 

@@ -31,6 +31,7 @@ extern "C" {
 #define TT_ERR_CUDA (-2)
 #define TT_ERR_WORKSPACE (-3)
 #define TT_ERR_UNSUPPORTED (-4)
+#define TT_ERR_INVALID (-5)   /* malformed input data (TFRecord framing / CRC / Example message) */
 
 #define TT_MAX_FEATURES 16   /* features per tower */
 #define TT_MAX_SRC 4         /* gradient sources that may share one table (same-named features) */
@@ -196,6 +197,35 @@ int tt_topk_merge(const float* scores, const int32_t* idx, int G, int nq, int K,
  * cand is (nq, k_stride) int32; hits is int32[nk] on the device and is accumulated into. */
 int tt_recall_hits(const int32_t* cand, int k_stride, const int32_t* true_idx, int nq, const int32_t* ks, int nk,
                    int32_t* hits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-side helpers on either side of the GPU path (no device work; csrc/tt_host.cu).
+ *
+ * Vocabulary map -- replaces tf.keras.layers.StringLookup(num_oov_indices=1, vocabulary=v) of input_layer.py:33-36
+ * (vocabulary order: features.py:119-127): string -> row id, 0 = out of vocabulary, v[i] -> i + 1 (the first
+ * occurrence wins when v holds duplicates).  Strings are byte strings; `blob`/`offsets` is the usual CSR form
+ * (string i = blob[offsets[i] .. offsets[i+1])).  Lookups are read-only and may run concurrently. */
+void* tt_vocab_create(const char* blob, const int64_t* offsets, int64_t n);
+void tt_vocab_destroy(void* vocab);
+int64_t tt_vocab_size(void* vocab);
+int tt_vocab_lookup(void* vocab, const char* blob, const int64_t* offsets, int64_t n, int32_t* out_rows, int nthreads);
+/* n fixed-width cells of `width` bytes, NUL padded on the right (numpy dtype 'S<width>') */
+int tt_vocab_lookup_fixed(void* vocab, const char* cells, int64_t n, int width, int32_t* out_rows, int nthreads);
+
+/* TFRecord files -- replace tf.io.TFRecordWriter (tfrecord_writer.py:122-126) and tf.data.TFRecordDataset +
+ * tf.io.parse_single_example (tfrecord_dataset.py:48-50,86-88).  A record is {u64 length, u32 masked CRC32C(length),
+ * payload, u32 masked CRC32C(payload)}, little endian; masked(c) = rotr(c, 15) + 0xa282ead8. */
+uint32_t tt_crc32c(const void* data, size_t n);           /* CRC-32C (Castagnoli), SSE4.2 when available */
+uint32_t tt_crc32c_portable(const void* data, size_t n);  /* table-driven twin */
+uint32_t tt_crc32c_masked(const void* data, size_t n);
+/* Returns the number of records in the file image (writing at most max_records (payload offset, payload length)
+ * pairs), or TT_ERR_INVALID for a truncated file / CRC mismatch. */
+int64_t tt_tfrecord_scan(const void* file, size_t nbytes, int verify_crc, int64_t* rec_offset, int64_t* rec_len, int64_t max_records);
+int tt_tfrecord_frame(const void* payload, uint64_t len, void* out /* len + 16 bytes */);
+/* Batch parser of serialized tf.train.Example payloads holding ONE value per requested feature (FixedLenFeature([1])):
+ * kind[f] 0 = bytes -> (str_off, str_len)[f * nrec + i] into `file`; 1 = float -> fvals[f * nrec + i]. */
+int tt_example_parse(const void* file, const int64_t* rec_offset, const int64_t* rec_len, int64_t nrec, const char* const* names,
+                     const int32_t* kind, int nfeat, int64_t* str_off, int64_t* str_len, float* fvals, int nthreads);
 
 #ifdef __cplusplus
 }
