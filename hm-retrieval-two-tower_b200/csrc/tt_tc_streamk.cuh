@@ -12,7 +12,7 @@
 // its partials are merged in slot order by a small kernel (fixed order: deterministic, no atomics).
 //
 //   kFwd  z = s*log2e - colv2_j; online max / sum 2^(z - max) per row; diagonal logit          (tt_inbatch_softmax_fwd)
-//   kBwd  P = 2^(z - rowv_i*log2e) - [j == i + d] -> fp16 -> swizzled smem = A operand of the 2nd MMA (kind::f16)
+//   kBwd  P = 2^(z - rowv_i*log2e) - [j == i + d] -> fp16 pairs -> tensor memory (tcgen05.st) = A operand of the 2nd MMA (kind::f16)
 //         G(128 x E) += P . T_tile; the B operand is a K-major fp16 tile of T^T (TMA from a transposed fp16 copy)
 //                                                                                                (tt_inbatch_softmax_bwd)
 #pragma once
@@ -20,7 +20,7 @@
 
 #define SK_TRACE(it, ev)                                                                                         \
     do {                                                                                                     \
-        if (p.trace && (it) < 64) p.trace[((size_t)blockIdx.x * 64 + (it)) * 4 + (ev)] = gtime();             \
+        if (p.trace && (it) < 64) p.trace[((size_t)blockIdx.x * 64 + (it)) * 8 + (ev)] = gtime();             \
     } while (0)
 
 namespace tt {
@@ -41,7 +41,7 @@ struct SkParams {
     SkPass pass[2];
     int n_pass;
     int units;           // work units of all passes
-    unsigned long long* trace;   // optional debug timeline [cta][64 units][4]: TMA issued, MMA issued, S seen by the epilogue, S released
+    unsigned long long* trace;   // optional debug timeline [cta][64 units][8]: TMA issued, MMA1 issued, S seen by the epilogue, S released, MMA warp: T landed, S buffer free, P ready, MMA2 issued
 };
 struct SkMaps {
     CUtensorMap r[2], t[2], tt[2];   // per pass: R panels (box 128 rows), T tiles (box BN rows), T^T tiles (box E rows)
@@ -80,8 +80,9 @@ struct SkCfg {
     static_assert(!H || E >= 64, "fp16 operands need E >= 64");
     static constexpr int kT2Bytes = (MODE == kBwd) ? (BN / 64) * E * 128 : 0;     // T^T tile (fp16, K-major over BN): second MMA
     static constexpr int kTBytes = kT1Bytes + kT2Bytes;
-    static constexpr int kPBytes = (MODE == kBwd) ? (BN / 64) * 128 * 128 : 0;    // P tile (fp16, K-major over BN)
-    static constexpr int kPBufs = (MODE == kBwd) ? 2 : 0;
+    static constexpr int kPBytes = 0;                                   // P lives in TMEM (A operand of the second MMA)
+    static constexpr int kPBufs = 0;
+    static constexpr int kPCols = BN / 2;                               // TMEM columns of one P buffer: fp16 pairs packed per 32-bit column
     static constexpr int kC2Bytes = BN * 4;
     static constexpr int kFixed = kRBytes + kPBufs * kPBytes + 4 * 1024 /*c2 stages*/ + 1024 /*barriers*/ + 1024 /*align*/;
     static constexpr int kFit = (232448 - kFixed) / kTBytes;
@@ -92,10 +93,12 @@ struct SkCfg {
     // dependent FMNMX / MUFU / FADD latencies better than 2 warps with two chunks each)
     static constexpr int kHalves = (BN / 32 >= 4) ? 4 : ((BN / 32 >= 2) ? 2 : 1);
     static constexpr int kEpiWarps = 4 * kHalves;
-    static constexpr int kThreads = 64 + 32 * kEpiWarps;
+    static constexpr int kThreads = 32 * kEpiWarps + 64 + (MODE == kBwd ? 32 : 0);   // epilogue warps, producer, MMA issuer(s)
     // S accumulators in flight: the MMA -> epilogue -> MMA hand-over latency is amortised over kAcc units
-    static constexpr int kAcc = (MODE == kFwd) ? (4 * BN <= 512 ? 4 : 2) : ((3 * BN + 2 * E <= 512) ? 3 : 2);
-    static constexpr int kTmemNeed = (MODE == kBwd) ? kAcc * BN + 2 * E : kAcc * BN;
+    static constexpr int kAcc = (MODE == kFwd) ? (4 * BN <= 512 ? 4 : 2) : 2;
+    // backward TMEM map: S[kAcc] | P[2] (fp16 pairs) | G[2]
+    static constexpr int kPBase = kAcc * BN, kGBase = kAcc * BN + 2 * (BN / 2);
+    static constexpr int kTmemNeed = (MODE == kBwd) ? kGBase + 2 * E : kAcc * BN;
     static constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512);
     static_assert(kStages >= 2, "shared memory budget");
     static_assert(kTmemNeed <= 512, "TMEM budget");
@@ -121,6 +124,27 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
         : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (M x K, fp16 pairs packed per 32-bit column, row m in lane m) is read from
+// tensor memory -- the epilogue writes P there with tcgen05.st, so P never touches shared memory
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns: thread t of the warp writes lane (lane_base + t)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&w)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]),
+        "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {   // round-to-nearest-even, lo in the low half
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -194,57 +218,42 @@ __device__ __forceinline__ void fwd_chunk_packed(const uint32_t (&r)[32], uint32
     m2 = -mneg;
 }
 
-// backward epilogue body, fast path (chunk fully in range, off the diagonal): P = 2^(s*log2e - r2 - c2_j) as fp16.
-// One FFMA2 per two columns (r2 is folded into the addend), two MUFU, one F2FP pack; 4 x STS.128 per 32 columns.
-__device__ __forceinline__ void bwd_chunk_packed(const uint32_t (&r)[32], uint32_t c2s, int row_l, float r2, uint32_t prow, int half_of_slab) {
+// backward epilogue bodies: 32 columns of one row -> P = 2^(s*log2e - r2 - c2_j) - [j == i + d] as 16 packed fp16 pairs
+// (fp16 keeps the 11 significant bits TF32 would; P lies in [-1, 1], values below 6e-5 lose relative precision only).
+// Fast path (chunk fully in range, off the diagonal): one FFMA2 per two columns (r2 folded into the addend), two MUFU,
+// one F2FP pack.
+__device__ __forceinline__ void bwd_chunk_packed(const uint32_t (&r)[32], uint32_t c2s, float r2, uint32_t (&w)[16]) {
     const f32x2 l2e = pk2(kLog2e, kLog2e), mone = pk2(-1.f, -1.f), nr2 = pk2(-r2, -r2);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {            // 16-byte pieces of 8 columns
-        uint32_t w[4];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float4 cc = lds128(c2s + (j * 2 + h) * 16);
-            const int i = j * 8 + h * 4;
-            // t = s*log2e - (c2 + r2):  addend = c2*(-1) + (-r2), then fma(s, log2e, addend)
-            const f32x2 ad0 = fma2(pk2(cc.x, cc.y), mone, nr2), ad1 = fma2(pk2(cc.z, cc.w), mone, nr2);
-            float a0, a1, b0, b1;
-            upk2(fma2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), l2e, ad0), a0, a1);
-            upk2(fma2(pk2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), l2e, ad1), b0, b1);
-            w[h * 2] = pack_f16x2(ex2_approx(a0), ex2_approx(a1));
-            w[h * 2 + 1] = pack_f16x2(ex2_approx(b0), ex2_approx(b1));
-        }
-        const uint32_t piece = static_cast<uint32_t>(half_of_slab * 4 + j);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((piece ^ (row_l & 7)) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+    for (int g4 = 0; g4 < 8; ++g4) {
+        const float4 cc = lds128(c2s + g4 * 16);
+        // t = s*log2e - (c2 + r2):  addend = c2*(-1) + (-r2), then fma(s, log2e, addend)
+        const f32x2 ad0 = fma2(pk2(cc.x, cc.y), mone, nr2), ad1 = fma2(pk2(cc.z, cc.w), mone, nr2);
+        float a0, a1, b0, b1;
+        upk2(fma2(pk2(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1])), l2e, ad0), a0, a1);
+        upk2(fma2(pk2(__uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])), l2e, ad1), b0, b1);
+        w[2 * g4] = pack_f16x2(ex2_approx(a0), ex2_approx(a1));
+        w[2 * g4 + 1] = pack_f16x2(ex2_approx(b0), ex2_approx(b1));
     }
 }
-
-// backward epilogue body: 32 columns of one row -> P = 2^(z - r2) - [diag] as fp16 into the swizzled A tile of the second MMA
-// (fp16 keeps the 11 significant bits TF32 would; P lies in [-1, 1], values below 6e-5 lose relative precision only)
-template <bool FAST>
-__device__ __forceinline__ void bwd_chunk_h(const uint32_t (&r)[32], uint32_t c2s, int nb, int row, int row_l, int nT, int nR, int d, float r2,
-                                            uint32_t prow, int half_of_slab) {
+__device__ __forceinline__ void bwd_chunk_checked(const uint32_t (&r)[32], uint32_t c2s, int nb, int row, int nT, int nR, int d, float r2,
+                                                  uint32_t (&w)[16]) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {            // 16-byte pieces of 8 columns
-        float pv[8];
+    for (int g4 = 0; g4 < 8; ++g4) {
+        const float4 cc = lds128(c2s + g4 * 16);
+        const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
+        float pv[4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float4 cc = lds128(c2s + (j * 2 + h) * 16);
-            const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int i = j * 8 + h * 4 + t;
-                float v = ex2_approx(fmaf(__uint_as_float(r[i]), kLog2e, -r2) - cv[t]);
-                if (!FAST) {
-                    const int n = nb + i;
-                    if (n >= nT || row >= nR) v = 0.f;
-                    else if (n == row + d) v -= 1.0f;
-                }
-                pv[h * 4 + t] = v;
-            }
+        for (int t = 0; t < 4; ++t) {
+            const int i = g4 * 4 + t;
+            float v = ex2_approx(fmaf(__uint_as_float(r[i]), kLog2e, -r2) - cv[t]);
+            const int n = nb + i;
+            if (n >= nT || row >= nR) v = 0.f;
+            else if (n == row + d) v -= 1.0f;
+            pv[t] = v;
         }
-        const uint32_t w0 = pack_f16x2(pv[0], pv[1]), w1 = pack_f16x2(pv[2], pv[3]), w2 = pack_f16x2(pv[4], pv[5]), w3 = pack_f16x2(pv[6], pv[7]);
-        const uint32_t piece = static_cast<uint32_t>(half_of_slab * 4 + j);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((piece ^ (row_l & 7)) << 4)), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+        w[2 * g4] = pack_f16x2(pv[0], pv[1]);
+        w[2 * g4 + 1] = pack_f16x2(pv[2], pv[3]);
     }
 }
 
@@ -272,14 +281,16 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
     unsigned char* sR = smem;
     unsigned char* sT = sR + Cfg::kRBytes;
     unsigned char* sP = sT + Cfg::kStages * Cfg::kTBytes;
-    unsigned char* sC2 = sP + Cfg::kPBufs * Cfg::kPBytes;       // kC2Slots x kC2Bytes (4 KB)
+    unsigned char* sC2 = sP;                                    // kC2Slots x kC2Bytes (4 KB)
     SkBars* bars = reinterpret_cast<SkBars*>(sC2 + 4 * 1024);
 
-    // roles: warps 0..kEpiWarps-1 epilogue, then the TMA producer, then the MMA issuer.  The two single-lane warps get the
+    // roles: warps 0..kEpiWarps-1 epilogue, then the TMA producer, then the MMA issuer(s).  The backward has TWO issuers (first
+    // MMA / second MMA): one lane issuing all 12 MMAs of a unit plus its three barrier waits was the per-unit critical path
+    // (~100 cycles per tcgen05.mma issue: descriptor math, R2UR, commit; 1.5 us per unit measured).  The single-lane warps get the
     // HIGHEST warp ids: the scheduler arbitrates highest-id-first, and behind 4 always-eligible epilogue warps per scheduler a
     // low-id MMA warp was issuing one unit per ~0.9 us (measured) although every barrier it waits on had long completed.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int kProducerWarp = Cfg::kEpiWarps, kMmaWarp = Cfg::kEpiWarps + 1;
+    constexpr int kProducerWarp = Cfg::kEpiWarps, kMmaWarp = Cfg::kEpiWarps + 1, kMma2Warp = Cfg::kEpiWarps + 2;
     if (warp == kProducerWarp && lane == 0) {
         for (int i = 0; i < 2; ++i) {
             if (i < p.n_pass) {
@@ -342,8 +353,7 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc1 = H ? make_idesc_f16(128, BN) : make_idesc_tf32(128, BN, false, false);
-        constexpr uint32_t idesc2 = make_idesc_f16(128, E);
-        const uint32_t sR_a = smem_u32(sR), sT_a = smem_u32(sT), sP_a = smem_u32(sP);
+        const uint32_t sR_a = smem_u32(sR), sT_a = smem_u32(sT);
         SkCursor c1;   // unit whose first MMA is issued next
         c1.init(p, u_begin);
         int k1 = -1;   // panel sequence number of c1's unit
@@ -359,15 +369,16 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
             const int acc = it % Cfg::kAcc;
             const uint32_t aph = (it / Cfg::kAcc) & 1;
             mbar_wait(&bars->t_full[stage], tph);
+            if (lane == 0) SK_TRACE(it, 4);
             mbar_wait(&bars->s_empty[acc], aph ^ 1);
+            if (lane == 0) SK_TRACE(it, 5);
             tc_fence_after();
             if (lane == 0) {
+                const uint64_t ad0 = make_smem_desc(sR_a, 16, 1024), bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes, 16, 1024);
 #pragma unroll
-                for (int k = 0; k < Cfg::kMma1; ++k) {
-                    const uint32_t off = (k >> 2) * 128 * 128 + (k & 3) * 32;
-                    const uint32_t offT = (k >> 2) * BN * 128 + (k & 3) * 32;
-                    uint64_t ad = make_smem_desc(sR_a + off, 16, 1024);
-                    uint64_t bd = make_smem_desc(sT_a + stage * Cfg::kTBytes + offT, 16, 1024);
+                for (int k = 0; k < Cfg::kMma1; ++k) {   // K steps differ only in the start-address field (units of 16 bytes)
+                    const uint64_t ad = ad0 + (uint64_t)(((k >> 2) * 128 * 128 + (k & 3) * 32) >> 4);
+                    const uint64_t bd = bd0 + (uint64_t)(((k >> 2) * BN * 128 + (k & 3) * 32) >> 4);
                     if (H) mma_f16(tmem + acc * BN, ad, bd, idesc1, k > 0 ? 1u : 0u);
                     else mma_tf32(tmem + acc * BN, ad, bd, idesc1, k > 0 ? 1u : 0u);
                 }
@@ -379,40 +390,41 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
             __syncwarp();
             c1.next(p);
         };
-        if constexpr (MODE != kBwd) {
-            for (int it = 0; it < my_units; ++it) issue_g1(it);
-        } else {
-            SkCursor c2;   // unit whose second MMA is issued next
-            c2.init(p, u_begin);
-            int k2 = -1;
-            issue_g1(0);
-            for (int it = 0; it < my_units; ++it, c2.next(p)) {
-                if (it + 1 < my_units) issue_g1(it + 1);  // keep the tensor core busy while the epilogue builds P(it)
-                const bool panel_start = (it == 0 || c2.tile == 0);
-                const bool panel_end = (it == my_units - 1 || c2.tile == p.pass[c2.pass].n_tiles - 1);
-                if (panel_start) {
-                    ++k2;
-                    mbar_wait(&bars->g_empty[k2 & 1], ((k2 >> 1) & 1) ^ 1);   // the epilogue has drained this G buffer
-                }
-                const int gb = k2 & 1;
-                const int stage = it % Cfg::kStages;
-                const int pb = it & 1;
-                const uint32_t pph = (it >> 1) & 1;
-                mbar_wait(&bars->p_full[pb], pph);
-                tc_fence_after();
-                if (lane == 0) {
-#pragma unroll
-                    for (int kk = 0; kk < BN / 16; ++kk) {   // fp16: 16 columns (32 bytes) per MMA, 64 per swizzle slab
-                        uint64_t ad = make_smem_desc(sP_a + pb * Cfg::kPBytes + (kk >> 2) * 128 * 128 + (kk & 3) * 32, 16, 1024);
-                        uint64_t bd = make_smem_desc(sT_a + stage * Cfg::kTBytes + Cfg::kT1Bytes + (kk >> 2) * E * 128 + (kk & 3) * 32, 16, 1024);
-                        mma_f16(tmem + Cfg::kAcc * BN + gb * E, ad, bd, idesc2, (!panel_start || kk > 0) ? 1u : 0u);
-                    }
-                    mma_commit(&bars->t_empty[stage]);  // T and T^T of this stage are consumed by now
-                    mma_commit(&bars->p_empty[pb]);
-                    if (panel_end) mma_commit(&bars->g_full[gb]);
-                }
-                __syncwarp();
+        for (int it = 0; it < my_units; ++it) issue_g1(it);   // (backward: runs ahead of the second-MMA issuer by up to kAcc units)
+    } else if (MODE == kBwd && warp == kMma2Warp) {
+        // ===================== second-MMA issuer (backward): G += P . T_tile, A = P from tensor memory =====================
+        constexpr uint32_t idesc2 = make_idesc_f16(128, E);
+        const uint32_t sT_a = smem_u32(sT);
+        SkCursor c2;
+        c2.init(p, u_begin);
+        int k2 = -1;
+        for (int it = 0; it < my_units; ++it, c2.next(p)) {
+            const bool panel_start = (it == 0 || c2.tile == 0);
+            const bool panel_end = (it == my_units - 1 || c2.tile == p.pass[c2.pass].n_tiles - 1);
+            if (panel_start) {
+                ++k2;
+                mbar_wait(&bars->g_empty[k2 & 1], ((k2 >> 1) & 1) ^ 1);   // the epilogue has drained this G buffer
             }
+            const int gb = k2 & 1;
+            const int stage = it % Cfg::kStages;
+            const int pb = it & 1;
+            mbar_wait(&bars->t_full[stage], (it / Cfg::kStages) & 1);     // T^T tile landed (long ago: the first MMA of this unit is done)
+            mbar_wait(&bars->p_full[pb], (it >> 1) & 1);
+            if (lane == 0) SK_TRACE(it, 6);
+            tc_fence_after();
+            if (lane == 0) {
+                // descriptor of the first K step; the others differ only in the 14-bit start-address field (units of 16 bytes)
+                const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes + Cfg::kT1Bytes, 16, 1024);
+                const uint32_t d_t = tmem + Cfg::kGBase + gb * E, a_t = tmem + Cfg::kPBase + pb * Cfg::kPCols;
+#pragma unroll
+                for (int kk = 0; kk < BN / 16; ++kk)   // fp16: 16 columns (32 bytes) per MMA, 64 per swizzle slab
+                    mma_f16_ts(d_t, a_t + kk * 8, bd0 + (uint64_t)(((kk >> 2) * E * 128 + (kk & 3) * 32) >> 4), idesc2, (!panel_start || kk > 0) ? 1u : 0u);
+                mma_commit(&bars->t_empty[stage]);  // T and T^T of this stage are consumed by now (the first MMA completed before P existed)
+                mma_commit(&bars->p_empty[pb]);
+                if (panel_end) mma_commit(&bars->g_full[gb]);
+                SK_TRACE(it, 7);
+            }
+            __syncwarp();
         }
     } else {
         // ===================== epilogue warps (0 .. kEpiWarps-1) =====================
@@ -472,12 +484,14 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
 #endif
                     else fwd_chunk<false>(r, c2s + cc * 128, nb, row, ps.nT, ps.d, m2, l, zd, has_diag);
                 } else {
-                    const uint32_t prow = smem_u32(sP + pb * Cfg::kPBytes + (cc >> 1) * 128 * 128 + row_l * 128);
-                    if (fast) bwd_chunk_packed(r, c2s + cc * 128, row_l, r2, prow, cc & 1);
-                    else bwd_chunk_h<false>(r, c2s + cc * 128, nb, row, row_l, ps.nT, ps.nR, ps.d, r2, prow, cc & 1);
+                    uint32_t w[16];
+                    if (fast) bwd_chunk_packed(r, c2s + cc * 128, r2, w);
+                    else bwd_chunk_checked(r, c2s + cc * 128, nb, row, ps.nT, ps.nR, ps.d, r2, w);
+                    tmem_st_32x16(tmem + lane_addr + Cfg::kPBase + pb * Cfg::kPCols + cc * 16, w);
                 }
             }
-            // this S buffer may be overwritten by the MMA of unit it+2
+            // this S buffer may be overwritten by the MMA of a later unit; backward: P is complete in tensor memory
+            if (MODE == kBwd) tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -486,9 +500,7 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
             }
             if (threadIdx.x == 0) SK_TRACE(it, 3);
             if constexpr (MODE == kBwd) {
-                fence_proxy_async_smem();   // P stores (generic proxy) -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->p_full[pb]);
+                if (lane == 0) mbar_arrive(&bars->p_full[pb]);   // (the P stores were completed and fenced above)
             }
             if (panel_end) {
                 if constexpr (MODE == kFwd) {
@@ -505,7 +517,7 @@ streamk_kernel(const __grid_constant__ SkMaps maps, const __grid_constant__ SkPa
 #pragma unroll
                     for (int cg = half; cg < E / 32; cg += Cfg::kHalves) {
                         float v[32];
-                        tmem_ld_32x32(tmem + lane_addr + Cfg::kAcc * BN + gb * E + cg * 32, v);
+                        tmem_ld_32x32(tmem + lane_addr + Cfg::kGBase + gb * E + cg * 32, v);
                         if (row < ps.nR) {
                             float4* dst = reinterpret_cast<float4*>(ps.out0 + ((int64_t)slot * ps.nR + row) * E + cg * 32);
 #pragma unroll

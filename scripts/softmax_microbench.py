@@ -57,23 +57,23 @@ def main():
     for cap in (1, 2, 4, 8, 16):
         lib.tt_debug_tc(None, cap)
         print(f"  max_splits={cap:2d}: fwd {time_ms(fwd):8.3f} ms   bwd(2 passes) {time_ms(bwd):8.3f} ms")
-    # stream-K timeline: [cta][64 units][4] = TMA issued, first MMA issued, S seen by an epilogue warp, S released
+    # stream-K timeline: [cta][64 units][8] (see SkParams::trace)
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
-        trace = torch.zeros(148 * 64 * 4, dtype=torch.int64, device="cuda")
+        trace = torch.zeros(148 * 64 * 8, dtype=torch.int64, device="cuda")
         lib.tt_debug_tc(trace.data_ptr(), 0)
         fn()
         torch.cuda.synchronize()
         lib.tt_debug_tc(None, 0)
-        t = trace.cpu().numpy().reshape(148, 64, 4)
+        t = trace.cpu().numpy().reshape(148, 64, 8)
         for cta in (0, 73):
             tt = t[cta]
             n = int((tt[:, 3] > 0).sum())
             if n == 0:
                 continue
             t0 = tt[0, 0]
-            print(f"{name} cta {cta}: {n} traced units; us since the first TMA issue: unit: tma mma s_seen s_released")
+            print(f"{name} cta {cta}: {n} traced units; us since the first TMA issue: unit: tma mma1 s_seen s_released | mma warp: t_landed s_free p_ready mma2")
             for u in list(range(min(n, 14))) + ([n - 1] if n > 14 else []):
-                print(f"    {u:3d}: " + " ".join(f"{(tt[u, e] - t0) / 1e3:7.2f}" for e in range(4)))
+                print(f"    {u:3d}: " + " ".join(f"{(tt[u, e] - t0) / 1e3:7.2f}" if tt[u, e] else "      -" for e in range(8)))
 
 
 if __name__ == "__main__":
