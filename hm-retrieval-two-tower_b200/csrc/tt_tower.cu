@@ -286,10 +286,8 @@ int panel_dense_fwd(const float* X, int ldx, const float* W, const float* b, flo
 int panel_input_dense_fwd(const tt_feature* feats, int nfeat, int D, const float* W, const float* b, float* Xout, int ldx, float* Y, int ldy,
                           float* Y32, int B, int N, int relu, cudaStream_t st);
 size_t panel_bwd_workspace(int B, int K, int N);
-int panel_dense_bwd_dx(const float* W, const float* Y, int ldy, const float* dY, int lddy, float* dX, int lddx, int B, int K, int N, int relu,
-                       cudaStream_t st);
-int panel_dense_bwd_dw(const float* X, int ldx, const float* Y, int ldy, const float* dY, int lddy, float* partial, int B, int K, int N, int relu,
-                       int* nchunk_out, cudaStream_t st);
+int panel_dense_bwd(const float* X, int ldx, const float* W, const float* Y, int ldy, const float* dY, int lddy, float* dX, int lddx, float* dW,
+                    float* db, float* partial, int B, int K, int N, int relu, cudaStream_t st);
 
 }  // namespace tt
 
@@ -386,20 +384,8 @@ int tt_dense_bwd(const float* X, int ldx, const float* W, const float* Y, int ld
         if (db) TT_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
         return TT_OK;
     }
-    if (panel_bwd_ok(K, N)) {
-        if (dX) {
-            int rc = panel_dense_bwd_dx(W, Y, ldy, dY, lddy, dX, lddx, B, K, N, relu, st);
-            if (rc) return rc;
-        }
-        float* partial = reinterpret_cast<float*>(ws);
-        int nchunk = 0;
-        int rc = panel_dense_bwd_dw(X, ldx, Y, ldy, dY, lddy, partial, B, K, N, relu, &nchunk, st);
-        if (rc) return rc;
-        int64_t total = (int64_t)(K + 1) * N;
-        dense_bwd_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(partial, nchunk, K, N, dW, db);
-        TT_LAUNCH_OK("dense_bwd_reduce_kernel");
-        return TT_OK;
-    }
+    if (panel_bwd_ok(K, N))
+        return panel_dense_bwd(X, ldx, W, Y, ldy, dY, lddy, dX, lddx, dW, db, reinterpret_cast<float*>(ws), B, K, N, relu, st);
     DPre dp{dY, Y, lddy, ldy, B, N, relu};
     if (dX) {
         dim3 grid((unsigned)ceil_div(B, BM), (unsigned)ceil_div(K, BN));

@@ -121,13 +121,12 @@ __global__ void __launch_bounds__(256) dense_fwd_panel_kernel(const __grid_const
 
 // ---- backward dX = dpre.W^T  (reduction over N <= 256) ----------------------------------------------------------
 // grid (ceil(B/64), ceil(K/64)); smem: DsT[N][PS] (dpre^T tile) + WsT[N][PS] (WsT[n][kk] = W[k0+kk][n])
-__global__ void __launch_bounds__(256) dense_bwd_dx_panel_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Yv, int ldy,
-                                                                 const float* __restrict__ W, float* __restrict__ dX, int lddx, int B, int K,
-                                                                 int N, int relu) {
-    extern __shared__ __align__(16) float sm[];
+__device__ __forceinline__ void dense_bwd_dx_tile(float* sm, int bx, int by, const float* __restrict__ dY, int lddy, const float* __restrict__ Yv,
+                                                  int ldy, const float* __restrict__ W, float* __restrict__ dX, int lddx, int B, int K, int N,
+                                                  int relu) {
     float* DsT = sm;
     float* WsT = sm + (size_t)N * PS;
-    const int m0 = blockIdx.x * PT, k0 = blockIdx.y * PT;
+    const int m0 = bx * PT, k0 = by * PT;
     const int tid = threadIdx.x;
 #pragma unroll 8
     for (int idx = tid; idx < PT * N; idx += 256) {
@@ -175,13 +174,13 @@ __global__ void __launch_bounds__(256) dense_bwd_dx_panel_kernel(const float* __
 // grid (nchunk, ceil((K+1)/96), ceil(N/64)); a chunk is `rows` batch rows processed 64 at a time.
 // thread (ty 0..15, tx 0..15): rows k0 + ty + 16*i (i < 6), cols n0 + 4*tx .. +3.
 constexpr int kDwRows = 96;
-__global__ void __launch_bounds__(256) dense_bwd_dw_panel_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int lddy,
-                                                                 const float* __restrict__ Yv, int ldy, float* __restrict__ partial, int B,
-                                                                 int K, int N, int rows, int relu) {
-    __shared__ __align__(16) float Xs[PT][kDwRows + 1];
-    __shared__ __align__(16) float Ds[PT][PS];
-    const int b_begin = blockIdx.x * rows, b_end = min(B, b_begin + rows);
-    const int k0 = blockIdx.y * kDwRows, n0 = blockIdx.z * PT;
+__device__ __forceinline__ void dense_bwd_dw_tile(float* sm, int bx, int by, int bz, const float* __restrict__ X, int ldx,
+                                                  const float* __restrict__ dY, int lddy, const float* __restrict__ Yv, int ldy,
+                                                  float* __restrict__ partial, int B, int K, int N, int rows, int relu) {
+    float(*Xs)[kDwRows + 1] = reinterpret_cast<float(*)[kDwRows + 1]>(sm);                       // [PT][kDwRows + 1]
+    float(*Ds)[PS] = reinterpret_cast<float(*)[PS]>(sm + (PT * (kDwRows + 1) + 3) / 4 * 4);     // [PT][PS], 16-byte aligned
+    const int b_begin = bx * rows, b_end = min(B, b_begin + rows);
+    const int k0 = by * kDwRows, n0 = bz * PT;
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
     float acc[6][4] = {};
@@ -219,7 +218,7 @@ __global__ void __launch_bounds__(256) dense_bwd_dw_panel_kernel(const float* __
         }
         __syncthreads();
     }
-    float* out = partial + (int64_t)blockIdx.x * (K + 1) * N;
+    float* out = partial + (int64_t)bx * (K + 1) * N;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         const int k = k0 + ty + 16 * i;
@@ -229,6 +228,47 @@ __global__ void __launch_bounds__(256) dense_bwd_dw_panel_kernel(const float* __
             const int n = n0 + tx * 4 + j;
             if (n < N) out[(int64_t)k * N + n] = acc[i][j];
         }
+    }
+}
+
+// ---- one launch for the whole layer backward: dX tiles and dW/db chunk partials are independent -----------------------
+// blocks [0, n_dx) compute dX tiles (grid_dx = (gx, gy)); the rest compute dW partials (grid_dw = (nchunk, hy, hz)).
+constexpr int kDwSmemFloats = (PT * (kDwRows + 1) + 3) / 4 * 4 + PT * PS;
+__global__ void __launch_bounds__(256) dense_bwd_panel_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
+                                                              const float* __restrict__ Yv, int ldy, const float* __restrict__ dY, int lddy,
+                                                              float* __restrict__ dX, int lddx, float* __restrict__ partial, int B, int K, int N,
+                                                              int relu, int rows, int n_dx, int gx, int nchunk, int hy) {
+    extern __shared__ __align__(16) float sm[];
+    const int b = blockIdx.x;
+    if (b < n_dx) {
+        dense_bwd_dx_tile(sm, b % gx, b / gx, dY, lddy, Yv, ldy, W, dX, lddx, B, K, N, relu);
+    } else {
+        const int d = b - n_dx;
+        dense_bwd_dw_tile(sm, d % nchunk, (d / nchunk) % hy, d / (nchunk * hy), X, ldx, dY, lddy, Yv, ldy, partial, B, K, N, rows, relu);
+    }
+}
+
+// dW / db = sum over chunks: four interleaved partial sums per element (chunks z = j mod 4, ascending), combined as
+// ((s0 + s1) + (s2 + s3)) -- a fixed order, so the result is deterministic; four times shorter dependent chains than one sum
+__global__ void __launch_bounds__(256) dense_bwd_reduce4_kernel(const float* __restrict__ partial, int nchunk, int K, int N, float* __restrict__ dW,
+                                                                float* __restrict__ db) {
+    const int64_t total = (int64_t)(K + 1) * N;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i = t >> 2;
+    const int j = (int)(t & 3);
+    float s = 0.f;
+    if (i < total) {
+#pragma unroll 8
+        for (int z = j; z < nchunk; z += 4) s = __fadd_rn(s, __ldg(partial + (int64_t)z * total + i));
+    }
+    const float s1 = __shfl_xor_sync(0xffffffffu, s, 1);
+    const float a = (j & 1) ? __fadd_rn(s1, s) : __fadd_rn(s, s1);     // lanes j=0,1 both hold s0 + s1; lanes 2,3 hold s2 + s3
+    const float a2 = __shfl_xor_sync(0xffffffffu, a, 2);
+    if (i < total && j == 0) {
+        const float v = __fadd_rn(a, a2);
+        const int k = (int)(i / N), n = (int)(i % N);
+        if (k < K) dW[(int64_t)k * N + n] = v;
+        else if (db) db[n] = v;
     }
 }
 
@@ -267,8 +307,8 @@ int panel_input_dense_fwd(const tt_feature* feats, int nfeat, int D, const float
     return launch_fwd<true>(fa, nullptr, ldx, W, b, Xout, Y, ldy, Y32, B, D, N, relu, st);
 }
 
-static int dw_plan(int B, int* rows) {   // batch rows per CTA: a multiple of 64, about two waves of CTAs overall
-    int64_t want = 2 * (int64_t)sm_count();
+static int dw_plan(int B, int* rows) {   // batch rows per CTA: a multiple of 64, about one wave of CTAs (the dX tiles share the launch)
+    int64_t want = (int64_t)sm_count();
     int64_t r = ceil_div(ceil_div(B, want), PT) * PT;
     if (r < PT) r = PT;
     *rows = (int)r;
@@ -281,29 +321,28 @@ size_t panel_bwd_workspace(int B, int K, int N) {
     return align_up((size_t)nchunk * (K + 1) * N * sizeof(float), 256) + 256;
 }
 
-int panel_dense_bwd_dx(const float* W, const float* Y, int ldy, const float* dY, int lddy, float* dX, int lddx, int B, int K, int N, int relu,
-                       cudaStream_t st) {
-    const size_t smem = 2 * (size_t)N * PS * sizeof(float);
+// dX (optional) and dW/db in one launch + the fixed-order chunk reduction
+int panel_dense_bwd(const float* X, int ldx, const float* W, const float* Y, int ldy, const float* dY, int lddy, float* dX, int lddx, float* dW,
+                    float* db, float* partial, int B, int K, int N, int relu, cudaStream_t st) {
+    int rows = 0;
+    const int nchunk = dw_plan(B, &rows);
+    const int gx = (int)ceil_div(B, PT), gy = (int)ceil_div(K, PT);
+    const int n_dx = dX ? gx * gy : 0;
+    const int hy = (int)ceil_div(K + 1, kDwRows), hz = (int)ceil_div(N, PT);
+    const size_t smem_dx = 2 * (size_t)N * PS * sizeof(float), smem_dw = (size_t)kDwSmemFloats * sizeof(float);
+    const size_t smem = smem_dx > smem_dw ? smem_dx : smem_dw;
     static bool set = false;
     if (!set) {
-        TT_CUDA_OK(cudaFuncSetAttribute(dense_bwd_dx_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kPanelMaxK * PS * sizeof(float))));
+        const size_t mx = 2 * (size_t)kPanelMaxK * PS * sizeof(float);
+        TT_CUDA_OK(cudaFuncSetAttribute(dense_bwd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mx > smem_dw ? mx : smem_dw)));
         set = true;
     }
-    dim3 grid((unsigned)ceil_div(B, PT), (unsigned)ceil_div(K, PT));
-    dense_bwd_dx_panel_kernel<<<grid, 256, smem, st>>>(dY, lddy, Y, ldy, W, dX, lddx, B, K, N, relu);
-    TT_LAUNCH_OK("dense_bwd_dx_panel_kernel");
-    return TT_OK;
-}
-
-// returns the number of chunks written to `partial` ([chunk][K+1][N])
-int panel_dense_bwd_dw(const float* X, int ldx, const float* Y, int ldy, const float* dY, int lddy, float* partial, int B, int K, int N, int relu,
-                       int* nchunk_out, cudaStream_t st) {
-    int rows = 0;
-    int nchunk = dw_plan(B, &rows);
-    dim3 grid((unsigned)nchunk, (unsigned)ceil_div(K + 1, kDwRows), (unsigned)ceil_div(N, PT));
-    dense_bwd_dw_panel_kernel<<<grid, 256, 0, st>>>(X, ldx, dY, lddy, Y, ldy, partial, B, K, N, rows, relu);
-    TT_LAUNCH_OK("dense_bwd_dw_panel_kernel");
-    *nchunk_out = nchunk;
+    dense_bwd_panel_kernel<<<(unsigned)(n_dx + nchunk * hy * hz), 256, smem, st>>>(X, ldx, W, Y, ldy, dY, lddy, dX, lddx, partial, B, K, N, relu, rows,
+                                                                                   n_dx, gx, nchunk, hy);
+    TT_LAUNCH_OK("dense_bwd_panel_kernel");
+    const int64_t total = (int64_t)(K + 1) * N;
+    dense_bwd_reduce4_kernel<<<(unsigned)ceil_div(total * 4, 256), 256, 0, st>>>(partial, nchunk, K, N, dW, db);
+    TT_LAUNCH_OK("dense_bwd_reduce4_kernel");
     return TT_OK;
 }
 
