@@ -249,7 +249,7 @@ def run_ours(args):
         from pkg.modelling.distributed import DataParallel
 
         DataParallel(model)
-    model.use_cuda_graph = (not args.no_graph) and world == 1
+    model.use_cuda_graph = not args.no_graph   # data parallel: two captured compute phases around the eager NCCL exchanges
     rng = np.random.default_rng(1000 + rank)
     pool = 8
     host_batches = [make_batch(rng, B) for _ in range(pool)]

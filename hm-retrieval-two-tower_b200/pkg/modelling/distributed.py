@@ -4,8 +4,8 @@ for the exchanges.  The reference is single-process (no t
 sharding below follows SURVEY.md 8(e):
 
 * training -- data parallel.  Every rank runs train_step on its own batch (in-batch negatives stay local,
-  exactly what one reference process sees for that batch).  Dense gradients: ONE all-reduce(SUM) of the flat
-  gradient buffer (SUM loss => no 1/G scaling; a step equals the reference's gradient of G independent
+  exactly what one reference process sees for that batch).  Dense gradients: summed over ranks in rank order
+  (they ride in the same all-gather as the embedding-gradient rows; SUM loss => no 1/G scaling; a step equals the reference's gradient of G independent
   batches evaluated at the same weights and summed, then one optimizer apply).  Embedding tables are
   replicated: ranks all-gather (ids, gradient rows) and every replica runs the same deterministic
   de-duplicated row update, ordered by (rank, position), so replicas stay bit-identical.
@@ -74,6 +74,9 @@ class DataParallel:
             dist.broadcast(t.weight, src=0, group=group)
 
     # ---- buffers ---------------------------------------------------------------------------------------
+    # Two collectives per step: (1) ONE all-gather of all id columns, (2) ONE all-gather of every rank's message
+    # [embedding-gradient rows of both towers | flat dense gradients]; the dense gradients are then summed over ranks in
+    # rank order (a fixed order: replicas stay bit-identical).
     def _ensure(self, sw):
         if getattr(sw, "dp", None) is not None:
             return sw.dp
@@ -81,44 +84,82 @@ class DataParallel:
 
         torch = N.require_cuda()
         g, b = self.world, sw.batch
-        dp = {"towers": []}
-        for tower, tws in ((self.model.query_tower, sw.q), (self.model.candidate_tower, sw.c)):
-            il = tower.input_layer
-            ids_all = [None if t is None else torch.zeros(g * b, dtype=torch.int32, device="cuda") for (_, t, _, _) in il.blocks]
-            dx_all = torch.zeros((g * b, il.ld), dtype=torch.float32, device="cuda")
-            dp["towers"].append((tower, tws, ids_all, dx_all))
+        towers = [(self.model.query_tower, sw.q), (self.model.candidate_tower, sw.c)]
+        id_slots = []                                   # (tower index, block index) of every id column
+        for ti, (tower, tws) in enumerate(towers):
+            for bi, (_, t, _, _) in enumerate(tower.input_layer.blocks):
+                if t is not None:
+                    id_slots.append((ti, bi))
+        n_id = len(id_slots)
+        lds = [tower.input_layer.ld for tower, _ in towers]
+        row_w = sum(lds)
+        n_dense = int(self.model._store.used)
+        msg = b * row_w + n_dense                       # floats per rank
+        dp = {
+            "towers": towers, "id_slots": id_slots, "lds": lds, "row_w": row_w, "n_dense": n_dense,
+            "ids_local": torch.zeros((max(n_id, 1), b), dtype=torch.int32, device="cuda"),
+            "ids_gathered": torch.zeros((g, max(n_id, 1), b), dtype=torch.int32, device="cuda"),
+            "ids_all": torch.zeros((max(n_id, 1), g * b), dtype=torch.int32, device="cuda"),      # per column: rank-major (rank, position)
+            "msg_local": torch.zeros(msg, dtype=torch.float32, device="cuda"),
+            "msg_all": torch.zeros((g, msg), dtype=torch.float32, device="cuda"),
+        }
         sw.dp = dp
         return dp
 
     def build_sparse_sources(self, model, sw):
         """Same structure as the single-GPU source list, but over the all-gathered buffers."""
+        from pkg import _native as N
+
+        torch = N.require_cuda()
         dp = self._ensure(sw)
+        g, b = self.world, sw.batch
+        msg = dp["msg_all"].shape[1]
+        if g * msg * 4 >= 2 ** 31:
+            raise ValueError("data-parallel message too large for the int32 row stride of tt_sparse_job")
+        # gradient row (rank r, position i) of a tower lives at msg_all[r, i * row_w + col0 ...]: viewed as a (g * b) x e block it
+        # has a constant row stride only inside one rank, so every rank's block is gathered into a rank-major copy first
+        dp["rows_all"] = torch.zeros((g * b, dp["row_w"]), dtype=torch.float32, device="cuda")
         srcs = []
-        for tower, tws, ids_all, dx_all in dp["towers"]:
+        slot = 0
+        col0 = 0
+        for ti, (tower, tws) in enumerate(dp["towers"]):
             il = tower.input_layer
             per_table = {}
-            for (f, t, col, w), ga in zip(il.blocks, ids_all):
+            for bi, (f, t, col, w) in enumerate(il.blocks):
                 if t is None:
                     continue
-                per_table.setdefault(f.name, (t, []))[1].append((ga, dx_all.data_ptr() + 4 * col, il.ld))
+                ids = dp["ids_all"][slot]
+                slot += 1
+                per_table.setdefault(f.name, (t, []))[1].append((ids, dp["rows_all"].data_ptr() + 4 * (col0 + col), dp["row_w"]))
             srcs.extend(per_table.values())
+            col0 += dp["lds"][ti]
         return srcs
 
-    # ---- exchanges (called from TwoTowerModel._launch_step) ---------------------------------------------
+    # ---- exchanges (called from TwoTowerModel.train_step) ------------------------------------------------
     def gather_ids(self, model, sw):
         dp = self._ensure(sw)
-        for tower, tws, ids_all, _ in dp["towers"]:
-            for buf, ga in zip(tws.bufs, ids_all):
-                if ga is not None:
-                    allgather_into(ga, buf, self.group)
+        for k, (ti, bi) in enumerate(dp["id_slots"]):
+            dp["ids_local"][k].copy_(dp["towers"][ti][1].bufs[bi])
+        allgather_into(dp["ids_gathered"].view(self.world * dp["ids_local"].shape[0], -1), dp["ids_local"], self.group)
+        g, n_id, b = dp["ids_gathered"].shape
+        dp["ids_all"].view(n_id, g, b).copy_(dp["ids_gathered"].permute(1, 0, 2))
 
     def reduce_dense_and_gather_rows(self, model, sw):
+        import torch
+
         dp = self._ensure(sw)
-        used = model._store.used
-        if used:
-            allreduce_sum_(model._store.grads[:used], self.group)
-        for tower, tws, _, dx_all in dp["towers"]:
-            allgather_into(dx_all, tws.dx, self.group)
+        g, b, row_w, n_dense = self.world, sw.batch, dp["row_w"], dp["n_dense"]
+        rows_local = dp["msg_local"][: b * row_w].view(b, row_w)
+        col0 = 0
+        for ti, (tower, tws) in enumerate(dp["towers"]):
+            rows_local[:, col0:col0 + dp["lds"][ti]].copy_(tws.dx)
+            col0 += dp["lds"][ti]
+        if n_dense:
+            dp["msg_local"][b * row_w:].copy_(model._store.grads[:n_dense])
+        allgather_into(dp["msg_all"], dp["msg_local"], self.group)
+        dp["rows_all"].view(g, b * row_w).copy_(dp["msg_all"][:, : b * row_w])
+        if n_dense:
+            torch.sum(dp["msg_all"][:, b * row_w:], dim=0, out=model._store.grads[:n_dense])   # fixed reduction order
 
 
 def make_sharded_index(k: int, query_model, id_candidate_pairs: Iterable, group=None):

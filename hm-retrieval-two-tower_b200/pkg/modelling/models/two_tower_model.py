@@ -221,17 +221,23 @@ class TwoTowerModel(AbstractKerasModel):
         else:
             sw.bias_from_strings = False
 
-    def _launch_step(self, sw: _StepWorkspace) -> None:
+    # A step is four phases; data parallel runs the two exchanges eagerly and replays one CUDA graph for each compute phase:
+    #   pre   (dist) all-gather of the batch ids            -- NCCL
+    #   A     id sort || towers fwd, softmax fwd+bwd, towers bwd (three streams, forked and joined inside)
+    #   mid   (dist) dense-gradient sum + all-gather of the embedding-gradient rows -- NCCL
+    #   B     dense optimizer, de-duplicated sparse optimizer
+    def _phase_pre(self, sw: _StepWorkspace) -> None:
+        if self.dist is not None:
+            self.dist.gather_ids(self, sw)
+
+    def _phase_a(self, sw: _StepWorkspace) -> None:
         torch = N.require_cuda()
         lib = N.load()
-        opt = self.optimizer
         b, e = sw.batch, self.joint_embedding_size
         main = torch.cuda.current_stream()
-        # fork: the id sort depends on the inputs only
+        # fork: the id sort depends on the (gathered) ids only
         sw.side.wait_stream(main)
         with torch.cuda.stream(sw.side):
-            if self.dist is not None:
-                self.dist.gather_ids(self, sw)
             N.check(lib.tt_sparse_sort(sw.jobs, sw.njobs, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), N.stream_ptr()), "tt_sparse_sort")
         st = N.stream_ptr()
         # the two towers are independent until the logits: candidate side on its own stream
@@ -262,8 +268,16 @@ class TwoTowerModel(AbstractKerasModel):
         with torch.cuda.stream(sw.cand):
             self.candidate_tower.backward_ws(sw.c, sw.dc)
         main.wait_stream(sw.cand)
+        main.wait_stream(sw.side)  # join
+
+    def _phase_mid(self, sw: _StepWorkspace) -> None:
         if self.dist is not None:
             self.dist.reduce_dense_and_gather_rows(self, sw)
+
+    def _phase_b(self, sw: _StepWorkspace) -> None:
+        lib = N.load()
+        opt = self.optimizer
+        st = N.stream_ptr()
         n_dense = self._store.used
         if n_dense:
             ds = self._opt_state["dense"]
@@ -274,13 +288,18 @@ class TwoTowerModel(AbstractKerasModel):
                 N.check(lib.tt_dense_adam(self._store.params.data_ptr(), ds[0].data_ptr(), ds[1].data_ptr(),
                                           self._store.grads.data_ptr(), n_dense, sw.lr_t, opt.beta_1, opt.beta_2, opt.epsilon, st),
                         "tt_dense_adam")
-        main.wait_stream(sw.side)  # join
         if isinstance(opt, Adagrad):
             N.check(lib.tt_sparse_adagrad(sw.jobs, sw.njobs, opt.learning_rate, opt.epsilon, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), st),
                     "tt_sparse_adagrad")
         else:
             N.check(lib.tt_sparse_adam(sw.jobs, sw.njobs, sw.lr_t, opt.beta_1, opt.beta_2, opt.epsilon, sw.sp_ws.data_ptr(),
                                        sw.sp_ws.numel(), st), "tt_sparse_adam")
+
+    def _launch_step(self, sw: _StepWorkspace) -> None:
+        self._phase_pre(sw)
+        self._phase_a(sw)
+        self._phase_mid(sw)
+        self._phase_b(sw)
 
     def _tc_ok(self) -> bool:
         return bool(N.load().tt_tc_available(0, self.joint_embedding_size))
@@ -295,7 +314,7 @@ class TwoTowerModel(AbstractKerasModel):
         sw = self._step_ws(batch)
         self._stage(sw, data)
         self.optimizer.iterations += 1
-        graph_ok = self.use_cuda_graph and not isinstance(self.optimizer, Adam) and not sw.bias_from_strings and self.dist is None
+        graph_ok = self.use_cuda_graph and not isinstance(self.optimizer, Adam) and not sw.bias_from_strings
         if isinstance(self.optimizer, Adam):
             sw.lr_t = self.optimizer.lr_t(self.optimizer.iterations)
         if graph_ok:
@@ -304,13 +323,31 @@ class TwoTowerModel(AbstractKerasModel):
                 torch.cuda.current_stream().synchronize()
                 sw.graph = "pending"
             elif sw.graph == "pending":
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._launch_step(sw)
-                sw.graph = g
-                g.replay()
+                if self.dist is None:   # the whole step is one graph
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._launch_step(sw)
+                    sw.graph = (g,)
+                    g.replay()
+                else:                   # data parallel: the NCCL exchanges stay eager between two captured compute phases
+                    self._phase_pre(sw)
+                    ga = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(ga):
+                        self._phase_a(sw)
+                    ga.replay()
+                    self._phase_mid(sw)
+                    gb = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gb):
+                        self._phase_b(sw)
+                    gb.replay()
+                    sw.graph = (ga, gb)
+            elif len(sw.graph) == 1:
+                sw.graph[0].replay()
             else:
-                sw.graph.replay()
+                self._phase_pre(sw)
+                sw.graph[0].replay()
+                self._phase_mid(sw)
+                sw.graph[1].replay()
         else:
             self._launch_step(sw)
         return {"loss": sw.loss[0]}
