@@ -17,6 +17,8 @@ int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const 
                         int d, float* G, int ldg, float* ws, cudaStream_t st);
 int softmax_bwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E, int off, int which,
                    float* G0, int ldg0, float* G1, int ldg1, float* ws, cudaStream_t st);
+int softmax_step_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
+                    float* dQ, int lddq, float* dC, int lddc, float* ws, cudaStream_t st);
 int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, float* Z, int ldz, cudaStream_t st);
 size_t softmax_tc_workspace_bytes(int Bq, int Bc, int E);
 void debug_tc(void* trace, int max_splits);
@@ -113,6 +115,24 @@ int tt_inbatch_softmax_bwd(const float* Q, int ldq, const float* C, int ldc, con
     rc = softmax_bwd_pass_simt(Q, ldq, C, ldc, lse, col_bias, Bq, Bc, E, diag_offset, dQ, lddq, st);
     if (rc) return rc;
     return softmax_bwd_pass_simt(C, ldc, Q, ldq, col_bias, lse, Bc, Bq, E, -diag_offset, dC, lddc, st);
+}
+
+/* forward + backward of one training step in one call (loss, lse, dQ, dC): the tensor-core path prepares its operand
+ * copies once and runs 5 launches; the exact path is the forward followed by the backward. */
+int tt_inbatch_softmax_step(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, int Bq, int Bc, int E, int diag_offset,
+                            float* lse, float* loss, float* dQ, int lddq, float* dC, int lddc, void* ws, size_t ws_bytes, int impl, void* stream) {
+    TT_REQUIRE(Q && C && lse && loss && dQ && dC, "tt_inbatch_softmax_step: null pointer");
+    TT_REQUIRE(Bq >= 0 && Bc >= 0 && E >= 1 && ldq >= E && ldc >= E && lddq >= E && lddc >= E, "tt_inbatch_softmax_step: bad shape");
+    TT_REQUIRE(diag_offset >= 0 && (Bq == 0 || diag_offset + Bq <= Bc), "tt_inbatch_softmax_step: bad diag_offset");
+    TT_REQUIRE(ws && ws_bytes >= tt_softmax_workspace_bytes(Bq, Bc, E), "tt_inbatch_softmax_step: workspace too small");
+    int use = Bq == 0 ? TT_IMPL_SIMT : pick_impl(impl, ldq, ldc, E, Q, C, "tt_inbatch_softmax_step");
+    if (use < 0) return use;
+    if (use == TT_IMPL_TC)
+        return softmax_step_tc(Q, ldq, C, ldc, col_bias, Bq, Bc, E, diag_offset, lse, loss, dQ, lddq, dC, lddc, reinterpret_cast<float*>(ws),
+                               as_stream(stream));
+    int rc = tt_inbatch_softmax_fwd(Q, ldq, C, ldc, col_bias, Bq, Bc, E, diag_offset, lse, loss, ws, ws_bytes, use, stream);
+    if (rc) return rc;
+    return tt_inbatch_softmax_bwd(Q, ldq, C, ldc, col_bias, lse, Bq, Bc, E, diag_offset, dQ, lddq, dC, lddc, ws, ws_bytes, use, stream);
 }
 
 /* one half of the backward: which = 0 -> dQ (G is (Bq,E)), which = 1 -> dC (G is (Bc,E)).  The halves are

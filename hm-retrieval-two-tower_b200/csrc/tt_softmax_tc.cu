@@ -210,24 +210,68 @@ static int launch_streamk(const SkMaps& maps, const SkParams& p, int grid, cudaS
     return TT_OK;
 }
 
-// per-row merge of the forward partials, slot order then warp-half order
-__global__ void fwd_combine_sk_kernel(const float* __restrict__ m2, const float* __restrict__ l, const float* __restrict__ zd, int nR, int n_tiles,
-                                      int units, int G, int halves, float* __restrict__ lse, float* __restrict__ rowloss) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nR) return;
-    const int first = (r >> 7) * n_tiles;
-    const int parts = (sk_owner(first + n_tiles - 1, units, G) - sk_owner(first, units, G) + 1) * halves;
-    float M = -CUDART_INF_F;
-    for (int s = 0; s < parts; ++s) M = fmaxf(M, m2[(int64_t)s * nR + r]);
-    float L = 0.f;
-    for (int s = 0; s < parts; ++s) {
-        float ms = m2[(int64_t)s * nR + r];
-        if (ms > -CUDART_INF_F) L += l[(int64_t)s * nR + r] * exp2f(ms - M);
+// per-row merge of the forward partials, slot order then warp-half order.  Also: the scaled, zero-padded lse column term
+// of the dC pass (c2_lse, optional), and the loss = sum of the row losses -- every block leaves its partial sum (double),
+// the last block to finish adds them in block order (a fixed order: deterministic) and re-arms the counter.
+__global__ void __launch_bounds__(256) fwd_combine_sk_kernel(const float* __restrict__ m2, const float* __restrict__ l, const float* __restrict__ zd,
+                                                             int nR, int n_tiles, int units, int G, int halves, float* __restrict__ lse,
+                                                             float* __restrict__ rowloss, float* __restrict__ c2_lse, int c2_pad,
+                                                             double* __restrict__ block_sums, unsigned int* __restrict__ counter,
+                                                             float* __restrict__ loss) {
+    __shared__ double s_sum[256];
+    __shared__ bool s_last;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    double mine = 0.0;
+    if (r < nR) {
+        const int first = (r >> 7) * n_tiles;
+        const int parts = (sk_owner(first + n_tiles - 1, units, G) - sk_owner(first, units, G) + 1) * halves;
+        float M = -CUDART_INF_F;
+        for (int s = 0; s < parts; ++s) M = fmaxf(M, m2[(int64_t)s * nR + r]);
+        float L = 0.f;
+        for (int s = 0; s < parts; ++s) {
+            float ms = m2[(int64_t)s * nR + r];
+            if (ms > -CUDART_INF_F) L += l[(int64_t)s * nR + r] * exp2f(ms - M);
+        }
+        const float v = (M + log2f(L)) * 0.6931471805599453f;
+        lse[r] = v;
+        const float rl = v - zd[r];
+        rowloss[r] = rl;
+        mine = (double)rl;
+        if (c2_lse) c2_lse[r] = v * kLog2e;
+    } else if (c2_lse && r < c2_pad) {
+        c2_lse[r] = 0.f;
     }
-    float v = (M + log2f(L)) * 0.6931471805599453f;
-    lse[r] = v;
-    rowloss[r] = v - zd[r];
+    s_sum[threadIdx.x] = mine;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        block_sums[blockIdx.x] = s_sum[0];
+        __threadfence();
+        s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += reinterpret_cast<volatile double*>(block_sums)[b];
+        loss[0] = (float)t;
+        *counter = 0u;
+    }
 }
+
+// operand copies and column terms prepared once for a forward + backward pair (tt_inbatch_softmax_step)
+struct SkPrepared {
+    const __half* Qh; const __half* Ch;    // fp16 row-major copies (E >= 64), else null
+    const __half* Qt; const __half* Ct;    // fp16 transposed copies (E x ld)
+    int ldqt, ldct;
+    const float* c2_bias;                  // bias * log2e, zero padded
+    float* c2_lse;                         // lse * log2e, zero padded to c2_lse_pad (written by the forward's combine kernel)
+    int c2_lse_pad;
+    double* block_sums; unsigned int* counter;   // loss reduction scratch (counter zeroed by the prep kernel)
+};
 
 struct SkSide {   // one backward pass
     const float* R; int ldr;
@@ -244,12 +288,13 @@ struct PrepItem {   // one matrix X (n x E, leading dimension ld) and/or one per
     int tblocks_x, tblocks;   // 32x32 tiles: per row of tiles, total (0 when no copy is wanted)
     int cblocks;              // scale/pad blocks of 256
 };
-struct PrepArgs { PrepItem s[3]; int n; int E; };
+struct PrepArgs { PrepItem s[3]; int n; int E; unsigned int* zero_me; };
 // one launch: fp16 copies (row-major: operands of the first MMA; transposed: B tiles of the second MMA) and scaled,
 // padded column terms, for every pass
 __global__ void __launch_bounds__(256) sk_prep_kernel(const PrepArgs a) {
     __shared__ float tile[32][33];
     int b = blockIdx.x;
+    if (b == 0 && threadIdx.x == 0 && a.zero_me) *a.zero_me = 0u;
     for (int i = 0; i < a.n; ++i) {
         const PrepItem& sd = a.s[i];
         if (b < sd.tblocks) {
@@ -332,25 +377,33 @@ static size_t bwd_sk_floats(int n_sides, const int* nR, const int* nT, int E) {
     return f + 512;
 }
 
-size_t softmax_tc_workspace(int Bq, int Bc, int E) {
+size_t softmax_step_floats(int Bq, int Bc, int E);
+static size_t sk_fwd_bytes(int Bq, int Bc, int E) {
     size_t rows = (size_t)(Bq > Bc ? Bq : Bc);
-    // forward: m2, l partials (slots x 2 halves) + zdiag + rowloss + scaled column term
+    // forward: m2, l partials (slots x halves) + zdiag + rowloss + scaled column term + fp16 copies + loss scratch
     int mt = (int)ceil_div(Bq, 128), nt = (int)ceil_div(Bc, kFwdBN);
     SkPlan pf = sk_plan(1, &mt, &nt);
     size_t seg = align_up(rows * sizeof(float), 256);
-    size_t fwd = (2 * kFwdHalves * (size_t)pf.slots[0] + 2) * seg + align_up(((size_t)nt * kFwdBN + 64) * sizeof(float), 256) +
-                 align_up((size_t)Bq * E * 2, 256) + align_up((size_t)Bc * E * 2, 256) + 2048;
+    return (2 * kFwdHalves * (size_t)pf.slots[0] + 2) * seg + align_up(((size_t)nt * kFwdBN + 64) * sizeof(float), 256) +
+           align_up((size_t)Bq * E * 2, 256) + align_up((size_t)Bc * E * 2, 256) + align_up(((size_t)ceil_div(rows, 256) + 64) * 8, 256) + 4096;
+}
+static size_t sk_bwd_bytes(int Bq, int Bc, int E) {
     // backward: both passes at once, or one pass alone (tt_inbatch_softmax_bwd_one)
     int nR[2] = {Bq, Bc}, nT[2] = {Bc, Bq};
     size_t both = bwd_sk_floats(2, nR, nT, E) * sizeof(float);
     int nRq[1] = {Bq}, nTq[1] = {Bc}, nRc[1] = {Bc}, nTc[1] = {Bq};
     size_t one_q = bwd_sk_floats(1, nRq, nTq, E) * sizeof(float), one_c = bwd_sk_floats(1, nRc, nTc, E) * sizeof(float);
     size_t bwd = both > one_q ? both : one_q;
-    bwd = bwd > one_c ? bwd : one_c;
+    return align_up(bwd > one_c ? bwd : one_c, 256);
+}
+size_t softmax_tc_workspace(int Bq, int Bc, int E) {
+    size_t rows = (size_t)(Bq > Bc ? Bq : Bc);
+    size_t fwd = sk_fwd_bytes(Bq, Bc, E), bwd = sk_bwd_bytes(Bq, Bc, E);
+    size_t step = fwd + bwd + softmax_step_floats(Bq, Bc, E) * sizeof(float);      // tt_inbatch_softmax_step keeps all three regions live
     // the split-launch kernels (debug / legacy path)
     size_t a = bwd_pass_floats(Bq, Bc, E) * sizeof(float), b = bwd_pass_floats(Bc, Bq, E) * sizeof(float);
     size_t legacy_fwd = (4 * (size_t)kMaxSplits + 4) * align_up(rows * sizeof(float), 256) + 2048;
-    size_t m = fwd > bwd ? fwd : bwd;
+    size_t m = step;
     m = m > a ? m : a;
     m = m > b ? m : b;
     m = m > legacy_fwd ? m : legacy_fwd;
@@ -377,8 +430,8 @@ bool softmax_tc_supported(int ldq, int ldc, int E, const void* Q, const void* C)
     return true;
 }
 
-int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
-                   float* ws, cudaStream_t st) {
+static int softmax_fwd_sk(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
+                          float* ws, cudaStream_t st, const SkPrepared* pre) {
     int mt = (int)ceil_div(Bq, 128), nt = (int)ceil_div(Bc, kFwdBN);
     SkPlan pl = sk_plan(1, &mt, &nt);
     SkMaps maps;
@@ -397,13 +450,20 @@ int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float
     const bool h16 = E >= 64;                              // fp16 operand tiles (see SkCfg)
     __half* Qh = reinterpret_cast<__half*>(c2 + align_up((size_t)nt * kFwdBN + 64, 64));
     __half* Ch = Qh + align_up((size_t)Bq * E, 128);
-    PrepArgs pa{};
-    pa.E = E;
-    int blocks = 0;
-    blocks += prep_item(pa.s[pa.n++], C, ldc, Bc, E, h16 ? Ch : nullptr, nullptr, 0, bias, c2, nt * kFwdBN);
-    if (h16) blocks += prep_item(pa.s[pa.n++], Q, ldq, Bq, E, Qh, nullptr, 0, nullptr, nullptr, 0);
-    sk_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(pa);
-    TT_LAUNCH_OK("sk_prep_kernel");
+    double* block_sums = reinterpret_cast<double*>(Ch + align_up((size_t)Bc * E, 128));
+    unsigned int* counter = reinterpret_cast<unsigned int*>(block_sums + align_up((size_t)ceil_div(Bq, 256), 32));
+    if (pre) {
+        Qh = const_cast<__half*>(pre->Qh); Ch = const_cast<__half*>(pre->Ch); c2 = const_cast<float*>(pre->c2_bias);
+        block_sums = pre->block_sums; counter = pre->counter;
+    } else {
+        PrepArgs pa{};
+        pa.E = E; pa.zero_me = counter;
+        int blocks = 0;
+        blocks += prep_item(pa.s[pa.n++], C, ldc, Bc, E, h16 ? Ch : nullptr, nullptr, 0, bias, c2, nt * kFwdBN);
+        if (h16) blocks += prep_item(pa.s[pa.n++], Q, ldq, Bq, E, Qh, nullptr, 0, nullptr, nullptr, 0);
+        sk_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(pa);
+        TT_LAUNCH_OK("sk_prep_kernel");
+    }
     if (h16) {
         rc = make_tmap_2d_f16(&maps.r[0], Qh, Bq, E, E, 128);
         if (rc) return rc;
@@ -421,13 +481,21 @@ int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float
         default: rc = launch_streamk<kFwd, 128, kFwdBN, true>(maps, p, pl.grid, st, "streamk_kernel<fwd,128>"); break;
     }
     if (rc) return rc;
-    fwd_combine_sk_kernel<<<(unsigned)ceil_div(Bq, 256), 256, 0, st>>>(m2, l, zd, Bq, nt, pl.units, pl.grid, kFwdHalves, lse, rowloss);
+    const int c2_pad = pre ? pre->c2_lse_pad : 0;
+    const int rows_c = c2_pad > Bq ? c2_pad : Bq;
+    fwd_combine_sk_kernel<<<(unsigned)ceil_div(rows_c, 256), 256, 0, st>>>(m2, l, zd, Bq, nt, pl.units, pl.grid, kFwdHalves, lse, rowloss,
+                                                                            pre ? pre->c2_lse : nullptr, c2_pad, block_sums, counter, loss);
     TT_LAUNCH_OK("fwd_combine_sk_kernel");
-    return sum_rows_launch(rowloss, Bq, loss, st);
+    return TT_OK;
+}
+
+int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
+                   float* ws, cudaStream_t st) {
+    return softmax_fwd_sk(Q, ldq, C, ldc, bias, Bq, Bc, E, off, lse, loss, ws, st, nullptr);
 }
 
 // one launch for `n` backward passes (dQ and dC, or one of them)
-int softmax_bwd_sk(const SkSide* sides, int n, int E, float* ws, cudaStream_t st) {
+int softmax_bwd_sk(const SkSide* sides, int n, int E, float* ws, cudaStream_t st, const SkPrepared* pre = nullptr) {
     const int bn = sk_bwd_bn(E);
     int mt[2] = {0, 0}, nt[2] = {0, 0};
     for (int i = 0; i < n; ++i) { mt[i] = (int)ceil_div(sides[i].nR, 128); nt[i] = (int)ceil_div(sides[i].nT, bn); }
@@ -452,12 +520,20 @@ int softmax_bwd_sk(const SkSide* sides, int n, int E, float* ws, cudaStream_t st
         Tt[i] = reinterpret_cast<__half*>(cur); ldtt[i] = (int)sk_ldtt(sd.nT); cur += align_up((size_t)E * ldtt[i] / 2, 64);
         c2[i] = cur; cur += align_up((size_t)nt[i] * bn, 64);
         if (h16) { Th[i] = reinterpret_cast<__half*>(cur); cur += align_up((size_t)sd.nT * E / 2, 64); }
-        prep_blocks += prep_item(pa.s[pa.n++], sd.T, sd.ldt, sd.nT, E, Th[i], Tt[i], ldtt[i], sd.colv, c2[i], nt[i] * bn);
+        if (pre) {   // side 0 streams C (column term: bias), side 1 streams Q (column term: lse)
+            Th[i] = const_cast<__half*>(i == 0 ? pre->Ch : pre->Qh);
+            Tt[i] = const_cast<__half*>(i == 0 ? pre->Ct : pre->Qt);
+            ldtt[i] = i == 0 ? pre->ldct : pre->ldqt;
+            c2[i] = i == 0 ? const_cast<float*>(pre->c2_bias) : pre->c2_lse;
+        } else {
+            prep_blocks += prep_item(pa.s[pa.n++], sd.T, sd.ldt, sd.nT, E, Th[i], Tt[i], ldtt[i], sd.colv, c2[i], nt[i] * bn);
+        }
     }
     // the resident operand of a pass is the streamed operand of the other one; a pass running alone converts its own
     __half* Rh[2] = {nullptr, nullptr};
     if (h16) {
-        if (n == 2) { Rh[0] = Th[1]; Rh[1] = Th[0]; }
+        if (pre) { Rh[0] = const_cast<__half*>(pre->Qh); Rh[1] = const_cast<__half*>(pre->Ch); }
+        else if (n == 2) { Rh[0] = Th[1]; Rh[1] = Th[0]; }
         else {
             Rh[0] = reinterpret_cast<__half*>(cur); cur += align_up((size_t)sides[0].nR * E / 2, 64);
             prep_blocks += prep_item(pa.s[pa.n++], sides[0].R, sides[0].ldr, sides[0].nR, E, Rh[0], nullptr, 0, nullptr, nullptr, 0);
@@ -487,8 +563,10 @@ int softmax_bwd_sk(const SkSide* sides, int n, int E, float* ws, cudaStream_t st
         unit0 += mt[i] * nt[i];
     }
     if (pl.units == 0) return TT_OK;
-    sk_prep_kernel<<<(unsigned)prep_blocks, 256, 0, st>>>(pa);
-    TT_LAUNCH_OK("sk_prep_kernel");
+    if (!pre) {
+        sk_prep_kernel<<<(unsigned)prep_blocks, 256, 0, st>>>(pa);
+        TT_LAUNCH_OK("sk_prep_kernel");
+    }
     int rc;
     switch (E) {
         case 32: rc = launch_streamk<kBwd, 32, 128, false>(maps, p, pl.grid, st, "streamk_kernel<bwd,32>"); break;
@@ -499,6 +577,55 @@ int softmax_bwd_sk(const SkSide* sides, int n, int E, float* ws, cudaStream_t st
     bwd_reduce_sk_kernel<<<(unsigned)ceil_div(red_items, 256), 256, 0, st>>>(ra);
     TT_LAUNCH_OK("bwd_reduce_sk_kernel");
     return TT_OK;
+}
+
+// forward + backward of one training step: ONE prep launch (fp16 row-major and transposed copies of Q and C, scaled bias),
+// forward, combine (lse, loss, scaled lse column term), backward (dQ and dC), reduction -- 5 launches.
+size_t tc::softmax_step_floats(int Bq, int Bc, int E) {
+    const int bn = sk_bwd_bn(E);
+    size_t f = 0;
+    f += 2 * align_up((size_t)Bq * E / 2, 64) + 2 * align_up((size_t)Bc * E / 2, 64);                   // Qh, Ch
+    f += align_up((size_t)E * sk_ldtt(Bq) / 2, 64) + align_up((size_t)E * sk_ldtt(Bc) / 2, 64);         // Qt, Ct
+    f += align_up((size_t)Bc + 512, 64) + align_up((size_t)Bq + 512, 64);                               // c2_bias, c2_lse (padded)
+    f += align_up(2 * ((size_t)ceil_div(Bq + 512, 256) + 64), 64) + 64;                                 // block sums (double), counter
+    (void)bn;
+    return f;
+}
+
+int softmax_step_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
+                    float* dQ, int lddq, float* dC, int lddc, float* ws, cudaStream_t st) {
+    const size_t ws_floats_fwd = sk_fwd_bytes(Bq, Bc, E) / sizeof(float), ws_floats_bwd = sk_bwd_bytes(Bq, Bc, E) / sizeof(float);
+    const bool h16 = E >= 64;
+    const int bn = sk_bwd_bn(E);
+    // workspace: [forward region | backward region | prepared operands]
+    float* ws_fwd = ws;
+    float* ws_bwd = ws + ws_floats_fwd;
+    float* cur = ws_bwd + ws_floats_bwd;
+    SkPrepared pre{};
+    __half* Qh = reinterpret_cast<__half*>(cur); cur += align_up((size_t)Bq * E / 2, 64);
+    __half* Ch = reinterpret_cast<__half*>(cur); cur += align_up((size_t)Bc * E / 2, 64);
+    pre.ldqt = (int)sk_ldtt(Bq); pre.ldct = (int)sk_ldtt(Bc);
+    __half* Qt = reinterpret_cast<__half*>(cur); cur += align_up((size_t)E * pre.ldqt / 2, 64);
+    __half* Ct = reinterpret_cast<__half*>(cur); cur += align_up((size_t)E * pre.ldct / 2, 64);
+    float* c2_bias = cur; cur += align_up((size_t)Bc + 512, 64);
+    float* c2_lse = cur; cur += align_up((size_t)Bq + 512, 64);
+    double* block_sums = reinterpret_cast<double*>(cur); cur += align_up(2 * ((size_t)ceil_div(Bq + 512, 256) + 64), 64);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(cur);
+    const int pad_bias = (int)(ceil_div(Bc, 256) * 256);                 // covers the forward (BN 256) and the dQ pass (BN <= 128)
+    const int pad_lse = (int)(ceil_div(Bq, bn) * bn);
+    PrepArgs pa{};
+    pa.E = E; pa.zero_me = counter;
+    int blocks = 0;
+    blocks += prep_item(pa.s[pa.n++], C, ldc, Bc, E, h16 ? Ch : nullptr, Ct, pre.ldct, bias, c2_bias, pad_bias);
+    blocks += prep_item(pa.s[pa.n++], Q, ldq, Bq, E, h16 ? Qh : nullptr, Qt, pre.ldqt, nullptr, nullptr, 0);
+    sk_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(pa);
+    TT_LAUNCH_OK("sk_prep_kernel");
+    pre.Qh = h16 ? Qh : nullptr; pre.Ch = h16 ? Ch : nullptr; pre.Qt = Qt; pre.Ct = Ct;
+    pre.c2_bias = c2_bias; pre.c2_lse = c2_lse; pre.c2_lse_pad = pad_lse; pre.block_sums = block_sums; pre.counter = counter;
+    int rc = softmax_fwd_sk(Q, ldq, C, ldc, bias, Bq, Bc, E, off, lse, loss, ws_fwd, st, &pre);
+    if (rc) return rc;
+    SkSide sides[2] = {SkSide{Q, ldq, C, ldc, lse, bias, Bq, Bc, off, dQ, lddq}, SkSide{C, ldc, Q, ldq, bias, lse, Bc, Bq, -off, dC, lddc}};
+    return softmax_bwd_sk(sides, 2, E, ws_bwd, st, &pre);
 }
 
 // (Q, C) backward: which = 0 dQ only, 1 dC only, 2 both (G0 = dQ, G1 = dC)

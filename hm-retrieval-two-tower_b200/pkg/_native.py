@@ -68,6 +68,8 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "tt_inbatch_softmax_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "tt_inbatch_softmax_step": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_int, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "tt_inbatch_softmax_bwd_one": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                            c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "tt_logits": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,

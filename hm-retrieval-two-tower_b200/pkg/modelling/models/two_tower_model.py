@@ -54,7 +54,6 @@ class _StepWorkspace:
         self.dq = torch.zeros((batch, e), **f32)
         self.dc = torch.zeros((batch, e), **f32)
         self.sm_ws = torch.empty(int(lib.tt_softmax_workspace_bytes(batch, batch, e)), dtype=torch.uint8, device="cuda")
-        self.sm_ws2 = torch.empty_like(self.sm_ws)    # the candidate-side half of the backward runs concurrently
         self.bias_feat = None
         if model.logq_correction:
             cid_buf = None
@@ -257,12 +256,11 @@ class TwoTowerModel(AbstractKerasModel):
         use_tc = self.impl != N.TT_IMPL_SIMT and self._tc_ok()
         qa, ca = (q32, c32) if use_tc else (q, c)
         impl = N.TT_IMPL_TC if use_tc else N.TT_IMPL_SIMT
-        N.check(lib.tt_inbatch_softmax_fwd(qa.data_ptr(), e, ca.data_ptr(), e, bias, b, b, e, 0, sw.lse.data_ptr(),
-                                           sw.loss.data_ptr(), sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st), "tt_inbatch_softmax_fwd")
-        # backward: ONE persistent launch covers the dQ and the dC pass; then dQ -> query tower on the main stream,
-        # dC -> candidate tower on the candidate stream
-        N.check(lib.tt_inbatch_softmax_bwd(qa.data_ptr(), e, ca.data_ptr(), e, bias, sw.lse.data_ptr(), b, b, e, 0, sw.dq.data_ptr(), e,
-                                           sw.dc.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st), "tt_inbatch_softmax_bwd")
+        # loss, lse, dQ and dC in one call: one prep launch, forward, combine, ONE persistent launch for the dQ and the dC
+        # pass, reduction; then dQ -> query tower on the main stream, dC -> candidate tower on the candidate stream
+        N.check(lib.tt_inbatch_softmax_step(qa.data_ptr(), e, ca.data_ptr(), e, bias, b, b, e, 0, sw.lse.data_ptr(), sw.loss.data_ptr(),
+                                            sw.dq.data_ptr(), e, sw.dc.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st),
+                "tt_inbatch_softmax_step")
         sw.cand.wait_stream(main)
         self.query_tower.backward_ws(sw.q, sw.dq)
         with torch.cuda.stream(sw.cand):

@@ -115,6 +115,11 @@ int tt_inbatch_softmax_fwd(const float* Q, int ldq, const float* C, int ldc, con
 int tt_inbatch_softmax_bwd(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, const float* lse,
                            int Bq, int Bc, int E, int diag_offset, float* dQ, int lddq, float* dC, int lddc,
                            void* ws, size_t ws_bytes, int impl, void* stream);
+/* Forward + backward of one training step in one call: loss, lse, dQ and dC (two_tower_model.py:113-124 minus the optimizer).
+ * Same arguments as the two calls above; the tensor-core path prepares its operand copies once (5 launches in all). */
+int tt_inbatch_softmax_step(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, int Bq, int Bc, int E,
+                            int diag_offset, float* lse, float* loss, float* dQ, int lddq, float* dC, int lddc, void* ws,
+                            size_t ws_bytes, int impl, void* stream);
 /* One half of the backward (which = 0: dQ into G (Bq,E); which = 1: dC into G (Bc,E)).  The halves are
  * independent: given separate workspaces they may run concurrently on two streams. */
 int tt_inbatch_softmax_bwd_one(const float* Q, int ldq, const float* C, int ldc, const float* col_bias, const float* lse,

@@ -244,3 +244,36 @@ def test_brute_force_index_uses_tc_and_matches_exact(lib, T):
     assert np.array_equal(got, index(x))
     _, want = O.index_topk(table[x["id"].reshape(-1)], c, 100)
     assert np.array_equal(got, ids[want])
+
+
+@pytest.mark.parametrize("Bq,Bc,E,off", [(1000, 1000, 64, 0), (257, 300, 32, 5), (130, 777, 128, 3)])
+def test_softmax_step_equals_fwd_then_bwd(lib, T, Bq, Bc, E, off):
+    """tt_inbatch_softmax_step (shared prep, fused loss sum) gives bit-identical lse/dQ/dC to the two separate calls and the same loss."""
+    from pkg import _native as N
+
+    rng = np.random.default_rng(11)
+    q = np.maximum(rng.standard_normal((Bq, E)) * 0.3, 0).astype(np.float32)
+    c = np.maximum(rng.standard_normal((Bc, E)) * 0.3, 0).astype(np.float32)
+    p = (rng.random(Bc) * 0.01 + 1e-5).astype(np.float32)
+    dq_, dc_ = T.from_numpy(q).cuda(), T.from_numpy(c).cuda()
+    q32, c32 = T.empty_like(dq_), T.empty_like(dc_)
+    N.check(lib.tt_round_tf32(dq_.data_ptr(), E, q32.data_ptr(), E, Bq, E, stream()))
+    N.check(lib.tt_round_tf32(dc_.data_ptr(), E, c32.data_ptr(), E, Bc, E, stream()))
+    bias = T.log(T.from_numpy(p).cuda())
+    ws = T.empty(int(lib.tt_softmax_workspace_bytes(Bq, Bc, E)), dtype=T.uint8, device="cuda")
+    out = {}
+    for name in ("sep", "step"):
+        lse = T.zeros(Bq, device="cuda"); loss = T.zeros(1, device="cuda")
+        gq = T.zeros((Bq, E), device="cuda"); gc = T.zeros((Bc, E), device="cuda")
+        if name == "sep":
+            N.check(lib.tt_inbatch_softmax_fwd(q32.data_ptr(), E, c32.data_ptr(), E, bias.data_ptr(), Bq, Bc, E, off, lse.data_ptr(), loss.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), N.TT_IMPL_TC, stream()))
+            N.check(lib.tt_inbatch_softmax_bwd(q32.data_ptr(), E, c32.data_ptr(), E, bias.data_ptr(), lse.data_ptr(), Bq, Bc, E, off, gq.data_ptr(), E,
+                                               gc.data_ptr(), E, ws.data_ptr(), ws.numel(), N.TT_IMPL_TC, stream()))
+        else:
+            N.check(lib.tt_inbatch_softmax_step(q32.data_ptr(), E, c32.data_ptr(), E, bias.data_ptr(), Bq, Bc, E, off, lse.data_ptr(), loss.data_ptr(),
+                                                gq.data_ptr(), E, gc.data_ptr(), E, ws.data_ptr(), ws.numel(), N.TT_IMPL_TC, stream()))
+        out[name] = [x.cpu().numpy() for x in (lse, loss, gq, gc)]
+    for a, b in zip(out["sep"][:1] + out["sep"][2:], out["step"][:1] + out["step"][2:]):
+        assert np.array_equal(a, b)
+    assert abs(out["sep"][1][0] - out["step"][1][0]) <= 1e-6 * abs(out["sep"][1][0])
