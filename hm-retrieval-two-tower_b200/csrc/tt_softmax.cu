@@ -13,8 +13,6 @@ int logits_simt(const float* Q, int ldq, const float* C, int ldc, const float* b
 bool softmax_tc_supported(int ldq, int ldc, int E, const void* Q, const void* C);
 int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse,
                    float* loss, float* ws, cudaStream_t st);
-int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const float* rowv, const float* colv, int nR, int nT, int E,
-                        int d, float* G, int ldg, float* ws, cudaStream_t st);
 int softmax_bwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E, int off, int which,
                    float* G0, int ldg0, float* G1, int ldg1, float* ws, cudaStream_t st);
 int softmax_step_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,

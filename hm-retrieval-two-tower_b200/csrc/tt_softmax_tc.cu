@@ -72,32 +72,6 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t c
 }
 
 // ---- small helper kernels ---------------------------------------------------------------------------------
-__global__ void fwd_combine_kernel(const float* __restrict__ m2, const float* __restrict__ l, const float* __restrict__ zd, int splits, int nR,
-                                   float* __restrict__ lse, float* __restrict__ rowloss) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nR) return;
-    float M = -CUDART_INF_F;
-    for (int s = 0; s < splits; ++s) M = fmaxf(M, m2[(int64_t)s * nR + r]);
-    float L = 0.f;
-    for (int s = 0; s < splits; ++s) {
-        float ms = m2[(int64_t)s * nR + r];
-        if (ms > -CUDART_INF_F) L += l[(int64_t)s * nR + r] * exp2f(ms - M);
-    }
-    float v = (M + log2f(L)) * 0.6931471805599453f;
-    lse[r] = v;
-    rowloss[r] = v - zd[r];
-}
-
-__global__ void bwd_reduce_kernel(const float* __restrict__ part, int splits, int64_t n, int E, float* __restrict__ G, int ldg) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s = __fadd_rn(s, part[(int64_t)z * n + i]);
-    int64_t r = i / E;
-    int c = (int)(i % E);
-    G[r * ldg + c] = s;
-}
-
 // out[i] = colv[i] * log2(e) for i < n (0 when colv is null), zero padding up to n_pad
 __global__ void scale_pad_kernel(const float* __restrict__ colv, int n, float* __restrict__ out, int n_pad) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,22 +82,6 @@ static int launch_scale_pad(const float* colv, int n, float* out, int n_pad, cud
     scale_pad_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, st>>>(colv, n, out, n_pad);
     TT_LAUNCH_OK("scale_pad_kernel");
     return TT_OK;
-}
-
-// out (cols x ldo) = in (rows x cols)^T, 32x32 shared-memory tiles, coalesced both ways
-__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int ld, int rows, int cols, float* __restrict__ out, int ldo) {
-    __shared__ float tile[32][33];
-    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int i = ty; i < 32; i += 8) {
-        int r = r0 + i, c = c0 + tx;
-        tile[i][tx] = (r < rows && c < cols) ? in[(int64_t)r * ld + c] : 0.f;
-    }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        int c = c0 + i, r = r0 + tx;
-        if (c < cols && r < rows) out[(int64_t)c * ldo + r] = tile[tx][i];
-    }
 }
 
 template <int MODE, int E, int BN>
@@ -149,7 +107,6 @@ constexpr int kMaxSplits = 16;   // column splits per launch; the forward keeps 
 // debug knobs (tt_debug_tc): timeline buffer and a cap on the column splits
 static unsigned long long* g_trace = nullptr;
 static int g_max_splits = kMaxSplits;
-static inline int bwd_bn(int E) { return E <= 64 ? 64 : 32; }  // shared-memory budget (see RowPanelCfg)
 
 struct Plan {
     int m_tiles, n_tiles, splits, tps;
@@ -164,10 +121,6 @@ static Plan plan_for(int nR, int nT, int bn) {
 
 static inline size_t tt_ld(int n) { return align_up((size_t)n, 4); }
 
-static size_t bwd_pass_floats(int nR, int nT, int E) {
-    Plan pl = plan_for(nR, nT, bwd_bn(E));
-    return align_up((size_t)pl.splits * nR * E, 64) + align_up((size_t)E * tt_ld(nT), 64) + (size_t)nT + 512;
-}
 
 
 
@@ -400,14 +353,8 @@ size_t softmax_tc_workspace(int Bq, int Bc, int E) {
     size_t rows = (size_t)(Bq > Bc ? Bq : Bc);
     size_t fwd = sk_fwd_bytes(Bq, Bc, E), bwd = sk_bwd_bytes(Bq, Bc, E);
     size_t step = fwd + bwd + softmax_step_floats(Bq, Bc, E) * sizeof(float);      // tt_inbatch_softmax_step keeps all three regions live
-    // the split-launch kernels (debug / legacy path)
-    size_t a = bwd_pass_floats(Bq, Bc, E) * sizeof(float), b = bwd_pass_floats(Bc, Bq, E) * sizeof(float);
-    size_t legacy_fwd = (4 * (size_t)kMaxSplits + 4) * align_up(rows * sizeof(float), 256) + 2048;
-    size_t m = step;
-    m = m > a ? m : a;
-    m = m > b ? m : b;
-    m = m > legacy_fwd ? m : legacy_fwd;
-    return m + 1024;
+    (void)rows;
+    return step + 1024;
 }
 
 }  // namespace tc
@@ -637,44 +584,6 @@ int softmax_bwd_tc(const float* Q, int ldq, const float* C, int ldc, const float
     if (which == 1) sides[n++] = SkSide{C, ldc, Q, ldq, bias, lse, Bc, Bq, -off, G0, ldg0};
     if (which == 2) sides[n++] = SkSide{C, ldc, Q, ldq, bias, lse, Bc, Bq, -off, G1, ldg1};
     return softmax_bwd_sk(sides, n, E, ws, st);
-}
-
-int softmax_bwd_pass_tc(const float* R, int ldr, const float* T, int ldt, const float* rowv, const float* colv, int nR, int nT, int E, int d,
-                        float* G, int ldg, float* ws, cudaStream_t st) {
-    if (nR == 0) return TT_OK;
-    const int bn = bwd_bn(E);
-    Plan pl = plan_for(nR, nT, bn);
-    float* part = ws;
-    float* Tt = ws + align_up((size_t)pl.splits * nR * E, 64);
-    const int ldtt = (int)tt_ld(nT);
-    float* c2 = Tt + align_up((size_t)E * ldtt, 64);
-    {
-        int rc0 = launch_scale_pad(colv, nT, c2, pl.n_tiles * bn, st);
-        if (rc0) return rc0;
-        dim3 grid((unsigned)ceil_div(nT, 32), (unsigned)ceil_div(E, 32));
-        transpose_kernel<<<grid, 256, 0, st>>>(T, ldt, nT, E, Tt, ldtt);
-        TT_LAUNCH_OK("transpose_kernel");
-    }
-    CUtensorMap tmR, tmT, tmTt;
-    int rc = make_tmap_2d(&tmR, R, nR, E, ldr, 128);
-    if (rc) return rc;
-    rc = make_tmap_2d(&tmT, T, nT, E, ldt, bn);
-    if (rc) return rc;
-    rc = make_tmap_2d(&tmTt, Tt, E, nT, ldtt, E);
-    if (rc) return rc;
-    RowPanelParams p{};
-    p.nR = nR; p.nT = nT; p.n_tiles = pl.n_tiles; p.tiles_per_split = pl.tps; p.rowv = rowv; p.colv2 = c2; p.d = d;
-    p.out0 = part; p.out1 = nullptr; p.out2 = nullptr; p.ld_out = 0; p.trace = g_trace;
-    switch (E) {
-        case 32: rc = launch_rowpanel<kBwd, 32, 64>(tmR, tmT, tmTt, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<bwd,32>"); break;
-        case 64: rc = launch_rowpanel<kBwd, 64, 64>(tmR, tmT, tmTt, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<bwd,64>"); break;
-        default: rc = launch_rowpanel<kBwd, 128, 32>(tmR, tmT, tmTt, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<bwd,128>"); break;
-    }
-    if (rc) return rc;
-    int64_t n = (int64_t)nR * E;
-    bwd_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(part, pl.splits, n, E, G, ldg);
-    TT_LAUNCH_OK("bwd_reduce_kernel");
-    return TT_OK;
 }
 
 int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, float* Z, int ldz, cudaStream_t st) {

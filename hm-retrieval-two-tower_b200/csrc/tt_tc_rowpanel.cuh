@@ -1,27 +1,21 @@
-// tt_tc_rowpanel.cuh -- the one tcgen05 kernel skeleton behind the logits-shaped hot ops.
+// tt_tc_rowpanel.cuh -- one CTA per (row panel, column split): the tcgen05 skeleton behind the index filter and tt_logits.
 //
 //   S(128 x BN) = R_panel(128 x E) . T_tile(BN x E)^T      tcgen05.mma kind::tf32, fp32 accumulate in TMEM
 //
 // A CTA owns a 128-row panel of R (loaded once by TMA, resident in shared memory) and streams tiles of T
 // through a TMA/mbarrier ring.  S is double-buffered in TMEM so the tensor core works on tile j+1 while
-// the epilogue warps consume tile j; S never goes to HBM.  Warp roles (192 threads):
+// the epilogue warps consume tile j; S never goes to HBM.  Warp roles:
 //   warp 0: TMA producer (one elected lane)      warp 1: MMA issuer (one elected lane), TMEM owner
 //   warps 2-9: epilogue; thread = one TMEM lane (= one R row); the two warps that share a lane quarter split
-//              the columns of every tile between them (two warps per scheduler hide each other's latencies)
+//              the columns of every tile between them
 // Modes (compile-time):
-//   kFwd    online log-sum-exp per row (+ diagonal logit)                -> partial (m2, l, zdiag) per split
-//   kBwd    P = exp(S - rowv - colv) - [col == row + d], written TF32 to swizzled smem as the A operand of a
-//           second MMA  G(128 x E) += P(128 x BN) . T_tile(BN x E).  MN-major TF32 operands need a different
-//           swizzle (128B_BASE32B) than the K-major tile of the first MMA, so the B operand of the second
-//           MMA is a K-major tile of T^T (E x BN) loaded by TMA from a transposed copy of T.
 //   kLogits Z = S - colv written out (tests / TwoTowerModel.call)
 //   kIndex  lower bound of the best score in each group of BN/2 consecutive columns -> group values (filter stage 1)
-//   kCollect every 32-column chunk that can hold a column reaching the row's threshold is dumped (32 TF32 scores)
-//           into the row's hit queue (filter stage 2; the queue is tested per column and rescored exactly afterwards)
-//
-// The per-column term arrives pre-scaled (colv2 = colv * log2 e, zero padded to whole tiles) and is staged
-// into shared memory by a 1-D bulk copy on the tile's barrier; the epilogue works in the log2 domain with
-// ex2.approx, and takes a check-free fast path for tiles that are fully in range and off the diagonal.
+//   kCollect every 32-column chunk that can hold a column reaching the row's threshold is appended (32 TF32 scores)
+//           to the dumping warp's hit log (filter stage 2; the log is tested per column and rescored exactly afterwards)
+// The in-batch softmax (kFwd / kBwd) moved to the persistent kernel in tt_tc_streamk.cuh, which reuses the helpers
+// below (mbarrier/TMA/TMEM wrappers, the checked per-chunk epilogue bodies); the kFwd/kBwd branches that remain in this
+// kernel body are compiled out (RowPanelCfg static_asserts the mode).
 #pragma once
 #include <math_constants.h>
 
@@ -144,6 +138,7 @@ struct RowPanelCfg {
     static constexpr int kTmemCols = (MODE == kBwd) ? (2 * BN + E <= 256 ? 256 : 512) : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
     static constexpr int kSmemBytes = kRBytes + kStages * kTBytes + kPBufs * kPBytes + 4 * 1024 /*c2 stages*/ + 1024 /*barriers*/ + 1024 /*align*/;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
+    static_assert(MODE == kLogits || MODE == kIndex || MODE == kCollect, "rowpanel_kernel: the softmax modes live in tt_tc_streamk.cuh");
     static_assert(E == 32 || E == 64 || E == 128, "E must be 32, 64 or 128");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 up to 256");
     static_assert(MODE != kBwd || 2 * BN + E <= 512, "TMEM budget");
