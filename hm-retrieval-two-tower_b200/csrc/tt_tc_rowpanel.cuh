@@ -118,9 +118,13 @@ __device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&r
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int MODE, int E, int BN>
+// H: fp16 operands (kind::f16, 64 columns per 128-byte slab) instead of TF32-rounded fp32 (kind::tf32, 32 per slab)
+template <int MODE, int E, int BN, bool H = false>
 struct RowPanelCfg {
-    static constexpr int kSlabs = E / 32;                       // 128-byte K slabs per operand row
+    static constexpr int kSlabCols = H ? 64 : 32;
+    static constexpr int kSlabs = E / kSlabCols;                // 128-byte K slabs per operand row
+    static constexpr int kMma1 = H ? E / 16 : E / 8;            // MMA instructions per tile (32 bytes of K each)
+    static_assert(!H || E >= 64, "fp16 operands need E >= 64");
     static constexpr int kRBytes = kSlabs * 128 * 128;
     static constexpr int kFit = (232448 - 6 * 1024 - kRBytes) / (kSlabs * BN * 128);   // T tiles that fit beside the R panel
     static constexpr int kStages = (MODE == kBwd) ? 3 : (kFit >= 4 ? 4 : (kFit >= 3 ? 3 : 2));   // T ring depth
@@ -214,11 +218,11 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t c2s,
     }
 }
 
-template <int MODE, int E, int BN>
+template <int MODE, int E, int BN, bool H = false>
 __global__ void __launch_bounds__(64 + 32 * 4 * ((BN / 32 >= 2) ? 2 : 1), 1)
 rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmTt,
                 const RowPanelParams p) {
-    using Cfg = RowPanelCfg<MODE, E, BN>;
+    using Cfg = RowPanelCfg<MODE, E, BN, H>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     unsigned char* sR = smem;
@@ -257,7 +261,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_arrive_expect_tx(&bars->r_full, Cfg::kRBytes);
-            for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(sR + s * 128 * 128, &tmR, &bars->r_full, s * 32, m0);
+            for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(sR + s * 128 * 128, &tmR, &bars->r_full, s * Cfg::kSlabCols, m0);
             for (int it = 0; it < my_tiles; ++it) {
                 const int stage = it % Cfg::kStages;
                 const uint32_t ph = (it / Cfg::kStages) & 1;
@@ -265,7 +269,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                 mbar_wait(&bars->t_empty[stage], ph ^ 1);
                 mbar_arrive_expect_tx(&bars->t_full[stage], Cfg::kTBytes + Cfg::kC2Bytes);
                 unsigned char* dst = sT + stage * Cfg::kTBytes;
-                for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(dst + s * BN * 128, &tmT, &bars->t_full[stage], s * 32, n0);
+                for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(dst + s * BN * 128, &tmT, &bars->t_full[stage], s * Cfg::kSlabCols, n0);
                 if (MODE == kBwd) {
                     for (int s = 0; s < BN / 32; ++s) tma_load_2d(dst + Cfg::kT1Bytes + s * E * 128, &tmTt, &bars->t_full[stage], n0 + s * 32, 0);
                 }
@@ -274,7 +278,7 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc1 = make_idesc_tf32(128, BN, false, false);
+        constexpr uint32_t idesc1 = H ? make_idesc_f16(128, BN) : make_idesc_tf32(128, BN, false, false);
         constexpr uint32_t idesc2 = make_idesc_tf32(128, E, false, false);
         const uint32_t sR_a = smem_u32(sR), sT_a = smem_u32(sT), sP_a = smem_u32(sP);
         auto issue_g1 = [&](int it) {
@@ -287,12 +291,13 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
             tc_fence_after();
             if (lane == 0) {
 #pragma unroll
-                for (int k = 0; k < E / 8; ++k) {
+                for (int k = 0; k < Cfg::kMma1; ++k) {
                     const uint32_t off = (k >> 2) * 128 * 128 + (k & 3) * 32;
                     const uint32_t offT = (k >> 2) * BN * 128 + (k & 3) * 32;
                     uint64_t ad = make_smem_desc(sR_a + off, 16, 1024);
                     uint64_t bd = make_smem_desc(sT_a + stage * Cfg::kTBytes + offT, 16, 1024);
-                    mma_tf32(tmem + acc * BN, ad, bd, idesc1, k > 0 ? 1u : 0u);
+                    if (H) mma_f16(tmem + acc * BN, ad, bd, idesc1, k > 0 ? 1u : 0u);
+                    else mma_tf32(tmem + acc * BN, ad, bd, idesc1, k > 0 ? 1u : 0u);
                 }
                 // non-bwd: the stage is released by this commit (T tile consumed) AND by the 4 epilogue warps (c2 consumed)
                 if (MODE != kBwd) mma_commit(&bars->t_empty[stage]);

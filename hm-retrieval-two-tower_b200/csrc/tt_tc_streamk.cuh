@@ -107,23 +107,6 @@ struct SkCfg {
     static_assert(E == 32 || E == 64 || E == 128, "E must be 32, 64 or 128");
 };
 
-// instruction descriptor for kind::f16 with fp16 operands, fp32 accumulate
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
-    return (1u << 4)                       // c_format  = F32
-           | (0u << 7)                     // a_format  = F16
-           | (0u << 10)                    // b_format  = F16
-           | (static_cast<uint32_t>(N >> 3) << 17)
-           | (static_cast<uint32_t>(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :
-        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 // D[tmem] (+)= A[tmem] . B[smem]: the A operand (M x K, fp16 pairs packed per 32-bit column, row m in lane m) is read from
 // tensor memory -- the epilogue writes P there with tcgen05.st, so P never touches shared memory
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
