@@ -317,6 +317,7 @@ def run_ours(args):
 
     if rank == 0:
         line["roofline"] = softmax_roofline(model, B, pk, lib)
+        line["hbm_kernels"] = hbm_rooflines(pk, lib)
     line["index"] = index_bench(model, pk, lib, K, world)      # every rank takes part (row-sharded corpus when N > 1)
     if world == 1:
         if not args.no_cpu:
@@ -366,8 +367,79 @@ def softmax_roofline(model, B, pk, lib):
     flops = 6.0 * B * B * e
     achieved = flops / sec / 1e12
     return {"bound": "tensor", "kernel": "in-batch softmax fwd+bwd (%s)" % ("tcgen05, fp16 operand tiles" if use_tc else "fp32 CUDA cores"),
-            "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_burst"], "traffic": None,
+            "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_burst"],
+            "traffic": NCU_SOFTMAX_DRAM_BYTES if (use_tc and B == 8192 and e == 64) else None, "traffic_source": NCU_SOFTMAX_SOURCE,
             "ms": sec * 1e3, "algorithmic_flop": flops, "peak_source": pk["source"] + ", dense bf16 burst (kernel timed alone)"}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of the two stream-K launches (forward 2.17 MB, backward 4.37 MB) from the
+# `ncu --set full` capture of this workload (B = 8192, E = 64); the operands are 2 x 1 MB of fp16 tiles + 2 x 2 MB fp32 outputs
+NCU_SOFTMAX_DRAM_BYTES = 2169088 + 4366336
+NCU_SOFTMAX_SOURCE = "profiles/r01b_softmax_streamk_ncu_full.md (ncu --set full, per launch, fwd + bwd)"
+
+
+def hbm_rooflines(pk, lib, b=1 << 20, e=64, rows=V_CUSTOMERS + 1):
+    """The HBM-bound kernels at a batch large enough to leave the launch-latency regime (2^20 ids; the step's own batch moves
+    only 5 MB): embedding gather (4.e B read + 4.e B written + 4 B id per example) and the de-duplicated sparse Adagrad
+    ((1 + 4.U/B).4.e B per example, U = unique rows).  Timed alone with CUDA events."""
+    import torch
+
+    from pkg import _native as N
+    from pkg.modelling._device import feature_array
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    table = torch.rand((rows, e), generator=g, device="cuda") * 0.1 - 0.05
+    acc = torch.full_like(table, 0.1)
+    ids = torch.randint(1, rows, (b,), generator=g, device="cuda", dtype=torch.int32)
+    grad = torch.randn((b, e), generator=g, device="cuda") * 1e-3
+    out = torch.empty((b, e), dtype=torch.float32, device="cuda")
+    uniq = int(torch.unique(ids).numel())
+    st = N.stream_ptr()
+    feats = feature_array([dict(table=table.data_ptr(), src=ids.data_ptr(), rows=rows, e=e, col=0)])
+    jobs = (N.TTSparseJob * 1)()
+    jobs[0].table, jobs[0].slot0, jobs[0].slot1 = table.data_ptr(), acc.data_ptr(), None
+    jobs[0].rows, jobs[0].e, jobs[0].nsrc, jobs[0].n_per_src = rows, e, 1, b
+    jobs[0].ids[0], jobs[0].grad[0], jobs[0].grad_ld[0] = ids.data_ptr(), grad.data_ptr(), e
+    ws = torch.empty(int(lib.tt_sparse_workspace_bytes(1, b, e)), dtype=torch.uint8, device="cuda")
+
+    def gather():
+        N.check(lib.tt_gather_concat(feats, 1, b, e, out.data_ptr(), e, st), "tt_gather_concat")
+
+    def sort():
+        N.check(lib.tt_sparse_sort(jobs, 1, ws.data_ptr(), ws.numel(), st), "tt_sparse_sort")
+
+    def update():
+        N.check(lib.tt_sparse_adagrad(jobs, 1, 0.05, 1e-7, ws.data_ptr(), ws.numel(), st), "tt_sparse_adagrad")
+
+    def timeit(fn, n=10, pre=None):
+        for _ in range(3):
+            if pre:
+                pre()
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(n):
+            if pre:
+                pre()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            tot += ev0.elapsed_time(ev1)
+        return tot * 1e-3 / n
+
+    res = []
+    for name, fn, pre, nbytes in (
+            ("embedding gather (tt_gather_concat)", gather, None, b * (8.0 * e + 4)),
+            ("sparse Adagrad: id sort + segmented reduce + row update", lambda: (sort(), update()), None, b * (1 + 4.0 * uniq / b) * 4 * e),
+            ("sparse Adagrad: segmented reduce + row update (ids already sorted)", update, sort, b * (1 + 4.0 * uniq / b) * 4 * e)):
+        sec = timeit(fn, pre=pre)
+        ach = nbytes / sec / 1e9
+        res.append({"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                    "traffic": None, "ms": sec * 1e3, "algorithmic_bytes": nbytes,
+                    "config": f"{b} ids into a {rows} x {e} fp32 table ({uniq} unique rows); table + accumulator 0.7 GB > L2"})
+    return res
 
 
 def index_bench(model, pk, lib, steps, world=1):

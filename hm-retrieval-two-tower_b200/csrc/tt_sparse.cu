@@ -76,30 +76,56 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const __grid_co
     pl.hist[(size_t)threadIdx.x * pl.ntiles + blockIdx.x] = s_hist[threadIdx.x];
 }
 
-// exclusive scan of hist viewed as one array of kRadix*ntiles entries (digit-major): one CTA per job
+// exclusive scan of hist viewed as one array of kRadix*ntiles entries (digit-major): one CTA per job.  Each warp owns a
+// contiguous segment and walks it 128 entries at a time (one 16-byte load per lane, fully coalesced); two sweeps: segment
+// totals, then the scan proper with the carried prefix.
 __global__ void __launch_bounds__(1024) sort_scan_kernel(const __grid_constant__ PlanArr plans, int pass) {
     const SortPlan& pl = plans.p[blockIdx.x];
     if (pass >= pl.npass) return;
-    __shared__ uint32_t s_part[1024];
-    const int total = kRadix * pl.ntiles;
-    const int per = (total + 1023) / 1024;
-    const int b = threadIdx.x * per, e = min(total, b + per);
+    __shared__ uint32_t s_warp[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = kRadix * pl.ntiles;                       // multiple of 256
+    const int seg = ((total + 32 * 128 - 1) / (32 * 128)) * 128;  // entries per warp, multiple of 128
+    const int b = min(total, warp * seg), e = min(total, b + seg);
+    uint4* h4 = reinterpret_cast<uint4*>(pl.hist);             // workspace slices are 256-byte aligned
     uint32_t sum = 0;
-    for (int i = b; i < e; ++i) sum += pl.hist[i];
-    s_part[threadIdx.x] = sum;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (int o = 1; o < 1024; o <<= 1) {
-        uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
-        __syncthreads();
-        s_part[threadIdx.x] += v;
-        __syncthreads();
+    for (int i = b + lane * 4; i < e; i += 128) {
+        uint4 v = h4[i >> 2];
+        sum += v.x + v.y + v.z + v.w;
     }
-    uint32_t run = threadIdx.x ? s_part[threadIdx.x - 1] : 0u;
-    for (int i = b; i < e; ++i) {
-        uint32_t c = pl.hist[i];
-        pl.hist[i] = run;
-        run += c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_warp[warp] = sum;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_warp[lane], inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        s_warp[lane] = inc - v;                                 // exclusive prefix of the warp segments
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp];
+    for (int i0 = b; i0 < e; i0 += 128) {
+        const int i = i0 + lane * 4;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i < e) v = h4[i >> 2];
+        const uint32_t mine = v.x + v.y + v.z + v.w;
+        uint32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        uint32_t base = run + inc - mine;
+        if (i < e) {
+            uint4 w;
+            w.x = base; w.y = base + v.x; w.z = w.y + v.y; w.w = w.z + v.z;
+            h4[i >> 2] = w;
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
     }
 }
 

@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_ROOT, "lib", "libtt.so")
 
 TT_IMPL_AUTO, TT_IMPL_SIMT, TT_IMPL_TC = 0, 1, 2
-TT_MAX_FEATURES, TT_MAX_SRC, TT_MAX_JOBS, TT_MAX_KS = 16, 4, 32, 8
+TT_MAX_FEATURES, TT_MAX_SRC, TT_MAX_JOBS, TT_MAX_KS = 16, 16, 32, 8
 
 c_void_p, c_int, c_int32, c_int64, c_float, c_size_t = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t)

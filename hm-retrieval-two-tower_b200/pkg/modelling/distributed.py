@@ -74,17 +74,24 @@ class DataParallel:
             dist.broadcast(t.weight, src=0, group=group)
 
     # ---- buffers ---------------------------------------------------------------------------------------
-    # Two collectives per step: (1) ONE all-gather of all id columns, (2) ONE all-gather of every rank's message
-    # [embedding-gradient rows of both towers | flat dense gradients]; the dense gradients are then summed over ranks in
-    # rank order (a fixed order: replicas stay bit-identical).
+    # Two collectives per step and nothing else outside the two captured compute phases:
+    #   (1) ONE all-gather of the id columns.  The towers' id buffers ARE rows of ``ids_local`` (staging writes them in place).
+    #   (2) ONE all-gather of every rank's message [dX of the query tower | dX of the candidate tower | flat dense gradients].
+    #       The towers' dX buffers ARE slices of ``msg_local`` (the tower backward writes them in place); the dense gradients are
+    #       copied in at the end of phase A and summed over ranks in rank order at the start of phase B (a fixed order: replicas
+    #       stay bit-identical) -- both inside the captured graphs.
+    # The sparse optimizer reads the gathered buffers where NCCL put them: one source per (feature, rank), in (feature, rank,
+    # position) order -- the order the single-process update of the concatenated batches would use.
     def _ensure(self, sw):
         if getattr(sw, "dp", None) is not None:
             return sw.dp
         from pkg import _native as N
+        from pkg.modelling import _device as D
 
         torch = N.require_cuda()
         g, b = self.world, sw.batch
-        towers = [(self.model.query_tower, sw.q), (self.model.candidate_tower, sw.c)]
+        model = self.model
+        towers = [(model.query_tower, sw.q), (model.candidate_tower, sw.c)]
         id_slots = []                                   # (tower index, block index) of every id column
         for ti, (tower, tws) in enumerate(towers):
             for bi, (_, t, _, _) in enumerate(tower.input_layer.blocks):
@@ -92,74 +99,81 @@ class DataParallel:
                     id_slots.append((ti, bi))
         n_id = len(id_slots)
         lds = [tower.input_layer.ld for tower, _ in towers]
-        row_w = sum(lds)
-        n_dense = int(self.model._store.used)
-        msg = b * row_w + n_dense                       # floats per rank
+        n_dense = int(model._store.used)
+        offs = [0, b * lds[0]]                          # first float of each tower's dX block inside a message
+        dense_off = b * (lds[0] + lds[1])
+        msg = (dense_off + n_dense + 63) // 64 * 64     # floats per rank (every rank's block stays 256-byte aligned)
+        if g * msg * 4 >= 2 ** 40:
+            raise ValueError("data-parallel message too large")
         dp = {
-            "towers": towers, "id_slots": id_slots, "lds": lds, "row_w": row_w, "n_dense": n_dense,
+            "towers": towers, "id_slots": id_slots, "lds": lds, "offs": offs, "dense_off": dense_off, "n_dense": n_dense,
             "ids_local": torch.zeros((max(n_id, 1), b), dtype=torch.int32, device="cuda"),
-            "ids_gathered": torch.zeros((g, max(n_id, 1), b), dtype=torch.int32, device="cuda"),
-            "ids_all": torch.zeros((max(n_id, 1), g * b), dtype=torch.int32, device="cuda"),      # per column: rank-major (rank, position)
+            "ids_all": torch.zeros((g, max(n_id, 1), b), dtype=torch.int32, device="cuda"),      # [rank, column, position]
             "msg_local": torch.zeros(msg, dtype=torch.float32, device="cuda"),
             "msg_all": torch.zeros((g, msg), dtype=torch.float32, device="cuda"),
         }
+        # alias the towers' staging / gradient buffers into the exchange buffers (no packing copies per step)
+        for k, (ti, bi) in enumerate(id_slots):
+            towers[ti][1].bufs[bi] = dp["ids_local"][k]
+        for ti, (tower, tws) in enumerate(towers):
+            tws.feats = tower.input_layer.descriptors(tws.bufs)
+            tws.dx = dp["msg_local"][offs[ti]:offs[ti] + b * lds[ti]].view(b, lds[ti])
+        if model.logq_correction is not None:           # the ln p(candidate) gather reads the candidate-id column
+            for (f, t, _, _), buf in zip(model.candidate_tower.input_layer.blocks, sw.c.bufs):
+                if f.name == model.candidate_id_col and t is not None:
+                    sw.cid_buf = buf
+            sw.bias_feat = D.feature_array([{"table": model._logq_rows.data_ptr(), "src": sw.cid_buf.data_ptr(),
+                                             "rows": model._logq_rows.shape[0], "e": 1, "col": 0}])
         sw.dp = dp
         return dp
 
     def build_sparse_sources(self, model, sw):
-        """Same structure as the single-GPU source list, but over the all-gathered buffers."""
+        """Same structure as the single-GPU source list, but every feature contributes one source per rank, read straight from
+        the all-gathered buffers."""
         from pkg import _native as N
 
-        torch = N.require_cuda()
         dp = self._ensure(sw)
-        g, b = self.world, sw.batch
-        msg = dp["msg_all"].shape[1]
-        if g * msg * 4 >= 2 ** 31:
-            raise ValueError("data-parallel message too large for the int32 row stride of tt_sparse_job")
-        # gradient row (rank r, position i) of a tower lives at msg_all[r, i * row_w + col0 ...]: viewed as a (g * b) x e block it
-        # has a constant row stride only inside one rank, so every rank's block is gathered into a rank-major copy first
-        dp["rows_all"] = torch.zeros((g * b, dp["row_w"]), dtype=torch.float32, device="cuda")
+        g = self.world
         srcs = []
         slot = 0
-        col0 = 0
         for ti, (tower, tws) in enumerate(dp["towers"]):
             il = tower.input_layer
             per_table = {}
             for bi, (f, t, col, w) in enumerate(il.blocks):
                 if t is None:
                     continue
-                ids = dp["ids_all"][slot]
+                lst = per_table.setdefault(f.name, (t, []))[1]
+                for r in range(g):
+                    lst.append((dp["ids_all"][r, slot], dp["msg_all"][r].data_ptr() + 4 * (dp["offs"][ti] + col), dp["lds"][ti]))
                 slot += 1
-                per_table.setdefault(f.name, (t, []))[1].append((ids, dp["rows_all"].data_ptr() + 4 * (col0 + col), dp["row_w"]))
+            for name, (t, lst) in per_table.items():
+                if len(lst) > N.TT_MAX_SRC:
+                    raise ValueError(f"table {name}: {len(lst) // g} features x {g} ranks exceed {N.TT_MAX_SRC} gradient sources")
             srcs.extend(per_table.values())
-            col0 += dp["lds"][ti]
         return srcs
 
     # ---- exchanges (called from TwoTowerModel.train_step) ------------------------------------------------
     def gather_ids(self, model, sw):
         dp = self._ensure(sw)
-        for k, (ti, bi) in enumerate(dp["id_slots"]):
-            dp["ids_local"][k].copy_(dp["towers"][ti][1].bufs[bi])
-        allgather_into(dp["ids_gathered"].view(self.world * dp["ids_local"].shape[0], -1), dp["ids_local"], self.group)
-        g, n_id, b = dp["ids_gathered"].shape
-        dp["ids_all"].view(n_id, g, b).copy_(dp["ids_gathered"].permute(1, 0, 2))
+        allgather_into(dp["ids_all"].view(self.world * dp["ids_local"].shape[0], -1), dp["ids_local"], self.group)
 
-    def reduce_dense_and_gather_rows(self, model, sw):
+    def pack_dense(self, model, sw):
+        """End of phase A (captured): the flat dense gradients join the message."""
+        dp = self._ensure(sw)
+        if dp["n_dense"]:
+            dp["msg_local"][dp["dense_off"]:dp["dense_off"] + dp["n_dense"]].copy_(model._store.grads[:dp["n_dense"]])
+
+    def gather_rows(self, model, sw):
+        dp = self._ensure(sw)
+        allgather_into(dp["msg_all"], dp["msg_local"], self.group)
+
+    def sum_dense(self, model, sw):
+        """Start of phase B (captured): dense gradients summed over ranks in rank order."""
         import torch
 
         dp = self._ensure(sw)
-        g, b, row_w, n_dense = self.world, sw.batch, dp["row_w"], dp["n_dense"]
-        rows_local = dp["msg_local"][: b * row_w].view(b, row_w)
-        col0 = 0
-        for ti, (tower, tws) in enumerate(dp["towers"]):
-            rows_local[:, col0:col0 + dp["lds"][ti]].copy_(tws.dx)
-            col0 += dp["lds"][ti]
-        if n_dense:
-            dp["msg_local"][b * row_w:].copy_(model._store.grads[:n_dense])
-        allgather_into(dp["msg_all"], dp["msg_local"], self.group)
-        dp["rows_all"].view(g, b * row_w).copy_(dp["msg_all"][:, : b * row_w])
-        if n_dense:
-            torch.sum(dp["msg_all"][:, b * row_w:], dim=0, out=model._store.grads[:n_dense])   # fixed reduction order
+        if dp["n_dense"]:
+            torch.sum(dp["msg_all"][:, dp["dense_off"]:dp["dense_off"] + dp["n_dense"]], dim=0, out=model._store.grads[:dp["n_dense"]])
 
 
 def make_sharded_index(k: int, query_model, id_candidate_pairs: Iterable, group=None):

@@ -267,16 +267,20 @@ class TwoTowerModel(AbstractKerasModel):
             self.candidate_tower.backward_ws(sw.c, sw.dc)
         main.wait_stream(sw.cand)
         main.wait_stream(sw.side)  # join
+        if self.dist is not None:
+            self.dist.pack_dense(self, sw)
 
     def _phase_mid(self, sw: _StepWorkspace) -> None:
         if self.dist is not None:
-            self.dist.reduce_dense_and_gather_rows(self, sw)
+            self.dist.gather_rows(self, sw)
 
     def _phase_b(self, sw: _StepWorkspace) -> None:
         lib = N.load()
         opt = self.optimizer
         st = N.stream_ptr()
         n_dense = self._store.used
+        if self.dist is not None:
+            self.dist.sum_dense(self, sw)
         if n_dense:
             ds = self._opt_state["dense"]
             if isinstance(opt, Adagrad):

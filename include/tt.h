@@ -34,7 +34,7 @@ extern "C" {
 #define TT_ERR_INVALID (-5)   /* malformed input data (TFRecord framing / CRC / Example message) */
 
 #define TT_MAX_FEATURES 16   /* features per tower */
-#define TT_MAX_SRC 4         /* gradient sources that may share one table (same-named features) */
+#define TT_MAX_SRC 16        /* gradient sources feeding one table: same-named features x data-parallel ranks */
 #define TT_MAX_JOBS 32       /* tables updated by one sparse-optimizer call */
 #define TT_MAX_KS 8
 
