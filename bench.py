@@ -248,7 +248,7 @@ def run_ours(args):
     if world > 1:
         from pkg.modelling.distributed import DataParallel
 
-        DataParallel(model)
+        DataParallel(model, shard_tables=(args.tables == "sharded"))
     model.use_cuda_graph = not args.no_graph   # data parallel: two captured compute phases around the eager NCCL exchanges
     rng = np.random.default_rng(1000 + rank)
     pool = 8
@@ -315,6 +315,11 @@ def run_ours(args):
         "gpu_launches": launches_per_step * K, "clocks": clocks,
     }
 
+    if world > 1:
+        line["config"]["tables"] = "row-sharded over the GPUs (rows read / gradient rows pulled over NVLink peer memory)" if model.dist.shard_tables \
+            else "replicated (all-gathered gradient rows)"
+        line["dp_phases_ms"] = dp_phase_times(model, B, dev_batches)
+        barrier()       # every rank's last table update has landed before anybody embeds the corpus
     if rank == 0:
         line["roofline"] = softmax_roofline(model, B, pk, lib)
         line["hbm_kernels"] = hbm_rooflines(pk, lib)
@@ -331,6 +336,28 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def dp_phase_times(model, B, dev_batches, n=20):
+    """Device time of the four phases of a data-parallel step (rank-local CUDA events; explains the scaling number)."""
+    import torch
+
+    sw = model._step_ws(B)
+    if not isinstance(sw.graph, tuple) or len(sw.graph) != 2:
+        return None
+    acc = [0.0] * 4
+    for i in range(n):
+        model._stage(sw, dev_batches[i % len(dev_batches)])
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record(); model._phase_pre(sw)
+        ev[1].record(); sw.graph[0].replay()
+        ev[2].record(); model._phase_mid(sw)
+        ev[3].record(); sw.graph[1].replay()
+        ev[4].record()
+        torch.cuda.synchronize()
+        for k in range(4):
+            acc[k] += ev[k].elapsed_time(ev[k + 1]) / n
+    return {"ids_allgather": acc[0], "phase_a_graph": acc[1], "grads_allgather": acc[2], "phase_b_graph": acc[3]}
 
 
 def softmax_roofline(model, B, pk, lib):
@@ -549,6 +576,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--simt", action="store_true", help="force the exact fp32 CUDA-core contraction path")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--tables", default="sharded", choices=["sharded", "replicated"], help="embedding-table layout when --gpus > 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=10)
     args = ap.parse_args()

@@ -1,5 +1,6 @@
 // tt_api.cu -- library plumbing and the small element-wise entry points of tt.h.
 #include <stdarg.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -156,6 +157,45 @@ int tt_version(void) { return 100; }
 const char* tt_last_error(void) { return tt::g_err; }
 
 int64_t tt_launch_count(void) { return tt::g_launches.load(); }
+
+// ---- peer-shareable memory (CUDA IPC; see tt.h) ---------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == TT_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+
+int tt_peer_alloc(size_t bytes, void** ptr, void* handle) {
+    TT_REQUIRE(ptr != nullptr && handle != nullptr && bytes > 0, "tt_peer_alloc: bad arguments");
+    void* p = nullptr;
+    TT_CUDA_OK(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        tt::set_error("tt_peer_alloc: %s", cudaGetErrorString(e));
+        return TT_ERR_CUDA;
+    }
+    memcpy(handle, &h, sizeof(h));
+    *ptr = p;
+    return TT_OK;
+}
+
+int tt_peer_open(const void* handle, void** ptr) {
+    TT_REQUIRE(ptr != nullptr && handle != nullptr, "tt_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    TT_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TT_OK;
+}
+
+int tt_peer_close(void* ptr) {
+    if (ptr) TT_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+    return TT_OK;
+}
+
+int tt_peer_free(void* ptr) {
+    if (ptr) TT_CUDA_OK(cudaFree(ptr));
+    return TT_OK;
+}
 
 int tt_device_supports_tc(void) {
     int dev = 0, major = 0;

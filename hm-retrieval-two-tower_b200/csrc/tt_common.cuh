@@ -68,6 +68,17 @@ __device__ __forceinline__ float tf32_rn(float x) {
     return __uint_as_float(r);
 }
 
+// first element of embedding row `id` of a feature's table.  Row-sharded tables (shards = G > 1): `table` is a device array of G
+// shard base pointers; row i lives in shard i % G at local row i / G, possibly in another GPU's HBM (peer-mapped, read over NVLink).
+__device__ __forceinline__ const float* feature_row(const tt_feature& ft, int id) {
+    if (ft.shards > 1) {
+        const unsigned long long* tabs = reinterpret_cast<const unsigned long long*>(ft.table);
+        const unsigned g = (unsigned)ft.shards, q = (unsigned)id / g;
+        return reinterpret_cast<const float*>(__ldg(tabs + ((unsigned)id - q * g))) + (int64_t)q * ft.e;
+    }
+    return ft.table + (int64_t)id * ft.e;
+}
+
 // strict ordering of the tf.math.top_k contract: higher score first, then lower index
 __device__ __forceinline__ bool ranks_before(float sa, int32_t ia, float sb, int32_t ib) {
     return (sa > sb) || (sa == sb && ia < ib);

@@ -31,6 +31,7 @@ struct SortPlan {  // per-job workspace pointers
     uint32_t* hist;  // [kRadix][ntiles]
     float* partL;    // [nblocks][e] piece sums of runs continuing from an earlier block
     float* partR;    // [nblocks][e] piece sums of runs that begin in the block and continue
+    float* stage;    // row-sharded tables: [n][e] gradient rows of the owned entries in sorted order (pulled from peer memory), else null
     int32_t n;       // elements
     int32_t ntiles;
     int32_t npass;
@@ -46,10 +47,19 @@ static int passes_for_rows(int rows) {
     return (bits + 7) / 8;
 }
 
+// row-sharded tables: number of local rows of every shard; also the key given to entries this rank does not own
+__host__ __device__ __forceinline__ uint32_t skip_key(const tt_sparse_job& job) {
+    return (uint32_t)((job.rows + job.shard_world - 1) / job.shard_world);
+}
+
 __device__ __forceinline__ uint32_t load_key(const tt_sparse_job& job, int i) {
     int src = i / job.n_per_src, r = i - src * job.n_per_src;
     int id = __ldg(job.ids[src] + r);
     if ((unsigned)id >= (unsigned)job.rows) id = 0;  // out-of-range -> OOV row, as in the forward gather
+    if (job.shard_world > 1) {                       // row-sharded table: local row, or the skip key (sorts last) for other ranks' rows
+        const unsigned g = (unsigned)job.shard_world, q = (unsigned)id / g;
+        return ((unsigned)id - q * g == (unsigned)job.shard_rank) ? q : skip_key(job);
+    }
     return (uint32_t)id;
 }
 
@@ -226,7 +236,8 @@ __device__ __forceinline__ void apply_row(const tt_sparse_job& job, int kMode, u
 template <int NC, int RB>
 __device__ __forceinline__ void block_body(const tt_sparse_job& job, int kMode, uint32_t key, int pos, uint32_t heads, int cnt, bool cont_in,
                                            bool cont_out, float* __restrict__ partL, float* __restrict__ partR, int lane, float lr, float eps,
-                                           float omb1, float omb2) {
+                                           float omb1, float omb2, const float* __restrict__ stage) {
+    // stage != null: the block's gradient rows were copied (from the producing GPUs' dX buffers) to stage[lane index], contiguous
     const int e = job.e;
     while (heads) {
         int s[RB], en[RB];
@@ -246,7 +257,8 @@ __device__ __forceinline__ void block_body(const tt_sparse_job& job, int kMode, 
         float g[RB][NC], a[RB][NC], w[RB][NC];
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
-            const float* r0 = grad_row(job, __shfl_sync(0xffffffffu, pos, s[u]));
+            const int p0 = __shfl_sync(0xffffffffu, pos, s[u]);
+            const float* r0 = stage ? stage + (int64_t)s[u] * e : grad_row(job, p0);
 #pragma unroll
             for (int ci = 0; ci < NC; ++ci) {
                 const int c = lane + 32 * ci;
@@ -262,7 +274,8 @@ __device__ __forceinline__ void block_body(const tt_sparse_job& job, int kMode, 
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
             for (int j = s[u] + 1; j < en[u]; ++j) {   // duplicates of the id inside this block: sequential, position order
-                const float* r0 = grad_row(job, __shfl_sync(0xffffffffu, pos, j));
+                const int pj = __shfl_sync(0xffffffffu, pos, j);
+                const float* r0 = stage ? stage + (int64_t)j * e : grad_row(job, pj);
 #pragma unroll
                 for (int ci = 0; ci < NC; ++ci) {
                     const int c = lane + 32 * ci;
@@ -298,6 +311,23 @@ __device__ __forceinline__ void block_body(const tt_sparse_job& job, int kMode, 
     }
 }
 
+// Row-sharded tables: one warp per sorted entry copies the gradient row of an OWNED entry from wherever it was produced (the dX
+// block of another GPU, peer-mapped over NVLink) into the local staging array, in sorted order.  Every load is independent, so the
+// NVLink latency is paid once; the segmented reduce then streams contiguous local rows.
+__global__ void __launch_bounds__(256) sparse_stage_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans) {
+    const SortPlan& pl = plans.p[blockIdx.y];
+    const tt_sparse_job& job = jobs.j[blockIdx.y];
+    if (pl.stage == nullptr) return;
+    const int lane = threadIdx.x & 31;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= pl.n) return;
+    const uint32_t key = pl.keys[pl.npass & 1][j];
+    if (key == skip_key(job)) return;
+    const float* src = grad_row(job, pl.vals[pl.npass & 1][j]);
+    float* dst = pl.stage + (int64_t)j * job.e;
+    for (int c = lane; c < job.e; c += 32) dst[c] = __ldg(src + c);
+}
+
 // phase A: grid (ceil(max_blocks / 8), njobs), 8 warps per CTA, one warp per block of 32 sorted entries
 __global__ void __launch_bounds__(256) sparse_block_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans, int kMode,
                                                            float lr, float eps, float omb1, float omb2) {
@@ -310,8 +340,12 @@ __global__ void __launch_bounds__(256) sparse_block_kernel(const __grid_constant
     const int nblk = (pl.n + 31) >> 5;
     if (b >= nblk) return;
     const int base = b << 5;
-    const int cnt = min(32, pl.n - base);
+    int cnt = min(32, pl.n - base);
     const uint32_t key = lane < cnt ? ks[base + lane] : 0xffffffffu;
+    if (job.shard_world > 1) {   // entries of rows other ranks own carry the skip key and sort last: keep the owned prefix
+        cnt = __popc(__ballot_sync(0xffffffffu, lane < cnt && key != skip_key(job)));
+        if (cnt == 0) return;
+    }
     const int pos = lane < cnt ? vs[base + lane] : 0;
     const uint32_t kprev_lane = __shfl_up_sync(0xffffffffu, key, 1);
     const bool cont_in = base > 0 && ks[base - 1] == __shfl_sync(0xffffffffu, key, 0);           // first run began earlier
@@ -322,11 +356,12 @@ __global__ void __launch_bounds__(256) sparse_block_kernel(const __grid_constant
     const int e = job.e;
     float* partL = pl.partL + (int64_t)b * e;
     float* partR = pl.partR + (int64_t)b * e;
+    const float* stage = pl.stage ? pl.stage + (int64_t)base * e : nullptr;
     const int nc = (e + 31) >> 5;
-    if (nc <= 1) block_body<1, 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2);
-    else if (nc <= 2) block_body<2, 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2);
-    else if (nc <= 4) block_body<4, 2>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2);
-    else block_body<8, 1>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2);
+    if (nc <= 1) block_body<1, 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
+    else if (nc <= 2) block_body<2, 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
+    else if (nc <= 4) block_body<4, 2>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
+    else block_body<8, 1>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
 }
 
 // phase B: the head block of every boundary-crossing run adds the pieces in block order and applies the update
@@ -343,6 +378,7 @@ __global__ void __launch_bounds__(256) sparse_combine_kernel(const __grid_consta
     if (base + 32 >= pl.n) return;                       // last block: nothing can continue
     const uint32_t id = ks[base + 31];
     if (ks[base + 32] != id) return;                     // last run does not continue
+    if (job.shard_world > 1 && id == skip_key(job)) return;   // rows owned by other ranks
     if (ks[base] == id && base > 0 && ks[base - 1] == id) return;   // whole block is a middle piece: the head block owns it
     // this block holds the head of the run (either mid-block, or at lane 0 with a different predecessor)
     const int e = job.e;
@@ -359,7 +395,7 @@ __global__ void __launch_bounds__(256) sparse_combine_kernel(const __grid_consta
 __global__ void __launch_bounds__(256) adam_sweep_kernel(const __grid_constant__ JobArr jobs, int phase, float b1, float b2, float lr_t,
                                                          float eps) {
     const tt_sparse_job& job = jobs.j[blockIdx.y];
-    const int64_t total = (int64_t)job.rows * job.e;
+    const int64_t total = (int64_t)(job.shard_world > 1 ? (int)skip_key(job) : job.rows) * job.e;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
         if (phase == 0) {
@@ -376,10 +412,13 @@ static size_t part_bytes(int max_n, int max_e) {
     size_t n = (size_t)(max_n > 0 ? max_n : 1);
     return align_up(((n + 31) / 32) * (size_t)(max_e > 0 ? max_e : 1) * sizeof(float), 256);
 }
+static size_t stage_bytes(int max_n, int max_e) {
+    return align_up((size_t)(max_n > 0 ? max_n : 1) * (size_t)(max_e > 0 ? max_e : 1) * sizeof(float), 256);
+}
 static size_t per_job_bytes(int max_n, int max_e) {
     size_t n = (size_t)(max_n > 0 ? max_n : 1);
     size_t ntiles = (n + kTile - 1) / kTile;
-    return 4 * align_up(n * 4, 256) + align_up(ntiles * kRadix * 4, 256) + 2 * part_bytes(max_n, max_e);
+    return 4 * align_up(n * 4, 256) + align_up(ntiles * kRadix * 4, 256) + 2 * part_bytes(max_n, max_e) + stage_bytes(max_n, max_e);
 }
 
 static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, JobArr* ja, PlanArr* pa, int* max_tiles,
@@ -395,6 +434,7 @@ static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_
         TT_REQUIRE(jb.table && jb.slot0 && jb.rows >= 1 && jb.e >= 1, "%s: job %d malformed", who, j);
         TT_REQUIRE(jb.e <= 32 * kMaxColsPerLane, "%s: job %d embedding width %d exceeds %d", who, j, jb.e, 32 * kMaxColsPerLane);
         TT_REQUIRE(jb.nsrc >= 1 && jb.nsrc <= TT_MAX_SRC && jb.n_per_src >= 0, "%s: job %d nsrc/n_per_src out of range", who, j);
+        TT_REQUIRE(jb.shard_world <= 1 || (jb.shard_rank >= 0 && jb.shard_rank < jb.shard_world), "%s: job %d shard rank/world out of range", who, j);
         TT_REQUIRE((int64_t)jb.nsrc * jb.n_per_src < (1ll << 31), "%s: job %d too many rows", who, j);
         for (int s = 0; s < jb.nsrc; ++s) TT_REQUIRE(jb.n_per_src == 0 || (jb.ids[s] && jb.grad[s] && jb.grad_ld[s] >= jb.e), "%s: job %d source %d malformed", who, j, s);
         ja->j[j] = jb;
@@ -417,9 +457,10 @@ static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_
         size_t hist_bytes = align_up((size_t)ceil_div(max_n > 0 ? max_n : 1, kTile) * kRadix * 4, 256);
         p.partL = reinterpret_cast<float*>(base + 4 * seg + hist_bytes);
         p.partR = reinterpret_cast<float*>(base + 4 * seg + hist_bytes + part_bytes(max_n, max_e));
+        p.stage = jobs[j].shard_world > 1 ? reinterpret_cast<float*>(base + 4 * seg + hist_bytes + 2 * part_bytes(max_n, max_e)) : nullptr;
         p.n = jobs[j].nsrc * jobs[j].n_per_src;
         p.ntiles = (int)ceil_div(p.n, kTile);
-        p.npass = passes_for_rows(jobs[j].rows);
+        p.npass = passes_for_rows(jobs[j].shard_world > 1 ? (int)skip_key(jobs[j]) + 1 : jobs[j].rows);
         if (p.ntiles > *max_tiles) *max_tiles = p.ntiles;
         if (p.npass > *max_pass) *max_pass = p.npass;
     }
@@ -435,6 +476,13 @@ static int apply_grid(const PlanArr& pa) {   // one warp per block of 32 sorted 
 
 static int launch_apply(const JobArr& ja, const PlanArr& pa, int njobs, int mode, float lr, float eps, float omb1, float omb2, cudaStream_t st) {
     dim3 grid((unsigned)apply_grid(pa), (unsigned)njobs);
+    bool staged = false;
+    int max_n = 0;
+    for (int j = 0; j < pa.n; ++j) { staged |= pa.p[j].stage != nullptr; max_n = pa.p[j].n > max_n ? pa.p[j].n : max_n; }
+    if (staged) {
+        sparse_stage_kernel<<<dim3((unsigned)ceil_div(max_n > 0 ? max_n : 1, 8), (unsigned)njobs), 256, 0, st>>>(ja, pa);
+        TT_LAUNCH_OK("sparse_stage_kernel");
+    }
     sparse_block_kernel<<<grid, 256, 0, st>>>(ja, pa, mode, lr, eps, omb1, omb2);
     TT_LAUNCH_OK("sparse_block_kernel");
     sparse_combine_kernel<<<grid, 256, 0, st>>>(ja, pa, mode, lr, eps, omb1, omb2);

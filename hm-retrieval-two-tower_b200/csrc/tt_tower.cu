@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) gather_concat_vec_kernel(const __grid_con
             const tt_feature& ft = fa.f[f];
             int id = __ldg(reinterpret_cast<const int32_t*>(ft.src) + b);
             if ((unsigned)id >= (unsigned)ft.rows) id = 0;
-            v = __ldg(reinterpret_cast<const float4*>(ft.table + (int64_t)id * ft.e) + s_off[c]);
+            v = __ldg(reinterpret_cast<const float4*>(feature_row(ft, id)) + s_off[c]);
         }
         X[t] = v;
     }
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) gather_concat_scalar_kernel(const __grid_
             } else {
                 int id = __ldg(reinterpret_cast<const int32_t*>(ft.src) + b);
                 if ((unsigned)id >= (unsigned)ft.rows) id = 0;
-                v = __ldg(ft.table + (int64_t)id * ft.e + s_off[c]);
+                v = __ldg(feature_row(ft, id) + s_off[c]);
             }
         }
         X[t] = v;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) dense_fwd_kernel(const __grid_constant__ 
             if (f != 255) {
                 const tt_feature& ft = fa.f[f];
                 if (ft.table == nullptr) v = __ldg(reinterpret_cast<const float*>(ft.src) + m);
-                else v = __ldg(ft.table + (int64_t)s_ids[(m - m0) * TT_MAX_FEATURES + f] * ft.e + s_off[k]);
+                else v = __ldg(feature_row(ft, s_ids[(m - m0) * TT_MAX_FEATURES + f]) + s_off[k]);
             }
             if (write_x) Xout[(int64_t)m * ldx + k] = v;
             return v;

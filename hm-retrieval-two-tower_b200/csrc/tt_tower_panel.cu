@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) dense_fwd_panel_kernel(const __grid_const
             if (row < B && f != 255) {
                 const tt_feature& ft = fa.f[f];
                 v = (ft.table == nullptr) ? __ldg(reinterpret_cast<const float*>(ft.src) + row)
-                                          : __ldg(ft.table + (int64_t)s_ids[r * TT_MAX_FEATURES + f] * ft.e + s_off[k]);
+                                          : __ldg(feature_row(ft, s_ids[r * TT_MAX_FEATURES + f]) + s_off[k]);
             }
             XsT[k * PS + r] = v;
             if (write_x && row < B) Xout[(int64_t)row * ldx + k] = v;

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_ROOT, "lib", "libtt.so")
 
 TT_IMPL_AUTO, TT_IMPL_SIMT, TT_IMPL_TC = 0, 1, 2
 TT_MAX_FEATURES, TT_MAX_SRC, TT_MAX_JOBS, TT_MAX_KS = 16, 16, 32, 8
+TT_PEER_SLOTS = 4
 
 c_void_p, c_int, c_int32, c_int64, c_float, c_size_t = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t)
@@ -22,12 +23,13 @@ c_void_p, c_int, c_int32, c_int64, c_float, c_size_t = (
 
 class TTFeature(ctypes.Structure):
     _fields_ = [("table", c_void_p), ("src", c_void_p), ("rows", c_int32), ("e", c_int32), ("col", c_int32),
-                ("_pad", c_int32)]
+                ("shards", c_int32)]
 
 
 class TTSparseJob(ctypes.Structure):
     _fields_ = [("table", c_void_p), ("slot0", c_void_p), ("slot1", c_void_p), ("rows", c_int32), ("e", c_int32),
-                ("nsrc", c_int32), ("n_per_src", c_int32), ("ids", c_void_p * TT_MAX_SRC),
+                ("nsrc", c_int32), ("n_per_src", c_int32), ("shard_rank", c_int32), ("shard_world", c_int32),
+                ("ids", c_void_p * TT_MAX_SRC),
                 ("grad", c_void_p * TT_MAX_SRC), ("grad_ld", c_int32 * TT_MAX_SRC)]
 
 
@@ -40,6 +42,12 @@ SIGNATURES = {
     "tt_launch_count": (c_int64, []),
     "tt_tc_available": (c_int, [c_int, c_int]),
     "tt_debug_tc": (c_int, [c_void_p, c_int]),
+    "tt_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), c_void_p]),
+    "tt_peer_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "tt_peer_close": (c_int, [c_void_p]),
+    "tt_peer_free": (c_int, [c_void_p]),
+    "tt_peer_barrier": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tt_peer_sum_f32": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "tt_debug_index_cap": (c_int, [c_int]),
     "tt_debug_index_stages": (c_int, [c_void_p]),
     # host-side helpers (csrc/tt_host.cu)

@@ -178,4 +178,5 @@ def feature_array(entries: Iterable[dict]):
         arr[i].rows = d["rows"]
         arr[i].e = d["e"]
         arr[i].col = d["col"]
+        arr[i].shards = d.get("shards", 0)
     return arr

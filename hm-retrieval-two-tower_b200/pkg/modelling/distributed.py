@@ -4,11 +4,19 @@ for the exchanges.  The reference is single-process (no t
 sharding below follows SURVEY.md 8(e):
 
 * training -- data parallel.  Every rank runs train_step on its own batch (in-batch negatives stay local,
-  exactly what one reference process sees for that batch).  Dense gradients: summed over ranks in rank order
-  (they ride in the same all-gather as the embedding-gradient rows; SUM loss => no 1/G scaling; a step equals the reference's gradient of G independent
-  batches evaluated at the same weights and summed, then one optimizer apply).  Embedding tables are
-  replicated: ranks all-gather (ids, gradient rows) and every replica runs the same deterministic
-  de-duplicated row update, ordered by (rank, position), so replicas stay bit-identical.
+  exactly what one reference process sees for that batch).  Dense gradients: all-gathered and summed over ranks in
+  rank order (SUM loss => no 1/G scaling; a step equals the reference's gradient of G independent batches evaluated
+  at the same weights and summed, then one optimizer apply).  Embedding tables, two layouts:
+    - row-sharded (``shard_tables=True``, the default for world > 1): row i lives on rank i % G.  The forward gather
+      reads rows where they live (peer-mapped HBM over NVLink, inside the gather / first-Dense kernels); ranks
+      all-gather the batch ids (4 B per id); the owner of a row pulls its gradient rows straight out of the producing
+      ranks' dX buffers (peer reads inside the segmented-reduce kernel) and applies the de-duplicated update once.
+      Per-rank traffic and optimizer work stay constant as G grows.  The two small NCCL all-gathers (ids, dense
+      gradients) also order the ranks: nobody reads a peer's dX before it is complete, nobody gathers a row before its
+      owner's previous update has landed.
+    - replicated: ranks all-gather (ids, gradient rows) and every replica runs the same update on the whole table.
+  Both apply each row's gradients in (feature, rank, position) order, so they are bit-identical to each other and
+  to the single-process update of the concatenated batches.
 * index -- the corpus is sharded row-wise; each rank returns its shard's exact top-K with GLOBAL row indices,
   ranks all-gather the (score, index) lists and merge them by (score desc, index asc) (tt_topk_merge), so the
   answer does not depend on the number of shards.
@@ -18,6 +26,7 @@ drive exactly this plumbing (tests/test_distributed_cpu.py).
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, List, Optional, Tuple
 
 import numpy as np
@@ -54,24 +63,64 @@ def allgather_into(out, local, group=None):
     return out
 
 
+class _DevPtr:
+    """A raw device address standing in for a tensor in the sparse-source lists (peer-mapped memory has no torch tensor)."""
+
+    def __init__(self, ptr: int, n: int):
+        self._ptr, self._n = int(ptr), int(n)
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+    def numel(self) -> int:
+        return self._n
+
+
 class DataParallel:
     """Attach to a compiled-or-not TwoTowerModel: ``DataParallel(model)``; then call model.train_step as usual."""
 
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, shard_tables: Optional[bool] = None, peer_sync: Optional[bool] = None):
         import torch.distributed as dist
+
+        from pkg import _native as N
 
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
+        torch = N.require_cuda()
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.model = model
+        self.shard_tables = (self.world > 1) if shard_tables is None else (bool(shard_tables) and self.world > 1)
+        # peer_sync (row-sharded tables only): the ranks are ordered by tt_peer_barrier kernels and read each other's ids / dense
+        # gradients in place, so a step contains no NCCL call and is captured as ONE CUDA graph.  False: the two small NCCL
+        # all-gathers (ids, dense gradients) order the ranks instead.
+        self.peer_sync = self.shard_tables and (os.environ.get("TT_DP_EXCHANGE", "peer") != "nccl" if peer_sync is None else bool(peer_sync))
         model.dist = self
         model._steps.clear()
         # replicas must start identical: parameters are broadcast from rank 0
         dist.broadcast(model._store.params, src=0, group=group)
         for _, _, t in model._tables():
             dist.broadcast(t.weight, src=0, group=group)
+        if self.shard_tables:
+            seen = set()
+            for _, _, t in model._tables():
+                if id(t) not in seen:
+                    seen.add(id(t))
+                    t.shard_rows(group)
+            for tower in (model.query_tower, model.candidate_tower):
+                tower._ws.clear()               # cached descriptors point at the unsharded tables
+            if model.optimizer is not None:
+                model._build_optimizer_state()  # slots take the shard's shape (fresh state: attach before training)
+            self.barrier()
+
+    def barrier(self):
+        """All ranks' queued work is complete (call before reading tables outside train_step, e.g. to build an index)."""
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
 
     # ---- buffers ---------------------------------------------------------------------------------------
     # Two collectives per step and nothing else outside the two captured compute phases:
@@ -102,16 +151,37 @@ class DataParallel:
         n_dense = int(model._store.used)
         offs = [0, b * lds[0]]                          # first float of each tower's dX block inside a message
         dense_off = b * (lds[0] + lds[1])
-        msg = (dense_off + n_dense + 63) // 64 * 64     # floats per rank (every rank's block stays 256-byte aligned)
-        if g * msg * 4 >= 2 ** 40:
-            raise ValueError("data-parallel message too large")
         dp = {
             "towers": towers, "id_slots": id_slots, "lds": lds, "offs": offs, "dense_off": dense_off, "n_dense": n_dense,
             "ids_local": torch.zeros((max(n_id, 1), b), dtype=torch.int32, device="cuda"),
             "ids_all": torch.zeros((g, max(n_id, 1), b), dtype=torch.int32, device="cuda"),      # [rank, column, position]
-            "msg_local": torch.zeros(msg, dtype=torch.float32, device="cuda"),
-            "msg_all": torch.zeros((g, msg), dtype=torch.float32, device="cuda"),
         }
+        if self.shard_tables:
+            # the dX blocks live in a peer-shareable buffer (read in place by the rows' owners); only the dense gradients travel
+            from pkg.modelling._peer import PeerBuffer
+
+            dp["peer_msg"] = PeerBuffer((max(dense_off, 64),), "float32", self.group)     # collective: same batch on every rank
+            dp["msg_local"] = dp["peer_msg"].local
+            dp["grad_base"] = list(dp["peer_msg"].ptrs)
+            if self.peer_sync:
+                dp["peer_ids"] = PeerBuffer((max(n_id, 1), b), "int32", self.group)
+                dp["ids_local"] = dp["peer_ids"].local
+                dp["peer_dense"] = PeerBuffer((max(n_dense, 64),), "float32", self.group)
+                dp["dense_local"] = dp["peer_dense"].local
+                dp["peer_flags"] = PeerBuffer((N.TT_PEER_SLOTS * (1 + g),), "int32", self.group)
+                self.barrier()                          # every rank's (zeroed) flag block exists before the first device barrier
+            else:
+                dp["dense_local"] = torch.zeros(max(n_dense, 1), dtype=torch.float32, device="cuda")
+                dp["dense_all"] = torch.zeros((g, max(n_dense, 1)), dtype=torch.float32, device="cuda")
+        else:
+            msg = (dense_off + n_dense + 63) // 64 * 64     # floats per rank (every rank's block stays 256-byte aligned)
+            if g * msg * 4 >= 2 ** 40:
+                raise ValueError("data-parallel message too large")
+            dp["msg_local"] = torch.zeros(msg, dtype=torch.float32, device="cuda")
+            dp["msg_all"] = torch.zeros((g, msg), dtype=torch.float32, device="cuda")
+            dp["grad_base"] = [dp["msg_all"][r].data_ptr() for r in range(g)]
+            dp["dense_local"] = dp["msg_local"][dense_off:dense_off + n_dense]
+            dp["dense_all"] = dp["msg_all"][:, dense_off:dense_off + n_dense]
         # alias the towers' staging / gradient buffers into the exchange buffers (no packing copies per step)
         for k, (ti, bi) in enumerate(id_slots):
             towers[ti][1].bufs[bi] = dp["ids_local"][k]
@@ -144,7 +214,9 @@ class DataParallel:
                     continue
                 lst = per_table.setdefault(f.name, (t, []))[1]
                 for r in range(g):
-                    lst.append((dp["ids_all"][r, slot], dp["msg_all"][r].data_ptr() + 4 * (dp["offs"][ti] + col), dp["lds"][ti]))
+                    # peer_sync: rank r's id column is read in place from its (peer-mapped) staging buffer
+                    ids = _DevPtr(dp["peer_ids"].ptrs[r] + 4 * slot * sw.batch, sw.batch) if self.peer_sync else dp["ids_all"][r, slot]
+                    lst.append((ids, dp["grad_base"][r] + 4 * (dp["offs"][ti] + col), dp["lds"][ti]))
                 slot += 1
             for name, (t, lst) in per_table.items():
                 if len(lst) > N.TT_MAX_SRC:
@@ -153,27 +225,49 @@ class DataParallel:
         return srcs
 
     # ---- exchanges (called from TwoTowerModel.train_step) ------------------------------------------------
+    def _device_barrier(self, dp, slot):
+        from pkg import _native as N
+
+        N.check(N.load().tt_peer_barrier(dp["peer_flags"].ptr_table.data_ptr(), self.rank, self.world, slot, N.stream_ptr()), "tt_peer_barrier")
+
     def gather_ids(self, model, sw):
+        """Start of a step.  Every rank's ids of this step are staged and its previous table update has landed: either the id
+        all-gather says so (NCCL), or a device barrier does and the ids are read where they are (peer_sync)."""
         dp = self._ensure(sw)
-        allgather_into(dp["ids_all"].view(self.world * dp["ids_local"].shape[0], -1), dp["ids_local"], self.group)
+        if self.peer_sync:
+            self._device_barrier(dp, 0)
+        else:
+            allgather_into(dp["ids_all"].view(self.world * dp["ids_local"].shape[0], -1), dp["ids_local"], self.group)
 
     def pack_dense(self, model, sw):
         """End of phase A (captured): the flat dense gradients join the message."""
         dp = self._ensure(sw)
         if dp["n_dense"]:
-            dp["msg_local"][dp["dense_off"]:dp["dense_off"] + dp["n_dense"]].copy_(model._store.grads[:dp["n_dense"]])
+            dp["dense_local"][:dp["n_dense"]].copy_(model._store.grads[:dp["n_dense"]])
 
     def gather_rows(self, model, sw):
+        """The one exchange between the compute phases: [dX blocks | dense gradients] (replicated tables) or the dense gradients
+        alone (row-sharded tables; the all-gather then also tells every rank that all dX blocks are complete)."""
         dp = self._ensure(sw)
-        allgather_into(dp["msg_all"], dp["msg_local"], self.group)
+        if self.peer_sync:
+            self._device_barrier(dp, 1)                 # every rank's dX blocks and dense gradients are complete
+        elif self.shard_tables:
+            allgather_into(dp["dense_all"], dp["dense_local"], self.group)
+        else:
+            allgather_into(dp["msg_all"], dp["msg_local"], self.group)
 
     def sum_dense(self, model, sw):
         """Start of phase B (captured): dense gradients summed over ranks in rank order."""
         import torch
 
         dp = self._ensure(sw)
-        if dp["n_dense"]:
-            torch.sum(dp["msg_all"][:, dp["dense_off"]:dp["dense_off"] + dp["n_dense"]], dim=0, out=model._store.grads[:dp["n_dense"]])
+        if dp["n_dense"] and self.peer_sync:
+            from pkg import _native as N
+
+            N.check(N.load().tt_peer_sum_f32(dp["peer_dense"].ptr_table.data_ptr(), self.world, dp["n_dense"], model._store.grads.data_ptr(),
+                                             N.stream_ptr()), "tt_peer_sum_f32")
+        elif dp["n_dense"]:
+            torch.sum(dp["dense_all"][:, :dp["n_dense"]], dim=0, out=model._store.grads[:dp["n_dense"]])
 
 
 def make_sharded_index(k: int, query_model, id_candidate_pairs: Iterable, group=None):

@@ -36,6 +36,53 @@ class EmbeddingTable:
         self.rows = self.vocab.rows
         self.weight = torch.empty((self.rows, self.e), dtype=torch.float32, device="cuda")
         self.weight.uniform_(-0.05, 0.05, generator=D.next_generator())
+        # row sharding over the ranks of a process group (pkg.modelling.distributed.DataParallel(shard_tables=True))
+        self.shard_rank, self.shard_world, self._peer, self._group = 0, 1, None, None
+
+    # ---- row sharding (one process per GPU) ---------------------------------------------------------
+    @property
+    def local_rows(self) -> int:
+        return (self.rows + self.shard_world - 1) // self.shard_world
+
+    def shard_rows(self, group=None) -> None:
+        """Collective.  Keep rows {i : i % G == rank} (local row i // G) in a peer-shareable buffer; every rank's kernels read
+        the other shards directly over NVLink.  The interleaved split spreads the hot head of a frequency-ordered vocabulary
+        (features.py:119-127) evenly over the GPUs."""
+        import torch.distributed as dist
+
+        from pkg.modelling._peer import PeerBuffer
+
+        if self.shard_world > 1:
+            return
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world == 1:
+            return
+        full = self.weight
+        self.shard_rank, self.shard_world, self._group = rank, world, group
+        self._peer = PeerBuffer((self.local_rows, self.e), "float32", group)
+        mine = full[rank::world]
+        self._peer.local[: mine.shape[0]].copy_(mine)
+        self.weight = self._peer.local
+
+    def table_pointer(self) -> int:
+        """What tt_feature.table holds: the table itself, or the device array of shard base pointers."""
+        return self.weight.data_ptr() if self.shard_world == 1 else self._peer.ptr_table.data_ptr()
+
+    def full_weight(self):
+        """(rows, e) table; collective when the table is row-sharded (all-gather of the shards)."""
+        if self.shard_world == 1:
+            return self.weight
+        import torch.distributed as dist
+
+        torch = N.require_cuda()
+        g = self.shard_world
+        shards = torch.empty((g,) + tuple(self.weight.shape), dtype=torch.float32, device="cuda")
+        dist.all_gather_into_tensor(shards, self.weight.contiguous(), group=self._group)
+        full = torch.empty((self.rows, self.e), dtype=torch.float32, device="cuda")
+        for r in range(g):
+            n_r = (self.rows - r + g - 1) // g
+            full[r::g] = shards[r, :n_r]
+        return full
 
 
 class InputLayer:
@@ -84,9 +131,12 @@ class InputLayer:
 
     def descriptors(self, bufs):
         return D.feature_array(
-            {"table": None if t is None else t.weight.data_ptr(), "src": buf.data_ptr(), "rows": 0 if t is None else t.rows,
-             "e": w, "col": c}
+            {"table": None if t is None else t.table_pointer(), "src": buf.data_ptr(), "rows": 0 if t is None else t.rows,
+             "e": w, "col": c, "shards": 0 if t is None or t.shard_world == 1 else t.shard_world}
             for (f, t, c, w), buf in zip(self.blocks, bufs))
+
+    def sharded(self) -> bool:
+        return any(t.shard_world > 1 for t in self.embedding_layers.values())
 
     def batch_size(self, x: Dict[str, object]) -> int:
         return D.batch_size_of(x[self.blocks[0][0].name])
@@ -110,4 +160,4 @@ class InputLayer:
         return self.embedding_layers
 
     def state_arrays(self, prefix: str = "") -> Dict[str, np.ndarray]:
-        return {f"{prefix}embedding/{n}": t.weight.detach().cpu().numpy() for n, t in self.embedding_layers.items()}
+        return {f"{prefix}embedding/{n}": t.full_weight().detach().cpu().numpy() for n, t in self.embedding_layers.items()}

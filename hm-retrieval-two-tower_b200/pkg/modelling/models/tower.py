@@ -106,10 +106,17 @@ class Tower(AbstractKerasModel):
         il = self.input_layer
         last = len(self.layer_units) - 1
         n0 = self.layer_units[0]
-        N.check(lib.tt_input_dense_fwd(ws.feats, len(il.blocks), il.output_dim, self.kernels[0].data_ptr(),
-                                       self.biases[0].data_ptr(), ws.x.data_ptr() if keep_input else None, il.ld,
-                                       ws.acts[0].data_ptr(), n0, ws.out_tf32.data_ptr() if last == 0 else None,
-                                       ws.batch, n0, 1, st), "tt_input_dense_fwd")
+        if il.sharded():
+            # row-sharded tables: most rows live in other GPUs' HBM.  A dedicated gather with every 16-byte load independent pays
+            # the NVLink latency once; the first Dense then reads the local copy (bit-identical to the fused kernel).
+            N.check(lib.tt_gather_concat(ws.feats, len(il.blocks), ws.batch, il.output_dim, ws.x.data_ptr(), il.ld, st), "tt_gather_concat")
+            N.check(lib.tt_dense_fwd(ws.x.data_ptr(), il.ld, self.kernels[0].data_ptr(), self.biases[0].data_ptr(), ws.acts[0].data_ptr(), n0,
+                                     ws.out_tf32.data_ptr() if last == 0 else None, ws.batch, il.output_dim, n0, 1, st), "tt_dense_fwd")
+        else:
+            N.check(lib.tt_input_dense_fwd(ws.feats, len(il.blocks), il.output_dim, self.kernels[0].data_ptr(),
+                                           self.biases[0].data_ptr(), ws.x.data_ptr() if keep_input else None, il.ld,
+                                           ws.acts[0].data_ptr(), n0, ws.out_tf32.data_ptr() if last == 0 else None,
+                                           ws.batch, n0, 1, st), "tt_input_dense_fwd")
         k = n0
         for i in range(1, len(self.layer_units)):
             n = self.layer_units[i]

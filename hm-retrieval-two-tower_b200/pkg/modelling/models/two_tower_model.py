@@ -194,6 +194,7 @@ class TwoTowerModel(AbstractKerasModel):
             jobs[j].slot0 = slots[0].data_ptr()
             jobs[j].slot1 = slots[1].data_ptr() if len(slots) > 1 else None
             jobs[j].rows, jobs[j].e, jobs[j].nsrc = table.rows, table.e, len(lst)
+            jobs[j].shard_rank, jobs[j].shard_world = (table.shard_rank, table.shard_world) if table.shard_world > 1 else (0, 0)
             n_per = lst[0][0].numel()
             jobs[j].n_per_src = n_per
             for s, (ids, gptr, gld) in enumerate(lst):
@@ -325,7 +326,7 @@ class TwoTowerModel(AbstractKerasModel):
                 torch.cuda.current_stream().synchronize()
                 sw.graph = "pending"
             elif sw.graph == "pending":
-                if self.dist is None:   # the whole step is one graph
+                if self.dist is None or self.dist.peer_sync:   # the whole step is one graph (peer_sync: the ranks are ordered by device barriers inside it)
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         self._launch_step(sw)

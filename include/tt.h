@@ -59,6 +59,30 @@ int tt_debug_index_cap(int cap);
 /* Profiling knob: while `host_ms8` (8 host floats, or NULL to stop) is set, every tensor-core tt_index_topk call adds
  * the device time of its stages (prep, filter, select, collect, rescore, fallback) to it and synchronises. */
 int tt_debug_index_stages(float* host_ms8);
+/* ------------------------------------------------------------------------------------------------
+ * Peer-shareable device memory (one process per GPU): row-sharded embedding tables and the towers' dX
+ * blocks are read by the other GPUs' kernels directly over NVLink.  tt_peer_alloc: cudaMalloc (zero-filled) on the
+ * current device + a 64-byte CUDA IPC handle to hand to the other processes (any transport; the host layer uses
+ * torch.distributed.all_gather_object).  tt_peer_open maps another process's allocation into this one (peer access
+ * enabled lazily); the pointer is valid in kernels launched on the current device.  Set-up calls, never on the hot path.
+ * ---------------------------------------------------------------------------------------------- */
+#define TT_PEER_HANDLE_BYTES 64
+int tt_peer_alloc(size_t bytes, void** ptr, void* handle /* TT_PEER_HANDLE_BYTES */);
+int tt_peer_open(const void* handle, void** ptr);
+int tt_peer_close(void* ptr);
+int tt_peer_free(void* ptr);
+/* Barrier across the G ranks of a peer group, executed by a kernel on `stream` (capturable in a CUDA graph; no NCCL).
+ * `flag_blocks`: device array of G pointers; entry r = rank r's flag block, TT_PEER_FLAG_WORDS(G) zero-initialised uint32 in
+ * peer-shareable memory.  `slot` < TT_PEER_SLOTS names the barrier (each call site of a step uses its own slot).  On return of the
+ * kernel every rank's work queued on its stream before its own call is complete and visible to peer reads.  All ranks must call
+ * the same slots in the same order; a rank that waits ~10 s traps (the launch fails loudly instead of hanging the GPUs). */
+#define TT_PEER_SLOTS 4
+#define TT_PEER_FLAG_WORDS(G) (TT_PEER_SLOTS * (1 + (G)))
+int tt_peer_barrier(const void* flag_blocks, int rank, int world, int slot, void* stream);
+/* out[i] = sum over ranks r = 0..G-1 (in that order) of src_r[i]; `src_ptrs`: device array of G (peer-mapped) float pointers.
+ * Dense-gradient all-reduce of the data-parallel step, read in place. */
+int tt_peer_sum_f32(const void* src_ptrs, int world, int64_t n, float* out, void* stream);
+
 /* Number of kernels this library has launched (or captured into a CUDA graph) in this process so far. */
 int64_t tt_launch_count(void);
 
@@ -73,7 +97,9 @@ typedef struct tt_feature {
     int32_t rows;
     int32_t e;
     int32_t col;        /* first output column of this block */
-    int32_t _pad;
+    int32_t shards;     /* 0 or 1: `table` is the whole table.  G > 1: the table is row-sharded over G GPUs and `table` is really a
+                         * device array of G base pointers (const float* const*): row i lives in shard i % G at local row i / G.
+                         * Shards of other GPUs are peer-mapped HBM (CUDA IPC over NVLink); rows are read where they live. */
 } tt_feature;
 
 /* X[b, col_f : col_f+e_f] = table_f[ids_f[b]]  (or the numeric value); columns [D, ldx) are zeroed.
@@ -152,8 +178,10 @@ typedef struct tt_sparse_job {
     int32_t e;
     int32_t nsrc;  /* number of (ids, grad) sources feeding this table */
     int32_t n_per_src; /* rows per source (the batch size) */
+    int32_t shard_rank;  /* row-sharded table (shard_world > 1): `table`/`slot*` are THIS rank's shard ((rows + G - 1) / G local rows); */
+    int32_t shard_world; /* only ids with id % shard_world == shard_rank are applied, at local row id / shard_world.  0/1: whole table */
     const int32_t* ids[TT_MAX_SRC];
-    const float* grad[TT_MAX_SRC]; /* first column of this feature's slice of dX */
+    const float* grad[TT_MAX_SRC]; /* first column of this feature's slice of dX (may be peer-mapped memory of another GPU) */
     int32_t grad_ld[TT_MAX_SRC];
 } tt_sparse_job;
 

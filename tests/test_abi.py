@@ -32,7 +32,7 @@ def test_struct_layout_matches_header(lib):
     from pkg import _native as N
 
     assert ctypes.sizeof(N.TTFeature) == 32
-    assert ctypes.sizeof(N.TTSparseJob) == 24 + 16 + 8 * N.TT_MAX_SRC * 2 + 4 * N.TT_MAX_SRC
+    assert ctypes.sizeof(N.TTSparseJob) == 24 + 24 + 8 * N.TT_MAX_SRC * 2 + 4 * N.TT_MAX_SRC
 
 
 def test_argument_errors_do_not_need_a_gpu(lib):

@@ -395,3 +395,69 @@ def test_recall_hits_integer_exact(lib, T):
     for _ in range(2):                                     # accumulates across calls
         N.check(lib.tt_recall_hits(dcand.data_ptr(), k, dtruth.data_ptr(), nq, ks.ctypes.data, 3, hits.data_ptr(), stream()))
     assert hits.cpu().numpy().tolist() == (2 * want).tolist()
+
+
+# ---------------------------------------------------------------------------------------------------
+# row-sharded tables (tt_feature.shards, tt_sparse_job.shard_rank/shard_world).  On one GPU every "shard" is local
+# memory; across processes the same kernels dereference peer-mapped pointers (tests/test_gpu_multi.py).
+# ---------------------------------------------------------------------------------------------------
+def _shard(T, full, g):
+    rows, e = full.shape
+    local = (rows + g - 1) // g
+    out = []
+    for r in range(g):
+        s = np.zeros((local, e), np.float32)
+        part = full[r::g]
+        s[: part.shape[0]] = part
+        out.append(dev(T, s))
+    return out
+
+
+@pytest.mark.parametrize("g", [2, 3, 8])
+def test_row_sharded_gather_and_sparse_adagrad_equal_unsharded(lib, T, g):
+    from pkg import _native as N
+
+    rng = np.random.default_rng(40 + g)
+    rows, e, B = 1001, 64, 700
+    table = rng.standard_normal((rows, e)).astype(np.float32)
+    ids = np.minimum(rng.zipf(1.2, size=B) - 1, rows - 1).astype(np.int32)
+    ids[5] = rows + 3                                        # out of range -> OOV row 0 (owned by shard 0)
+    d_ids = dev(T, ids)
+    shards = _shard(T, table, g)
+    ptrs = T.tensor([s.data_ptr() for s in shards], dtype=T.int64, device="cuda")
+    # gather: sharded descriptor == plain descriptor
+    d_table = dev(T, table)
+    X0 = T.empty((B, e), dtype=T.float32, device="cuda"); X1 = T.empty_like(X0)
+    N.check(lib.tt_gather_concat(feats_array(N, [dict(table=d_table.data_ptr(), src=d_ids.data_ptr(), rows=rows, e=e, col=0)]), 1, B, e,
+                                 X0.data_ptr(), e, stream()))
+    N.check(lib.tt_gather_concat(feats_array(N, [dict(table=ptrs.data_ptr(), src=d_ids.data_ptr(), rows=rows, e=e, col=0, shards=g)]), 1, B, e,
+                                 X1.data_ptr(), e, stream()))
+    assert T.equal(X0, X1)
+    # sparse Adagrad: every "rank" applies its own rows; reassembled == the oracle on the whole table
+    grad = rng.standard_normal((B, e)).astype(np.float32)
+    d_grad = dev(T, grad)
+    accs = [T.full_like(s, 0.1) for s in shards]
+    ws = T.empty(int(lib.tt_sparse_workspace_bytes(1, B, e)), dtype=T.uint8, device="cuda")
+    for r in range(g):
+        jobs = (N.TTSparseJob * 1)()
+        jobs[0].table, jobs[0].slot0, jobs[0].slot1 = shards[r].data_ptr(), accs[r].data_ptr(), None
+        jobs[0].rows, jobs[0].e, jobs[0].nsrc, jobs[0].n_per_src = rows, e, 1, B
+        jobs[0].shard_rank, jobs[0].shard_world = r, g
+        jobs[0].ids[0], jobs[0].grad[0], jobs[0].grad_ld[0] = d_ids.data_ptr(), d_grad.data_ptr(), e
+        N.check(lib.tt_sparse_sort(jobs, 1, ws.data_ptr(), ws.numel(), stream()))
+        N.check(lib.tt_sparse_adagrad(jobs, 1, 0.05, 1e-7, ws.data_ptr(), ws.numel(), stream()))
+    T.cuda.synchronize()
+    # oracle: the update of shard r is the de-duplicated update of the entries it owns, in their original order (runs are summed
+    # piecewise along 32-entry blocks of the SORTED OWNED list, so the rounding of a heavily duplicated row may differ in the last
+    # bit from the unsharded update -- compared with a tolerance below, bit-exactly against the per-shard oracle here)
+    ids_c = np.where((ids < 0) | (ids >= rows), 0, ids)
+    whole = table.copy(); whole_acc = np.full_like(table, 0.1)
+    O.adagrad_sparse(whole, whole_acc, O.IndexedSlices(ids_c, grad), 0.05)
+    for r in range(g):
+        n_r = (rows - r + g - 1) // g
+        mine = ids_c % g == r
+        t_r = np.ascontiguousarray(table[r::g]); a_r = np.full_like(t_r, 0.1)
+        O.adagrad_sparse(t_r, a_r, O.IndexedSlices(ids_c[mine] // g, grad[mine]), 0.05)
+        assert np.array_equal(shards[r].cpu().numpy()[:n_r], t_r)
+        assert np.array_equal(accs[r].cpu().numpy()[:n_r], a_r)
+        np.testing.assert_allclose(t_r, whole[r::g], rtol=0, atol=1e-6)
