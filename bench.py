@@ -339,25 +339,37 @@ def run_ours(args):
 
 
 def dp_phase_times(model, B, dev_batches, n=20):
-    """Device time of the four phases of a data-parallel step (rank-local CUDA events; explains the scaling number)."""
+    """Device time of the four phases of a data-parallel step (rank-local CUDA events; explains the scaling number).  The phases are
+    replayed as separate CUDA graphs here (the timed step itself is one graph when the ranks synchronise through device barriers), so
+    the barrier phases show how long this rank waited for the slowest one."""
     import torch
 
     sw = model._step_ws(B)
-    if not isinstance(sw.graph, tuple) or len(sw.graph) != 2:
+    if not isinstance(sw.graph, tuple):
         return None
+    if len(sw.graph) == 2:
+        phases = [lambda: model._phase_pre(sw), sw.graph[0].replay, lambda: model._phase_mid(sw), sw.graph[1].replay]
+    else:
+        graphs = []
+        for fn in (model._phase_pre, model._phase_a, model._phase_mid, model._phase_b):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn(sw)
+            graphs.append(g)
+        phases = [g.replay for g in graphs]
     acc = [0.0] * 4
     for i in range(n):
         model._stage(sw, dev_batches[i % len(dev_batches)])
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        ev[0].record(); model._phase_pre(sw)
-        ev[1].record(); sw.graph[0].replay()
-        ev[2].record(); model._phase_mid(sw)
-        ev[3].record(); sw.graph[1].replay()
+        for k in range(4):
+            ev[k].record()
+            phases[k]()
         ev[4].record()
         torch.cuda.synchronize()
         for k in range(4):
             acc[k] += ev[k].elapsed_time(ev[k + 1]) / n
-    return {"ids_allgather": acc[0], "phase_a_graph": acc[1], "grads_allgather": acc[2], "phase_b_graph": acc[3]}
+    return {"sync_ids": acc[0], "phase_a": acc[1], "sync_grads": acc[2], "phase_b": acc[3],
+            "note": "this rank's CUDA events; sync_* = NCCL all-gather or device barrier incl. waiting for the slowest rank"}
 
 
 def softmax_roofline(model, B, pk, lib):

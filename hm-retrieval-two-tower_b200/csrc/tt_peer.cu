@@ -52,6 +52,16 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(const unsigned long long*
     }
 }
 
+// out[r][i] = src_r[i] for every rank r: all-gather by peer reads (16-byte loads when n is a multiple of 4 floats)
+__global__ void __launch_bounds__(256) peer_gather_kernel(const unsigned long long* __restrict__ srcs, int world, int64_t n4, float4* __restrict__ out) {
+    const int64_t total = n4 * world;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int r = (int)(i / n4);
+        out[i] = __ldg(reinterpret_cast<const float4*>(srcs[r]) + (i - (int64_t)r * n4));
+    }
+}
+
 }  // namespace tt
 
 using namespace tt;
@@ -73,6 +83,18 @@ int tt_peer_sum_f32(const void* src_ptrs, int world, int64_t n, float* out, void
     if (g > 4 * (int64_t)sm_count()) g = 4 * (int64_t)sm_count();
     peer_sum_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(src_ptrs), world, n, out);
     TT_LAUNCH_OK("peer_sum_kernel");
+    return TT_OK;
+}
+
+int tt_peer_gather_f32(const void* src_ptrs, int world, int64_t n, float* out, void* stream) {
+    TT_REQUIRE(src_ptrs != nullptr && out != nullptr && world >= 1 && n >= 0, "tt_peer_gather_f32: bad arguments");
+    TT_REQUIRE(n % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "tt_peer_gather_f32: n must be a multiple of 4 floats, buffers 16-byte aligned");
+    if (n == 0) return TT_OK;
+    int64_t g = ceil_div(n / 4 * world, 256);
+    if (g > 8 * (int64_t)sm_count()) g = 8 * (int64_t)sm_count();
+    peer_gather_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(src_ptrs), world, n / 4,
+                                                                     reinterpret_cast<float4*>(out));
+    TT_LAUNCH_OK("peer_gather_kernel");
     return TT_OK;
 }
 

@@ -319,13 +319,17 @@ __global__ void __launch_bounds__(256) sparse_stage_kernel(const __grid_constant
     const tt_sparse_job& job = jobs.j[blockIdx.y];
     if (pl.stage == nullptr) return;
     const int lane = threadIdx.x & 31;
-    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= pl.n) return;
-    const uint32_t key = pl.keys[pl.npass & 1][j];
-    if (key == skip_key(job)) return;
-    const float* src = grad_row(job, pl.vals[pl.npass & 1][j]);
-    float* dst = pl.stage + (int64_t)j * job.e;
-    for (int c = lane; c < job.e; c += 32) dst[c] = __ldg(src + c);
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t* ks = pl.keys[pl.npass & 1];
+    const int32_t* vs = pl.vals[pl.npass & 1];
+    const uint32_t skip = skip_key(job);
+    // the owned entries are a prefix of the sorted array (the skip key sorts last): grid-stride over it, stop at the first foreign entry
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < pl.n; j += nw) {
+        if (ks[j] == skip) break;
+        const float* src = grad_row(job, vs[j]);
+        float* dst = pl.stage + (int64_t)j * job.e;
+        for (int c = lane; c < job.e; c += 32) dst[c] = __ldg(src + c);
+    }
 }
 
 // phase A: grid (ceil(max_blocks / 8), njobs), 8 warps per CTA, one warp per block of 32 sorted entries
@@ -383,10 +387,25 @@ __global__ void __launch_bounds__(256) sparse_combine_kernel(const __grid_consta
     // this block holds the head of the run (either mid-block, or at lane 0 with a different predecessor)
     const int e = job.e;
     int last = b + 1;                                    // last block touched by the run
-    while ((last + 1) * 32 < pl.n && ks[(last + 1) * 32] == id) ++last;
+    const bool longer = (int64_t)(last + 1) * 32 < pl.n && ks[(int64_t)(last + 1) * 32] == id;
+    while (longer) {                                     // a hot id spanning many blocks: the lanes probe 32 blocks at a time
+        const int64_t idx = (int64_t)(last + 1 + lane) * 32;
+        const bool same = idx < pl.n && ks[idx] == id;
+        const uint32_t m = __ballot_sync(0xffffffffu, same);
+        if (m == 0xffffffffu) { last += 32; continue; }
+        last += __ffs(~m) - 1;
+        break;
+    }
     for (int c = lane; c < e; c += 32) {
         float g = pl.partR[(int64_t)b * e + c];
-        for (int nb = b + 1; nb <= last; ++nb) g = __fadd_rn(g, pl.partL[(int64_t)nb * e + c]);
+        for (int nb0 = b + 1; nb0 <= last; nb0 += 8) {  // pieces added in block order; eight loads in flight
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = (nb0 + t <= last) ? pl.partL[(int64_t)(nb0 + t) * e + c] : 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                if (nb0 + t <= last) g = __fadd_rn(g, v[t]);
+        }
         apply_row(job, kMode, id, c, g, lr, eps, omb1, omb2);
     }
 }
@@ -480,7 +499,9 @@ static int launch_apply(const JobArr& ja, const PlanArr& pa, int njobs, int mode
     int max_n = 0;
     for (int j = 0; j < pa.n; ++j) { staged |= pa.p[j].stage != nullptr; max_n = pa.p[j].n > max_n ? pa.p[j].n : max_n; }
     if (staged) {
-        sparse_stage_kernel<<<dim3((unsigned)ceil_div(max_n > 0 ? max_n : 1, 8), (unsigned)njobs), 256, 0, st>>>(ja, pa);
+        int64_t sg = ceil_div(max_n > 0 ? max_n : 1, 8);
+        if (sg > 4 * (int64_t)sm_count()) sg = 4 * (int64_t)sm_count();
+        sparse_stage_kernel<<<dim3((unsigned)sg, (unsigned)njobs), 256, 0, st>>>(ja, pa);
         TT_LAUNCH_OK("sparse_stage_kernel");
     }
     sparse_block_kernel<<<grid, 256, 0, st>>>(ja, pa, mode, lr, eps, omb1, omb2);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "tt_peer_free": (c_int, [c_void_p]),
     "tt_peer_barrier": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "tt_peer_sum_f32": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "tt_peer_gather_f32": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "tt_debug_index_cap": (c_int, [c_int]),
     "tt_debug_index_stages": (c_int, [c_void_p]),
     # host-side helpers (csrc/tt_host.cu)

@@ -79,7 +79,8 @@ class _DevPtr:
 class DataParallel:
     """Attach to a compiled-or-not TwoTowerModel: ``DataParallel(model)``; then call model.train_step as usual."""
 
-    def __init__(self, model, group=None, shard_tables: Optional[bool] = None, peer_sync: Optional[bool] = None):
+    def __init__(self, model, group=None, shard_tables: Optional[bool] = None, peer_sync: Optional[bool] = None,
+                 global_negatives: bool = False):
         import torch.distributed as dist
 
         from pkg import _native as N
@@ -96,6 +97,13 @@ class DataParallel:
         # gradients in place, so a step contains no NCCL call and is captured as ONE CUDA graph.  False: the two small NCCL
         # all-gathers (ids, dense gradients) order the ranks instead.
         self.peer_sync = self.shard_tables and (os.environ.get("TT_DP_EXCHANGE", "peer") != "nccl" if peer_sync is None else bool(peer_sync))
+        # global_negatives (BASELINE configs[4], SURVEY.md 8e "training with global negatives"): every rank scores its B query rows
+        # against the candidates of ALL ranks (G.B columns, diagonal offset rank.B) -- the step of ONE reference process on the
+        # concatenated batch.  Candidate embeddings / logQ terms are all-gathered and the partial dC reduce-scattered by peer reads
+        # between device barriers, so it needs the peer_sync layout.
+        self.global_negatives = bool(global_negatives) and self.world > 1
+        if self.global_negatives and not self.peer_sync:
+            raise ValueError("global_negatives needs row-sharded tables with peer_sync (device barriers + peer reads)")
         model.dist = self
         model._steps.clear()
         # replicas must start identical: parameters are broadcast from rank 0
@@ -169,6 +177,26 @@ class DataParallel:
                 dp["peer_dense"] = PeerBuffer((max(n_dense, 64),), "float32", self.group)
                 dp["dense_local"] = dp["peer_dense"].local
                 dp["peer_flags"] = PeerBuffer((N.TT_PEER_SLOTS * (1 + g),), "int32", self.group)
+                if self.global_negatives:
+                    e = model.joint_embedding_size
+                    if b % 4:
+                        raise ValueError("global_negatives: the per-rank batch must be a multiple of 4")
+                    lib = N.load()
+                    use_tc = model.impl != N.TT_IMPL_SIMT and model._tc_ok()
+                    dp["peer_c"] = PeerBuffer((b, e), "float32", self.group)          # this rank's candidate embeddings, as the softmax consumes them
+                    if use_tc:
+                        sw.c.out_tf32 = dp["peer_c"].local
+                    else:
+                        sw.c.acts[-1] = dp["peer_c"].local
+                    dp["c_all"] = torch.zeros((g * b, e), dtype=torch.float32, device="cuda")
+                    if sw.col_bias is not None:
+                        dp["peer_bias"] = PeerBuffer((b,), "float32", self.group)
+                        sw.col_bias = dp["peer_bias"].local
+                        dp["bias_all"] = torch.zeros(g * b, dtype=torch.float32, device="cuda")
+                    dp["peer_dc"] = PeerBuffer((g * b, e), "float32", self.group)     # d(loss of MY rows)/d(all candidates)
+                    # reduce-scatter sources: every rank's partial, offset to the slice of my own candidates
+                    dp["dc_srcs"] = torch.tensor([p + 4 * self.rank * b * e for p in dp["peer_dc"].ptrs], dtype=torch.int64, device="cuda")
+                    sw.sm_ws = torch.empty(int(lib.tt_softmax_workspace_bytes(b, g * b, e)), dtype=torch.uint8, device="cuda")
                 self.barrier()                          # every rank's (zeroed) flag block exists before the first device barrier
             else:
                 dp["dense_local"] = torch.zeros(max(n_dense, 1), dtype=torch.float32, device="cuda")
@@ -238,6 +266,30 @@ class DataParallel:
             self._device_barrier(dp, 0)
         else:
             allgather_into(dp["ids_all"].view(self.world * dp["ids_local"].shape[0], -1), dp["ids_local"], self.group)
+
+    def gather_candidates(self, model, sw):
+        """global_negatives: (C_all, ln p_all or None, diagonal offset, number of columns) once every rank's candidate tower is done."""
+        from pkg import _native as N
+
+        dp = self._ensure(sw)
+        lib = N.load()
+        b, e, st = sw.batch, model.joint_embedding_size, N.stream_ptr()
+        self._device_barrier(dp, 2)
+        N.check(lib.tt_peer_gather_f32(dp["peer_c"].ptr_table.data_ptr(), self.world, b * e, dp["c_all"].data_ptr(), st), "tt_peer_gather_f32(C)")
+        bias_all = None
+        if "peer_bias" in dp:
+            N.check(lib.tt_peer_gather_f32(dp["peer_bias"].ptr_table.data_ptr(), self.world, b, dp["bias_all"].data_ptr(), st), "tt_peer_gather_f32(ln p)")
+            bias_all = dp["bias_all"]
+        return dp["c_all"], bias_all, self.rank * b, self.world * b
+
+    def reduce_dc(self, model, sw):
+        """global_negatives: dC of my own candidates = sum over ranks (rank order) of their partial gradients for my slice."""
+        from pkg import _native as N
+
+        dp = self._ensure(sw)
+        self._device_barrier(dp, 3)
+        N.check(N.load().tt_peer_sum_f32(dp["dc_srcs"].data_ptr(), self.world, sw.batch * model.joint_embedding_size, sw.dc.data_ptr(),
+                                         N.stream_ptr()), "tt_peer_sum_f32(dC)")
 
     def pack_dense(self, model, sw):
         """End of phase A (captured): the flat dense gradients join the message."""

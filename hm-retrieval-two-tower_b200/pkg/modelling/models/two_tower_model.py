@@ -259,9 +259,19 @@ class TwoTowerModel(AbstractKerasModel):
         impl = N.TT_IMPL_TC if use_tc else N.TT_IMPL_SIMT
         # loss, lse, dQ and dC in one call: one prep launch, forward, combine, ONE persistent launch for the dQ and the dC
         # pass, reduction; then dQ -> query tower on the main stream, dC -> candidate tower on the candidate stream
-        N.check(lib.tt_inbatch_softmax_step(qa.data_ptr(), e, ca.data_ptr(), e, bias, b, b, e, 0, sw.lse.data_ptr(), sw.loss.data_ptr(),
-                                            sw.dq.data_ptr(), e, sw.dc.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st),
-                "tt_inbatch_softmax_step")
+        if self.dist is not None and self.dist.global_negatives:
+            # cross-GPU in-batch negatives: my B query rows against the G.B candidates of all ranks (diagonal at rank.B); the
+            # partial dC over all candidates is reduce-scattered back to the candidates' owners
+            c_all, bias_all, off, bc = self.dist.gather_candidates(self, sw)
+            dc_all = sw.dp["peer_dc"].local
+            N.check(lib.tt_inbatch_softmax_step(qa.data_ptr(), e, c_all.data_ptr(), e, bias_all.data_ptr() if bias_all is not None else None,
+                                                b, bc, e, off, sw.lse.data_ptr(), sw.loss.data_ptr(), sw.dq.data_ptr(), e, dc_all.data_ptr(), e,
+                                                sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st), "tt_inbatch_softmax_step(global negatives)")
+            self.dist.reduce_dc(self, sw)
+        else:
+            N.check(lib.tt_inbatch_softmax_step(qa.data_ptr(), e, ca.data_ptr(), e, bias, b, b, e, 0, sw.lse.data_ptr(), sw.loss.data_ptr(),
+                                                sw.dq.data_ptr(), e, sw.dc.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st),
+                    "tt_inbatch_softmax_step")
         sw.cand.wait_stream(main)
         self.query_tower.backward_ws(sw.q, sw.dq)
         with torch.cuda.stream(sw.cand):

@@ -82,6 +82,10 @@ int tt_peer_barrier(const void* flag_blocks, int rank, int world, int slot, void
 /* out[i] = sum over ranks r = 0..G-1 (in that order) of src_r[i]; `src_ptrs`: device array of G (peer-mapped) float pointers.
  * Dense-gradient all-reduce of the data-parallel step, read in place. */
 int tt_peer_sum_f32(const void* src_ptrs, int world, int64_t n, float* out, void* stream);
+/* out[r * n + i] = src_r[i]: all-gather by peer reads (n a multiple of 4, buffers 16-byte aligned).  Candidate embeddings and their
+ * logQ terms for cross-GPU in-batch negatives (BASELINE configs[4]); the matching reduce-scatter of dC is tt_peer_sum_f32 over the
+ * ranks' partial-gradient buffers offset to this rank's slice. */
+int tt_peer_gather_f32(const void* src_ptrs, int world, int64_t n, float* out, void* stream);
 
 /* Number of kernels this library has launched (or captured into a CUDA graph) in this process so far. */
 int64_t tt_launch_count(void);
