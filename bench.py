@@ -248,7 +248,7 @@ def run_ours(args):
     if world > 1:
         from pkg.modelling.distributed import DataParallel
 
-        DataParallel(model, shard_tables=(args.tables == "sharded"))
+        DataParallel(model, shard_tables=(args.tables == "sharded"), global_negatives=args.global_negatives)
     model.use_cuda_graph = not args.no_graph   # data parallel: two captured compute phases around the eager NCCL exchanges
     rng = np.random.default_rng(1000 + rank)
     pool = 8
@@ -318,6 +318,8 @@ def run_ours(args):
     if world > 1:
         line["config"]["tables"] = "row-sharded over the GPUs (rows read / gradient rows pulled over NVLink peer memory)" if model.dist.shard_tables \
             else "replicated (all-gathered gradient rows)"
+        if args.global_negatives:
+            line["config"]["negatives"] = f"cross-GPU: {world * B} candidate columns per query row (all-gathered over NVLink peer memory)"
         line["dp_phases_ms"] = dp_phase_times(model, B, dev_batches)
         barrier()       # every rank's last table update has landed before anybody embeds the corpus
     if rank == 0:
@@ -588,6 +590,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--simt", action="store_true", help="force the exact fp32 CUDA-core contraction path")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--global-negatives", action="store_true",
+                    help="--gpus > 1: every rank scores its batch against the candidates of ALL ranks (BASELINE configs[4]); not the headline workload")
     ap.add_argument("--tables", default="sharded", choices=["sharded", "replicated"], help="embedding-table layout when --gpus > 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=10)
