@@ -55,7 +55,6 @@ class BruteForceIndex(AbstractKerasModel):
         # copies only the (B, k) result out (through a pinned buffer) instead of gathering on the host
         self._identifiers_dev = (torch.from_numpy(np.ascontiguousarray(identifiers)).cuda()
                                  if np.issubdtype(np.asarray(identifiers).dtype, np.integer) else None)
-        self._out_pinned = None
         self._candidates = candidates.contiguous()            # (N_local, E) fp32, non-trainable
         # operand preparation for the tensor-core filter, done once at build time: permuted TF32-rounded copy of
         # the corpus and the row norms (error bound of the filter); the exact fp32 rows stay authoritative
@@ -134,11 +133,13 @@ class BruteForceIndex(AbstractKerasModel):
         _, idx = self.query_indices(queries)
         if self._identifiers_dev is not None:
             ids_dev = self._identifiers_dev[idx.long().clamp_(min=0)]
-            if self._out_pinned is None or self._out_pinned.shape != ids_dev.shape or self._out_pinned.dtype != ids_dev.dtype:
-                self._out_pinned = torch.empty(ids_dev.shape, dtype=ids_dev.dtype).pin_memory()
-            self._out_pinned.copy_(ids_dev, non_blocking=True)
+            # result delivery without a second host copy: a pinned block from torch's caching host allocator receives the (B, k)
+            # identifiers and is handed to the caller as the numpy array itself (the array keeps the block alive; dropped arrays
+            # return their block to the cache, so steady state allocates nothing)
+            out = torch.empty(ids_dev.shape, dtype=ids_dev.dtype, pin_memory=True)
+            out.copy_(ids_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return self._out_pinned.numpy().copy()
+            return out.numpy()
         return self._identifiers[idx.cpu().numpy()]
 
     def positions_of(self, ids) -> np.ndarray:
@@ -154,5 +155,41 @@ class BruteForceIndex(AbstractKerasModel):
     def get_input_signature(self) -> Dict[str, TensorSpec]:
         return self.query_model.get_input_signature()
 
+    # ---- bulk build / reload -----------------------------------------------------------
+    @classmethod
+    def from_candidate_tower(cls, k: int, query_model, candidate_tower, candidate_batches: Iterable, id_col: str,
+                             shard: Optional[Tuple[int, int]] = None) -> "BruteForceIndex":
+        """The reference's ``candidate_ds.map(lambda x: (x[id_col], model.candidate_tower(x)))`` (runner.py:88-93) without a host
+        round trip: every batch is embedded on the device straight into one pre-sized (N, E) corpus buffer (no per-batch
+        tensors, no concatenate), which the index then adopts and prepares."""
+        torch = N.require_cuda()
+        batches = list(candidate_batches)
+        sizes = [int(np.asarray(b[id_col]).reshape(-1).shape[0]) for b in batches]
+        e = candidate_tower.joint_embedding_size
+        corpus = torch.empty((sum(sizes), e), dtype=torch.float32, device="cuda")
+        ids, lo = [], 0
+        for b, n in zip(batches, sizes):
+            out, _ = candidate_tower.embed_tf32({f.name: b[f.name] for f in candidate_tower.features})
+            corpus[lo:lo + n].copy_(out)
+            ids.append(np.asarray(b[id_col]).reshape(-1))
+            lo += n
+        return cls(k, query_model, [(np.concatenate(ids, axis=0), corpus)], shard=shard)
+
+    def save(self, model_path: str) -> None:
+        """identifiers + exact corpus rows as variables.npz under ``model_path`` (the reference exports a SavedModel here)."""
+        super().save(model_path)
+
+    @classmethod
+    def load(cls, model_path: str, k: int, query_model, shard: Optional[Tuple[int, int]] = None) -> "BruteForceIndex":
+        """Rebuild an index from what ``save`` wrote; the prepared (tensor-core) copy is regenerated on the device."""
+        import os
+
+        f = model_path if model_path.endswith(".npz") else os.path.join(model_path, "variables.npz")
+        with np.load(f) as z:
+            ids, cand = z["identifiers"], z["candidates"]
+        return cls(k, query_model, [(ids, cand)], shard=shard)
+
     def state_arrays(self) -> Dict[str, np.ndarray]:
-        return {"identifiers": np.asarray(self._identifiers).astype(str), "candidates": self._candidates.detach().cpu().numpy()}
+        ids = np.asarray(self._identifiers)
+        return {"identifiers": ids if np.issubdtype(ids.dtype, np.integer) else ids.astype(str),
+                "candidates": self._candidates.detach().cpu().numpy()}

@@ -161,3 +161,14 @@ class InputLayer:
 
     def state_arrays(self, prefix: str = "") -> Dict[str, np.ndarray]:
         return {f"{prefix}embedding/{n}": t.full_weight().detach().cpu().numpy() for n, t in self.embedding_layers.items()}
+
+    def load_state_arrays(self, arrs, prefix: str = "") -> None:
+        """Inverse of state_arrays (row-sharded tables keep their own rows)."""
+        torch = N.require_cuda()
+        for n, t in self.embedding_layers.items():
+            a = np.asarray(arrs[f"{prefix}embedding/{n}"], dtype=np.float32)
+            if a.shape != (t.rows, t.e):
+                raise ValueError(f"embedding {n}: saved shape {a.shape} != {(t.rows, t.e)}")
+            if t.shard_world > 1:
+                a = a[t.shard_rank::t.shard_world]
+            t.weight[: a.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(a)))

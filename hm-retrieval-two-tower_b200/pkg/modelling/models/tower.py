@@ -174,6 +174,29 @@ class Tower(AbstractKerasModel):
     def get_input_signature(self) -> Dict[str, TensorSpec]:
         return {f.name: TensorSpec((None, 1), f.dtype, f.name) for f in self.features}
 
+    def load_state_arrays(self, arrs, prefix: str = "") -> None:
+        """Inverse of state_arrays: restores tables, kernels and biases (shapes must match this tower's schema)."""
+        torch = N.require_cuda()
+        self.input_layer.load_state_arrays(arrs, prefix)
+        for i, (w, b) in enumerate(zip(self.kernels, self.biases)):
+            kw, kb = np.asarray(arrs[f"{prefix}dense_{i}/kernel"], np.float32), np.asarray(arrs[f"{prefix}dense_{i}/bias"], np.float32)
+            if kw.shape != tuple(w.shape) or kb.shape != tuple(b.shape):
+                raise ValueError(f"dense_{i}: saved shapes {kw.shape}/{kb.shape} != {tuple(w.shape)}/{tuple(b.shape)}")
+            w.copy_(torch.from_numpy(kw)); b.copy_(torch.from_numpy(kb))
+
+    @staticmethod
+    def _read(path: str):
+        import os
+
+        f = path if path.endswith(".npz") else os.path.join(path, "variables.npz")
+        with np.load(f) as z:
+            return {k: z[k] for k in z.files}
+
+    def load(self, model_path: str) -> "Tower":
+        """Restore what ``save`` wrote (query_tower/ or candidate_tower/ directory, or its variables.npz)."""
+        self.load_state_arrays(self._read(model_path))
+        return self
+
     def state_arrays(self, prefix: str = "") -> Dict[str, np.ndarray]:
         arrs = self.input_layer.state_arrays(prefix)
         for i, (w, b) in enumerate(zip(self.kernels, self.biases)):

@@ -404,6 +404,21 @@ class TwoTowerModel(AbstractKerasModel):
         arrs.update(self.candidate_tower.state_arrays("candidate_tower/"))
         return arrs
 
+    def load(self, model_path: str) -> "TwoTowerModel":
+        """Restore the weights ``save(model_path)`` wrote (the two_tower/ directory next to ``model_path``, or a directory /
+        variables.npz given directly).  The reference has no load path; optimizer slots restart fresh."""
+        base = os.path.dirname(model_path)
+        cand = [os.path.join(base, "two_tower"), model_path]
+        path = next((c for c in cand if os.path.exists(os.path.join(c, "variables.npz")) or (c.endswith(".npz") and os.path.exists(c))), None)
+        if path is None:
+            raise FileNotFoundError(f"no saved two-tower variables under {cand}")
+        arrs = Tower._read(path)
+        self.query_tower.load_state_arrays(arrs, "query_tower/")
+        self.candidate_tower.load_state_arrays(arrs, "candidate_tower/")
+        if self.optimizer is not None:
+            self._build_optimizer_state()
+        return self
+
     def save(self, model_path: str) -> None:
         """two_tower/, query_tower/, candidate_tower/ next to ``model_path`` (reference :176-205), each holding
         variables.npz instead of a SavedModel."""

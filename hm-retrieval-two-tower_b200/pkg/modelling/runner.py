@@ -39,7 +39,10 @@ def _candidate_pairs(model: TwoTowerModel, candidate_ds, candidate_col: str):
 
 
 def evaluate(model: TwoTowerModel, schema: Schema, candidate_ds, test_ds, candidate_col: str) -> IndexRecall:
-    index = BruteForceIndex(max(schema.model_config.ks), model.query_tower, _candidate_pairs(model, candidate_ds, candidate_col))
+    # reference :88-93 maps the candidate tower over the candidate dataset and hands (ids, embeddings) pairs to the index;
+    # from_candidate_tower does the same on the device, straight into the corpus buffer (no per-batch host round trip)
+    index = BruteForceIndex.from_candidate_tower(max(schema.model_config.ks), model.query_tower, model.candidate_tower, candidate_ds,
+                                                 candidate_col)
     metric_calc = IndexRecall(index, schema.model_config.ks)
     for query_features, true_candidates in test_ds:
         metric_calc(query_features, true_candidates)

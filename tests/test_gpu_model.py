@@ -293,3 +293,57 @@ def test_index_over_trained_towers_recall_at_12_bit_exact(lib):
     metric(queries, truth)
     rec = O.RecallOracle([1, 12]); rec.update(truth, art[want])
     assert metric.hits[12] == rec.hits[12] and metric.metric[12] == rec.metric[12]
+
+
+def test_save_load_round_trip_and_bulk_index_build(lib, tmp_path):
+    """weights survive save -> load into a fresh model (bit-exact tower outputs); an index built by
+    BruteForceIndex.from_candidate_tower equals the one built from per-batch (ids, embeddings) pairs; a saved index reloads."""
+    import torch
+
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.indices.brute_force import BruteForceIndex
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+    from pkg.schema import dtypes as tt
+    from pkg.schema.features import Feature, FeatureFamily
+
+    def make(seed):
+        set_seed(seed)
+        qf = [Feature("age", tt.float32, FeatureFamily.QUERY), Feature("customer_id", tt.string, FeatureFamily.QUERY, embedding_size=32)]
+        cf = [Feature("article_id", tt.string, FeatureFamily.CANDIDATE, embedding_size=32),
+              Feature("colour_group_name", tt.string, FeatureFamily.CANDIDATE, embedding_size=8)]
+        qf[1].set_vocab_size(500); cf[0].set_vocab_size(6000); cf[1].set_vocab_size(50)
+        m = TwoTowerModel(qf, cf, "article_id", 32, query_tower_units=[48])
+        m.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))
+        return m
+
+    rng = np.random.default_rng(3)
+    m = make(1)
+    art = rng.integers(1, 6001, size=(256, 1)).astype(np.int32)
+    batch = {"age": rng.random((256, 1)).astype(np.float32), "customer_id": rng.integers(0, 501, size=(256, 1)).astype(np.int32),
+             "article_id": art, "colour_group_name": (art % 50 + 1).astype(np.int32)}
+    m.train_step(batch)
+    m.save(str(tmp_path / "model") + "/")
+    m2 = make(2)                                              # different initialisation
+    q = {"age": batch["age"], "customer_id": batch["customer_id"]}
+    assert not torch.equal(m.query_tower(q), m2.query_tower(q))
+    m2.load(str(tmp_path / "model") + "/")
+    assert torch.equal(m.query_tower(q), m2.query_tower(q))
+    c = {"article_id": batch["article_id"], "colour_group_name": batch["colour_group_name"]}
+    assert torch.equal(m.candidate_tower(c), m2.candidate_tower(c))
+    m3 = make(3)
+    m3.candidate_tower.load(str(tmp_path / "model" / "candidate_tower"))   # single-tower artefact
+    assert torch.equal(m.candidate_tower(c), m3.candidate_tower(c))
+    # bulk build == per-batch pairs (runner.py:88-93)
+    ids = np.arange(1, 6001, dtype=np.int32)
+    cand_batches = [{"article_id": ids[lo:lo + 2500].reshape(-1, 1), "colour_group_name": (ids[lo:lo + 2500] % 50 + 1).reshape(-1, 1)}
+                    for lo in range(0, 6000, 2500)]
+    pairs = [(b["article_id"].reshape(-1), m.candidate_tower(b)) for b in cand_batches]
+    a = BruteForceIndex(12, m.query_tower, pairs)
+    b = BruteForceIndex.from_candidate_tower(12, m.query_tower, m.candidate_tower, cand_batches, "article_id")
+    assert torch.equal(a._candidates, b._candidates) and np.array_equal(a._identifiers, b._identifiers)
+    want = a(q)
+    assert np.array_equal(want, b(q))
+    b.save(str(tmp_path / "index"))
+    c2 = BruteForceIndex.load(str(tmp_path / "index"), 12, m.query_tower)
+    assert np.array_equal(want, c2(q))
