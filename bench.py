@@ -324,7 +324,8 @@ def run_ours(args):
         barrier()       # every rank's last table update has landed before anybody embeds the corpus
     if rank == 0:
         line["roofline"] = softmax_roofline(model, B, pk, lib)
-        line["hbm_kernels"] = hbm_rooflines(pk, lib)
+        if not args.no_hbm:
+            line["hbm_kernels"] = hbm_rooflines(pk, lib)
     line["index"] = index_bench(model, pk, lib, K, world)      # every rank takes part (row-sharded corpus when N > 1)
     if world == 1:
         if not args.no_cpu:
@@ -387,12 +388,11 @@ def softmax_roofline(model, B, pk, lib):
     impl = N.TT_IMPL_TC if use_tc else N.TT_IMPL_SIMT
     bias = sw.col_bias.data_ptr() if sw.col_bias is not None else None
     st = N.stream_ptr()
+    ws = torch.empty(int(lib.tt_softmax_workspace_bytes(B, B, e)), dtype=torch.uint8, device="cuda")
 
-    def once():
-        N.check(lib.tt_inbatch_softmax_fwd(q.data_ptr(), e, c.data_ptr(), e, bias, B, B, e, 0, sw.lse.data_ptr(), sw.loss.data_ptr(),
-                                           sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st))
-        N.check(lib.tt_inbatch_softmax_bwd(q.data_ptr(), e, c.data_ptr(), e, bias, sw.lse.data_ptr(), B, B, e, 0, sw.dq.data_ptr(), e,
-                                           sw.dc.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st))
+    def once():   # the call the train step makes: shared operand prep, forward, combine, dQ+dC passes in one launch, reduction
+        N.check(lib.tt_inbatch_softmax_step(q.data_ptr(), e, c.data_ptr(), e, bias, B, B, e, 0, sw.lse.data_ptr(), sw.loss.data_ptr(),
+                                            sw.dq.data_ptr(), e, sw.dc.data_ptr(), e, ws.data_ptr(), ws.numel(), impl, st))
 
     for _ in range(3):
         once()
@@ -415,8 +415,8 @@ def softmax_roofline(model, B, pk, lib):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the two stream-K launches (forward 2.17 MB, backward 4.37 MB) from the
 # `ncu --set full` capture of this workload (B = 8192, E = 64); the operands are 2 x 1 MB of fp16 tiles + 2 x 2 MB fp32 outputs
-NCU_SOFTMAX_DRAM_BYTES = 2169088 + 4366336
-NCU_SOFTMAX_SOURCE = "profiles/r01b_softmax_streamk_ncu_full.md (ncu --set full, per launch, fwd + bwd)"
+NCU_SOFTMAX_DRAM_BYTES = 2169600 + 4365568 + 256
+NCU_SOFTMAX_SOURCE = "profiles/r01c_softmax_streamk_ncu_full.md (ncu --set full, per launch, fwd + bwd)"
 
 
 def hbm_rooflines(pk, lib, b=1 << 20, e=64, rows=V_CUSTOMERS + 1):
@@ -594,6 +594,7 @@ def main():
                     help="--gpus > 1: every rank scores its batch against the candidates of ALL ranks (BASELINE configs[4]); not the headline workload")
     ap.add_argument("--tables", default="sharded", choices=["sharded", "replicated"], help="embedding-table layout when --gpus > 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-hbm", action="store_true", help="skip the HBM-bound kernel rooflines (shorter ncu launch lists)")
     ap.add_argument("--cpu-steps", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
