@@ -178,12 +178,27 @@ __global__ void __launch_bounds__(256) fwd_combine_sk_kernel(const float* __rest
     if (r < nR) {
         const int first = (r >> 7) * n_tiles;
         const int parts = (sk_owner(first + n_tiles - 1, units, G) - sk_owner(first, units, G) + 1) * halves;
+        // the partials of a row are independent loads: fetch them eight at a time (the merge order is unchanged)
         float M = -CUDART_INF_F;
-        for (int s = 0; s < parts; ++s) M = fmaxf(M, m2[(int64_t)s * nR + r]);
+        for (int s0 = 0; s0 < parts; s0 += 8) {
+            float mv[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) mv[t] = (s0 + t < parts) ? m2[(int64_t)(s0 + t) * nR + r] : -CUDART_INF_F;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) M = fmaxf(M, mv[t]);
+        }
         float L = 0.f;
-        for (int s = 0; s < parts; ++s) {
-            float ms = m2[(int64_t)s * nR + r];
-            if (ms > -CUDART_INF_F) L += l[(int64_t)s * nR + r] * exp2f(ms - M);
+        for (int s0 = 0; s0 < parts; s0 += 8) {
+            float mv[8], lv[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const bool on = s0 + t < parts;
+                mv[t] = on ? m2[(int64_t)(s0 + t) * nR + r] : -CUDART_INF_F;
+                lv[t] = on ? l[(int64_t)(s0 + t) * nR + r] : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                if (mv[t] > -CUDART_INF_F) L += lv[t] * exp2f(mv[t] - M);
         }
         const float v = (M + log2f(L)) * 0.6931471805599453f;
         lse[r] = v;

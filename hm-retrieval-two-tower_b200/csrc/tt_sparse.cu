@@ -333,6 +333,9 @@ __global__ void __launch_bounds__(256) sparse_stage_kernel(const __grid_constant
 }
 
 // phase A: grid (ceil(max_blocks / 8), njobs), 8 warps per CTA, one warp per block of 32 sorted entries
+// kWide: eight runs in flight per warp for narrow tables (more registers, fewer round trips) -- the latency-bound regime of a
+// training step's batch; the bandwidth-bound regime (hundreds of thousands of entries) keeps four and the higher occupancy
+template <bool kWide>
 __global__ void __launch_bounds__(256) sparse_block_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans, int kMode,
                                                            float lr, float eps, float omb1, float omb2) {
     const SortPlan& pl = plans.p[blockIdx.y];
@@ -362,10 +365,64 @@ __global__ void __launch_bounds__(256) sparse_block_kernel(const __grid_constant
     float* partR = pl.partR + (int64_t)b * e;
     const float* stage = pl.stage ? pl.stage + (int64_t)base * e : nullptr;
     const int nc = (e + 31) >> 5;
-    if (nc <= 1) block_body<1, 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
-    else if (nc <= 2) block_body<2, 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
+    if (nc <= 1) block_body<1, kWide ? 8 : 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
+    else if (nc <= 2) block_body<2, kWide ? 8 : 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
     else if (nc <= 4) block_body<4, 2>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
     else block_body<8, 1>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
+}
+
+// pieces of one boundary-crossing run added in block order, all NC column groups of a lane at once, 16 / NC pieces per round of loads
+template <int NC>
+__device__ __forceinline__ void combine_body(const tt_sparse_job& job, const SortPlan& pl, int kMode, uint32_t id, int b, int last, int lane, float lr,
+                                             float eps, float omb1, float omb2) {
+    constexpr int T = 16 / NC;
+    const int e = job.e;
+    float g[NC];
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci) {
+        const int c = lane + 32 * ci;
+        g[ci] = c < e ? pl.partR[(int64_t)b * e + c] : 0.f;
+    }
+    for (int nb0 = b + 1; nb0 <= last; nb0 += T) {
+        float v[T][NC];
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int ci = 0; ci < NC; ++ci) {
+                const int c = lane + 32 * ci;
+                v[t][ci] = (nb0 + t <= last && c < e) ? pl.partL[(int64_t)(nb0 + t) * e + c] : 0.f;
+            }
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+            if (nb0 + t <= last) {
+#pragma unroll
+                for (int ci = 0; ci < NC; ++ci) g[ci] = __fadd_rn(g[ci], v[t][ci]);
+            }
+    }
+    // apply: state loads of all column groups first, then the update
+    float a[NC], w[NC];
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci) {
+        const int c = lane + 32 * ci;
+        const int64_t o = (int64_t)id * e + c;
+        a[ci] = c < e ? job.slot0[o] : 0.f;
+        w[ci] = c < e ? (kMode == kModeAdagrad ? job.table[o] : job.slot1[o]) : 0.f;
+    }
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci) {
+        const int c = lane + 32 * ci;
+        if (c >= e) continue;
+        const int64_t o = (int64_t)id * e + c;
+        const float gv = g[ci];
+        if (kMode == kModeAdagrad) {
+            const float an = __fadd_rn(a[ci], __fmul_rn(gv, gv));
+            job.slot0[o] = an;
+            job.table[o] = __fsub_rn(w[ci], __fdiv_rn(__fmul_rn(gv, lr), __fadd_rn(__fsqrt_rn(an), eps)));
+        } else {
+            job.slot0[o] = __fadd_rn(a[ci], __fmul_rn(gv, omb1));
+            job.slot1[o] = __fadd_rn(w[ci], __fmul_rn(__fmul_rn(gv, gv), omb2));
+        }
+    }
 }
 
 // phase B: the head block of every boundary-crossing run adds the pieces in block order and applies the update
@@ -396,18 +453,11 @@ __global__ void __launch_bounds__(256) sparse_combine_kernel(const __grid_consta
         last += __ffs(~m) - 1;
         break;
     }
-    for (int c = lane; c < e; c += 32) {
-        float g = pl.partR[(int64_t)b * e + c];
-        for (int nb0 = b + 1; nb0 <= last; nb0 += 8) {  // pieces added in block order; eight loads in flight
-            float v[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = (nb0 + t <= last) ? pl.partL[(int64_t)(nb0 + t) * e + c] : 0.f;
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-                if (nb0 + t <= last) g = __fadd_rn(g, v[t]);
-        }
-        apply_row(job, kMode, id, c, g, lr, eps, omb1, omb2);
-    }
+    const int nc = (e + 31) >> 5;
+    if (nc <= 1) combine_body<1>(job, pl, kMode, id, b, last, lane, lr, eps, omb1, omb2);
+    else if (nc <= 2) combine_body<2>(job, pl, kMode, id, b, last, lane, lr, eps, omb1, omb2);
+    else if (nc <= 4) combine_body<4>(job, pl, kMode, id, b, last, lane, lr, eps, omb1, omb2);
+    else combine_body<8>(job, pl, kMode, id, b, last, lane, lr, eps, omb1, omb2);
 }
 
 // Adam whole-table sweeps (legacy Adam is not lazy): phase 0: m *= b1, v *= b2; phase 1: w -= (m*lr_t)/(sqrt(v)+eps)
@@ -504,7 +554,8 @@ static int launch_apply(const JobArr& ja, const PlanArr& pa, int njobs, int mode
         sparse_stage_kernel<<<dim3((unsigned)sg, (unsigned)njobs), 256, 0, st>>>(ja, pa);
         TT_LAUNCH_OK("sparse_stage_kernel");
     }
-    sparse_block_kernel<<<grid, 256, 0, st>>>(ja, pa, mode, lr, eps, omb1, omb2);
+    if (max_n <= (1 << 17)) sparse_block_kernel<true><<<grid, 256, 0, st>>>(ja, pa, mode, lr, eps, omb1, omb2);
+    else sparse_block_kernel<false><<<grid, 256, 0, st>>>(ja, pa, mode, lr, eps, omb1, omb2);
     TT_LAUNCH_OK("sparse_block_kernel");
     sparse_combine_kernel<<<grid, 256, 0, st>>>(ja, pa, mode, lr, eps, omb1, omb2);
     TT_LAUNCH_OK("sparse_combine_kernel");

@@ -20,15 +20,18 @@ constexpr int kPanelMaxK = 256;
 
 // ---- forward: Y = relu?(X.W + b), X either dense or gathered from the embedding tables ----------------------
 // grid (ceil(B/64), ceil(N/64)), 256 threads, dynamic smem = 2 * K * PS floats (+ ids for the gather)
-template <bool kGather>
+// PM: batch rows per CTA (64, or 32 when that is what it takes to give every SM two CTAs: these launches are latency-bound)
+template <bool kGather, int PM>
 __global__ void __launch_bounds__(256) dense_fwd_panel_kernel(const __grid_constant__ FeatArr fa, const float* __restrict__ X, int ldx,
                                                               const float* __restrict__ W, const float* __restrict__ bias,
                                                               float* __restrict__ Xout, float* __restrict__ Y, int ldy,
                                                               float* __restrict__ Ytf32, int B, int K, int N, int relu) {
     extern __shared__ __align__(16) float sm[];
-    float* XsT = sm;                 // [K][PS]  XsT[k][r]
-    float* Ws = sm + (size_t)K * PS;  // [K][PS]  Ws[k][n]
-    const int m0 = blockIdx.x * PT, n0 = blockIdx.y * PT;
+    constexpr int PMS = PM + 4;      // padded row of the staged A operand
+    constexpr int RM = PM / 16;      // batch rows per thread
+    float* XsT = sm;                 // [K][PMS]  XsT[k][r]
+    float* Ws = sm + (size_t)K * PMS;  // [K][PS]  Ws[k][n]
+    const int m0 = blockIdx.x * PM, n0 = blockIdx.y * PT;
     const int tid = threadIdx.x;
     // All staging loops are flat and free of loop-carried dependences, so each thread keeps many independent
     // global loads in flight (these kernels are latency-bound: one CTA per SM, one staging phase per CTA).
@@ -38,7 +41,7 @@ __global__ void __launch_bounds__(256) dense_fwd_panel_kernel(const __grid_const
         Ws[k * PS + n] = (n0 + n < N) ? __ldg(W + (int64_t)k * N + n0 + n) : 0.f;
     }
     if constexpr (kGather) {
-        __shared__ int32_t s_ids[PT * TT_MAX_FEATURES];
+        __shared__ int32_t s_ids[PM * TT_MAX_FEATURES];
         __shared__ uint8_t s_feat[kPanelMaxK];
         __shared__ uint16_t s_off[kPanelMaxK];
         for (int c = tid; c < K; c += 256) {
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(256) dense_fwd_panel_kernel(const __grid_const
             s_feat[c] = ff;
             s_off[c] = oo;
         }
-        for (int i = tid; i < PT * fa.n; i += 256) {
+        for (int i = tid; i < PM * fa.n; i += 256) {
             const int r = i / fa.n, f = i - r * fa.n;
             int id = 0;
             if (m0 + r < B && fa.f[f].table != nullptr) {
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(256) dense_fwd_panel_kernel(const __grid_const
         __syncthreads();
         const bool write_x = (Xout != nullptr) && blockIdx.y == 0;
 #pragma unroll 8
-        for (int idx = tid; idx < PT * K; idx += 256) {   // consecutive threads -> consecutive columns of one row
+        for (int idx = tid; idx < PM * K; idx += 256) {   // consecutive threads -> consecutive columns of one row
             const int r = idx / K, k = idx - r * K;
             const int row = m0 + r;
             const int f = s_feat[k];
@@ -71,40 +74,46 @@ __global__ void __launch_bounds__(256) dense_fwd_panel_kernel(const __grid_const
                 v = (ft.table == nullptr) ? __ldg(reinterpret_cast<const float*>(ft.src) + row)
                                           : __ldg(feature_row(ft, s_ids[r * TT_MAX_FEATURES + f]) + s_off[k]);
             }
-            XsT[k * PS + r] = v;
+            XsT[k * PMS + r] = v;
             if (write_x && row < B) Xout[(int64_t)row * ldx + k] = v;
         }
         if (write_x) {
             const int padc = ldx - K;
-            for (int idx = tid; idx < PT * padc; idx += 256) {   // zero the padding columns
+            for (int idx = tid; idx < PM * padc; idx += 256) {   // zero the padding columns
                 const int r = idx / padc, c = K + idx - r * padc;
                 if (m0 + r < B) Xout[(int64_t)(m0 + r) * ldx + c] = 0.f;
             }
         }
     } else {
 #pragma unroll 8
-        for (int idx = tid; idx < PT * K; idx += 256) {
+        for (int idx = tid; idx < PM * K; idx += 256) {
             const int r = idx / K, k = idx - r * K;
-            XsT[k * PS + r] = (m0 + r < B) ? __ldg(X + (int64_t)(m0 + r) * ldx + k) : 0.f;
+            XsT[k * PMS + r] = (m0 + r < B) ? __ldg(X + (int64_t)(m0 + r) * ldx + k) : 0.f;
         }
     }
     __syncthreads();
     const int ty = tid >> 4, tx = tid & 15;
-    float acc[4][4] = {};
+    float acc[RM][4] = {};
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-        const float4 a4 = *reinterpret_cast<const float4*>(XsT + k * PS + ty * 4);
+        float a[RM];
+        if constexpr (RM == 4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(XsT + k * PMS + ty * 4);
+            a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+        } else {
+            const float2 a2 = *reinterpret_cast<const float2*>(XsT + k * PMS + ty * 2);
+            a[0] = a2.x; a[1] = a2.y;
+        }
         const float4 b4 = *reinterpret_cast<const float4*>(Ws + k * PS + tx * 4);
-        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
         const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < RM; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < RM; ++i) {
+        const int m = m0 + ty * RM + i;
         if (m >= B) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -234,7 +243,8 @@ __device__ __forceinline__ void dense_bwd_dw_tile(float* sm, int bx, int by, int
 // ---- one launch for the whole layer backward: dX tiles and dW/db chunk partials are independent -----------------------
 // blocks [0, n_dx) compute dX tiles (grid_dx = (gx, gy)); the rest compute dW partials (grid_dw = (nchunk, hy, hz)).
 constexpr int kDwSmemFloats = (PT * (kDwRows + 1) + 3) / 4 * 4 + PT * PS;
-__global__ void __launch_bounds__(256) dense_bwd_panel_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
+// three CTAs per SM (<= 85 registers): the 384 CTAs of a B = 8192 layer then fit one wave instead of 1.3
+__global__ void __launch_bounds__(256, 3) dense_bwd_panel_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
                                                               const float* __restrict__ Yv, int ldy, const float* __restrict__ dY, int lddy,
                                                               float* __restrict__ dX, int lddx, float* __restrict__ partial, int B, int K, int N,
                                                               int relu, int rows, int n_dx, int gx, int nchunk, int hy) {
@@ -276,19 +286,28 @@ __global__ void __launch_bounds__(256) dense_bwd_reduce4_kernel(const float* __r
 bool panel_fwd_ok(int K, int N) { return K >= 1 && K <= kPanelMaxK && N >= 1; }
 bool panel_bwd_ok(int K, int N) { return K >= 1 && K <= 1024 && N >= 1 && N <= kPanelMaxK; }
 
+template <bool G, int PM>
+static int launch_fwd_pm(const FeatArr& fa, const float* X, int ldx, const float* W, const float* b, float* Xout, float* Y, int ldy, float* Y32, int B,
+                         int K, int N, int relu, cudaStream_t st) {
+    const size_t smem = (size_t)K * (PM + 4 + PS) * sizeof(float);
+    static bool set = false;   // static + dynamic shared memory can exceed 48 KB even for small K: always opt in
+    if (!set) {
+        TT_CUDA_OK(cudaFuncSetAttribute(dense_fwd_panel_kernel<G, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kPanelMaxK * PS * sizeof(float))));
+        set = true;
+    }
+    dim3 grid((unsigned)ceil_div(B, PM), (unsigned)ceil_div(N, PT));
+    dense_fwd_panel_kernel<G, PM><<<grid, 256, smem, st>>>(fa, X, ldx, W, b, Xout, Y, ldy, Y32, B, K, N, relu);
+    TT_LAUNCH_OK("dense_fwd_panel_kernel");
+    return TT_OK;
+}
+
 template <bool G>
 static int launch_fwd(const FeatArr& fa, const float* X, int ldx, const float* W, const float* b, float* Xout, float* Y, int ldy, float* Y32, int B,
                       int K, int N, int relu, cudaStream_t st) {
-    const size_t smem = 2 * (size_t)K * PS * sizeof(float);
-    static bool set = false;   // static + dynamic shared memory can exceed 48 KB even for small K: always opt in
-    if (!set) {
-        TT_CUDA_OK(cudaFuncSetAttribute(dense_fwd_panel_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kPanelMaxK * PS * sizeof(float))));
-        set = true;
-    }
-    dim3 grid((unsigned)ceil_div(B, PT), (unsigned)ceil_div(N, PT));
-    dense_fwd_panel_kernel<G><<<grid, 256, smem, st>>>(fa, X, ldx, W, b, Xout, Y, ldy, Y32, B, K, N, relu);
-    TT_LAUNCH_OK("dense_fwd_panel_kernel");
-    return TT_OK;
+    // 32-row tiles while 64-row tiles would leave SMs with fewer than two CTAs
+    if (ceil_div(B, PT) * ceil_div(N, PT) < 2 * (int64_t)sm_count())
+        return launch_fwd_pm<G, 32>(fa, X, ldx, W, b, Xout, Y, ldy, Y32, B, K, N, relu, st);
+    return launch_fwd_pm<G, 64>(fa, X, ldx, W, b, Xout, Y, ldy, Y32, B, K, N, relu, st);
 }
 
 int panel_dense_fwd(const float* X, int ldx, const float* W, const float* b, float* Y, int ldy, float* Y32, int B, int K, int N, int relu,
