@@ -133,14 +133,32 @@ class BruteForceIndex(AbstractKerasModel):
         _, idx = self.query_indices(queries)
         if self._identifiers_dev is not None:
             ids_dev = self._identifiers_dev[idx.long().clamp_(min=0)]
-            # result delivery without a second host copy: a pinned block from torch's caching host allocator receives the (B, k)
-            # identifiers and is handed to the caller as the numpy array itself (the array keeps the block alive; dropped arrays
-            # return their block to the cache, so steady state allocates nothing)
-            out = torch.empty(ids_dev.shape, dtype=ids_dev.dtype, pin_memory=True)
+            # result delivery without a second host copy: the (B, k) identifiers land in a pinned buffer that is handed to the
+            # caller as the numpy array itself.  Buffers are recycled once the caller has dropped the array (and every view of it).
+            out, nd = self._pinned_result(tuple(ids_dev.shape), ids_dev.dtype)
             out.copy_(ids_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return out.numpy()
+            return nd
         return self._identifiers[idx.cpu().numpy()]
+
+    def _pinned_result(self, shape, dtype):
+        """A pinned host buffer nobody else references: (tensor, the numpy array viewing it)."""
+        import sys
+
+        torch = N.require_cuda()
+        pool = self.__dict__.setdefault("_pin_pool", [])
+        for i in range(len(pool)):
+            t, nd = pool[i]
+            # references to nd: the pool entry, the local name, getrefcount's argument; a caller's array or view adds more
+            if tuple(t.shape) == shape and t.dtype == dtype and sys.getrefcount(nd) <= 3:
+                return t, nd
+            del t, nd
+        t = torch.empty(shape, dtype=dtype).pin_memory()
+        nd = t.numpy()
+        if len(pool) >= 8:          # callers are holding many results: stop tracking the oldest buffer (it stays valid for its holder)
+            pool.pop(0)
+        pool.append((t, nd))
+        return t, nd
 
     def positions_of(self, ids) -> np.ndarray:
         """Global row index of each identifier (-1 when absent); used by IndexRecall's device path."""
