@@ -217,19 +217,6 @@ constexpr int kMaxColsPerLane = 8;   // embedding widths up to 256
 // (partL: the piece that continues a run begun in an earlier block; partR: the piece of a run that begins
 // here and continues) which phase B adds up from the run's head block.  The order depends only on the
 // sorted array, so the result is deterministic and equals oracle/two_tower_oracle.py:dedup_indexed_slices.
-__device__ __forceinline__ void apply_row(const tt_sparse_job& job, int kMode, uint32_t id, int c, float g, float lr, float eps, float omb1,
-                                          float omb2) {
-    const int64_t o = (int64_t)id * job.e + c;
-    if (kMode == kModeAdagrad) {
-        float a = __fadd_rn(job.slot0[o], __fmul_rn(g, g));
-        job.slot0[o] = a;
-        job.table[o] = __fsub_rn(job.table[o], __fdiv_rn(__fmul_rn(g, lr), __fadd_rn(__fsqrt_rn(a), eps)));
-    } else {  // Adam: scatter-add into the already decayed moments
-        job.slot0[o] = __fadd_rn(job.slot0[o], __fmul_rn(g, omb1));
-        job.slot1[o] = __fadd_rn(job.slot1[o], __fmul_rn(__fmul_rn(g, g), omb2));
-    }
-}
-
 // Body of phase A for one block, NC columns per lane, RB runs in flight.  The loads of a batch of RB runs
 // (first gradient row of each run plus the table / slot values their update will need) are issued together so a
 // block of 32 distinct ids costs ~32/RB memory round trips instead of 64.

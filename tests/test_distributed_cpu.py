@@ -59,6 +59,20 @@ def _dp_worker(rank, world, port, out):
         allgather_into(rows_all, torch.from_numpy(g.tables_c["c"].values.copy()))
         table = ct.tables["c"].copy(); acc = np.full_like(table, 0.1)
         O.adagrad_sparse(table, acc, O.IndexedSlices(ids_all.numpy(), rows_all.numpy()), 0.05)
+        # row-sharded table (DataParallel(shard_tables=True)): row i is owned by rank i % G at local row i // G; the owner applies
+        # the de-duplicated update of the entries it owns, in (rank, position) order; shards are all-gathered to compare
+        mine = ids_all.numpy() % world == rank
+        local = (20 + world - 1) // world
+        shard = np.zeros((local, 8), np.float32); shard_acc = np.full_like(shard, 0.1)
+        part = ct.tables["c"][rank::world]
+        shard[: part.shape[0]] = part
+        O.adagrad_sparse(shard, shard_acc, O.IndexedSlices(ids_all.numpy()[mine] // world, rows_all.numpy()[mine]), 0.05)
+        shards = torch.zeros(world * local, 8)
+        allgather_into(shards, torch.from_numpy(shard))
+        table_sharded = np.zeros_like(table)
+        for r in range(world):
+            n_r = (20 - r + world - 1) // world
+            table_sharded[r::world] = shards.numpy().reshape(world, local, 8)[r, :n_r]
         # sharded index: local exact top-k with global indices, all-gather, merge
         corpus = np.random.default_rng(5).integers(0, 4, size=(103, 6)).astype(np.float32)
         queries = np.random.default_rng(6).integers(0, 4, size=(9, 6)).astype(np.float32)
@@ -67,7 +81,7 @@ def _dp_worker(rank, world, port, out):
         all_s = torch.zeros(world * 9, 10); all_i = torch.zeros(world * 9, 10, dtype=torch.int64)
         allgather_into(all_s, torch.from_numpy(s)); allgather_into(all_i, torch.from_numpy(i))
         ms, mi = O.merge_topk(all_s.numpy().reshape(world, 9, 10), all_i.numpy().reshape(world, 9, 10), 10)
-        np.savez(out, flat=flat.numpy(), table=table, acc=acc, ms=ms, mi=mi)
+        np.savez(out, flat=flat.numpy(), table=table, acc=acc, ms=ms, mi=mi, table_sharded=table_sharded)
     finally:
         dist.destroy_process_group()
 
@@ -89,7 +103,10 @@ def test_dp_and_sharded_index_protocols_world2(tmp_path):
         assert p.exitcode == 0
     res = [np.load(o) for o in outs]
     # replicas agree bit for bit
-    for k in ("flat", "table", "acc", "ms", "mi"):
+    # the row-sharded layout reproduces the replicated update (last-bit differences only where a row's duplicates straddle
+    # different 32-entry blocks of the two sorted lists; none at this size)
+    np.testing.assert_allclose(res[0]["table_sharded"], res[0]["table"], rtol=0, atol=1e-7)
+    for k in ("flat", "table", "acc", "ms", "mi", "table_sharded"):
         assert np.array_equal(res[0][k], res[1][k]), k
     # == the single-process statement: G batches at the same weights, gradients summed, one apply
     rng = np.random.default_rng(0)

@@ -461,3 +461,40 @@ def test_row_sharded_gather_and_sparse_adagrad_equal_unsharded(lib, T, g):
         assert np.array_equal(shards[r].cpu().numpy()[:n_r], t_r)
         assert np.array_equal(accs[r].cpu().numpy()[:n_r], a_r)
         np.testing.assert_allclose(t_r, whole[r::g], rtol=0, atol=1e-6)
+
+
+def test_row_sharded_sparse_adam_equals_per_shard_oracle(lib, T):
+    """Legacy (non-lazy) Adam on a row-sharded table: whole-shard decay sweep, scatter of the owned entries, whole-shard update."""
+    from pkg import _native as N
+
+    rng = np.random.default_rng(77)
+    g, rows, e, B = 3, 400, 16, 300
+    table = rng.standard_normal((rows, e)).astype(np.float32)
+    m0 = (rng.standard_normal((rows, e)) * 0.01).astype(np.float32); v0 = (rng.random((rows, e)) * 0.01).astype(np.float32)
+    ids = np.minimum(rng.zipf(1.3, size=B) - 1, rows - 1).astype(np.int32)
+    grad = rng.standard_normal((B, e)).astype(np.float32)
+    d_ids, d_grad = dev(T, ids), dev(T, grad)
+    ws = T.empty(int(lib.tt_sparse_workspace_bytes(1, B, e)), dtype=T.uint8, device="cuda")
+    lr_t = float(O.adam_lr_t(0.01, 3))
+    for r in range(g):
+        sh = [np.ascontiguousarray(a[r::g]) for a in (table, m0, v0)]
+        local = (rows + g - 1) // g
+        pad = [np.zeros((local, e), np.float32) for _ in range(3)]
+        for p_, s_ in zip(pad, sh):
+            p_[: s_.shape[0]] = s_
+        dt, dm, dv = (dev(T, a) for a in pad)
+        jobs = (N.TTSparseJob * 1)()
+        jobs[0].table, jobs[0].slot0, jobs[0].slot1 = dt.data_ptr(), dm.data_ptr(), dv.data_ptr()
+        jobs[0].rows, jobs[0].e, jobs[0].nsrc, jobs[0].n_per_src = rows, e, 1, B
+        jobs[0].shard_rank, jobs[0].shard_world = r, g
+        jobs[0].ids[0], jobs[0].grad[0], jobs[0].grad_ld[0] = d_ids.data_ptr(), d_grad.data_ptr(), e
+        N.check(lib.tt_sparse_sort(jobs, 1, ws.data_ptr(), ws.numel(), stream()))
+        N.check(lib.tt_sparse_adam(jobs, 1, lr_t, 0.9, 0.999, 1e-7, ws.data_ptr(), ws.numel(), stream()))
+        T.cuda.synchronize()
+        mine = ids % g == r
+        t_r, m_r, v_r = (a.copy() for a in sh)
+        O.adam_sparse(t_r, m_r, v_r, O.IndexedSlices(ids[mine] // g, grad[mine]), 0.01, 3)
+        n_r = t_r.shape[0]
+        np.testing.assert_allclose(dt.cpu().numpy()[:n_r], t_r, rtol=1e-5, atol=1e-6)   # tolerances of the unsharded Adam test
+        np.testing.assert_allclose(dm.cpu().numpy()[:n_r], m_r, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(dv.cpu().numpy()[:n_r], v_r, rtol=1e-5, atol=1e-9)
