@@ -347,3 +347,54 @@ def test_save_load_round_trip_and_bulk_index_build(lib, tmp_path):
     b.save(str(tmp_path / "index"))
     c2 = BruteForceIndex.load(str(tmp_path / "index"), 12, m.query_tower)
     assert np.array_equal(want, c2(q))
+
+
+def test_c1_config_full_vocabularies_train_step_and_top12_index(lib):
+    """BASELINE configs[0] at its real sizes: id-only towers (1 371 980 customers + OOV, 105 542 articles + OOV), embedding = joint
+    = 32, batch 1024, logQ in-batch softmax, Adagrad; then the brute-force top-12 index over all 105 542 candidate-tower rows."""
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.indices.brute_force import BruteForceIndex
+    from pkg.modelling.metrics.index_recall import IndexRecall
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+
+    set_seed(5)
+    vq, vc, B = 1_371_980, 105_542, 1024
+    qf = [Feature("customer_id", tt.string, FeatureFamily.QUERY, embedding_size=32)]
+    cf = [Feature("article_id", tt.string, FeatureFamily.CANDIDATE, embedding_size=32)]
+    qf[0].set_vocab_size(vq); cf[0].set_vocab_size(vc)
+    rng = np.random.default_rng(31)
+    w = 1.0 / np.arange(1, vc + 1)
+    p = (w / w.sum()).astype(np.float32)                                       # Zipf(1) sampling probabilities
+    probs = {str(i + 1): float(p[i]) for i in range(vc)}
+    m = TwoTowerModel(qf, cf, "article_id", 32, candidate_prob_lookup=probs)
+    m.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))
+    qt, ct = _oracle_twin(m)
+    art = (np.searchsorted(np.cumsum(p.astype(np.float64)), rng.random(B)) + 1).clip(1, vc).astype(np.int32)
+    data = {"customer_id": rng.integers(1, vq + 1, size=(B, 1)).astype(np.int32), "article_id": art.reshape(B, 1)}
+    p_rows = np.ones(vc + 1, np.float32); p_rows[1:] = p
+    g = O.train_step_grads(qt, ct, {"customer_id": data["customer_id"]}, {}, {"article_id": data["article_id"]}, {}, p_rows[art])
+    loss = float(m.train_step(data)["loss"])
+    assert abs(loss - g.loss) <= 1e-3 * abs(g.loss)                           # north star (TF32 tensor-core path at E = 32)
+    for tower, ot, sl in ((m.query_tower, qt, g.tables_q), (m.candidate_tower, ct, g.tables_c)):
+        for name, s in sl.items():
+            t = ot.tables[name]; acc = np.full_like(t, 0.1)
+            O.adagrad_sparse(t, acc, s, 0.05)
+            got = _np(tower.input_layer.embedding_layers[name].weight)
+            rows = np.unique(s.indices)
+            np.testing.assert_allclose(got[rows], t[rows], rtol=0, atol=2e-3)
+            probe = rng.integers(0, t.shape[0], 4096)
+            probe = probe[~np.isin(probe, rows)]
+            assert np.array_equal(got[probe], t[probe])                          # untouched rows do not move
+    # index over the whole candidate vocabulary, top-12, bit-exact against the canonical oracle
+    ids = np.arange(1, vc + 1, dtype=np.int32)
+    index = BruteForceIndex.from_candidate_tower(12, m.query_tower, m.candidate_tower,
+                                                 [{"article_id": ids[lo:lo + 10000].reshape(-1, 1)} for lo in range(0, vc, 10000)], "article_id")
+    q = {"customer_id": rng.integers(1, vq + 1, size=(256, 1)).astype(np.int32)}
+    got = index(q)
+    q_emb = _np(m.query_tower(q)); c_emb = _np(index._candidates)
+    _, want = O.index_topk(q_emb, c_emb, 12)
+    assert np.array_equal(got, ids[want])
+    metric = IndexRecall(index, ks=[1, 12])
+    metric(q, ids[want[:, 3]].reshape(-1, 1))                                   # "truth" = each query's 4th-ranked article
+    assert metric.hits[1] == 0 and metric.hits[12] == 256 and metric.metric[12] == np.float64(1.0)
