@@ -73,6 +73,27 @@ class IndexRecall:
             self.metric[k] = np.float64(self.hits[k]) / np.float64(self.seen)
         return self.metric
 
+    def all_reduce(self, group=None) -> Dict[int, float]:
+        """Multi-GPU evaluation: every rank has scored its own share of the test queries; the int32 hit and seen
+        counters are summed over the ranks (exact) and the ratios recomputed, so every rank ends with the global Recall@k."""
+        import torch
+        import torch.distributed as dist
+
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return self.metric
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor([int(self.hits[k]) for k in self.ks] + [int(self.seen)], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        vals = t.cpu().numpy()
+        for k, h in zip(self.ks, vals[:-1]):
+            self.hits[k] = np.int32(h)
+        self.seen = np.int32(vals[-1])
+        if self._dev_hits is not None:        # keep the device counters consistent with the merged totals
+            self._dev_hits.copy_(torch.from_numpy(np.asarray(vals[:-1], dtype=np.int32)))
+        for k in self.ks:
+            self.metric[k] = np.float64(self.hits[k]) / np.float64(self.seen)
+        return self.metric
+
     def log_metric(self, epoch: Optional[int] = None, to_tensorboard: bool = True) -> None:
         for k in self.ks:
             logger.info(f"Start of epoch {epoch} recall@{k}: {self.metric[k]}")

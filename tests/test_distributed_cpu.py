@@ -126,6 +126,54 @@ def test_dp_and_sharded_index_protocols_world2(tmp_path):
     assert np.array_equal(res[0]["mi"], i) and np.array_equal(res[0]["ms"], s)
 
 
+def _recall_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "hm-retrieval-two-tower_b200"))
+    from pkg.modelling.metrics.index_recall import IndexRecall
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        class Fixed:                       # an index returning the same 5 candidates for every query (host path of IndexRecall)
+            def __call__(self, queries):
+                n = len(queries["q"])
+                return np.tile(np.array([["a", "b", "c", "d", "e"]], dtype=object), (n, 1))
+
+        truth = np.array(list("abcdxaybzc"), dtype=object)            # the reference's ragged-batch fixture, split over the ranks
+        metric = IndexRecall(Fixed(), ks=[1, 2, 5])
+        mine = truth[rank::world]
+        for lo in range(0, len(mine), 2):                             # ragged batches
+            t = mine[lo:lo + 2]
+            metric({"q": np.zeros((len(t), 1))}, t.reshape(-1, 1))
+        metric.all_reduce()
+        np.savez(out, hits=np.array([metric.hits[k] for k in (1, 2, 5)]), seen=metric.seen, m=np.array([metric.metric[k] for k in (1, 2, 5)]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_recall_counters_all_reduce_world2(tmp_path):
+    import torch.multiprocessing as mp
+
+    world, port = 2, _free_port()
+    outs = [str(tmp_path / f"rec{r}.npz") for r in range(world)]
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_recall_worker, args=(r, world, port, outs[r])) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(100)
+        assert p.exitcode == 0
+    res = [np.load(o) for o in outs]
+    truth = np.array(list("abcdxaybzc"), dtype=object)
+    cand = np.array(list("abcde"), dtype=object)
+    want_hits = [int(sum(t in cand[:k] for t in truth)) for k in (1, 2, 5)]
+    for r in res:
+        assert r["hits"].tolist() == want_hits and int(r["seen"]) == 10
+        assert r["hits"].dtype == np.int32 and r["m"].dtype == np.float64
+        assert r["m"].tolist() == [h / 10 for h in want_hits]
+
+
 def test_shard_bounds_cover_everything():
     from pkg.modelling.distributed import shard_bounds
 
