@@ -35,7 +35,7 @@ def _batch(rng, b):
             "article_id": art.reshape(b, 1), "colour_group_name": (art % 50 + 1).reshape(b, 1).astype(np.int32)}
 
 
-def _worker(rank, world, port, out, shard_tables, peer_sync, global_negatives=False, impl=1):
+def _worker(rank, world, port, out, shard_tables, peer_sync, global_negatives=False, impl=1, opt="adagrad"):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "hm-retrieval-two-tower_b200"))
     import torch
     import torch.distributed as dist
@@ -53,7 +53,7 @@ def _worker(rank, world, port, out, shard_tables, peer_sync, global_negatives=Fa
         qf, cf = _features()
         model = TwoTowerModel(qf, cf, "article_id", 32, candidate_prob_lookup={str(i + 1): 1.0 / 300 for i in range(300)})
         model.impl = impl
-        model.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))
+        model.compile(optimizer=OptimizerFactory.get_optimizer(opt, {"learning_rate": 0.05 if opt == "adagrad" else 0.01}))
         before = {k: v.copy() for k, v in model.state_arrays().items()}
         dp = DataParallel(model, shard_tables=shard_tables, peer_sync=peer_sync, global_negatives=global_negatives)
         assert dp.shard_tables == shard_tables and dp.peer_sync == peer_sync
@@ -82,13 +82,13 @@ def _worker(rank, world, port, out, shard_tables, peer_sync, global_negatives=Fa
         dist.destroy_process_group()
 
 
-def _run(tmp_path, world, shard_tables, peer_sync=False, global_negatives=False, impl=1):
+def _run(tmp_path, world, shard_tables, peer_sync=False, global_negatives=False, impl=1, opt="adagrad"):
     import torch.multiprocessing as mp
 
     port = _free_port()
-    outs = [str(tmp_path / f"r{r}_{int(shard_tables)}{int(peer_sync)}{int(global_negatives)}{impl}.npz") for r in range(world)]
+    outs = [str(tmp_path / f"r{r}_{int(shard_tables)}{int(peer_sync)}{int(global_negatives)}{impl}{opt}.npz") for r in range(world)]
     ctx = mp.get_context("spawn")
-    procs = [ctx.Process(target=_worker, args=(r, world, port, outs[r], shard_tables, peer_sync, global_negatives, impl)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, outs[r], shard_tables, peer_sync, global_negatives, impl, opt)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -202,3 +202,24 @@ def test_global_negatives_equal_one_process_on_the_concatenated_batch(tmp_path, 
         t = tower.tables[name.split("/")[-1]].copy(); acc = np.full_like(t, 0.1)
         O.adagrad_sparse(t, acc, slices, 0.05)
         np.testing.assert_allclose(res[0]["after/" + name], t, rtol=0, atol=atol)
+
+
+@pytest.mark.timeout(600)
+def test_data_parallel_adam_row_sharded_equals_replicated(tmp_path):
+    """Legacy (non-lazy) Adam: whole-table sweeps run on each rank's shard; four steps agree with the replicated layout."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    rep = _run(tmp_path, world, False, opt="adam")
+    sh = _run(tmp_path, world, True, True, opt="adam")
+    for k in rep[0].files:
+        for r in range(world):
+            a, b_ = rep[r][k], sh[r][k]
+            if a.dtype.kind == "f":
+                np.testing.assert_allclose(b_, a, rtol=0, atol=2e-6 * (1.0 + float(np.abs(a).max())), err_msg=k)
+            else:
+                assert np.array_equal(a, b_), k
+    moved = [k for k in rep[0].files if k.startswith("after3/") and "embedding" in k]
+    assert moved and all(not np.array_equal(rep[0][k], rep[0]["before/" + k[len("after3/"):]]) for k in moved)
