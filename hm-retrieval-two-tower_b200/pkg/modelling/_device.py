@@ -92,7 +92,28 @@ class Vocab:
         return "[UNK]" if row == 0 else _as_str(self._vocab[row - 1])
 
 
+def unwrap(value):
+    """Foreign tensors -> torch tensor or numpy array, zero-copy where the producer allows it.
+
+    The reference feeds its layers TF/Keras tensors (input_layer.py:45-69).  Numeric TF EagerTensors, CuPy and JAX arrays
+    export ``__dlpack__``: they are imported with ``torch.from_dlpack`` (a device tensor stays on the device and is read in
+    place by the staging copy).  TF string tensors have no DLPack form; they come through ``.numpy()`` (an object array of
+    bytes) and take the host vocabulary lookup like any other string batch."""
+    import torch
+    if isinstance(value, (torch.Tensor, np.ndarray, list, tuple)) or np.isscalar(value):
+        return value
+    if hasattr(value, "__dlpack__"):
+        try:
+            return torch.from_dlpack(value)
+        except Exception:      # string / ragged / unsupported dtype: fall through to the host view
+            pass
+    if hasattr(value, "numpy"):
+        return value.numpy()
+    return value
+
+
 def is_string_like(a) -> bool:
+    a = unwrap(a)
     if isinstance(a, np.ndarray):
         return a.dtype.kind in ("U", "S", "O")
     if isinstance(a, (list, tuple)):
@@ -109,8 +130,9 @@ def batch_size_of(x) -> int:
 
 def stage_ids(value, vocab: Vocab, out):
     """Fill the int32 device buffer ``out`` (B,) with row ids for one categorical feature.
-    Accepts: strings (host lookup), integer numpy arrays / torch tensors (already row ids)."""
+    Accepts: strings (host lookup), integer numpy arrays / torch tensors / DLPack exporters (already row ids)."""
     torch = N.require_cuda()
+    value = unwrap(value)
     if isinstance(value, torch.Tensor):
         out.copy_(value.reshape(-1), non_blocking=True)
         return
@@ -123,6 +145,7 @@ def stage_ids(value, vocab: Vocab, out):
 
 def stage_floats(value, out):
     torch = N.require_cuda()
+    value = unwrap(value)
     if isinstance(value, torch.Tensor):
         out.copy_(value.reshape(-1), non_blocking=True)
         return

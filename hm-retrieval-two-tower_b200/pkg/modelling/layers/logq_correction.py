@@ -25,7 +25,7 @@ class LogQCorrection:
         self.default_value = np.float32(1.0)
 
     def probabilities(self, candidate_ids) -> np.ndarray:
-        flat = np.asarray(candidate_ids).reshape(-1)
+        flat = np.asarray(D.unwrap(candidate_ids)).reshape(-1)
         return np.fromiter((self.lookup.get(D._as_str(v), self.default_value) for v in flat), dtype=np.float32,
                            count=flat.shape[0])
 

@@ -15,6 +15,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from pkg import _native as N
+from pkg.modelling import _device as D
 
 logger = logging.getLogger(__name__)
 _SUMMARY_WRITER = [None]
@@ -57,6 +58,7 @@ class IndexRecall:
             self.hits[k] = np.int32(h)
 
     def __call__(self, queries, true_candidate_ids) -> Dict[int, float]:
+        true_candidate_ids = D.unwrap(true_candidate_ids)      # TF / DLPack tensors -> torch or numpy
         n = int(true_candidate_ids.shape[0])
         self.seen = np.int32(self.seen + n)
         if hasattr(self.index, "query_indices"):

@@ -62,6 +62,35 @@ def test_kat_a_train_step_through_the_api(lib, golden, encoded):
                                a["acc_c_after"], atol=1e-6)
 
 
+class _DLPackOnly:
+    """A device tensor as a TF EagerTensor / CuPy array would present it: DLPack export and a shape, nothing else."""
+
+    def __init__(self, t):
+        self._t, self.shape = t, tuple(t.shape)
+
+    def __dlpack__(self, *args, **kwargs):
+        return self._t.__dlpack__(*args, **kwargs)
+
+    def __dlpack_device__(self):
+        return self._t.__dlpack_device__()
+
+
+def test_kat_a_train_step_with_dlpack_inputs(lib, golden):
+    """Row ids handed over as foreign device tensors (DLPack) give the KAT-A step of the string path."""
+    import torch
+
+    _, kat = golden
+    a = kat["A"]
+    m = _kat_model(a, lib)
+    data = {"q": _DLPackOnly(torch.tensor(a["query_ids"], dtype=torch.int32, device="cuda").reshape(-1, 1)),
+            "c": _DLPackOnly(torch.tensor(a["candidate_ids"], dtype=torch.int32, device="cuda").reshape(-1, 1))}
+    np.testing.assert_allclose(_np(m(data)), a["S"], atol=1e-7)
+    out = m.train_step(data)
+    assert abs(float(out["loss"]) - a["loss"]) < 1e-5
+    np.testing.assert_allclose(_np(m.candidate_tower.input_layer.embedding_layers["c"].weight), a["Tc_after"], atol=1e-6)
+    np.testing.assert_allclose(_np(m.query_tower.kernels[0]), a["Wq_after"], atol=1e-6)
+
+
 def test_constructor_errors(lib):
     from pkg.modelling.models.two_tower_model import TwoTowerModel
 

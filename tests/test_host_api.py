@@ -86,6 +86,53 @@ def test_recall_with_static_index_reference_fixture(golden):
     assert set(index.get_input_signature()) == {"query_id"}
 
 
+class _ForeignTensor:
+    """Stands in for a TF EagerTensor / CuPy array: exports DLPack and .numpy(), is neither numpy nor torch."""
+
+    def __init__(self, array, dlpack_ok=True):
+        self._a, self._ok = array, dlpack_ok
+        self.shape = array.shape
+
+    def __dlpack__(self, *args, **kwargs):
+        if not self._ok:
+            raise TypeError("DT_STRING has no DLPack representation")      # what tf.experimental.dlpack says for strings
+        import torch
+
+        return torch.from_numpy(self._a).__dlpack__(*args, **kwargs)
+
+    def __dlpack_device__(self):
+        return (1, 0)
+
+    def numpy(self):
+        return self._a
+
+
+def test_foreign_tensors_enter_through_dlpack_or_numpy(golden):
+    """north_star: DLPack interop with the TF/Keras tensors the reference feeds its layers (input_layer.py:45-69)."""
+    import torch
+
+    from pkg.modelling import _device as D
+
+    ids = D.unwrap(_ForeignTensor(np.arange(6, dtype=np.int32).reshape(6, 1)))
+    assert isinstance(ids, torch.Tensor) and ids.dtype == torch.int32 and tuple(ids.shape) == (6, 1)
+    strings = _ForeignTensor(np.array([[b"a"], [b"zz"]], dtype=object), dlpack_ok=False)
+    assert D.is_string_like(strings) and D.batch_size_of(strings) == 2
+    assert list(Vocab(["zz", "a"]).encode(D.unwrap(strings))) == [2, 1]
+    for passthrough in (np.zeros(3), torch.zeros(3), [1, 2], 3.0):
+        assert D.unwrap(passthrough) is passthrough
+    # the reference's recall fixture with the true ids arriving as a string tensor (tests/test_recall.py:48-76)
+    fix, _ = golden
+    g = fix["recall"]
+    index = StaticIndex(k=g["static_k"], input_features=[Feature("query_id", tt.string, FeatureFamily.QUERY, embedding_size=2)],
+                        candidates=np.array([s.encode() for s in g["static_candidates"]], dtype=object).reshape(1, -1))
+    metric = IndexRecall(index, ks=g["ks"])
+    q = np.array(g["query_ids"], dtype=object).reshape(-1, 1)
+    t = np.array([s.encode() for s in g["true_candidate_ids"]], dtype=object).reshape(-1, 1)
+    for i in range(0, 5, g["batch_size"]):
+        metric({"query_id": _ForeignTensor(q[i:i + 2], dlpack_ok=False)}, _ForeignTensor(t[i:i + 2], dlpack_ok=False))
+    assert {str(k): float(v) for k, v in metric.metric.items()} == {k: float(v) for k, v in g["expected"].items()}
+
+
 def test_product_path_fails_loudly_without_cuda():
     import torch
 
