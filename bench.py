@@ -183,6 +183,12 @@ def cpu_index_rate(bq, warmup, steps, seed=2):
     return bq / sec, sec, cores
 
 
+def workload_name(batch):
+    """config.workload: BASELINE.json configs[1], the same string on both arms."""
+    return ("c2: H&M-shaped two-tower (1.37M customers, 105k articles), id emb + joint dim 64, side features age/product_type/colour, "
+            f"batch {batch}/GPU, logQ in-batch softmax, Adagrad lr 0.05")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -194,7 +200,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "examples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "c2: H&M-shaped two-tower dim 64 + side features, batch %d, logQ in-batch softmax, Adagrad" % args.batch,
+        "config": {"workload": workload_name(args.batch),
                    "note": "reference TF is not installable here; this is the oracle restatement run with torch-CPU ops"},
         "cpu_baseline": {"value": rate, "unit": "examples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -306,8 +312,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32/fp16 operands, fp32 accumulate" if model._tc_ok() and model.impl != N.TT_IMPL_SIMT else "f32",
         "data": "synthetic",
-        "config": {"workload": "c2: H&M-shaped two-tower (1.37M customers, 105k articles), id emb + joint dim 64, side features age/product_type/colour, "
-                               f"batch {B}/GPU, logQ in-batch softmax, Adagrad lr 0.05",
+        "config": {"workload": workload_name(B),
                    "parallelism": f"dp{world}" if world > 1 else "single", "cuda_graph": bool(model.use_cuda_graph),
                    "l2": "inputs larger than L2: tables + Adagrad accumulators 0.76 GB, random rows each step; no explicit flush",
                    "last_loss": loss},
