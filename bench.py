@@ -424,6 +424,9 @@ NCU_SOFTMAX_DRAM_BYTES = 2169600 + 4365568 + 256
 NCU_SOFTMAX_SOURCE = "profiles/r01c_softmax_streamk_ncu_full.md (ncu --set full, per launch, fwd + bwd)"
 
 
+HBM_TIMING = None     # (warm-up launches, timed launches) override used by scripts/hbm_microbench.py --once under ncu
+
+
 def hbm_rooflines(pk, lib, b=1 << 20, e=64, rows=V_CUSTOMERS + 1):
     """The HBM-bound kernels at a batch large enough to leave the launch-latency regime (2^20 ids; the step's own batch moves
     only 5 MB): embedding gather (4.e B read + 4.e B written + 4 B id per example) and the de-duplicated sparse Adagrad
@@ -458,7 +461,8 @@ def hbm_rooflines(pk, lib, b=1 << 20, e=64, rows=V_CUSTOMERS + 1):
         N.check(lib.tt_sparse_adagrad(jobs, 1, 0.05, 1e-7, ws.data_ptr(), ws.numel(), st), "tt_sparse_adagrad")
 
     def timeit(fn, n=10, pre=None):
-        for _ in range(3):
+        warm, n = HBM_TIMING if HBM_TIMING else (3, n)
+        for _ in range(warm):
             if pre:
                 pre()
             fn()

@@ -35,6 +35,8 @@ struct SortPlan {  // per-job workspace pointers
     int32_t n;       // elements
     int32_t ntiles;
     int32_t npass;
+    int32_t vec;     // floats per lane access in the segmented reduce (1, 2 or 4): widest that divides e and the alignment of every row base
+    int32_t gvec;    // 1: the gradient sources are aligned for `vec`-wide loads too (a feature's dX slice may start at any column)
 };
 struct PlanArr {
     SortPlan p[TT_MAX_JOBS];
@@ -298,6 +300,136 @@ __device__ __forceinline__ void block_body(const tt_sparse_job& job, int kMode, 
     }
 }
 
+// ---- the same body with 64 / 128-bit accesses -----------------------------------------------------------------------------------
+// A lane owns VW CONSECUTIVE columns per chunk of 32 * VW columns, so a 64-wide row is one 8-byte access per lane and a 128-wide row
+// one 16-byte access (ncu, 2^20 ids into a 1.37 M x 64 table: the scalar body above executes ~250 warp instructions per run -- address
+// arithmetic, the position / n_per_src division, per-column predicates -- and is issue-bound at 41 % of DRAM throughput).  Every column
+// is still summed sequentially in position order, so the result is bit-identical to the scalar body and to the oracle.
+template <int VW>
+__device__ __forceinline__ void vload(const float* p, float (&o)[VW]) {
+    if constexpr (VW == 4) { const float4 t = *reinterpret_cast<const float4*>(p); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+    else if constexpr (VW == 2) { const float2 t = *reinterpret_cast<const float2*>(p); o[0] = t.x; o[1] = t.y; }
+    else o[0] = *p;
+}
+template <int VW>
+__device__ __forceinline__ void vload_nc(const float* p, float (&o)[VW]) {
+    if constexpr (VW == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+    else if constexpr (VW == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); o[0] = t.x; o[1] = t.y; }
+    else o[0] = __ldg(p);
+}
+template <int VW>
+__device__ __forceinline__ void vstore(float* p, const float (&v)[VW]) {
+    if constexpr (VW == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else if constexpr (VW == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    else *p = v[0];
+}
+
+template <int VW, int NC, int RB>
+__device__ __forceinline__ void block_body_vec(const tt_sparse_job& job, int kMode, uint32_t key, int pos, uint32_t heads, int cnt, bool cont_in,
+                                               bool cont_out, float* __restrict__ partL, float* __restrict__ partR, int lane, float lr, float eps,
+                                               float omb1, float omb2, const float* __restrict__ stage, bool gvec) {
+    const int e = job.e;
+    float* const s0 = job.slot0;                                              // Adagrad accumulator / Adam m
+    float* const s1 = (kMode == kModeAdagrad) ? job.table : job.slot1;        // the second array of the update: weights / Adam v
+    const bool single = job.nsrc == 1;                                        // one gradient source: no position / n_per_src division
+    const float* const g0 = job.grad[0];
+    const int64_t ld0 = job.grad_ld[0];
+    int c0[NC];
+    bool cv[NC];
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci) {
+        c0[ci] = (ci * 32 + lane) * VW;
+        cv[ci] = c0[ci] < e;                                                  // e % VW == 0: the VW columns of a lane are valid together
+    }
+    auto grow = [&](int j, int p) -> const float* {
+        return stage ? stage + (int64_t)j * e : (single ? g0 + (int64_t)p * ld0 : grad_row(job, p));
+    };
+    auto gload = [&](const float* r, float (&o)[VW]) {
+        if (gvec) vload_nc<VW>(r, o);
+        else {
+#pragma unroll
+            for (int v = 0; v < VW; ++v) o[v] = __ldg(r + v);
+        }
+    };
+    while (heads) {
+        int s[RB], en[RB];
+        uint32_t id[RB];
+        int nb = 0;
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            s[u] = 0; en[u] = 0;
+            if (heads) {
+                s[u] = __ffs(heads) - 1;
+                heads &= heads - 1;
+                en[u] = heads ? (__ffs(heads) - 1) : cnt;
+                nb = u + 1;
+            }
+            id[u] = __shfl_sync(0xffffffffu, key, s[u]);
+        }
+        float g[RB][NC][VW], a[RB][NC][VW], w[RB][NC][VW];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const int p0 = __shfl_sync(0xffffffffu, pos, s[u]);
+            const float* r0 = grow(s[u], p0);
+            const int64_t ro = (int64_t)id[u] * e;
+#pragma unroll
+            for (int ci = 0; ci < NC; ++ci) {
+#pragma unroll
+                for (int v = 0; v < VW; ++v) { g[u][ci][v] = 0.f; a[u][ci][v] = 0.f; w[u][ci][v] = 0.f; }
+                if (u < nb && cv[ci]) {
+                    gload(r0 + c0[ci], g[u][ci]);
+                    vload<VW>(s0 + ro + c0[ci], a[u][ci]);
+                    vload<VW>(s1 + ro + c0[ci], w[u][ci]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            for (int j = s[u] + 1; j < en[u]; ++j) {   // duplicates of the id inside this block: sequential, position order
+                const int pj = __shfl_sync(0xffffffffu, pos, j);
+                const float* r = grow(j, pj);
+#pragma unroll
+                for (int ci = 0; ci < NC; ++ci) {
+                    if (!cv[ci]) continue;
+                    float t[VW];
+                    gload(r + c0[ci], t);
+#pragma unroll
+                    for (int v = 0; v < VW; ++v) g[u][ci][v] = __fadd_rn(g[u][ci][v], t[v]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            if (u >= nb) continue;
+            const bool to_l = (s[u] == 0) && cont_in;
+            const bool to_r = (en[u] == cnt) && cont_out && !to_l;
+            const int64_t ro = (int64_t)id[u] * e;
+#pragma unroll
+            for (int ci = 0; ci < NC; ++ci) {
+                if (!cv[ci]) continue;
+                if (to_l) vstore<VW>(partL + c0[ci], g[u][ci]);          // continuation piece (may also continue further)
+                else if (to_r) vstore<VW>(partR + c0[ci], g[u][ci]);     // run begins here and continues
+                else {                                                   // run lives entirely in this block: apply with the prefetched state
+                    float x0[VW], x1[VW];
+#pragma unroll
+                    for (int v = 0; v < VW; ++v) {
+                        const float gv = g[u][ci][v];
+                        if (kMode == kModeAdagrad) {
+                            x0[v] = __fadd_rn(a[u][ci][v], __fmul_rn(gv, gv));
+                            x1[v] = __fsub_rn(w[u][ci][v], __fdiv_rn(__fmul_rn(gv, lr), __fadd_rn(__fsqrt_rn(x0[v]), eps)));
+                        } else {
+                            x0[v] = __fadd_rn(a[u][ci][v], __fmul_rn(gv, omb1));
+                            x1[v] = __fadd_rn(w[u][ci][v], __fmul_rn(__fmul_rn(gv, gv), omb2));
+                        }
+                    }
+                    vstore<VW>(s0 + ro + c0[ci], x0);
+                    vstore<VW>(s1 + ro + c0[ci], x1);
+                }
+            }
+        }
+    }
+}
+
 // Row-sharded tables: one warp per sorted entry copies the gradient row of an OWNED entry from wherever it was produced (the dX
 // block of another GPU, peer-mapped over NVLink) into the local staging array, in sorted order.  Every load is independent, so the
 // NVLink latency is paid once; the segmented reduce then streams contiguous local rows.
@@ -323,7 +455,7 @@ __global__ void __launch_bounds__(256) sparse_stage_kernel(const __grid_constant
 // kWide: eight runs in flight per warp for narrow tables (more registers, fewer round trips) -- the latency-bound regime of a
 // training step's batch; the bandwidth-bound regime (hundreds of thousands of entries) keeps four and the higher occupancy
 template <bool kWide>
-__global__ void __launch_bounds__(256) sparse_block_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans, int kMode,
+__global__ void __launch_bounds__(256, kWide ? 2 : 4) sparse_block_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans, int kMode,
                                                            float lr, float eps, float omb1, float omb2) {
     const SortPlan& pl = plans.p[blockIdx.y];
     const tt_sparse_job& job = jobs.j[blockIdx.y];
@@ -351,6 +483,13 @@ __global__ void __launch_bounds__(256) sparse_block_kernel(const __grid_constant
     float* partL = pl.partL + (int64_t)b * e;
     float* partR = pl.partR + (int64_t)b * e;
     const float* stage = pl.stage ? pl.stage + (int64_t)base * e : nullptr;
+    const int vw = pl.vec, ncv = (e + 32 * vw - 1) / (32 * vw);   // chunks of 32 * vw columns
+    const bool gvec = pl.gvec != 0;
+    if (ncv == 1 && vw == 1) { block_body_vec<1, 1, kWide ? 8 : 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage, gvec); return; }
+    if (ncv == 1 && vw == 2) { block_body_vec<2, 1, kWide ? 8 : 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage, gvec); return; }
+    if (ncv == 1 && vw == 4) { block_body_vec<4, 1, 2>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage, gvec); return; }
+    if (ncv == 2 && vw == 4) { block_body_vec<4, 2, 1>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage, gvec); return; }
+    // rows whose width or alignment rules out vector accesses (e.g. e = 64 at an odd column offset of a 4-byte aligned table)
     const int nc = (e + 31) >> 5;
     if (nc <= 1) block_body<1, kWide ? 8 : 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
     else if (nc <= 2) block_body<2, kWide ? 8 : 4>(job, kMode, key, pos, heads, cnt, cont_in, cont_out, partL, partR, lane, lr, eps, omb1, omb2, stage);
@@ -517,6 +656,18 @@ static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_
         p.n = jobs[j].nsrc * jobs[j].n_per_src;
         p.ntiles = (int)ceil_div(p.n, kTile);
         p.npass = passes_for_rows(jobs[j].shard_world > 1 ? (int)skip_key(jobs[j]) + 1 : jobs[j].rows);
+        {   // access width of the segmented reduce: e <= 32 -> 1 float per lane, <= 64 -> 2, wider -> 4, narrowed until it divides e
+            // and the alignment of every base pointer the kernels add `row * e + column` to
+            const tt_sparse_job& jb = jobs[j];
+            int want = jb.e <= 32 ? 1 : (jb.e <= 64 ? 2 : 4);
+            while (want > 1 && jb.e % want) want >>= 1;
+            uintptr_t bits = (uintptr_t)jb.table | (uintptr_t)jb.slot0 | (uintptr_t)jb.slot1 | (uintptr_t)p.partL | (uintptr_t)p.partR | (uintptr_t)p.stage;
+            while (want > 1 && (bits % (want * sizeof(float))) != 0) want >>= 1;
+            uintptr_t gbits = 0;
+            for (int s = 0; s < jb.nsrc; ++s) gbits |= (uintptr_t)jb.grad[s] | ((uintptr_t)(uint32_t)jb.grad_ld[s] * sizeof(float));
+            p.vec = want;
+            p.gvec = (p.stage != nullptr || (gbits % (want * sizeof(float))) == 0) ? 1 : 0;   // staged rows are read from the workspace
+        }
         if (p.ntiles > *max_tiles) *max_tiles = p.ntiles;
         if (p.npass > *max_pass) *max_pass = p.npass;
     }
