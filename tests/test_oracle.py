@@ -158,3 +158,138 @@ def test_adam_sparse_is_not_lazy():
     t = np.ones((4, 2), np.float32); m = np.full((4, 2), 0.5, np.float32); v = np.full((4, 2), 0.25, np.float32)
     O.adam_sparse(t, m, v, O.IndexedSlices(np.array([2]), np.array([[1.0, -1.0]], np.float32)), lr=0.1, step=1)
     assert np.all(t[0] != 1.0) and np.all(m[0] == np.float32(0.5) * np.float32(0.9))   # untouched rows still decay and move
+
+
+def _c2_like_problem(seed=7, B=24, E=8):
+    """C2-shaped towers: numeric feature, side features, a hidden layer, duplicate ids in the batch, logQ probabilities."""
+    rng = np.random.default_rng(seed)
+
+    def tower(feats, rows, hidden):
+        tables = {f.name: rng.uniform(-0.5, 0.5, (rows[f.name], f.embedding_size)).astype(np.float32) for f in feats if f.is_string}
+        d = sum(1 if not f.is_string else f.embedding_size for f in feats)
+        dims = [d] + hidden + [E]
+        dense = [(rng.uniform(-0.6, 0.6, (dims[i], dims[i + 1])).astype(np.float32), rng.uniform(0.05, 0.3, dims[i + 1]).astype(np.float32))
+                 for i in range(len(dims) - 1)]
+        return O.OracleTower(feats, tables, dense)
+
+    qt = tower([O.OracleFeature("age", False), O.OracleFeature("q", True, 6)], {"q": 40}, [10])
+    ct = tower([O.OracleFeature("c", True, 6), O.OracleFeature("colour", True, 3)], {"c": 12, "colour": 5}, [])
+    q_ids = {"q": rng.integers(0, 40, B)}
+    q_num = {"age": rng.uniform(0.1, 0.9, B).astype(np.float32)}
+    c_ids = {"c": rng.integers(0, 12, B), "colour": rng.integers(0, 5, B)}          # 24 draws from 12 rows: duplicates
+    probs = rng.uniform(0.01, 0.3, B).astype(np.float32)
+    return rng, qt, ct, q_ids, q_num, c_ids, probs
+
+
+def _dense_table_grads(t, slices):
+    out = {}
+    for k in sorted(t.tables):
+        d = np.zeros(t.tables[k].shape, np.float64)
+        np.add.at(d, slices[k].indices, slices[k].values.astype(np.float64))
+        out[k] = d
+    return out
+
+
+def test_gradients_equal_torch_autograd_of_the_forward():
+    """The reference differentiates its forward with tf.GradientTape (two_tower_model.py:110-124).  An independent float64
+    torch forward (gather, concat numerics-first, relu Dense on every layer, Q.C^T - ln p, CE SUM against eye) differentiated by
+    autograd must give the oracle's hand-written backward."""
+    import torch
+
+    _, qt, ct, q_ids, q_num, c_ids, probs = _c2_like_problem()
+
+    def leaves(t):
+        tabs = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in t.tables.items()}
+        dense = [(torch.tensor(w, dtype=torch.float64, requires_grad=True), torch.tensor(b, dtype=torch.float64, requires_grad=True))
+                 for w, b in t.dense]
+        return tabs, dense
+
+    def fwd(t, tabs, dense, ids, nums):
+        cols = [torch.tensor(nums[f.name], dtype=torch.float64).reshape(-1, 1) for f in t.numerical]
+        cols += [tabs[f.name][torch.tensor(ids[f.name])] for f in t.categorical]
+        h = torch.cat(cols, dim=1)
+        for w, b in dense:
+            h = torch.relu(h @ w + b)
+        return h
+
+    qtab, qden = leaves(qt)
+    ctab, cden = leaves(ct)
+    z = fwd(qt, qtab, qden, q_ids, q_num) @ fwd(ct, ctab, cden, c_ids, {}).T - torch.log(torch.tensor(probs, dtype=torch.float64))[None, :]
+    loss = torch.nn.functional.cross_entropy(z, torch.arange(z.shape[0]), reduction="sum")
+    loss.backward()
+    g = O.train_step_grads(qt, ct, q_ids, q_num, c_ids, {}, probs)
+    assert abs(g.loss - loss.item()) < 1e-4 * loss.item()
+    for t, tabs, den, sl, dg in ((qt, qtab, qden, g.tables_q, g.dense_q), (ct, ctab, cden, g.tables_c, g.dense_c)):
+        for k, d in _dense_table_grads(t, sl).items():
+            np.testing.assert_allclose(d, tabs[k].grad.numpy(), rtol=2e-4, atol=2e-5)
+        for (w, b), (dw, db) in zip(den, dg):
+            np.testing.assert_allclose(dw, w.grad.numpy(), rtol=2e-4, atol=2e-5)
+            np.testing.assert_allclose(db, b.grad.numpy(), rtol=2e-4, atol=2e-5)
+
+
+def test_gradients_equal_finite_differences_of_the_loss():
+    """No reference test pins a gradient, so the oracle's backward pass is also checked against the derivative
+    of its own forward loss: directional central differences, one random direction per parameter tensor."""
+    rng, qt, ct, q_ids, q_num, c_ids, probs = _c2_like_problem()
+
+    def params(t):
+        return [t.tables[k] for k in sorted(t.tables)] + [a for wb in t.dense for a in wb]
+
+    def loss():
+        return O.train_step_grads(qt, ct, q_ids, q_num, c_ids, {}, probs).loss
+
+    g = O.train_step_grads(qt, ct, q_ids, q_num, c_ids, {}, probs)
+
+    def grads(t, slices, dense):
+        out = []
+        for k in sorted(t.tables):
+            d = np.zeros(t.tables[k].shape, np.float64)
+            np.add.at(d, slices[k].indices, slices[k].values.astype(np.float64))
+            out.append(d)
+        return out + [a.astype(np.float64) for wb in dense for a in wb]
+
+    ps = params(qt) + params(ct)
+    gs = grads(qt, g.tables_q, g.dense_q) + grads(ct, g.tables_c, g.dense_c)
+    assert [p.shape for p in ps] == [x.shape for x in gs]
+    # one random direction per parameter tensor; h small enough that ReLU kinks crossed by the step do not matter
+    # (observed agreement 1e-3 .. 3e-3; a wrong formula is off by O(1))
+    h = 2e-4
+    for p, x in zip(ps, gs):
+        for _ in range(2):
+            d = rng.standard_normal(p.shape)
+            keep = p.copy()
+            p[...] = (keep.astype(np.float64) + h * d).astype(np.float32)
+            up = loss()
+            p[...] = (keep.astype(np.float64) - h * d).astype(np.float32)
+            down = loss()
+            p[...] = keep
+            numeric, analytic = (up - down) / (2 * h), float(np.sum(x * d))
+            assert abs(numeric - analytic) <= 1e-2 * max(abs(analytic), 1.0), (p.shape, numeric, analytic)
+
+
+def test_adagrad_equals_an_independent_implementation():
+    """tf-keras legacy Adagrad (acc0 = 0.1, eps = 1e-7 added OUTSIDE the square root) is the rule torch.optim.Adagrad implements;
+    the sparse path with duplicates summed first must equal the dense rule applied to the densified gradient (untouched rows have
+    zero gradient and do not move).  Four steps, fp32."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    rows, e, lr = 9, 4, 0.05
+    table = rng.uniform(-0.05, 0.05, (rows, e)).astype(np.float32)
+    acc = np.full_like(table, O.ADAGRAD_INIT_ACC)
+    dense_w, dense_acc = table.copy(), acc.copy()
+    p = torch.nn.Parameter(torch.tensor(table.copy()))
+    opt = torch.optim.Adagrad([p], lr=lr, initial_accumulator_value=float(O.ADAGRAD_INIT_ACC), eps=float(O.KERAS_EPS))
+    for _ in range(4):
+        idx = rng.integers(0, rows, 14)                         # 14 draws from 9 rows: duplicates every step
+        val = rng.standard_normal((14, e)).astype(np.float32)
+        O.adagrad_sparse(table, acc, O.IndexedSlices(idx, val), lr)
+        g = np.zeros((rows, e), np.float32)
+        for i, v in zip(idx, val):                              # position order, fp32: the order dedup_indexed_slices defines
+            g[i] += v
+        O.adagrad_dense(dense_w, dense_acc, g, lr)
+        p.grad = torch.tensor(g)
+        opt.step()
+        np.testing.assert_array_equal(table, dense_w)
+        np.testing.assert_array_equal(acc, dense_acc)
+        np.testing.assert_allclose(table, p.detach().numpy(), rtol=0, atol=1e-7)
