@@ -731,6 +731,17 @@ int tt_sparse_sort(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_byt
     return TT_OK;
 }
 
+int tt_debug_sparse_plan(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, int32_t* vec, int32_t* gvec) {
+    JobArr ja;
+    PlanArr pa;
+    int max_tiles = 0, max_pass = 0;
+    TT_REQUIRE(vec != nullptr && gvec != nullptr, "tt_debug_sparse_plan: null pointer");
+    int rc = make_plans(jobs, njobs, ws, ws_bytes, &ja, &pa, &max_tiles, &max_pass, "tt_debug_sparse_plan");
+    if (rc) return rc;
+    for (int j = 0; j < njobs; ++j) { vec[j] = pa.p[j].vec; gvec[j] = pa.p[j].gvec; }
+    return TT_OK;
+}
+
 int tt_sparse_adagrad(const tt_sparse_job* jobs, int njobs, float lr, float eps, void* ws, size_t ws_bytes, void* stream) {
     JobArr ja;
     PlanArr pa;

@@ -94,6 +94,7 @@ SIGNATURES = {
     "tt_sparse_adagrad": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "tt_sparse_adam": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_float, c_float, c_float, c_float, c_void_p, c_size_t,
                                c_void_p]),
+    "tt_debug_sparse_plan": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "tt_index_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int, c_int, c_int]),
     "tt_index_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int64,
                               c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),

@@ -199,6 +199,10 @@ int tt_sparse_adagrad(const tt_sparse_job* jobs, int njobs, float lr, float eps,
  * per-job bitmap workspace inside ws. */
 int tt_sparse_adam(const tt_sparse_job* jobs, int njobs, float lr_t, float beta1, float beta2, float eps, void* ws,
                    size_t ws_bytes, void* stream);
+/* Host-only (no CUDA call; tests): the access width the segmented reduce will use for every job -- vec[j] = floats per
+ * lane access (1, 2 or 4: the widest that divides e and the alignment of the table, slots and workspace), gvec[j] = 1 when
+ * the gradient sources allow the same width (a feature's dX slice may start at any column), 0 for scalar gradient loads. */
+int tt_debug_sparse_plan(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, int32_t* vec, int32_t* gvec);
 
 /* ------------------------------------------------------------------------------------------------
  * Brute-force index (pkg/modelling/indices/brute_force.py:75-83): scores = Q.corpus^T, top_k
