@@ -29,7 +29,9 @@ PINNED against the reference's own fixtures (tests/test_oracle.py, tests/golden/
 PARITY UNPINNED (no reference test or runnable reference covers them): embedding gather / concat order,
   Dense/ReLU, CE-SUM value, every gradient, Adagrad/Adam (dense and sparse-dedup), top_k tie order,
   StaticIndex.call.  These follow upstream documentation and are frozen by the known-answer vectors
-  KAT-A/B/C in tests/golden/kat.json.
+  KAT-A/B/C in tests/golden/kat.json, and cross-checked without TensorFlow in tests/test_oracle.py: the gradients against
+  torch autograd of an independently written float64 forward and against finite differences of the loss; sparse Adagrad
+  against the dense rule on the densified gradient and torch.optim.Adagrad (the same update rule).
 
 Two evaluation modes are offered for contractions:
   ``canonical=True``  sequential k-ascending fused multiply-add in fp32 (C helper, oracle/tt_oracle.c);
