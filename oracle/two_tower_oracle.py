@@ -178,6 +178,13 @@ def logits_qct(q: np.ndarray, c: np.ndarray, canonical: bool = False) -> np.ndar
     return (q.astype(np.float64) @ c.astype(np.float64).T).astype(np.float32)
 
 
+def round_tf32(x: np.ndarray) -> np.ndarray:
+    """fp32 -> TF32 (10 explicit mantissa bits), round to nearest with ties away from zero: what cvt.rna.tf32.f32 and the
+    product's tt_round_tf32 produce for finite values.  Used to restate the operands of the tensor-core index filter."""
+    bits = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
 def logq_correction(logits: np.ndarray, probs: np.ndarray) -> np.ndarray:
     """logits - log(p)[None, :] in fp32 (logq_correction.py:66-71).  ``probs`` is the per-column
     sampling probability after the table lookup (default 1.0 for unknown ids, :38-41)."""

@@ -293,3 +293,56 @@ def test_adagrad_equals_an_independent_implementation():
         np.testing.assert_array_equal(table, dense_w)
         np.testing.assert_array_equal(acc, dense_acc)
         np.testing.assert_allclose(table, p.detach().numpy(), rtol=0, atol=1e-7)
+
+
+def _trunc_f32(v):
+    """float64 -> fp32 rounded TOWARD ZERO (the most pessimistic model of a tensor-core accumulator)."""
+    f = v.astype(np.float32)
+    over = np.abs(f.astype(np.float64)) > np.abs(v)
+    f[over] = np.nextafter(f[over], np.float32(0))
+    return f
+
+
+@pytest.mark.parametrize("E", [32, 64, 128])
+def test_index_filter_error_bound_covers_tf32_scores(E):
+    """The exactness argument of the tensor-core index rests on |a_ij - s_ij| <= 2^-9 ||q_i|| ||c_j||, where a is the
+    score of the TF32-rounded operands however the tensor core accumulates it and s the canonical fp32 score the oracle (and the
+    exact rescoring kernel) computes.  Restated on the CPU: random rows, ReLU-like rows, and the adversarial case (parallel
+    vectors whose every entry sits just below a TF32 rounding tie, so all 2E operand roundings push the score the same way)."""
+    rng = np.random.default_rng(E)
+    nq, n = 48, 96
+    worst = np.float32(1.0 + (2 ** 12 - 1) * 2.0 ** -23)            # rounds up by (almost) half a TF32 ulp
+    cases = {
+        "gaussian": (rng.standard_normal((nq, E)), rng.standard_normal((n, E))),
+        "relu": (np.abs(rng.standard_normal((nq, E))) * 0.1, np.maximum(rng.standard_normal((n, E)), 0) * 0.1),
+        "adversarial": (np.full((nq, E), worst) * 2.0 ** rng.integers(-3, 3, (nq, 1)), np.full((n, E), worst) * 2.0 ** rng.integers(-3, 3, (n, 1))),
+    }
+    for name, (q, c) in cases.items():
+        q, c = q.astype(np.float32), c.astype(np.float32)
+        s = O.logits_qct(q, c, canonical=True).astype(np.float64)
+        qt, ct = O.round_tf32(q).astype(np.float64), O.round_tf32(c).astype(np.float64)
+        assert np.all(np.abs(qt - q) <= 2.0 ** -11 * np.abs(q) * (1 + 1e-6))
+        bound = 2.0 ** -9 * np.linalg.norm(q.astype(np.float64), axis=1)[:, None] * np.linalg.norm(c.astype(np.float64), axis=1)[None, :]
+        exact = qt @ ct.T                                               # products of TF32 values are exact in float64
+        acc = np.zeros((nq, n), np.float32)                             # sequential accumulation, every add truncated
+        for k in range(E):
+            acc = _trunc_f32(acc.astype(np.float64) + qt[:, k:k + 1] * ct[None, :, k])
+        for a in (exact, acc.astype(np.float64)):
+            ratio = np.max(np.abs(a - s) / np.maximum(bound, 1e-300))
+            assert ratio <= 0.55, (name, ratio)                         # 2^-10 from the operand roundings + accumulation, of 2^-9
+        if name == "adversarial":
+            assert np.max(np.abs(exact - s) / bound) > 0.45             # the case really is near the analytical worst (half the bound)
+
+
+def test_tf32_rounded_values_convert_to_fp16_exactly_in_range():
+    """The softmax kernels feed fp16 operand tiles made from TF32-rounded tower outputs: TF32 and fp16 carry the
+    same 11-bit significand, so inside fp16's normal range the conversion is exact and the logits are those of the TF32 path.
+    Below 2^-14 the value lands on fp16's subnormal grid (absolute error <= 2^-25), above 65504 it overflows -- stated limits."""
+    rng = np.random.default_rng(3)
+    mag = np.exp2(rng.uniform(-14, np.log2(65504.0), 200000)).astype(np.float32)
+    x = O.round_tf32(mag * rng.choice([-1.0, 1.0], mag.shape).astype(np.float32))
+    x = x[(np.abs(x) >= 2.0 ** -14) & (np.abs(x) <= 65504)]
+    assert np.array_equal(x.astype(np.float16).astype(np.float32), x)
+    tiny = O.round_tf32(np.exp2(rng.uniform(-30, -14, 50000)).astype(np.float32))
+    assert np.max(np.abs(tiny.astype(np.float16).astype(np.float64) - tiny)) <= 2.0 ** -25
+    assert np.isinf(np.float32(70000.0).astype(np.float16))
