@@ -424,6 +424,12 @@ NCU_SOFTMAX_DRAM_BYTES = 2169600 + 4365568 + 256
 NCU_SOFTMAX_SOURCE = "profiles/r01c_softmax_streamk_ncu_full.md (ncu --set full, per launch, fwd + bwd)"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default size of hbm_rooflines (2^20 ids, 1.37 M x 64 table):
+# gather 245.1 + 222.6 MB (duplicate ids hit L2, part of the output is still in L2 when the kernel ends); segmented reduce
+# 655.0 + 344.9 MB plus the combine kernel's 14.4 MB, for 1.02 GB of algorithmic bytes
+NCU_HBM_DRAM_BYTES = {"gather": 245108480 + 222646272, "update": 655021568 + 344898048 + 14365696}
+NCU_HBM_SOURCE = "profiles/r01d_hbm_kernels_ncu_full.md (gather), profiles/r01e_sparse_block_ncu_full.md (update); ncu --set full, per launch"
+
 HBM_TIMING = None     # (warm-up launches, timed launches) override used by scripts/hbm_microbench.py --once under ncu
 
 
@@ -480,14 +486,16 @@ def hbm_rooflines(pk, lib, b=1 << 20, e=64, rows=V_CUSTOMERS + 1):
         return tot * 1e-3 / n
 
     res = []
-    for name, fn, pre, nbytes in (
-            ("embedding gather (tt_gather_concat)", gather, None, b * (8.0 * e + 4)),
-            ("sparse Adagrad: id sort + segmented reduce + row update", lambda: (sort(), update()), None, b * (1 + 4.0 * uniq / b) * 4 * e),
-            ("sparse Adagrad: segmented reduce + row update (ids already sorted)", update, sort, b * (1 + 4.0 * uniq / b) * 4 * e)):
+    default_size = (b, e, rows) == (1 << 20, 64, V_CUSTOMERS + 1)     # the size the committed ncu captures were taken at
+    for name, fn, pre, nbytes, cap in (
+            ("embedding gather (tt_gather_concat)", gather, None, b * (8.0 * e + 4), "gather"),
+            ("sparse Adagrad: id sort + segmented reduce + row update", lambda: (sort(), update()), None, b * (1 + 4.0 * uniq / b) * 4 * e, None),
+            ("sparse Adagrad: segmented reduce + row update (ids already sorted)", update, sort, b * (1 + 4.0 * uniq / b) * 4 * e, "update")):
         sec = timeit(fn, pre=pre)
         ach = nbytes / sec / 1e9
         res.append({"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                    "traffic": None, "ms": sec * 1e3, "algorithmic_bytes": nbytes,
+                    "traffic": NCU_HBM_DRAM_BYTES[cap] if (cap and default_size) else None,
+                    "traffic_source": NCU_HBM_SOURCE if (cap and default_size) else None, "ms": sec * 1e3, "algorithmic_bytes": nbytes,
                     "config": f"{b} ids into a {rows} x {e} fp32 table ({uniq} unique rows); table + accumulator 0.7 GB > L2"})
     return res
 
