@@ -158,3 +158,22 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|tt_oracle\.h|libtt_oracle", src, flags=re.M):
                     bad.append(f)
     assert not bad, f"product files reference the oracle: {bad}"
+
+
+def test_popularity_index_is_value_counts_order_with_k_max_of_ks():
+    """static_index.py:87-95: ids in value_counts() order (descending frequency), k = max(ks), query features as inputs; the
+    index then answers every query with the same top-k list (static_index.py:54-55) and feeds IndexRecall unchanged."""
+    import pandas as pd
+
+    feats = [Feature("customer_id", tt.string, FeatureFamily.QUERY, 8, vocab=["1"]),
+             Feature("article_id", tt.string, FeatureFamily.CANDIDATE, 8, vocab=["2"])]
+    schema = Schema(feats, TrainingConfig(512, 2048, "adagrad", {"learning_rate": 0.05}), ModelConfig(128, [1, 3]))
+    bought = pd.Series([108, 7, 108, 42, 7, 108, 9])                     # integer ids become strings, as the reference does
+    index = StaticIndex.build_popularity_index_from_series_schema(schema, bought)
+    assert index.k == 3 and [f.name for f in index.input_features] == ["customer_id"]
+    assert index.candidates.shape == (1, 4) and list(index.candidates[0, :2]) == ["108", "7"]
+    out = index({"customer_id": np.array([["a"], ["b"]], dtype=object)})
+    assert out.shape == (2, 3) and (out[0] == out[1]).all() and list(out[0][:2]) == ["108", "7"]
+    metric = IndexRecall(index, ks=[1, 3])
+    got = metric({"customer_id": np.array([["a"], ["b"], ["c"]], dtype=object)}, np.array([["108"], ["7"], ["nope"]], dtype=object))
+    assert got[1] == np.float64(1) / 3 and got[3] == np.float64(2) / 3 and metric.seen == 3
