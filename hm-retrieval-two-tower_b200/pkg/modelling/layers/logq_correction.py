@@ -29,9 +29,9 @@ class LogQCorrection:
         return np.fromiter((self.lookup.get(D._as_str(v), self.default_value) for v in flat), dtype=np.float32,
                            count=flat.shape[0])
 
-    def row_log_probabilities(self, vocab: "D.Vocab") -> np.ndarray:
-        """ln p for every embedding row of the candidate-id table (row 0 = OOV -> ln 1 = 0); used by the
-        fused training path, where ids are already row numbers."""
+    def row_probabilities(self, vocab: "D.Vocab") -> np.ndarray:
+        """p for every embedding row of the candidate-id table (row 0 = OOV -> 1.0, i.e. ln p = 0); the fused training path,
+        where ids are already row numbers, takes the fp32 ln of this table once on the device."""
         p = np.ones(vocab.rows, dtype=np.float32)
         if getattr(vocab, "_range", False):
             for k, v in self.lookup.items():

@@ -101,7 +101,7 @@ class TwoTowerModel(AbstractKerasModel):
         if candidate_prob_lookup:
             self.logq_correction = LogQCorrection(candidate_prob_lookup)
             table = self.candidate_tower.input_layer.embedding_layers[candidate_id_col]
-            rows_p = self.logq_correction.row_log_probabilities(table.vocab)  # probabilities per row
+            rows_p = self.logq_correction.row_probabilities(table.vocab)  # probabilities per row
             self._logq_rows = torch.log(torch.from_numpy(rows_p).cuda())     # fp32 ln, as logq_correction.py:69
         else:
             self.logq_correction = None

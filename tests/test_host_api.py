@@ -177,3 +177,20 @@ def test_popularity_index_is_value_counts_order_with_k_max_of_ks():
     metric = IndexRecall(index, ks=[1, 3])
     got = metric({"customer_id": np.array([["a"], ["b"], ["c"]], dtype=object)}, np.array([["108"], ["7"], ["nope"]], dtype=object))
     assert got[1] == np.float64(1) / 3 and got[3] == np.float64(2) / 3 and metric.seen == 3
+
+
+def test_logq_host_lookup_on_the_reference_fixture(golden):
+    """Host half of LogQCorrection on the reference's fixture (tests/test_layers.py:8-36): string -> probability with default 1.0
+    (logq_correction.py:32-42), per-row ln p for the fused path; ln and the subtraction are the GPU half (tests/test_gpu_model.py)."""
+    from pkg.modelling.layers.logq_correction import LogQCorrection
+
+    fix, _ = golden
+    g = fix["logq"]
+    layer = LogQCorrection(g["candidate_prob_lookup"])
+    ids = np.array([[s.encode()] for s in g["candidate_ids"]], dtype=object)
+    p = layer.probabilities(ids)
+    assert p.dtype == np.float32 and p.tolist() == [np.float32(0.3), np.float32(0.2), np.float32(0.5)]
+    np.testing.assert_allclose(np.asarray(g["logits"], np.float32) - np.log(p)[None, :], g["expected"], rtol=1e-6)
+    assert layer.probabilities(np.array([["id9"], ["id2"]], dtype=object)).tolist() == [1.0, np.float32(0.2)]   # unknown id: p = 1
+    rows = layer.row_probabilities(Vocab(["id3", "id1", "zz"]))        # row 0 = OOV, then vocabulary order; id2 is outside
+    assert rows.tolist() == [1.0, np.float32(0.5), np.float32(0.3), 1.0]
