@@ -194,3 +194,24 @@ def test_logq_host_lookup_on_the_reference_fixture(golden):
     assert layer.probabilities(np.array([["id9"], ["id2"]], dtype=object)).tolist() == [1.0, np.float32(0.2)]   # unknown id: p = 1
     rows = layer.row_probabilities(Vocab(["id3", "id1", "zz"]))        # row 0 = OOV, then vocabulary order; id2 is outside
     assert rows.tolist() == [1.0, np.float32(0.5), np.float32(0.3), 1.0]
+
+
+def test_abstract_model_signature_defaults_and_save(tmp_path):
+    """abstract_keras_model.py:10-131 without TensorFlow: (None, 1) signature per feature, default (1, 1) inputs per dtype,
+    TypeError for any other dtype (:63-68), save() writes the model's arrays."""
+    from pkg.modelling.models.abstract_keras_model import AbstractKerasModel, TensorSpec
+
+    feats = [Feature("query_id", tt.string, FeatureFamily.QUERY, embedding_size=2), Feature("age", tt.float32, FeatureFamily.QUERY)]
+    index = StaticIndex(k=2, input_features=feats, candidates=np.array([["a", "b", "c"]], dtype=object))
+    sig = index.get_input_signature()
+    assert sig == {"query_id": TensorSpec((None, 1), tt.string, "query_id"), "age": TensorSpec((None, 1), tt.float32, "age")}
+    assert index._input_signature == sig                                  # recorded by initialise_model() in the constructor
+    d = index.get_default_inputs(sig)
+    assert d["query_id"].shape == (1, 1) and d["query_id"][0, 0] == "a" and d["age"].dtype == np.float32 and d["age"][0, 0] == 0.0
+    with pytest.raises(TypeError):
+        AbstractKerasModel._get_default_tensor("int64")
+    index.save(str(tmp_path / "m" / "static"))
+    with np.load(tmp_path / "m" / "static" / "variables.npz") as z:
+        assert z["candidates"].tolist() == [["a", "b", "c"]]
+    with pytest.raises(TypeError):
+        AbstractKerasModel()                                              # abstract: call / get_input_signature must be provided
