@@ -94,9 +94,12 @@ def baseline_modelling_runner(settings: Settings, candidates=None, test_ds=None)
     if candidates is None:
         import pandas as pd
 
-        df = pd.read_csv(settings.raw_data_filepath, dtype={settings.candidate_col_name: str})
+        # exactly the reference's load_dataframe + date_filter (etl/transformations.py:38-40,63): default dtype inference -- an id
+        # column of digits is read as integers, so "0108775015" becomes "108775015" here AND in the TFRecords its ETL writes --
+        # and an inclusive comparison of the ISO date strings
+        df = pd.read_csv(settings.raw_data_filepath)
         lo, hi = settings.baseline_model_date_range
-        d = pd.to_datetime(df[settings.date_col_name])
+        d = df[settings.date_col_name]
         candidates = df[(d >= lo) & (d <= hi)][settings.candidate_col_name]
     if not hasattr(candidates, "value_counts"):
         import pandas as pd

@@ -1,0 +1,56 @@
+"""baseline_modelling_runner end to end on the CPU (reference pkg/modelling/runner.py:111-152): raw transactions CSV -> date filter ->
+popularity StaticIndex -> Recall@k over the test TFRecords -> saved index.  Nothing on this path is numeric, so it needs no GPU."""
+import os
+
+import numpy as np
+
+from pkg.modelling.runner import baseline_modelling_runner
+from pkg.schema import dtypes as tt
+from pkg.schema.config import ModelConfig, TrainingConfig
+from pkg.schema.features import Feature, FeatureFamily
+from pkg.schema.schema import Schema
+from pkg.tfrecord_writer.tfrecord_writer import TFRecordWriter
+from pkg.utils.settings import Settings
+
+
+def test_baseline_runner_from_csv_and_tfrecords(tmp_path):
+    import pandas as pd
+
+    rng = np.random.default_rng(5)
+    n = 400
+    days = pd.date_range("2020-08-01", "2020-09-22").strftime("%Y-%m-%d")
+    popular = np.array([108775015, 108775044, 110065001, 111565001, 111586001, 111593001, 111609001])
+    weights = np.array([30, 20, 15, 12, 10, 8, 5], dtype=np.float64)
+    raw = pd.DataFrame({"t_dat": rng.choice(days, n), "customer_id": [f"c{i}" for i in rng.integers(0, 50, n)],
+                        "article_id": [f"0{a}" for a in rng.choice(popular, n, p=weights / weights.sum())]})   # leading zero, as in H&M's file
+    d = str(tmp_path)
+    raw.to_csv(f"{d}/transactions.csv", index=False)
+    feats = [Feature("customer_id", tt.string, FeatureFamily.QUERY, embedding_size=4, vocab=["c0"]),
+             Feature("article_id", tt.string, FeatureFamily.CANDIDATE, embedding_size=4, vocab=["108775015"])]
+    schema = Schema(feats, TrainingConfig(train_batch_size=64, test_batch_size=32, optimizer_name="adagrad", optimizer_kwargs={"learning_rate": 0.1}),
+                    ModelConfig(joint_embedding_size=8, ks=[1, 3, 5]))
+    s = Settings(raw_data_filepath=f"{d}/transactions.csv", articles_data_filepath="", customers_data_filepath="",
+                 train_data_range=("2020-08-01", "2020-09-15"), test_data_range=("2020-09-16", "2020-09-22"),
+                 baseline_model_date_range=("2020-09-01", "2020-09-15"), date_col_name="t_dat", candidate_col_name="article_id",
+                 candidate_tfrecord_path=f"{d}/cand/c.tfrecord", train_data_filepath="", test_data_filepath="",
+                 train_data_tfrecord_path=f"{d}/train/train.tfrecord", test_data_tfrecord_path=f"{d}/test/test.tfrecord",
+                 schema_filepath=f"{d}/schema.pkl", trained_model_path=f"{d}/model/m", index_path=f"{d}/index/i",
+                 baseline_index_path=f"{d}/baseline/index")
+    schema.save(s.schema_filepath)
+    # the test period as the reference's ETL would write it: the CSV re-read with pandas' dtype inference, ids stringified
+    df = pd.read_csv(s.raw_data_filepath)
+    test = df[(df.t_dat >= s.test_data_range[0]) & (df.t_dat <= s.test_data_range[1])]
+    assert len(test) > 20 and df.article_id.dtype.kind == "i"
+    TFRecordWriter(schema.features).write_tfrecords(
+        {"customer_id": test.customer_id.to_numpy(dtype=object), "article_id": np.array([str(a) for a in test.article_id], dtype=object)},
+        s.test_data_tfrecord_path)
+    metric = baseline_modelling_runner(s)
+    window = df[(df.t_dat >= "2020-09-01") & (df.t_dat <= "2020-09-15")].article_id       # both ends inclusive
+    order = [str(a) for a in window.value_counts().index]
+    assert not order[0].startswith("0")
+    for k in (1, 3, 5):
+        want = np.float64(sum(str(a) in order[:k] for a in test.article_id)) / np.float64(len(test))
+        assert metric[k] == want and 0 < want <= 1
+    assert metric[1] <= metric[3] <= metric[5]
+    with np.load(os.path.join(s.baseline_index_path, "variables.npz")) as z:
+        assert z["candidates"].reshape(-1).tolist() == order
