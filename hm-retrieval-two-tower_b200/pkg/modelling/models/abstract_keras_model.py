@@ -67,6 +67,6 @@ class AbstractKerasModel(ABC):
 
     def save(self, model_path: str) -> None:
         os.makedirs(os.path.dirname(model_path) or ".", exist_ok=True)
-        logging.info(f"Saving model at path: {model_path}")
+        logger.info(f"Saving model at path: {model_path}")
         os.makedirs(model_path, exist_ok=True)
         np.savez(os.path.join(model_path, "variables.npz"), **self.state_arrays())

@@ -427,6 +427,6 @@ class TwoTowerModel(AbstractKerasModel):
         for sub, arrs in (("two_tower", self.state_arrays()), ("query_tower", self.query_tower.state_arrays()),
                           ("candidate_tower", self.candidate_tower.state_arrays())):
             path = os.path.join(base, sub)
-            logging.info(f"Saving {sub} at path: {path}")
+            logger.info(f"Saving {sub} at path: {path}")
             os.makedirs(path, exist_ok=True)
             np.savez(os.path.join(path, "variables.npz"), **arrs)
