@@ -13,6 +13,56 @@ from pkg.tfrecord_writer.tfrecord_writer import TFRecordWriter
 from pkg.utils.settings import Settings
 
 
+def test_tfrecord_writer_runner_then_baseline(tmp_path):
+    """tfrecord_writer/runner.py:13-60 followed by the baseline runner, as main.py chains them: train / test CSVs -> candidate,
+    train and test TFRecord partitions -> popularity recall.  Ids with leading zeros survive consistently (both sides drop them)."""
+    import pandas as pd
+
+    from pkg.modelling.tfrecord_dataset import TFRecordDatasetFactory
+    from pkg.tfrecord_writer.runner import tfrecord_writer_runner
+
+    rng = np.random.default_rng(9)
+    arts = np.array(["0108775015", "0108775044", "0110065001", "0111565001", "0111586001"])
+    colour = {a: f"col{i % 2}" for i, a in enumerate(arts)}
+
+    def period(n, lo, hi):
+        a = rng.choice(arts, n, p=[0.4, 0.25, 0.15, 0.12, 0.08])
+        return pd.DataFrame({"t_dat": rng.choice(pd.date_range(lo, hi).strftime("%Y-%m-%d"), n),
+                             "customer_id": [f"c{i}" for i in rng.integers(0, 30, n)], "article_id": a, "colour": [colour[x] for x in a]})
+
+    d = str(tmp_path)
+    train, test = period(230, "2020-09-01", "2020-09-15"), period(70, "2020-09-16", "2020-09-22")
+    train.to_csv(f"{d}/train.csv", index=False)
+    test.to_csv(f"{d}/test.csv", index=False)
+    pd.concat([train, test]).to_csv(f"{d}/transactions.csv", index=False)
+    feats = [Feature("customer_id", tt.string, FeatureFamily.QUERY, embedding_size=4, vocab=["c0"]),
+             Feature("article_id", tt.string, FeatureFamily.CANDIDATE, embedding_size=4, vocab=["108775015"]),
+             Feature("colour", tt.string, FeatureFamily.CANDIDATE, embedding_size=2, vocab=["col0", "col1"])]
+    schema = Schema(feats, TrainingConfig(train_batch_size=64, test_batch_size=32, optimizer_name="adagrad", optimizer_kwargs={"learning_rate": 0.1}),
+                    ModelConfig(joint_embedding_size=8, ks=[1, 2]))
+    s = Settings(raw_data_filepath=f"{d}/transactions.csv", articles_data_filepath="", customers_data_filepath="",
+                 train_data_range=("2020-09-01", "2020-09-15"), test_data_range=("2020-09-16", "2020-09-22"),
+                 baseline_model_date_range=("2020-09-01", "2020-09-15"), date_col_name="t_dat", candidate_col_name="article_id",
+                 candidate_tfrecord_path=f"{d}/cand/candidates.tfrecord", train_data_filepath=f"{d}/train.csv", test_data_filepath=f"{d}/test.csv",
+                 train_data_tfrecord_path=f"{d}/train/train.tfrecord", test_data_tfrecord_path=f"{d}/test/test.tfrecord",
+                 schema_filepath=f"{d}/schema.pkl", trained_model_path=f"{d}/model/m", index_path=f"{d}/index/i",
+                 baseline_index_path=f"{d}/baseline/index", max_tfrecord_rows=100)
+    schema.save(s.schema_filepath)
+    tfrecord_writer_runner(s)
+    assert sorted(os.listdir(f"{d}/train")) == ["train_0.tfrecord", "train_1.tfrecord", "train_2.tfrecord"]       # 100 + 100 + 30 rows
+    assert os.listdir(f"{d}/test") == ["test_0.tfrecord"] and os.listdir(f"{d}/cand") == ["candidates_0.tfrecord"]
+    cand = list(TFRecordDatasetFactory(schema.candidate_features).create_tfrecord_dataset(f"{d}/cand", batch_size=100))[0]
+    got = sorted((a.decode(), c.decode()) for a, c in zip(cand["article_id"].reshape(-1), cand["colour"].reshape(-1)))
+    assert got == sorted((str(int(a)), colour[a]) for a in arts)                 # five unique candidates, ids as pandas inferred them
+    rows = sum(b["customer_id"].shape[0] for b in TFRecordDatasetFactory(schema.features).create_tfrecord_dataset(f"{d}/train", batch_size=64))
+    assert rows == 230
+    metric = baseline_modelling_runner(s)
+    order = [str(a) for a in pd.read_csv(f"{d}/train.csv").article_id.value_counts().index]
+    truth = [str(int(a)) for a in test.article_id]
+    for k in (1, 2):
+        assert metric[k] == np.float64(sum(t in order[:k] for t in truth)) / np.float64(len(truth)) and metric[k] > 0
+
+
 def test_baseline_runner_from_csv_and_tfrecords(tmp_path):
     import pandas as pd
 
