@@ -104,3 +104,49 @@ def test_baseline_runner_from_csv_and_tfrecords(tmp_path):
     assert metric[1] <= metric[3] <= metric[5]
     with np.load(os.path.join(s.baseline_index_path, "variables.npz")) as z:
         assert z["candidates"].reshape(-1).tolist() == order
+
+
+def test_build_schema_runner_vocabulary_order_and_logq_table(tmp_path):
+    """etl/runner.py:54-84: vocabularies in value_counts order (row i + 1 = i-th most frequent id, features.py:119-127) and
+    p(id) = count / len(train) keyed by str(id) (:75-78)."""
+    import pandas as pd
+
+    from pkg.etl.runner import build_schema_runner
+
+    d = str(tmp_path)
+    train = pd.DataFrame({"customer_id": ["b", "a", "b", "c", "b", "a"], "article_id": [7, 7, 9, 7, 108, 9]})
+    train.to_csv(f"{d}/train.csv", index=False)
+    feats = [Feature("customer_id", tt.string, FeatureFamily.QUERY, embedding_size=4),
+             Feature("article_id", tt.string, FeatureFamily.CANDIDATE, embedding_size=4, max_vocab_size=2)]
+    schema = Schema(feats, TrainingConfig(8, 8, "adagrad", {"learning_rate": 0.05}), ModelConfig(8, [1]))
+    s = Settings(raw_data_filepath="", articles_data_filepath="", customers_data_filepath="", train_data_range=("", ""), test_data_range=("", ""),
+                 baseline_model_date_range=("", ""), date_col_name="t_dat", candidate_col_name="article_id", candidate_tfrecord_path="",
+                 train_data_filepath=f"{d}/train.csv", test_data_filepath="", train_data_tfrecord_path="", test_data_tfrecord_path="",
+                 schema_filepath=f"{d}/out/schema.pkl", trained_model_path="", index_path="", baseline_index_path="")
+    build_schema_runner(s, schema)
+    loaded = Schema.load_from_filepath(s.schema_filepath)
+    assert list(loaded.features[0].vocab) == ["b", "a", "c"] and list(loaded.features[1].vocab) == ["7", "9"]     # max_vocab_size = 2
+    assert loaded.training_config.candidate_prob_lookup == {"7": 3 / 6, "9": 2 / 6, "108": 1 / 6}
+    assert all(f.is_built for f in loaded.features)
+
+
+def test_main_entry_point_cpu_steps(tmp_path):
+    """main.py-shaped entry (reference main.py:13-127) on synthetic transactions: schema -> TFRecords -> popularity baseline."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("tt_main", os.path.join(root, "hm-retrieval-two-tower_b200", "main.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.main(["--data-dir", str(tmp_path), "--synthetic", "3000", "--steps", "schema,tfrecords,baseline", "--max-tfrecord-rows", "1000"])
+    recall = out["baseline"]
+    assert set(recall) == {10, 100} and 0 < recall[10] <= recall[100] <= 1
+    schema = Schema.load_from_filepath(str(tmp_path / "schema.pkl"))
+    assert [f.name for f in schema.candidate_features] == ["article_id", "product_type_name", "colour_group_name"]
+    probs = schema.training_config.candidate_prob_lookup
+    assert abs(sum(probs.values()) - 1.0) < 1e-9 and all(k.isdigit() for k in probs)
+    assert len(os.listdir(tmp_path / "tfrecords" / "train")) == 3 and os.path.exists(tmp_path / "trained_models" / "baseline_index" / "variables.npz")
+    import pytest
+
+    with pytest.raises(ValueError):
+        mod.main(["--data-dir", str(tmp_path), "--steps", "etl"])
