@@ -1,12 +1,12 @@
 """Entry point in the shape of the reference's main.py (main.py:13-127): Settings + Schema, then the runners in order.
 
-    python main.py --data-dir ./data                          # train.csv / test.csv already there (the reference's ETL output)
-    python main.py --data-dir /tmp/run --synthetic 200000     # H&M-shaped synthetic transactions instead
+    python main.py --data-dir ./data                          # H&M's transactions_train.csv / articles.csv / customers.csv in ./data
+    python main.py --data-dir /tmp/run --synthetic 200000     # H&M-shaped synthetic raw tables instead
     python main.py --data-dir ./data --steps schema,tfrecords,baseline      # any subset; `model` needs a B200
 
-Steps: ``schema`` (vocabularies + logQ table, etl/runner.py:54-84), ``tfrecords`` (tfrecord_writer/runner.py:13-60), ``model``
-(modelling/runner.py:18-108) and ``baseline`` (modelling/runner.py:111-152).  The raw-table join of the reference's etl_runner is
-not part of this repository."""
+Steps, in the reference's order (main.py:123-127): ``etl`` (raw tables -> train.csv / test.csv, etl/runner.py:15-51), ``schema``
+(vocabularies + logQ table, etl/runner.py:54-84), ``tfrecords`` (tfrecord_writer/runner.py:13-60), ``model``
+(modelling/runner.py:18-108) and ``baseline`` (modelling/runner.py:111-152)."""
 from __future__ import annotations
 
 import argparse
@@ -23,7 +23,7 @@ from pkg.schema.schema import Schema  # noqa: E402
 from pkg.utils.settings import Settings  # noqa: E402
 
 logger = logging.getLogger("pkg.main")
-STEPS = ("schema", "tfrecords", "model", "baseline")
+STEPS = ("etl", "schema", "tfrecords", "model", "baseline")
 
 
 def make_settings(data_dir: str, max_tfrecord_rows: int = 100000) -> Settings:
@@ -53,8 +53,8 @@ def make_schema(joint: int = 64, batch: int = 8192, epochs: int = 1) -> Schema:
 
 
 def write_synthetic(settings: Settings, rows: int, customers: int = 20000, articles: int = 2000, seed: int = 0) -> None:
-    """H&M-shaped transactions: uniform customers, Zipf-popular articles whose side features are functions of the article, and a
-    per-customer taste so that a trained model can beat popularity.  Writes train.csv, test.csv and the raw transactions file."""
+    """H&M-shaped raw tables: transactions (uniform customers, Zipf-popular articles, a per-customer taste so that a trained model
+    can beat popularity), articles with side features that are functions of the article, customers."""
     import numpy as np
     import pandas as pd
 
@@ -65,16 +65,22 @@ def write_synthetic(settings: Settings, rows: int, customers: int = 20000, artic
     a = np.where(rng.random(rows) < 0.6, taste[c], rng.choice(articles, size=rows, p=pop / pop.sum()))
     lo, hi = pd.Timestamp(settings.train_data_range[0]), pd.Timestamp(settings.test_data_range[1])
     day = lo + pd.to_timedelta(np.sort(rng.integers(0, (hi - lo).days + 1, rows)), unit="D")
-    df = pd.DataFrame({"t_dat": day.strftime("%Y-%m-%d"), "customer_id": [f"cust{i:07d}" for i in c], "article_id": 100000000 + a,
-                       "product_type_name": [f"type{i % 131}" for i in a], "colour_group_name": [f"colour{i % 50}" for i in a]})
     os.makedirs(os.path.dirname(settings.raw_data_filepath) or ".", exist_ok=True)
-    df.to_csv(settings.raw_data_filepath, index=False)
-    for path, (start, end) in ((settings.train_data_filepath, settings.train_data_range), (settings.test_data_filepath, settings.test_data_range)):
-        df[(df.t_dat >= start) & (df.t_dat <= end)].to_csv(path, index=False)
+    pd.DataFrame({"t_dat": day.strftime("%Y-%m-%d"), "customer_id": [f"cust{i:07d}" for i in c], "article_id": 100000000 + a}).to_csv(
+        settings.raw_data_filepath, index=False)
+    ids = np.arange(articles)
+    pd.DataFrame({"article_id": 100000000 + ids, "product_type_name": [f"type{i % 131}" for i in ids],
+                  "colour_group_name": [f"colour{i % 50}" for i in ids]}).to_csv(settings.articles_data_filepath, index=False)
+    pd.DataFrame({"customer_id": [f"cust{i:07d}" for i in range(customers)], "age": rng.integers(16, 90, customers)}).to_csv(
+        settings.customers_data_filepath, index=False)
 
 
 def run(settings: Settings, schema: Schema, steps) -> dict:
     out = {}
+    if "etl" in steps:
+        from pkg.etl.runner import etl_runner
+
+        etl_runner(settings)
     if "schema" in steps:
         from pkg.etl.runner import build_schema_runner
 
@@ -97,7 +103,7 @@ def run(settings: Settings, schema: Schema, steps) -> dict:
 def main(argv=None) -> dict:
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--data-dir", default="./data")
-    ap.add_argument("--synthetic", type=int, default=0, metavar="ROWS", help="generate ROWS synthetic transactions into --data-dir first")
+    ap.add_argument("--synthetic", type=int, default=0, metavar="ROWS", help="write synthetic raw tables with ROWS transactions into --data-dir first")
     ap.add_argument("--steps", default=",".join(STEPS), help="comma-separated subset of " + ",".join(STEPS))
     ap.add_argument("--joint", type=int, default=64)
     ap.add_argument("--batch", type=int, default=8192)

@@ -14,6 +14,7 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
+from pkg.etl.transformations import date_filter, load_dataframe
 from pkg.modelling.indices.brute_force import BruteForceIndex
 from pkg.modelling.indices.static_index import StaticIndex
 from pkg.modelling.losses import CategoricalCrossentropy
@@ -92,15 +93,10 @@ def baseline_modelling_runner(settings: Settings, candidates=None, test_ds=None)
     logger.info("--- Baseline Modelling Starting ---")
     schema = Schema.load_from_filepath(settings.schema_filepath)
     if candidates is None:
-        import pandas as pd
-
-        # exactly the reference's load_dataframe + date_filter (etl/transformations.py:38-40,63): default dtype inference -- an id
-        # column of digits is read as integers, so "0108775015" becomes "108775015" here AND in the TFRecords its ETL writes --
-        # and an inclusive comparison of the ISO date strings
-        df = pd.read_csv(settings.raw_data_filepath)
-        lo, hi = settings.baseline_model_date_range
-        d = df[settings.date_col_name]
-        candidates = df[(d >= lo) & (d <= hi)][settings.candidate_col_name]
+        # the reference's load_dataframe + date_filter (etl/transformations.py:9-64): dtype inference -- an id column of digits is
+        # read as integers, so "0108775015" becomes "108775015" here AND in the TFRecords its ETL writes -- inclusive string dates
+        df = load_dataframe(settings.raw_data_filepath, "raw_transactions")
+        candidates = date_filter(df, "raw_transactions", settings.date_col_name, settings.baseline_model_date_range)[settings.candidate_col_name]
     if not hasattr(candidates, "value_counts"):
         import pandas as pd
 

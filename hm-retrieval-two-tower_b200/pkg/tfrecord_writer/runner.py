@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import logging
 
+from pkg.etl.transformations import load_dataframe
 from pkg.schema.schema import Schema
 from pkg.tfrecord_writer.tfrecord_writer import TFRecordWriter
 from pkg.utils.settings import Settings
@@ -20,7 +21,7 @@ def tfrecord_writer_runner(settings: Settings) -> None:
 
     logger.info("--- TFRecord Writing Starting ---")
     schema = Schema.load_from_filepath(settings.schema_filepath)
-    frames = {"train": pd.read_csv(settings.train_data_filepath), "test": pd.read_csv(settings.test_data_filepath)}
+    frames = {"train": load_dataframe(settings.train_data_filepath, "train"), "test": load_dataframe(settings.test_data_filepath, "test")}
     # every candidate seen in either period, one row each (a candidate is assumed to carry the same side features everywhere)
     cols = [f.name for f in schema.candidate_features]
     seen = pd.concat(list(frames.values()))[cols]

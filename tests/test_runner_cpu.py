@@ -131,14 +131,14 @@ def test_build_schema_runner_vocabulary_order_and_logq_table(tmp_path):
 
 
 def test_main_entry_point_cpu_steps(tmp_path):
-    """main.py-shaped entry (reference main.py:13-127) on synthetic transactions: schema -> TFRecords -> popularity baseline."""
+    """main.py-shaped entry (reference main.py:13-127) on synthetic raw tables: ETL -> schema -> TFRecords -> popularity baseline."""
     import importlib.util
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     spec = importlib.util.spec_from_file_location("tt_main", os.path.join(root, "hm-retrieval-two-tower_b200", "main.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    out = mod.main(["--data-dir", str(tmp_path), "--synthetic", "3000", "--steps", "schema,tfrecords,baseline", "--max-tfrecord-rows", "1000"])
+    out = mod.main(["--data-dir", str(tmp_path), "--synthetic", "3000", "--steps", "etl,schema,tfrecords,baseline", "--max-tfrecord-rows", "1000"])
     recall = out["baseline"]
     assert set(recall) == {10, 100} and 0 < recall[10] <= recall[100] <= 1
     schema = Schema.load_from_filepath(str(tmp_path / "schema.pkl"))
@@ -149,4 +149,41 @@ def test_main_entry_point_cpu_steps(tmp_path):
     import pytest
 
     with pytest.raises(ValueError):
-        mod.main(["--data-dir", str(tmp_path), "--steps", "etl"])
+        mod.main(["--data-dir", str(tmp_path), "--steps", "bogus"])
+
+
+def test_date_filter_like_the_reference_test():
+    """The reference's tests/test_transformations.py:7-38 on the same frame: both ends of the range are inclusive."""
+    import pandas as pd
+
+    from pkg.etl.transformations import date_filter
+
+    df = pd.DataFrame({"date_col": ["2024-01-01", "2024-02-01", "2024-03-01", "2024-04-01", "2024-05-01"],
+                       "query_id": ["123", "456", "123", "789", "456"], "candidate_id": ["abc", "def", "ghi", "abc", "def"]})
+    train = date_filter(df, "train", "date_col", ("2024-01-01", "2024-02-01"))
+    test = date_filter(df, "train", "date_col", ("2024-03-01", "2024-04-01"))
+    assert (train["date_col"].min(), train["date_col"].max()) == ("2024-01-01", "2024-02-01")
+    assert (test["date_col"].min(), test["date_col"].max()) == ("2024-03-01", "2024-04-01")
+    assert len(date_filter(df, "none", "date_col", ("2025-01-01", "2025-02-01"))) == 0
+
+
+def test_etl_runner_joins_and_splits(tmp_path):
+    """etl/runner.py:15-51: inner joins with the article and customer tables, then the two date windows."""
+    import pandas as pd
+
+    from pkg.etl.runner import etl_runner
+
+    d = str(tmp_path)
+    pd.DataFrame({"t_dat": ["2020-01-01", "2020-01-05", "2020-02-01", "2020-02-03", "2020-03-01"], "customer_id": ["a", "b", "a", "zz", "b"],
+                  "article_id": ["0101", "0102", "0101", "0102", "0999"]}).to_csv(f"{d}/tx.csv", index=False)
+    pd.DataFrame({"article_id": ["0101", "0102"], "colour": ["red", "blue"]}).to_csv(f"{d}/articles.csv", index=False)
+    pd.DataFrame({"customer_id": ["a", "b"], "age": [30, 40]}).to_csv(f"{d}/customers.csv", index=False)
+    s = Settings(raw_data_filepath=f"{d}/tx.csv", articles_data_filepath=f"{d}/articles.csv", customers_data_filepath=f"{d}/customers.csv",
+                 train_data_range=("2020-01-01", "2020-01-31"), test_data_range=("2020-02-01", "2020-03-31"), baseline_model_date_range=("", ""),
+                 date_col_name="t_dat", candidate_col_name="article_id", candidate_tfrecord_path="", train_data_filepath=f"{d}/out/train.csv",
+                 test_data_filepath=f"{d}/out/test.csv", train_data_tfrecord_path="", test_data_tfrecord_path="", schema_filepath="",
+                 trained_model_path="", index_path="", baseline_index_path="")
+    etl_runner(s)
+    train, test = pd.read_csv(s.train_data_filepath), pd.read_csv(s.test_data_filepath)
+    assert train[["customer_id", "article_id", "colour", "age"]].values.tolist() == [["a", 101, "red", 30], ["b", 102, "blue", 40]]
+    assert test[["customer_id", "article_id"]].values.tolist() == [["a", 101]]      # unknown customer zz and unknown article 0999 are dropped
