@@ -35,7 +35,7 @@ class StaticIndex(AbstractKerasModel):
         """Ids ordered by frequency in the pandas Series ``s`` (value_counts order)."""
         ids = s.value_counts().index
         return cls(k=max(schema.model_config.ks), input_features=schema.query_features,
-                   candidates=np.array([str(i) for i in ids], dtype=object).reshape(1, len(ids)))
+                   candidates=np.array([str(i) for i in ids]).reshape(1, len(ids)))      # fixed-width strings: cheap to tile and compare
 
     def state_arrays(self) -> Dict[str, np.ndarray]:
         return {"candidates": self.candidates.astype(str)}

@@ -67,8 +67,16 @@ class IndexRecall:
             candidates = np.asarray(self.index(queries))
             truth = np.asarray(true_candidate_ids).reshape(-1, 1)
             if truth.dtype.kind in ("S", "O", "U") or candidates.dtype.kind in ("S", "O", "U"):
-                conv = np.vectorize(lambda v: v.decode() if isinstance(v, bytes) else str(v), otypes=[object])
-                truth, candidates = conv(truth), conv(candidates)
+                # ids may arrive as str on one side and bytes on the other (TFRecords yield bytes).  The (B, 1) truth column is
+                # brought to the dtype of the (B, k) candidate block, which is then compared in one vectorised pass -- not a Python
+                # call per element: the reference's main.py evaluates k = 1000 candidates per query
+                if candidates.dtype.kind == "O":
+                    candidates = D._as_bytes_array(candidates).reshape(candidates.shape)
+                if candidates.dtype.kind == "U":
+                    flat = truth.reshape(-1)
+                    truth = np.array([D._as_str(v) for v in flat]).reshape(-1, 1) if flat.shape[0] else truth.astype("U1")
+                else:
+                    truth = D._as_bytes_array(truth).reshape(-1, 1)
             for k in self.ks:
                 self.hits[k] = np.int32(self.hits[k] + np.int32(np.sum(truth == candidates[:, :k])))
         for k in self.ks:
