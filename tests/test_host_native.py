@@ -157,3 +157,64 @@ def test_vocab_native_lookup_matches_string_lookup():
 
     v2 = pickle.loads(pickle.dumps(v))                                            # Schema objects are pickled (schema.py)
     np.testing.assert_array_equal(v2.encode(queries), want)
+
+
+def _frame(lib, payload: bytes) -> bytes:
+    out = ctypes.create_string_buffer(len(payload) + 16)
+    assert lib.tt_tfrecord_frame(payload, len(payload), out) == 0
+    return out.raw
+
+
+def test_corrupted_files_are_rejected_not_crashed_on(lib, tmp_path):
+    """The native readers see files from disk: truncated, bit-flipped, random or absurd-length framing must come back as an error
+    (or as slices inside the file), and a well-framed record whose payload is not a valid Example as a ValueError -- never a crash."""
+    rng = np.random.default_rng(5)
+    good = b"".join(_frame(lib, bytes(rng.integers(0, 256, int(rng.integers(0, 40)), dtype=np.uint8))) for _ in range(6))
+    for _ in range(3000):
+        b = bytearray(good)
+        mode = int(rng.integers(0, 4))
+        if mode == 0:
+            b = b[:int(rng.integers(0, len(b) + 1))]
+        elif mode == 1:
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        elif mode == 2:
+            b = bytearray(rng.integers(0, 256, int(rng.integers(0, 100)), dtype=np.uint8).tobytes())
+        else:
+            b[0:8] = struct.pack("<Q", int(rng.integers(0, 2 ** 63 - 1)))          # a length field far beyond the file
+        buf = bytes(b)
+        for verify in (0, 1):
+            off, ln = (ctypes.c_int64 * 8)(), (ctypes.c_int64 * 8)()
+            n = lib.tt_tfrecord_scan(buf, len(buf), verify, off, ln, 8)
+            assert n == -5 or 0 <= n <= 6
+            for i in range(max(n, 0)):
+                assert 0 <= off[i] and off[i] + ln[i] <= len(buf)
+    feats = _features()
+    w = TFRecordWriter(feats)
+    base = [w._get_features_from_row({"customer_id": f"c{i}", "age": 0.25 * i, "article_id": f"{i * 7919:010d}"}) for i in range(8)]
+    path = str(tmp_path / "f.tfrecord")
+    parsed = rejected = 0
+    for _ in range(1500):
+        recs = []
+        for _ in range(int(rng.integers(1, 5))):
+            p = bytearray(base[int(rng.integers(0, 8))])
+            mode = int(rng.integers(0, 5))
+            if mode == 0:
+                for _ in range(int(rng.integers(1, 4))):
+                    p[int(rng.integers(0, len(p)))] = int(rng.integers(0, 256))
+            elif mode == 1:
+                p = p[:int(rng.integers(0, len(p)))]
+            elif mode == 2:
+                p = p + bytes(rng.integers(0, 256, int(rng.integers(1, 20)), dtype=np.uint8))
+            elif mode == 3:
+                p = bytearray(rng.integers(0, 256, int(rng.integers(0, 60)), dtype=np.uint8).tobytes())
+            recs.append(_frame(lib, bytes(p)))
+        with open(path, "wb") as fh:
+            fh.write(b"".join(recs))
+        try:
+            cols = read_tfrecord_file(path, feats)
+            assert all(len(v) == len(recs) for v in cols.values())
+            parsed += 1
+        except ValueError:
+            rejected += 1
+    assert parsed > 50 and rejected > 1000
