@@ -88,30 +88,82 @@ static uint32_t crc32c(const void* data, size_t n, bool force_sw = false) {
 static inline uint32_t mask_crc(uint32_t crc) { return ((crc >> 15) | (crc << 17)) + 0xa282ead8u; }   // TFRecord's masking
 
 // ---- vocabulary map -----------------------------------------------------------------------------------------------
-static inline uint64_t hash_bytes(const char* p, size_t n) {   // FNV-1a with a final avalanche
-    uint64_t h = 1469598103934665603ull;
-    for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; }
+// Word-at-a-time multiply / xor-shift hash.  Only speed depends on it: every hit is confirmed by comparing the bytes.
+static inline uint64_t hash_bytes(const char* p, size_t n) {
+    uint64_t h = 0x9e3779b97f4a7c15ull ^ (n * 0xd6e8feb86659fd93ull);
+    while (n >= 8) {
+        uint64_t w;
+        memcpy(&w, p, 8);
+        h = (h ^ w) * 0xff51afd7ed558ccdull;
+        h ^= h >> 29;
+        p += 8; n -= 8;
+    }
+    if (n) {
+        uint64_t w = 0;
+        memcpy(&w, p, n);
+        h = (h ^ w) * 0xc4ceb9fe1a85ec53ull;
+    }
     h ^= h >> 32; h *= 0xd6e8feb86659fd93ull; h ^= h >> 32;
     return h;
 }
 
+// Open addressing, load factor <= 1/2.  An entry carries everything a probe needs before it touches the string bytes -- the high
+// hash bits, the vocabulary index and where the string lies -- so a lookup costs two dependent cache misses (entry, bytes), and
+// lookup_block overlaps those misses across 16 keys with software prefetches (a 1.37 M-entry table does not fit any cache).
 struct Vocab {
-    std::string blob;               // all vocabulary strings back to back
-    std::vector<int64_t> off;       // n + 1 offsets into blob
-    std::vector<int32_t> slot;      // open addressing: vocabulary index + 1, 0 = empty
-    std::vector<uint32_t> tag;      // high hash bits of the occupant (skips most string compares)
+    struct Ent {
+        uint32_t tag;       // high hash bits | 1; 0 = empty slot
+        int32_t idx1;       // vocabulary index + 1
+        uint64_t where;     // (offset into blob << 24) | length
+    };
+    static constexpr uint64_t kMaxLen = (1ull << 24) - 1;
+    std::string blob;       // all vocabulary strings back to back
+    std::vector<Ent> ent;
     uint64_t mask = 0;
+    int64_t n = 0;
 
-    int32_t find(const char* s, size_t n) const {
-        const uint64_t h = hash_bytes(s, n);
-        const uint32_t tg = (uint32_t)(h >> 32) | 1u;
-        for (uint64_t i = h & mask;; i = (i + 1) & mask) {
-            const int32_t v = slot[i];
-            if (v == 0) return 0;   // OOV
-            if (tag[i] == tg) {
-                const int64_t a = off[v - 1], len = off[v] - a;
-                if ((size_t)len == n && memcmp(blob.data() + a, s, n) == 0) return v;
+    static inline uint32_t tag_of(uint64_t h) { return (uint32_t)(h >> 32) | 1u; }
+
+    // first slot at or after `i` that is empty or carries the tag
+    inline uint64_t seek(uint64_t i, uint32_t tg) const {
+        while (ent[i].tag != 0 && ent[i].tag != tg) i = (i + 1) & mask;
+        return i;
+    }
+    // resolve from a slot returned by seek
+    inline int32_t finish(uint64_t i, uint32_t tg, const char* s, size_t len) const {
+        for (;; i = (i + 1) & mask) {
+            const Ent& e = ent[i];
+            if (e.tag == 0) return 0;   // OOV
+            if (e.tag == tg && (e.where & kMaxLen) == len && memcmp(blob.data() + (e.where >> 24), s, len) == 0) return e.idx1;
+        }
+    }
+    int32_t find(const char* s, size_t len) const {
+        const uint64_t h = hash_bytes(s, len);
+        const uint32_t tg = tag_of(h);
+        return finish(seek(h & mask, tg), tg, s, len);
+    }
+    // keys lo..hi-1 through key_at(i, &ptr, &len), results to out[i]
+    template <typename KeyAt>
+    void lookup_block(int64_t lo, int64_t hi, KeyAt key_at, int32_t* out) const {
+        constexpr int W = 16;
+        const char* s[W];
+        size_t len[W];
+        uint64_t pos[W];
+        uint32_t tg[W];
+        for (int64_t i = lo; i < hi; i += W) {
+            const int m = (int)(hi - i < W ? hi - i : W);
+            for (int k = 0; k < m; ++k) {
+                key_at(i + k, &s[k], &len[k]);
+                const uint64_t h = hash_bytes(s[k], len[k]);
+                tg[k] = tag_of(h);
+                pos[k] = h & mask;
+                __builtin_prefetch(&ent[pos[k]]);
             }
+            for (int k = 0; k < m; ++k) {
+                pos[k] = seek(pos[k], tg[k]);
+                if (ent[pos[k]].tag != 0) __builtin_prefetch(blob.data() + (ent[pos[k]].where >> 24));
+            }
+            for (int k = 0; k < m; ++k) out[i + k] = finish(pos[k], tg[k], s[k], len[k]);
         }
     }
 };
@@ -175,44 +227,46 @@ uint32_t tt_crc32c_masked(const void* data, size_t n) { return mask_crc(crc32c(d
 
 void* tt_vocab_create(const char* blob, const int64_t* offsets, int64_t n) {
     if (n < 0 || (n > 0 && (!blob || !offsets))) { set_error("tt_vocab_create: null pointer"); return nullptr; }
+    for (int64_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i] || (uint64_t)(offsets[i + 1] - offsets[i]) > Vocab::kMaxLen) {
+            set_error("tt_vocab_create: entry %lld has a negative or oversized length", (long long)i);
+            return nullptr;
+        }
+    }
     Vocab* v = new Vocab();
+    v->n = n;
     v->blob.assign(blob ? blob : "", n > 0 ? (size_t)offsets[n] : 0);
-    v->off.assign(offsets, offsets + n + 1);
     uint64_t cap = 16;
     while (cap < (uint64_t)n * 2 + 2) cap <<= 1;
-    v->slot.assign(cap, 0);
-    v->tag.assign(cap, 0);
+    v->ent.assign(cap, Vocab::Ent{0u, 0, 0ull});
     v->mask = cap - 1;
     for (int64_t i = 0; i < n; ++i) {
-        const char* s = v->blob.data() + v->off[i];
-        const size_t len = (size_t)(v->off[i + 1] - v->off[i]);
+        const char* s = v->blob.data() + offsets[i];
+        const size_t len = (size_t)(offsets[i + 1] - offsets[i]);
         const uint64_t h = hash_bytes(s, len);
-        const uint32_t tg = (uint32_t)(h >> 32) | 1u;
-        bool dup = false;
+        const uint32_t tg = Vocab::tag_of(h);
         uint64_t j = h & v->mask;
+        bool dup = false;
         for (;; j = (j + 1) & v->mask) {
-            const int32_t o = v->slot[j];
-            if (o == 0) break;
-            if (v->tag[j] == tg) {
-                const int64_t a = v->off[o - 1], l2 = v->off[o] - a;
-                if ((size_t)l2 == len && memcmp(v->blob.data() + a, s, len) == 0) { dup = true; break; }   // first occurrence wins
-            }
+            const Vocab::Ent& e = v->ent[j];
+            if (e.tag == 0) break;
+            if (e.tag == tg && (e.where & Vocab::kMaxLen) == len && memcmp(v->blob.data() + (e.where >> 24), s, len) == 0) { dup = true; break; }
         }
-        if (!dup) { v->slot[j] = (int32_t)(i + 1); v->tag[j] = tg; }
+        if (!dup) v->ent[j] = Vocab::Ent{tg, (int32_t)(i + 1), ((uint64_t)offsets[i] << 24) | (uint64_t)len};   // first occurrence wins
     }
     return v;
 }
 
 void tt_vocab_destroy(void* h) { delete reinterpret_cast<Vocab*>(h); }
 
-int64_t tt_vocab_size(void* h) { return h ? (int64_t)reinterpret_cast<Vocab*>(h)->off.size() - 1 : -1; }
+int64_t tt_vocab_size(void* h) { return h ? reinterpret_cast<Vocab*>(h)->n : -1; }
 
 /* strings = blob[offsets[i] .. offsets[i+1]) */
 int tt_vocab_lookup(void* h, const char* blob, const int64_t* offsets, int64_t n, int32_t* out, int nthreads) {
     TT_REQUIRE(h && out && (n == 0 || (blob && offsets)), "tt_vocab_lookup: null pointer");
     const Vocab* v = reinterpret_cast<const Vocab*>(h);
     parallel_for(n, nthreads, [=](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) out[i] = v->find(blob + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
+        v->lookup_block(lo, hi, [=](int64_t i, const char** s, size_t* len) { *s = blob + offsets[i]; *len = (size_t)(offsets[i + 1] - offsets[i]); }, out);
     });
     return TT_OK;
 }
@@ -222,12 +276,12 @@ int tt_vocab_lookup_fixed(void* h, const char* data, int64_t n, int width, int32
     TT_REQUIRE(h && out && (n == 0 || data) && width >= 1, "tt_vocab_lookup_fixed: bad argument");
     const Vocab* v = reinterpret_cast<const Vocab*>(h);
     parallel_for(n, nthreads, [=](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
-            const char* s = data + i * width;
-            size_t len = (size_t)width;
-            while (len > 0 && s[len - 1] == '\0') --len;
-            out[i] = v->find(s, len);
-        }
+        v->lookup_block(lo, hi, [=](int64_t i, const char** s, size_t* len) {
+            const char* c = data + i * width;
+            size_t l = (size_t)width;
+            while (l > 0 && c[l - 1] == '\0') --l;
+            *s = c; *len = l;
+        }, out);
     });
     return TT_OK;
 }
