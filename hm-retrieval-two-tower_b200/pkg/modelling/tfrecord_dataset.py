@@ -72,8 +72,7 @@ class TFRecordDataset:
         if self._cols is None:
             parts = [read_tfrecord_file(p, self.features) for p in self.filenames]
             self._cols = {f.name: (np.concatenate([p[f.name] for p in parts]) if parts else np.zeros(0, dtype=np.float32)) for f in self.features}
-            for f in self.features:   # string columns of different files may have different widths: numpy widens on concatenate
-                pass
+            # string columns of different files may have different widths: numpy widens on concatenate
         return self._cols
 
     def __len__(self) -> int:
@@ -82,21 +81,30 @@ class TFRecordDataset:
         return n if not self.batch_size else (n + self.batch_size - 1) // self.batch_size
 
     def _order(self, n: int) -> np.ndarray:
+        """Element order of tf.data's buffer shuffle: a buffer of ``shuffle_size`` slots; every step a uniformly random slot emits its
+        element and takes the next input element; once the input is exhausted the remaining slots are emitted in random order.
+        Vectorised: with r[t] the slot picked at step t, the element a slot emits at one of its picks is the one it took at its
+        previous pick (its initial element at the first), so grouping the steps by slot gives the whole order without a Python loop."""
         if not self.shuffle_size or n == 0:
             return np.arange(n)
         rng = np.random.default_rng(self.seed)
-        buf = list(range(min(self.shuffle_size, n)))
-        nxt = len(buf)
+        s = min(self.shuffle_size, n)
+        m = n - s                                          # steps during which the input still has elements: slot r[t] takes element s + t
         out = np.empty(n, dtype=np.int64)
-        for i in range(n):
-            j = int(rng.integers(len(buf)))
-            out[i] = buf[j]
-            if nxt < n:
-                buf[j] = nxt
-                nxt += 1
-            else:
-                buf[j] = buf[-1]
-                buf.pop()
+        content = np.arange(s, dtype=np.int64)             # what the slots hold when the input runs out
+        if m:
+            r = rng.integers(0, s, size=m)
+            by_slot = np.argsort(r, kind="stable")         # steps grouped by slot, ascending within a slot
+            rs = r[by_slot]
+            new_slot = np.ones(m, dtype=bool)
+            new_slot[1:] = rs[1:] != rs[:-1]
+            prev_step = np.zeros(m, dtype=np.int64)
+            prev_step[1:] = by_slot[:-1]
+            out[by_slot] = np.where(new_slot, rs, s + prev_step)
+            last_of_slot = np.ones(m, dtype=bool)
+            last_of_slot[:-1] = new_slot[1:]
+            content[rs[last_of_slot]] = s + by_slot[last_of_slot]
+        out[m:] = rng.permutation(content)
         return out
 
     def map(self, fn: Callable) -> "TFRecordDataset":
