@@ -218,3 +218,37 @@ def test_corrupted_files_are_rejected_not_crashed_on(lib, tmp_path):
         except ValueError:
             rejected += 1
     assert parsed > 50 and rejected > 1000
+
+
+def test_buffer_shuffle_order_properties():
+    """tf.data buffer-shuffle semantics of TFRecordDataset._order (tfrecord_dataset.py:86-92 of the reference: ds.shuffle(size)): a
+    permutation; an element is never emitted more than ``size - 1`` steps early; size 1 is the identity; the emission time of an
+    element follows the distribution of the step-by-step simulation."""
+    from pkg.modelling.tfrecord_dataset import TFRecordDataset
+
+    def sequential(n, size, rng):
+        buf, nxt, out = list(range(min(size, n))), min(size, n), []
+        for _ in range(n):
+            j = int(rng.integers(len(buf)))
+            out.append(buf[j])
+            if nxt < n:
+                buf[j] = nxt
+                nxt += 1
+            else:
+                buf[j] = buf[-1]
+                buf.pop()
+        return out
+
+    for n in (0, 1, 2, 5, 50, 1000):
+        for size in (1, 2, 7, 49, 50, 51, 5000):
+            o = TFRecordDataset([], [], None, size, seed=n + size)._order(n)
+            assert sorted(o.tolist()) == list(range(n))
+            assert all(int(v) - i < min(size, n) for i, v in enumerate(o))
+            if size == 1:
+                assert o.tolist() == list(range(n))
+    n, size, trials = 60, 8, 3000
+    fast = np.array([np.argsort(TFRecordDataset([], [], None, size, seed=k)._order(n)) for k in range(trials)])
+    slow = np.array([np.argsort(sequential(n, size, np.random.default_rng(10_000 + k))) for k in range(trials)])
+    for element in (0, 10, 59):
+        assert abs(fast[:, element].mean() - slow[:, element].mean()) < 0.6
+        assert abs(fast[:, element].std() - slow[:, element].std()) < 0.5
