@@ -24,7 +24,12 @@ from pkg.schema.features import Feature
 logger = logging.getLogger(__name__)
 
 
+_ONE_BYTE = [bytes((i,)) for i in range(128)]
+
+
 def _varint(n: int) -> bytes:
+    if n < 128:                       # almost every length on this path: feature names, ids, one-float lists
+        return _ONE_BYTE[n]
     out = bytearray()
     while True:
         b = n & 0x7F
@@ -36,14 +41,18 @@ def _varint(n: int) -> bytes:
             return bytes(out)
 
 
+_LD_TAG = [_varint((field << 3) | 2) for field in range(16)]
+
+
 def _ld(field: int, payload: bytes) -> bytes:
     """length-delimited field"""
-    return _varint((field << 3) | 2) + _varint(len(payload)) + payload
+    return _LD_TAG[field] + _varint(len(payload)) + payload
 
 
 class TFRecordWriter:
     def __init__(self, features: List[Feature]):
         self.features = features
+        self._key_bytes = {}             # feature name -> serialized map key (constant per feature)
 
     def _parse_feature(self, feature_val: Union[str, float, int], dtype) -> bytes:
         """Serialized tf.train.Feature holding ``feature_val``; TypeError for an unsupported dtype (reference :49-53)."""
@@ -57,9 +66,13 @@ class TFRecordWriter:
     def _get_features_from_row(self, row) -> bytes:
         """``row``: a NamedTuple from DataFrame.itertuples() or a mapping name -> value.  Returns Example bytes."""
         entries = []
+        is_dict = isinstance(row, dict)
         for feature in self.features:
-            v = row[feature.name] if isinstance(row, dict) else getattr(row, feature.name)
-            entry = _ld(1, feature.name.encode()) + _ld(2, self._parse_feature(v, feature.dtype))   # map entry {key, value}
+            v = row[feature.name] if is_dict else getattr(row, feature.name)
+            key = self._key_bytes.get(feature.name)
+            if key is None:
+                key = self._key_bytes[feature.name] = _ld(1, feature.name.encode())
+            entry = key + _ld(2, self._parse_feature(v, feature.dtype))                             # map entry {key, value}
             entries.append(_ld(1, entry))
         return _ld(1, b"".join(entries))                                        # Example { features { feature: ... } }
 
