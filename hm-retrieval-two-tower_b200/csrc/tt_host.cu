@@ -332,6 +332,23 @@ int tt_tfrecord_frame(const void* payload, uint64_t len, void* out) {
  * (str_off[f*nrec + i], str_len[f*nrec + i]) into `file`; for a float feature it is written to fvals[f*nrec + i].
  * A record that lacks a requested feature, or holds it with another type or not exactly one value, is an error
  * (tf.io.parse_single_example with FixedLenFeature([1]) raises too). */
+int tt_gather_cells(const void* file, size_t nbytes, const int64_t* str_off, const int64_t* str_len, int64_t n, int width, char* out, int nthreads) {
+    TT_REQUIRE(out && width >= 1 && n >= 0 && (n == 0 || (file && str_off && str_len)), "tt_gather_cells: bad argument");
+    for (int64_t i = 0; i < n; ++i)
+        TT_REQUIRE(str_len[i] >= 0 && str_len[i] <= width && str_off[i] >= 0 && (uint64_t)str_off[i] + (uint64_t)str_len[i] <= nbytes,
+                   "tt_gather_cells: string %lld lies outside the file image or exceeds the cell width", (long long)i);
+    const char* base = reinterpret_cast<const char*>(file);
+    parallel_for(n, nthreads, [=](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            char* cell = out + i * (int64_t)width;
+            const size_t len = (size_t)str_len[i];
+            memcpy(cell, base + str_off[i], len);
+            memset(cell + len, 0, (size_t)width - len);
+        }
+    });
+    return TT_OK;
+}
+
 int tt_example_parse(const void* file, const int64_t* rec_offset, const int64_t* rec_len, int64_t nrec, const char* const* names, const int32_t* kind,
                      int nfeat, int64_t* str_off, int64_t* str_len, float* fvals, int nthreads) {
     TT_REQUIRE(file && rec_offset && rec_len && names && kind && nfeat >= 1 && nfeat <= 64, "tt_example_parse: bad argument");

@@ -62,6 +62,7 @@ SIGNATURES = {
     "tt_crc32c_masked": (ctypes.c_uint32, [c_void_p, c_size_t]),
     "tt_tfrecord_scan": (c_int64, [c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int64]),
     "tt_tfrecord_frame": (c_int, [c_void_p, ctypes.c_uint64, c_void_p]),
+    "tt_gather_cells": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int]),
     "tt_example_parse": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, ctypes.POINTER(ctypes.c_char_p), c_void_p, c_int, c_void_p,
                                  c_void_p, c_void_p, c_int]),
     "tt_gather_concat": (c_int, [ctypes.POINTER(TTFeature), c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

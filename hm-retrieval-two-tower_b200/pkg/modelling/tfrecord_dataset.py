@@ -49,13 +49,11 @@ def read_tfrecord_file(path: str, features: List[Feature], verify_crc: bool = Tr
         if kind[j] == 1:
             cols[f.name] = fv[j].copy()
             continue
-        width = int(s_len[j].max()) if n else 1
-        out = np.zeros((n, max(width, 1)), dtype=np.uint8)
-        # gather the variable-length byte strings into fixed-width cells (vectorised: one pass per byte position)
-        for b in range(width):
-            m = s_len[j] > b
-            out[m, b] = data[s_off[j][m] + b]
-        cols[f.name] = out.view(f"S{max(width, 1)}").reshape(n)
+        width = max(int(s_len[j].max()) if n else 1, 1)
+        out = np.empty((n, width), dtype=np.uint8)
+        # the variable-length byte strings into fixed-width, NUL-padded cells: one native pass (a numpy 'S<width>' column)
+        N.check(lib.tt_gather_cells(base, data.size, s_off[j].ctypes.data, s_len[j].ctypes.data, n, width, out.ctypes.data, nthreads), "tt_gather_cells")
+        cols[f.name] = out.view(f"S{width}").reshape(n)
     return cols
 
 

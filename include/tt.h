@@ -267,6 +267,9 @@ int tt_tfrecord_frame(const void* payload, uint64_t len, void* out /* len + 16 b
  * kind[f] 0 = bytes -> (str_off, str_len)[f * nrec + i] into `file`; 1 = float -> fvals[f * nrec + i]. */
 int tt_example_parse(const void* file, const int64_t* rec_offset, const int64_t* rec_len, int64_t nrec, const char* const* names,
                      const int32_t* kind, int nfeat, int64_t* str_off, int64_t* str_len, float* fvals, int nthreads);
+/* Copies the n byte strings file[str_off[i] .. str_off[i] + str_len[i]) into fixed-width cells out[i * width ..], NUL padded on the
+ * right (a numpy 'S<width>' column); strings longer than `width` or lying outside the nbytes-long file image are an error. */
+int tt_gather_cells(const void* file, size_t nbytes, const int64_t* str_off, const int64_t* str_len, int64_t n, int width, char* out, int nthreads);
 
 #ifdef __cplusplus
 }
