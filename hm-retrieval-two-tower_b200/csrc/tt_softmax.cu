@@ -20,6 +20,7 @@ int softmax_step_tc(const float* Q, int ldq, const float* C, int ldc, const floa
 int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, float* Z, int ldz, cudaStream_t st);
 size_t softmax_tc_workspace_bytes(int Bq, int Bc, int E);
 void debug_tc(void* trace, int max_splits);
+void debug_flash(void* trace, int mn_lbo, int mn_sbo);
 void debug_index_cap(int cap);
 void debug_index_stages(float* host_ms8);
 
@@ -47,6 +48,11 @@ extern "C" {
 
 int tt_debug_tc(void* trace, int max_splits) {
     debug_tc(trace, max_splits);
+    return TT_OK;
+}
+
+int tt_debug_flash(void* trace, int mn_lbo, int mn_sbo) {
+    debug_flash(trace, mn_lbo, mn_sbo);
     return TT_OK;
 }
 

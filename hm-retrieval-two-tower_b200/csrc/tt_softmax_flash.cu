@@ -1,0 +1,440 @@
+// tt_softmax_flash.cu -- host side of the two-pass in-batch softmax (tt_tc_flash.cuh) for E in {64, 128}.
+//
+// Replaces (reference file:line): two_tower_model.py:90-92 (Q.C^T), logq_correction.py:66-71, two_tower_model.py:119-122 +
+// runner.py:78-83 (eye labels, CE from logits, SUM) and the autodiff of those (two_tower_model.py:110-124).
+//
+//   step     : amax -> per-tensor power-of-two scales | fp16 operand copies + scaled column terms | pass 1 (forward + dQ) |
+//              combine 1 (lse, loss, dQ, lse column term) | pass 2 (dC) | combine 2          -- 6 launches + one 64-byte memset
+//   forward  : the same up to combine 1 without the dQ output
+//   backward : (lse given) pass 2 on one or both sides + combine 2
+// Precision contract: operands are rounded to fp16 AFTER scaling each tensor so that its largest magnitude lies in [2^14, 2^15):
+// 11 significant bits like TF32, no overflow for any finite input, entries below 2^-29 of the tensor's maximum lose relative
+// precision only (absolute logit error < 2^-40 of the largest product).  Products are exact, accumulation is fp32.
+#include <cuda_fp16.h>
+
+#include "tt_tc_flash.cuh"
+
+namespace tt {
+namespace tc {
+
+int make_tmap_2d_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);   // tt_softmax_tc.cu
+
+static int g_fl_lbo = 0, g_fl_sbo = 0;          // debug: MN-major descriptor fields
+static unsigned long long* g_fl_trace = nullptr;
+
+// ---- scales ---------------------------------------------------------------------------------------------------
+// scal[0] sq  [1] sc  [2],[3] kmul = log2e / (sq*sc)  [4] 1/sq  [5] 1/sc ; bits[8] amax(Q) [9] amax(C) [10] ticket   (64 floats)
+constexpr int kScalFloats = 64;
+
+__device__ __forceinline__ float pow2_scale_for(uint32_t amax_bits) {
+    const int e = (int)(amax_bits >> 23);                       // biased exponent of the largest magnitude
+    if (e == 0 || e == 255) return 1.f;                         // all zero / denormal, or inf / NaN (the result is inf / NaN either way)
+    int se = 268 - e;                                           // 2^(14 - floor(log2 amax)), biased
+    se = se > 167 ? 167 : se;                                   // cap at 2^40
+    return __uint_as_float((uint32_t)se << 23);
+}
+
+struct AmaxArgs { const float* X[2]; int ld[2]; int n[2]; int E; };
+__global__ void __launch_bounds__(256) fl_amax_kernel(const AmaxArgs a, float* __restrict__ scal) {
+    uint32_t* bits = reinterpret_cast<uint32_t*>(scal) + 8;
+    __shared__ uint32_t s_max[2][8];
+    __shared__ bool s_last;
+    uint32_t mx[2] = {0u, 0u};
+    const int e4 = a.E >> 2;
+    for (int t = 0; t < 2; ++t) {
+        const int64_t cnt = (int64_t)a.n[t] * e4;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
+            const int r = (int)(i / e4), c4 = (int)(i % e4);
+            const float4 v = *reinterpret_cast<const float4*>(a.X[t] + (int64_t)r * a.ld[t] + 4 * c4);
+            const uint32_t m0 = max(__float_as_uint(fabsf(v.x)), __float_as_uint(fabsf(v.y)));
+            const uint32_t m1 = max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)));
+            mx[t] = max(mx[t], max(m0, m1));
+        }
+    }
+    for (int t = 0; t < 2; ++t) {
+        for (int o = 16; o > 0; o >>= 1) mx[t] = max(mx[t], __shfl_xor_sync(0xffffffffu, mx[t], o));
+        if ((threadIdx.x & 31) == 0) s_max[t][threadIdx.x >> 5] = mx[t];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < 2; ++t) {
+            uint32_t m = 0;
+            for (int w = 0; w < 8; ++w) m = max(m, s_max[t][w]);
+            atomicMax(bits + t, m);                              // integer max: order-independent, deterministic
+        }
+        __threadfence();
+        s_last = (atomicAdd(bits + 2, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const float sq = pow2_scale_for(reinterpret_cast<volatile uint32_t*>(bits)[0]);
+        const float sc = pow2_scale_for(reinterpret_cast<volatile uint32_t*>(bits)[1]);
+        scal[0] = sq; scal[1] = sc;
+        const float inv = (1.f / sq) * (1.f / sc);               // exact: powers of two, |exponent| <= 80
+        scal[2] = kLog2e * inv; scal[3] = kLog2e * inv;
+        scal[4] = 1.f / sq; scal[5] = 1.f / sc;
+    }
+}
+
+// ---- operand copies and column terms ----------------------------------------------------------------------------------
+struct CvtItem {
+    const float* X; int ld, n; __half* Xh; int which;            // Xh[n][E] = fp16(X * scal[which])
+    const float* colv; float* c2; int n_col, n_pad; float cmul;  // c2[j] = colv[j] * cmul (0 when colv is null), zero padded to n_pad
+    int xblocks, cblocks;
+};
+struct CvtArgs { CvtItem s[3]; int n; int E; };
+__global__ void __launch_bounds__(256) fl_convert_kernel(const CvtArgs a, const float* __restrict__ scal) {
+    int b = blockIdx.x;
+    const int e8 = a.E >> 3;
+    for (int i = 0; i < a.n; ++i) {
+        const CvtItem& it = a.s[i];
+        if (b < it.xblocks) {
+            const int64_t idx = (int64_t)b * 256 + threadIdx.x;
+            if (idx < (int64_t)it.n * e8) {
+                const int r = (int)(idx / e8), c8 = (int)(idx % e8);
+                const float s = scal[it.which];
+                const float4 v0 = *reinterpret_cast<const float4*>(it.X + (int64_t)r * it.ld + 8 * c8);
+                const float4 v1 = *reinterpret_cast<const float4*>(it.X + (int64_t)r * it.ld + 8 * c8 + 4);
+                uint4 o;
+                o.x = pack_f16x2(v0.x * s, v0.y * s); o.y = pack_f16x2(v0.z * s, v0.w * s);
+                o.z = pack_f16x2(v1.x * s, v1.y * s); o.w = pack_f16x2(v1.z * s, v1.w * s);
+                *reinterpret_cast<uint4*>(it.Xh + (int64_t)r * a.E + 8 * c8) = o;
+            }
+            return;
+        }
+        b -= it.xblocks;
+        if (b < it.cblocks) {
+            const int j = b * 256 + threadIdx.x;
+            if (j < it.n_pad) it.c2[j] = (j < it.n_col && it.colv) ? it.colv[j] * it.cmul : 0.f;
+            return;
+        }
+        b -= it.cblocks;
+    }
+}
+static int cvt_item(CvtItem& it, const float* X, int ld, int n, int E, __half* Xh, int which, const float* colv, float* c2, int n_col, int n_pad, float cmul) {
+    it.X = X; it.ld = ld; it.n = n; it.Xh = Xh; it.which = which; it.colv = colv; it.c2 = c2; it.n_col = n_col; it.n_pad = n_pad; it.cmul = cmul;
+    it.xblocks = Xh ? (int)ceil_div((int64_t)n * (E / 8), 256) : 0;
+    it.cblocks = c2 ? (int)ceil_div(n_pad, 256) : 0;
+    return it.xblocks + it.cblocks;
+}
+
+// ---- plan ---------------------------------------------------------------------------------------------------------------
+static inline int fl_bn(int E) { return E <= 64 ? 128 : 64; }
+struct FlPlan { int grid, units, slots[2], unit0[2], m_pairs[2], n_tiles[2]; };
+static FlPlan fl_plan(int n_pass, const int* nR, const int* nT, int E) {
+    FlPlan pl{};
+    const int bn = fl_bn(E);
+    for (int i = 0; i < n_pass; ++i) {
+        pl.m_pairs[i] = (int)ceil_div(nR[i], 256);
+        pl.n_tiles[i] = (int)ceil_div(nT[i], bn);
+        pl.unit0[i] = pl.units;
+        pl.units += pl.m_pairs[i] * pl.n_tiles[i];
+    }
+    const int sms = sm_count();
+    pl.grid = pl.units < sms ? (pl.units > 0 ? pl.units : 1) : sms;
+    for (int i = 0; i < n_pass; ++i) {
+        int mx = 1;
+        for (int pr = 0; pr < pl.m_pairs[i]; ++pr) {
+            const int first = pl.unit0[i] + pr * pl.n_tiles[i];
+            const int s = sk_owner(first + pl.n_tiles[i] - 1, pl.units, pl.grid) - sk_owner(first, pl.units, pl.grid) + 1;
+            mx = s > mx ? s : mx;
+        }
+        pl.slots[i] = mx;
+    }
+    return pl;
+}
+
+template <int MODE, int E, int BN>
+static int launch_flash(const FlMaps& maps, const FlParams& p, int grid, cudaStream_t st, const char* name) {
+    using Cfg = FlCfg<MODE, E, BN>;
+    TT_CUDA_OK(cudaFuncSetAttribute(flash_kernel<MODE, E, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    flash_kernel<MODE, E, BN><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
+    TT_LAUNCH_OK(name);
+    return TT_OK;
+}
+template <int MODE>
+static int launch_flash_e(int E, const FlMaps& maps, const FlParams& p, int grid, cudaStream_t st) {
+    if (E == 64) return launch_flash<MODE, 64, 128>(maps, p, grid, st, MODE == kP1 ? "flash_kernel<p1,64>" : "flash_kernel<p2,64>");
+    return launch_flash<MODE, 128, 64>(maps, p, grid, st, MODE == kP1 ? "flash_kernel<p1,128>" : "flash_kernel<p2,128>");
+}
+
+// ---- combine 1: per-row merge of the pass-1 partials in slot order -> lse, row loss, loss, dQ, lse column term ---------------------
+// One thread per (row, 4 columns).  dQ_i = (sum_s G_s 2^(m_s - M)) / (L * scale_C) + (p_ii - 1) C[i + d]
+struct Comb1Args {
+    const float* pm; const float* pl; const float* pzd; const float* pg;
+    int nR, rows_pad, n_tiles, units, grid, unit0, E, d;
+    const float* C; int ldc;
+    const float* scal;
+    float* lse; float* rowloss; float* c2_lse; int c2_pad;
+    float* dQ; int lddq;
+    double* block_sums; unsigned int* counter; float* loss;
+};
+__global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
+    __shared__ double s_sum[256];
+    __shared__ bool s_last;
+    const int e4 = a.E >> 2;
+    const int rpb = 256 / e4;                                    // rows per block
+    const int r = blockIdx.x * rpb + threadIdx.x / e4, c4 = threadIdx.x % e4;
+    double mine = 0.0;
+    if (r < a.nR) {
+        const int first = a.unit0 + (r >> 8) * a.n_tiles;
+        const int slots = sk_owner(first + a.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1;
+        float M = -CUDART_INF_F;
+        for (int s = 0; s < slots; ++s) M = fmaxf(M, a.pm[(int64_t)s * a.rows_pad + r]);
+        float L = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < slots; ++s) {
+            const float w = exp2f(a.pm[(int64_t)s * a.rows_pad + r] - M);
+            L = fmaf(a.pl[(int64_t)s * a.rows_pad + r], w, L);
+            if (a.dQ) {
+                const float4 g = *reinterpret_cast<const float4*>(a.pg + ((int64_t)s * a.rows_pad + r) * a.E + 4 * c4);
+                acc.x = fmaf(g.x, w, acc.x); acc.y = fmaf(g.y, w, acc.y); acc.z = fmaf(g.z, w, acc.z); acc.w = fmaf(g.w, w, acc.w);
+            }
+        }
+        const float lse2 = M + log2f(L);
+        const float zd = a.pzd[r];
+        if (a.dQ) {
+            const float inv = a.scal[5] / L;                     // 1 / (L * scale_C)
+            const float pm1 = exp2f(zd - lse2) - 1.f;            // p_ii - 1
+            const float4 cv = *reinterpret_cast<const float4*>(a.C + (int64_t)(r + a.d) * a.ldc + 4 * c4);
+            float* dst = a.dQ + (int64_t)r * a.lddq + 4 * c4;
+            dst[0] = fmaf(acc.x, inv, pm1 * cv.x); dst[1] = fmaf(acc.y, inv, pm1 * cv.y);
+            dst[2] = fmaf(acc.z, inv, pm1 * cv.z); dst[3] = fmaf(acc.w, inv, pm1 * cv.w);
+        }
+        if (c4 == 0) {
+            const float v = lse2 * kLn2;
+            a.lse[r] = v;
+            const float rl = (lse2 - zd) * kLn2;
+            a.rowloss[r] = rl;
+            mine = (double)rl;
+            if (a.c2_lse) a.c2_lse[r] = lse2;
+        }
+    } else if (a.c2_lse && c4 == 0 && r < a.c2_pad) {
+        a.c2_lse[r] = 0.f;
+    }
+    s_sum[threadIdx.x] = mine;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        a.block_sums[blockIdx.x] = s_sum[0];
+        __threadfence();
+        s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += reinterpret_cast<volatile double*>(a.block_sums)[b];   // block order: deterministic
+        a.loss[0] = (float)t;
+        *a.counter = 0u;
+    }
+}
+
+// ---- combine 2: G[r][:] = 2^-kOff2 / scale_T * sum over the pair's CTA slots, in slot order -------------------------------------
+struct Comb2Side { const float* part; float* G; int ldg, nR, rows_pad, n_tiles, unit0, scal_idx; };
+struct Comb2Args { Comb2Side s[2]; int n, E, units, grid; const float* scal; };
+__global__ void __launch_bounds__(256) fl_combine2_kernel(const Comb2Args a) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int e4 = a.E >> 2;
+    for (int k = 0; k < a.n; ++k) {
+        const Comb2Side& sd = a.s[k];
+        const int64_t cnt = (int64_t)sd.nR * e4;
+        if (i < cnt) {
+            const int r = (int)(i / e4), c4 = (int)(i % e4);
+            const int first = sd.unit0 + (r >> 8) * sd.n_tiles;
+            const int slots = sk_owner(first + sd.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int z = 0; z < slots; ++z) {
+                const float4 v = *reinterpret_cast<const float4*>(sd.part + ((int64_t)z * sd.rows_pad + r) * a.E + 4 * c4);
+                acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+            }
+            const float f = a.scal[sd.scal_idx] * 6.103515625e-05f;   // 2^-14 / scale_T (exact)
+            float* dst = sd.G + (int64_t)r * sd.ldg + 4 * c4;
+            dst[0] = acc.x * f; dst[1] = acc.y * f; dst[2] = acc.z * f; dst[3] = acc.w * f;
+            return;
+        }
+        i -= cnt;
+    }
+}
+
+// ---- workspace ------------------------------------------------------------------------------------------------------------
+struct FlWs {
+    float* scal; __half* Qh; __half* Ch; float* c2_bias; float* c2_lse; double* block_sums; unsigned int* counter;
+    float* rowloss; float* p1_m; float* p1_l; float* p1_zd; float* p1_g; float* p2_g[2];
+    size_t bytes;
+};
+// one layout for every entry point (step / forward / backward with one or both sides)
+static FlWs fl_carve(void* ws, int Bq, int Bc, int E) {
+    FlWs w{};
+    Carver cv(ws ? ws : reinterpret_cast<void*>(256));           // ws == null: size query only
+    const int bn = fl_bn(E);
+    const int pad_c = (int)(ceil_div(Bc, bn) * bn) + 256, pad_q = (int)(ceil_div(Bq, bn) * bn) + 256;
+    w.rowloss = cv.take<float>((size_t)(Bq > Bc ? Bq : Bc));      // first: the SIMT path keeps its row losses at the workspace base too
+    w.scal = cv.take<float>(kScalFloats);
+    w.Qh = cv.take<__half>((size_t)Bq * E);
+    w.Ch = cv.take<__half>((size_t)Bc * E);
+    w.c2_bias = cv.take<float>((size_t)pad_c);
+    w.c2_lse = cv.take<float>((size_t)pad_q);
+    w.block_sums = cv.take<double>((size_t)ceil_div((int64_t)Bq * (E / 4), 256) + 64);
+    w.counter = reinterpret_cast<unsigned int*>(w.scal) + 11;     // zeroed with the amax words by fl_prepare's memset
+    // pass 1: R = Q, T = C
+    int nR1[1] = {Bq}, nT1[1] = {Bc};
+    FlPlan p1 = fl_plan(1, nR1, nT1, E);
+    const size_t rp1 = (size_t)p1.m_pairs[0] * 256;
+    w.p1_m = cv.take<float>(p1.slots[0] * rp1);
+    w.p1_l = cv.take<float>(p1.slots[0] * rp1);
+    w.p1_zd = cv.take<float>(rp1);
+    w.p1_g = cv.take<float>(p1.slots[0] * rp1 * E);
+    // pass 2: up to two sides in one launch (dQ side: R = Q; dC side: R = C); sized for the larger of {both, either alone}
+    int nRb[2] = {Bq, Bc}, nTb[2] = {Bc, Bq};
+    FlPlan pb = fl_plan(2, nRb, nTb, E);
+    int nRq[1] = {Bq}, nTq[1] = {Bc}, nRc[1] = {Bc}, nTc[1] = {Bq};
+    FlPlan pq = fl_plan(1, nRq, nTq, E), pc = fl_plan(1, nRc, nTc, E);
+    const int sq = pb.slots[0] > pq.slots[0] ? pb.slots[0] : pq.slots[0], sc = pb.slots[1] > pc.slots[0] ? pb.slots[1] : pc.slots[0];
+    w.p2_g[0] = cv.take<float>((size_t)sq * pb.m_pairs[0] * 256 * E);
+    w.p2_g[1] = cv.take<float>((size_t)sc * pb.m_pairs[1] * 256 * E);
+    w.bytes = align_up(cv.off, 256) + 256;
+    return w;
+}
+size_t softmax_flash_workspace(int Bq, int Bc, int E) { return fl_carve(nullptr, Bq, Bc, E).bytes; }
+
+// amax -> scales, fp16 copies, column terms
+static int fl_prepare(const FlWs& w, const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E,
+                      cudaStream_t st) {
+    const int bn = fl_bn(E);
+    TT_CUDA_OK(cudaMemsetAsync(w.scal + 8, 0, 16, st));          // amax bits, ticket
+    AmaxArgs aa{};
+    aa.X[0] = Q; aa.ld[0] = ldq; aa.n[0] = Bq; aa.X[1] = C; aa.ld[1] = ldc; aa.n[1] = Bc; aa.E = E;
+    int64_t work = ((int64_t)Bq + Bc) * (E / 4);
+    int blocks = (int)ceil_div(work, 256 * 4);
+    blocks = blocks > 2 * sm_count() ? 2 * sm_count() : (blocks < 1 ? 1 : blocks);
+    fl_amax_kernel<<<(unsigned)blocks, 256, 0, st>>>(aa, w.scal);
+    TT_LAUNCH_OK("fl_amax_kernel");
+    CvtArgs ca{};
+    ca.E = E;
+    int cb = 0;
+    cb += cvt_item(ca.s[ca.n++], Q, ldq, Bq, E, w.Qh, 0, lse, lse ? w.c2_lse : nullptr, Bq, (int)(ceil_div(Bq, bn) * bn), kLog2e);
+    cb += cvt_item(ca.s[ca.n++], C, ldc, Bc, E, w.Ch, 1, bias, w.c2_bias, Bc, (int)(ceil_div(Bc, bn) * bn), kLog2e);
+    fl_convert_kernel<<<(unsigned)cb, 256, 0, st>>>(ca, w.scal);
+    TT_LAUNCH_OK("fl_convert_kernel");
+    return TT_OK;
+}
+
+static int fl_pass1(const FlWs& w, const float* C, int ldc, int Bq, int Bc, int E, int off, float* lse, float* loss, float* dQ, int lddq,
+                    bool want_c2_lse, cudaStream_t st) {
+    const int bn = fl_bn(E);
+    int nR[1] = {Bq}, nT[1] = {Bc};
+    FlPlan pl = fl_plan(1, nR, nT, E);
+    FlMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc = make_tmap_2d_f16(&maps.r[0], w.Qh, Bq, E, E, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d_f16(&maps.t[0], w.Ch, Bc, E, E, bn);
+    if (rc) return rc;
+    FlParams p{};
+    p.n_pass = 1; p.units = pl.units; p.kmul = w.scal + 2; p.mn_lbo = g_fl_lbo; p.mn_sbo = g_fl_sbo; p.trace = g_fl_trace;
+    FlPass& ps = p.pass[0];
+    ps.nR = Bq; ps.nT = Bc; ps.m_pairs = pl.m_pairs[0]; ps.n_tiles = pl.n_tiles[0]; ps.d = off; ps.unit0 = 0; ps.rowv = nullptr;
+    ps.colv2 = w.c2_bias; ps.out_g = w.p1_g; ps.out_m = w.p1_m; ps.out_l = w.p1_l; ps.out_zd = w.p1_zd;
+    rc = launch_flash_e<kP1>(E, maps, p, pl.grid, st);
+    if (rc) return rc;
+    Comb1Args ca{};
+    ca.pm = w.p1_m; ca.pl = w.p1_l; ca.pzd = w.p1_zd; ca.pg = w.p1_g;
+    ca.nR = Bq; ca.rows_pad = pl.m_pairs[0] * 256; ca.n_tiles = pl.n_tiles[0]; ca.units = pl.units; ca.grid = pl.grid; ca.unit0 = 0; ca.E = E; ca.d = off;
+    ca.C = C; ca.ldc = ldc; ca.scal = w.scal; ca.lse = lse; ca.rowloss = w.rowloss;
+    ca.c2_lse = want_c2_lse ? w.c2_lse : nullptr; ca.c2_pad = (int)(ceil_div(Bq, bn) * bn);
+    ca.dQ = dQ; ca.lddq = lddq; ca.block_sums = w.block_sums; ca.counter = w.counter; ca.loss = loss;
+    const int rpb = 256 / (E / 4);
+    const int rows_c = ca.c2_pad > Bq ? ca.c2_pad : Bq;
+    fl_combine1_kernel<<<(unsigned)ceil_div(rows_c, rpb), 256, 0, st>>>(ca);
+    TT_LAUNCH_OK("fl_combine1_kernel");
+    return TT_OK;
+}
+
+struct FlSide { int r_is_q; float* G; int ldg; };   // r_is_q: resident operand Q (gradient dQ) or C (gradient dC)
+static int fl_pass2(const FlWs& w, const float* bias, const float* lse, int Bq, int Bc, int E, int off, const FlSide* sides, int n, cudaStream_t st) {
+    const int bn = fl_bn(E);
+    int nR[2], nT[2];
+    for (int i = 0; i < n; ++i) { nR[i] = sides[i].r_is_q ? Bq : Bc; nT[i] = sides[i].r_is_q ? Bc : Bq; }
+    FlPlan pl = fl_plan(n, nR, nT, E);
+    if (pl.units == 0) return TT_OK;
+    FlMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    FlParams p{};
+    p.n_pass = n; p.units = pl.units; p.kmul = w.scal + 2; p.mn_lbo = g_fl_lbo; p.mn_sbo = g_fl_sbo; p.trace = g_fl_trace;
+    Comb2Args ca{};
+    ca.n = n; ca.E = E; ca.units = pl.units; ca.grid = pl.grid; ca.scal = w.scal;
+    int64_t items = 0;
+    for (int i = 0; i < n; ++i) {
+        const bool rq = sides[i].r_is_q != 0;
+        int rc = make_tmap_2d_f16(&maps.r[i], rq ? w.Qh : w.Ch, nR[i], E, E, 128);
+        if (rc) return rc;
+        rc = make_tmap_2d_f16(&maps.t[i], rq ? w.Ch : w.Qh, nT[i], E, E, bn);
+        if (rc) return rc;
+        FlPass& ps = p.pass[i];
+        ps.nR = nR[i]; ps.nT = nT[i]; ps.m_pairs = pl.m_pairs[i]; ps.n_tiles = pl.n_tiles[i]; ps.d = rq ? off : -off; ps.unit0 = pl.unit0[i];
+        ps.rowv = rq ? lse : bias; ps.colv2 = rq ? w.c2_bias : w.c2_lse;
+        ps.out_g = w.p2_g[rq ? 0 : 1]; ps.out_m = nullptr; ps.out_l = nullptr; ps.out_zd = nullptr;
+        Comb2Side& cs = ca.s[i];
+        cs.part = ps.out_g; cs.G = sides[i].G; cs.ldg = sides[i].ldg; cs.nR = nR[i]; cs.rows_pad = pl.m_pairs[i] * 256; cs.n_tiles = pl.n_tiles[i];
+        cs.unit0 = pl.unit0[i]; cs.scal_idx = rq ? 5 : 4;   // the streamed operand's scale: C for the dQ side, Q for the dC side
+        items += (int64_t)nR[i] * (E / 4);
+    }
+    int rc = launch_flash_e<kP2>(E, maps, p, pl.grid, st);
+    if (rc) return rc;
+    fl_combine2_kernel<<<(unsigned)ceil_div(items, 256), 256, 0, st>>>(ca);
+    TT_LAUNCH_OK("fl_combine2_kernel");
+    return TT_OK;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+bool softmax_flash_supported(int E) { return E == 64 || E == 128; }
+size_t softmax_flash_workspace_bytes(int Bq, int Bc, int E) { return tc::softmax_flash_workspace(Bq, Bc, E); }
+
+int softmax_step_flash(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
+                       float* dQ, int lddq, float* dC, int lddc, float* ws, cudaStream_t st) {
+    FlWs w = fl_carve(ws, Bq, Bc, E);
+    int rc = fl_prepare(w, Q, ldq, C, ldc, bias, nullptr, Bq, Bc, E, st);
+    if (rc) return rc;
+    rc = fl_pass1(w, C, ldc, Bq, Bc, E, off, lse, loss, dQ, lddq, true, st);
+    if (rc) return rc;
+    FlSide side{0, dC, lddc};
+    return fl_pass2(w, bias, lse, Bq, Bc, E, off, &side, 1, st);
+}
+
+int softmax_fwd_flash(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
+                      float* ws, cudaStream_t st) {
+    FlWs w = fl_carve(ws, Bq, Bc, E);
+    int rc = fl_prepare(w, Q, ldq, C, ldc, bias, nullptr, Bq, Bc, E, st);
+    if (rc) return rc;
+    return fl_pass1(w, C, ldc, Bq, Bc, E, off, lse, loss, nullptr, 0, false, st);
+}
+
+// which = 0 dQ only, 1 dC only, 2 both (G0 = dQ, G1 = dC)
+int softmax_bwd_flash(const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E, int off, int which,
+                      float* G0, int ldg0, float* G1, int ldg1, float* ws, cudaStream_t st) {
+    FlWs w = fl_carve(ws, Bq, Bc, E);
+    int rc = fl_prepare(w, Q, ldq, C, ldc, bias, lse, Bq, Bc, E, st);
+    if (rc) return rc;
+    FlSide sides[2];
+    int n = 0;
+    if (which == 0 || which == 2) sides[n++] = FlSide{1, G0, ldg0};
+    if (which == 1) sides[n++] = FlSide{0, G0, ldg0};
+    if (which == 2) sides[n++] = FlSide{0, G1, ldg1};
+    return fl_pass2(w, bias, lse, Bq, Bc, E, off, sides, n, st);
+}
+
+void debug_flash(void* trace, int mn_lbo, int mn_sbo) {
+    tc::g_fl_trace = reinterpret_cast<unsigned long long*>(trace);
+    tc::g_fl_lbo = mn_lbo;
+    tc::g_fl_sbo = mn_sbo;
+}
+
+}  // namespace tt

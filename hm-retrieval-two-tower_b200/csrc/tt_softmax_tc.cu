@@ -19,6 +19,15 @@
 namespace tt {
 
 int sum_rows_launch(const float* v, int n, float* out, cudaStream_t st);  // tt_softmax_simt.cu
+// tt_softmax_flash.cu: the two-pass kernels that serve E in {64, 128}; the stream-K kernels below keep E = 32
+bool softmax_flash_supported(int E);
+size_t softmax_flash_workspace_bytes(int Bq, int Bc, int E);
+int softmax_step_flash(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
+                       float* dQ, int lddq, float* dC, int lddc, float* ws, cudaStream_t st);
+int softmax_fwd_flash(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
+                      float* ws, cudaStream_t st);
+int softmax_bwd_flash(const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E, int off, int which,
+                      float* G0, int ldg0, float* G1, int ldg1, float* ws, cudaStream_t st);
 
 namespace tc {
 
@@ -453,6 +462,7 @@ static int softmax_fwd_sk(const float* Q, int ldq, const float* C, int ldc, cons
 
 int softmax_fwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
                    float* ws, cudaStream_t st) {
+    if (softmax_flash_supported(E)) return softmax_fwd_flash(Q, ldq, C, ldc, bias, Bq, Bc, E, off, lse, loss, ws, st);
     return softmax_fwd_sk(Q, ldq, C, ldc, bias, Bq, Bc, E, off, lse, loss, ws, st, nullptr);
 }
 
@@ -556,6 +566,7 @@ size_t tc::softmax_step_floats(int Bq, int Bc, int E) {
 
 int softmax_step_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
                     float* dQ, int lddq, float* dC, int lddc, float* ws, cudaStream_t st) {
+    if (softmax_flash_supported(E)) return softmax_step_flash(Q, ldq, C, ldc, bias, Bq, Bc, E, off, lse, loss, dQ, lddq, dC, lddc, ws, st);
     const size_t ws_floats_fwd = sk_fwd_bytes(Bq, Bc, E) / sizeof(float), ws_floats_bwd = sk_bwd_bytes(Bq, Bc, E) / sizeof(float);
     const bool h16 = E >= 64;
     const int bn = sk_bwd_bn(E);
@@ -593,6 +604,7 @@ int softmax_step_tc(const float* Q, int ldq, const float* C, int ldc, const floa
 // (Q, C) backward: which = 0 dQ only, 1 dC only, 2 both (G0 = dQ, G1 = dC)
 int softmax_bwd_tc(const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E, int off, int which,
                    float* G0, int ldg0, float* G1, int ldg1, float* ws, cudaStream_t st) {
+    if (softmax_flash_supported(E)) return softmax_bwd_flash(Q, ldq, C, ldc, bias, lse, Bq, Bc, E, off, which, G0, ldg0, G1, ldg1, ws, st);
     SkSide sides[2];
     int n = 0;
     if (which == 0 || which == 2) sides[n++] = SkSide{Q, ldq, C, ldc, lse, bias, Bq, Bc, off, G0, ldg0};
@@ -629,7 +641,9 @@ int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bia
     }
 }
 
-size_t softmax_tc_workspace_bytes(int Bq, int Bc, int E) { return tc::softmax_tc_workspace(Bq, Bc, E); }
+size_t softmax_tc_workspace_bytes(int Bq, int Bc, int E) {
+    return softmax_flash_supported(E) ? softmax_flash_workspace_bytes(Bq, Bc, E) : tc::softmax_tc_workspace(Bq, Bc, E);
+}
 
 void debug_tc(void* trace, int max_splits) {
     tc::g_trace = reinterpret_cast<unsigned long long*>(trace);

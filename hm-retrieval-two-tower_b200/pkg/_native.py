@@ -42,6 +42,7 @@ SIGNATURES = {
     "tt_launch_count": (c_int64, []),
     "tt_tc_available": (c_int, [c_int, c_int]),
     "tt_debug_tc": (c_int, [c_void_p, c_int]),
+    "tt_debug_flash": (c_int, [c_void_p, c_int, c_int]),
     "tt_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), c_void_p]),
     "tt_peer_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "tt_peer_close": (c_int, [c_void_p]),

@@ -53,6 +53,9 @@ int tt_tc_available(int kind, int E);
 /* Debug/profiling knobs of the tensor-core kernels: `trace` (device, u64[ctas][16], or NULL) receives
  * globaltimer stamps of subsequent launches; `max_splits` caps the column splits (0 = default). */
 int tt_debug_tc(void* trace, int max_splits);
+/* Debug knobs of the two-pass softmax kernels (E = 64 / 128): `trace` (device, u64[ctas][64][8] or NULL) receives globaltimer
+ * stamps; mn_lbo / mn_sbo override the byte offsets in the MN-major shared-memory descriptor of the second product (0 = default). */
+int tt_debug_flash(void* trace, int mn_lbo, int mn_sbo);
 /* Test knob: cap the candidate lists of the tensor-core index filter (0 = default 4K+512) to force the
  * on-device exact fallback. */
 int tt_debug_index_cap(int cap);
