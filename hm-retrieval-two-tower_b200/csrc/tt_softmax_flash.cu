@@ -160,13 +160,15 @@ static int launch_flash_e(int E, const FlMaps& maps, const FlParams& p, int grid
 }
 
 // ---- combine 1: per-row merge of the pass-1 partials in slot order -> lse, row loss, loss, dQ, lse column term ---------------------
-// One thread per (row, 4 columns).  dQ_i = (sum_s G_s 2^(m_s - M)) / (L * scale_C) + (p_ii - 1) C[i + d]
+// One thread per (row, 4 columns).  The positive was left out of the sums: with L_off = sum_s l_s 2^(m_s - M), pd = 2^(zd - M),
+//   L = L_off + pd,  lse = M + log2 L,  p_ii - 1 = -L_off / L  (no cancellation when the softmax is sharp),
+//   row loss = ln(1 + L_off / pd),      dQ_i = (sum_s G_s 2^(m_s - M)) / (L * scale_C) + (p_ii - 1) C[i + d]
 struct Comb1Args {
     const float* pm; const float* pl; const float* pzd; const float* pg;
     int nR, rows_pad, n_tiles, units, grid, unit0, E, d;
     const float* C; int ldc;
     const float* scal;
-    float* lse; float* rowloss; float* c2_lse; int c2_pad;
+    float* lse; float* rowloss; float* c2_lse; int c2_pad; float* pm1;
     float* dQ; int lddq;
     double* block_sums; unsigned int* counter; float* loss;
 };
@@ -180,35 +182,37 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
     if (r < a.nR) {
         const int first = a.unit0 + (r >> 8) * a.n_tiles;
         const int slots = sk_owner(first + a.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1;
-        float M = -CUDART_INF_F;
+        const float zd = a.pzd[r];
+        float M = zd;                                            // the positive takes part in the maximum
         for (int s = 0; s < slots; ++s) M = fmaxf(M, a.pm[(int64_t)s * a.rows_pad + r]);
-        float L = 0.f;
+        float Loff = 0.f;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = 0; s < slots; ++s) {
             const float w = exp2f(a.pm[(int64_t)s * a.rows_pad + r] - M);
-            L = fmaf(a.pl[(int64_t)s * a.rows_pad + r], w, L);
+            Loff = fmaf(a.pl[(int64_t)s * a.rows_pad + r], w, Loff);
             if (a.dQ) {
                 const float4 g = *reinterpret_cast<const float4*>(a.pg + ((int64_t)s * a.rows_pad + r) * a.E + 4 * c4);
                 acc.x = fmaf(g.x, w, acc.x); acc.y = fmaf(g.y, w, acc.y); acc.z = fmaf(g.z, w, acc.z); acc.w = fmaf(g.w, w, acc.w);
             }
         }
+        const float pd = exp2f(zd - M);
+        const float L = Loff + pd;
         const float lse2 = M + log2f(L);
-        const float zd = a.pzd[r];
+        const float pm1 = -Loff / L;                             // p_ii - 1
         if (a.dQ) {
             const float inv = a.scal[5] / L;                     // 1 / (L * scale_C)
-            const float pm1 = exp2f(zd - lse2) - 1.f;            // p_ii - 1
             const float4 cv = *reinterpret_cast<const float4*>(a.C + (int64_t)(r + a.d) * a.ldc + 4 * c4);
             float* dst = a.dQ + (int64_t)r * a.lddq + 4 * c4;
             dst[0] = fmaf(acc.x, inv, pm1 * cv.x); dst[1] = fmaf(acc.y, inv, pm1 * cv.y);
             dst[2] = fmaf(acc.z, inv, pm1 * cv.z); dst[3] = fmaf(acc.w, inv, pm1 * cv.w);
         }
         if (c4 == 0) {
-            const float v = lse2 * kLn2;
-            a.lse[r] = v;
-            const float rl = (lse2 - zd) * kLn2;
+            a.lse[r] = lse2 * kLn2;
+            const float rl = (pd >= Loff) ? log1pf(Loff / pd) : (lse2 - zd) * kLn2;
             a.rowloss[r] = rl;
             mine = (double)rl;
             if (a.c2_lse) a.c2_lse[r] = lse2;
+            if (a.pm1) a.pm1[r] = pm1;
         }
     } else if (a.c2_lse && c4 == 0 && r < a.c2_pad) {
         a.c2_lse[r] = 0.f;
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(256) fl_combine2_kernel(const Comb2Args a) {
 
 // ---- workspace ------------------------------------------------------------------------------------------------------------
 struct FlWs {
-    float* scal; __half* Qh; __half* Ch; float* c2_bias; float* c2_lse; double* block_sums; unsigned int* counter;
+    float* scal; __half* Qh; __half* Ch; float* c2_bias; float* c2_lse; float* pm1; double* block_sums; unsigned int* counter;
     float* rowloss; float* p1_m; float* p1_l; float* p1_zd; float* p1_g; float* p2_g[2];
     size_t bytes;
 };
@@ -279,6 +283,7 @@ static FlWs fl_carve(void* ws, int Bq, int Bc, int E) {
     w.Ch = cv.take<__half>((size_t)Bc * E);
     w.c2_bias = cv.take<float>((size_t)pad_c);
     w.c2_lse = cv.take<float>((size_t)pad_q);
+    w.pm1 = cv.take<float>((size_t)pad_q);
     w.block_sums = cv.take<double>((size_t)ceil_div((int64_t)Bq * (E / 4), 256) + 64);
     w.counter = reinterpret_cast<unsigned int*>(w.scal) + 11;     // zeroed with the amax words by fl_prepare's memset
     // pass 1: R = Q, T = C
@@ -346,7 +351,7 @@ static int fl_pass1(const FlWs& w, const float* C, int ldc, int Bq, int Bc, int 
     ca.pm = w.p1_m; ca.pl = w.p1_l; ca.pzd = w.p1_zd; ca.pg = w.p1_g;
     ca.nR = Bq; ca.rows_pad = pl.m_pairs[0] * 256; ca.n_tiles = pl.n_tiles[0]; ca.units = pl.units; ca.grid = pl.grid; ca.unit0 = 0; ca.E = E; ca.d = off;
     ca.C = C; ca.ldc = ldc; ca.scal = w.scal; ca.lse = lse; ca.rowloss = w.rowloss;
-    ca.c2_lse = want_c2_lse ? w.c2_lse : nullptr; ca.c2_pad = (int)(ceil_div(Bq, bn) * bn);
+    ca.c2_lse = want_c2_lse ? w.c2_lse : nullptr; ca.c2_pad = (int)(ceil_div(Bq, bn) * bn); ca.pm1 = want_c2_lse ? w.pm1 : nullptr;
     ca.dQ = dQ; ca.lddq = lddq; ca.block_sums = w.block_sums; ca.counter = w.counter; ca.loss = loss;
     const int rpb = 256 / (E / 4);
     const int rows_c = ca.c2_pad > Bq ? ca.c2_pad : Bq;
@@ -356,7 +361,8 @@ static int fl_pass1(const FlWs& w, const float* C, int ldc, int Bq, int Bc, int 
 }
 
 struct FlSide { int r_is_q; float* G; int ldg; };   // r_is_q: resident operand Q (gradient dQ) or C (gradient dC)
-static int fl_pass2(const FlWs& w, const float* bias, const float* lse, int Bq, int Bc, int E, int off, const FlSide* sides, int n, cudaStream_t st) {
+static int fl_pass2(const FlWs& w, const float* bias, const float* lse, int Bq, int Bc, int E, int off, const FlSide* sides, int n, bool have_pm1,
+                    cudaStream_t st) {
     const int bn = fl_bn(E);
     int nR[2], nT[2];
     for (int i = 0; i < n; ++i) { nR[i] = sides[i].r_is_q ? Bq : Bc; nT[i] = sides[i].r_is_q ? Bc : Bq; }
@@ -379,6 +385,7 @@ static int fl_pass2(const FlWs& w, const float* bias, const float* lse, int Bq, 
         ps.nR = nR[i]; ps.nT = nT[i]; ps.m_pairs = pl.m_pairs[i]; ps.n_tiles = pl.n_tiles[i]; ps.d = rq ? off : -off; ps.unit0 = pl.unit0[i];
         ps.rowv = rq ? lse : bias; ps.colv2 = rq ? w.c2_bias : w.c2_lse;
         ps.out_g = w.p2_g[rq ? 0 : 1]; ps.out_m = nullptr; ps.out_l = nullptr; ps.out_zd = nullptr;
+        ps.diag_pm1 = (!rq && have_pm1) ? w.pm1 : nullptr;   // dC side: column n is query n, whose p_nn - 1 the pass-1 combine left in pm1
         Comb2Side& cs = ca.s[i];
         cs.part = ps.out_g; cs.G = sides[i].G; cs.ldg = sides[i].ldg; cs.nR = nR[i]; cs.rows_pad = pl.m_pairs[i] * 256; cs.n_tiles = pl.n_tiles[i];
         cs.unit0 = pl.unit0[i]; cs.scal_idx = rq ? 5 : 4;   // the streamed operand's scale: C for the dQ side, Q for the dC side
@@ -406,7 +413,7 @@ int softmax_step_flash(const float* Q, int ldq, const float* C, int ldc, const f
     rc = fl_pass1(w, C, ldc, Bq, Bc, E, off, lse, loss, dQ, lddq, true, st);
     if (rc) return rc;
     FlSide side{0, dC, lddc};
-    return fl_pass2(w, bias, lse, Bq, Bc, E, off, &side, 1, st);
+    return fl_pass2(w, bias, lse, Bq, Bc, E, off, &side, 1, true, st);
 }
 
 int softmax_fwd_flash(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
@@ -428,7 +435,7 @@ int softmax_bwd_flash(const float* Q, int ldq, const float* C, int ldc, const fl
     if (which == 0 || which == 2) sides[n++] = FlSide{1, G0, ldg0};
     if (which == 1) sides[n++] = FlSide{0, G0, ldg0};
     if (which == 2) sides[n++] = FlSide{0, G1, ldg1};
-    return fl_pass2(w, bias, lse, Bq, Bc, E, off, sides, n, st);
+    return fl_pass2(w, bias, lse, Bq, Bc, E, off, sides, n, false, st);
 }
 
 void debug_flash(void* trace, int mn_lbo, int mn_sbo) {

@@ -40,6 +40,7 @@ struct FlPass {
     float* out_m;           // kP1: reference exponent (log2 units) [slot][m_pairs*256]
     float* out_l;           // kP1: sum of P~                      [slot][m_pairs*256]
     float* out_zd;          // kP1: diagonal logit, log2 units     [m_pairs*256]
+    const float* diag_pm1;  // kP2: (p - 1) of the positive in T-row (column) n, computed without cancellation by the pass-1 combine; may be null
 };
 struct FlParams {
     FlPass pass[2];
@@ -93,11 +94,14 @@ struct FlCfg {
     static_assert(kStages >= 3, "shared memory budget");
 };
 
+// S and P of a panel are handed over in two HALVES of BN/2 columns, each with its own full/empty pair: the first product of the
+// next tile refills the first half of S while the epilogue is still working on the second, which is what a second S buffer
+// would buy (tensor memory has no room for one: 2 x (S + P + G) = 512 columns)
 struct FlBars {
     uint64_t r_full, r_empty;
     uint64_t t_full[8], t_empty[8];
-    uint64_t s_full[2], s_empty[2];
-    uint64_t p_full[2], p_empty[2];
+    uint64_t s_full[2][2], s_empty[2][2];   // [panel of the pair][half]
+    uint64_t p_full[2][2], p_empty[2][2];
     uint64_t g_full[2], g_empty[2];
     uint32_t tmem_base;
 };
@@ -193,10 +197,11 @@ __device__ __forceinline__ void p1_exp_checked(const f32x2 (&zn)[16], float a, i
         float z0, z1;
         upk2(zn[i], z0, z1);
         float p0 = ex2_approx(a - z0), p1 = ex2_approx(a - z1);     // +inf -> 0
-        lsum = add2(lsum, pk2(p0, p1));
-        // the positive is left out of the product: the combine kernel adds (p_ii - 1) c_ii in fp32
+        // the positive is left out of the sum and of the product: the combine kernel forms p_ii - 1 = -sum_offdiag / sum without
+        // cancellation and adds (p_ii - 1) c_ii in fp32
         if (dloc == 2 * i) { p0 = 0.f; zd = -z0; }
         if (dloc == 2 * i + 1) { p1 = 0.f; zd = -z1; }
+        lsum = add2(lsum, pk2(p0, p1));
         w[i] = pack_f16x2(p0, p1);
     }
 }
@@ -215,7 +220,7 @@ __device__ __forceinline__ void p2_chunk_fast(const uint32_t (&r)[32], uint32_t 
     }
 }
 __device__ __forceinline__ void p2_chunk_checked(const uint32_t (&r)[32], uint32_t c2s, float kmul, float rowc, int nb, int nT, bool row_ok,
-                                                 int dcol_abs, uint32_t (&w)[16]) {
+                                                 int dcol_abs, const float* __restrict__ diag_pm1, uint32_t (&w)[16]) {
 #pragma unroll
     for (int g4 = 0; g4 < 8; ++g4) {
         const float4 cc = lds128(c2s + g4 * 16);
@@ -226,7 +231,7 @@ __device__ __forceinline__ void p2_chunk_checked(const uint32_t (&r)[32], uint32
             const int i = g4 * 4 + t;
             float v = ex2_approx(fmaf(__uint_as_float(r[i]), kmul, rowc - cv[t]));
             if (nb + i >= nT || !row_ok) v = 0.f;
-            else if (nb + i == dcol_abs) v -= 16384.f;   // 2^kOff2
+            else if (nb + i == dcol_abs) v = diag_pm1 ? __ldg(diag_pm1 + nb + i) * 16384.f : v - 16384.f;   // (p - 1) 2^kOff2
             pv[t] = v;
         }
         w[2 * g4] = pack_f16x2(pv[0], pv[1]);
@@ -235,7 +240,8 @@ __device__ __forceinline__ void p2_chunk_checked(const uint32_t (&r)[32], uint32
 }
 
 // pass 1, rare path: raise the reference exponent of the rows whose chunk exceeds it by more than 2^kTau; rescale their running
-// sums, their G rows (valid once a second product of this segment has completed) and the P chunks already written for this tile
+// sums, their G rows (valid once a second product of this segment has been issued; the caller has waited for all of them) and
+// the P chunks of the current half that are already written (earlier halves are already inside G)
 struct P1State { float a; f32x2 l; };   // returned by value: a by-reference state would live in local memory in the hot loop
 template <int E>
 __device__ __noinline__ P1State p1_raise(bool need, float cmin, bool g_valid, int chunks_done, uint32_t tG, uint32_t tP, float a_run, f32x2 lsum) {
@@ -279,6 +285,8 @@ template <int MODE, int E, int BN>
 __global__ void __launch_bounds__(FlCfg<MODE, E, BN>::kThreads, 1)
 flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlParams p) {
     using Cfg = FlCfg<MODE, E, BN>;
+    constexpr int kHC = Cfg::kChunks / 2;      // 32-column chunks per half
+    constexpr int kHN = BN / 2;                // columns per half
     const int u_begin = sk_begin(blockIdx.x, p.units, gridDim.x), u_end = sk_begin(blockIdx.x + 1, p.units, gridDim.x);
     const int my_units = u_end - u_begin;
     if (my_units <= 0) return;
@@ -300,8 +308,10 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
         mbar_init(&bars->r_empty, 1);
         for (int i = 0; i < 8; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 4);
-            mbar_init(&bars->p_full[i], 4); mbar_init(&bars->p_empty[i], 1);
+            for (int h = 0; h < 2; ++h) {
+                mbar_init(&bars->s_full[i][h], 1); mbar_init(&bars->s_empty[i][h], 4);
+                mbar_init(&bars->p_full[i][h], 4); mbar_init(&bars->p_empty[i][h], 1);
+            }
             mbar_init(&bars->g_full[i], 1); mbar_init(&bars->g_empty[i], 4);
         }
         fence_barrier_init();
@@ -339,8 +349,8 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             }
         }
     } else if (warp == kMma1Warp) {
-        // ===================== first product: S_g = R_g . T^T for both panels of the pair =====================
-        constexpr uint32_t idesc1 = make_idesc_f16(128, BN);
+        // ===================== first product, per panel and half: S_g[:, half] = R_g . T[half]^T =====================
+        constexpr uint32_t idesc1 = make_idesc_f16(128, kHN);
         const uint32_t sR_a = smem_u32(sR), sT_a = smem_u32(sT);
         FlCursor c;
         c.init(p, u_begin);
@@ -356,25 +366,30 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             mbar_wait(&bars->t_full[stage], (it / Cfg::kStages) & 1);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-                mbar_wait(&bars->s_empty[g], (it & 1) ^ 1);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint64_t ad0 = make_smem_desc(sR_a + g * Cfg::kPanelBytes, 16, 1024), bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes, 16, 1024);
 #pragma unroll
-                    for (int kk = 0; kk < Cfg::kMma1; ++kk) {
-                        const uint64_t ad = ad0 + (uint64_t)(((kk >> 2) * 128 * 128 + (kk & 3) * 32) >> 4);
-                        const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * BN * 128 + (kk & 3) * 32) >> 4);
-                        mma_f16(tmem + g * 256 + Cfg::kSCol, ad, bd, idesc1, kk > 0 ? 1u : 0u);
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(&bars->s_empty[g][h], (it & 1) ^ 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t ad0 = make_smem_desc(sR_a + g * Cfg::kPanelBytes, 16, 1024);
+                        const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes + h * kHN * 128, 16, 1024);   // rows [h*BN/2, +BN/2) of every slab
+#pragma unroll
+                        for (int kk = 0; kk < Cfg::kMma1; ++kk) {
+                            const uint64_t ad = ad0 + (uint64_t)(((kk >> 2) * 128 * 128 + (kk & 3) * 32) >> 4);
+                            const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * BN * 128 + (kk & 3) * 32) >> 4);
+                            mma_f16(tmem + g * 256 + Cfg::kSCol + h * kHN, ad, bd, idesc1, kk > 0 ? 1u : 0u);
+                        }
+                        mma_commit(&bars->s_full[g][h]);
+                        if (g == 1 && h == 1 && seg_end) mma_commit(&bars->r_empty);
+                        if (g == 0 && h == 0) FL_TRACE(it, 1);
                     }
-                    mma_commit(&bars->s_full[g]);
-                    if (g == 1 && seg_end) mma_commit(&bars->r_empty);
-                    if (g == 0) FL_TRACE(it, 1);
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else if (warp == kMma2Warp) {
-        // ===================== second product: G_g += P_g . T  (A = P from tensor memory, B = the same tile, MN-major) =====================
+        // ===================== second product, per panel and half: G_g += P_g[:, half] . T[half]  (A = P from tensor memory,
+        // B = the same tile, MN-major) =====================
         constexpr uint32_t idesc2 = make_idesc_f16_bmn(128, E);
         const uint32_t sT_a = smem_u32(sT);
         const uint32_t lbo = p.mn_lbo ? (uint32_t)p.mn_lbo : (uint32_t)(BN * 128), sbo = p.mn_sbo ? (uint32_t)p.mn_sbo : 1024u;
@@ -389,20 +404,25 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 if (seg_start) mbar_wait(&bars->g_empty[g], (k & 1) ^ 1);   // the epilogue has drained the previous segment's G
-                mbar_wait(&bars->p_full[g], it & 1);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes, lbo, sbo);
-                    const uint32_t d_t = tmem + g * 256 + Cfg::kGCol, a_t = tmem + g * 256 + Cfg::kPCol;
 #pragma unroll
-                    for (int kk = 0; kk < Cfg::kMma2; ++kk)   // 16 rows of T (2048 bytes of every slab) per instruction
-                        mma_f16_ts(d_t, a_t + kk * 8, bd0 + (uint64_t)((kk * 2048) >> 4), idesc2, (!seg_start || kk > 0) ? 1u : 0u);
-                    mma_commit(&bars->p_empty[g]);
-                    if (g == 1) mma_commit(&bars->t_empty[stage]);   // both panels are done with this tile (and its column term)
-                    if (seg_end) mma_commit(&bars->g_full[g]);
-                    if (g == 0) FL_TRACE(it, 7);
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(&bars->p_full[g][h], it & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes, lbo, sbo);
+                        const uint32_t d_t = tmem + g * 256 + Cfg::kGCol, a_t = tmem + g * 256 + Cfg::kPCol;
+#pragma unroll
+                        for (int k2 = 0; k2 < Cfg::kMma2 / 2; ++k2) {   // 16 rows of T (2048 bytes of every slab) per instruction
+                            const int kk = h * (Cfg::kMma2 / 2) + k2;
+                            mma_f16_ts(d_t, a_t + kk * 8, bd0 + (uint64_t)((kk * 2048) >> 4), idesc2, (!seg_start || kk > 0) ? 1u : 0u);
+                        }
+                        mma_commit(&bars->p_empty[g][h]);
+                        if (g == 1 && h == 1) mma_commit(&bars->t_empty[stage]);   // both panels are done with this tile (and its column term)
+                        if (h == 1 && seg_end) mma_commit(&bars->g_full[g]);
+                        if (g == 0 && h == 1) FL_TRACE(it, 7);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
@@ -442,9 +462,9 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             const int n0 = c.tile * BN;
             const bool fast = (n0 + BN <= ps.nT) && (wrow0 + 32 <= ps.nR) && (wrow0 + ps.d + 32 <= n0 || wrow0 + ps.d >= n0 + BN);
             const int dcol_abs = row_ok ? row + ps.d : -1;
-            mbar_wait(&bars->s_full[g], it & 1);
+            const uint32_t ph = it & 1;
             mbar_wait(&bars->t_full[stage], (it / Cfg::kStages) & 1);   // the staged column term (landed long ago)
-            mbar_wait(&bars->p_empty[g], (it & 1) ^ 1);                  // MMA2 of the previous unit is done: P free, G quiescent
+            mbar_wait(&bars->s_full[g][0], ph);
             tc_fence_after();
             if (lane == 0 && q == 0 && g == 0) FL_TRACE(it, 2);
             const uint32_t c2s = smem_u32(sC2 + stage * Cfg::kC2Bytes);
@@ -452,22 +472,45 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             tmem_ld_32x32_issue(tS, rbuf[0]);
 #pragma unroll
             for (int cc = 0; cc < Cfg::kChunks; ++cc) {
+                const int h = cc / kHC;
+                const bool first_of_half = (cc % kHC) == 0, last_of_half = (cc % kHC) == kHC - 1;
                 tmem_ld_wait();
-                if (cc + 1 < Cfg::kChunks) tmem_ld_32x32_issue(tS + (cc + 1) * 32, rbuf[(cc + 1) & 1]);
+                if (cc + 1 < Cfg::kChunks) {
+                    if ((cc + 1) % kHC == 0) {   // the next chunk opens the second half of S
+                        mbar_wait(&bars->s_full[g][1], ph);
+                        tc_fence_after();
+                    }
+                    tmem_ld_32x32_issue(tS + (cc + 1) * 32, rbuf[(cc + 1) & 1]);
+                }
+                if (last_of_half) {   // every column of this half of S is in registers: the next tile's first product may refill it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->s_empty[g][h]);
+                }
+                if (first_of_half) {  // the second product of the previous tile has consumed this half of P
+                    mbar_wait(&bars->p_empty[g][h], ph ^ 1);
+                    tc_fence_after();
+                }
                 uint32_t(&r)[32] = rbuf[cc & 1];
                 const int nb = n0 + cc * 32;
                 if constexpr (MODE == kP1) {
                     // (the fast and the checked form are separate branches end to end: joining them after phase A costs a register
                     // move per logit)
+                    auto raise = [&](bool need, float cmin) {
+                        // G must be quiescent: every second product issued so far has to be complete (the previous tile's second half;
+                        // this tile's first half when we are in the second)
+                        mbar_wait(&bars->p_empty[g][1], ph ^ 1);
+                        if (h == 1) mbar_wait(&bars->p_empty[g][0], ph);
+                        tc_fence_after();
+                        const P1State ns = p1_raise<E>(need, cmin, !seg_start || h == 1, cc % kHC, tG, tP + h * kHC * 16, a_run, lsum);
+                        a_run = ns.a; lsum = ns.l;
+                    };
                     if (fast) {
                         f32x2 zn[16];
                         uint32_t w[16];
                         const float cmin = p1_zn_fast(r, c2s + cc * 128, kmul, zn);
                         const bool need = cmin < a_run - (kOff1 + kTau);   // this chunk exceeds the row's reference by more than 2^kTau
-                        if (__any_sync(0xffffffffu, need)) {
-                            const P1State ns = p1_raise<E>(need, cmin, !seg_start, cc, tG, tP, a_run, lsum);
-                            a_run = ns.a; lsum = ns.l;
-                        }
+                        if (__any_sync(0xffffffffu, need)) raise(need, cmin);
                         p1_exp_fast(zn, a_run, lsum, w);
                         tmem_st_32x16(tP + cc * 16, w);
                     } else {
@@ -476,10 +519,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                         int dloc = -1;
                         const float cmin = p1_zn_checked(r, c2s + cc * 128, kmul, nb, ps.nT, dcol_abs, zn, dloc);
                         const bool need = cmin < a_run - (kOff1 + kTau);
-                        if (__any_sync(0xffffffffu, need)) {
-                            const P1State ns = p1_raise<E>(need, cmin, !seg_start, cc, tG, tP, a_run, lsum);
-                            a_run = ns.a; lsum = ns.l;
-                        }
+                        if (__any_sync(0xffffffffu, need)) raise(need, cmin);
                         p1_exp_checked(zn, a_run, dloc, lsum, w, zd);
                         if (dloc >= 0) has_diag = true;
                         tmem_st_32x16(tP + cc * 16, w);
@@ -487,16 +527,15 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                 } else {
                     uint32_t w[16];
                     if (fast) p2_chunk_fast(r, c2s + cc * 128, kmul, rowc, w);
-                    else p2_chunk_checked(r, c2s + cc * 128, kmul, rowc, nb, ps.nT, row_ok, dcol_abs, w);
+                    else p2_chunk_checked(r, c2s + cc * 128, kmul, rowc, nb, ps.nT, row_ok, dcol_abs, ps.diag_pm1, w);
                     tmem_st_32x16(tP + cc * 16, w);
                 }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&bars->s_empty[g]);
-                mbar_arrive(&bars->p_full[g]);
+                if (last_of_half) {   // this half of P is complete in tensor memory
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->p_full[g][h]);
+                }
             }
             if (lane == 0 && q == 0 && g == 0) FL_TRACE(it, 3);
             if (seg_end) {
