@@ -121,6 +121,7 @@ static int cvt_item(CvtItem& it, const float* X, int ld, int n, int E, __half* X
 
 // ---- plan ---------------------------------------------------------------------------------------------------------------
 static inline int fl_bn(int E) { return E <= 64 ? 128 : 64; }
+static inline int fl_split(int E) { return fl_bn(E) / 64; }   // partials per (panel pair, CTA slot): one per 64-column half of the tile
 struct FlPlan { int grid, units, slots[2], unit0[2], m_pairs[2], n_tiles[2]; };
 static FlPlan fl_plan(int n_pass, const int* nR, const int* nT, int E) {
     FlPlan pl{};
@@ -145,18 +146,18 @@ static FlPlan fl_plan(int n_pass, const int* nR, const int* nT, int E) {
     return pl;
 }
 
-template <int MODE, int E, int BN>
+template <int MODE, int E>
 static int launch_flash(const FlMaps& maps, const FlParams& p, int grid, cudaStream_t st, const char* name) {
-    using Cfg = FlCfg<MODE, E, BN>;
-    TT_CUDA_OK(cudaFuncSetAttribute(flash_kernel<MODE, E, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    flash_kernel<MODE, E, BN><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
+    using Cfg = FlCfg<E>;
+    TT_CUDA_OK(cudaFuncSetAttribute(flash_kernel<MODE, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    flash_kernel<MODE, E><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
     TT_LAUNCH_OK(name);
     return TT_OK;
 }
 template <int MODE>
 static int launch_flash_e(int E, const FlMaps& maps, const FlParams& p, int grid, cudaStream_t st) {
-    if (E == 64) return launch_flash<MODE, 64, 128>(maps, p, grid, st, MODE == kP1 ? "flash_kernel<p1,64>" : "flash_kernel<p2,64>");
-    return launch_flash<MODE, 128, 64>(maps, p, grid, st, MODE == kP1 ? "flash_kernel<p1,128>" : "flash_kernel<p2,128>");
+    if (E == 64) return launch_flash<MODE, 64>(maps, p, grid, st, MODE == kP1 ? "flash_kernel<p1,64>" : "flash_kernel<p2,64>");
+    return launch_flash<MODE, 128>(maps, p, grid, st, MODE == kP1 ? "flash_kernel<p1,128>" : "flash_kernel<p2,128>");
 }
 
 // ---- combine 1: per-row merge of the pass-1 partials in slot order -> lse, row loss, loss, dQ, lse column term ---------------------
@@ -165,7 +166,7 @@ static int launch_flash_e(int E, const FlMaps& maps, const FlParams& p, int grid
 //   row loss = ln(1 + L_off / pd),      dQ_i = (sum_s G_s 2^(m_s - M)) / (L * scale_C) + (p_ii - 1) C[i + d]
 struct Comb1Args {
     const float* pm; const float* pl; const float* pzd; const float* pg;
-    int nR, rows_pad, n_tiles, units, grid, unit0, E, d;
+    int nR, rows_pad, n_tiles, units, grid, unit0, E, d, ksplit;
     const float* C; int ldc;
     const float* scal;
     float* lse; float* rowloss; float* c2_lse; int c2_pad; float* pm1;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
     double mine = 0.0;
     if (r < a.nR) {
         const int first = a.unit0 + (r >> 8) * a.n_tiles;
-        const int slots = sk_owner(first + a.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1;
+        const int slots = (sk_owner(first + a.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1) * a.ksplit;
         const float zd = a.pzd[r];
         float M = zd;                                            // the positive takes part in the maximum
         for (int s = 0; s < slots; ++s) M = fmaxf(M, a.pm[(int64_t)s * a.rows_pad + r]);
@@ -229,18 +230,26 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
         s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last) {   // the last block adds the block sums: thread t takes blocks t, t + 256, ... in order, then a fixed tree (deterministic)
         __threadfence();
         double t = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += reinterpret_cast<volatile double*>(a.block_sums)[b];   // block order: deterministic
-        a.loss[0] = (float)t;
-        *a.counter = 0u;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += 256) t += reinterpret_cast<volatile double*>(a.block_sums)[b];
+        s_sum[threadIdx.x] = t;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            a.loss[0] = (float)s_sum[0];
+            *a.counter = 0u;
+        }
     }
 }
 
 // ---- combine 2: G[r][:] = 2^-kOff2 / scale_T * sum over the pair's CTA slots, in slot order -------------------------------------
 struct Comb2Side { const float* part; float* G; int ldg, nR, rows_pad, n_tiles, unit0, scal_idx; };
-struct Comb2Args { Comb2Side s[2]; int n, E, units, grid; const float* scal; };
+struct Comb2Args { Comb2Side s[2]; int n, E, units, grid, ksplit; const float* scal; };
 __global__ void __launch_bounds__(256) fl_combine2_kernel(const Comb2Args a) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int e4 = a.E >> 2;
@@ -250,7 +259,7 @@ __global__ void __launch_bounds__(256) fl_combine2_kernel(const Comb2Args a) {
         if (i < cnt) {
             const int r = (int)(i / e4), c4 = (int)(i % e4);
             const int first = sd.unit0 + (r >> 8) * sd.n_tiles;
-            const int slots = sk_owner(first + sd.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1;
+            const int slots = (sk_owner(first + sd.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1) * a.ksplit;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int z = 0; z < slots; ++z) {
                 const float4 v = *reinterpret_cast<const float4*>(sd.part + ((int64_t)z * sd.rows_pad + r) * a.E + 4 * c4);
@@ -289,19 +298,19 @@ static FlWs fl_carve(void* ws, int Bq, int Bc, int E) {
     // pass 1: R = Q, T = C
     int nR1[1] = {Bq}, nT1[1] = {Bc};
     FlPlan p1 = fl_plan(1, nR1, nT1, E);
-    const size_t rp1 = (size_t)p1.m_pairs[0] * 256;
-    w.p1_m = cv.take<float>(p1.slots[0] * rp1);
-    w.p1_l = cv.take<float>(p1.slots[0] * rp1);
+    const size_t rp1 = (size_t)p1.m_pairs[0] * 256, ks = (size_t)fl_split(E);
+    w.p1_m = cv.take<float>(ks * p1.slots[0] * rp1);
+    w.p1_l = cv.take<float>(ks * p1.slots[0] * rp1);
     w.p1_zd = cv.take<float>(rp1);
-    w.p1_g = cv.take<float>(p1.slots[0] * rp1 * E);
+    w.p1_g = cv.take<float>(ks * p1.slots[0] * rp1 * E);
     // pass 2: up to two sides in one launch (dQ side: R = Q; dC side: R = C); sized for the larger of {both, either alone}
     int nRb[2] = {Bq, Bc}, nTb[2] = {Bc, Bq};
     FlPlan pb = fl_plan(2, nRb, nTb, E);
     int nRq[1] = {Bq}, nTq[1] = {Bc}, nRc[1] = {Bc}, nTc[1] = {Bq};
     FlPlan pq = fl_plan(1, nRq, nTq, E), pc = fl_plan(1, nRc, nTc, E);
     const int sq = pb.slots[0] > pq.slots[0] ? pb.slots[0] : pq.slots[0], sc = pb.slots[1] > pc.slots[0] ? pb.slots[1] : pc.slots[0];
-    w.p2_g[0] = cv.take<float>((size_t)sq * pb.m_pairs[0] * 256 * E);
-    w.p2_g[1] = cv.take<float>((size_t)sc * pb.m_pairs[1] * 256 * E);
+    w.p2_g[0] = cv.take<float>(ks * sq * pb.m_pairs[0] * 256 * E);
+    w.p2_g[1] = cv.take<float>(ks * sc * pb.m_pairs[1] * 256 * E);
     w.bytes = align_up(cv.off, 256) + 256;
     return w;
 }
@@ -349,7 +358,7 @@ static int fl_pass1(const FlWs& w, const float* C, int ldc, int Bq, int Bc, int 
     if (rc) return rc;
     Comb1Args ca{};
     ca.pm = w.p1_m; ca.pl = w.p1_l; ca.pzd = w.p1_zd; ca.pg = w.p1_g;
-    ca.nR = Bq; ca.rows_pad = pl.m_pairs[0] * 256; ca.n_tiles = pl.n_tiles[0]; ca.units = pl.units; ca.grid = pl.grid; ca.unit0 = 0; ca.E = E; ca.d = off;
+    ca.nR = Bq; ca.rows_pad = pl.m_pairs[0] * 256; ca.n_tiles = pl.n_tiles[0]; ca.units = pl.units; ca.grid = pl.grid; ca.unit0 = 0; ca.E = E; ca.d = off; ca.ksplit = fl_split(E);
     ca.C = C; ca.ldc = ldc; ca.scal = w.scal; ca.lse = lse; ca.rowloss = w.rowloss;
     ca.c2_lse = want_c2_lse ? w.c2_lse : nullptr; ca.c2_pad = (int)(ceil_div(Bq, bn) * bn); ca.pm1 = want_c2_lse ? w.pm1 : nullptr;
     ca.dQ = dQ; ca.lddq = lddq; ca.block_sums = w.block_sums; ca.counter = w.counter; ca.loss = loss;
@@ -373,7 +382,7 @@ static int fl_pass2(const FlWs& w, const float* bias, const float* lse, int Bq, 
     FlParams p{};
     p.n_pass = n; p.units = pl.units; p.kmul = w.scal + 2; p.mn_lbo = g_fl_lbo; p.mn_sbo = g_fl_sbo; p.trace = g_fl_trace;
     Comb2Args ca{};
-    ca.n = n; ca.E = E; ca.units = pl.units; ca.grid = pl.grid; ca.scal = w.scal;
+    ca.n = n; ca.E = E; ca.units = pl.units; ca.grid = pl.grid; ca.ksplit = fl_split(E); ca.scal = w.scal;
     int64_t items = 0;
     for (int i = 0; i < n; ++i) {
         const bool rq = sides[i].r_is_q != 0;
