@@ -15,7 +15,8 @@
 // Streams never talk to each other: the partial (reference exponent, sum, G) of every stream is merged by the combine kernel
 // exactly like the partials of two CTAs that share a panel.  The cycle of a stream is
 //     first product (S)  ->  epilogue (exponentials, P)  ->  second product (G += P . T)  ->  first product of the next tile
-// and the four streams of a CTA (16 epilogue warps, four per scheduler) interleave on the MUFU and tensor pipes.
+// and the four streams of a CTA (16 epilogue warps, four per scheduler) interleave on the MUFU and tensor pipes.  Each stream has
+// its own MMA issuer warp, so no stream ever waits behind another one's barrier.
 //
 // Operands are fp16 copies scaled by a per-tensor power of two (tt_softmax_flash.cu: amax -> scale), so any finite fp32 input is in
 // range; products are exact and accumulate in fp32 in TMEM.  The second product reads P from TENSOR MEMORY (A operand) and the
@@ -90,7 +91,7 @@ struct FlCfg {
     static constexpr int kRBytes = 2 * kPanelBytes;               // the pair
     static constexpr int kTBytes = kSlabs * BN * 128;             // one T tile (K-major over E for MMA1 == MN-major over E for MMA2)
     static constexpr int kC2Bytes = BN * 4;
-    static constexpr int kFixed = kRBytes + 8 * kC2Bytes + 1024 /*barriers*/ + 1024 /*align*/;
+    static constexpr int kFixed = 2 * kRBytes /*two pairs: the next one is prefetched*/ + 8 * kC2Bytes + 1024 /*barriers*/ + 1024 /*align*/;
     static constexpr int kFit = (232448 - kFixed) / kTBytes;
     static constexpr int kStages = kFit >= 8 ? 8 : kFit;
     static constexpr int kSmemBytes = kFixed + kStages * kTBytes;
@@ -98,12 +99,13 @@ struct FlCfg {
     static constexpr int kStreamCols = 64 + E;                    // TMEM columns of a stream: S (64; P over its first 32) | G (E)
     static constexpr int kGCol = 64;
     static_assert(NS * kStreamCols <= 512, "TMEM budget");
-    static constexpr int kThreads = 32 * (kEpiWarps + 3);         // + producer, MMA1 issuer, MMA2 issuer
+    static constexpr int kThreads = 32 * (kEpiWarps + NS);        // + one issuer warp per stream (MMA, and its share of the TMA loads)
+    static constexpr int kLook = kStages - 2;                     // tiles prefetched ahead of the one being multiplied
     static_assert(kStages >= 3, "shared memory budget");
 };
 
 struct FlBars {
-    uint64_t r_full, r_empty;
+    uint64_t r_full[2], r_empty[2];
     uint64_t t_full[8], t_empty[8];
     uint64_t s_full[4];     // first product of the stream's tile complete
     uint64_t p_full[4];     // P of the stream's tile complete in tensor memory (4 epilogue warps)
@@ -314,6 +316,17 @@ __device__ __forceinline__ void p2_chunk_fast(const uint32_t (&r)[16], uint32_t 
         w[2 * g4 + 1] = pack_f16x2(ex2_approx(b0), ex2_approx(b1));
     }
 }
+// pass 2, fast chunk, exponent arguments only (the exponentials are taken one chunk later, see the epilogue's software pipeline)
+__device__ __forceinline__ void p2_x_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, float rowc, float (&x)[16]) {
+    const f32x2 km = pk2(kmul, kmul), mone = pk2(-1.f, -1.f), rc = pk2(rowc, rowc);
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+        const float4 cc = lds128(c2s + g4 * 16);
+        const f32x2 ad0 = fma2(pk2(cc.x, cc.y), mone, rc), ad1 = fma2(pk2(cc.z, cc.w), mone, rc);
+        upk2(fma2(pk2(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1])), km, ad0), x[4 * g4], x[4 * g4 + 1]);
+        upk2(fma2(pk2(__uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])), km, ad1), x[4 * g4 + 2], x[4 * g4 + 3]);
+    }
+}
 __device__ __noinline__ void p2_chunk_checked(uint32_t tS_chunk, uint32_t c2s, float kmul, float rowc, int nb, int nT, bool row_ok, int dcol_abs,
                                               const float* __restrict__ diag_pm1, uint32_t tP_chunk) {
     uint32_t r[16];
@@ -356,19 +369,18 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     unsigned char* sR = smem;
-    unsigned char* sT = sR + Cfg::kRBytes;
+    unsigned char* sT = sR + 2 * Cfg::kRBytes;                    // two R pairs (double buffered)
     unsigned char* sC2 = sT + Cfg::kStages * Cfg::kTBytes;
     FlBars* bars = reinterpret_cast<FlBars*>(sC2 + 8 * Cfg::kC2Bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int kProducerWarp = Cfg::kEpiWarps, kMma1Warp = Cfg::kEpiWarps + 1, kMma2Warp = Cfg::kEpiWarps + 2;
-    if (warp == kProducerWarp && lane == 0) {
+    constexpr int kIssuerWarp0 = Cfg::kEpiWarps;
+    if (warp == kIssuerWarp0 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
             if (i < p.n_pass) { prefetch_tmap(&maps.r[i]); prefetch_tmap(&maps.t[i]); }
         }
-        mbar_init(&bars->r_full, 1);
-        mbar_init(&bars->r_empty, 1);
-        for (int i = 0; i < 8; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->r_full[i], 1); mbar_init(&bars->r_empty[i], NS); }
+        for (int i = 0; i < 8; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], NS); }
         for (int i = 0; i < 4; ++i) {
             mbar_init(&bars->s_full[i], 1);
             mbar_init(&bars->p_full[i], 4); mbar_init(&bars->p_empty[i], 1);
@@ -376,114 +388,115 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
         }
         fence_barrier_init();
     }
-    if (warp == kMma1Warp) tmem_alloc(&bars->tmem_base, 512);
+    if (warp == kIssuerWarp0) tmem_alloc(&bars->tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    const uint32_t b_rfull = smem_u32(&bars->r_full), b_rempty = smem_u32(&bars->r_empty), b_tfull = smem_u32(&bars->t_full[0]),
+    const uint32_t b_rfull = smem_u32(&bars->r_full[0]), b_rempty = smem_u32(&bars->r_empty[0]), b_tfull = smem_u32(&bars->t_full[0]),
                    b_tempty = smem_u32(&bars->t_empty[0]), b_sfull = smem_u32(&bars->s_full[0]), b_pfull = smem_u32(&bars->p_full[0]),
                    b_pempty = smem_u32(&bars->p_empty[0]), b_gfull = smem_u32(&bars->g_full[0]), b_gempty = smem_u32(&bars->g_empty[0]);
 
-    if (warp >= Cfg::kEpiWarps) {
-        if (warp == kProducerWarp) {
-            // ===================== TMA producer =====================
-            if (lane == 0) {
-                FlCursor c;
-                c.init(p, u_begin);
-                int k = 0;
-                for (int it = 0; it < my_units; ++it, c.next(p)) {
-                    const FlPass& ps = p.pass[c.pass];
-                    if (it == 0 || c.tile == 0) {   // a new pair of panels
-                        mbar_wait_a(b_rempty, (k & 1) ^ 1);
-                        mbar_arrive_expect_tx(&bars->r_full, Cfg::kRBytes);
-                        for (int g = 0; g < 2; ++g)
-                            for (int s = 0; s < Cfg::kSlabs; ++s)
-                                tma_load_2d(sR + g * Cfg::kPanelBytes + s * 128 * 128, &maps.r[c.pass], &bars->r_full, s * 64, (c.pair * 2 + g) * 128);
-                        ++k;
+    if (warp >= kIssuerWarp0) {
+        // ===================== issuer of stream s (one lane) =====================
+        //   first product   S_s = R_g . T[half]^T            (N = 64)
+        //   second product  G_s += P_s . T[half]              (A = P from tensor memory, B = the same tile, MN-major; K = 64 = 4 instructions)
+        // The first product of tile it+1 follows the second product of tile it as soon as that one has completed (P lives in the S
+        // columns).  The issuers also share the TMA loads: issuer s fetches every tile j with j % NS == s, kLook tiles ahead, and the
+        // pair of R panels when that tile opens a new pair (R is double buffered, so the switch does not drain the pipeline).
+        if (lane == 0) {
+            const int s = warp - kIssuerWarp0;
+            const int g = s / kSplit, h = s % kSplit;
+            constexpr uint32_t idesc1 = make_idesc_f16(128, 64);
+            constexpr uint32_t idesc2 = make_idesc_f16_bmn(128, E);
+            const uint32_t sR_a = smem_u32(sR), sT_a = smem_u32(sT);
+            const uint32_t lbo = p.mn_lbo ? (uint32_t)p.mn_lbo : (uint32_t)(BN * 128), sbo = p.mn_sbo ? (uint32_t)p.mn_sbo : 1024u;
+            const uint32_t tS = tmem + s * Cfg::kStreamCols, tG = tS + Cfg::kGCol;
+            FlCursor c, pc;
+            c.init(p, u_begin);
+            pc = c;
+            int pk = -1;   // pairs of panels met by the prefetch cursor - 1
+            auto prefetch = [&](int j) {   // tile j of this CTA's range; pc stands on it
+                const bool newseg = (j == 0 || pc.tile == 0);
+                if (newseg) ++pk;
+                if (j % NS == s) {
+                    if (newseg) {   // every stream's last first-product on the pair that used this buffer is complete
+                        mbar_wait_a(b_rempty + (pk & 1) * 8, ((pk >> 1) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&bars->r_full[pk & 1], Cfg::kRBytes);
+                        for (int gg = 0; gg < 2; ++gg)
+                            for (int sl = 0; sl < Cfg::kSlabs; ++sl)
+                                tma_load_2d(sR + (pk & 1) * Cfg::kRBytes + gg * Cfg::kPanelBytes + sl * 128 * 128, &maps.r[pc.pass], &bars->r_full[pk & 1], sl * 64,
+                                            (pc.pair * 2 + gg) * 128);
                     }
-                    const int stage = it % Cfg::kStages;
-                    const int n0 = c.tile * BN;
-                    mbar_wait_a(b_tempty + stage * 8, ((it / Cfg::kStages) & 1) ^ 1);
+                    const int stage = j % Cfg::kStages;
+                    const int n0 = pc.tile * BN;
+                    mbar_wait_a(b_tempty + stage * 8, ((j / Cfg::kStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->t_full[stage], Cfg::kTBytes + Cfg::kC2Bytes);
                     unsigned char* dst = sT + stage * Cfg::kTBytes;
-                    for (int s = 0; s < Cfg::kSlabs; ++s) tma_load_2d(dst + s * BN * 128, &maps.t[c.pass], &bars->t_full[stage], s * 64, n0);
-                    bulk_copy_1d(sC2 + stage * Cfg::kC2Bytes, ps.colv2 + n0, Cfg::kC2Bytes, &bars->t_full[stage]);
-                    FL_TRACE(it, 0);
+                    for (int sl = 0; sl < Cfg::kSlabs; ++sl) tma_load_2d(dst + sl * BN * 128, &maps.t[pc.pass], &bars->t_full[stage], sl * 64, n0);
+                    bulk_copy_1d(sC2 + stage * Cfg::kC2Bytes, p.pass[pc.pass].colv2 + n0, Cfg::kC2Bytes, &bars->t_full[stage]);
+                    if (s == 0) FL_TRACE(j, 0);
                 }
-            }
-        } else if (warp == kMma1Warp) {
-            // ===================== first product per stream: S_s = R_g . T[half]^T (N = 64) =====================
-            constexpr uint32_t idesc1 = make_idesc_f16(128, 64);
-            const uint32_t sR_a = smem_u32(sR), sT_a = smem_u32(sT);
-            FlCursor c;
-            c.init(p, u_begin);
+                pc.next(p);
+            };
+            auto first_product = [&](int it, int kseg) {   // S_s of tile `it`, which belongs to pair number kseg of this CTA
+                const int stage = it % Cfg::kStages;
+                const uint64_t ad0 = make_smem_desc(sR_a + (kseg & 1) * Cfg::kRBytes + g * Cfg::kPanelBytes, 16, 1024);
+                const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes + h * 64 * 128, 16, 1024);   // rows [h*64, +64) of every slab
+#pragma unroll
+                for (int kk = 0; kk < Cfg::kMma1; ++kk) {
+                    const uint64_t ad = ad0 + (uint64_t)(((kk >> 2) * 128 * 128 + (kk & 3) * 32) >> 4);
+                    const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * BN * 128 + (kk & 3) * 32) >> 4);
+                    mma_f16(tS, ad, bd, idesc1, kk > 0 ? 1u : 0u);
+                }
+                mma_commit_a(b_sfull + s * 8);
+            };
+            int pf = 0;
+            for (; pf < Cfg::kLook && pf < my_units; ++pf) prefetch(pf);
+            // the first tile
+            mbar_wait_a(b_rfull, 0);
+            mbar_wait_a(b_tfull, 0);
+            tc_fence_after();
+            first_product(0, 0);
+            if (s == 0) FL_TRACE(0, 1);
             int k = -1;
-            for (int it = 0; it < my_units; ++it, c.next(p)) {
+            for (int it = 0; it < my_units; ++it) {
+                if (pf < my_units) prefetch(pf++);
                 const bool seg_start = (it == 0 || c.tile == 0);
                 const bool seg_end = (it == my_units - 1 || c.tile == p.pass[c.pass].n_tiles - 1);
                 if (seg_start) {
                     ++k;
-                    mbar_wait_a(b_rfull, k & 1);
+                    mbar_wait_a(b_gempty + s * 8, (k & 1) ^ 1);   // the epilogue has drained the previous segment's G
                 }
                 const int stage = it % Cfg::kStages;
-                mbar_wait_a(b_tfull + stage * 8, (it / Cfg::kStages) & 1);
+                mbar_wait_a(b_pfull + s * 8, it & 1);
+                tc_fence_after();
+                {
+                    const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes, lbo, sbo);
 #pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const int g = s / kSplit, h = s % kSplit;
-                    mbar_wait_a(b_pempty + s * 8, (it & 1) ^ 1);   // the stream's second product of the previous tile has consumed P (= S columns)
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint64_t ad0 = make_smem_desc(sR_a + g * Cfg::kPanelBytes, 16, 1024);
-                        const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes + h * 64 * 128, 16, 1024);   // rows [h*64, +64) of every slab
-#pragma unroll
-                        for (int kk = 0; kk < Cfg::kMma1; ++kk) {
-                            const uint64_t ad = ad0 + (uint64_t)(((kk >> 2) * 128 * 128 + (kk & 3) * 32) >> 4);
-                            const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * BN * 128 + (kk & 3) * 32) >> 4);
-                            mma_f16(tmem + s * Cfg::kStreamCols, ad, bd, idesc1, kk > 0 ? 1u : 0u);
-                        }
-                        mma_commit_a(b_sfull + s * 8);
-                        if (s == NS - 1 && seg_end) mma_commit_a(b_rempty);
-                        if (s == 0) FL_TRACE(it, 1);
+                    for (int k2 = 0; k2 < 4; ++k2)   // 16 rows of T (2048 bytes of every slab) per instruction
+                        mma_f16_ts(tG, tS + k2 * 8, bd0 + (uint64_t)(((h * 4 + k2) * 2048) >> 4), idesc2, (!seg_start || k2 > 0) ? 1u : 0u);
+                    mma_commit_a(b_tempty + stage * 8);   // (one of NS arrivals) this stream is done with the tile and its column term
+                    if (seg_end) {
+                        mma_commit_a(b_gfull + s * 8);
+                        mma_commit_a(b_rempty + (k & 1) * 8);   // (one of NS arrivals) ... and with this pair of panels
                     }
-                    __syncwarp();
+                    mma_commit_a(b_pempty + s * 8);
+                    if (s == 0) FL_TRACE(it, 7);
                 }
-            }
-        } else if (warp == kMma2Warp) {
-            // ===================== second product per stream: G_s += P_s . T[half]  (A = P from tensor memory, B = the same tile,
-            // MN-major; K = 64 columns of the tile = 4 instructions) =====================
-            constexpr uint32_t idesc2 = make_idesc_f16_bmn(128, E);
-            const uint32_t sT_a = smem_u32(sT);
-            const uint32_t lbo = p.mn_lbo ? (uint32_t)p.mn_lbo : (uint32_t)(BN * 128), sbo = p.mn_sbo ? (uint32_t)p.mn_sbo : 1024u;
-            FlCursor c;
-            c.init(p, u_begin);
-            int k = -1;
-            for (int it = 0; it < my_units; ++it, c.next(p)) {
-                const bool seg_start = (it == 0 || c.tile == 0);
-                const bool seg_end = (it == my_units - 1 || c.tile == p.pass[c.pass].n_tiles - 1);
-                if (seg_start) ++k;
-                const int stage = it % Cfg::kStages;
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const int h = s % kSplit;
-                    if (seg_start) mbar_wait_a(b_gempty + s * 8, (k & 1) ^ 1);   // the epilogue has drained the previous segment's G
-                    mbar_wait_a(b_pfull + s * 8, it & 1);
+                c.next(p);
+                if (it + 1 < my_units) {
+                    const int kn = k + (c.tile == 0 ? 1 : 0);      // the next tile may open a new pair of panels
+                    if (kn != k) mbar_wait_a(b_rfull + (kn & 1) * 8, (kn >> 1) & 1);
+                    mbar_wait_a(b_tfull + ((it + 1) % Cfg::kStages) * 8, ((it + 1) / Cfg::kStages) & 1);
+                    mbar_wait_a(b_pempty + s * 8, it & 1);         // the second product has consumed P: the S columns may be refilled
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes, lbo, sbo);
-                        const uint32_t d_t = tmem + s * Cfg::kStreamCols + Cfg::kGCol, a_t = tmem + s * Cfg::kStreamCols;
-#pragma unroll
-                        for (int k2 = 0; k2 < 4; ++k2)   // 16 rows of T (2048 bytes of every slab) per instruction
-                            mma_f16_ts(d_t, a_t + k2 * 8, bd0 + (uint64_t)(((h * 4 + k2) * 2048) >> 4), idesc2, (!seg_start || k2 > 0) ? 1u : 0u);
-                        mma_commit_a(b_pempty + s * 8);
-                        if (s == NS - 1) mma_commit_a(b_tempty + stage * 8);   // every stream is done with this tile (and its column term)
-                        if (seg_end) mma_commit_a(b_gfull + s * 8);
-                        if (s == 0) FL_TRACE(it, 7);
-                    }
-                    __syncwarp();
+                    first_product(it + 1, kn);
+                    if (s == 0) FL_TRACE(it + 1, 1);
                 }
             }
         }
+        __syncwarp();
     } else {
         // ===================== epilogue: stream s = warp / 4 (panel g, half h), TMEM lane quarter q = warp % 4 =====================
         const int s = warp >> 2, q = warp & 3;
@@ -525,24 +538,49 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             tc_fence_after();
             if (lane == 0 && warp == 0) FL_TRACE(it, 2);
             if (fast) {
+                // software pipeline over the four 16-column chunks: the address arithmetic of chunk j+1 (FFMA2, min) sits in the same
+                // basic block as the exponentials of chunk j, so the scheduler overlaps them and the MUFU pipe stays fed
                 uint32_t rb[2][kCW];
                 tmem_ld_32x16_issue(tS, rb[0]);
-#pragma unroll
-                for (int j = 0; j < 64 / kCW; ++j) {
-                    tmem_ld_wait();
-                    if (j + 1 < 64 / kCW) tmem_ld_32x16_issue(tS + (j + 1) * kCW, rb[(j + 1) & 1]);
-                    uint32_t(&r)[kCW] = rb[j & 1];
-                    uint32_t w[kCW / 2];
-                    if constexpr (MODE == kP1) {
-                        f32x2 zn[kCW / 2];
-                        const float cmin = p1_zn_fast(r, c2s + j * kCW * 4, kmul, zn);
+                tmem_ld_wait();
+                tmem_ld_32x16_issue(tS + kCW, rb[1]);
+                if constexpr (MODE == kP1) {
+                    f32x2 zn[2][kCW / 2];
+                    float cmin = p1_zn_fast(rb[0], c2s, kmul, zn[0]);
+                    {
                         const bool need = cmin < st.a - (kOff1 + kTau);   // this chunk exceeds the row's reference by more than 2^kTau
-                        if (__any_sync(0xffffffffu, need)) st = p1_raise<E>(need, cmin, !seg_start, j, tG, tP, st);
-                        p1_exp_fast(zn, st.a, st.l, w);
-                    } else {
-                        p2_chunk_fast(r, c2s + j * kCW * 4, kmul, rowc, w);
+                        if (__any_sync(0xffffffffu, need)) st = p1_raise<E>(need, cmin, !seg_start, 0, tG, tP, st);
                     }
-                    tmem_st_32x8(tP + j * (kCW / 2), w);
+#pragma unroll
+                    for (int j = 0; j < 64 / kCW; ++j) {
+                        uint32_t w[kCW / 2];
+                        if (j + 1 < 64 / kCW) {
+                            tmem_ld_wait();                                                       // chunk j+1 is in registers
+                            cmin = p1_zn_fast(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, zn[(j + 1) & 1]);
+                            if (j + 2 < 64 / kCW) tmem_ld_32x16_issue(tS + (j + 2) * kCW, rb[j & 1]);
+                        }
+                        p1_exp_fast(zn[j & 1], st.a, st.l, w);
+                        tmem_st_32x8(tP + j * (kCW / 2), w);
+                        if (j + 1 < 64 / kCW) {
+                            const bool need = cmin < st.a - (kOff1 + kTau);
+                            if (__any_sync(0xffffffffu, need)) st = p1_raise<E>(need, cmin, !seg_start, j + 1, tG, tP, st);
+                        }
+                    }
+                } else {
+                    float x[2][kCW];
+                    p2_x_fast(rb[0], c2s, kmul, rowc, x[0]);
+#pragma unroll
+                    for (int j = 0; j < 64 / kCW; ++j) {
+                        uint32_t w[kCW / 2];
+                        if (j + 1 < 64 / kCW) {
+                            tmem_ld_wait();
+                            p2_x_fast(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, rowc, x[(j + 1) & 1]);
+                            if (j + 2 < 64 / kCW) tmem_ld_32x16_issue(tS + (j + 2) * kCW, rb[j & 1]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < kCW / 2; ++i) w[i] = pack_f16x2(ex2_approx(x[j & 1][2 * i]), ex2_approx(x[j & 1][2 * i + 1]));
+                        tmem_st_32x8(tP + j * (kCW / 2), w);
+                    }
                 }
             } else {
                 const int dcol_abs = row_ok ? row + ps.d : -1;
@@ -586,7 +624,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
         }
     }
     __syncthreads();
-    if (warp == kMma1Warp) {
+    if (warp == kIssuerWarp0) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
