@@ -138,6 +138,12 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
     if (!mbar_try_a(addr, parity)) mbar_wait_slow(addr, parity);
 }
+// one lane of a converged warp (the same lane every time for the same mask)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive_a(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
 __device__ __forceinline__ void mma_commit_a(uint32_t addr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
@@ -404,8 +410,12 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
         // The first product of tile it+1 follows the second product of tile it as soon as that one has completed (P lives in the S
         // columns).  The issuers also share the TMA loads: issuer s fetches every tile j with j % NS == s, kLook tiles ahead, and the
         // pair of R panels when that tile opens a new pair (R is double buffered, so the switch does not drain the pipeline).
-        if (lane == 0) {
-            const int s = warp - kIssuerWarp0;
+        // The warp runs converged with warp-uniform values (descriptors then live in uniform registers and a tcgen05.mma costs a few
+        // issue slots; from inside a one-lane branch every operand goes through an R2UR election loop, ~100 cycles per MMA); only
+        // the tcgen05 / TMA / arrive instructions themselves are predicated on the elected lane.
+        {
+            const int s = __shfl_sync(0xffffffffu, warp, 0) - kIssuerWarp0;
+            const bool lead = elect_one();
             const int g = s / kSplit, h = s % kSplit;
             constexpr uint32_t idesc1 = make_idesc_f16(128, 64);
             constexpr uint32_t idesc2 = make_idesc_f16_bmn(128, E);
@@ -422,20 +432,25 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                 if (j % NS == s) {
                     if (newseg) {   // every stream's last first-product on the pair that used this buffer is complete
                         mbar_wait_a(b_rempty + (pk & 1) * 8, ((pk >> 1) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&bars->r_full[pk & 1], Cfg::kRBytes);
-                        for (int gg = 0; gg < 2; ++gg)
-                            for (int sl = 0; sl < Cfg::kSlabs; ++sl)
-                                tma_load_2d(sR + (pk & 1) * Cfg::kRBytes + gg * Cfg::kPanelBytes + sl * 128 * 128, &maps.r[pc.pass], &bars->r_full[pk & 1], sl * 64,
-                                            (pc.pair * 2 + gg) * 128);
+                        if (lead) {
+                            mbar_arrive_expect_tx(&bars->r_full[pk & 1], Cfg::kRBytes);
+                            for (int gg = 0; gg < 2; ++gg)
+                                for (int sl = 0; sl < Cfg::kSlabs; ++sl)
+                                    tma_load_2d(sR + (pk & 1) * Cfg::kRBytes + gg * Cfg::kPanelBytes + sl * 128 * 128, &maps.r[pc.pass], &bars->r_full[pk & 1],
+                                                sl * 64, (pc.pair * 2 + gg) * 128);
+                        }
                     }
                     const int stage = j % Cfg::kStages;
                     const int n0 = pc.tile * BN;
                     mbar_wait_a(b_tempty + stage * 8, ((j / Cfg::kStages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&bars->t_full[stage], Cfg::kTBytes + Cfg::kC2Bytes);
-                    unsigned char* dst = sT + stage * Cfg::kTBytes;
-                    for (int sl = 0; sl < Cfg::kSlabs; ++sl) tma_load_2d(dst + sl * BN * 128, &maps.t[pc.pass], &bars->t_full[stage], sl * 64, n0);
-                    bulk_copy_1d(sC2 + stage * Cfg::kC2Bytes, p.pass[pc.pass].colv2 + n0, Cfg::kC2Bytes, &bars->t_full[stage]);
-                    if (s == 0) FL_TRACE(j, 0);
+                    if (lead) {
+                        mbar_arrive_expect_tx(&bars->t_full[stage], Cfg::kTBytes + Cfg::kC2Bytes);
+                        unsigned char* dst = sT + stage * Cfg::kTBytes;
+                        for (int sl = 0; sl < Cfg::kSlabs; ++sl) tma_load_2d(dst + sl * BN * 128, &maps.t[pc.pass], &bars->t_full[stage], sl * 64, n0);
+                        bulk_copy_1d(sC2 + stage * Cfg::kC2Bytes, p.pass[pc.pass].colv2 + n0, Cfg::kC2Bytes, &bars->t_full[stage]);
+                        if (s == 0) FL_TRACE(j, 0);
+                    }
+                    __syncwarp();
                 }
                 pc.next(p);
             };
@@ -443,13 +458,17 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                 const int stage = it % Cfg::kStages;
                 const uint64_t ad0 = make_smem_desc(sR_a + (kseg & 1) * Cfg::kRBytes + g * Cfg::kPanelBytes, 16, 1024);
                 const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes + h * 64 * 128, 16, 1024);   // rows [h*64, +64) of every slab
+                if (lead) {
 #pragma unroll
-                for (int kk = 0; kk < Cfg::kMma1; ++kk) {
-                    const uint64_t ad = ad0 + (uint64_t)(((kk >> 2) * 128 * 128 + (kk & 3) * 32) >> 4);
-                    const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * BN * 128 + (kk & 3) * 32) >> 4);
-                    mma_f16(tS, ad, bd, idesc1, kk > 0 ? 1u : 0u);
+                    for (int kk = 0; kk < Cfg::kMma1; ++kk) {
+                        const uint64_t ad = ad0 + (uint64_t)(((kk >> 2) * 128 * 128 + (kk & 3) * 32) >> 4);
+                        const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * BN * 128 + (kk & 3) * 32) >> 4);
+                        mma_f16(tS, ad, bd, idesc1, kk > 0 ? 1u : 0u);
+                    }
+                    mma_commit_a(b_sfull + s * 8);
+                    if (s == 0) FL_TRACE(it, 1);
                 }
-                mma_commit_a(b_sfull + s * 8);
+                __syncwarp();
             };
             int pf = 0;
             for (; pf < Cfg::kLook && pf < my_units; ++pf) prefetch(pf);
@@ -458,7 +477,6 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             mbar_wait_a(b_tfull, 0);
             tc_fence_after();
             first_product(0, 0);
-            if (s == 0) FL_TRACE(0, 1);
             int k = -1;
             for (int it = 0; it < my_units; ++it) {
                 if (pf < my_units) prefetch(pf++);
@@ -473,16 +491,19 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                 tc_fence_after();
                 {
                     const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes, lbo, sbo);
+                    if (lead) {
 #pragma unroll
-                    for (int k2 = 0; k2 < 4; ++k2)   // 16 rows of T (2048 bytes of every slab) per instruction
-                        mma_f16_ts(tG, tS + k2 * 8, bd0 + (uint64_t)(((h * 4 + k2) * 2048) >> 4), idesc2, (!seg_start || k2 > 0) ? 1u : 0u);
-                    mma_commit_a(b_tempty + stage * 8);   // (one of NS arrivals) this stream is done with the tile and its column term
-                    if (seg_end) {
-                        mma_commit_a(b_gfull + s * 8);
-                        mma_commit_a(b_rempty + (k & 1) * 8);   // (one of NS arrivals) ... and with this pair of panels
+                        for (int k2 = 0; k2 < 4; ++k2)   // 16 rows of T (2048 bytes of every slab) per instruction
+                            mma_f16_ts(tG, tS + k2 * 8, bd0 + (uint64_t)(((h * 4 + k2) * 2048) >> 4), idesc2, (!seg_start || k2 > 0) ? 1u : 0u);
+                        mma_commit_a(b_tempty + stage * 8);   // (one of NS arrivals) this stream is done with the tile and its column term
+                        if (seg_end) {
+                            mma_commit_a(b_gfull + s * 8);
+                            mma_commit_a(b_rempty + (k & 1) * 8);   // (one of NS arrivals) ... and with this pair of panels
+                        }
+                        mma_commit_a(b_pempty + s * 8);
+                        if (s == 0) FL_TRACE(it, 7);
                     }
-                    mma_commit_a(b_pempty + s * 8);
-                    if (s == 0) FL_TRACE(it, 7);
+                    __syncwarp();
                 }
                 c.next(p);
                 if (it + 1 < my_units) {
@@ -492,7 +513,6 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                     mbar_wait_a(b_pempty + s * 8, it & 1);         // the second product has consumed P: the S columns may be refilled
                     tc_fence_after();
                     first_product(it + 1, kn);
-                    if (s == 0) FL_TRACE(it + 1, 1);
                 }
             }
         }
