@@ -119,6 +119,8 @@ static int cvt_item(CvtItem& it, const float* X, int ld, int n, int E, __half* X
     return it.xblocks + it.cblocks;
 }
 
+__host__ __device__ inline int64_t align_up_dev(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
 // ---- plan ---------------------------------------------------------------------------------------------------------------
 static inline int fl_bn(int E) { return E <= 64 ? 128 : 64; }
 static inline int fl_split(int E) { return fl_bn(E) / 64; }   // partials per (panel pair, CTA slot): one per 64-column half of the tile
@@ -247,27 +249,56 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
     }
 }
 
-// ---- combine 2: G[r][:] = 2^-kOff2 / scale_T * sum over the pair's CTA slots, in slot order -------------------------------------
-struct Comb2Side { const float* part; float* G; int ldg, nR, rows_pad, n_tiles, unit0, scal_idx; };
+// ---- combine 2: G[r][:] = 2^-kOff2 / scale_T * sum over the pair's CTA slots, in slot order, + (p_rr' - 1) T[r + d] -----------------
+// The positive (row r <-> T row r + d) is left out of the tensor-core product; its term is added here in fp32.  p - 1 comes from the
+// pass-1 combine (pm1_t, indexed by the T row: the step) or is formed from the operands and the given lse (the backward entry points).
+struct Comb2Side {
+    const float* part; float* G; int ldg, nR, rows_pad, n_tiles, unit0, scal_idx;
+    const float* T; int ldt, nT, d;
+    const float* pm1_t;
+    const float* R; int ldr; const float* rowv; const float* colv;   // natural units; null = 0
+};
 struct Comb2Args { Comb2Side s[2]; int n, E, units, grid, ksplit; const float* scal; };
 __global__ void __launch_bounds__(256) fl_combine2_kernel(const Comb2Args a) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int e4 = a.E >> 2;
     for (int k = 0; k < a.n; ++k) {
         const Comb2Side& sd = a.s[k];
-        const int64_t cnt = (int64_t)sd.nR * e4;
+        const int64_t cnt = align_up_dev((int64_t)sd.nR * e4, 256);   // sides start on block boundaries: the e4 lanes of a row stay together
         if (i < cnt) {
             const int r = (int)(i / e4), c4 = (int)(i % e4);
-            const int first = sd.unit0 + (r >> 8) * sd.n_tiles;
-            const int slots = (sk_owner(first + sd.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1) * a.ksplit;
+            const bool live = r < sd.nR;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z = 0; z < slots; ++z) {
-                const float4 v = *reinterpret_cast<const float4*>(sd.part + ((int64_t)z * sd.rows_pad + r) * a.E + 4 * c4);
-                acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+            if (live) {
+                const int first = sd.unit0 + (r >> 8) * sd.n_tiles;
+                const int slots = (sk_owner(first + sd.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1) * a.ksplit;
+                for (int z = 0; z < slots; ++z) {
+                    const float4 v = *reinterpret_cast<const float4*>(sd.part + ((int64_t)z * sd.rows_pad + r) * a.E + 4 * c4);
+                    acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+                }
             }
-            const float f = a.scal[sd.scal_idx] * 6.103515625e-05f;   // 2^-14 / scale_T (exact)
-            float* dst = sd.G + (int64_t)r * sd.ldg + 4 * c4;
-            dst[0] = acc.x * f; dst[1] = acc.y * f; dst[2] = acc.z * f; dst[3] = acc.w * f;
+            const int tr = r + sd.d;
+            const bool has_pos = live && tr >= 0 && tr < sd.nT;
+            float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_pos) tv = *reinterpret_cast<const float4*>(sd.T + (int64_t)tr * sd.ldt + 4 * c4);
+            float pm1;
+            if (sd.pm1_t) {
+                pm1 = has_pos ? sd.pm1_t[tr] : 0.f;
+            } else {   // z = R[r] . T[r + d] - rowv[r] - colv[r + d]: the e4 lanes of the row each hold four products
+                float dot = 0.f;
+                if (has_pos) {
+                    const float4 rv = *reinterpret_cast<const float4*>(sd.R + (int64_t)r * sd.ldr + 4 * c4);
+                    dot = fmaf(rv.x, tv.x, fmaf(rv.y, tv.y, fmaf(rv.z, tv.z, rv.w * tv.w)));
+                }
+                for (int o = e4 >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                pm1 = has_pos ? expf(dot - (sd.rowv ? sd.rowv[r] : 0.f) - (sd.colv ? sd.colv[tr] : 0.f)) - 1.f : 0.f;
+            }
+            if (live) {
+                const float f = a.scal[sd.scal_idx] * 6.103515625e-05f;   // 2^-14 / scale_T (exact)
+                float* dst = sd.G + (int64_t)r * sd.ldg + 4 * c4;
+                dst[0] = fmaf(acc.x, f, pm1 * tv.x); dst[1] = fmaf(acc.y, f, pm1 * tv.y);
+                dst[2] = fmaf(acc.z, f, pm1 * tv.z); dst[3] = fmaf(acc.w, f, pm1 * tv.w);
+            }
             return;
         }
         i -= cnt;
@@ -370,8 +401,8 @@ static int fl_pass1(const FlWs& w, const float* C, int ldc, int Bq, int Bc, int 
 }
 
 struct FlSide { int r_is_q; float* G; int ldg; };   // r_is_q: resident operand Q (gradient dQ) or C (gradient dC)
-static int fl_pass2(const FlWs& w, const float* bias, const float* lse, int Bq, int Bc, int E, int off, const FlSide* sides, int n, bool have_pm1,
-                    cudaStream_t st) {
+static int fl_pass2(const FlWs& w, const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E, int off,
+                    const FlSide* sides, int n, bool have_pm1, cudaStream_t st) {
     const int bn = fl_bn(E);
     int nR[2], nT[2];
     for (int i = 0; i < n; ++i) { nR[i] = sides[i].r_is_q ? Bq : Bc; nT[i] = sides[i].r_is_q ? Bc : Bq; }
@@ -394,11 +425,13 @@ static int fl_pass2(const FlWs& w, const float* bias, const float* lse, int Bq, 
         ps.nR = nR[i]; ps.nT = nT[i]; ps.m_pairs = pl.m_pairs[i]; ps.n_tiles = pl.n_tiles[i]; ps.d = rq ? off : -off; ps.unit0 = pl.unit0[i];
         ps.rowv = rq ? lse : bias; ps.colv2 = rq ? w.c2_bias : w.c2_lse;
         ps.out_g = w.p2_g[rq ? 0 : 1]; ps.out_m = nullptr; ps.out_l = nullptr; ps.out_zd = nullptr;
-        ps.diag_pm1 = (!rq && have_pm1) ? w.pm1 : nullptr;   // dC side: column n is query n, whose p_nn - 1 the pass-1 combine left in pm1
         Comb2Side& cs = ca.s[i];
         cs.part = ps.out_g; cs.G = sides[i].G; cs.ldg = sides[i].ldg; cs.nR = nR[i]; cs.rows_pad = pl.m_pairs[i] * 256; cs.n_tiles = pl.n_tiles[i];
         cs.unit0 = pl.unit0[i]; cs.scal_idx = rq ? 5 : 4;   // the streamed operand's scale: C for the dQ side, Q for the dC side
-        items += (int64_t)nR[i] * (E / 4);
+        cs.T = rq ? C : Q; cs.ldt = rq ? ldc : ldq; cs.nT = nT[i]; cs.d = ps.d;
+        cs.pm1_t = (!rq && have_pm1) ? w.pm1 : nullptr;     // dC side of a step: T row n is query n, whose p - 1 the pass-1 combine left in pm1
+        cs.R = rq ? Q : C; cs.ldr = rq ? ldq : ldc; cs.rowv = rq ? lse : bias; cs.colv = rq ? bias : lse;
+        items += align_up((size_t)nR[i] * (E / 4), 256);
     }
     int rc = launch_flash_e<kP2>(E, maps, p, pl.grid, st);
     if (rc) return rc;
@@ -422,7 +455,7 @@ int softmax_step_flash(const float* Q, int ldq, const float* C, int ldc, const f
     rc = fl_pass1(w, C, ldc, Bq, Bc, E, off, lse, loss, dQ, lddq, true, st);
     if (rc) return rc;
     FlSide side{0, dC, lddc};
-    return fl_pass2(w, bias, lse, Bq, Bc, E, off, &side, 1, true, st);
+    return fl_pass2(w, Q, ldq, C, ldc, bias, lse, Bq, Bc, E, off, &side, 1, true, st);
 }
 
 int softmax_fwd_flash(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
@@ -444,7 +477,7 @@ int softmax_bwd_flash(const float* Q, int ldq, const float* C, int ldc, const fl
     if (which == 0 || which == 2) sides[n++] = FlSide{1, G0, ldg0};
     if (which == 1) sides[n++] = FlSide{0, G0, ldg0};
     if (which == 2) sides[n++] = FlSide{0, G1, ldg1};
-    return fl_pass2(w, bias, lse, Bq, Bc, E, off, sides, n, false, st);
+    return fl_pass2(w, Q, ldq, C, ldc, bias, lse, Bq, Bc, E, off, sides, n, false, st);
 }
 
 void debug_flash(void* trace, int mn_lbo, int mn_sbo) {

@@ -27,6 +27,8 @@
 // panel; G is quiescent whenever the epilogue runs, because the stream's next product is only issued after the epilogue).
 // Every mbarrier wait is bounded.
 #pragma once
+#include <type_traits>
+
 #include "tt_tc_streamk.cuh"
 
 namespace tt {
@@ -49,7 +51,6 @@ struct FlPass {
     float* out_m;           // kP1: reference exponent (log2 units) [slot * kSplit + half][m_pairs*256]
     float* out_l;           // kP1: sum of P~ (positive excluded)   [slot * kSplit + half][m_pairs*256]
     float* out_zd;          // kP1: diagonal logit, log2 units       [m_pairs*256]
-    const float* diag_pm1;  // kP2: (p - 1) of the positive in T-row (column) n, computed without cancellation by the pass-1 combine; may be null
 };
 struct FlParams {
     FlPass pass[2];
@@ -194,14 +195,27 @@ constexpr int kCW = 16;
 // by value: a by-reference state would live in local memory in the hot loop.
 struct P1State { float a; f32x2 l; float zd; int has_diag; };
 
-// pass 1, fast chunk, phase A: zn of 16 columns and their minimum
-__device__ __forceinline__ float p1_zn_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, f32x2 (&zn)[8]) {
+// pass 1, fast chunk, phase A: zn of 16 columns and their minimum.  DIAG: the chunk may hold the row's positive (column dcol_abs);
+// it takes no part in minimum, sum or product (the combine kernel adds its contribution in fp32) and its logit is recorded.
+template <bool DIAG>
+__device__ __forceinline__ float p1_zn_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, f32x2 (&zn)[8], int nb, int dcol_abs, P1State& st) {
     const f32x2 nk = pk2(-kmul, -kmul);
 #pragma unroll
     for (int g4 = 0; g4 < 4; ++g4) {
         const float4 cc = lds128(c2s + g4 * 16);
         zn[2 * g4] = fma2(pk2(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1])), nk, pk2(cc.x, cc.y));
         zn[2 * g4 + 1] = fma2(pk2(__uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])), nk, pk2(cc.z, cc.w));
+    }
+    if (DIAG) {
+        const int dl = dcol_abs - nb;   // chunk-local column of the positive (any value outside [0, 16) when it is elsewhere)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float z0, z1;
+            upk2(zn[i], z0, z1);
+            if (dl == 2 * i) { st.zd = -z0; st.has_diag = 1; z0 = CUDART_INF_F; }
+            if (dl == 2 * i + 1) { st.zd = -z1; st.has_diag = 1; z1 = CUDART_INF_F; }
+            zn[i] = pk2(z0, z1);
+        }
     }
     float a0, a1, b0, b1;
     upk2(zn[0], a0, a1);
@@ -308,22 +322,11 @@ __device__ __noinline__ P1State p1_chunk_checked(uint32_t tS_chunk, uint32_t c2s
     return st;
 }
 
-// ---- pass 2: P' = 2^(s*kmul - c2_j - r2 + kOff2) - [diagonal] 2^kOff2 -----------------------------------------------------------
-__device__ __forceinline__ void p2_chunk_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, float rowc, uint32_t (&w)[8]) {
-    const f32x2 km = pk2(kmul, kmul), mone = pk2(-1.f, -1.f), rc = pk2(rowc, rowc);
-#pragma unroll
-    for (int g4 = 0; g4 < 4; ++g4) {
-        const float4 cc = lds128(c2s + g4 * 16);
-        const f32x2 ad0 = fma2(pk2(cc.x, cc.y), mone, rc), ad1 = fma2(pk2(cc.z, cc.w), mone, rc);
-        float a0, a1, b0, b1;
-        upk2(fma2(pk2(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1])), km, ad0), a0, a1);
-        upk2(fma2(pk2(__uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])), km, ad1), b0, b1);
-        w[2 * g4] = pack_f16x2(ex2_approx(a0), ex2_approx(a1));
-        w[2 * g4 + 1] = pack_f16x2(ex2_approx(b0), ex2_approx(b1));
-    }
-}
-// pass 2, fast chunk, exponent arguments only (the exponentials are taken one chunk later, see the epilogue's software pipeline)
-__device__ __forceinline__ void p2_x_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, float rowc, float (&x)[16]) {
+// ---- pass 2: P' = 2^(s*kmul - c2_j - r2 + kOff2), the positive left out (weight 0) ------------------------------------------------
+// pass 2, fast chunk, exponent arguments only (the exponentials are taken one chunk later, see the epilogue's software pipeline).
+// DIAG: the chunk may hold the row's positive; it is left out of the product (weight 0) and the combine kernel adds (p - 1) t in fp32.
+template <bool DIAG>
+__device__ __forceinline__ void p2_x_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, float rowc, float (&x)[16], int nb, int dcol_abs) {
     const f32x2 km = pk2(kmul, kmul), mone = pk2(-1.f, -1.f), rc = pk2(rowc, rowc);
 #pragma unroll
     for (int g4 = 0; g4 < 4; ++g4) {
@@ -332,9 +335,15 @@ __device__ __forceinline__ void p2_x_fast(const uint32_t (&r)[16], uint32_t c2s,
         upk2(fma2(pk2(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1])), km, ad0), x[4 * g4], x[4 * g4 + 1]);
         upk2(fma2(pk2(__uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])), km, ad1), x[4 * g4 + 2], x[4 * g4 + 3]);
     }
+    if (DIAG) {
+        const int dl = dcol_abs - nb;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (dl == i) x[i] = -CUDART_INF_F;
+    }
 }
 __device__ __noinline__ void p2_chunk_checked(uint32_t tS_chunk, uint32_t c2s, float kmul, float rowc, int nb, int nT, bool row_ok, int dcol_abs,
-                                              const float* __restrict__ diag_pm1, uint32_t tP_chunk) {
+                                              uint32_t tP_chunk) {
     uint32_t r[16];
     tmem_ld_32x16_issue(tS_chunk, r);
     tmem_ld_wait();
@@ -349,7 +358,7 @@ __device__ __noinline__ void p2_chunk_checked(uint32_t tS_chunk, uint32_t c2s, f
             const int i = g4 * 4 + t;
             float v = ex2_approx(fmaf(__uint_as_float(r[i]), kmul, rowc - cv[t]));
             if (nb + i >= nT || !row_ok) v = 0.f;
-            else if (nb + i == dcol_abs) v = diag_pm1 ? __ldg(diag_pm1 + nb + i) * 16384.f : v - 16384.f;   // (p - 1) 2^kOff2
+            else if (nb + i == dcol_abs) v = 0.f;   // the positive: added by the combine kernel in fp32
             pv[t] = v;
         }
         w[2 * g4] = pack_f16x2(pv[0], pv[1]);
@@ -371,6 +380,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
     const int u_begin = sk_begin(blockIdx.x, p.units, gridDim.x), u_end = sk_begin(blockIdx.x + 1, p.units, gridDim.x);
     const int my_units = u_end - u_begin;
     if (my_units <= 0) return;
+    if (p.trace && threadIdx.x == 0) p.trace[((size_t)blockIdx.x * 64 + 63) * 8 + 0] = gtime();   // CTA entry
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -420,7 +430,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             constexpr uint32_t idesc1 = make_idesc_f16(128, 64);
             constexpr uint32_t idesc2 = make_idesc_f16_bmn(128, E);
             const uint32_t sR_a = smem_u32(sR), sT_a = smem_u32(sT);
-            const uint32_t lbo = p.mn_lbo ? (uint32_t)p.mn_lbo : (uint32_t)(BN * 128), sbo = p.mn_sbo ? (uint32_t)p.mn_sbo : 1024u;
+            const uint32_t lbo = p.mn_lbo > 0 ? (uint32_t)p.mn_lbo : (uint32_t)(BN * 128), sbo = p.mn_sbo > 0 ? (uint32_t)p.mn_sbo : 1024u;
             const uint32_t tS = tmem + s * Cfg::kStreamCols, tG = tS + Cfg::kGCol;
             FlCursor c, pc;
             c.init(p, u_begin);
@@ -510,7 +520,8 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                     const int kn = k + (c.tile == 0 ? 1 : 0);      // the next tile may open a new pair of panels
                     if (kn != k) mbar_wait_a(b_rfull + (kn & 1) * 8, (kn >> 1) & 1);
                     mbar_wait_a(b_tfull + ((it + 1) % Cfg::kStages) * 8, ((it + 1) / Cfg::kStages) & 1);
-                    mbar_wait_a(b_pempty + s * 8, it & 1);         // the second product has consumed P: the S columns may be refilled
+                    if (p.mn_lbo >= 0) mbar_wait_a(b_pempty + s * 8, it & 1);   // the second product has consumed P: the S columns may be refilled
+                                                                                // (mn_lbo < 0: debug, rely on the tensor pipe executing one thread's MMAs in order)
                     tc_fence_after();
                     first_product(it + 1, kn);
                 }
@@ -550,23 +561,26 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             const int wrow0 = (c.pair * 2 + g) * 128 + q * 32;
             const int stage = it % Cfg::kStages;
             const int n0 = c.tile * BN + h * 64;                     // first column of this stream's half
-            // warp-uniform: the half is fully in range and holds no diagonal element of this warp's rows
-            const bool fast = (n0 + 64 <= ps.nT) && (wrow0 + 32 <= ps.nR) && (wrow0 + ps.d + 32 <= n0 || wrow0 + ps.d >= n0 + 64);
+            // warp-uniform: the half is fully in range (else: the checked path) / holds a diagonal element of this warp's rows
+            const bool in_range = (n0 + 64 <= ps.nT) && (wrow0 + 32 <= ps.nR) && p.mn_sbo >= 0;   // (mn_sbo < 0: debug, every chunk takes the checked path)
+            const bool has_d = !(wrow0 + ps.d + 32 <= n0 || wrow0 + ps.d >= n0 + 64);
+            const int dcol_abs = row_ok ? row + ps.d : -1;
             const uint32_t c2s = smem_u32(sC2 + stage * Cfg::kC2Bytes) + h * 256;
             mbar_wait_a(b_tfull + stage * 8, (it / Cfg::kStages) & 1);   // the staged column term (landed long ago)
             mbar_wait_a(bs_full, it & 1);
             tc_fence_after();
             if (lane == 0 && warp == 0) FL_TRACE(it, 2);
-            if (fast) {
-                // software pipeline over the four 16-column chunks: the address arithmetic of chunk j+1 (FFMA2, min) sits in the same
-                // basic block as the exponentials of chunk j, so the scheduler overlaps them and the MUFU pipe stays fed
+            // software pipeline over the four 16-column chunks: the address arithmetic of chunk j+1 (FFMA2, min) sits in the same basic
+            // block as the exponentials of chunk j, so the scheduler overlaps them and the MUFU pipe stays fed
+            auto fast_half = [&](auto diag_tag) {
+                constexpr bool DIAG = decltype(diag_tag)::value;
                 uint32_t rb[2][kCW];
                 tmem_ld_32x16_issue(tS, rb[0]);
                 tmem_ld_wait();
                 tmem_ld_32x16_issue(tS + kCW, rb[1]);
                 if constexpr (MODE == kP1) {
                     f32x2 zn[2][kCW / 2];
-                    float cmin = p1_zn_fast(rb[0], c2s, kmul, zn[0]);
+                    float cmin = p1_zn_fast<DIAG>(rb[0], c2s, kmul, zn[0], n0, dcol_abs, st);
                     {
                         const bool need = cmin < st.a - (kOff1 + kTau);   // this chunk exceeds the row's reference by more than 2^kTau
                         if (__any_sync(0xffffffffu, need)) st = p1_raise<E>(need, cmin, !seg_start, 0, tG, tP, st);
@@ -576,7 +590,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                         uint32_t w[kCW / 2];
                         if (j + 1 < 64 / kCW) {
                             tmem_ld_wait();                                                       // chunk j+1 is in registers
-                            cmin = p1_zn_fast(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, zn[(j + 1) & 1]);
+                            cmin = p1_zn_fast<DIAG>(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, zn[(j + 1) & 1], n0 + (j + 1) * kCW, dcol_abs, st);
                             if (j + 2 < 64 / kCW) tmem_ld_32x16_issue(tS + (j + 2) * kCW, rb[j & 1]);
                         }
                         p1_exp_fast(zn[j & 1], st.a, st.l, w);
@@ -588,13 +602,13 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                     }
                 } else {
                     float x[2][kCW];
-                    p2_x_fast(rb[0], c2s, kmul, rowc, x[0]);
+                    p2_x_fast<DIAG>(rb[0], c2s, kmul, rowc, x[0], n0, dcol_abs);
 #pragma unroll
                     for (int j = 0; j < 64 / kCW; ++j) {
                         uint32_t w[kCW / 2];
                         if (j + 1 < 64 / kCW) {
                             tmem_ld_wait();
-                            p2_x_fast(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, rowc, x[(j + 1) & 1]);
+                            p2_x_fast<DIAG>(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, rowc, x[(j + 1) & 1], n0 + (j + 1) * kCW, dcol_abs);
                             if (j + 2 < 64 / kCW) tmem_ld_32x16_issue(tS + (j + 2) * kCW, rb[j & 1]);
                         }
 #pragma unroll
@@ -602,14 +616,18 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                         tmem_st_32x8(tP + j * (kCW / 2), w);
                     }
                 }
+            };
+            if (in_range && !has_d) {
+                fast_half(std::false_type{});
+            } else if (in_range) {
+                fast_half(std::true_type{});
             } else {
-                const int dcol_abs = row_ok ? row + ps.d : -1;
 #pragma unroll 1
                 for (int j = 0; j < 64 / kCW; ++j) {
                     if constexpr (MODE == kP1)
                         st = p1_chunk_checked<E>(tS + j * kCW, c2s + j * kCW * 4, kmul, n0 + j * kCW, ps.nT, dcol_abs, !seg_start, j, tG, tP, st);
                     else
-                        p2_chunk_checked(tS + j * kCW, c2s + j * kCW * 4, kmul, rowc, n0 + j * kCW, ps.nT, row_ok, dcol_abs, ps.diag_pm1, tP + j * (kCW / 2));
+                        p2_chunk_checked(tS + j * kCW, c2s + j * kCW * 4, kmul, rowc, n0 + j * kCW, ps.nT, row_ok, dcol_abs, tP + j * (kCW / 2));
                 }
             }
             tmem_st_wait();
@@ -644,6 +662,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
         }
     }
     __syncthreads();
+    if (p.trace && threadIdx.x == 0) p.trace[((size_t)blockIdx.x * 64 + 63) * 8 + 1] = gtime();   // CTA exit
     if (warp == kIssuerWarp0) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);

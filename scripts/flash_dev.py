@@ -133,7 +133,21 @@ def timeline(lib, step, B, label):
     lib.tt_debug_flash(None, 0, 0)
     t = trace.cpu().numpy().reshape(148, 64, 8)
     # the trace buffer is shared by both passes of a step: the later launch (pass 2) overwrites pass 1
-    for cta in (0, 73):
+    import numpy as np
+    first = np.array([t[c, 0, 0] if t[c, 0, 0] else 0 for c in range(148)], dtype=np.int64)
+    last = t[:, :63, :].reshape(148, -1).max(axis=1)
+    live = first > 0
+    base = first[live].min()
+    print(f"  {label}: CTAs with a trace {int(live.sum())}; first TMA issue after the earliest CTA (us): median {np.median(first[live] - base) / 1e3:.2f} "
+          f"max {(first[live] - base).max() / 1e3:.2f}; last stamp: median {np.median(last[live] - base) / 1e3:.2f} max {(last[live] - base).max() / 1e3:.2f}; "
+          f"units per CTA {int((t[:, :, 3] > 0).sum(axis=1)[live].min())}..{int((t[:, :, 3] > 0).sum(axis=1)[live].max())}")
+    slow = int(np.argmax(np.where(live, last, 0)))
+    ent, ext = t[:, 63, 0][live], t[:, 63, 1][live]
+    print(f"  {label}: CTA entry after the earliest entry (us): median {np.median(ent - ent.min()) / 1e3:.2f} max {(ent - ent.min()).max() / 1e3:.2f}; "
+          f"first TMA issue after own entry: median {np.median(first[live] - ent) / 1e3:.2f}; exit after the earliest entry: median {np.median(ext - ent.min()) / 1e3:.2f} "
+          f"max {(ext - ent.min()).max() / 1e3:.2f}")
+    t[:, 63, :] = 0
+    for cta in (0, 73, slow):
         tt = t[cta]
         n = int((tt[:, 3] > 0).sum())
         if n == 0:
@@ -157,6 +171,28 @@ def main():
         check_sep(lib)
         print("ALL OK" if ok else "FAILED")
         sys.exit(0 if ok else 1)
+    if mode == "slow":   # every chunk through the checked path (cost of the out-of-line code when it is warm)
+        lib.tt_debug_flash(None, 0, -1)
+        step = timeit(lib, 8192, 64, n=5)
+        trace = torch.zeros(148 * 64 * 8, dtype=torch.int64, device="cuda")
+        lib.tt_debug_flash(trace.data_ptr(), 0, -1)
+        step()
+        torch.cuda.synchronize()
+        lib.tt_debug_flash(None, 0, 0)
+        t = trace.cpu().numpy().reshape(148, 64, 8)
+        for cta in (5, 100):
+            tt = t[cta]
+            print(f"  cta {cta} (every chunk checked): unit: s_seen -> s_done (us)")
+            print("    " + " ".join(f"{(tt[u, 3] - tt[u, 2]) / 1e3:5.2f}" for u in range(14) if tt[u, 3]))
+        return
+    if mode == "inorder":   # first product issued right behind the second one (no completion wait): parity, then time
+        lib.tt_debug_flash(None, -1, 0)
+        ok = check(lib)
+        print("in-order issue: parity", "ok" if ok else "FAILED")
+        for B in (8192, 65536):
+            timeit(lib, B, 64, n=20 if B <= 16384 else 5)
+        lib.tt_debug_flash(None, 0, 0)
+        return
     if mode == "once":   # a few steps only (under ncu)
         B = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
         timeit(lib, B, 64, n=2)
