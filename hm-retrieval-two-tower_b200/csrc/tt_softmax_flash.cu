@@ -167,7 +167,8 @@ static int launch_flash_e(int E, const FlMaps& maps, const FlParams& p, int grid
 //   L = L_off + pd,  lse = M + log2 L,  p_ii - 1 = -L_off / L  (no cancellation when the softmax is sharp),
 //   row loss = ln(1 + L_off / pd),      dQ_i = (sum_s G_s 2^(m_s - M)) / (L * scale_C) + (p_ii - 1) C[i + d]
 struct Comb1Args {
-    const float* pm; const float* pl; const float* pzd; const float* pg;
+    const float* pm; const float* pl; const float* pg;
+    const float* Q; int ldq; const float* bias;
     int nR, rows_pad, n_tiles, units, grid, unit0, E, d, ksplit;
     const float* C; int ldc;
     const float* scal;
@@ -182,10 +183,22 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
     const int rpb = 256 / e4;                                    // rows per block
     const int r = blockIdx.x * rpb + threadIdx.x / e4, c4 = threadIdx.x % e4;
     double mine = 0.0;
+    // the positive's logit from the fp32 operands: z_ii = Q[i] . C[i + d] - bias[i + d]; the e4 lanes of a row hold four products each
+    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float zd = 0.f;
+    {
+        float dot = 0.f;
+        if (r < a.nR) {
+            cv = *reinterpret_cast<const float4*>(a.C + (int64_t)(r + a.d) * a.ldc + 4 * c4);
+            const float4 qv = *reinterpret_cast<const float4*>(a.Q + (int64_t)r * a.ldq + 4 * c4);
+            dot = fmaf(qv.x, cv.x, fmaf(qv.y, cv.y, fmaf(qv.z, cv.z, qv.w * cv.w)));
+        }
+        for (int o = e4 >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (r < a.nR) zd = (dot - (a.bias ? a.bias[r + a.d] : 0.f)) * kLog2e;
+    }
     if (r < a.nR) {
         const int first = a.unit0 + (r >> 8) * a.n_tiles;
         const int slots = (sk_owner(first + a.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1) * a.ksplit;
-        const float zd = a.pzd[r];
         float M = zd;                                            // the positive takes part in the maximum
         for (int s = 0; s < slots; ++s) M = fmaxf(M, a.pm[(int64_t)s * a.rows_pad + r]);
         float Loff = 0.f;
@@ -204,7 +217,6 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
         const float pm1 = -Loff / L;                             // p_ii - 1
         if (a.dQ) {
             const float inv = a.scal[5] / L;                     // 1 / (L * scale_C)
-            const float4 cv = *reinterpret_cast<const float4*>(a.C + (int64_t)(r + a.d) * a.ldc + 4 * c4);
             float* dst = a.dQ + (int64_t)r * a.lddq + 4 * c4;
             dst[0] = fmaf(acc.x, inv, pm1 * cv.x); dst[1] = fmaf(acc.y, inv, pm1 * cv.y);
             dst[2] = fmaf(acc.z, inv, pm1 * cv.z); dst[3] = fmaf(acc.w, inv, pm1 * cv.w);
@@ -308,7 +320,7 @@ __global__ void __launch_bounds__(256) fl_combine2_kernel(const Comb2Args a) {
 // ---- workspace ------------------------------------------------------------------------------------------------------------
 struct FlWs {
     float* scal; __half* Qh; __half* Ch; float* c2_bias; float* c2_lse; float* pm1; double* block_sums; unsigned int* counter;
-    float* rowloss; float* p1_m; float* p1_l; float* p1_zd; float* p1_g; float* p2_g[2];
+    float* rowloss; float* p1_m; float* p1_l; float* p1_g; float* p2_g[2];
     size_t bytes;
 };
 // one layout for every entry point (step / forward / backward with one or both sides)
@@ -332,7 +344,6 @@ static FlWs fl_carve(void* ws, int Bq, int Bc, int E) {
     const size_t rp1 = (size_t)p1.m_pairs[0] * 256, ks = (size_t)fl_split(E);
     w.p1_m = cv.take<float>(ks * p1.slots[0] * rp1);
     w.p1_l = cv.take<float>(ks * p1.slots[0] * rp1);
-    w.p1_zd = cv.take<float>(rp1);
     w.p1_g = cv.take<float>(ks * p1.slots[0] * rp1 * E);
     // pass 2: up to two sides in one launch (dQ side: R = Q; dC side: R = C); sized for the larger of {both, either alone}
     int nRb[2] = {Bq, Bc}, nTb[2] = {Bc, Bq};
@@ -369,8 +380,8 @@ static int fl_prepare(const FlWs& w, const float* Q, int ldq, const float* C, in
     return TT_OK;
 }
 
-static int fl_pass1(const FlWs& w, const float* C, int ldc, int Bq, int Bc, int E, int off, float* lse, float* loss, float* dQ, int lddq,
-                    bool want_c2_lse, cudaStream_t st) {
+static int fl_pass1(const FlWs& w, const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse,
+                    float* loss, float* dQ, int lddq, bool want_c2_lse, cudaStream_t st) {
     const int bn = fl_bn(E);
     int nR[1] = {Bq}, nT[1] = {Bc};
     FlPlan pl = fl_plan(1, nR, nT, E);
@@ -384,11 +395,11 @@ static int fl_pass1(const FlWs& w, const float* C, int ldc, int Bq, int Bc, int 
     p.n_pass = 1; p.units = pl.units; p.kmul = w.scal + 2; p.mn_lbo = g_fl_lbo; p.mn_sbo = g_fl_sbo; p.trace = g_fl_trace;
     FlPass& ps = p.pass[0];
     ps.nR = Bq; ps.nT = Bc; ps.m_pairs = pl.m_pairs[0]; ps.n_tiles = pl.n_tiles[0]; ps.d = off; ps.unit0 = 0; ps.rowv = nullptr;
-    ps.colv2 = w.c2_bias; ps.out_g = w.p1_g; ps.out_m = w.p1_m; ps.out_l = w.p1_l; ps.out_zd = w.p1_zd;
+    ps.colv2 = w.c2_bias; ps.out_g = w.p1_g; ps.out_m = w.p1_m; ps.out_l = w.p1_l;
     rc = launch_flash_e<kP1>(E, maps, p, pl.grid, st);
     if (rc) return rc;
     Comb1Args ca{};
-    ca.pm = w.p1_m; ca.pl = w.p1_l; ca.pzd = w.p1_zd; ca.pg = w.p1_g;
+    ca.pm = w.p1_m; ca.pl = w.p1_l; ca.pg = w.p1_g; ca.Q = Q; ca.ldq = ldq; ca.bias = bias;
     ca.nR = Bq; ca.rows_pad = pl.m_pairs[0] * 256; ca.n_tiles = pl.n_tiles[0]; ca.units = pl.units; ca.grid = pl.grid; ca.unit0 = 0; ca.E = E; ca.d = off; ca.ksplit = fl_split(E);
     ca.C = C; ca.ldc = ldc; ca.scal = w.scal; ca.lse = lse; ca.rowloss = w.rowloss;
     ca.c2_lse = want_c2_lse ? w.c2_lse : nullptr; ca.c2_pad = (int)(ceil_div(Bq, bn) * bn); ca.pm1 = want_c2_lse ? w.pm1 : nullptr;
@@ -424,7 +435,7 @@ static int fl_pass2(const FlWs& w, const float* Q, int ldq, const float* C, int 
         FlPass& ps = p.pass[i];
         ps.nR = nR[i]; ps.nT = nT[i]; ps.m_pairs = pl.m_pairs[i]; ps.n_tiles = pl.n_tiles[i]; ps.d = rq ? off : -off; ps.unit0 = pl.unit0[i];
         ps.rowv = rq ? lse : bias; ps.colv2 = rq ? w.c2_bias : w.c2_lse;
-        ps.out_g = w.p2_g[rq ? 0 : 1]; ps.out_m = nullptr; ps.out_l = nullptr; ps.out_zd = nullptr;
+        ps.out_g = w.p2_g[rq ? 0 : 1]; ps.out_m = nullptr; ps.out_l = nullptr;
         Comb2Side& cs = ca.s[i];
         cs.part = ps.out_g; cs.G = sides[i].G; cs.ldg = sides[i].ldg; cs.nR = nR[i]; cs.rows_pad = pl.m_pairs[i] * 256; cs.n_tiles = pl.n_tiles[i];
         cs.unit0 = pl.unit0[i]; cs.scal_idx = rq ? 5 : 4;   // the streamed operand's scale: C for the dQ side, Q for the dC side
@@ -452,7 +463,7 @@ int softmax_step_flash(const float* Q, int ldq, const float* C, int ldc, const f
     FlWs w = fl_carve(ws, Bq, Bc, E);
     int rc = fl_prepare(w, Q, ldq, C, ldc, bias, nullptr, Bq, Bc, E, st);
     if (rc) return rc;
-    rc = fl_pass1(w, C, ldc, Bq, Bc, E, off, lse, loss, dQ, lddq, true, st);
+    rc = fl_pass1(w, Q, ldq, C, ldc, bias, Bq, Bc, E, off, lse, loss, dQ, lddq, true, st);
     if (rc) return rc;
     FlSide side{0, dC, lddc};
     return fl_pass2(w, Q, ldq, C, ldc, bias, lse, Bq, Bc, E, off, &side, 1, true, st);
@@ -463,7 +474,7 @@ int softmax_fwd_flash(const float* Q, int ldq, const float* C, int ldc, const fl
     FlWs w = fl_carve(ws, Bq, Bc, E);
     int rc = fl_prepare(w, Q, ldq, C, ldc, bias, nullptr, Bq, Bc, E, st);
     if (rc) return rc;
-    return fl_pass1(w, C, ldc, Bq, Bc, E, off, lse, loss, nullptr, 0, false, st);
+    return fl_pass1(w, Q, ldq, C, ldc, bias, Bq, Bc, E, off, lse, loss, nullptr, 0, false, st);
 }
 
 // which = 0 dQ only, 1 dC only, 2 both (G0 = dQ, G1 = dC)

@@ -49,8 +49,7 @@ struct FlPass {
     const float* colv2;     // per-T-row term * log2(e), zero padded to n_tiles*BN entries
     float* out_g;           // G partials [slot * kSplit + half][m_pairs*256][E]
     float* out_m;           // kP1: reference exponent (log2 units) [slot * kSplit + half][m_pairs*256]
-    float* out_l;           // kP1: sum of P~ (positive excluded)   [slot * kSplit + half][m_pairs*256]
-    float* out_zd;          // kP1: diagonal logit, log2 units       [m_pairs*256]
+    float* out_l;           // kP1: sum of P~ (positive excluded)    [slot * kSplit + half][m_pairs*256]
 };
 struct FlParams {
     FlPass pass[2];
@@ -193,29 +192,26 @@ constexpr int kCW = 16;
 // ---- pass 1 state of one row ----------------------------------------------------------------------------------------------
 // P~ = 2^(a - zn) with zn = c2_j - s*kmul the negated log2-domain logit; a = +inf until the first chunk.  Passed and returned
 // by value: a by-reference state would live in local memory in the hot loop.
-struct P1State { float a; f32x2 l; float zd; int has_diag; };
+struct P1State { float a; f32x2 l; };
 
-// pass 1, fast chunk, phase A: zn of 16 columns and their minimum.  DIAG: the chunk may hold the row's positive (column dcol_abs);
-// it takes no part in minimum, sum or product (the combine kernel adds its contribution in fp32) and its logit is recorded.
-template <bool DIAG>
-__device__ __forceinline__ float p1_zn_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, f32x2 (&zn)[8], int nb, int dcol_abs, P1State& st) {
+// The positive of a row (column dcol_abs) takes no part in maximum, sum or product: its logit is formed from the fp32 operands by
+// the combine kernels, which add its term there.  Inside the kernel it is masked on the raw accumulator (s = -inf gives weight 0 in
+// both passes); the block below is only entered for the (at most three) chunks per panel that hold positives of this warp's rows.
+__device__ __forceinline__ void mask_positive(uint32_t (&r)[16], int nb, int dcol_abs) {
+    const int dl = dcol_abs - nb;   // chunk-local column of the positive (outside [0, 16) when it is elsewhere)
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (dl == i) r[i] = 0xff800000u;
+}
+
+// pass 1, fast chunk, phase A: zn of 16 columns and their minimum
+__device__ __forceinline__ float p1_zn_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, f32x2 (&zn)[8]) {
     const f32x2 nk = pk2(-kmul, -kmul);
 #pragma unroll
     for (int g4 = 0; g4 < 4; ++g4) {
         const float4 cc = lds128(c2s + g4 * 16);
         zn[2 * g4] = fma2(pk2(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1])), nk, pk2(cc.x, cc.y));
         zn[2 * g4 + 1] = fma2(pk2(__uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])), nk, pk2(cc.z, cc.w));
-    }
-    if (DIAG) {
-        const int dl = dcol_abs - nb;   // chunk-local column of the positive (any value outside [0, 16) when it is elsewhere)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float z0, z1;
-            upk2(zn[i], z0, z1);
-            if (dl == 2 * i) { st.zd = -z0; st.has_diag = 1; z0 = CUDART_INF_F; }
-            if (dl == 2 * i + 1) { st.zd = -z1; st.has_diag = 1; z1 = CUDART_INF_F; }
-            zn[i] = pk2(z0, z1);
-        }
     }
     float a0, a1, b0, b1;
     upk2(zn[0], a0, a1);
@@ -303,7 +299,7 @@ __device__ __noinline__ P1State p1_chunk_checked(uint32_t tS_chunk, uint32_t c2s
             const int i = g4 * 4 + t;
             float v = fmaf(__uint_as_float(r[i]), -kmul, cv[t]);
             if (nb + i >= nT) v = CUDART_INF_F;
-            if (nb + i == dcol_abs) { st.zd = -v; st.has_diag = 1; v = CUDART_INF_F; }   // the positive takes no part in max, sum or product
+            if (nb + i == dcol_abs) v = CUDART_INF_F;   // the positive takes no part in max, sum or product
             z[i] = v;
             mn = fminf(mn, v);
         }
@@ -323,10 +319,8 @@ __device__ __noinline__ P1State p1_chunk_checked(uint32_t tS_chunk, uint32_t c2s
 }
 
 // ---- pass 2: P' = 2^(s*kmul - c2_j - r2 + kOff2), the positive left out (weight 0) ------------------------------------------------
-// pass 2, fast chunk, exponent arguments only (the exponentials are taken one chunk later, see the epilogue's software pipeline).
-// DIAG: the chunk may hold the row's positive; it is left out of the product (weight 0) and the combine kernel adds (p - 1) t in fp32.
-template <bool DIAG>
-__device__ __forceinline__ void p2_x_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, float rowc, float (&x)[16], int nb, int dcol_abs) {
+// pass 2, fast chunk, exponent arguments only (the exponentials are taken one chunk later, see the epilogue's software pipeline)
+__device__ __forceinline__ void p2_x_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, float rowc, float (&x)[16]) {
     const f32x2 km = pk2(kmul, kmul), mone = pk2(-1.f, -1.f), rc = pk2(rowc, rowc);
 #pragma unroll
     for (int g4 = 0; g4 < 4; ++g4) {
@@ -334,12 +328,6 @@ __device__ __forceinline__ void p2_x_fast(const uint32_t (&r)[16], uint32_t c2s,
         const f32x2 ad0 = fma2(pk2(cc.x, cc.y), mone, rc), ad1 = fma2(pk2(cc.z, cc.w), mone, rc);
         upk2(fma2(pk2(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1])), km, ad0), x[4 * g4], x[4 * g4 + 1]);
         upk2(fma2(pk2(__uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])), km, ad1), x[4 * g4 + 2], x[4 * g4 + 3]);
-    }
-    if (DIAG) {
-        const int dl = dcol_abs - nb;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (dl == i) x[i] = -CUDART_INF_F;
     }
 }
 __device__ __noinline__ void p2_chunk_checked(uint32_t tS_chunk, uint32_t c2s, float kmul, float rowc, int nb, int nT, bool row_ok, int dcol_abs,
@@ -542,7 +530,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
         int row = 0, part = 0, rows_pad = 0;
         bool row_ok = false;
         float kmul = 0.f;
-        P1State st{CUDART_INF_F, pk2(0.f, 0.f), 0.f, 0};
+        P1State st{CUDART_INF_F, pk2(0.f, 0.f)};
         float rowc = 0.f;   // pass 2: kOff2 - rowv*log2e
         for (int it = 0; it < my_units; ++it, c.next(p)) {
             const FlPass& ps = p.pass[c.pass];
@@ -555,7 +543,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                 rows_pad = ps.m_pairs * 256;
                 part = (blockIdx.x - sk_owner(ps.unit0 + c.pair * ps.n_tiles, p.units, gridDim.x)) * kSplit + h;
                 kmul = __ldg(p.kmul + c.pass);
-                st = P1State{CUDART_INF_F, pk2(0.f, 0.f), 0.f, 0};
+                st = P1State{CUDART_INF_F, pk2(0.f, 0.f)};
                 if (MODE == kP2) rowc = kOff2 - ((row_ok && ps.rowv) ? __ldg(ps.rowv + row) * kLog2e : 0.f);
             }
             const int wrow0 = (c.pair * 2 + g) * 128 + q * 32;
@@ -572,15 +560,18 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             if (lane == 0 && warp == 0) FL_TRACE(it, 2);
             // software pipeline over the four 16-column chunks: the address arithmetic of chunk j+1 (FFMA2, min) sits in the same basic
             // block as the exponentials of chunk j, so the scheduler overlaps them and the MUFU pipe stays fed
-            auto fast_half = [&](auto diag_tag) {
-                constexpr bool DIAG = decltype(diag_tag)::value;
+            if (in_range) {
+                // positives of this warp's rows sit in columns [dlo, dlo + 32): chunk j holds some iff it intersects that range
+                const int dlo = wrow0 + ps.d;
+                auto chunk_has_d = [&](int j) { return has_d && dlo < n0 + (j + 1) * kCW && dlo + 32 > n0 + j * kCW; };
                 uint32_t rb[2][kCW];
                 tmem_ld_32x16_issue(tS, rb[0]);
                 tmem_ld_wait();
                 tmem_ld_32x16_issue(tS + kCW, rb[1]);
+                if (chunk_has_d(0)) mask_positive(rb[0], n0, dcol_abs);
                 if constexpr (MODE == kP1) {
                     f32x2 zn[2][kCW / 2];
-                    float cmin = p1_zn_fast<DIAG>(rb[0], c2s, kmul, zn[0], n0, dcol_abs, st);
+                    float cmin = p1_zn_fast(rb[0], c2s, kmul, zn[0]);
                     {
                         const bool need = cmin < st.a - (kOff1 + kTau);   // this chunk exceeds the row's reference by more than 2^kTau
                         if (__any_sync(0xffffffffu, need)) st = p1_raise<E>(need, cmin, !seg_start, 0, tG, tP, st);
@@ -590,7 +581,8 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                         uint32_t w[kCW / 2];
                         if (j + 1 < 64 / kCW) {
                             tmem_ld_wait();                                                       // chunk j+1 is in registers
-                            cmin = p1_zn_fast<DIAG>(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, zn[(j + 1) & 1], n0 + (j + 1) * kCW, dcol_abs, st);
+                            if (chunk_has_d(j + 1)) mask_positive(rb[(j + 1) & 1], n0 + (j + 1) * kCW, dcol_abs);
+                            cmin = p1_zn_fast(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, zn[(j + 1) & 1]);
                             if (j + 2 < 64 / kCW) tmem_ld_32x16_issue(tS + (j + 2) * kCW, rb[j & 1]);
                         }
                         p1_exp_fast(zn[j & 1], st.a, st.l, w);
@@ -602,13 +594,14 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                     }
                 } else {
                     float x[2][kCW];
-                    p2_x_fast<DIAG>(rb[0], c2s, kmul, rowc, x[0], n0, dcol_abs);
+                    p2_x_fast(rb[0], c2s, kmul, rowc, x[0]);
 #pragma unroll
                     for (int j = 0; j < 64 / kCW; ++j) {
                         uint32_t w[kCW / 2];
                         if (j + 1 < 64 / kCW) {
                             tmem_ld_wait();
-                            p2_x_fast<DIAG>(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, rowc, x[(j + 1) & 1], n0 + (j + 1) * kCW, dcol_abs);
+                            if (chunk_has_d(j + 1)) mask_positive(rb[(j + 1) & 1], n0 + (j + 1) * kCW, dcol_abs);
+                            p2_x_fast(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, rowc, x[(j + 1) & 1]);
                             if (j + 2 < 64 / kCW) tmem_ld_32x16_issue(tS + (j + 2) * kCW, rb[j & 1]);
                         }
 #pragma unroll
@@ -616,11 +609,6 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                         tmem_st_32x8(tP + j * (kCW / 2), w);
                     }
                 }
-            };
-            if (in_range && !has_d) {
-                fast_half(std::false_type{});
-            } else if (in_range) {
-                fast_half(std::true_type{});
             } else {
 #pragma unroll 1
                 for (int j = 0; j < 64 / kCW; ++j) {
@@ -656,7 +644,6 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                     upk2(st.l, l0, l1);
                     ps.out_m[(int64_t)part * rows_pad + row] = -st.a;
                     ps.out_l[(int64_t)part * rows_pad + row] = l0 + l1;
-                    if (st.has_diag) ps.out_zd[row] = st.zd;
                 }
             }
         }
