@@ -10,13 +10,13 @@
 // times one BN-column tile, so the streamed tile is loaded once and used by eight MMAs.
 //
 // A unit is worked on as NS = 2 * kSplit independent STREAMS (panel of the pair, 64-column half of the tile).  A stream owns
-// 64 + E columns of tensor memory -- its half of S, with the fp16 P written over the S columns that are already in registers,
-// and its OWN accumulator G -- four epilogue warps (thread = one row = one TMEM lane) and a private online-softmax state.
-// Streams never talk to each other: the partial (reference exponent, sum, G) of every stream is merged by the combine kernel
-// exactly like the partials of two CTAs that share a panel.  The cycle of a stream is
-//     first product (S)  ->  epilogue (exponentials, P)  ->  second product (G += P . T)  ->  first product of the next tile
-// and the four streams of a CTA (16 epilogue warps, four per scheduler) interleave on the MUFU and tensor pipes.  Each stream has
-// its own MMA issuer warp, so no stream ever waits behind another one's barrier.
+// 64 + E columns of tensor memory -- TWO 32-column S buffers (its half of a tile is two sub-tiles), with the fp16 P written over
+// the S columns that are already in registers, and its OWN accumulator G -- four epilogue warps (thread = one row = one TMEM
+// lane), its own MMA issuer warp and a private online-softmax state.  Streams never talk to each other: the partial (reference
+// exponent, sum, G) of every stream is merged by the combine kernel exactly like the partials of two CTAs that share a panel.
+// Per sub-tile:  first product (S)  ->  epilogue (exponentials, P)  ->  second product (G += P . T); with two S buffers the first
+// product of sub-tile v+1 is complete before the epilogue has finished v, so the 16 epilogue warps (four per scheduler) never
+// wait for the tensor pipe and the MUFU pipe is the only limit.
 //
 // Operands are fp16 copies scaled by a per-tensor power of two (tt_softmax_flash.cu: amax -> scale), so any finite fp32 input is in
 // range; products are exact and accumulate in fp32 in TMEM.  The second product reads P from TENSOR MEMORY (A operand) and the
@@ -107,9 +107,9 @@ struct FlCfg {
 struct FlBars {
     uint64_t r_full[2], r_empty[2];
     uint64_t t_full[8], t_empty[8];
-    uint64_t s_full[4];     // first product of the stream's tile complete
-    uint64_t p_full[4];     // P of the stream's tile complete in tensor memory (4 epilogue warps)
-    uint64_t p_empty[4];    // second product complete: the stream's S/P columns may be refilled
+    uint64_t s_full[4][2];  // [stream][S buffer] first product of the sub-tile complete
+    uint64_t p_full[4][2];  // P of the sub-tile complete in tensor memory (4 epilogue warps)
+    uint64_t p_empty[4][2]; // second product complete: the buffer's columns may be refilled
     uint64_t g_full[4], g_empty[4];
     uint32_t tmem_base;
 };
@@ -386,8 +386,10 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->r_full[i], 1); mbar_init(&bars->r_empty[i], NS); }
         for (int i = 0; i < 8; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], NS); }
         for (int i = 0; i < 4; ++i) {
-            mbar_init(&bars->s_full[i], 1);
-            mbar_init(&bars->p_full[i], 4); mbar_init(&bars->p_empty[i], 1);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&bars->s_full[i][b], 1);
+                mbar_init(&bars->p_full[i][b], 4); mbar_init(&bars->p_empty[i][b], 1);
+            }
             mbar_init(&bars->g_full[i], 1); mbar_init(&bars->g_empty[i], 4);
         }
         fence_barrier_init();
@@ -398,15 +400,14 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
     const uint32_t b_rfull = smem_u32(&bars->r_full[0]), b_rempty = smem_u32(&bars->r_empty[0]), b_tfull = smem_u32(&bars->t_full[0]),
-                   b_tempty = smem_u32(&bars->t_empty[0]), b_sfull = smem_u32(&bars->s_full[0]), b_pfull = smem_u32(&bars->p_full[0]),
-                   b_pempty = smem_u32(&bars->p_empty[0]), b_gfull = smem_u32(&bars->g_full[0]), b_gempty = smem_u32(&bars->g_empty[0]);
+                   b_tempty = smem_u32(&bars->t_empty[0]), b_sfull = smem_u32(&bars->s_full[0][0]), b_pfull = smem_u32(&bars->p_full[0][0]),
+                   b_pempty = smem_u32(&bars->p_empty[0][0]), b_gfull = smem_u32(&bars->g_full[0]), b_gempty = smem_u32(&bars->g_empty[0]);
 
     if (warp >= kIssuerWarp0) {
         // ===================== issuer of stream s (one lane) =====================
-        //   first product   S_s = R_g . T[half]^T            (N = 64)
-        //   second product  G_s += P_s . T[half]              (A = P from tensor memory, B = the same tile, MN-major; K = 64 = 4 instructions)
-        // The first product of tile it+1 follows the second product of tile it as soon as that one has completed (P lives in the S
-        // columns).  The issuers also share the TMA loads: issuer s fetches every tile j with j % NS == s, kLook tiles ahead, and the
+        //   first product   S_s[sub] = R_g . T[32 rows]^T     (N = 32)
+        //   second product  G_s += P_s[sub] . T[32 rows]       (A = P from tensor memory, B = the same tile, MN-major; K = 32 = 2 instructions)
+        // The issuers also share the TMA loads: issuer s fetches every tile j with j % NS == s, kLook tiles ahead, and the
         // pair of R panels when that tile opens a new pair (R is double buffered, so the switch does not drain the pipeline).
         // The warp runs converged with warp-uniform values (descriptors then live in uniform registers and a tcgen05.mma costs a few
         // issue slots; from inside a one-lane branch every operand goes through an R2UR election loop, ~100 cycles per MMA); only
@@ -415,7 +416,6 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             const int s = __shfl_sync(0xffffffffu, warp, 0) - kIssuerWarp0;
             const bool lead = elect_one();
             const int g = s / kSplit, h = s % kSplit;
-            constexpr uint32_t idesc1 = make_idesc_f16(128, 64);
             constexpr uint32_t idesc2 = make_idesc_f16_bmn(128, E);
             const uint32_t sR_a = smem_u32(sR), sT_a = smem_u32(sT);
             const uint32_t lbo = p.mn_lbo > 0 ? (uint32_t)p.mn_lbo : (uint32_t)(BN * 128), sbo = p.mn_sbo > 0 ? (uint32_t)p.mn_sbo : 1024u;
@@ -452,67 +452,79 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                 }
                 pc.next(p);
             };
-            auto first_product = [&](int it, int kseg) {   // S_s of tile `it`, which belongs to pair number kseg of this CTA
+            // sub-tile v = 2 * tile + sub lives in S buffer `sub` of the stream (columns [sub * 32, +32) of its tensor-memory block)
+            constexpr uint32_t idesc1s = make_idesc_f16(128, 32);
+            auto first_product = [&](int it, int sub, int kseg) {   // tile `it` belongs to pair number kseg of this CTA
                 const int stage = it % Cfg::kStages;
                 const uint64_t ad0 = make_smem_desc(sR_a + (kseg & 1) * Cfg::kRBytes + g * Cfg::kPanelBytes, 16, 1024);
-                const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes + h * 64 * 128, 16, 1024);   // rows [h*64, +64) of every slab
+                const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes + (h * 64 + sub * 32) * 128, 16, 1024);   // 32 rows of every slab
                 if (lead) {
 #pragma unroll
                     for (int kk = 0; kk < Cfg::kMma1; ++kk) {
                         const uint64_t ad = ad0 + (uint64_t)(((kk >> 2) * 128 * 128 + (kk & 3) * 32) >> 4);
                         const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * BN * 128 + (kk & 3) * 32) >> 4);
-                        mma_f16(tS, ad, bd, idesc1, kk > 0 ? 1u : 0u);
+                        mma_f16(tS + sub * 32, ad, bd, idesc1s, kk > 0 ? 1u : 0u);
                     }
-                    mma_commit_a(b_sfull + s * 8);
-                    if (s == 0) FL_TRACE(it, 1);
+                    mma_commit_a(b_sfull + (s * 2 + sub) * 8);
+                    if (s == 0 && sub == 0) FL_TRACE(it, 1);
                 }
                 __syncwarp();
             };
             int pf = 0;
             for (; pf < Cfg::kLook && pf < my_units; ++pf) prefetch(pf);
-            // the first tile
+            // the first tile: both sub-tiles
             mbar_wait_a(b_rfull, 0);
             mbar_wait_a(b_tfull, 0);
             tc_fence_after();
-            first_product(0, 0);
+            first_product(0, 0, 0);
+            first_product(0, 1, 0);
+            const bool inorder = p.mn_lbo < 0;   // debug: 0 = wait for the second product's completion before refilling its buffer
             int k = -1;
             for (int it = 0; it < my_units; ++it) {
                 if (pf < my_units) prefetch(pf++);
                 const bool seg_start = (it == 0 || c.tile == 0);
-                const bool seg_end = (it == my_units - 1 || c.tile == p.pass[c.pass].n_tiles - 1);
+                const bool pair_end = (c.tile == p.pass[c.pass].n_tiles - 1);
+                const bool seg_end = (it == my_units - 1 || pair_end);
                 if (seg_start) {
                     ++k;
                     mbar_wait_a(b_gempty + s * 8, (k & 1) ^ 1);   // the epilogue has drained the previous segment's G
                 }
+                const int kn = k + (pair_end ? 1 : 0);            // pair number of the next tile
                 const int stage = it % Cfg::kStages;
-                mbar_wait_a(b_pfull + s * 8, it & 1);
-                tc_fence_after();
-                {
-                    const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes, lbo, sbo);
+                const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes, lbo, sbo);
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    mbar_wait_a(b_pfull + (s * 2 + sub) * 8, it & 1);
+                    tc_fence_after();
                     if (lead) {
 #pragma unroll
-                        for (int k2 = 0; k2 < 4; ++k2)   // 16 rows of T (2048 bytes of every slab) per instruction
-                            mma_f16_ts(tG, tS + k2 * 8, bd0 + (uint64_t)(((h * 4 + k2) * 2048) >> 4), idesc2, (!seg_start || k2 > 0) ? 1u : 0u);
-                        mma_commit_a(b_tempty + stage * 8);   // (one of NS arrivals) this stream is done with the tile and its column term
-                        if (seg_end) {
-                            mma_commit_a(b_gfull + s * 8);
-                            mma_commit_a(b_rempty + (k & 1) * 8);   // (one of NS arrivals) ... and with this pair of panels
+                        for (int k2 = 0; k2 < 2; ++k2)   // 16 rows of T (2048 bytes of every slab) per instruction
+                            mma_f16_ts(tG, tS + sub * 32 + k2 * 8, bd0 + (uint64_t)(((h * 64 + sub * 32 + k2 * 16) * 128) >> 4), idesc2,
+                                       (!seg_start || sub > 0 || k2 > 0) ? 1u : 0u);
+                        if (sub == 1) {
+                            mma_commit_a(b_tempty + stage * 8);   // (one of NS arrivals) this stream is done with the tile and its column term
+                            if (seg_end) {
+                                mma_commit_a(b_gfull + s * 8);
+                                mma_commit_a(b_rempty + (k & 1) * 8);   // (one of NS arrivals) ... and with this pair of panels
+                            }
                         }
-                        mma_commit_a(b_pempty + s * 8);
-                        if (s == 0) FL_TRACE(it, 7);
+                        mma_commit_a(b_pempty + (s * 2 + sub) * 8);
+                        if (s == 0 && sub == 1) FL_TRACE(it, 7);
                     }
                     __syncwarp();
+                    if (it + 1 < my_units) {   // refill this S buffer with the same sub-tile of the next tile
+                        if (sub == 0) {
+                            if (kn != k) mbar_wait_a(b_rfull + (kn & 1) * 8, (kn >> 1) & 1);
+                            mbar_wait_a(b_tfull + ((it + 1) % Cfg::kStages) * 8, ((it + 1) / Cfg::kStages) & 1);
+                        }
+                        // The second product reads P from this buffer.  One thread's tcgen05.mma execute in issue order, so the refill may
+                        // follow directly (inorder); otherwise wait until the second product has completed.
+                        if (!inorder) mbar_wait_a(b_pempty + (s * 2 + sub) * 8, it & 1);
+                        tc_fence_after();
+                        first_product(it + 1, sub, kn);
+                    }
                 }
                 c.next(p);
-                if (it + 1 < my_units) {
-                    const int kn = k + (c.tile == 0 ? 1 : 0);      // the next tile may open a new pair of panels
-                    if (kn != k) mbar_wait_a(b_rfull + (kn & 1) * 8, (kn >> 1) & 1);
-                    mbar_wait_a(b_tfull + ((it + 1) % Cfg::kStages) * 8, ((it + 1) / Cfg::kStages) & 1);
-                    if (p.mn_lbo >= 0) mbar_wait_a(b_pempty + s * 8, it & 1);   // the second product has consumed P: the S columns may be refilled
-                                                                                // (mn_lbo < 0: debug, rely on the tensor pipe executing one thread's MMAs in order)
-                    tc_fence_after();
-                    first_product(it + 1, kn);
-                }
             }
         }
         __syncwarp();
@@ -522,8 +534,9 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
         const int g = s / kSplit, h = s % kSplit;
         const int row_l = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t tS = tmem + lane_addr + s * Cfg::kStreamCols, tP = tS, tG = tS + Cfg::kGCol;
-        const uint32_t bs_full = b_sfull + s * 8, bp_full = b_pfull + s * 8, bg_full = b_gfull + s * 8, bg_empty = b_gempty + s * 8;
+        const uint32_t tS0 = tmem + lane_addr + s * Cfg::kStreamCols, tG = tS0 + Cfg::kGCol;
+        const uint32_t bs_full = b_sfull + s * 16, bp_full = b_pfull + s * 16, bp_empty = b_pempty + s * 16, bg_full = b_gfull + s * 8,
+                       bg_empty = b_gempty + s * 8;
         FlCursor c;
         c.init(p, u_begin);
         int k = -1;
@@ -548,80 +561,80 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             }
             const int wrow0 = (c.pair * 2 + g) * 128 + q * 32;
             const int stage = it % Cfg::kStages;
-            const int n0 = c.tile * BN + h * 64;                     // first column of this stream's half
-            // warp-uniform: the half is fully in range (else: the checked path) / holds a diagonal element of this warp's rows
-            const bool in_range = (n0 + 64 <= ps.nT) && (wrow0 + 32 <= ps.nR) && p.mn_sbo >= 0;   // (mn_sbo < 0: debug, every chunk takes the checked path)
-            const bool has_d = !(wrow0 + ps.d + 32 <= n0 || wrow0 + ps.d >= n0 + 64);
+            const int dlo = wrow0 + ps.d;                            // positives of this warp's rows sit in columns [dlo, dlo + 32)
             const int dcol_abs = row_ok ? row + ps.d : -1;
-            const uint32_t c2s = smem_u32(sC2 + stage * Cfg::kC2Bytes) + h * 256;
             mbar_wait_a(b_tfull + stage * 8, (it / Cfg::kStages) & 1);   // the staged column term (landed long ago)
-            mbar_wait_a(bs_full, it & 1);
-            tc_fence_after();
-            if (lane == 0 && warp == 0) FL_TRACE(it, 2);
-            // software pipeline over the four 16-column chunks: the address arithmetic of chunk j+1 (FFMA2, min) sits in the same basic
-            // block as the exponentials of chunk j, so the scheduler overlaps them and the MUFU pipe stays fed
-            if (in_range) {
-                // positives of this warp's rows sit in columns [dlo, dlo + 32): chunk j holds some iff it intersects that range
-                const int dlo = wrow0 + ps.d;
-                auto chunk_has_d = [&](int j) { return has_d && dlo < n0 + (j + 1) * kCW && dlo + 32 > n0 + j * kCW; };
-                uint32_t rb[2][kCW];
-                tmem_ld_32x16_issue(tS, rb[0]);
-                tmem_ld_wait();
-                tmem_ld_32x16_issue(tS + kCW, rb[1]);
-                if (chunk_has_d(0)) mask_positive(rb[0], n0, dcol_abs);
-                if constexpr (MODE == kP1) {
-                    f32x2 zn[2][kCW / 2];
-                    float cmin = p1_zn_fast(rb[0], c2s, kmul, zn[0]);
-                    {
-                        const bool need = cmin < st.a - (kOff1 + kTau);   // this chunk exceeds the row's reference by more than 2^kTau
-                        if (__any_sync(0xffffffffu, need)) st = p1_raise<E>(need, cmin, !seg_start, 0, tG, tP, st);
-                    }
 #pragma unroll
-                    for (int j = 0; j < 64 / kCW; ++j) {
-                        uint32_t w[kCW / 2];
-                        if (j + 1 < 64 / kCW) {
-                            tmem_ld_wait();                                                       // chunk j+1 is in registers
-                            if (chunk_has_d(j + 1)) mask_positive(rb[(j + 1) & 1], n0 + (j + 1) * kCW, dcol_abs);
-                            cmin = p1_zn_fast(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, zn[(j + 1) & 1]);
-                            if (j + 2 < 64 / kCW) tmem_ld_32x16_issue(tS + (j + 2) * kCW, rb[j & 1]);
-                        }
-                        p1_exp_fast(zn[j & 1], st.a, st.l, w);
-                        tmem_st_32x8(tP + j * (kCW / 2), w);
-                        if (j + 1 < 64 / kCW) {
-                            const bool need = cmin < st.a - (kOff1 + kTau);
-                            if (__any_sync(0xffffffffu, need)) st = p1_raise<E>(need, cmin, !seg_start, j + 1, tG, tP, st);
-                        }
+            for (int sub = 0; sub < 2; ++sub) {
+                const int n0 = c.tile * BN + h * 64 + sub * 32;      // first column of this sub-tile
+                const uint32_t tS = tS0 + sub * 32, tP = tS;
+                const uint32_t c2s = smem_u32(sC2 + stage * Cfg::kC2Bytes) + (h * 64 + sub * 32) * 4;
+                // warp-uniform: the sub-tile is fully in range (else: the checked path) / holds a positive of this warp's rows
+                const bool in_range = (n0 + 32 <= ps.nT) && (wrow0 + 32 <= ps.nR) && p.mn_sbo >= 0;   // (mn_sbo < 0: debug, checked path everywhere)
+                const bool has_d = dlo < n0 + 32 && dlo + 32 > n0;
+                const bool g_valid = !seg_start || sub > 0;          // a second product of this segment has been issued
+                // pass 1, rare: before G is rescaled every second product issued so far must be complete (the previous sub-tile's)
+                auto raise = [&](bool need, float cmin, int chunks_done) {
+                    if (g_valid) {
+                        mbar_wait_a(bp_empty + (sub ^ 1) * 8, (sub == 1 ? it : it - 1) & 1);
+                        tc_fence_after();
                     }
+                    st = p1_raise<E>(need, cmin, g_valid, chunks_done, tG, tP, st);
+                };
+                mbar_wait_a(bs_full + sub * 8, it & 1);
+                tc_fence_after();
+                if (sub == 0 && lane == 0 && warp == 0) FL_TRACE(it, 2);
+                if (in_range) {
+                    uint32_t r0[kCW], r1[kCW];
+                    tmem_ld_32x16_issue(tS, r0);
+                    tmem_ld_32x16_issue(tS + kCW, r1);
+                    tmem_ld_wait();
+                    if (has_d) {
+                        mask_positive(r0, n0, dcol_abs);
+                        mask_positive(r1, n0 + kCW, dcol_abs);
+                    }
+                    uint32_t w0[kCW / 2], w1[kCW / 2];
+                    if constexpr (MODE == kP1) {
+                        f32x2 zn0[kCW / 2], zn1[kCW / 2];
+                        const float cmin0 = p1_zn_fast(r0, c2s, kmul, zn0);
+                        const float cmin1 = p1_zn_fast(r1, c2s + kCW * 4, kmul, zn1);
+                        // one check for the sub-tile: raising the reference to the smaller of the two minima before either chunk is
+                        // exponentiated keeps every P~ of the sub-tile within 2^kTau of it
+                        const float cmin = fminf(cmin0, cmin1);
+                        const bool need = cmin < st.a - (kOff1 + kTau);
+                        if (__any_sync(0xffffffffu, need)) raise(need, cmin, 0);
+                        p1_exp_fast(zn0, st.a, st.l, w0);
+                        p1_exp_fast(zn1, st.a, st.l, w1);
+                    } else {
+                        float x0[kCW], x1[kCW];
+                        p2_x_fast(r0, c2s, kmul, rowc, x0);
+                        p2_x_fast(r1, c2s + kCW * 4, kmul, rowc, x1);
+#pragma unroll
+                        for (int i = 0; i < kCW / 2; ++i) w0[i] = pack_f16x2(ex2_approx(x0[2 * i]), ex2_approx(x0[2 * i + 1]));
+#pragma unroll
+                        for (int i = 0; i < kCW / 2; ++i) w1[i] = pack_f16x2(ex2_approx(x1[2 * i]), ex2_approx(x1[2 * i + 1]));
+                    }
+                    tmem_st_32x8(tP, w0);
+                    tmem_st_32x8(tP + kCW / 2, w1);
                 } else {
-                    float x[2][kCW];
-                    p2_x_fast(rb[0], c2s, kmul, rowc, x[0]);
-#pragma unroll
-                    for (int j = 0; j < 64 / kCW; ++j) {
-                        uint32_t w[kCW / 2];
-                        if (j + 1 < 64 / kCW) {
-                            tmem_ld_wait();
-                            if (chunk_has_d(j + 1)) mask_positive(rb[(j + 1) & 1], n0 + (j + 1) * kCW, dcol_abs);
-                            p2_x_fast(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, rowc, x[(j + 1) & 1]);
-                            if (j + 2 < 64 / kCW) tmem_ld_32x16_issue(tS + (j + 2) * kCW, rb[j & 1]);
+#pragma unroll 1
+                    for (int j = 0; j < 32 / kCW; ++j) {
+                        if constexpr (MODE == kP1) {
+                            if (g_valid) {   // (the checked chunk may raise the reference: G has to be quiescent)
+                                mbar_wait_a(bp_empty + (sub ^ 1) * 8, (sub == 1 ? it : it - 1) & 1);
+                                tc_fence_after();
+                            }
+                            st = p1_chunk_checked<E>(tS + j * kCW, c2s + j * kCW * 4, kmul, n0 + j * kCW, ps.nT, dcol_abs, g_valid, j, tG, tP, st);
+                        } else {
+                            p2_chunk_checked(tS + j * kCW, c2s + j * kCW * 4, kmul, rowc, n0 + j * kCW, ps.nT, row_ok, dcol_abs, tP + j * (kCW / 2));
                         }
-#pragma unroll
-                        for (int i = 0; i < kCW / 2; ++i) w[i] = pack_f16x2(ex2_approx(x[j & 1][2 * i]), ex2_approx(x[j & 1][2 * i + 1]));
-                        tmem_st_32x8(tP + j * (kCW / 2), w);
                     }
                 }
-            } else {
-#pragma unroll 1
-                for (int j = 0; j < 64 / kCW; ++j) {
-                    if constexpr (MODE == kP1)
-                        st = p1_chunk_checked<E>(tS + j * kCW, c2s + j * kCW * 4, kmul, n0 + j * kCW, ps.nT, dcol_abs, !seg_start, j, tG, tP, st);
-                    else
-                        p2_chunk_checked(tS + j * kCW, c2s + j * kCW * 4, kmul, rowc, n0 + j * kCW, ps.nT, row_ok, dcol_abs, tP + j * (kCW / 2));
-                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(bp_full + sub * 8);
             }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(bp_full);
             if (lane == 0 && warp == 0) FL_TRACE(it, 3);
             if (seg_end) {
                 mbar_wait_a(bg_full, k & 1);

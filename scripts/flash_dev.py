@@ -153,9 +153,9 @@ def timeline(lib, step, B, label):
         if n == 0:
             continue
         t0 = tt[0, 0]
-        print(f"  {label} cta {cta}: {n} traced units; us since the first TMA issue: unit: tma | mma1(g0) | s_seen(g0) | s_done(g0) | mma2(g0)")
+        print(f"  {label} cta {cta}: {n} traced units; us since the first TMA issue: unit: tma | mma1(s0) | s_seen(w0) | chunk0 chunk1 chunk2 | s_done(w0) | mma2(s0)")
         for u in list(range(min(n, 16))):
-            print(f"    {u:3d}: " + " ".join(f"{(tt[u, e] - t0) / 1e3:7.2f}" if tt[u, e] else "      -" for e in (0, 1, 2, 3, 7)))
+            print(f"    {u:3d}: " + " ".join(f"{(tt[u, e] - t0) / 1e3:7.2f}" if tt[u, e] else "      -" for e in (0, 1, 2, 4, 5, 6, 3, 7)))
 
 
 def main():
