@@ -38,6 +38,9 @@ enum FlashMode { kP1 = 0, kP2 = 1 };
 
 constexpr float kTau = 8.f;      // pass 1: a row's reference exponent may lag its true maximum by up to 2^kTau
 constexpr float kOff1 = 6.f;     // pass 1: P~ = 2^(z - ref + kOff1) <= 2^(kTau + kOff1) = 2^14 < 65504
+#ifndef TT_FLASH_POLY_PAIRS
+#define TT_FLASH_POLY_PAIRS 3
+#endif
 constexpr float kOff2 = 14.f;    // pass 2: P' = 2^(z - lse + kOff2) <= 2^14; fp16 normals then reach down to p = 2^-28
 
 struct FlPass {
@@ -75,6 +78,30 @@ struct FlCursor {
         if (++tile == p.pass[pass].n_tiles) {
             tile = 0;
             if (++pair == p.pass[pass].m_pairs) { pair = 0; ++pass; }
+        }
+    }
+};
+
+// position in the unit list with the constants of the current pass in registers (p.pass[] is read only when the pass changes)
+struct FlWalk {
+    int pass, pair, tile, n_tiles, m_pairs, n_pass;
+    __device__ __forceinline__ void init(const FlParams& p, int u) {
+        n_pass = p.n_pass;
+        pass = (p.n_pass > 1 && u >= p.pass[1].unit0) ? 1 : 0;
+        n_tiles = p.pass[pass].n_tiles;
+        m_pairs = p.pass[pass].m_pairs;
+        const int local = u - p.pass[pass].unit0;
+        pair = local / n_tiles;
+        tile = local - pair * n_tiles;
+    }
+    __device__ __forceinline__ bool last_tile() const { return tile == n_tiles - 1; }
+    __device__ __forceinline__ void next(const FlParams& p) {
+        if (++tile == n_tiles) {
+            tile = 0;
+            if (++pair == m_pairs) {
+                pair = 0;
+                if (++pass < n_pass) { n_tiles = p.pass[pass].n_tiles; m_pairs = p.pass[pass].m_pairs; }
+            }
         }
     }
 };
@@ -226,15 +253,44 @@ __device__ __forceinline__ float p1_zn_fast(const uint32_t (&r)[16], uint32_t c2
     }
     return fminf(mn0, mn1);
 }
+// 2^x of two values on the FMA pipe instead of the MUFU unit (which is the bottleneck of both passes: one exponential per logit
+// against 16 per clock and SM): Cody-Waite split x = n + f with |f| <= 0.5 by magic-number rounding, degree-4 minimax polynomial for
+// 2^f (relative error 2.7e-6 -- the result is rounded to fp16 for the second product and summed in fp32), exponent inserted with one
+// integer multiply-add.  x is clamped at -125 (2^-125 stands in for anything smaller, including the -inf of masked columns).
+__device__ __forceinline__ void ex2_poly2(f32x2 x, float& p0, float& p1) {
+    float x0, x1;
+    upk2(x, x0, x1);
+    const f32x2 xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+    const f32x2 t = add2(xc, pk2(12582912.f, 12582912.f));              // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const f32x2 f = add2(xc, fma2(t, pk2(-1.f, -1.f), pk2(12582912.f, 12582912.f)));   // x - n
+    f32x2 q = fma2(f, pk2(0.009570039808750153f, 0.009570039808750153f), pk2(0.05591772496700287f, 0.05591772496700287f));
+    q = fma2(q, f, pk2(0.240247443318367f, 0.240247443318367f));
+    q = fma2(q, f, pk2(0.6931218504905701f, 0.6931218504905701f));
+    q = fma2(q, f, pk2(0.9999992847442627f, 0.9999992847442627f));
+    float t0, t1, q0, q1;
+    upk2(t, t0, t1);
+    upk2(q, q0, q1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));   // (bits(1.5 * 2^23) << 23 == 0 mod 2^32)
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+// of the eight column pairs of a chunk, the first kPolyPairs take the polynomial, the others the MUFU unit
+constexpr int kPolyPairs = TT_FLASH_POLY_PAIRS;
+
 // pass 1, fast chunk, phase B: P~ as packed fp16, running sum (two accumulators: halves the dependent FADD2 chain)
 __device__ __forceinline__ void p1_exp_fast(const f32x2 (&zn)[8], float a, f32x2& lsum, uint32_t (&w)[8]) {
     const f32x2 mone = pk2(-1.f, -1.f), aa = pk2(a, a);
     f32x2 s1 = pk2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        float x0, x1;
-        upk2(fma2(zn[i], mone, aa), x0, x1);
-        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        float p0, p1;
+        if (i < kPolyPairs) {
+            ex2_poly2(fma2(zn[i], mone, aa), p0, p1);
+        } else {
+            float x0, x1;
+            upk2(fma2(zn[i], mone, aa), x0, x1);
+            p0 = ex2_approx(x0);
+            p1 = ex2_approx(x1);
+        }
         if (i & 1) s1 = add2(s1, pk2(p0, p1));
         else lsum = add2(lsum, pk2(p0, p1));
         w[i] = pack_f16x2(p0, p1);
@@ -319,15 +375,22 @@ __device__ __noinline__ P1State p1_chunk_checked(uint32_t tS_chunk, uint32_t c2s
 }
 
 // ---- pass 2: P' = 2^(s*kmul - c2_j - r2 + kOff2), the positive left out (weight 0) ------------------------------------------------
-// pass 2, fast chunk, exponent arguments only (the exponentials are taken one chunk later, see the epilogue's software pipeline)
-__device__ __forceinline__ void p2_x_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, float rowc, float (&x)[16]) {
+// pass 2, fast chunk: P' of 16 columns as packed fp16
+__device__ __forceinline__ void p2_chunk_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, float rowc, uint32_t (&w)[8]) {
     const f32x2 km = pk2(kmul, kmul), mone = pk2(-1.f, -1.f), rc = pk2(rowc, rowc);
 #pragma unroll
     for (int g4 = 0; g4 < 4; ++g4) {
         const float4 cc = lds128(c2s + g4 * 16);
         const f32x2 ad0 = fma2(pk2(cc.x, cc.y), mone, rc), ad1 = fma2(pk2(cc.z, cc.w), mone, rc);
-        upk2(fma2(pk2(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1])), km, ad0), x[4 * g4], x[4 * g4 + 1]);
-        upk2(fma2(pk2(__uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])), km, ad1), x[4 * g4 + 2], x[4 * g4 + 3]);
+        const f32x2 xa = fma2(pk2(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1])), km, ad0);
+        const f32x2 xb = fma2(pk2(__uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])), km, ad1);
+        float p0, p1, p2, p3;
+        if (2 * g4 < kPolyPairs) ex2_poly2(xa, p0, p1);
+        else { upk2(xa, p0, p1); p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
+        if (2 * g4 + 1 < kPolyPairs) ex2_poly2(xb, p2, p3);
+        else { upk2(xb, p2, p3); p2 = ex2_approx(p2); p3 = ex2_approx(p3); }
+        w[2 * g4] = pack_f16x2(p0, p1);
+        w[2 * g4 + 1] = pack_f16x2(p2, p3);
     }
 }
 __device__ __noinline__ void p2_chunk_checked(uint32_t tS_chunk, uint32_t c2s, float kmul, float rowc, int nb, int nT, bool row_ok, int dcol_abs,
@@ -420,7 +483,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             const uint32_t sR_a = smem_u32(sR), sT_a = smem_u32(sT);
             const uint32_t lbo = p.mn_lbo > 0 ? (uint32_t)p.mn_lbo : (uint32_t)(BN * 128), sbo = p.mn_sbo > 0 ? (uint32_t)p.mn_sbo : 1024u;
             const uint32_t tS = tmem + s * Cfg::kStreamCols, tG = tS + Cfg::kGCol;
-            FlCursor c, pc;
+            FlWalk c, pc;
             c.init(p, u_begin);
             pc = c;
             int pk = -1;   // pairs of panels met by the prefetch cursor - 1
@@ -469,6 +532,10 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                     if (s == 0 && sub == 0) FL_TRACE(it, 1);
                 }
                 __syncwarp();
+                if (p.trace && s == 0 && sub == 0) {   // debug: completion latency of the first product (blocks the issuer)
+                    mbar_wait_a(b_sfull + (s * 2 + sub) * 8, it & 1);
+                    if (lead) FL_TRACE(it, 4);
+                }
             };
             int pf = 0;
             for (; pf < Cfg::kLook && pf < my_units; ++pf) prefetch(pf);
@@ -483,7 +550,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             for (int it = 0; it < my_units; ++it) {
                 if (pf < my_units) prefetch(pf++);
                 const bool seg_start = (it == 0 || c.tile == 0);
-                const bool pair_end = (c.tile == p.pass[c.pass].n_tiles - 1);
+                const bool pair_end = c.last_tile();
                 const bool seg_end = (it == my_units - 1 || pair_end);
                 if (seg_start) {
                     ++k;
@@ -512,6 +579,10 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                         if (s == 0 && sub == 1) FL_TRACE(it, 7);
                     }
                     __syncwarp();
+                    if (p.trace && s == 0 && sub == 1) {   // debug: completion latency of the second product (blocks the issuer)
+                        mbar_wait_a(b_pempty + (s * 2 + sub) * 8, it & 1);
+                        if (lead) FL_TRACE(it, 5);
+                    }
                     if (it + 1 < my_units) {   // refill this S buffer with the same sub-tile of the next tile
                         if (sub == 0) {
                             if (kn != k) mbar_wait_a(b_rfull + (kn & 1) * 8, (kn >> 1) & 1);
@@ -532,55 +603,48 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
         // ===================== epilogue: stream s = warp / 4 (panel g, half h), TMEM lane quarter q = warp % 4 =====================
         const int s = warp >> 2, q = warp & 3;
         const int g = s / kSplit, h = s % kSplit;
-        const int row_l = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t tS0 = tmem + lane_addr + s * Cfg::kStreamCols, tG = tS0 + Cfg::kGCol;
         const uint32_t bs_full = b_sfull + s * 16, bp_full = b_pfull + s * 16, bp_empty = b_pempty + s * 16, bg_full = b_gfull + s * 8,
                        bg_empty = b_gempty + s * 8;
-        FlCursor c;
+        FlWalk c;
         c.init(p, u_begin);
         int k = -1;
-        int row = 0, part = 0, rows_pad = 0;
+        int row = 0, part = 0, rows_pad = 0, nT = 0, nR = 0, dlo = 0, dcol_abs = -1, wrow0 = 0;
         bool row_ok = false;
         float kmul = 0.f;
         P1State st{CUDART_INF_F, pk2(0.f, 0.f)};
         float rowc = 0.f;   // pass 2: kOff2 - rowv*log2e
+        const uint32_t c2s0 = smem_u32(sC2) + h * 256;
         for (int it = 0; it < my_units; ++it, c.next(p)) {
-            const FlPass& ps = p.pass[c.pass];
             const bool seg_start = (it == 0 || c.tile == 0);
-            const bool seg_end = (it == my_units - 1 || c.tile == ps.n_tiles - 1);
+            const bool seg_end = (it == my_units - 1 || c.last_tile());
+            const FlPass& ps = p.pass[c.pass];   // (only dereferenced at the ends of a segment)
             if (seg_start) {
                 ++k;
-                row = (c.pair * 2 + g) * 128 + row_l;
-                row_ok = row < ps.nR;
-                rows_pad = ps.m_pairs * 256;
-                part = (blockIdx.x - sk_owner(ps.unit0 + c.pair * ps.n_tiles, p.units, gridDim.x)) * kSplit + h;
+                nT = ps.nT; nR = ps.nR;
+                wrow0 = (c.pair * 2 + g) * 128 + q * 32;
+                row = wrow0 + lane;
+                row_ok = row < nR;
+                dlo = wrow0 + ps.d;                                  // positives of this warp's rows sit in columns [dlo, dlo + 32)
+                dcol_abs = row_ok ? row + ps.d : -1;
+                rows_pad = c.m_pairs * 256;
+                part = (blockIdx.x - sk_owner(ps.unit0 + c.pair * c.n_tiles, p.units, gridDim.x)) * kSplit + h;
                 kmul = __ldg(p.kmul + c.pass);
                 st = P1State{CUDART_INF_F, pk2(0.f, 0.f)};
                 if (MODE == kP2) rowc = kOff2 - ((row_ok && ps.rowv) ? __ldg(ps.rowv + row) * kLog2e : 0.f);
             }
-            const int wrow0 = (c.pair * 2 + g) * 128 + q * 32;
             const int stage = it % Cfg::kStages;
-            const int dlo = wrow0 + ps.d;                            // positives of this warp's rows sit in columns [dlo, dlo + 32)
-            const int dcol_abs = row_ok ? row + ps.d : -1;
-            mbar_wait_a(b_tfull + stage * 8, (it / Cfg::kStages) & 1);   // the staged column term (landed long ago)
+            // (the staged column term needs no wait of its own: S of this tile exists, so the issuer had seen the tile's TMA barrier)
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
                 const int n0 = c.tile * BN + h * 64 + sub * 32;      // first column of this sub-tile
                 const uint32_t tS = tS0 + sub * 32, tP = tS;
-                const uint32_t c2s = smem_u32(sC2 + stage * Cfg::kC2Bytes) + (h * 64 + sub * 32) * 4;
+                const uint32_t c2s = c2s0 + stage * Cfg::kC2Bytes + sub * 128;
                 // warp-uniform: the sub-tile is fully in range (else: the checked path) / holds a positive of this warp's rows
-                const bool in_range = (n0 + 32 <= ps.nT) && (wrow0 + 32 <= ps.nR) && p.mn_sbo >= 0;   // (mn_sbo < 0: debug, checked path everywhere)
+                const bool in_range = (n0 + 32 <= nT) && (wrow0 + 32 <= nR) && p.mn_sbo >= 0;   // (mn_sbo < 0: debug, checked path everywhere)
                 const bool has_d = dlo < n0 + 32 && dlo + 32 > n0;
                 const bool g_valid = !seg_start || sub > 0;          // a second product of this segment has been issued
-                // pass 1, rare: before G is rescaled every second product issued so far must be complete (the previous sub-tile's)
-                auto raise = [&](bool need, float cmin, int chunks_done) {
-                    if (g_valid) {
-                        mbar_wait_a(bp_empty + (sub ^ 1) * 8, (sub == 1 ? it : it - 1) & 1);
-                        tc_fence_after();
-                    }
-                    st = p1_raise<E>(need, cmin, g_valid, chunks_done, tG, tP, st);
-                };
                 mbar_wait_a(bs_full + sub * 8, it & 1);
                 tc_fence_after();
                 if (sub == 0 && lane == 0 && warp == 0) FL_TRACE(it, 2);
@@ -602,20 +666,23 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                         // exponentiated keeps every P~ of the sub-tile within 2^kTau of it
                         const float cmin = fminf(cmin0, cmin1);
                         const bool need = cmin < st.a - (kOff1 + kTau);
-                        if (__any_sync(0xffffffffu, need)) raise(need, cmin, 0);
+                        if (__any_sync(0xffffffffu, need)) {
+                            if (g_valid) {   // rare: before G is rescaled every second product issued so far must be complete
+                                mbar_wait_a(bp_empty + (sub ^ 1) * 8, (sub == 1 ? it : it - 1) & 1);
+                                tc_fence_after();
+                            }
+                            st = p1_raise<E>(need, cmin, g_valid, 0, tG, tP, st);
+                        }
                         p1_exp_fast(zn0, st.a, st.l, w0);
+                        tmem_st_32x8(tP, w0);
                         p1_exp_fast(zn1, st.a, st.l, w1);
+                        tmem_st_32x8(tP + kCW / 2, w1);
                     } else {
-                        float x0[kCW], x1[kCW];
-                        p2_x_fast(r0, c2s, kmul, rowc, x0);
-                        p2_x_fast(r1, c2s + kCW * 4, kmul, rowc, x1);
-#pragma unroll
-                        for (int i = 0; i < kCW / 2; ++i) w0[i] = pack_f16x2(ex2_approx(x0[2 * i]), ex2_approx(x0[2 * i + 1]));
-#pragma unroll
-                        for (int i = 0; i < kCW / 2; ++i) w1[i] = pack_f16x2(ex2_approx(x1[2 * i]), ex2_approx(x1[2 * i + 1]));
+                        p2_chunk_fast(r0, c2s, kmul, rowc, w0);
+                        tmem_st_32x8(tP, w0);
+                        p2_chunk_fast(r1, c2s + kCW * 4, kmul, rowc, w1);
+                        tmem_st_32x8(tP + kCW / 2, w1);
                     }
-                    tmem_st_32x8(tP, w0);
-                    tmem_st_32x8(tP + kCW / 2, w1);
                 } else {
 #pragma unroll 1
                     for (int j = 0; j < 32 / kCW; ++j) {
@@ -624,9 +691,9 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                                 mbar_wait_a(bp_empty + (sub ^ 1) * 8, (sub == 1 ? it : it - 1) & 1);
                                 tc_fence_after();
                             }
-                            st = p1_chunk_checked<E>(tS + j * kCW, c2s + j * kCW * 4, kmul, n0 + j * kCW, ps.nT, dcol_abs, g_valid, j, tG, tP, st);
+                            st = p1_chunk_checked<E>(tS + j * kCW, c2s + j * kCW * 4, kmul, n0 + j * kCW, nT, dcol_abs, g_valid, j, tG, tP, st);
                         } else {
-                            p2_chunk_checked(tS + j * kCW, c2s + j * kCW * 4, kmul, rowc, n0 + j * kCW, ps.nT, row_ok, dcol_abs, tP + j * (kCW / 2));
+                            p2_chunk_checked(tS + j * kCW, c2s + j * kCW * 4, kmul, rowc, n0 + j * kCW, nT, row_ok, dcol_abs, tP + j * (kCW / 2));
                         }
                     }
                 }

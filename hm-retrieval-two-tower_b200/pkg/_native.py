@@ -11,7 +11,7 @@ from typing import Optional
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG_DIR)
-LIB_PATH = os.path.join(_ROOT, "lib", "libtt.so")
+LIB_PATH = os.environ.get("TT_LIB_PATH") or os.path.join(_ROOT, "lib", "libtt.so")   # (TT_LIB_PATH: development override, e.g. a build variant)
 
 TT_IMPL_AUTO, TT_IMPL_SIMT, TT_IMPL_TC = 0, 1, 2
 TT_MAX_FEATURES, TT_MAX_SRC, TT_MAX_JOBS, TT_MAX_KS = 16, 16, 32, 8

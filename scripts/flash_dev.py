@@ -147,15 +147,25 @@ def timeline(lib, step, B, label):
           f"first TMA issue after own entry: median {np.median(first[live] - ent) / 1e3:.2f}; exit after the earliest entry: median {np.median(ext - ent.min()) / 1e3:.2f} "
           f"max {(ext - ent.min()).max() / 1e3:.2f}")
     t[:, 63, :] = 0
+    # long gaps of warp 0 between finishing one unit and seeing the next S, or inside a unit: (cta, unit, kind, gap us, at us)
+    ev = []
+    for cta in range(148):
+        for u in range(1, 16):
+            if t[cta, u, 2] and t[cta, u - 1, 3] and t[cta, u, 2] - t[cta, u - 1, 3] > 1000:
+                ev.append((cta, u, 'wait', (t[cta, u, 2] - t[cta, u - 1, 3]) / 1e3, (t[cta, u, 2] - base) / 1e3))
+        for u in range(0, 16):
+            if t[cta, u, 2] and t[cta, u, 3] and t[cta, u, 3] - t[cta, u, 2] > 2200:
+                ev.append((cta, u, 'epi', (t[cta, u, 3] - t[cta, u, 2]) / 1e3, (t[cta, u, 3] - base) / 1e3))
+    print(f"  {label}: {len(ev)} long gaps of warp 0:", ' '.join(f'({c},{u},{k},{g:.1f}us@{a:.1f})' for c, u, k, g, a in ev[:60]))
     for cta in (0, 73, slow):
         tt = t[cta]
         n = int((tt[:, 3] > 0).sum())
         if n == 0:
             continue
         t0 = tt[0, 0]
-        print(f"  {label} cta {cta}: {n} traced units; us since the first TMA issue: unit: tma | mma1(s0) | s_seen(w0) | chunk0 chunk1 chunk2 | s_done(w0) | mma2(s0)")
+        print(f"  {label} cta {cta}: {n} traced units; us since the first TMA issue: unit: tma | mma1(s0,sub0) issued, complete | s_seen(w0) | s_done(w0) | mma2(s0,sub1) issued, complete")
         for u in list(range(min(n, 16))):
-            print(f"    {u:3d}: " + " ".join(f"{(tt[u, e] - t0) / 1e3:7.2f}" if tt[u, e] else "      -" for e in (0, 1, 2, 4, 5, 6, 3, 7)))
+            print(f"    {u:3d}: " + " ".join(f"{(tt[u, e] - t0) / 1e3:7.2f}" if tt[u, e] else "      -" for e in (0, 1, 4, 2, 3, 7, 5)))
 
 
 def main():
