@@ -77,16 +77,39 @@ __global__ void __launch_bounds__(256) fl_amax_kernel(const AmaxArgs a, float* _
     }
 }
 
-// ---- operand copies and column terms ----------------------------------------------------------------------------------
+// ---- operand copies, column terms, the positives' logits ------------------------------------------------------------------
 struct CvtItem {
     const float* X; int ld, n; __half* Xh; int which;            // Xh[n][E] = fp16(X * scal[which])
     const float* colv; float* c2; int n_col, n_pad; float cmul;  // c2[j] = colv[j] * cmul (0 when colv is null), zero padded to n_pad
     int xblocks, cblocks;
 };
-struct CvtArgs { CvtItem s[3]; int n; int E; };
+// z_ii = Q[i] . C[i + off] - bias[i + off] from the fp32 operands (the positive is left out of the tensor-core products):
+// zd2[i] = z_ii * log2e for the pass-1 combine; with lse given (backward entry points) also pm1[i] = exp(z_ii - lse_i) - 1
+struct DiagItem { const float* Q; int ldq; const float* C; int ldc; const float* bias; const float* lse; int Bq, off; float* zd2; float* pm1; int blocks; };
+struct CvtArgs { CvtItem s[2]; int n; int E; DiagItem dg; };
 __global__ void __launch_bounds__(256) fl_convert_kernel(const CvtArgs a, const float* __restrict__ scal) {
     int b = blockIdx.x;
     const int e8 = a.E >> 3;
+    if (b < a.dg.blocks) {   // e8 consecutive lanes per row
+        const int64_t idx = (int64_t)b * 256 + threadIdx.x;
+        const int r = (int)(idx / e8), c8 = (int)(idx % e8);
+        float dot = 0.f;
+        if (r < a.dg.Bq) {
+            const float* q = a.dg.Q + (int64_t)r * a.dg.ldq + 8 * c8;
+            const float* c = a.dg.C + (int64_t)(r + a.dg.off) * a.dg.ldc + 8 * c8;
+            const float4 q0 = *reinterpret_cast<const float4*>(q), q1 = *reinterpret_cast<const float4*>(q + 4);
+            const float4 c0 = *reinterpret_cast<const float4*>(c), c1 = *reinterpret_cast<const float4*>(c + 4);
+            dot = fmaf(q0.x, c0.x, fmaf(q0.y, c0.y, fmaf(q0.z, c0.z, q0.w * c0.w))) + fmaf(q1.x, c1.x, fmaf(q1.y, c1.y, fmaf(q1.z, c1.z, q1.w * c1.w)));
+        }
+        for (int o = e8 >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (r < a.dg.Bq && c8 == 0) {
+            const float z = dot - (a.dg.bias ? a.dg.bias[r + a.dg.off] : 0.f);
+            a.dg.zd2[r] = z * kLog2e;
+            if (a.dg.lse) a.dg.pm1[r] = expf(z - a.dg.lse[r]) - 1.f;
+        }
+        return;
+    }
+    b -= a.dg.blocks;
     for (int i = 0; i < a.n; ++i) {
         const CvtItem& it = a.s[i];
         if (b < it.xblocks) {
@@ -118,8 +141,6 @@ static int cvt_item(CvtItem& it, const float* X, int ld, int n, int E, __half* X
     it.cblocks = c2 ? (int)ceil_div(n_pad, 256) : 0;
     return it.xblocks + it.cblocks;
 }
-
-__host__ __device__ inline int64_t align_up_dev(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 // ---- plan ---------------------------------------------------------------------------------------------------------------
 static inline int fl_bn(int E) { return E <= 64 ? 128 : 64; }
@@ -162,13 +183,15 @@ static int launch_flash_e(int E, const FlMaps& maps, const FlParams& p, int grid
     return launch_flash<MODE, 128>(maps, p, grid, st, MODE == kP1 ? "flash_kernel<p1,128>" : "flash_kernel<p2,128>");
 }
 
-// ---- combine 1: per-row merge of the pass-1 partials in slot order -> lse, row loss, loss, dQ, lse column term ---------------------
-// One thread per (row, 4 columns).  The positive was left out of the sums: with L_off = sum_s l_s 2^(m_s - M), pd = 2^(zd - M),
+// Partial G blocks are stored [part][E/4][rows] as float4, so that the flush of a segment (thread = row) and the merges below
+// (thread = row, blockIdx.y = float4 column) touch consecutive rows with consecutive lanes.
+
+// ---- combine 1: per-row merge of the pass-1 partials in slot order -> lse, row loss, loss, dQ, lse column term, p_ii - 1 -------------
+// The positive was left out of the sums: with L_off = sum_s l_s 2^(m_s - M), pd = 2^(zd - M) (zd from the fp32 operands),
 //   L = L_off + pd,  lse = M + log2 L,  p_ii - 1 = -L_off / L  (no cancellation when the softmax is sharp),
 //   row loss = ln(1 + L_off / pd),      dQ_i = (sum_s G_s 2^(m_s - M)) / (L * scale_C) + (p_ii - 1) C[i + d]
 struct Comb1Args {
-    const float* pm; const float* pl; const float* pg;
-    const float* Q; int ldq; const float* bias;
+    const float* pm; const float* pl; const float4* pg; const float* zd2;
     int nR, rows_pad, n_tiles, units, grid, unit0, E, d, ksplit;
     const float* C; int ldc;
     const float* scal;
@@ -180,34 +203,21 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
     __shared__ double s_sum[256];
     __shared__ bool s_last;
     const int e4 = a.E >> 2;
-    const int rpb = 256 / e4;                                    // rows per block
-    const int r = blockIdx.x * rpb + threadIdx.x / e4, c4 = threadIdx.x % e4;
+    const int r = blockIdx.x * 256 + threadIdx.x, c4 = blockIdx.y;
     double mine = 0.0;
-    // the positive's logit from the fp32 operands: z_ii = Q[i] . C[i + d] - bias[i + d]; the e4 lanes of a row hold four products each
-    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-    float zd = 0.f;
-    {
-        float dot = 0.f;
-        if (r < a.nR) {
-            cv = *reinterpret_cast<const float4*>(a.C + (int64_t)(r + a.d) * a.ldc + 4 * c4);
-            const float4 qv = *reinterpret_cast<const float4*>(a.Q + (int64_t)r * a.ldq + 4 * c4);
-            dot = fmaf(qv.x, cv.x, fmaf(qv.y, cv.y, fmaf(qv.z, cv.z, qv.w * cv.w)));
-        }
-        for (int o = e4 >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        if (r < a.nR) zd = (dot - (a.bias ? a.bias[r + a.d] : 0.f)) * kLog2e;
-    }
     if (r < a.nR) {
         const int first = a.unit0 + (r >> 8) * a.n_tiles;
-        const int slots = (sk_owner(first + a.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1) * a.ksplit;
+        const int parts = (sk_owner(first + a.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1) * a.ksplit;
+        const float zd = a.zd2[r];
         float M = zd;                                            // the positive takes part in the maximum
-        for (int s = 0; s < slots; ++s) M = fmaxf(M, a.pm[(int64_t)s * a.rows_pad + r]);
+        for (int s = 0; s < parts; ++s) M = fmaxf(M, a.pm[(int64_t)s * a.rows_pad + r]);
         float Loff = 0.f;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < slots; ++s) {
+        for (int s = 0; s < parts; ++s) {
             const float w = exp2f(a.pm[(int64_t)s * a.rows_pad + r] - M);
             Loff = fmaf(a.pl[(int64_t)s * a.rows_pad + r], w, Loff);
             if (a.dQ) {
-                const float4 g = *reinterpret_cast<const float4*>(a.pg + ((int64_t)s * a.rows_pad + r) * a.E + 4 * c4);
+                const float4 g = a.pg[((int64_t)s * e4 + c4) * a.rows_pad + r];
                 acc.x = fmaf(g.x, w, acc.x); acc.y = fmaf(g.y, w, acc.y); acc.z = fmaf(g.z, w, acc.z); acc.w = fmaf(g.w, w, acc.w);
             }
         }
@@ -217,9 +227,9 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
         const float pm1 = -Loff / L;                             // p_ii - 1
         if (a.dQ) {
             const float inv = a.scal[5] / L;                     // 1 / (L * scale_C)
-            float* dst = a.dQ + (int64_t)r * a.lddq + 4 * c4;
-            dst[0] = fmaf(acc.x, inv, pm1 * cv.x); dst[1] = fmaf(acc.y, inv, pm1 * cv.y);
-            dst[2] = fmaf(acc.z, inv, pm1 * cv.z); dst[3] = fmaf(acc.w, inv, pm1 * cv.w);
+            const float4 cv = *reinterpret_cast<const float4*>(a.C + (int64_t)(r + a.d) * a.ldc + 4 * c4);
+            *reinterpret_cast<float4*>(a.dQ + (int64_t)r * a.lddq + 4 * c4) =
+                make_float4(fmaf(acc.x, inv, pm1 * cv.x), fmaf(acc.y, inv, pm1 * cv.y), fmaf(acc.z, inv, pm1 * cv.z), fmaf(acc.w, inv, pm1 * cv.w));
         }
         if (c4 == 0) {
             a.lse[r] = lse2 * kLn2;
@@ -232,6 +242,7 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
     } else if (a.c2_lse && c4 == 0 && r < a.c2_pad) {
         a.c2_lse[r] = 0.f;
     }
+    if (c4 != 0) return;   // (uniform per block) the loss is summed by the blocks of float4 column 0
     s_sum[threadIdx.x] = mine;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -261,65 +272,49 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
     }
 }
 
-// ---- combine 2: G[r][:] = 2^-kOff2 / scale_T * sum over the pair's CTA slots, in slot order, + (p_rr' - 1) T[r + d] -----------------
-// The positive (row r <-> T row r + d) is left out of the tensor-core product; its term is added here in fp32.  p - 1 comes from the
-// pass-1 combine (pm1_t, indexed by the T row: the step) or is formed from the operands and the given lse (the backward entry points).
+// ---- combine 2: G[r][:] = 2^-kOff2 / scale_T * sum over the pair's CTA slots, in slot order, + (p - 1) T[r + d] ----------------------
+// The positive (row r <-> T row r + d) is left out of the tensor-core product; its term is added here in fp32.  p - 1 is indexed by
+// the QUERY of the pair: the pass-1 combine wrote it (step), or the convert kernel formed it from the given lse (backward).
 struct Comb2Side {
-    const float* part; float* G; int ldg, nR, rows_pad, n_tiles, unit0, scal_idx;
+    const float4* part; float* G; int ldg, nR, rows_pad, n_tiles, unit0, scal_idx, rblocks;
     const float* T; int ldt, nT, d;
-    const float* pm1_t;
-    const float* R; int ldr; const float* rowv; const float* colv;   // natural units; null = 0
+    const float* pm1_q; int q_is_row;   // query index of row r: r (dQ side) or r + d (dC side)
 };
 struct Comb2Args { Comb2Side s[2]; int n, E, units, grid, ksplit; const float* scal; };
 __global__ void __launch_bounds__(256) fl_combine2_kernel(const Comb2Args a) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int e4 = a.E >> 2;
+    int rb = blockIdx.x;
+    const int e4 = a.E >> 2, c4 = blockIdx.y;
     for (int k = 0; k < a.n; ++k) {
         const Comb2Side& sd = a.s[k];
-        const int64_t cnt = align_up_dev((int64_t)sd.nR * e4, 256);   // sides start on block boundaries: the e4 lanes of a row stay together
-        if (i < cnt) {
-            const int r = (int)(i / e4), c4 = (int)(i % e4);
-            const bool live = r < sd.nR;
+        if (rb < sd.rblocks) {
+            const int r = rb * 256 + threadIdx.x;
+            if (r >= sd.nR) return;
+            const int first = sd.unit0 + (r >> 8) * sd.n_tiles;
+            const int parts = (sk_owner(first + sd.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1) * a.ksplit;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) {
-                const int first = sd.unit0 + (r >> 8) * sd.n_tiles;
-                const int slots = (sk_owner(first + sd.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1) * a.ksplit;
-                for (int z = 0; z < slots; ++z) {
-                    const float4 v = *reinterpret_cast<const float4*>(sd.part + ((int64_t)z * sd.rows_pad + r) * a.E + 4 * c4);
-                    acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
-                }
+            for (int z = 0; z < parts; ++z) {
+                const float4 v = sd.part[((int64_t)z * e4 + c4) * sd.rows_pad + r];
+                acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
             }
             const int tr = r + sd.d;
-            const bool has_pos = live && tr >= 0 && tr < sd.nT;
             float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_pos) tv = *reinterpret_cast<const float4*>(sd.T + (int64_t)tr * sd.ldt + 4 * c4);
-            float pm1;
-            if (sd.pm1_t) {
-                pm1 = has_pos ? sd.pm1_t[tr] : 0.f;
-            } else {   // z = R[r] . T[r + d] - rowv[r] - colv[r + d]: the e4 lanes of the row each hold four products
-                float dot = 0.f;
-                if (has_pos) {
-                    const float4 rv = *reinterpret_cast<const float4*>(sd.R + (int64_t)r * sd.ldr + 4 * c4);
-                    dot = fmaf(rv.x, tv.x, fmaf(rv.y, tv.y, fmaf(rv.z, tv.z, rv.w * tv.w)));
-                }
-                for (int o = e4 >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-                pm1 = has_pos ? expf(dot - (sd.rowv ? sd.rowv[r] : 0.f) - (sd.colv ? sd.colv[tr] : 0.f)) - 1.f : 0.f;
+            float pm1 = 0.f;
+            if (tr >= 0 && tr < sd.nT) {
+                tv = *reinterpret_cast<const float4*>(sd.T + (int64_t)tr * sd.ldt + 4 * c4);
+                pm1 = sd.pm1_q[sd.q_is_row ? r : tr];
             }
-            if (live) {
-                const float f = a.scal[sd.scal_idx] * 6.103515625e-05f;   // 2^-14 / scale_T (exact)
-                float* dst = sd.G + (int64_t)r * sd.ldg + 4 * c4;
-                dst[0] = fmaf(acc.x, f, pm1 * tv.x); dst[1] = fmaf(acc.y, f, pm1 * tv.y);
-                dst[2] = fmaf(acc.z, f, pm1 * tv.z); dst[3] = fmaf(acc.w, f, pm1 * tv.w);
-            }
+            const float f = a.scal[sd.scal_idx] * 6.103515625e-05f;   // 2^-14 / scale_T (exact)
+            *reinterpret_cast<float4*>(sd.G + (int64_t)r * sd.ldg + 4 * c4) =
+                make_float4(fmaf(acc.x, f, pm1 * tv.x), fmaf(acc.y, f, pm1 * tv.y), fmaf(acc.z, f, pm1 * tv.z), fmaf(acc.w, f, pm1 * tv.w));
             return;
         }
-        i -= cnt;
+        rb -= sd.rblocks;
     }
 }
 
 // ---- workspace ------------------------------------------------------------------------------------------------------------
 struct FlWs {
-    float* scal; __half* Qh; __half* Ch; float* c2_bias; float* c2_lse; float* pm1; double* block_sums; unsigned int* counter;
+    float* scal; __half* Qh; __half* Ch; float* c2_bias; float* c2_lse; float* pm1; float* zd2; double* block_sums; unsigned int* counter;
     float* rowloss; float* p1_m; float* p1_l; float* p1_g; float* p2_g[2];
     size_t bytes;
 };
@@ -336,7 +331,8 @@ static FlWs fl_carve(void* ws, int Bq, int Bc, int E) {
     w.c2_bias = cv.take<float>((size_t)pad_c);
     w.c2_lse = cv.take<float>((size_t)pad_q);
     w.pm1 = cv.take<float>((size_t)pad_q);
-    w.block_sums = cv.take<double>((size_t)ceil_div((int64_t)Bq * (E / 4), 256) + 64);
+    w.zd2 = cv.take<float>((size_t)pad_q);
+    w.block_sums = cv.take<double>((size_t)ceil_div(Bq, 256) + 64);
     w.counter = reinterpret_cast<unsigned int*>(w.scal) + 11;     // zeroed with the amax words by fl_prepare's memset
     // pass 1: R = Q, T = C
     int nR1[1] = {Bq}, nT1[1] = {Bc};
@@ -360,7 +356,7 @@ size_t softmax_flash_workspace(int Bq, int Bc, int E) { return fl_carve(nullptr,
 
 // amax -> scales, fp16 copies, column terms
 static int fl_prepare(const FlWs& w, const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E,
-                      cudaStream_t st) {
+                      int off, cudaStream_t st) {
     const int bn = fl_bn(E);
     TT_CUDA_OK(cudaMemsetAsync(w.scal + 8, 0, 16, st));          // amax bits, ticket
     AmaxArgs aa{};
@@ -372,7 +368,8 @@ static int fl_prepare(const FlWs& w, const float* Q, int ldq, const float* C, in
     TT_LAUNCH_OK("fl_amax_kernel");
     CvtArgs ca{};
     ca.E = E;
-    int cb = 0;
+    ca.dg = DiagItem{Q, ldq, C, ldc, bias, lse, Bq, off, w.zd2, w.pm1, (int)ceil_div((int64_t)Bq * (E / 8), 256)};
+    int cb = ca.dg.blocks;
     cb += cvt_item(ca.s[ca.n++], Q, ldq, Bq, E, w.Qh, 0, lse, lse ? w.c2_lse : nullptr, Bq, (int)(ceil_div(Bq, bn) * bn), kLog2e);
     cb += cvt_item(ca.s[ca.n++], C, ldc, Bc, E, w.Ch, 1, bias, w.c2_bias, Bc, (int)(ceil_div(Bc, bn) * bn), kLog2e);
     fl_convert_kernel<<<(unsigned)cb, 256, 0, st>>>(ca, w.scal);
@@ -380,8 +377,8 @@ static int fl_prepare(const FlWs& w, const float* Q, int ldq, const float* C, in
     return TT_OK;
 }
 
-static int fl_pass1(const FlWs& w, const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse,
-                    float* loss, float* dQ, int lddq, bool want_c2_lse, cudaStream_t st) {
+static int fl_pass1(const FlWs& w, const float* C, int ldc, int Bq, int Bc, int E, int off, float* lse, float* loss, float* dQ, int lddq,
+                    bool want_c2_lse, cudaStream_t st) {
     const int bn = fl_bn(E);
     int nR[1] = {Bq}, nT[1] = {Bc};
     FlPlan pl = fl_plan(1, nR, nT, E);
@@ -399,21 +396,20 @@ static int fl_pass1(const FlWs& w, const float* Q, int ldq, const float* C, int 
     rc = launch_flash_e<kP1>(E, maps, p, pl.grid, st);
     if (rc) return rc;
     Comb1Args ca{};
-    ca.pm = w.p1_m; ca.pl = w.p1_l; ca.pg = w.p1_g; ca.Q = Q; ca.ldq = ldq; ca.bias = bias;
+    ca.pm = w.p1_m; ca.pl = w.p1_l; ca.pg = reinterpret_cast<const float4*>(w.p1_g); ca.zd2 = w.zd2;
     ca.nR = Bq; ca.rows_pad = pl.m_pairs[0] * 256; ca.n_tiles = pl.n_tiles[0]; ca.units = pl.units; ca.grid = pl.grid; ca.unit0 = 0; ca.E = E; ca.d = off; ca.ksplit = fl_split(E);
     ca.C = C; ca.ldc = ldc; ca.scal = w.scal; ca.lse = lse; ca.rowloss = w.rowloss;
     ca.c2_lse = want_c2_lse ? w.c2_lse : nullptr; ca.c2_pad = (int)(ceil_div(Bq, bn) * bn); ca.pm1 = want_c2_lse ? w.pm1 : nullptr;
     ca.dQ = dQ; ca.lddq = lddq; ca.block_sums = w.block_sums; ca.counter = w.counter; ca.loss = loss;
-    const int rpb = 256 / (E / 4);
     const int rows_c = ca.c2_pad > Bq ? ca.c2_pad : Bq;
-    fl_combine1_kernel<<<(unsigned)ceil_div(rows_c, rpb), 256, 0, st>>>(ca);
+    fl_combine1_kernel<<<dim3((unsigned)ceil_div(rows_c, 256), (unsigned)(E / 4)), 256, 0, st>>>(ca);
     TT_LAUNCH_OK("fl_combine1_kernel");
     return TT_OK;
 }
 
 struct FlSide { int r_is_q; float* G; int ldg; };   // r_is_q: resident operand Q (gradient dQ) or C (gradient dC)
 static int fl_pass2(const FlWs& w, const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E, int off,
-                    const FlSide* sides, int n, bool have_pm1, cudaStream_t st) {
+                    const FlSide* sides, int n, cudaStream_t st) {
     const int bn = fl_bn(E);
     int nR[2], nT[2];
     for (int i = 0; i < n; ++i) { nR[i] = sides[i].r_is_q ? Bq : Bc; nT[i] = sides[i].r_is_q ? Bc : Bq; }
@@ -425,7 +421,7 @@ static int fl_pass2(const FlWs& w, const float* Q, int ldq, const float* C, int 
     p.n_pass = n; p.units = pl.units; p.kmul = w.scal + 2; p.mn_lbo = g_fl_lbo; p.mn_sbo = g_fl_sbo; p.trace = g_fl_trace;
     Comb2Args ca{};
     ca.n = n; ca.E = E; ca.units = pl.units; ca.grid = pl.grid; ca.ksplit = fl_split(E); ca.scal = w.scal;
-    int64_t items = 0;
+    int rblocks = 0;
     for (int i = 0; i < n; ++i) {
         const bool rq = sides[i].r_is_q != 0;
         int rc = make_tmap_2d_f16(&maps.r[i], rq ? w.Qh : w.Ch, nR[i], E, E, 128);
@@ -437,16 +433,16 @@ static int fl_pass2(const FlWs& w, const float* Q, int ldq, const float* C, int 
         ps.rowv = rq ? lse : bias; ps.colv2 = rq ? w.c2_bias : w.c2_lse;
         ps.out_g = w.p2_g[rq ? 0 : 1]; ps.out_m = nullptr; ps.out_l = nullptr;
         Comb2Side& cs = ca.s[i];
-        cs.part = ps.out_g; cs.G = sides[i].G; cs.ldg = sides[i].ldg; cs.nR = nR[i]; cs.rows_pad = pl.m_pairs[i] * 256; cs.n_tiles = pl.n_tiles[i];
+        cs.part = reinterpret_cast<const float4*>(ps.out_g); cs.G = sides[i].G; cs.ldg = sides[i].ldg; cs.nR = nR[i]; cs.rows_pad = pl.m_pairs[i] * 256;
+        cs.n_tiles = pl.n_tiles[i]; cs.rblocks = (int)ceil_div(nR[i], 256);
         cs.unit0 = pl.unit0[i]; cs.scal_idx = rq ? 5 : 4;   // the streamed operand's scale: C for the dQ side, Q for the dC side
         cs.T = rq ? C : Q; cs.ldt = rq ? ldc : ldq; cs.nT = nT[i]; cs.d = ps.d;
-        cs.pm1_t = (!rq && have_pm1) ? w.pm1 : nullptr;     // dC side of a step: T row n is query n, whose p - 1 the pass-1 combine left in pm1
-        cs.R = rq ? Q : C; cs.ldr = rq ? ldq : ldc; cs.rowv = rq ? lse : bias; cs.colv = rq ? bias : lse;
-        items += align_up((size_t)nR[i] * (E / 4), 256);
+        cs.pm1_q = w.pm1; cs.q_is_row = rq ? 1 : 0;
+        rblocks += cs.rblocks;
     }
     int rc = launch_flash_e<kP2>(E, maps, p, pl.grid, st);
     if (rc) return rc;
-    fl_combine2_kernel<<<(unsigned)ceil_div(items, 256), 256, 0, st>>>(ca);
+    fl_combine2_kernel<<<dim3((unsigned)rblocks, (unsigned)(E / 4)), 256, 0, st>>>(ca);
     TT_LAUNCH_OK("fl_combine2_kernel");
     return TT_OK;
 }
@@ -461,34 +457,34 @@ size_t softmax_flash_workspace_bytes(int Bq, int Bc, int E) { return tc::softmax
 int softmax_step_flash(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
                        float* dQ, int lddq, float* dC, int lddc, float* ws, cudaStream_t st) {
     FlWs w = fl_carve(ws, Bq, Bc, E);
-    int rc = fl_prepare(w, Q, ldq, C, ldc, bias, nullptr, Bq, Bc, E, st);
+    int rc = fl_prepare(w, Q, ldq, C, ldc, bias, nullptr, Bq, Bc, E, off, st);
     if (rc) return rc;
-    rc = fl_pass1(w, Q, ldq, C, ldc, bias, Bq, Bc, E, off, lse, loss, dQ, lddq, true, st);
+    rc = fl_pass1(w, C, ldc, Bq, Bc, E, off, lse, loss, dQ, lddq, true, st);
     if (rc) return rc;
     FlSide side{0, dC, lddc};
-    return fl_pass2(w, Q, ldq, C, ldc, bias, lse, Bq, Bc, E, off, &side, 1, true, st);
+    return fl_pass2(w, Q, ldq, C, ldc, bias, lse, Bq, Bc, E, off, &side, 1, st);
 }
 
 int softmax_fwd_flash(const float* Q, int ldq, const float* C, int ldc, const float* bias, int Bq, int Bc, int E, int off, float* lse, float* loss,
                       float* ws, cudaStream_t st) {
     FlWs w = fl_carve(ws, Bq, Bc, E);
-    int rc = fl_prepare(w, Q, ldq, C, ldc, bias, nullptr, Bq, Bc, E, st);
+    int rc = fl_prepare(w, Q, ldq, C, ldc, bias, nullptr, Bq, Bc, E, off, st);
     if (rc) return rc;
-    return fl_pass1(w, Q, ldq, C, ldc, bias, Bq, Bc, E, off, lse, loss, nullptr, 0, false, st);
+    return fl_pass1(w, C, ldc, Bq, Bc, E, off, lse, loss, nullptr, 0, false, st);
 }
 
 // which = 0 dQ only, 1 dC only, 2 both (G0 = dQ, G1 = dC)
 int softmax_bwd_flash(const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E, int off, int which,
                       float* G0, int ldg0, float* G1, int ldg1, float* ws, cudaStream_t st) {
     FlWs w = fl_carve(ws, Bq, Bc, E);
-    int rc = fl_prepare(w, Q, ldq, C, ldc, bias, lse, Bq, Bc, E, st);
+    int rc = fl_prepare(w, Q, ldq, C, ldc, bias, lse, Bq, Bc, E, off, st);
     if (rc) return rc;
     FlSide sides[2];
     int n = 0;
     if (which == 0 || which == 2) sides[n++] = FlSide{1, G0, ldg0};
     if (which == 1) sides[n++] = FlSide{0, G0, ldg0};
     if (which == 2) sides[n++] = FlSide{0, G1, ldg1};
-    return fl_pass2(w, Q, ldq, C, ldc, bias, lse, Bq, Bc, E, off, sides, n, false, st);
+    return fl_pass2(w, Q, ldq, C, ldc, bias, lse, Bq, Bc, E, off, sides, n, st);
 }
 
 void debug_flash(void* trace, int mn_lbo, int mn_sbo) {

@@ -39,7 +39,7 @@ enum FlashMode { kP1 = 0, kP2 = 1 };
 constexpr float kTau = 8.f;      // pass 1: a row's reference exponent may lag its true maximum by up to 2^kTau
 constexpr float kOff1 = 6.f;     // pass 1: P~ = 2^(z - ref + kOff1) <= 2^(kTau + kOff1) = 2^14 < 65504
 #ifndef TT_FLASH_POLY_PAIRS
-#define TT_FLASH_POLY_PAIRS 3
+#define TT_FLASH_POLY_PAIRS 0   // measured: any share on the polynomial is slower -- the passes are issue-bound, not MUFU-bound
 #endif
 constexpr float kOff2 = 14.f;    // pass 2: P' = 2^(z - lse + kOff2) <= 2^14; fp16 normals then reach down to p = 2^-28
 
@@ -50,7 +50,7 @@ struct FlPass {
     int unit0;
     const float* rowv;      // kP2: per-R-row term, natural units (lse or ln p); may be null
     const float* colv2;     // per-T-row term * log2(e), zero padded to n_tiles*BN entries
-    float* out_g;           // G partials [slot * kSplit + half][m_pairs*256][E]
+    float* out_g;           // G partials [slot * kSplit + half][E / 4][m_pairs*256] as float4 (the flush writes consecutive rows per float4 column)
     float* out_m;           // kP1: reference exponent (log2 units) [slot * kSplit + half][m_pairs*256]
     float* out_l;           // kP1: sum of P~ (positive excluded)    [slot * kSplit + half][m_pairs*256]
 };
@@ -710,10 +710,10 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                 for (int cg = 0; cg < E / 32; ++cg) {
                     float v[32];
                     tmem_ld_32x32(tG + cg * 32, v);
-                    if (row_ok) {
-                        float4* dst = reinterpret_cast<float4*>(ps.out_g + ((int64_t)part * rows_pad + row) * E + cg * 32);
+                    if (row_ok) {   // 32 lanes = 32 consecutive rows of one float4 column: 512 contiguous bytes per store instruction
+                        float4* dst = reinterpret_cast<float4*>(ps.out_g) + ((int64_t)part * (E / 4) + cg * 8) * rows_pad + row;
 #pragma unroll
-                        for (int g4 = 0; g4 < 8; ++g4) dst[g4] = make_float4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
+                        for (int g4 = 0; g4 < 8; ++g4) dst[(int64_t)g4 * rows_pad] = make_float4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
                     }
                 }
                 tc_fence_before();
