@@ -5,22 +5,28 @@
 // canonical fp32 values -- bit-identical to the exact path and to oracle/tt_oracle.c -- although the
 // heavy lifting runs in TF32 on tcgen05:
 //
-//   1. rowpanel_kernel<kIndex>   TF32 scores a_ij with the error bound eps_ij = kappa_i*||c_j||, kappa_i = 2^-9*||q_i||;
+//   1. rowpanel_kernel<kIndex>   on a SAMPLE of the corpus (the first quarter of the permuted copy, i.e. a pseudo-random quarter of
+//                                the rows): TF32 scores a_ij with the error bound eps_ij = kappa_i*||c_j||, kappa_i = 2^-9*||q_i||;
 //                                only a lower bound of the best score of every group of consecutive corpus rows
 //                                (128 rows; 32 for small corpora) is kept: max_j a_ij - kappa_i * max_j ||c_j||.
-//   2. select_threshold_kernel   lambda_i = (a lower bound, tight to 16 bits, of) the K-th largest group value.
+//   2. select_threshold_kernel   lambda_i = (a lower bound, tight to 16 bits, of) the r-th largest group value of the sample,
+//                                r = K f + 6 sqrt(K f (1 - f)) + 1 for a sample fraction f: with probability 1 - 1e-9 fewer than r
+//                                of the true top-K rows fall into the sample, so lambda_i <= the exact K-th best score.  (One and a
+//                                quarter tensor passes instead of two; lambda sits near rank r / f, so ~2x more columns are rescored.)
 //   3. rowpanel_kernel<kCollect> same TF32 contraction; every chunk of 32 columns whose maximum can reach lambda_i
 //                                (~1.25 K chunks per query) is appended whole to the dumping warp's hit log.
 //   4. column_test_kernel        per logged column: a_ij >= lambda_i - kappa_i * max_chunk ||c|| -> the query's list.
 //   5. exact_score_kernel        exact canonical fp32 score of every listed column from the authoritative corpus; rows
 //                                with s < lambda_i are dropped.
 //   6. sort_topk_kernel          exact top-K by (score desc, index asc).
-//   7. a query whose log or list overflowed is redone by the exact CUDA-core kernel (tt_index.cu), on the device.
+//   7. a query whose log or list overflowed, OR that ends with fewer than K rescored rows at or above lambda_i (the sampled
+//      threshold was too high: never observed, probability ~1e-9), is redone by the exact CUDA-core kernel (tt_index.cu), on
+//      the device.
 //
 // Why it is exact: |a_ij - s_ij| <= eps_ij (TF32 operand rounding 2^-11 each and Cauchy-Schwarz, plus the fp32
-// accumulation error of both evaluations, with a 2x margin).  K groups hold a row with s >= a - eps >= lambda,
-// so the exact K-th best score s_K >= lambda; every true top-K row has s >= s_K, hence a + eps >= lambda, and is
-// listed; steps 5-6 order the listed rows by the exact (score desc, index asc) rule.
+// accumulation error of both evaluations, with a 2x margin), so every row with s >= lambda has a + eps >= lambda and is
+// listed.  When at least K listed rows have an exact score >= lambda, the exact K-th best score s_K is >= lambda, every true
+// top-K row (s >= s_K) is among them, and steps 5-6 order them by the exact (score desc, index asc) rule; otherwise step 7.
 #include "tt_tc_rowpanel.cuh"
 
 namespace tt {
@@ -39,9 +45,9 @@ static inline int idx_halves(int E) { return idx_bn(E) / 32 >= 2 ? 2 : 1; }   //
 constexpr float kEpsCoef = 1.0f / 512.0f;   // 2^-9
 static int g_cap_override = 0;              // tests: force tiny candidate lists to exercise the fallback
 
-static inline int cand_cap(int K) {   // listed columns per query (a power of two: it is also the largest sort size)
+static inline int cand_cap(int rank) {   // listed columns per query for a threshold near `rank` (a power of two: it is also the largest sort size)
     int c = 128;
-    while (c < K + K / 2 + 32) c <<= 1;
+    while (c < rank + rank / 2 + 32) c <<= 1;
     return c < 1024 ? c : 1024;
 }
 
@@ -314,11 +320,18 @@ __device__ __forceinline__ void ce_desc(unsigned long long& a, unsigned long lon
 // sorts the 32*S keys of a warp (element g = lane*S + i, the first m of them read from `src`) into descending order and
 // writes the first K as (score, index)
 template <int S>
-__device__ __forceinline__ void sort_write(const unsigned long long* __restrict__ src, int m, int K, int64_t idx_base, float* __restrict__ os,
+__device__ __forceinline__ bool sort_write(const unsigned long long* __restrict__ src, int m, int K, int need_k, int64_t idx_base, float* __restrict__ os,
                                            int32_t* __restrict__ oi, int lane) {
     unsigned long long key[S];
+    int alive = 0;
 #pragma unroll
-    for (int i = 0; i < S; ++i) key[i] = (i * 32 + lane < m) ? src[i * 32 + lane] : 0ull;   // 0 sorts after every real key
+    for (int i = 0; i < S; ++i) {
+        key[i] = (i * 32 + lane < m) ? src[i * 32 + lane] : 0ull;   // 0 sorts after every real key
+        alive += key[i] != 0ull;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) alive += __shfl_xor_sync(0xffffffffu, alive, o);
+    if (alive < need_k) return false;   // fewer than K rescored rows reach lambda: the threshold was too high (exact fallback)
     for (int k = 2; k <= 32 * S; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             if (j >= S) {
@@ -350,12 +363,13 @@ __device__ __forceinline__ void sort_write(const unsigned long long* __restrict_
             oi[g] = pad ? -1 : (int32_t)((int64_t)(0xFFFFFFFFu - (uint32_t)key[i]) + idx_base);
         }
     }
+    return true;
 }
 
 constexpr int kSortWarps = 4;             // queries per CTA
 template <bool BIG>                       // BIG: up to 1024 listed columns (32 keys per lane); otherwise up to 256 (8 per lane)
 __global__ void __launch_bounds__(32 * kSortWarps) sort_topk_kernel(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ cand_cnt,
-                                                                    int nq, int cap, int K, int64_t idx_base, float* __restrict__ out_s,
+                                                                    int nq, int cap, int K, int need_k, int64_t idx_base, float* __restrict__ out_s,
                                                                     int32_t* __restrict__ out_i, int32_t* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * kSortWarps + (threadIdx.x >> 5);
@@ -369,13 +383,15 @@ __global__ void __launch_bounds__(32 * kSortWarps) sort_topk_kernel(const unsign
     float* os = out_s + (int64_t)q * K;
     int32_t* oi = out_i + (int64_t)q * K;
     const int need = m1 > K ? m1 : K;
+    bool ok;
     if constexpr (!BIG) {
-        if (need <= 128) sort_write<4>(src, m1, K, idx_base, os, oi, lane);
-        else sort_write<8>(src, m1, K, idx_base, os, oi, lane);
+        if (need <= 128) ok = sort_write<4>(src, m1, K, need_k, idx_base, os, oi, lane);
+        else ok = sort_write<8>(src, m1, K, need_k, idx_base, os, oi, lane);
     } else {
-        if (need <= 512) sort_write<16>(src, m1, K, idx_base, os, oi, lane);
-        else sort_write<32>(src, m1, K, idx_base, os, oi, lane);
+        if (need <= 512) ok = sort_write<16>(src, m1, K, need_k, idx_base, os, oi, lane);
+        else ok = sort_write<32>(src, m1, K, need_k, idx_base, os, oi, lane);
     }
+    if (!ok && lane == 0) flags[q] = 1;
 }
 
 // C32p[pos][:] = tf32_rn(C[orig(pos)][:]); norms[pos] = ||C[orig(pos)]|| (rounded up a hair); norms[n..n_pad) = 0.
@@ -428,11 +444,7 @@ static int launch_idx(const CUtensorMap& tmQ, const CUtensorMap& tmC, const RowP
                       const char* name) {
     constexpr int BN = (E <= 64) ? 256 : 128;
     using Cfg = RowPanelCfg<MODE, E, BN>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        TT_CUDA_OK(cudaFuncSetAttribute(rowpanel_kernel<MODE, E, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_done = true;
-    }
+    TT_CUDA_OK(cudaFuncSetAttribute(rowpanel_kernel<MODE, E, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     dim3 grid((unsigned)m_tiles, (unsigned)splits);
     rowpanel_kernel<MODE, E, BN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmQ, tmC, tmC, p);
     TT_LAUNCH_OK(name);
@@ -453,20 +465,36 @@ struct IdxLayout {
     size_t q32, eps, thr, gmax, cnt, flags, queue, cand, ccnt, keys, c32, norms, exact, total;
     int ngroups, n_tiles, cap;
     int m_tiles, splits, tps, n_logs, cap_log, fine;
+    int n_tiles_s, splits_s, tps_s, k_sel, rank;   // threshold pass: tiles of the sample, its launch shape, the order statistic taken, the rank lambda sits near
 };
 
 static IdxLayout layout(int nq, int64_t n, int E, int K, bool need_corpus_copy) {
     IdxLayout L;
     L.n_tiles = (int)ceil_div(n, idx_bn(E));
     // one filter group per (tile, warp half) = BN/2 consecutive rows; per 32-row chunk when that leaves fewer than 8 K groups
-    L.fine = (int64_t)L.n_tiles * idx_halves(E) < 8 * (int64_t)K;
-    L.ngroups = L.n_tiles * (L.fine ? idx_bn(E) / 32 : idx_halves(E));
-    L.cap = cand_cap(K);
+    L.fine = (int64_t)L.n_tiles * idx_halves(E) < 32 * (int64_t)K;
+    const int gpt = L.fine ? idx_bn(E) / 32 : idx_halves(E);   // groups per tile
+    // sample for the threshold pass: a quarter of the tiles (half for large K), more when that leaves fewer than 8 r groups
+    double f = K <= 256 ? 0.25 : 0.5;
+    for (;;) {
+        L.n_tiles_s = (int)ceil_div((int64_t)(L.n_tiles * f), 1);
+        if (L.n_tiles_s < 1) L.n_tiles_s = 1;
+        if (L.n_tiles_s >= L.n_tiles) { L.n_tiles_s = L.n_tiles; f = 1.0; }
+        const double fe = (double)L.n_tiles_s / L.n_tiles;
+        L.k_sel = f >= 1.0 ? K : (int)(K * fe + 6.0 * sqrt(K * fe * (1.0 - fe)) + 1.0);
+        if (L.k_sel > K) L.k_sel = K;
+        L.rank = f >= 1.0 ? K : (int)(L.k_sel / fe) + 1;
+        if (f >= 1.0 || ((int64_t)L.n_tiles_s * gpt >= 8 * (int64_t)L.k_sel && L.rank + L.rank / 4 <= 1000)) break;
+        f *= 2.0;
+    }
+    L.ngroups = L.n_tiles_s * gpt;
+    L.cap = cand_cap(L.rank);
     L.m_tiles = (int)ceil_div(nq, 128);
     choose_splits(L.m_tiles, L.n_tiles, 2, 64, &L.splits, &L.tps);
+    choose_splits(L.m_tiles, L.n_tiles_s, 2, 64, &L.splits_s, &L.tps_s);
     // hit logs of the collect pass: a warp's 32 rows each see ~1.25 K / (splits * halves) qualifying chunks; generous slack because an overflow costs a trip through the exact CUDA-core fallback
     L.n_logs = L.m_tiles * L.splits * 4 * idx_halves(E);   // one log per epilogue warp (32 rows x its share of the columns)
-    L.cap_log = g_cap_override > 0 ? 32 * (1 + g_cap_override / (4 * L.splits)) : 32 * (int)ceil_div(5 * (int64_t)K, 2 * L.splits * idx_halves(E)) + 128;
+    L.cap_log = g_cap_override > 0 ? 32 * (1 + g_cap_override / (4 * L.splits)) : 32 * (int)ceil_div(5 * (int64_t)L.rank, 2 * L.splits * idx_halves(E)) + 128;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     L.q32 = take((size_t)nq * E * 4);
@@ -557,10 +585,15 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
     p.nR = nq; p.nT = (int)n; p.n_tiles = L.n_tiles; p.tiles_per_split = tps; p.rowv = eps; p.rowv2 = thr; p.colv2 = norms; p.gnorm = norms + TT_INDEX_ROWS_PAD(n); p.d = -(1 << 30); p.fine_groups = L.fine;
     p.out0 = gmax; p.out1 = nullptr; p.out2 = nullptr; p.ld_out = L.ngroups; p.trace = nullptr;
     mark();
-    rc = launch_idx_e<kIndex>(E, tmQ, tmC, p, m_tiles, splits, st, "rowpanel_kernel<index>");
-    if (rc) return rc;
+    {   // threshold pass over the sample: the first n_tiles_s tiles of the permuted copy
+        RowPanelParams ps = p;
+        const int64_t rows_s = (int64_t)L.n_tiles_s * idx_bn(E);
+        ps.nT = (int)(rows_s < n ? rows_s : n); ps.n_tiles = L.n_tiles_s; ps.tiles_per_split = L.tps_s;
+        rc = launch_idx_e<kIndex>(E, tmQ, tmC, ps, m_tiles, L.splits_s, st, "rowpanel_kernel<index>");
+        if (rc) return rc;
+    }
     mark();
-    select_threshold_kernel<<<(unsigned)nq, kSelectThreads, 0, st>>>(gmax, L.ngroups, L.ngroups, K, thr, flags, ccnt);
+    select_threshold_kernel<<<(unsigned)nq, kSelectThreads, 0, st>>>(gmax, L.ngroups, L.ngroups, L.k_sel, thr, flags, ccnt);
     TT_LAUNCH_OK("select_threshold_kernel");
     mark();
     p.out0 = queue;
@@ -582,8 +615,9 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
 #undef TT_SCORE
         TT_LAUNCH_OK("exact_score_kernel");
         const unsigned tgrid = (unsigned)ceil_div(nq, kSortWarps);
-        if (L.cap <= 256) sort_topk_kernel<false><<<tgrid, 32 * kSortWarps, 0, st>>>(keys, ccnt, nq, L.cap, K, idx_base, out_s, out_i, flags);
-        else sort_topk_kernel<true><<<tgrid, 32 * kSortWarps, 0, st>>>(keys, ccnt, nq, L.cap, K, idx_base, out_s, out_i, flags);
+        const int need_k = (int)((int64_t)K < n ? K : n);   // rows a query must end with (fewer: the sampled threshold was too high -> exact fallback)
+        if (L.cap <= 256) sort_topk_kernel<false><<<tgrid, 32 * kSortWarps, 0, st>>>(keys, ccnt, nq, L.cap, K, need_k, idx_base, out_s, out_i, flags);
+        else sort_topk_kernel<true><<<tgrid, 32 * kSortWarps, 0, st>>>(keys, ccnt, nq, L.cap, K, need_k, idx_base, out_s, out_i, flags);
         TT_LAUNCH_OK("sort_topk_kernel");
     }
     mark();

@@ -12,6 +12,8 @@
 // precision only (absolute logit error < 2^-40 of the largest product).  Products are exact, accumulation is fp32.
 #include <cuda_fp16.h>
 
+#include <atomic>
+
 #include "tt_tc_flash.cuh"
 
 namespace tt {
@@ -19,8 +21,8 @@ namespace tc {
 
 int make_tmap_2d_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);   // tt_softmax_tc.cu
 
-static int g_fl_lbo = 0, g_fl_sbo = 0;          // debug: MN-major descriptor fields
-static unsigned long long* g_fl_trace = nullptr;
+static std::atomic<int> g_fl_lbo{0}, g_fl_sbo{0};                  // debug knobs (process-wide, read once per call)
+static std::atomic<unsigned long long*> g_fl_trace{nullptr};
 
 // ---- scales ---------------------------------------------------------------------------------------------------
 // scal[0] sq  [1] sc  [2],[3] kmul = log2e / (sq*sc)  [4] 1/sq  [5] 1/sc ; bits[8] amax(Q) [9] amax(C) [10] ticket   (64 floats)
@@ -389,7 +391,7 @@ static int fl_pass1(const FlWs& w, const float* C, int ldc, int Bq, int Bc, int 
     rc = make_tmap_2d_f16(&maps.t[0], w.Ch, Bc, E, E, bn);
     if (rc) return rc;
     FlParams p{};
-    p.n_pass = 1; p.units = pl.units; p.kmul = w.scal + 2; p.mn_lbo = g_fl_lbo; p.mn_sbo = g_fl_sbo; p.trace = g_fl_trace;
+    p.n_pass = 1; p.units = pl.units; p.kmul = w.scal + 2; p.mn_lbo = g_fl_lbo.load(); p.mn_sbo = g_fl_sbo.load(); p.trace = g_fl_trace.load();
     FlPass& ps = p.pass[0];
     ps.nR = Bq; ps.nT = Bc; ps.m_pairs = pl.m_pairs[0]; ps.n_tiles = pl.n_tiles[0]; ps.d = off; ps.unit0 = 0; ps.rowv = nullptr;
     ps.colv2 = w.c2_bias; ps.out_g = w.p1_g; ps.out_m = w.p1_m; ps.out_l = w.p1_l;
@@ -418,7 +420,7 @@ static int fl_pass2(const FlWs& w, const float* Q, int ldq, const float* C, int 
     FlMaps maps;
     memset(&maps, 0, sizeof(maps));
     FlParams p{};
-    p.n_pass = n; p.units = pl.units; p.kmul = w.scal + 2; p.mn_lbo = g_fl_lbo; p.mn_sbo = g_fl_sbo; p.trace = g_fl_trace;
+    p.n_pass = n; p.units = pl.units; p.kmul = w.scal + 2; p.mn_lbo = g_fl_lbo.load(); p.mn_sbo = g_fl_sbo.load(); p.trace = g_fl_trace.load();
     Comb2Args ca{};
     ca.n = n; ca.E = E; ca.units = pl.units; ca.grid = pl.grid; ca.ksplit = fl_split(E); ca.scal = w.scal;
     int rblocks = 0;
@@ -488,9 +490,9 @@ int softmax_bwd_flash(const float* Q, int ldq, const float* C, int ldc, const fl
 }
 
 void debug_flash(void* trace, int mn_lbo, int mn_sbo) {
-    tc::g_fl_trace = reinterpret_cast<unsigned long long*>(trace);
-    tc::g_fl_lbo = mn_lbo;
-    tc::g_fl_sbo = mn_sbo;
+    tc::g_fl_trace.store(reinterpret_cast<unsigned long long*>(trace));
+    tc::g_fl_lbo.store(mn_lbo);
+    tc::g_fl_sbo.store(mn_sbo);
 }
 
 }  // namespace tt

@@ -13,6 +13,8 @@
 //             the per-(panel, CTA) partial blocks (deterministic, no atomics)
 #include <cuda_fp16.h>
 
+#include <atomic>
+
 #include "tt_tc_rowpanel.cuh"
 #include "tt_tc_streamk.cuh"
 
@@ -97,11 +99,7 @@ template <int MODE, int E, int BN>
 static int launch_rowpanel(const CUtensorMap& tmR, const CUtensorMap& tmT, const CUtensorMap& tmTt, const RowPanelParams& p, int m_tiles,
                            int splits, cudaStream_t st, const char* name) {
     using Cfg = RowPanelCfg<MODE, E, BN>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        TT_CUDA_OK(cudaFuncSetAttribute(rowpanel_kernel<MODE, E, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_done = true;
-    }
+    TT_CUDA_OK(cudaFuncSetAttribute(rowpanel_kernel<MODE, E, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     dim3 grid((unsigned)m_tiles, (unsigned)splits);
     rowpanel_kernel<MODE, E, BN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmR, tmT, tmTt, p);
     TT_LAUNCH_OK(name);
@@ -114,8 +112,8 @@ constexpr int kFwdHalves = 4;    // SkCfg<kFwd, E, 128>::kHalves
 constexpr int kMaxSplits = 16;   // column splits per launch; the forward keeps 2 partials per split (one per warp half)
 
 // debug knobs (tt_debug_tc): timeline buffer and a cap on the column splits
-static unsigned long long* g_trace = nullptr;
-static int g_max_splits = kMaxSplits;
+static std::atomic<unsigned long long*> g_trace{nullptr};   // (debug knobs: process-wide, read once per call)
+static std::atomic<int> g_max_splits{kMaxSplits};
 
 struct Plan {
     int m_tiles, n_tiles, splits, tps;
@@ -124,7 +122,7 @@ static Plan plan_for(int nR, int nT, int bn) {
     Plan pl;
     pl.m_tiles = (int)ceil_div(nR, 128);
     pl.n_tiles = (int)ceil_div(nT, bn);
-    choose_splits(pl.m_tiles, pl.n_tiles, 2, g_max_splits, &pl.splits, &pl.tps);
+    choose_splits(pl.m_tiles, pl.n_tiles, 2, g_max_splits.load(), &pl.splits, &pl.tps);
     return pl;
 }
 
@@ -162,11 +160,7 @@ static SkPlan sk_plan(int n_pass, const int* m_tiles, const int* n_tiles) {
 template <int MODE, int E, int BN, bool H>
 static int launch_streamk(const SkMaps& maps, const SkParams& p, int grid, cudaStream_t st, const char* name) {
     using Cfg = SkCfg<MODE, E, BN, H>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        TT_CUDA_OK(cudaFuncSetAttribute(streamk_kernel<MODE, E, BN, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_done = true;
-    }
+    TT_CUDA_OK(cudaFuncSetAttribute(streamk_kernel<MODE, E, BN, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     streamk_kernel<MODE, E, BN, H><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
     TT_LAUNCH_OK(name);
     return TT_OK;
@@ -442,7 +436,7 @@ static int softmax_fwd_sk(const float* Q, int ldq, const float* C, int ldc, cons
         if (rc) return rc;
     }
     SkParams p{};
-    p.n_pass = 1; p.units = pl.units; p.trace = g_trace;
+    p.n_pass = 1; p.units = pl.units; p.trace = g_trace.load();
     SkPass& ps = p.pass[0];
     ps.nR = Bq; ps.nT = Bc; ps.m_tiles = mt; ps.n_tiles = nt; ps.d = off; ps.unit0 = 0; ps.rowv = nullptr; ps.colv2 = c2;
     ps.out0 = m2; ps.out1 = l; ps.out2 = zd;
@@ -475,7 +469,7 @@ int softmax_bwd_sk(const SkSide* sides, int n, int E, float* ws, cudaStream_t st
     SkMaps maps;
     memset(&maps, 0, sizeof(maps));
     SkParams p{};
-    p.n_pass = n; p.units = pl.units; p.trace = g_trace;
+    p.n_pass = n; p.units = pl.units; p.trace = g_trace.load();
     PrepArgs pa{};
     pa.E = E;
     RedArgs ra{};
@@ -620,19 +614,9 @@ int logits_tc(const float* Q, int ldq, const float* C, int ldc, const float* bia
     if (rc) return rc;
     rc = make_tmap_2d(&tmC, C, Bc, E, ldc, kLogitsBN);
     if (rc) return rc;
-    // test / API-convenience path: the scaled column term lives in a lazily grown static buffer
-    static float* c2 = nullptr;
-    static size_t c2_cap = 0;
-    size_t need = (size_t)pl.n_tiles * kLogitsBN;
-    if (need > c2_cap) {
-        if (c2) cudaFree(c2);
-        TT_CUDA_OK(cudaMalloc(&c2, need * sizeof(float)));
-        c2_cap = need;
-    }
-    rc = launch_scale_pad(bias, Bc, c2, (int)need, st);
-    if (rc) return rc;
+    // (test / API-convenience path: the column bias is read from global memory by the epilogue, no scratch needed)
     RowPanelParams p{};
-    p.nR = Bq; p.nT = Bc; p.n_tiles = pl.n_tiles; p.tiles_per_split = pl.tps; p.colv2 = c2; p.out0 = Z; p.ld_out = ldz;
+    p.nR = Bq; p.nT = Bc; p.n_tiles = pl.n_tiles; p.tiles_per_split = pl.tps; p.colv2 = nullptr; p.rowv2 = bias; p.out0 = Z; p.ld_out = ldz;
     p.d = -(1 << 30);
     switch (E) {
         case 32: return launch_rowpanel<kLogits, 32, kLogitsBN>(tmQ, tmC, tmC, p, pl.m_tiles, pl.splits, st, "rowpanel_kernel<logits,32>");
@@ -646,8 +630,8 @@ size_t softmax_tc_workspace_bytes(int Bq, int Bc, int E) {
 }
 
 void debug_tc(void* trace, int max_splits) {
-    tc::g_trace = reinterpret_cast<unsigned long long*>(trace);
-    tc::g_max_splits = (max_splits >= 1 && max_splits <= tc::kMaxSplits) ? max_splits : tc::kMaxSplits;
+    tc::g_trace.store(reinterpret_cast<unsigned long long*>(trace));
+    tc::g_max_splits.store((max_splits >= 1 && max_splits <= tc::kMaxSplits) ? max_splits : tc::kMaxSplits);
 }
 
 }  // namespace tt

@@ -31,7 +31,7 @@ struct RowPanelParams {
     int n_tiles;          // ceil(nT / BN)
     int tiles_per_split;  // tiles handled by one blockIdx.y
     const float* rowv;    // kBwd: per-R-row term (lse or ln p), natural units | kIndex/kCollect: kappa_q = c*||q||
-    const float* rowv2;   // kCollect: per-row threshold lambda_q
+    const float* rowv2;   // kCollect: per-row threshold lambda_q | kLogits: per-COLUMN bias, natural units (may be null)
     const float* gnorm;   // kIndex/kCollect: max ||c_j|| over each chunk of 32 columns (colv2 holds the per-column norms)
     const float* colv2;   // per-T-row term * log2(e), padded with zeros to n_tiles*BN entries (never null)
     int d;                // diagonal: column == row + d
@@ -134,7 +134,7 @@ struct RowPanelCfg {
     static constexpr int kPSlabs = BN / 32;
     static constexpr int kPBytes = (MODE == kBwd) ? kPSlabs * 128 * 128 : 0;
     static constexpr int kPBufs = (MODE == kBwd) ? 2 : 0;
-    static constexpr bool kUsesC2 = (MODE != kIndex && MODE != kCollect);   // staged per-column vector (softmax: colv * log2 e)
+    static constexpr bool kUsesC2 = (MODE != kIndex && MODE != kCollect && MODE != kLogits);   // staged per-column vector (softmax: colv * log2 e); kLogits reads the bias (rowv2, natural units) from global memory
     static constexpr int kC2Bytes = kUsesC2 ? BN * 4 : 0;
     static constexpr int kHalves = (BN / 32 >= 2) ? 2 : 1;                   // epilogue warps per TMEM lane quarter
     static constexpr int kEpiWarps = 4 * kHalves;
@@ -406,12 +406,10 @@ rowpanel_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
                     if (row < p.nR) {
 #pragma unroll
                         for (int g4 = 0; g4 < 8; ++g4) {
-                            const float4 cc = c2v[c * 8 + g4];
-                            const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
                                 const int n = nb + g4 * 4 + t;
-                                if (n < p.nT) p.out0[(int64_t)row * p.ld_out + n] = __uint_as_float(r[g4 * 4 + t]) - cv[t] * kLn2;
+                                if (n < p.nT) p.out0[(int64_t)row * p.ld_out + n] = __uint_as_float(r[g4 * 4 + t]) - (p.rowv2 ? __ldg(p.rowv2 + n) : 0.f);
                             }
                         }
                     }

@@ -156,6 +156,9 @@ class TwoTowerModel(AbstractKerasModel):
         torch = N.require_cuda()
         opt = self.optimizer
         init = opt.slot_init()
+        # cached step workspaces (their sparse-optimizer job lists and captured CUDA graphs) hold raw pointers to the OLD slot tensors:
+        # drop them, or a compile() / load() after training would update freed memory and never touch the new accumulators
+        self._steps.clear()
         self._opt_state = {
             "dense": [torch.full_like(self._store.params, v) for v in init],
             "tables": {id(t): [torch.full_like(t.weight, v) for v in init] for _, _, t in self._tables()},

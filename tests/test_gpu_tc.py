@@ -248,7 +248,9 @@ def test_brute_force_index_uses_tc_and_matches_exact(lib, T):
 
 @pytest.mark.parametrize("Bq,Bc,E,off", [(1000, 1000, 64, 0), (257, 300, 32, 5), (130, 777, 128, 3)])
 def test_softmax_step_equals_fwd_then_bwd(lib, T, Bq, Bc, E, off):
-    """tt_inbatch_softmax_step (shared prep, fused loss sum) gives bit-identical lse/dQ/dC to the two separate calls and the same loss."""
+    """tt_inbatch_softmax_step against the two separate calls.  E = 32 (stream-K kernels, shared prep): bit-identical lse / dQ / dC.
+    E >= 64 (two-pass kernels): the step forms dQ inside the forward sweep from the un-normalised weights, the backward entry point
+    from the normalised ones -- same lse bit for bit, gradients equal to the fp16 rounding of the weights (2^-11 of the row scale)."""
     from pkg import _native as N
 
     rng = np.random.default_rng(11)
@@ -274,6 +276,92 @@ def test_softmax_step_equals_fwd_then_bwd(lib, T, Bq, Bc, E, off):
             N.check(lib.tt_inbatch_softmax_step(q32.data_ptr(), E, c32.data_ptr(), E, bias.data_ptr(), Bq, Bc, E, off, lse.data_ptr(), loss.data_ptr(),
                                                 gq.data_ptr(), E, gc.data_ptr(), E, ws.data_ptr(), ws.numel(), N.TT_IMPL_TC, stream()))
         out[name] = [x.cpu().numpy() for x in (lse, loss, gq, gc)]
-    for a, b in zip(out["sep"][:1] + out["sep"][2:], out["step"][:1] + out["step"][2:]):
-        assert np.array_equal(a, b)
+    assert np.array_equal(out["sep"][0], out["step"][0])
     assert abs(out["sep"][1][0] - out["step"][1][0]) <= 1e-6 * abs(out["sep"][1][0])
+    for a, b in zip(out["sep"][2:], out["step"][2:]):
+        if E == 32:
+            assert np.array_equal(a, b)
+        else:
+            np.testing.assert_allclose(a, b, rtol=0, atol=2e-3 * np.abs(a).max())
+
+
+def _softmax_step(lib, T, q, c, bias, off=0):
+    from pkg import _native as N
+
+    Bq, E = q.shape
+    Bc = c.shape[0]
+    dq_, dc_ = dev(T, q), dev(T, c)
+    db = dev(T, bias) if bias is not None else None
+    lse = T.zeros(Bq, device="cuda"); loss = T.zeros(1, device="cuda")
+    gq = T.full((Bq, E), 9.0, device="cuda"); gc = T.full((Bc, E), 9.0, device="cuda")
+    ws = T.empty(int(lib.tt_softmax_workspace_bytes(Bq, Bc, E)), dtype=T.uint8, device="cuda")
+    N.check(lib.tt_inbatch_softmax_step(dq_.data_ptr(), E, dc_.data_ptr(), E, db.data_ptr() if db is not None else None, Bq, Bc, E, off, lse.data_ptr(),
+                                        loss.data_ptr(), gq.data_ptr(), E, gc.data_ptr(), E, ws.data_ptr(), ws.numel(), TC, stream()))
+    return float(loss.cpu()[0]), lse.cpu().numpy(), gq.cpu().numpy(), gc.cpu().numpy()
+
+
+def _row_err(got, want):
+    """per-row error relative to the row norm; rows whose norm is below 1e-3 of the largest are measured against that floor"""
+    n = np.linalg.norm(want, axis=1)
+    return float((np.linalg.norm(got - want, axis=1) / np.maximum(n, 1e-3 * n.max())).max())
+
+
+def test_softmax_step_c2_shape_vs_fp32_oracle_on_unrounded_inputs(lib, T):
+    """The bench's configuration (B = 8192, E = 64, logQ correction) on the tensor-core path against the oracle evaluated on the SAME
+    un-rounded fp32 operands (float64 arithmetic): north-star tolerance -- loss within 1e-3 relative (measured ~1e-6), lse within 1e-3,
+    every row of dQ and dC within 1e-3 of its norm."""
+    rng = np.random.default_rng(21)
+    B, E = 8192, 64
+    q = np.maximum(rng.standard_normal((B, E)) * 0.3, 0).astype(np.float32)
+    c = np.maximum(rng.standard_normal((B, E)) * 0.3, 0).astype(np.float32)
+    p = (rng.random(B) * 0.01 + 1e-5).astype(np.float32)
+    z = O.logits_qct(q, c).astype(np.float64) - np.log(p.astype(np.float64))[None, :]      # float64 product of the fp32 operands
+    loss, lse, dz = O.ce_sum_from_logits(z)
+    want_dq, want_dc = dz @ c.astype(np.float64), dz.T @ q.astype(np.float64)
+    got_loss, got_lse, gq, gc = _softmax_step(lib, T, q, c, np.log(p))
+    assert abs(got_loss - loss) <= 1e-3 * abs(loss)
+    assert abs(got_loss - loss) <= 2e-5 * abs(loss)            # (what the fp16/TF32-class operands actually deliver)
+    np.testing.assert_allclose(got_lse, lse, rtol=0, atol=1e-3)
+    assert _row_err(gq, want_dq) <= 1e-3
+    assert _row_err(gc, want_dc) <= 1e-3
+
+
+@pytest.mark.parametrize("qs,cs", [(3.0e5, 1.0e-5), (2.0e-6, 2.0e5), (1.0, 1.0)])
+def test_softmax_step_operands_outside_the_fp16_range(lib, T, qs, cs):
+    """Tower outputs above 65504 or below 2^-14 (un-normalised numeric features, a diverging run): the operands are scaled per tensor by
+    a power of two before the fp16 conversion, so nothing saturates or flushes -- results stay within the north-star tolerance of the
+    float64 oracle, and nothing is NaN / inf."""
+    rng = np.random.default_rng(22)
+    Bq, Bc, E = 700, 900, 64
+    q = (np.maximum(rng.standard_normal((Bq, E)) * 0.3, 0) * qs).astype(np.float32)
+    c = (np.maximum(rng.standard_normal((Bc, E)) * 0.3, 0) * cs).astype(np.float32)
+    assert qs == 1.0 or q.max() > 65504 or c.max() > 65504
+    p = (rng.random(Bc) * 0.01 + 1e-5).astype(np.float32)
+    z = O.logits_qct(q, c).astype(np.float64) - np.log(p.astype(np.float64))[None, :]
+    loss, lse, dz = O.ce_sum_from_logits(z, diag_offset=100)
+    want_dq, want_dc = dz @ c.astype(np.float64), dz.T @ q.astype(np.float64)
+    got_loss, got_lse, gq, gc = _softmax_step(lib, T, q, c, np.log(p), off=100)
+    assert np.isfinite(got_loss) and np.isfinite(gq).all() and np.isfinite(gc).all()
+    assert abs(got_loss - loss) <= 1e-3 * abs(loss)
+    np.testing.assert_allclose(got_lse, lse, rtol=0, atol=1e-3 * max(1.0, np.abs(lse).max()))
+    assert _row_err(gq, want_dq) <= 2e-3
+    assert _row_err(gc, want_dc) <= 2e-3
+
+
+def test_softmax_step_sharp_softmax_keeps_the_positive_term_exact(lib, T):
+    """A trained model: the positive dominates its row, so dQ_i = sum_j p_ij c_j - c_i is a difference of nearly equal vectors.  The
+    positive is kept out of the tensor-core products and its term (p_ii - 1) is formed without cancellation in fp32: every row stays
+    within 1e-2 of its norm although the logits themselves carry the operand rounding (~1e-4 relative)."""
+    rng = np.random.default_rng(23)
+    B, E = 1000, 64
+    q = np.maximum(rng.standard_normal((B, E)) * 0.3, 0).astype(np.float32)
+    c = (q + 0.05 * np.maximum(rng.standard_normal((B, E)) * 0.3, 0)).astype(np.float32)
+    q = (q * 6.0).astype(np.float32)
+    p = (rng.random(B) * 0.01 + 1e-5).astype(np.float32)
+    z = O.logits_qct(q, c).astype(np.float64) - np.log(p.astype(np.float64))[None, :]
+    loss, lse, dz = O.ce_sum_from_logits(z)
+    want_dq, want_dc = dz @ c.astype(np.float64), dz.T @ q.astype(np.float64)
+    got_loss, got_lse, gq, gc = _softmax_step(lib, T, q, c, np.log(p))
+    assert abs(got_loss - loss) <= 1e-3 * abs(loss)
+    assert _row_err(gq, want_dq) <= 1e-2
+    assert _row_err(gc, want_dc) <= 1e-2
