@@ -13,6 +13,8 @@
 #include <cuda_fp16.h>
 
 #include <atomic>
+#include <cstdlib>
+#include <utility>
 
 #include "tt_tc_flash.cuh"
 
@@ -23,6 +25,28 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t c
 
 static std::atomic<int> g_fl_lbo{0}, g_fl_sbo{0};                  // debug knobs (process-wide, read once per call)
 static std::atomic<unsigned long long*> g_fl_trace{nullptr};
+
+// ---- programmatic dependent launch -----------------------------------------------------------------------------------------
+// The six kernels of a step run back to back on one stream.  Each is launched with the programmatic-stream-serialization
+// attribute and calls pdl_trigger() first thing (the next kernel may be launched: its blocks become resident as soon as ours leave
+// room, and run their set-up) and pdl_wait() before it touches anything its predecessors wrote (returns once they have completed
+// and their memory is visible).  That hides each kernel's launch latency and prologue behind the previous kernel's tail.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+static bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("TT_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- scales ---------------------------------------------------------------------------------------------------
 // scal[0] sq  [1] sc  [2],[3] kmul = log2e / (sq*sc)  [4] 1/sq  [5] 1/sc ; bits[8] amax(Q) [9] amax(C) [10] ticket   (64 floats)
@@ -38,6 +62,8 @@ __device__ __forceinline__ float pow2_scale_for(uint32_t amax_bits) {
 
 struct AmaxArgs { const float* X[2]; int ld[2]; int n[2]; int E; };
 __global__ void __launch_bounds__(256) fl_amax_kernel(const AmaxArgs a, float* __restrict__ scal) {
+    pdl_trigger();
+    pdl_wait();   // (the inputs may come from a kernel launched the same way)
     uint32_t* bits = reinterpret_cast<uint32_t*>(scal) + 8;
     __shared__ uint32_t s_max[2][8];
     __shared__ bool s_last;
@@ -90,6 +116,8 @@ struct CvtItem {
 struct DiagItem { const float* Q; int ldq; const float* C; int ldc; const float* bias; const float* lse; int Bq, off; float* zd2; float* pm1; int blocks; };
 struct CvtArgs { CvtItem s[2]; int n; int E; DiagItem dg; };
 __global__ void __launch_bounds__(256) fl_convert_kernel(const CvtArgs a, const float* __restrict__ scal) {
+    pdl_trigger();
+    pdl_wait();
     int b = blockIdx.x;
     const int e8 = a.E >> 3;
     if (b < a.dg.blocks) {   // e8 consecutive lanes per row
@@ -175,7 +203,7 @@ template <int MODE, int E>
 static int launch_flash(const FlMaps& maps, const FlParams& p, int grid, cudaStream_t st, const char* name) {
     using Cfg = FlCfg<E>;
     TT_CUDA_OK(cudaFuncSetAttribute(flash_kernel<MODE, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    flash_kernel<MODE, E><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
+    TT_CUDA_OK(launch_pdl(flash_kernel<MODE, E>, dim3((unsigned)grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, st, maps, p));
     TT_LAUNCH_OK(name);
     return TT_OK;
 }
@@ -206,6 +234,8 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
     __shared__ bool s_last;
     const int e4 = a.E >> 2;
     const int r = blockIdx.x * 256 + threadIdx.x, c4 = blockIdx.y;
+    pdl_trigger();
+    pdl_wait();
     double mine = 0.0;
     if (r < a.nR) {
         const int first = a.unit0 + (r >> 8) * a.n_tiles;
@@ -284,6 +314,8 @@ struct Comb2Side {
 };
 struct Comb2Args { Comb2Side s[2]; int n, E, units, grid, ksplit; const float* scal; };
 __global__ void __launch_bounds__(256) fl_combine2_kernel(const Comb2Args a) {
+    pdl_trigger();
+    pdl_wait();
     int rb = blockIdx.x;
     const int e4 = a.E >> 2, c4 = blockIdx.y;
     for (int k = 0; k < a.n; ++k) {
@@ -366,7 +398,7 @@ static int fl_prepare(const FlWs& w, const float* Q, int ldq, const float* C, in
     int64_t work = ((int64_t)Bq + Bc) * (E / 4);
     int blocks = (int)ceil_div(work, 256 * 4);
     blocks = blocks > 2 * sm_count() ? 2 * sm_count() : (blocks < 1 ? 1 : blocks);
-    fl_amax_kernel<<<(unsigned)blocks, 256, 0, st>>>(aa, w.scal);
+    TT_CUDA_OK(launch_pdl(fl_amax_kernel, dim3((unsigned)blocks), dim3(256), 0, st, aa, w.scal));
     TT_LAUNCH_OK("fl_amax_kernel");
     CvtArgs ca{};
     ca.E = E;
@@ -374,7 +406,7 @@ static int fl_prepare(const FlWs& w, const float* Q, int ldq, const float* C, in
     int cb = ca.dg.blocks;
     cb += cvt_item(ca.s[ca.n++], Q, ldq, Bq, E, w.Qh, 0, lse, lse ? w.c2_lse : nullptr, Bq, (int)(ceil_div(Bq, bn) * bn), kLog2e);
     cb += cvt_item(ca.s[ca.n++], C, ldc, Bc, E, w.Ch, 1, bias, w.c2_bias, Bc, (int)(ceil_div(Bc, bn) * bn), kLog2e);
-    fl_convert_kernel<<<(unsigned)cb, 256, 0, st>>>(ca, w.scal);
+    TT_CUDA_OK(launch_pdl(fl_convert_kernel, dim3((unsigned)cb), dim3(256), 0, st, ca, (const float*)w.scal));
     TT_LAUNCH_OK("fl_convert_kernel");
     return TT_OK;
 }
@@ -404,7 +436,7 @@ static int fl_pass1(const FlWs& w, const float* C, int ldc, int Bq, int Bc, int 
     ca.c2_lse = want_c2_lse ? w.c2_lse : nullptr; ca.c2_pad = (int)(ceil_div(Bq, bn) * bn); ca.pm1 = want_c2_lse ? w.pm1 : nullptr;
     ca.dQ = dQ; ca.lddq = lddq; ca.block_sums = w.block_sums; ca.counter = w.counter; ca.loss = loss;
     const int rows_c = ca.c2_pad > Bq ? ca.c2_pad : Bq;
-    fl_combine1_kernel<<<dim3((unsigned)ceil_div(rows_c, 256), (unsigned)(E / 4)), 256, 0, st>>>(ca);
+    TT_CUDA_OK(launch_pdl(fl_combine1_kernel, dim3((unsigned)ceil_div(rows_c, 256), (unsigned)(E / 4)), dim3(256), 0, st, ca));
     TT_LAUNCH_OK("fl_combine1_kernel");
     return TT_OK;
 }
@@ -444,7 +476,7 @@ static int fl_pass2(const FlWs& w, const float* Q, int ldq, const float* C, int 
     }
     int rc = launch_flash_e<kP2>(E, maps, p, pl.grid, st);
     if (rc) return rc;
-    fl_combine2_kernel<<<dim3((unsigned)rblocks, (unsigned)(E / 4)), 256, 0, st>>>(ca);
+    TT_CUDA_OK(launch_pdl(fl_combine2_kernel, dim3((unsigned)rblocks, (unsigned)(E / 4)), dim3(256), 0, st, ca));
     TT_LAUNCH_OK("fl_combine2_kernel");
     return TT_OK;
 }

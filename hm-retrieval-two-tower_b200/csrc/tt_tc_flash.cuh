@@ -38,6 +38,9 @@ enum FlashMode { kP1 = 0, kP2 = 1 };
 
 constexpr float kTau = 8.f;      // pass 1: a row's reference exponent may lag its true maximum by up to 2^kTau
 constexpr float kOff1 = 6.f;     // pass 1: P~ = 2^(z - ref + kOff1) <= 2^(kTau + kOff1) = 2^14 < 65504
+#ifndef TT_FLASH_SBUF
+#define TT_FLASH_SBUF 1   // S buffers per stream: 1 = one 64-column buffer (N = 64 products), 2 = two 32-column buffers
+#endif
 #ifndef TT_FLASH_POLY_PAIRS
 #define TT_FLASH_POLY_PAIRS 0   // measured: any share on the polynomial is slower -- the passes are issue-bound, not MUFU-bound
 #endif
@@ -215,6 +218,8 @@ __device__ __forceinline__ void unpack_f16x2(uint32_t w, float& lo, float& hi) {
 // worked on; P of chunk j -- 8 packed columns -- lands on S columns [8j, 8j+8), which are in registers by then).  16 keeps the
 // epilogue at ~90 registers, so 16 epilogue warps fit an SM without spilling.
 constexpr int kCW = 16;
+constexpr int kSBuf = TT_FLASH_SBUF;          // S buffers (sub-tiles) per stream and tile
+constexpr int kSW = 64 / kSBuf;               // columns per sub-tile
 
 // ---- pass 1 state of one row ----------------------------------------------------------------------------------------------
 // P~ = 2^(a - zn) with zn = c2_j - s*kmul the negated log2-domain logit; a = +inf until the first chunk.  Passed and returned
@@ -375,7 +380,18 @@ __device__ __noinline__ P1State p1_chunk_checked(uint32_t tS_chunk, uint32_t c2s
 }
 
 // ---- pass 2: P' = 2^(s*kmul - c2_j - r2 + kOff2), the positive left out (weight 0) ------------------------------------------------
-// pass 2, fast chunk: P' of 16 columns as packed fp16
+// pass 2, fast chunk, exponent arguments only (the exponentials are taken one chunk later: software pipeline in the epilogue)
+__device__ __forceinline__ void p2_x_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, float rowc, f32x2 (&x)[8]) {
+    const f32x2 km = pk2(kmul, kmul), mone = pk2(-1.f, -1.f), rc = pk2(rowc, rowc);
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+        const float4 cc = lds128(c2s + g4 * 16);
+        const f32x2 ad0 = fma2(pk2(cc.x, cc.y), mone, rc), ad1 = fma2(pk2(cc.z, cc.w), mone, rc);
+        x[2 * g4] = fma2(pk2(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1])), km, ad0);
+        x[2 * g4 + 1] = fma2(pk2(__uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])), km, ad1);
+    }
+}
+// pass 2, fast chunk: P' of 16 columns as packed fp16 (unpipelined form)
 __device__ __forceinline__ void p2_chunk_fast(const uint32_t (&r)[16], uint32_t c2s, float kmul, float rowc, uint32_t (&w)[8]) {
     const f32x2 km = pk2(kmul, kmul), mone = pk2(-1.f, -1.f), rc = pk2(rowc, rowc);
 #pragma unroll
@@ -430,6 +446,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
     constexpr int BN = Cfg::BN, NS = Cfg::NS, kSplit = Cfg::kSplit;
     const int u_begin = sk_begin(blockIdx.x, p.units, gridDim.x), u_end = sk_begin(blockIdx.x + 1, p.units, gridDim.x);
     const int my_units = u_end - u_begin;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // (programmatic dependent launch, see tt_softmax_flash.cu)
     if (my_units <= 0) return;
     if (p.trace && threadIdx.x == 0) p.trace[((size_t)blockIdx.x * 64 + 63) * 8 + 0] = gtime();   // CTA entry
 
@@ -461,6 +478,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the kernels before this one have completed: operand copies, scales, lse are visible
     const uint32_t tmem = bars->tmem_base;
     const uint32_t b_rfull = smem_u32(&bars->r_full[0]), b_rempty = smem_u32(&bars->r_empty[0]), b_tfull = smem_u32(&bars->t_full[0]),
                    b_tempty = smem_u32(&bars->t_empty[0]), b_sfull = smem_u32(&bars->s_full[0][0]), b_pfull = smem_u32(&bars->p_full[0][0]),
@@ -516,17 +534,17 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                 pc.next(p);
             };
             // sub-tile v = 2 * tile + sub lives in S buffer `sub` of the stream (columns [sub * 32, +32) of its tensor-memory block)
-            constexpr uint32_t idesc1s = make_idesc_f16(128, 32);
+            constexpr uint32_t idesc1s = make_idesc_f16(128, kSW);
             auto first_product = [&](int it, int sub, int kseg) {   // tile `it` belongs to pair number kseg of this CTA
                 const int stage = it % Cfg::kStages;
                 const uint64_t ad0 = make_smem_desc(sR_a + (kseg & 1) * Cfg::kRBytes + g * Cfg::kPanelBytes, 16, 1024);
-                const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes + (h * 64 + sub * 32) * 128, 16, 1024);   // 32 rows of every slab
+                const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes + (h * 64 + sub * kSW) * 128, 16, 1024);   // kSW rows of every slab
                 if (lead) {
 #pragma unroll
                     for (int kk = 0; kk < Cfg::kMma1; ++kk) {
                         const uint64_t ad = ad0 + (uint64_t)(((kk >> 2) * 128 * 128 + (kk & 3) * 32) >> 4);
                         const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * BN * 128 + (kk & 3) * 32) >> 4);
-                        mma_f16(tS + sub * 32, ad, bd, idesc1s, kk > 0 ? 1u : 0u);
+                        mma_f16(tS + sub * kSW, ad, bd, idesc1s, kk > 0 ? 1u : 0u);
                     }
                     mma_commit_a(b_sfull + (s * 2 + sub) * 8);
                     if (s == 0 && sub == 0) FL_TRACE(it, 1);
@@ -543,8 +561,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             mbar_wait_a(b_rfull, 0);
             mbar_wait_a(b_tfull, 0);
             tc_fence_after();
-            first_product(0, 0, 0);
-            first_product(0, 1, 0);
+            for (int sub = 0; sub < kSBuf; ++sub) first_product(0, sub, 0);
             const bool inorder = p.mn_lbo < 0;   // debug: 0 = wait for the second product's completion before refilling its buffer
             int k = -1;
             for (int it = 0; it < my_units; ++it) {
@@ -560,15 +577,15 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                 const int stage = it % Cfg::kStages;
                 const uint64_t bd0 = make_smem_desc(sT_a + stage * Cfg::kTBytes, lbo, sbo);
 #pragma unroll
-                for (int sub = 0; sub < 2; ++sub) {
+                for (int sub = 0; sub < kSBuf; ++sub) {
                     mbar_wait_a(b_pfull + (s * 2 + sub) * 8, it & 1);
                     tc_fence_after();
                     if (lead) {
 #pragma unroll
-                        for (int k2 = 0; k2 < 2; ++k2)   // 16 rows of T (2048 bytes of every slab) per instruction
-                            mma_f16_ts(tG, tS + sub * 32 + k2 * 8, bd0 + (uint64_t)(((h * 64 + sub * 32 + k2 * 16) * 128) >> 4), idesc2,
+                        for (int k2 = 0; k2 < kSW / 16; ++k2)   // 16 rows of T (2048 bytes of every slab) per instruction
+                            mma_f16_ts(tG, tS + sub * kSW + k2 * 8, bd0 + (uint64_t)(((h * 64 + sub * kSW + k2 * 16) * 128) >> 4), idesc2,
                                        (!seg_start || sub > 0 || k2 > 0) ? 1u : 0u);
-                        if (sub == 1) {
+                        if (sub == kSBuf - 1) {
                             mma_commit_a(b_tempty + stage * 8);   // (one of NS arrivals) this stream is done with the tile and its column term
                             if (seg_end) {
                                 mma_commit_a(b_gfull + s * 8);
@@ -576,10 +593,10 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                             }
                         }
                         mma_commit_a(b_pempty + (s * 2 + sub) * 8);
-                        if (s == 0 && sub == 1) FL_TRACE(it, 7);
+                        if (s == 0 && sub == kSBuf - 1) FL_TRACE(it, 7);
                     }
                     __syncwarp();
-                    if (p.trace && s == 0 && sub == 1) {   // debug: completion latency of the second product (blocks the issuer)
+                    if (p.trace && s == 0 && sub == kSBuf - 1) {   // debug: completion latency of the second product (blocks the issuer)
                         mbar_wait_a(b_pempty + (s * 2 + sub) * 8, it & 1);
                         if (lead) FL_TRACE(it, 5);
                     }
@@ -637,60 +654,89 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             const int stage = it % Cfg::kStages;
             // (the staged column term needs no wait of its own: S of this tile exists, so the issuer had seen the tile's TMA barrier)
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-                const int n0 = c.tile * BN + h * 64 + sub * 32;      // first column of this sub-tile
-                const uint32_t tS = tS0 + sub * 32, tP = tS;
-                const uint32_t c2s = c2s0 + stage * Cfg::kC2Bytes + sub * 128;
+            for (int sub = 0; sub < kSBuf; ++sub) {
+                constexpr int NCH = kSW / kCW;                        // 16-column chunks per sub-tile
+                const int n0 = c.tile * BN + h * 64 + sub * kSW;      // first column of this sub-tile
+                const uint32_t tS = tS0 + sub * kSW, tP = tS;
+                const uint32_t c2s = c2s0 + stage * Cfg::kC2Bytes + sub * kSW * 4;
                 // warp-uniform: the sub-tile is fully in range (else: the checked path) / holds a positive of this warp's rows
-                const bool in_range = (n0 + 32 <= nT) && (wrow0 + 32 <= nR) && p.mn_sbo >= 0;   // (mn_sbo < 0: debug, checked path everywhere)
-                const bool has_d = dlo < n0 + 32 && dlo + 32 > n0;
-                const bool g_valid = !seg_start || sub > 0;          // a second product of this segment has been issued
+                const bool in_range = (n0 + kSW <= nT) && (wrow0 + 32 <= nR) && p.mn_sbo >= 0;   // (mn_sbo < 0: debug, checked path everywhere)
+                const bool has_d = dlo < n0 + kSW && dlo + 32 > n0;
+                const bool g_valid = !seg_start || sub > 0;           // a second product of this segment has been issued
+                // pass 1, rare: before G is rescaled every second product issued so far must be complete (with one S buffer that is
+                // implied by S being there; with two, the previous sub-tile's may still run)
+                auto g_quiet = [&]() {
+                    if (kSBuf > 1 && g_valid) {
+                        mbar_wait_a(bp_empty + (sub ^ 1) * 8, (sub == 1 ? it : it - 1) & 1);
+                        tc_fence_after();
+                    }
+                };
                 mbar_wait_a(bs_full + sub * 8, it & 1);
                 tc_fence_after();
                 if (sub == 0 && lane == 0 && warp == 0) FL_TRACE(it, 2);
-                if (in_range) {
-                    uint32_t r0[kCW], r1[kCW];
-                    tmem_ld_32x16_issue(tS, r0);
-                    tmem_ld_32x16_issue(tS + kCW, r1);
+                // software pipeline over the chunks: the address arithmetic of chunk j+1 (FFMA2, min) sits in the same basic block as the
+                // exponentials of chunk j, so the scheduler overlaps them.  DIAG: chunks may hold positives of this warp's rows.
+                auto fast_sub = [&](auto diag_tag) {
+                    constexpr bool DIAG = decltype(diag_tag)::value;
+                    uint32_t rb[2][kCW];
+                    tmem_ld_32x16_issue(tS, rb[0]);
                     tmem_ld_wait();
-                    if (has_d) {
-                        mask_positive(r0, n0, dcol_abs);
-                        mask_positive(r1, n0 + kCW, dcol_abs);
-                    }
-                    uint32_t w0[kCW / 2], w1[kCW / 2];
+                    if (NCH > 1) tmem_ld_32x16_issue(tS + kCW, rb[1]);
+                    if (DIAG) mask_positive(rb[0], n0, dcol_abs);
                     if constexpr (MODE == kP1) {
-                        f32x2 zn0[kCW / 2], zn1[kCW / 2];
-                        const float cmin0 = p1_zn_fast(r0, c2s, kmul, zn0);
-                        const float cmin1 = p1_zn_fast(r1, c2s + kCW * 4, kmul, zn1);
-                        // one check for the sub-tile: raising the reference to the smaller of the two minima before either chunk is
-                        // exponentiated keeps every P~ of the sub-tile within 2^kTau of it
-                        const float cmin = fminf(cmin0, cmin1);
-                        const bool need = cmin < st.a - (kOff1 + kTau);
-                        if (__any_sync(0xffffffffu, need)) {
-                            if (g_valid) {   // rare: before G is rescaled every second product issued so far must be complete
-                                mbar_wait_a(bp_empty + (sub ^ 1) * 8, (sub == 1 ? it : it - 1) & 1);
-                                tc_fence_after();
-                            }
-                            st = p1_raise<E>(need, cmin, g_valid, 0, tG, tP, st);
+                        f32x2 zn[2][kCW / 2];
+                        float cmin = p1_zn_fast(rb[0], c2s, kmul, zn[0]);
+                        {
+                            const bool need = cmin < st.a - (kOff1 + kTau);   // this chunk exceeds the row's reference by more than 2^kTau
+                            if (__any_sync(0xffffffffu, need)) { g_quiet(); st = p1_raise<E>(need, cmin, g_valid, 0, tG, tP, st); }
                         }
-                        p1_exp_fast(zn0, st.a, st.l, w0);
-                        tmem_st_32x8(tP, w0);
-                        p1_exp_fast(zn1, st.a, st.l, w1);
-                        tmem_st_32x8(tP + kCW / 2, w1);
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j) {
+                            uint32_t w[kCW / 2];
+                            if (j + 1 < NCH) {
+                                tmem_ld_wait();                                                   // chunk j+1 is in registers
+                                if (DIAG) mask_positive(rb[(j + 1) & 1], n0 + (j + 1) * kCW, dcol_abs);
+                                cmin = p1_zn_fast(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, zn[(j + 1) & 1]);
+                                if (j + 2 < NCH) tmem_ld_32x16_issue(tS + (j + 2) * kCW, rb[j & 1]);
+                            }
+                            p1_exp_fast(zn[j & 1], st.a, st.l, w);
+                            tmem_st_32x8(tP + j * (kCW / 2), w);
+                            if (j + 1 < NCH) {
+                                const bool need = cmin < st.a - (kOff1 + kTau);
+                                if (__any_sync(0xffffffffu, need)) { g_quiet(); st = p1_raise<E>(need, cmin, g_valid, j + 1, tG, tP, st); }
+                            }
+                        }
                     } else {
-                        p2_chunk_fast(r0, c2s, kmul, rowc, w0);
-                        tmem_st_32x8(tP, w0);
-                        p2_chunk_fast(r1, c2s + kCW * 4, kmul, rowc, w1);
-                        tmem_st_32x8(tP + kCW / 2, w1);
+                        f32x2 x[2][kCW / 2];
+                        p2_x_fast(rb[0], c2s, kmul, rowc, x[0]);
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j) {
+                            uint32_t w[kCW / 2];
+                            if (j + 1 < NCH) {
+                                tmem_ld_wait();
+                                if (DIAG) mask_positive(rb[(j + 1) & 1], n0 + (j + 1) * kCW, dcol_abs);
+                                p2_x_fast(rb[(j + 1) & 1], c2s + (j + 1) * kCW * 4, kmul, rowc, x[(j + 1) & 1]);
+                                if (j + 2 < NCH) tmem_ld_32x16_issue(tS + (j + 2) * kCW, rb[j & 1]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < kCW / 2; ++i) {
+                                float x0, x1;
+                                upk2(x[j & 1][i], x0, x1);
+                                w[i] = pack_f16x2(ex2_approx(x0), ex2_approx(x1));
+                            }
+                            tmem_st_32x8(tP + j * (kCW / 2), w);
+                        }
                     }
+                };
+                if (in_range && !has_d) {
+                    fast_sub(std::false_type{});
+                } else if (in_range) {
+                    fast_sub(std::true_type{});
                 } else {
 #pragma unroll 1
-                    for (int j = 0; j < 32 / kCW; ++j) {
+                    for (int j = 0; j < NCH; ++j) {
                         if constexpr (MODE == kP1) {
-                            if (g_valid) {   // (the checked chunk may raise the reference: G has to be quiescent)
-                                mbar_wait_a(bp_empty + (sub ^ 1) * 8, (sub == 1 ? it : it - 1) & 1);
-                                tc_fence_after();
-                            }
+                            g_quiet();   // (the checked chunk may raise the reference: G has to be quiescent)
                             st = p1_chunk_checked<E>(tS + j * kCW, c2s + j * kCW * 4, kmul, n0 + j * kCW, nT, dcol_abs, g_valid, j, tG, tP, st);
                         } else {
                             p2_chunk_checked(tS + j * kCW, c2s + j * kCW * 4, kmul, rowc, n0 + j * kCW, nT, row_ok, dcol_abs, tP + j * (kCW / 2));
