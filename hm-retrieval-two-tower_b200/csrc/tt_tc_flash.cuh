@@ -27,6 +27,7 @@
 // panel; G is quiescent whenever the epilogue runs, because the stream's next product is only issued after the epilogue).
 // Every mbarrier wait is bounded.
 #pragma once
+#include <cstddef>
 #include <type_traits>
 
 #include "tt_tc_streamk.cuh"
@@ -622,13 +623,17 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
         const int g = s / kSplit, h = s % kSplit;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t tS0 = tmem + lane_addr + s * Cfg::kStreamCols, tG = tS0 + Cfg::kGCol;
-        const uint32_t bs_full = b_sfull + s * 16, bp_full = b_pfull + s * 16, bp_empty = b_pempty + s * 16, bg_full = b_gfull + s * 8,
-                       bg_empty = b_gempty + s * 8;
+        // (barrier addresses are formed from one base at the use sites, and what only the ends of a segment need -- row, partial slot,
+        // padded row count -- is recomputed there: the loop is register-bound at 96)
+        const uint32_t bs_full = b_sfull + s * 16;
+#define bp_full (bs_full + (uint32_t)(offsetof(FlBars, p_full) - offsetof(FlBars, s_full)))
+#define bp_empty (bs_full + (uint32_t)(offsetof(FlBars, p_empty) - offsetof(FlBars, s_full)))
+        const uint32_t bg_full = b_gfull + s * 8, bg_empty = b_gempty + s * 8;
         FlWalk c;
         c.init(p, u_begin);
         int k = -1;
-        int row = 0, part = 0, rows_pad = 0, nT = 0, nR = 0, dlo = 0, dcol_abs = -1, wrow0 = 0;
-        bool row_ok = false;
+        int nT = 0, dlo = 0, dcol_abs = -1;
+        bool rows_in = false;
         float kmul = 0.f;
         P1State st{CUDART_INF_F, pk2(0.f, 0.f)};
         float rowc = 0.f;   // pass 2: kOff2 - rowv*log2e
@@ -637,16 +642,14 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             const bool seg_start = (it == 0 || c.tile == 0);
             const bool seg_end = (it == my_units - 1 || c.last_tile());
             const FlPass& ps = p.pass[c.pass];   // (only dereferenced at the ends of a segment)
+            const int wrow0 = (c.pair * 2 + g) * 128 + q * 32, row = wrow0 + lane;
+            const bool row_ok = row < ps.nR;
             if (seg_start) {
                 ++k;
-                nT = ps.nT; nR = ps.nR;
-                wrow0 = (c.pair * 2 + g) * 128 + q * 32;
-                row = wrow0 + lane;
-                row_ok = row < nR;
+                nT = ps.nT;
+                rows_in = wrow0 + 32 <= ps.nR;
                 dlo = wrow0 + ps.d;                                  // positives of this warp's rows sit in columns [dlo, dlo + 32)
                 dcol_abs = row_ok ? row + ps.d : -1;
-                rows_pad = c.m_pairs * 256;
-                part = (blockIdx.x - sk_owner(ps.unit0 + c.pair * c.n_tiles, p.units, gridDim.x)) * kSplit + h;
                 kmul = __ldg(p.kmul + c.pass);
                 st = P1State{CUDART_INF_F, pk2(0.f, 0.f)};
                 if (MODE == kP2) rowc = kOff2 - ((row_ok && ps.rowv) ? __ldg(ps.rowv + row) * kLog2e : 0.f);
@@ -660,7 +663,7 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
                 const uint32_t tS = tS0 + sub * kSW, tP = tS;
                 const uint32_t c2s = c2s0 + stage * Cfg::kC2Bytes + sub * kSW * 4;
                 // warp-uniform: the sub-tile is fully in range (else: the checked path) / holds a positive of this warp's rows
-                const bool in_range = (n0 + kSW <= nT) && (wrow0 + 32 <= nR) && p.mn_sbo >= 0;   // (mn_sbo < 0: debug, checked path everywhere)
+                const bool in_range = (n0 + kSW <= nT) && rows_in && p.mn_sbo >= 0;   // (mn_sbo < 0: debug, checked path everywhere)
                 const bool has_d = dlo < n0 + kSW && dlo + 32 > n0;
                 const bool g_valid = !seg_start || sub > 0;           // a second product of this segment has been issued
                 // pass 1, rare: before G is rescaled every second product issued so far must be complete (with one S buffer that is
@@ -750,6 +753,8 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             }
             if (lane == 0 && warp == 0) FL_TRACE(it, 3);
             if (seg_end) {
+                const int rows_pad = c.m_pairs * 256;
+                const int part = (blockIdx.x - sk_owner(ps.unit0 + c.pair * c.n_tiles, p.units, gridDim.x)) * kSplit + h;
                 mbar_wait_a(bg_full, k & 1);
                 tc_fence_after();
 #pragma unroll
@@ -774,6 +779,8 @@ flash_kernel(const __grid_constant__ FlMaps maps, const __grid_constant__ FlPara
             }
         }
     }
+#undef bp_full
+#undef bp_empty
     __syncthreads();
     if (p.trace && threadIdx.x == 0) p.trace[((size_t)blockIdx.x * 64 + 63) * 8 + 1] = gtime();   // CTA exit
     if (warp == kIssuerWarp0) {
