@@ -138,6 +138,15 @@ __global__ void recall_hits_kernel(const int32_t* __restrict__ cand, int k_strid
     if (threadIdx.x < nk && s_hits[threadIdx.x]) atomicAdd(&hits[threadIdx.x], s_hits[threadIdx.x]);
 }
 
+__global__ void take_i32_kernel(const int32_t* __restrict__ table, const int32_t* __restrict__ idx, int64_t n, int32_t* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int32_t j = idx[i];
+        out[i] = __ldg(table + (j > 0 ? j : 0));
+    }
+}
+
 static inline int grid_for(int64_t n, int block) {
     int64_t g = ceil_div(n, block);
     int64_t cap = (int64_t)sm_count() * 8;
@@ -252,6 +261,14 @@ int tt_dense_adam(float* w, float* m, float* v, const float* g, int64_t n, float
     if (n == 0) return TT_OK;
     dense_adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, m, v, g, n, lr_t, 1.0f - beta1, 1.0f - beta2, eps);
     TT_LAUNCH_OK("dense_adam_kernel");
+    return TT_OK;
+}
+
+int tt_take_i32(const int32_t* table, const int32_t* idx, int64_t n, int32_t* out, void* stream) {
+    TT_REQUIRE((table && idx && out) || n == 0, "tt_take_i32: null pointer");
+    if (n == 0) return TT_OK;
+    take_i32_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(table, idx, n, out);
+    TT_LAUNCH_OK("take_i32_kernel");
     return TT_OK;
 }
 

@@ -103,6 +103,7 @@ SIGNATURES = {
     "tt_index_prepare": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "tt_round_tf32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "tt_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tt_take_i32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "tt_recall_hits": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
 }
 

@@ -127,38 +127,35 @@ class BruteForceIndex(AbstractKerasModel):
     def query_indices(self, queries, k: Optional[int] = None):
         return self.search(self._embed_queries(queries), k)
 
-    def call(self, queries, training: bool = False):
-        """{query feature: (B,1)} -> (B, k) array of candidate identifiers."""
+    def call(self, queries, training: bool = False, out=None):
+        """{query feature: (B,1)} -> (B, k) array of candidate identifiers.
+
+        `out` (optional): a pinned host tensor of shape (B, k) and the identifiers' dtype that receives the result; the returned numpy
+        array then views it (no further host copy -- the caller owns the buffer and decides when it is reused).  Without `out` the
+        result is an array of its own."""
         torch = N.require_cuda()
+        lib = N.load()
         _, idx = self.query_indices(queries)
         if self._identifiers_dev is not None:
-            ids_dev = self._identifiers_dev[idx.long().clamp_(min=0)]
-            # result delivery without a second host copy: the (B, k) identifiers land in a pinned buffer that is handed to the
-            # caller as the numpy array itself.  Buffers are recycled once the caller has dropped the array (and every view of it).
-            out, nd = self._pinned_result(tuple(ids_dev.shape), ids_dev.dtype)
-            out.copy_(ids_dev, non_blocking=True)
+            if self._identifiers_dev.dtype == torch.int32:
+                ids_dev = torch.empty_like(idx)
+                N.check(lib.tt_take_i32(self._identifiers_dev.data_ptr(), idx.data_ptr(), idx.numel(), ids_dev.data_ptr(), N.stream_ptr()), "tt_take_i32")
+            else:
+                ids_dev = self._identifiers_dev[idx.long().clamp_(min=0)]
+            shape = tuple(ids_dev.shape)
+            if out is not None:
+                if tuple(out.shape) != shape or out.dtype != ids_dev.dtype or not out.is_pinned():
+                    raise ValueError(f"out must be a pinned host tensor of shape {shape} and dtype {ids_dev.dtype}")
+                out.copy_(ids_dev, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return out.numpy()
+            stage = self.__dict__.get("_pin_stage")
+            if stage is None or tuple(stage.shape) != shape or stage.dtype != ids_dev.dtype:
+                stage = self.__dict__["_pin_stage"] = torch.empty(shape, dtype=ids_dev.dtype).pin_memory()
+            stage.copy_(ids_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return nd
+            return stage.numpy().copy()    # the caller's own array: the staging buffer is reused by the next call
         return self._identifiers[idx.cpu().numpy()]
-
-    def _pinned_result(self, shape, dtype):
-        """A pinned host buffer nobody else references: (tensor, the numpy array viewing it)."""
-        import sys
-
-        torch = N.require_cuda()
-        pool = self.__dict__.setdefault("_pin_pool", [])
-        for i in range(len(pool)):
-            t, nd = pool[i]
-            # references to nd: the pool entry, the local name, getrefcount's argument; a caller's array or view adds more
-            if tuple(t.shape) == shape and t.dtype == dtype and sys.getrefcount(nd) <= 3:
-                return t, nd
-            del t, nd
-        t = torch.empty(shape, dtype=dtype).pin_memory()
-        nd = t.numpy()
-        if len(pool) >= 8:          # callers are holding many results: stop tracking the oldest buffer (it stays valid for its holder)
-            pool.pop(0)
-        pool.append((t, nd))
-        return t, nd
 
     def positions_of(self, ids) -> np.ndarray:
         """Global row index of each identifier (-1 when absent); used by IndexRecall's device path."""

@@ -237,6 +237,10 @@ int tt_round_tf32(const float* src, int lds, float* dst, int ldd, int64_t rows, 
 int tt_topk_merge(const float* scores, const int32_t* idx, int G, int nq, int K, float* out_scores,
                   int32_t* out_idx, void* stream);
 
+/* out[i] = table[max(idx[i], 0)]: row indices -> identifiers on the device (tf.gather(identifiers, indices), brute_force.py:83, for
+ * integer identifiers; absent entries (-1) read row 0). */
+int tt_take_i32(const int32_t* table, const int32_t* idx, int64_t n, int32_t* out, void* stream);
+
 /* hits[t] += sum_{b, j < ks[t]} [true_idx[b] == cand[b, j]]   (index_recall.py:54-58; int32 exact).
  * cand is (nq, k_stride) int32; hits is int32[nk] on the device and is accumulated into. */
 int tt_recall_hits(const int32_t* cand, int k_stride, const int32_t* true_idx, int nq, const int32_t* ks, int nk,
