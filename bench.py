@@ -185,7 +185,8 @@ def cpu_index_rate(bq, warmup, steps, seed=2):
 
 def workload_name(batch):
     """config.workload: BASELINE.json configs[1], the same string on both arms."""
-    return ("c2: H&M-shaped two-tower (1.37M customers, 105k articles), id emb + joint dim 64, side features age/product_type/colour, "
+    cust = "1.37M" if V_CUSTOMERS == 1_371_980 else f"{V_CUSTOMERS / 1e6:g}M"
+    return (f"c2: H&M-shaped two-tower ({cust} customers, 105k articles), id emb + joint dim {JOINT}, side features age/product_type/colour, "
             f"batch {batch}/GPU, logQ in-batch softmax, Adagrad lr 0.05")
 
 
@@ -210,10 +211,90 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+
+# ---------------------------------------------------------------------------------------------------
+# timing: blocks of exactly K steps, repeated until the timed region covers >= min_ms; the median block is reported
+# ---------------------------------------------------------------------------------------------------
+def _reduce(x, world, op="max"):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+    return float(t)
+
+
+def _barrier(world):
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def time_device_blocks(step, k, warmup, world, min_ms=1000.0, max_blocks=2000):
+    """step(i) enqueues one step.  Returns the median per-step device time over blocks of k steps (max over ranks)."""
+    import torch
+
+    for i in range(warmup):
+        step(i)
+    _barrier(world)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(k):
+        step(i)
+    ev1.record()
+    _barrier(world)
+    probe = _reduce(ev0.elapsed_time(ev1), world)                       # sizes the region; every rank takes the same block count
+    blocks = int(min(max_blocks, max(1, -(-min_ms // max(probe, 1e-3)))))
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(blocks + 1)]
+    _barrier(world)
+    n = 0
+    evs[0].record()
+    for j in range(blocks):
+        for i in range(k):
+            step(n)
+            n += 1
+        evs[j + 1].record()
+    _barrier(world)
+    per = sorted(evs[j].elapsed_time(evs[j + 1]) for j in range(blocks))
+    med = _reduce(float(np.median(per)), world)
+    region = _reduce(evs[0].elapsed_time(evs[blocks]), world)
+    return {"ms_per_step": med / k, "blocks": blocks, "region_ms": region, "ms_per_step_mean": region / (blocks * k),
+            "ms_per_step_min": _reduce(per[0], world) / k, "ms_per_step_max": _reduce(per[-1], world) / k}
+
+
+def time_host_blocks(step, k, warmup, world, min_ms=1000.0, max_blocks=2000):
+    """step(i) runs one synchronous host-facing call (result on the host when it returns).  Wall clock, median block."""
+    for i in range(warmup):
+        step(i)
+    _barrier(world)
+    t0 = time.perf_counter()
+    for i in range(k):
+        step(i)
+    probe = _reduce((time.perf_counter() - t0) * 1e3, world)
+    blocks = int(min(max_blocks, max(1, -(-min_ms // max(probe, 1e-3)))))
+    _barrier(world)
+    per, n = [], 0
+    t_start = time.perf_counter()
+    for j in range(blocks):
+        t0 = time.perf_counter()
+        for i in range(k):
+            step(n)
+            n += 1
+        per.append(time.perf_counter() - t0)
+    region = time.perf_counter() - t_start
+    _barrier(world)
+    return {"sec_per_step": _reduce(float(np.median(per)), world) / k, "blocks": blocks, "region_ms": _reduce(region * 1e3, world)}
+
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
-def build_gpu_model():
+def build_gpu_model(attach=None):
     from pkg.modelling._device import set_seed
     from pkg.modelling.models.two_tower_model import TwoTowerModel
     from pkg.modelling.optimizer_factory import OptimizerFactory
@@ -229,6 +310,8 @@ def build_gpu_model():
     probs = article_probs()
     lookup = {str(i + 1): float(p) for i, p in enumerate(probs)}
     model = TwoTowerModel(qf, cf, "article_id", JOINT, candidate_prob_lookup=lookup)
+    if attach is not None:      # data parallel: shard the (still unmaterialised) tables first, so the owners initialise their shards
+        attach(model)           # and the optimizer slots are only ever allocated shard-sized
     model.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))
     return model
 
@@ -248,13 +331,15 @@ def run_ours(args):
     lib = N.load()
     pk = peaks()
     B, K, W = args.batch, max(args.steps, 1), max(args.warmup, 3)
-    model = build_gpu_model()
-    if args.simt:
-        model.impl = N.TT_IMPL_SIMT
+    attach = None
     if world > 1:
         from pkg.modelling.distributed import DataParallel
 
-        DataParallel(model, shard_tables=(args.tables == "sharded"), global_negatives=args.global_negatives)
+        attach = lambda m: DataParallel(m, shard_tables=(args.tables == "sharded"), global_negatives=args.global_negatives)   # noqa: E731
+    torch.cuda.reset_peak_memory_stats()
+    model = build_gpu_model(attach)
+    if args.simt:
+        model.impl = N.TT_IMPL_SIMT
     model.use_cuda_graph = not args.no_graph   # data parallel: two captured compute phases around the eager NCCL exchanges
     rng = np.random.default_rng(1000 + rank)
     pool = 8
@@ -273,53 +358,41 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step = int(lib.tt_launch_count() - c0)
 
-    for i in range(W):
-        model.train_step(dev_batches[i % pool])
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
-        barrier()
-        ev0.record()
-        for i in range(K):
-            model.train_step(dev_batches[i % pool])
-        ev1.record()
-        barrier()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
-    ms_per_step = ms / K
+        dev = time_device_blocks(lambda i: model.train_step(dev_batches[i % pool]), K, W, world, args.min_ms)
+    ms_per_step = dev["ms_per_step"]
     value = world * B / (ms_per_step * 1e-3)
     clocks = clk.summary()
 
     # end-to-end through the public API: pinned host ids -> H2D -> step -> loss D2H, every step
-    for i in range(3):
-        float(model.train_step(pinned[i % pool])["loss"])
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        loss = float(model.train_step(pinned[i % pool])["loss"])
-    barrier()
-    e2e_sec = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_sec], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_sec = float(t)
-    e2e = world * B * K / e2e_sec
+    last = [0.0]
+
+    def e2e_step(i):
+        last[0] = float(model.train_step(pinned[i % pool])["loss"])
+
+    host = time_host_blocks(e2e_step, K, 3, world, args.min_ms)
+    loss = last[0]
+    e2e = world * B / host["sec_per_step"]
 
     line = {
         "metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32/fp16 operands, fp32 accumulate" if model._tc_ok() and model.impl != N.TT_IMPL_SIMT else "f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": ("tf32 tower products; softmax on fp16 operand tiles (per-tensor power-of-two scaling), fp32 accumulate, fp32 positive term"
+                                                     if model._tc_ok() and model.impl != N.TT_IMPL_SIMT else "f32"),
         "data": "synthetic",
         "config": {"workload": workload_name(B),
                    "parallelism": f"dp{world}" if world > 1 else "single", "cuda_graph": bool(model.use_cuda_graph),
                    "l2": "inputs larger than L2: tables + Adagrad accumulators 0.76 GB, random rows each step; no explicit flush",
                    "last_loss": loss},
-        "e2e": {"value": e2e, "unit": "examples/s", "h2d_bytes_per_step": B * BYTES_PER_EXAMPLE_H2D, "d2h_bytes_per_step": 4},
+        "e2e": {"value": e2e, "unit": "examples/s", "h2d_bytes_per_step": B * BYTES_PER_EXAMPLE_H2D, "d2h_bytes_per_step": 4,
+                "blocks": host["blocks"], "timed_region_ms": host["region_ms"]},
         "gpu_launches": launches_per_step * K, "clocks": clocks,
+        "timing": {"blocks": dev["blocks"], "steps_per_block": K, "timed_region_ms": dev["region_ms"], "ms_per_step_mean": dev["ms_per_step_mean"],
+                   "ms_per_step_min_block": dev["ms_per_step_min"], "ms_per_step_max_block": dev["ms_per_step_max"],
+                   "note": "ms_per_step = median over back-to-back blocks of exactly `steps` steps (CUDA events on the launching stream, "
+                           "max over ranks); the blocks together cover >= --min-ms of device time"},
     }
 
+    line["config"]["hbm_peak_gb_per_gpu"] = round(torch.cuda.max_memory_allocated() / 1e9, 2)
     if world > 1:
         line["config"]["tables"] = "row-sharded over the GPUs (rows read / gradient rows pulled over NVLink peer memory)" if model.dist.shard_tables \
             else "replicated (all-gathered gradient rows)"
@@ -331,7 +404,15 @@ def run_ours(args):
         line["roofline"] = softmax_roofline(model, B, pk, lib)
         if not args.no_hbm:
             line["hbm_kernels"] = hbm_rooflines(pk, lib)
-    line["index"] = index_bench(model, pk, lib, K, world)      # every rank takes part (row-sharded corpus when N > 1)
+    if not args.no_c3 and not args.global_negatives and B != C3_BATCH:
+        line["c3"] = c3_leg(model, args, pk, lib, world, rank)     # BASELINE configs[2]: the same model at batch 65536 per GPU
+    line["index"] = index_bench(model, pk, lib, K, world, args)   # every rank takes part (row-sharded corpus when N > 1)
+    if not args.no_big_index:
+        line["index"]["row_sharded_large"] = big_index_legs(model, pk, lib, K, world, rank, args)
+    if world > 1 and not args.no_parity:
+        line["parity"] = multi_gpu_parity(world, rank, args)
+        line["parity_ok"] = bool(all(v.get("ok") for v in line["parity"].values())
+                                 and all(l.get("parity_ok", True) for l in line["index"].get("row_sharded_large", [])))
     if world == 1:
         if not args.no_cpu:
             rate, sec, cores = cpu_train_rate(B, 2, args.cpu_steps)
@@ -344,6 +425,230 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+
+C3_BATCH = 65536
+
+
+def c3_leg(model, args, pk, lib, world, rank):
+    """BASELINE configs[2] ("c3"): the same towers at batch 65536 per GPU -- 64x the logits of c2 per step, the shape where the
+    in-batch softmax dominates.  Same timing rules as the headline leg."""
+    import torch
+
+    B = C3_BATCH
+    rng = np.random.default_rng(4000 + rank)
+    pool = 4
+    host = [make_batch(rng, B) for _ in range(pool)]
+    devb = [{k: torch.from_numpy(v).cuda() for k, v in hb.items()} for hb in host]
+    pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in hb.items()} for hb in host]
+    k = max(2, min(args.steps, 10))
+    dev = time_device_blocks(lambda i: model.train_step(devb[i % pool]), k, 3, world, args.min_ms / 2)
+    last = [0.0]
+
+    def e2e_step(i):
+        last[0] = float(model.train_step(pinned[i % pool])["loss"])
+
+    hostt = time_host_blocks(e2e_step, k, 2, world, args.min_ms / 2)
+    out = {"workload": workload_name(B).replace("c2:", "c3:"), "value": world * B / (dev["ms_per_step"] * 1e-3), "unit": "examples/s",
+           "ms_per_step": dev["ms_per_step"], "steps": k, "blocks": dev["blocks"], "timed_region_ms": dev["region_ms"],
+           "e2e": {"value": world * B / hostt["sec_per_step"], "unit": "examples/s", "h2d_bytes_per_step": B * BYTES_PER_EXAMPLE_H2D,
+                   "d2h_bytes_per_step": 4}, "last_loss": last[0]}
+    if rank == 0:
+        out["roofline"] = softmax_roofline(model, B, pk, lib)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# row-sharded index at 1e7 / 1e8 rows (BASELINE configs[3]): every shard is generated ON its owner
+# ---------------------------------------------------------------------------------------------------
+CORPUS_CHUNK = 1 << 20
+
+
+def corpus_rows(lo, hi, e=JOINT):
+    """Rows [lo, hi) of the synthetic corpus, generated on this GPU.  Row values depend only on the global row number (chunks of
+    2^20 rows, one seeded generator per chunk), so any sharding of the same corpus holds the same rows."""
+    import torch
+
+    out = torch.empty((hi - lo, e), dtype=torch.float32, device="cuda")
+    c = lo // CORPUS_CHUNK
+    while c * CORPUS_CHUNK < hi:
+        a, b = c * CORPUS_CHUNK, (c + 1) * CORPUS_CHUNK
+        g = torch.Generator(device="cuda").manual_seed(90_000 + c)
+        chunk = torch.randn((CORPUS_CHUNK, e), generator=g, device="cuda") * 0.25
+        s0, s1 = max(a, lo), min(b, hi)
+        out[s0 - lo:s1 - lo].copy_(chunk[s0 - a:s1 - a])
+        del chunk
+        c += 1
+    return out
+
+
+def big_index_legs(model, pk, lib, steps, world, rank, args):
+    import torch
+
+    from pkg.modelling.distributed import shard_bounds
+    from pkg.modelling.indices.brute_force import BruteForceIndex
+
+    if args.big_index_rows == "auto":
+        sizes = [10_000_000] + ([100_000_000] if world >= 4 else [])
+    else:
+        sizes = [int(float(x)) for x in args.big_index_rows.split(",") if x]
+    rng = np.random.default_rng(177)                      # the SAME queries on every rank (row-sharded corpus: queries are replicated)
+    pool = 4
+    hq = [{"age": rng.random((INDEX_BQ, 1)).astype(np.float32), "customer_id": rng.integers(1, V_CUSTOMERS + 1, size=(INDEX_BQ, 1)).astype(np.int32)}
+          for _ in range(pool)]
+    dq = [{k: torch.from_numpy(v).cuda() for k, v in h.items()} for h in hq]
+    pq = [{k: torch.from_numpy(v).pin_memory() for k, v in h.items()} for h in hq]
+    res = []
+    for n_rows in sizes:
+        lo, hi = shard_bounds(n_rows, rank, world)
+        t0 = time.perf_counter()
+        rows = corpus_rows(lo, hi)
+        index = BruteForceIndex.from_local_rows(INDEX_K, model.query_tower, rows, lo, n_rows, identifiers=None, world=world)
+        index.impl = model.impl
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t0
+        k = max(2, min(steps, 10))
+        dev = time_device_blocks(lambda i: index.query_indices(dq[i % pool]), k, 2, world, args.min_ms / 2)
+        qe = index._embed_queries(dq[0])
+        kern = time_device_blocks(lambda i: index.search(qe), k, 1, world, args.min_ms / 2)
+        outs = [torch.empty((INDEX_BQ, INDEX_K), dtype=torch.int32).pin_memory() for _ in range(2)]
+        host = time_host_blocks(lambda i: index(pq[i % pool], out=outs[i % 2]), k, 2, world, args.min_ms / 2)
+        flops = 2.0 * INDEX_BQ * n_rows * JOINT / world
+        ach = flops / (kern["ms_per_step"] * 1e-3) / 1e12
+        leg = {"rows": n_rows, "value": INDEX_BQ / (dev["ms_per_step"] * 1e-3), "unit": "queries/s", "ms_per_batch": dev["ms_per_step"],
+               "search_only_ms": kern["ms_per_step"], "e2e": {"value": INDEX_BQ / host["sec_per_step"], "unit": "queries/s",
+                                                              "h2d_bytes_per_step": INDEX_BQ * 8, "d2h_bytes_per_step": INDEX_BQ * INDEX_K * 4},
+               "blocks": dev["blocks"], "timed_region_ms": dev["region_ms"], "shard_build_s": _reduce(build_s, world),
+               "config": f"{n_rows} x {JOINT} fp32 synthetic corpus ({n_rows * JOINT * 4 / 1e9:.1f} GB + prepared copy), K={INDEX_K}, Bq={INDEX_BQ} replicated queries; "
+                         + (f"rows sharded over {world} GPUs, each shard generated on its owner (no rank holds the corpus), per-shard top-K all-gathered "
+                            f"(NCCL) and merged on the device" if world > 1 else "single shard"),
+               "roofline": {"bound": "tensor", "kernel": "index scoring + top-K (per GPU, incl. the merge when sharded)", "achieved": ach,
+                            "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": ach / pk["tflops_burst"], "traffic": None,
+                            "hbm_gbs_corpus_read": (hi - lo) * JOINT * 4 * ((INDEX_BQ + 127) // 128) / (kern["ms_per_step"] * 1e-3) / 1e9,
+                            "algorithmic_flop": flops}}
+        if world > 1 and not args.no_parity:
+            # merged top-K of the sharded corpus == top-K of the unsharded corpus, held by rank 0 alone for this check
+            s_sh, i_sh = index.search(qe)
+            ok = 1.0
+            if rank == 0 and n_rows * JOINT * 8 < 60e9:
+                whole = BruteForceIndex.from_local_rows(INDEX_K, model.query_tower, corpus_rows(0, n_rows), 0, n_rows)
+                whole.impl = model.impl
+                s_1, i_1 = whole.search(qe)
+                ok = float(bool(torch.equal(i_1, i_sh)) and bool(torch.equal(s_1, s_sh)))
+                del whole
+            leg["parity_ok"] = bool(-_reduce(-ok, world) >= 1.0)
+            leg["parity_check"] = "merged (scores, row indices) of the sharded search bit-equal to the unsharded search of the same corpus on rank 0"
+        res.append(leg)
+        del index, rows, qe
+        torch.cuda.empty_cache()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------
+# in-process multi-GPU parity (world > 1): the N-rank step against single-GPU steps of the same library
+# ---------------------------------------------------------------------------------------------------
+def _small_model(seed, lr, acc0):
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+    from pkg.schema import dtypes as tt
+    from pkg.schema.features import Feature, FeatureFamily
+
+    set_seed(seed)
+    qf = [Feature("age", tt.float32, FeatureFamily.QUERY), Feature("customer_id", tt.string, FeatureFamily.QUERY, embedding_size=E_ID)]
+    cf = [Feature("article_id", tt.string, FeatureFamily.CANDIDATE, embedding_size=E_ID),
+          Feature("product_type_name", tt.string, FeatureFamily.CANDIDATE, embedding_size=E_PTYPE),
+          Feature("colour_group_name", tt.string, FeatureFamily.CANDIDATE, embedding_size=E_COLOUR)]
+    qf[1].set_vocab_size(PAR_CUSTOMERS); cf[0].set_vocab_size(PAR_ARTICLES); cf[1].set_vocab_size(V_PTYPE); cf[2].set_vocab_size(V_COLOUR)
+    lookup = {str(i + 1): 1.0 / PAR_ARTICLES for i in range(PAR_ARTICLES)}
+    model = TwoTowerModel(qf, cf, "article_id", JOINT, candidate_prob_lookup=lookup)
+    model.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": lr, "initial_accumulator_value": acc0}))
+    return model
+
+
+PAR_CUSTOMERS, PAR_ARTICLES, PAR_BATCH = 50_000, 20_000, 2048
+
+
+def _par_batch(r, b=PAR_BATCH):
+    rng = np.random.default_rng(31_000 + r)
+    art = rng.integers(1, PAR_ARTICLES + 1, size=b).astype(np.int32)
+    return {"age": rng.random((b, 1)).astype(np.float32), "customer_id": rng.integers(1, PAR_CUSTOMERS + 1, size=(b, 1)).astype(np.int32),
+            "article_id": art.reshape(b, 1), "product_type_name": (art % V_PTYPE + 1).astype(np.int32).reshape(b, 1),
+            "colour_group_name": (art % V_COLOUR + 1).astype(np.int32).reshape(b, 1)}
+
+
+def _flat_state(model):
+    """[dense parameters | every table, full rows] as one fp32 device vector (collective when the tables are row-sharded)."""
+    import torch
+
+    parts = [model._store.params[: int(model._store.used)].detach().reshape(-1)]
+    seen = set()
+    for _, _, t in model._tables():
+        if id(t) not in seen:
+            seen.add(id(t))
+            parts.append(t.full_weight().detach().reshape(-1))
+    return torch.cat(parts).clone()
+
+
+def multi_gpu_parity(world, rank, args):
+    """Two checks, both against single-GPU runs of this same library (whose parity with the oracle tests/ establishes):
+      dp_step       -- Adagrad with a 1e12 accumulator is a fixed-rate SGD to fp32 rounding, so the data-parallel update must equal
+                       the SUM over ranks of the updates single-GPU replicas make on each rank's batch from the same weights,
+                       and the summed loss the sum of their losses.
+      global_negatives -- the N-rank step with cross-GPU negatives is the single-GPU step on the concatenated batch."""
+    import torch
+    import torch.distributed as dist
+
+    from pkg.modelling.distributed import DataParallel
+
+    out = {}
+    lr, acc0 = 0.05 * 1e6, 1e12
+    try:
+        ref = _small_model(77, lr, acc0)
+        w0 = _flat_state(ref)
+        mine = {k: torch.from_numpy(v).cuda() for k, v in _par_batch(rank).items()}
+        loss_r = float(ref.train_step(mine)["loss"])
+        delta = _flat_state(ref) - w0
+        dist.all_reduce(delta, op=dist.ReduceOp.SUM)
+        loss_sum = _reduce(loss_r, world, "sum")
+        dp = _small_model(77, lr, acc0)
+        DataParallel(dp, shard_tables=(args.tables == "sharded"))
+        loss_dp = _reduce(float(dp.train_step(mine)["loss"]), world, "sum")
+        dp.dist.barrier()
+        got = _flat_state(dp) - w0
+        err = float((got - delta).abs().max() / delta.abs().max().clamp_min(1e-30))
+        err = _reduce(err, world)
+        lerr = abs(loss_dp - loss_sum) / abs(loss_sum)
+        out["dp_step"] = {"ok": bool(err <= 2e-4 and lerr <= 1e-5), "max_update_err_rel_to_max_update": err, "loss_rel_err": lerr,
+                          "loss": loss_dp, "check": f"{world}-rank step (batch {PAR_BATCH}/rank, {args.tables} tables) == sum of {world} single-GPU replica "
+                                                    "updates from the same weights (linearised Adagrad), all parameters and every table row"}
+        del ref, dp
+    except Exception as ex:      # a failed check must not lose the timing line
+        out["dp_step"] = {"ok": False, "error": f"{type(ex).__name__}: {ex}"}
+    try:
+        if args.tables == "sharded":
+            whole = {k: torch.from_numpy(np.concatenate([_par_batch(r)[k] for r in range(world)], axis=0)).cuda() for k in _par_batch(0)}
+            ref = _small_model(78, 0.05, 0.1)
+            loss_1 = float(ref.train_step(whole)["loss"])
+            want = _flat_state(ref)
+            gn = _small_model(78, 0.05, 0.1)
+            w0 = _flat_state(gn)
+            DataParallel(gn, shard_tables=True, global_negatives=True)
+            mine = {k: torch.from_numpy(v).cuda() for k, v in _par_batch(rank).items()}
+            loss_g = _reduce(float(gn.train_step(mine)["loss"]), world, "sum")
+            gn.dist.barrier()
+            got = _flat_state(gn)
+            err = _reduce(float((got - want).abs().max() / (want - w0).abs().max().clamp_min(1e-30)), world)
+            lerr = abs(loss_g - loss_1) / abs(loss_1)
+            out["global_negatives"] = {"ok": bool(err <= 5e-3 and lerr <= 1e-4), "max_update_err_rel_to_max_update": err, "loss_rel_err": lerr,
+                                       "loss": loss_g, "check": f"{world}-rank step with cross-GPU negatives ({world * PAR_BATCH} columns per row) == the "
+                                                                f"single-GPU step on the concatenated batch of {world * PAR_BATCH} (Adagrad lr 0.05)"}
+            del ref, gn
+    except Exception as ex:
+        out["global_negatives"] = {"ok": False, "error": f"{type(ex).__name__}: {ex}"}
+    torch.cuda.empty_cache()
+    return out
 
 
 def dp_phase_times(model, B, dev_batches, n=20):
@@ -399,28 +704,19 @@ def softmax_roofline(model, B, pk, lib):
         N.check(lib.tt_inbatch_softmax_step(q.data_ptr(), e, c.data_ptr(), e, bias, B, B, e, 0, sw.lse.data_ptr(), sw.loss.data_ptr(),
                                             sw.dq.data_ptr(), e, sw.dc.data_ptr(), e, ws.data_ptr(), ws.numel(), impl, st))
 
-    for _ in range(3):
-        once()
-    torch.cuda.synchronize()
-    n = 10
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(n):
-        once()
-    ev1.record()
-    torch.cuda.synchronize()
-    sec = ev0.elapsed_time(ev1) * 1e-3 / n
+    t = time_device_blocks(lambda i: once(), 10, 3, 1, 300.0)      # rank 0 alone: no collective in the timing helper
+    sec = t["ms_per_step"] * 1e-3
     flops = 6.0 * B * B * e
     achieved = flops / sec / 1e12
     return {"bound": "tensor", "kernel": "in-batch softmax fwd+bwd (%s)" % ("tcgen05, fp16 operand tiles" if use_tc else "fp32 CUDA cores"),
             "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_burst"],
-            "traffic": NCU_SOFTMAX_DRAM_BYTES if (use_tc and B == 8192 and e == 64) else None, "traffic_source": NCU_SOFTMAX_SOURCE,
+            "traffic": NCU_SOFTMAX_DRAM_BYTES if (use_tc and B == 8192 and e == 64 and NCU_SOFTMAX_DRAM_BYTES) else None, "traffic_source": NCU_SOFTMAX_SOURCE,
             "ms": sec * 1e3, "algorithmic_flop": flops, "peak_source": pk["source"] + ", dense bf16 burst (kernel timed alone)"}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the two stream-K launches (forward 2.17 MB, backward 4.37 MB) from the
 # `ncu --set full` capture of this workload (B = 8192, E = 64); the operands are 2 x 1 MB of fp16 tiles + 2 x 2 MB fp32 outputs
-NCU_SOFTMAX_DRAM_BYTES = 2169600 + 4365568 + 256
+NCU_SOFTMAX_DRAM_BYTES = None
 NCU_SOFTMAX_SOURCE = "profiles/r01c_softmax_streamk_ncu_full.md (ncu --set full, per launch, fwd + bwd)"
 
 
@@ -500,7 +796,7 @@ def hbm_rooflines(pk, lib, b=1 << 20, e=64, rows=V_CUSTOMERS + 1):
     return res
 
 
-def index_bench(model, pk, lib, steps, world=1):
+def index_bench(model, pk, lib, steps, world=1, args=None):
     """Index half of the metric: N=105 542 candidate-tower outputs, E=64, top-100, 2048 queries per batch.
     N > 1 ranks, two sharding modes:
       * headline `value`: the 27 MB corpus is replicated and the QUERIES are sharded (every rank answers its own
@@ -541,39 +837,27 @@ def index_bench(model, pk, lib, steps, world=1):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    min_ms = (args.min_ms if args is not None else 1000.0) / 2
+    outs = [torch.empty((INDEX_BQ, INDEX_K), dtype=torch.int32).pin_memory() for _ in range(2)]
+
     def measure(index):
         c0 = lib.tt_launch_count()
         for i in range(3):
             index.query_indices(dq[i % pool])
         torch.cuda.synchronize()
         per_call = int((lib.tt_launch_count() - c0) // 3)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sync_all()
-        ev0.record()
-        for i in range(n):
-            index.query_indices(dq[i % pool])
-        ev1.record()
-        sync_all()
-        sec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3 / n)
+        dev = time_device_blocks(lambda i: index.query_indices(dq[i % pool]), n, 2, world, min_ms)
         # scoring + selection alone (embeddings resident): the dominant kernel group of the index path
         qe = index._embed_queries(dq[0])
-        for _ in range(2):
-            index.search(qe)
-        sync_all()
-        ev0.record()
-        for _ in range(n):
-            index.search(qe)
-        ev1.record()
-        sync_all()
-        ksec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3 / n)
-        for i in range(3):                     # warm-up of the host-facing path (pinned result buffer, lazy kernel loads)
-            index(pq[i % pool])
-        sync_all()
-        t0 = time.perf_counter()
-        for i in range(n):
-            ids = index(pq[i % pool])          # host ids in, (Bq, K) identifiers out on the host
-        e2e_sec = max_over_ranks((time.perf_counter() - t0) / n)
-        return sec, ksec, e2e_sec, per_call, ids
+        kern = time_device_blocks(lambda i: index.search(qe), n, 2, world, min_ms)
+        # host-facing call: pinned host ids in, (Bq, K) identifiers out in a caller-owned pinned buffer
+        ids = [None]
+
+        def call(i):
+            ids[0] = index(pq[i % pool], out=outs[i % 2])
+
+        host = time_host_blocks(call, n, 3, world, min_ms)
+        return dev["ms_per_step"] * 1e-3, kern["ms_per_step"] * 1e-3, host["sec_per_step"], per_call, ids[0].copy()
 
     replicated = BruteForceIndex(INDEX_K, model.query_tower, pairs)
     replicated.impl = model.impl
@@ -613,7 +897,16 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hbm", action="store_true", help="skip the HBM-bound kernel rooflines (shorter ncu launch lists)")
     ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--customers", type=int, default=V_CUSTOMERS, help="rows of the customer table (BASELINE configs[4]: 100000000)")
+    ap.add_argument("--emb", type=int, default=JOINT, help="id-embedding and joint dimension (64 or 128)")
+    ap.add_argument("--min-ms", type=float, default=1000.0, help="every timed region repeats its block of --steps steps until it covers this much time")
+    ap.add_argument("--no-c3", action="store_true", help="skip the batch-65536 leg (BASELINE configs[2])")
+    ap.add_argument("--no-big-index", action="store_true", help="skip the 10M / 100M-row index legs (BASELINE configs[3])")
+    ap.add_argument("--big-index-rows", type=str, default="auto", help="comma list of corpus sizes for the row-sharded index leg (auto: 1e7, and 1e8 from 4 GPUs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-process multi-GPU parity checks")
     args = ap.parse_args()
+    g = globals()
+    g["V_CUSTOMERS"], g["E_ID"], g["JOINT"] = args.customers, args.emb, args.emb
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -147,6 +147,28 @@ __global__ void take_i32_kernel(const int32_t* __restrict__ table, const int32_t
     }
 }
 
+// value (global row r, column c) of the table initialiser: a hash of (seed, r * e + c) only, so a shard that holds rows
+// {row0 + i * row_stride} gets exactly the values the whole table would hold there
+__device__ __forceinline__ float unit_hash(uint64_t seed, uint64_t ctr) {
+    uint64_t z = ctr * 0x9E3779B97F4A7C15ull + seed;      // splitmix64 finaliser over a Weyl sequence
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);   // 24 random bits -> [0, 1)
+}
+
+__global__ void fill_uniform_kernel(float* __restrict__ out, int64_t rows_local, int e, int64_t row0, int64_t row_stride, uint64_t seed,
+                                    float lo, float span) {
+    const int64_t n = rows_local * e;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t r = i / e;
+        const int c = (int)(i - r * e);
+        out[i] = fmaf(unit_hash(seed, (uint64_t)((row0 + r * row_stride) * e + c)), span, lo);
+    }
+}
+
 static inline int grid_for(int64_t n, int block) {
     int64_t g = ceil_div(n, block);
     int64_t cap = (int64_t)sm_count() * 8;
@@ -269,6 +291,15 @@ int tt_take_i32(const int32_t* table, const int32_t* idx, int64_t n, int32_t* ou
     if (n == 0) return TT_OK;
     take_i32_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(table, idx, n, out);
     TT_LAUNCH_OK("take_i32_kernel");
+    return TT_OK;
+}
+
+int tt_fill_uniform(float* out, int64_t rows_local, int e, int64_t row0, int64_t row_stride, uint64_t seed, float lo, float hi, void* stream) {
+    TT_REQUIRE(out || rows_local == 0, "tt_fill_uniform: null pointer");
+    TT_REQUIRE(rows_local >= 0 && e >= 1 && row0 >= 0 && row_stride >= 1 && hi >= lo, "tt_fill_uniform: bad arguments");
+    if (rows_local == 0) return TT_OK;
+    fill_uniform_kernel<<<grid_for(rows_local * e, 256), 256, 0, as_stream(stream)>>>(out, rows_local, e, row0, row_stride, seed, lo, hi - lo);
+    TT_LAUNCH_OK("fill_uniform_kernel");
     return TT_OK;
 }
 

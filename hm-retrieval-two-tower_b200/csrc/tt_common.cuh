@@ -1,5 +1,6 @@
 // tt_common.cuh -- shared helpers for libtt.so (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -46,6 +47,29 @@ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize of one kernel, set once per device and raised when a launch needs more.  Lock-free
+// and safe from any number of host threads and devices (a lost race only repeats the idempotent driver call).  Declare one
+// `static SmemAttr` next to each launch site.
+struct SmemAttr {
+    static constexpr int kMaxDevices = 32;
+    std::atomic<int> cur[kMaxDevices];
+    SmemAttr() { for (auto& c : cur) c.store(0, std::memory_order_relaxed); }
+    template <typename F>
+    cudaError_t ensure(F* kernel, int bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const bool tracked = dev >= 0 && dev < kMaxDevices;
+        if (tracked && cur[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess && tracked) {
+            int old = cur[dev].load(std::memory_order_relaxed);
+            while (old < bytes && !cur[dev].compare_exchange_weak(old, bytes, std::memory_order_release)) {}
+        }
+        return e;
+    }
+};
 
 // carve a caller-provided workspace
 struct Carver {

@@ -211,7 +211,7 @@ int merge_launch(const float* s_in, const int32_t* i_in, int G, int nq, int K, i
     if (P < 2) P = 2;
     if (P > 16384) { set_error("tt_topk_merge: G*K=%d exceeds 16384", G * K); return TT_ERR_UNSUPPORTED; }
     size_t smem = (size_t)P * 8;
-    TT_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(topk_merge_kernel, 16384 * 8)); }
     topk_merge_kernel<<<(unsigned)nq, 256, smem, st>>>(s_in, i_in, G, nq, K, P, idx_add, s_out, i_out, flags);
     TT_LAUNCH_OK("topk_merge_kernel");
     return TT_OK;
@@ -234,10 +234,10 @@ int index_exact(const float* Q, int ldq, const float* C, int ldc, int nq, int64_
     int32_t* pi = cv.take<int32_t>((size_t)pl.nsplit * nq * K);
     dim3 grid((unsigned)ceil_div(nq, pl.bq), (unsigned)pl.nsplit);
     if (pl.bq == 64) {
-                TT_CUDA_OK(cudaFuncSetAttribute(index_exact_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IndexSmem<64, 256>)));
+                { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(index_exact_kernel<64, 256>, (int)sizeof(IndexSmem<64, 256>))); }
         index_exact_kernel<64, 256><<<grid, 256, pl.smem, st>>>(Q, ldq, C, ldc, nq, n, E, K, pl.per_split, ps, pi, flags);
     } else {
-                TT_CUDA_OK(cudaFuncSetAttribute(index_exact_kernel<8, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IndexSmem<8, 2048>)));
+                { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(index_exact_kernel<8, 2048>, (int)sizeof(IndexSmem<8, 2048>))); }
         index_exact_kernel<8, 2048><<<grid, 256, pl.smem, st>>>(Q, ldq, C, ldc, nq, n, E, K, pl.per_split, ps, pi, flags);
     }
     TT_LAUNCH_OK("index_exact_kernel");

@@ -202,7 +202,7 @@ static FlPlan fl_plan(int n_pass, const int* nR, const int* nT, int E) {
 template <int MODE, int E>
 static int launch_flash(const FlMaps& maps, const FlParams& p, int grid, cudaStream_t st, const char* name) {
     using Cfg = FlCfg<E>;
-    TT_CUDA_OK(cudaFuncSetAttribute(flash_kernel<MODE, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(flash_kernel<MODE, E>, Cfg::kSmemBytes)); }
     TT_CUDA_OK(launch_pdl(flash_kernel<MODE, E>, dim3((unsigned)grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, st, maps, p));
     TT_LAUNCH_OK(name);
     return TT_OK;

@@ -99,7 +99,7 @@ template <int MODE, int E, int BN>
 static int launch_rowpanel(const CUtensorMap& tmR, const CUtensorMap& tmT, const CUtensorMap& tmTt, const RowPanelParams& p, int m_tiles,
                            int splits, cudaStream_t st, const char* name) {
     using Cfg = RowPanelCfg<MODE, E, BN>;
-    TT_CUDA_OK(cudaFuncSetAttribute(rowpanel_kernel<MODE, E, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(rowpanel_kernel<MODE, E, BN>, Cfg::kSmemBytes)); }
     dim3 grid((unsigned)m_tiles, (unsigned)splits);
     rowpanel_kernel<MODE, E, BN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmR, tmT, tmTt, p);
     TT_LAUNCH_OK(name);
@@ -160,7 +160,7 @@ static SkPlan sk_plan(int n_pass, const int* m_tiles, const int* n_tiles) {
 template <int MODE, int E, int BN, bool H>
 static int launch_streamk(const SkMaps& maps, const SkParams& p, int grid, cudaStream_t st, const char* name) {
     using Cfg = SkCfg<MODE, E, BN, H>;
-    TT_CUDA_OK(cudaFuncSetAttribute(streamk_kernel<MODE, E, BN, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(streamk_kernel<MODE, E, BN, H>, Cfg::kSmemBytes)); }
     streamk_kernel<MODE, E, BN, H><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
     TT_LAUNCH_OK(name);
     return TT_OK;

@@ -290,7 +290,7 @@ template <bool G, int PM>
 static int launch_fwd_pm(const FeatArr& fa, const float* X, int ldx, const float* W, const float* b, float* Xout, float* Y, int ldy, float* Y32, int B,
                          int K, int N, int relu, cudaStream_t st) {
     const size_t smem = (size_t)K * (PM + 4 + PS) * sizeof(float);
-    TT_CUDA_OK(cudaFuncSetAttribute(dense_fwd_panel_kernel<G, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kPanelMaxK * PS * sizeof(float))));
+    { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(dense_fwd_panel_kernel<G, PM>, (int)(2 * kPanelMaxK * PS * sizeof(float)))); }
     dim3 grid((unsigned)ceil_div(B, PM), (unsigned)ceil_div(N, PT));
     dense_fwd_panel_kernel<G, PM><<<grid, 256, smem, st>>>(fa, X, ldx, W, b, Xout, Y, ldy, Y32, B, K, N, relu);
     TT_LAUNCH_OK("dense_fwd_panel_kernel");
@@ -347,7 +347,7 @@ int panel_dense_bwd(const float* X, int ldx, const float* W, const float* Y, int
     const size_t smem_dx = 2 * (size_t)N * PS * sizeof(float), smem_dw = (size_t)kDwSmemFloats * sizeof(float);
     const size_t smem = smem_dx > smem_dw ? smem_dx : smem_dw;
             const size_t mx = 2 * (size_t)kPanelMaxK * PS * sizeof(float);
-        TT_CUDA_OK(cudaFuncSetAttribute(dense_bwd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mx > smem_dw ? mx : smem_dw)));
+        { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(dense_bwd_panel_kernel, (int)(mx > smem_dw ? mx : smem_dw))); }
     dense_bwd_panel_kernel<<<(unsigned)(n_dx + nchunk * hy * hz), 256, smem, st>>>(X, ldx, W, Y, ldy, dY, lddy, dX, lddx, partial, B, K, N, relu, rows,
                                                                                    n_dx, gx, nchunk, hy);
     TT_LAUNCH_OK("dense_bwd_panel_kernel");

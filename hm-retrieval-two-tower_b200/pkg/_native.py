@@ -104,6 +104,7 @@ SIGNATURES = {
     "tt_round_tf32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "tt_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tt_take_i32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "tt_fill_uniform": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int64, ctypes.c_uint64, c_float, c_float, c_void_p]),
     "tt_recall_hits": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
 }
 

@@ -183,6 +183,13 @@ def set_seed(seed: int) -> None:
     _SEED[0] = int(seed)
 
 
+def next_seed() -> int:
+    """Seed of the next parameter tensor (same sequence as next_generator)."""
+    s = _SEED[0]
+    _SEED[0] += 1
+    return s
+
+
 def next_generator():
     torch = N.require_cuda()
     g = torch.Generator(device="cuda")

@@ -106,10 +106,25 @@ class DataParallel:
             raise ValueError("global_negatives needs row-sharded tables with peer_sync (device barriers + peer reads)")
         model.dist = self
         model._steps.clear()
-        # replicas must start identical: parameters are broadcast from rank 0
+        # replicas must start identical: the dense parameters are broadcast from rank 0.  Embedding tables nobody has used yet are
+        # NOT materialised for that: rank 0 broadcasts their 8-byte initialiser seeds and every rank fills the rows it will own
+        # (counter-based initialiser, EmbeddingTable) -- no whole-table allocation or broadcast.  Tables that already hold values
+        # (restored from a checkpoint, trained before attaching) are broadcast as before.
         dist.broadcast(model._store.params, src=0, group=group)
+        tables = []
         for _, _, t in model._tables():
-            dist.broadcast(t.weight, src=0, group=group)
+            if id(t) not in [id(x) for x in tables]:
+                tables.append(t)
+        meta = torch.tensor([[t.seed, int(t.materialised)] for t in tables], dtype=torch.int64, device="cuda").reshape(-1, 2)
+        mine = meta.clone()
+        dist.broadcast(meta, src=0, group=group)
+        used = torch.maximum(meta[:, 1], mine[:, 1])
+        dist.all_reduce(used, op=dist.ReduceOp.MAX, group=group)          # materialised on ANY rank -> take rank 0's values
+        for t, (seed, _), u in zip(tables, meta.tolist(), used.tolist()):
+            if u or not self.shard_tables:
+                dist.broadcast(t.weight, src=0, group=group)
+            else:
+                t.seed = int(seed)
         if self.shard_tables:
             seen = set()
             for _, _, t in model._tables():

@@ -25,36 +25,60 @@ def _to_device_f32(a):
 
 
 class BruteForceIndex(AbstractKerasModel):
-    def __init__(self, k: int, query_model, id_candidate_pairs: Iterable, shard: Optional[Tuple[int, int]] = None):
+    def __init__(self, k: int, query_model, id_candidate_pairs: Iterable, shard: Optional[Tuple[int, int]] = None,
+                 _local_rows: Optional[Tuple[int, int]] = None):
         """``id_candidate_pairs`` yields (ids (n,), embeddings (n, E)) batches.  ``shard=(rank, world)`` keeps only
-        this rank's contiguous slice of rows (see pkg.modelling.distributed.ShardedBruteForceIndex)."""
+        this rank's contiguous slice of rows (see pkg.modelling.distributed.make_sharded_index)."""
         super().__init__()
         self.k = int(k)
         self.query_model = query_model
         self.impl = N.TT_IMPL_AUTO
         self._shard = shard
-        self._index(id_candidate_pairs)
+        self._index(id_candidate_pairs, _local_rows)
         self._ws = None
         self._pos_of = None
         self.initialise_model()
 
-    def _index(self, id_candidate_pairs: Iterable) -> None:
+    @classmethod
+    def from_local_rows(cls, k: int, query_model, candidates_local, row_base: int, n_total: int, identifiers=None, group=None,
+                        world: int = 1) -> "BruteForceIndex":
+        """Row-sharded corpus whose shards are built where they live: this rank hands over ONLY its own rows
+        ``[row_base, row_base + n_local)`` of an ``n_total``-row corpus (no rank ever holds the whole corpus).
+        ``identifiers``: all ``n_total`` identifiers (position == global row), or None when a row's identifier is its
+        global row number.  ``world`` > 1: results are merged over the ranks of ``group`` like make_sharded_index's."""
+        n_local = int(candidates_local.shape[0])
+        if row_base < 0 or row_base + n_local > n_total:
+            raise ValueError(f"rows [{row_base}, {row_base + n_local}) lie outside a corpus of {n_total} rows")
+        if identifiers is not None and len(identifiers) != n_total:
+            raise ValueError(f"{len(identifiers)} identifiers for a corpus of {n_total} rows")
+        index = cls(k, query_model, [(identifiers, candidates_local)], _local_rows=(int(row_base), int(n_total)))
+        index._group, index._world = group, int(world)
+        return index
+
+    def _index(self, id_candidate_pairs: Iterable, local_rows: Optional[Tuple[int, int]] = None) -> None:
         torch = N.require_cuda()
-        identifiers, candidates = self.get_id_embeddings_from_dataset(id_candidate_pairs)
-        n_total = candidates.shape[0]
-        self.idx_base = 0
-        if self._shard is not None:
-            rank, world = self._shard
-            per = (n_total + world - 1) // world
-            lo, hi = min(n_total, rank * per), min(n_total, (rank + 1) * per)
-            self.idx_base = lo
-            candidates = candidates[lo:hi]
+        if local_rows is not None:
+            (identifiers, candidates), = list(id_candidate_pairs)
+            candidates = _to_device_f32(candidates)
+            self.idx_base, n_total = local_rows
+            if identifiers is not None:
+                identifiers = np.asarray(identifiers).reshape(-1)
+        else:
+            identifiers, candidates = self.get_id_embeddings_from_dataset(id_candidate_pairs)
+            n_total = candidates.shape[0]
+            self.idx_base = 0
+            if self._shard is not None:
+                rank, world = self._shard
+                per = (n_total + world - 1) // world
+                lo, hi = min(n_total, rank * per), min(n_total, (rank + 1) * per)
+                self.idx_base = lo
+                candidates = candidates[lo:hi]
         self.n_total = n_total
-        self._identifiers = identifiers                       # all ids (host), position == global row index
+        self._identifiers = identifiers                       # all ids (host), position == global row index; None: id == row number
         # numeric identifiers are also kept on the device: `call` then maps row indices to identifiers there and
         # copies only the (B, k) result out (through a pinned buffer) instead of gathering on the host
         self._identifiers_dev = (torch.from_numpy(np.ascontiguousarray(identifiers)).cuda()
-                                 if np.issubdtype(np.asarray(identifiers).dtype, np.integer) else None)
+                                 if identifiers is not None and np.issubdtype(np.asarray(identifiers).dtype, np.integer) else None)
         self._candidates = candidates.contiguous()            # (N_local, E) fp32, non-trainable
         # operand preparation for the tensor-core filter, done once at build time: permuted TF32-rounded copy of
         # the corpus and the row norms (error bound of the filter); the exact fp32 rows stay authoritative
@@ -136,8 +160,10 @@ class BruteForceIndex(AbstractKerasModel):
         torch = N.require_cuda()
         lib = N.load()
         _, idx = self.query_indices(queries)
-        if self._identifiers_dev is not None:
-            if self._identifiers_dev.dtype == torch.int32:
+        if self._identifiers_dev is not None or self._identifiers is None:
+            if self._identifiers is None:
+                ids_dev = idx
+            elif self._identifiers_dev.dtype == torch.int32:
                 ids_dev = torch.empty_like(idx)
                 N.check(lib.tt_take_i32(self._identifiers_dev.data_ptr(), idx.data_ptr(), idx.numel(), ids_dev.data_ptr(), N.stream_ptr()), "tt_take_i32")
             else:
@@ -160,6 +186,9 @@ class BruteForceIndex(AbstractKerasModel):
     def positions_of(self, ids) -> np.ndarray:
         """Global row index of each identifier (-1 when absent); used by IndexRecall's device path."""
         flat = np.asarray(ids).reshape(-1)
+        if self._identifiers is None:     # identifier == global row number
+            pos = np.array([int(v) for v in flat], dtype=np.int64)
+            return np.where((pos >= 0) & (pos < self.n_total), pos, -1).astype(np.int32)
         if self._pos_of is None:
             self._pos_of = {}
             for i, v in enumerate(self._identifiers):
@@ -205,6 +234,6 @@ class BruteForceIndex(AbstractKerasModel):
         return cls(k, query_model, [(ids, cand)], shard=shard)
 
     def state_arrays(self) -> Dict[str, np.ndarray]:
-        ids = np.asarray(self._identifiers)
+        ids = np.asarray(self._identifiers if self._identifiers is not None else np.arange(self.n_total, dtype=np.int32))
         return {"identifiers": ids if np.issubdtype(ids.dtype, np.integer) else ids.astype(str),
                 "candidates": self._candidates.detach().cpu().numpy()}

@@ -22,7 +22,12 @@ from pkg.schema.features import Feature
 
 
 class EmbeddingTable:
-    """Embedding(len(vocab)+1, e) with tf-keras' default RandomUniform(-0.05, 0.05) initialiser."""
+    """Embedding(len(vocab)+1, e) with tf-keras' default RandomUniform(-0.05, 0.05) initialiser.
+
+    The rows are materialised on first use, by a counter-based generator (tt_fill_uniform): a cell's value depends on
+    (seed, row, column) only.  A table that is row-sharded BEFORE its first use (DataParallel(shard_tables=True) attached to a
+    fresh model) is therefore initialised shard by shard on the owning GPUs -- no rank ever allocates, fills or broadcasts the
+    whole table -- and holds exactly the values the unsharded table would."""
 
     def __init__(self, feature: Feature):
         torch = N.require_cuda()
@@ -34,10 +39,37 @@ class EmbeddingTable:
         self.vocab = D.Vocab(feature.vocab)
         self.e = int(feature.embedding_size)
         self.rows = self.vocab.rows
-        self.weight = torch.empty((self.rows, self.e), dtype=torch.float32, device="cuda")
-        self.weight.uniform_(-0.05, 0.05, generator=D.next_generator())
+        self._weight = None
+        self.seed = D.next_seed()
         # row sharding over the ranks of a process group (pkg.modelling.distributed.DataParallel(shard_tables=True))
         self.shard_rank, self.shard_world, self._peer, self._group = 0, 1, None, None
+
+    # ---- storage -------------------------------------------------------------------------------------
+    @property
+    def materialised(self) -> bool:
+        return self._weight is not None
+
+    @property
+    def weight(self):
+        """(rows, e) fp32 rows in HBM -- this rank's (local_rows, e) shard once the table is row-sharded."""
+        if self._weight is None:
+            torch = N.require_cuda()
+            self._weight = torch.empty((self.rows, self.e), dtype=torch.float32, device="cuda")
+            self._fill(self._weight, self.rows, 0, 1)
+        return self._weight
+
+    @weight.setter
+    def weight(self, value) -> None:
+        self._weight = value
+
+    @property
+    def local_shape(self):
+        """Shape of ``weight`` without materialising it (optimizer slots take this shape)."""
+        return (self.rows, self.e) if self.shard_world == 1 else (self.local_rows, self.e)
+
+    def _fill(self, out, n_rows: int, row0: int, row_stride: int) -> None:
+        N.check(N.load().tt_fill_uniform(out.data_ptr(), n_rows, self.e, row0, row_stride, self.seed, -0.05, 0.05, N.stream_ptr()),
+                "tt_fill_uniform")
 
     # ---- row sharding (one process per GPU) ---------------------------------------------------------
     @property
@@ -57,12 +89,15 @@ class EmbeddingTable:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world == 1:
             return
-        full = self.weight
+        full = self._weight
         self.shard_rank, self.shard_world, self._group = rank, world, group
         self._peer = PeerBuffer((self.local_rows, self.e), "float32", group)
-        mine = full[rank::world]
-        self._peer.local[: mine.shape[0]].copy_(mine)
-        self.weight = self._peer.local
+        if full is None:       # never used: the owner initialises its rows {rank, rank + world, ...} in place
+            self._fill(self._peer.local, (self.rows - rank + world - 1) // world, rank, world)
+        else:
+            mine = full[rank::world]
+            self._peer.local[: mine.shape[0]].copy_(mine)
+        self._weight = self._peer.local
 
     def table_pointer(self) -> int:
         """What tt_feature.table holds: the table itself, or the device array of shard base pointers."""

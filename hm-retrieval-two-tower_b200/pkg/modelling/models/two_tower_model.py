@@ -161,7 +161,9 @@ class TwoTowerModel(AbstractKerasModel):
         self._steps.clear()
         self._opt_state = {
             "dense": [torch.full_like(self._store.params, v) for v in init],
-            "tables": {id(t): [torch.full_like(t.weight, v) for v in init] for _, _, t in self._tables()},
+            # table slots take the shape of the table's local storage WITHOUT materialising a table nobody has used yet (a table
+            # that is about to be row-sharded is initialised shard by shard, see EmbeddingTable)
+            "tables": {id(t): [torch.full(t.local_shape, v, dtype=torch.float32, device="cuda") for v in init] for _, _, t in self._tables()},
         }
 
     def _step_ws(self, batch: int) -> _StepWorkspace:

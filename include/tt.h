@@ -241,6 +241,11 @@ int tt_topk_merge(const float* scores, const int32_t* idx, int G, int nq, int K,
  * integer identifiers; absent entries (-1) read row 0). */
 int tt_take_i32(const int32_t* table, const int32_t* idx, int64_t n, int32_t* out, void* stream);
 
+/* Embedding-table initialiser (tf-keras RandomUniform(lo, hi), reference input_layer.py:33-38 builds Embedding() with the default):
+ * out[i, c] = lo + (hi - lo) * u(seed, (row0 + i * row_stride) * e + c), u a counter-based hash -> the value of a table cell depends
+ * on (seed, global row, column) only, so a row shard initialised by its owner holds what the whole table would hold in those rows. */
+int tt_fill_uniform(float* out, int64_t rows_local, int e, int64_t row0, int64_t row_stride, uint64_t seed, float lo, float hi, void* stream);
+
 /* hits[t] += sum_{b, j < ks[t]} [true_idx[b] == cand[b, j]]   (index_recall.py:54-58; int32 exact).
  * cand is (nq, k_stride) int32; hits is int32[nk] on the device and is accumulated into. */
 int tt_recall_hits(const int32_t* cand, int k_stride, const int32_t* true_idx, int nq, const int32_t* ks, int nk,

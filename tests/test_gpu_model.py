@@ -427,3 +427,105 @@ def test_c1_config_full_vocabularies_train_step_and_top12_index(lib):
     metric = IndexRecall(index, ks=[1, 12])
     metric(q, ids[want[:, 3]].reshape(-1, 1))                                   # "truth" = each query's 4th-ranked article
     assert metric.hits[1] == 0 and metric.hits[12] == 256 and metric.metric[12] == np.float64(1.0)
+
+
+def test_recompile_after_training_uses_the_new_optimizer_slots(lib):
+    """compile() / load() after training replace the optimizer slot tensors; the cached step workspaces (job lists, captured
+    graphs) pointed at the old ones.  A recompiled model must continue exactly like a fresh model holding the same weights."""
+    import torch
+
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+
+    def fresh():
+        set_seed(11)
+        qf, cf = _c2_features(3000, 500)
+        m = TwoTowerModel(qf, cf, "article_id", 64, candidate_prob_lookup={str(i + 1): 1.0 / 500 for i in range(500)})
+        m.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))
+        return m
+
+    rng = np.random.default_rng(3)
+    b1, b2 = _batch(rng, 512, 3000, 500), _batch(rng, 512, 3000, 500)
+    a = fresh()
+    a.train_step(b1)
+    a.train_step(b1)                                   # second call replays the captured graph
+    weights = {k: v.copy() for k, v in a.state_arrays().items()}
+    a.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))     # fresh accumulators (0.1)
+    junk = [torch.full((1 << 20,), 7.0, device="cuda") for _ in range(8)]                        # recycle the freed slot memory
+    la = float(a.train_step(b2)["loss"])
+    b = fresh()
+    b.query_tower.load_state_arrays(weights, "query_tower/")
+    b.candidate_tower.load_state_arrays(weights, "candidate_tower/")
+    sb0 = b.state_arrays()
+    assert all(np.array_equal(sb0[k], weights[k]) for k in weights)
+    lb = float(b.train_step(b2)["loss"])
+    sa, sb = a.state_arrays(), b.state_arrays()
+    assert la == lb and all(np.array_equal(sa[k], sb[k]) for k in sa)
+    del junk
+
+
+def test_embedding_rows_do_not_depend_on_the_sharding(lib):
+    """tt_fill_uniform: a cell is a function of (seed, global row, column), so shards filled by their owners hold what the whole
+    table holds; values are uniform on [-0.05, 0.05) like tf-keras' Embedding default."""
+    import torch
+
+    from pkg import _native as N
+
+    rows, e, seed = 10_007, 24, 1234
+    full = torch.empty((rows, e), device="cuda")
+    N.check(lib.tt_fill_uniform(full.data_ptr(), rows, e, 0, 1, seed, -0.05, 0.05, N.stream_ptr()))
+    for world in (2, 3, 8):
+        for r in range(world):
+            n_r = (rows - r + world - 1) // world
+            part = torch.full((n_r + 1, e), 9.0, device="cuda")
+            N.check(lib.tt_fill_uniform(part.data_ptr(), n_r, e, r, world, seed, -0.05, 0.05, N.stream_ptr()))
+            assert torch.equal(part[:n_r], full[r::world]) and bool((part[n_r] == 9.0).all())
+    f = full.double()
+    assert float(f.min()) >= -0.05 and float(f.max()) < 0.05
+    assert abs(float(f.mean())) < 5e-4 and abs(float(f.std()) - 0.1 / np.sqrt(12)) < 5e-4
+    assert abs(float(torch.corrcoef(torch.stack([f[:-1, 0], f[1:, 0]]))[0, 1])) < 0.05      # neighbouring rows uncorrelated
+    other = torch.empty_like(full)
+    N.check(lib.tt_fill_uniform(other.data_ptr(), rows, e, 0, 1, seed + 1, -0.05, 0.05, N.stream_ptr()))
+    assert not torch.equal(other, full)
+    assert lib.tt_fill_uniform(None, 4, e, 0, 1, seed, -0.05, 0.05, None) != 0                # null pointer is an error, not a crash
+
+
+def test_index_from_local_rows_equals_the_whole_corpus_index(lib):
+    """from_local_rows: two shards built from their own rows, merged, answer like the index over the whole corpus; without
+    identifiers the call returns global row numbers."""
+    import torch
+
+    from pkg import _native as N
+    from pkg.modelling.indices.brute_force import BruteForceIndex
+
+    n, e, k, nq = 20_000, 64, 50, 96
+    g = torch.Generator(device="cuda").manual_seed(8)
+    corpus = torch.randn((n, e), generator=g, device="cuda") * 0.3
+    q = torch.randn((nq, e), generator=g, device="cuda")
+    class Ident:                    # query "tower": the embeddings themselves
+        def __call__(self, x):
+            return x["q"]
+
+        def get_input_signature(self):
+            return {}
+
+    ident = Ident()
+    whole = BruteForceIndex(k, ident, [(np.arange(n, dtype=np.int32), corpus)])
+    s0, i0 = whole.search(q)
+    cut = 7_777
+    parts = [BruteForceIndex.from_local_rows(k, ident, corpus[:cut], 0, n), BruteForceIndex.from_local_rows(k, ident, corpus[cut:], cut, n)]
+    ss, ii = zip(*(p.search(q) for p in parts))
+    all_s, all_i = torch.stack(ss).contiguous(), torch.stack(ii).contiguous()
+    out_s, out_i = torch.empty_like(s0), torch.empty_like(i0)
+    N.check(lib.tt_topk_merge(all_s.data_ptr(), all_i.data_ptr(), 2, nq, k, out_s.data_ptr(), out_i.data_ptr(), N.stream_ptr()))
+    assert torch.equal(out_i, i0) and torch.equal(out_s, s0)
+    one = BruteForceIndex.from_local_rows(k, ident, corpus, 0, n)
+    got = one({"q": q})
+    assert got.dtype == np.int32 and np.array_equal(got, i0.cpu().numpy())
+    pinned = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+    view = one({"q": q}, out=pinned)
+    assert np.array_equal(view, got) and view.ctypes.data == pinned.data_ptr()
+    assert np.array_equal(one.positions_of([0, 5, n - 1, n, -3]), [0, 5, n - 1, -1, -1])
+    with pytest.raises(ValueError):
+        BruteForceIndex.from_local_rows(k, ident, corpus[:10], n - 5, n)

@@ -223,3 +223,75 @@ def test_data_parallel_adam_row_sharded_equals_replicated(tmp_path):
                 assert np.array_equal(a, b_), k
     moved = [k for k in rep[0].files if k.startswith("after3/") and "embedding" in k]
     assert moved and all(not np.array_equal(rep[0][k], rep[0]["before/" + k[len("after3/"):]]) for k in moved)
+
+
+def _worker_owner_init(rank, world, port, out):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "hm-retrieval-two-tower_b200"))
+    import torch
+    import torch.distributed as dist
+
+    from pkg.modelling._device import set_seed
+    from pkg.modelling.distributed import DataParallel
+    from pkg.modelling.models.two_tower_model import TwoTowerModel
+    from pkg.modelling.optimizer_factory import OptimizerFactory
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        def build(seed):
+            set_seed(seed)
+            qf, cf = _features()
+            m = TwoTowerModel(qf, cf, "article_id", 32, candidate_prob_lookup={str(i + 1): 1.0 / 300 for i in range(300)})
+            m.compile(optimizer=OptimizerFactory.get_optimizer("adagrad", {"learning_rate": 0.05}))
+            return m
+
+        a = build(17 + rank)                              # different seeds per rank: rank 0's must win, as with the broadcast
+        assert not any(t.materialised for _, _, t in a._tables())
+        DataParallel(a, shard_tables=True)
+        assert all(t.materialised and t.weight.shape[0] == t.local_rows for _, _, t in a._tables())   # only the shard exists
+        sa = a.state_arrays()
+        b = build(17)                                     # the single-process model of rank 0's seed
+        sb = b.state_arrays()
+        c = build(17 + rank)
+        for _, _, t in c._tables():
+            t.weight                                      # materialise first: the broadcast-and-slice path
+        DataParallel(c, shard_tables=True)
+        rng = np.random.default_rng(100)
+        batches = [_batch(rng, 96) for _ in range(world)]
+        la, lc = float(a.train_step(batches[rank])["loss"]), float(c.train_step(batches[rank])["loss"])
+        a.dist.barrier(); c.dist.barrier()
+        ta, tc = a.state_arrays(), c.state_arrays()
+        np.savez(out, la=la, lc=lc, **{"a/" + k: v for k, v in sa.items()}, **{"b/" + k: v for k, v in sb.items()},
+                 **{"ta/" + k: v for k, v in ta.items()}, **{"tc/" + k: v for k, v in tc.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_row_shards_initialised_by_their_owners_equal_the_unsharded_table(tmp_path):
+    """A table that is row-sharded before its first use is filled shard by shard on the owners (no whole-table allocation or
+    broadcast); it must hold the single-process table of rank 0's seed, and training must not depend on which path built it."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, port = 2, _free_port()
+    outs = [str(tmp_path / f"owner{r}.npz") for r in range(world)]
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_worker_owner_init, args=(r, world, port, outs[r])) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(280)
+        assert p.exitcode == 0
+    res = [np.load(o) for o in outs]
+    keys = [k[2:] for k in res[0].files if k.startswith("a/")]
+    assert any("embedding" in k for k in keys)
+    for r in res:
+        for k in keys:
+            assert np.array_equal(r["a/" + k], r["b/" + k]), k              # owner-initialised == unsharded, bit for bit
+            assert np.array_equal(r["ta/" + k], r["tc/" + k]), k            # and trains like the broadcast-and-slice path
+        assert float(r["la"]) == float(r["lc"])
+    for k in keys:
+        assert np.array_equal(res[0]["ta/" + k], res[1]["ta/" + k]), k
