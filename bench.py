@@ -212,6 +212,25 @@ def run_reference(args):
 
 
 
+def index_stage_ms(lib, index, qe, reps=5):
+    """Device time of the index search by stage (tt_debug_index_stages: CUDA events around each stage of a few extra, untimed calls)."""
+    import ctypes
+
+    import torch
+
+    arr = (ctypes.c_float * 8)()
+    torch.cuda.synchronize()
+    lib.tt_debug_index_stages(arr)
+    try:
+        for _ in range(reps):
+            index.search(qe)
+        torch.cuda.synchronize()
+    finally:
+        lib.tt_debug_index_stages(None)
+    names = ["prepare_queries", "threshold_pass", "select_threshold", "collect_pass", "rescore_sort", "exact_fallback"]
+    return {n: arr[i] / reps for i, n in enumerate(names)}
+
+
 # ---------------------------------------------------------------------------------------------------
 # timing: blocks of exactly K steps, repeated until the timed region covers >= min_ms; the median block is reported
 # ---------------------------------------------------------------------------------------------------
@@ -404,11 +423,13 @@ def run_ours(args):
         line["roofline"] = softmax_roofline(model, B, pk, lib)
         if not args.no_hbm:
             line["hbm_kernels"] = hbm_rooflines(pk, lib)
-    if not args.no_c3 and not args.global_negatives and B != C3_BATCH:
-        line["c3"] = c3_leg(model, args, pk, lib, world, rank)     # BASELINE configs[2]: the same model at batch 65536 per GPU
     line["index"] = index_bench(model, pk, lib, K, world, args)   # every rank takes part (row-sharded corpus when N > 1)
     if not args.no_big_index:
         line["index"]["row_sharded_large"] = big_index_legs(model, pk, lib, K, world, rank, args)
+    if not args.no_c3 and not args.global_negatives and B != C3_BATCH:
+        # after the index legs: a few hundred more SUM-loss steps at 8x the batch, unscheduled lr, collapse this synthetic model onto
+        # the Zipf head, and an index over a collapsed corpus measures the exact-fallback path instead of the filter
+        line["c3"] = c3_leg(model, args, pk, lib, world, rank)     # BASELINE configs[2]: the same model at batch 65536 per GPU
     if world > 1 and not args.no_parity:
         line["parity"] = multi_gpu_parity(world, rank, args)
         line["parity_ok"] = bool(all(v.get("ok") for v in line["parity"].values())
@@ -520,6 +541,7 @@ def big_index_legs(model, pk, lib, steps, world, rank, args):
                "search_only_ms": kern["ms_per_step"], "e2e": {"value": INDEX_BQ / host["sec_per_step"], "unit": "queries/s",
                                                               "h2d_bytes_per_step": INDEX_BQ * 8, "d2h_bytes_per_step": INDEX_BQ * INDEX_K * 4},
                "blocks": dev["blocks"], "timed_region_ms": dev["region_ms"], "shard_build_s": _reduce(build_s, world),
+               "stage_ms": index_stage_ms(lib, index, qe, 2),
                "config": f"{n_rows} x {JOINT} fp32 synthetic corpus ({n_rows * JOINT * 4 / 1e9:.1f} GB + prepared copy), K={INDEX_K}, Bq={INDEX_BQ} replicated queries; "
                          + (f"rows sharded over {world} GPUs, each shard generated on its owner (no rank holds the corpus), per-shard top-K all-gathered "
                             f"(NCCL) and merged on the device" if world > 1 else "single shard"),
@@ -857,7 +879,10 @@ def index_bench(model, pk, lib, steps, world=1, args=None):
             ids[0] = index(pq[i % pool], out=outs[i % 2])
 
         host = time_host_blocks(call, n, 3, world, min_ms)
+        stages[0] = index_stage_ms(lib, index, qe)
         return dev["ms_per_step"] * 1e-3, kern["ms_per_step"] * 1e-3, host["sec_per_step"], per_call, ids[0].copy()
+
+    stages = [None]
 
     replicated = BruteForceIndex(INDEX_K, model.query_tower, pairs)
     replicated.impl = model.impl
@@ -871,7 +896,7 @@ def index_bench(model, pk, lib, steps, world=1, args=None):
            "gpu_launches_per_batch": per_call,
            "roofline": {"bound": "tensor", "kernel": "index scoring + top-K (per GPU)", "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
                         "frac": ach / pk["tflops_burst"], "traffic": None, "ms": ksec * 1e3, "algorithmic_flop": flops},
-           "sample_ids": [str(x) for x in ids[0, :3]]}
+           "stage_ms": stages[0], "sample_ids": [str(x) for x in ids[0, :3]]}
     if world > 1:
         sharded = make_sharded_index(INDEX_K, model.query_tower, pairs)
         sharded.impl = model.impl

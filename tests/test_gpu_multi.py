@@ -121,7 +121,7 @@ def test_data_parallel_step_and_sharded_index_on_two_gpus(tmp_path):
         for r in range(world):
             a, b_ = res[r][k], res_sh[r][k]
             if a.dtype.kind == "f":
-                np.testing.assert_allclose(b_, a, rtol=0, atol=2e-6 * (1.0 + float(np.abs(a).max())), err_msg=k)
+                np.testing.assert_allclose(b_, a, rtol=0, atol=1e-5 * (1.0 + float(np.abs(a).max())), err_msg=k)   # the dense-gradient sums round differently (torch.sum vs rank-order peer sum); Adam's m / sqrt(v) amplifies an ulp
             else:
                 assert np.array_equal(a, b_), k
     keys = [k for k in res[0].files if k.startswith("after")]
@@ -218,7 +218,7 @@ def test_data_parallel_adam_row_sharded_equals_replicated(tmp_path):
         for r in range(world):
             a, b_ = rep[r][k], sh[r][k]
             if a.dtype.kind == "f":
-                np.testing.assert_allclose(b_, a, rtol=0, atol=2e-6 * (1.0 + float(np.abs(a).max())), err_msg=k)
+                np.testing.assert_allclose(b_, a, rtol=0, atol=1e-5 * (1.0 + float(np.abs(a).max())), err_msg=k)   # the dense-gradient sums round differently (torch.sum vs rank-order peer sum); Adam's m / sqrt(v) amplifies an ulp
             else:
                 assert np.array_equal(a, b_), k
     moved = [k for k in rep[0].files if k.startswith("after3/") and "embedding" in k]
