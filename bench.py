@@ -384,11 +384,7 @@ def run_ours(args):
     clocks = clk.summary()
 
     # end-to-end through the public API: pinned host ids -> H2D -> step -> loss D2H, every step
-    last = [0.0]
-
-    def e2e_step(i):
-        last[0] = float(model.train_step(pinned[i % pool])["loss"])
-
+    e2e_step, last = pipelined_loss_step(model, pinned)
     host = time_host_blocks(e2e_step, K, 3, world, args.min_ms)
     loss = last[0]
     e2e = world * B / host["sec_per_step"]
@@ -403,7 +399,9 @@ def run_ours(args):
                    "l2": "inputs larger than L2: tables + Adagrad accumulators 0.76 GB, random rows each step; no explicit flush",
                    "last_loss": loss},
         "e2e": {"value": e2e, "unit": "examples/s", "h2d_bytes_per_step": B * BYTES_PER_EXAMPLE_H2D, "d2h_bytes_per_step": 4,
-                "blocks": host["blocks"], "timed_region_ms": host["region_ms"]},
+                "blocks": host["blocks"], "timed_region_ms": host["region_ms"],
+                "how": "model.train_step on pinned host columns (staged by one kernel reading them in place), loss of every step copied to "
+                       "pinned memory and read on the host one step late"},
         "gpu_launches": launches_per_step * K, "clocks": clocks,
         "timing": {"blocks": dev["blocks"], "steps_per_block": K, "timed_region_ms": dev["region_ms"], "ms_per_step_mean": dev["ms_per_step_mean"],
                    "ms_per_step_min_block": dev["ms_per_step_min"], "ms_per_step_max_block": dev["ms_per_step_max"],
@@ -417,8 +415,9 @@ def run_ours(args):
             else "replicated (all-gathered gradient rows)"
         if args.global_negatives:
             line["config"]["negatives"] = f"cross-GPU: {world * B} candidate columns per query row (all-gathered over NVLink peer memory)"
-        line["dp_phases_ms"] = dp_phase_times(model, B, dev_batches)
         barrier()       # every rank's last table update has landed before anybody embeds the corpus
+    line["dp_phases_ms" if world > 1 else "step_phases_ms"] = dp_phase_times(model, B, dev_batches)
+    barrier()
     if rank == 0:
         line["roofline"] = softmax_roofline(model, B, pk, lib)
         if not args.no_hbm:
@@ -452,6 +451,32 @@ def run_ours(args):
 C3_BATCH = 65536
 
 
+def pipelined_loss_step(model, pinned):
+    """The end-to-end step: pinned host columns in (read in place by the one staging kernel), train_step, and the step's loss copied
+    to pinned host memory and READ on the host -- one step late, while the next step already runs (two slots, one event each), so
+    the read does not drain the GPU.  Every step's loss is read exactly once."""
+    import torch
+
+    slots = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    evs = [torch.cuda.Event(), torch.cuda.Event()]
+    pending = [False, False]
+    last = [0.0]
+    pool = len(pinned)
+
+    def step(i):
+        s = i & 1
+        out = model.train_step(pinned[i % pool])
+        slots[s].copy_(out["loss"].reshape(1), non_blocking=True)
+        evs[s].record()
+        pending[s] = True
+        if pending[1 - s]:
+            evs[1 - s].synchronize()
+            last[0] = float(slots[1 - s][0])
+            pending[1 - s] = False
+
+    return step, last
+
+
 def c3_leg(model, args, pk, lib, world, rank):
     """BASELINE configs[2] ("c3"): the same towers at batch 65536 per GPU -- 64x the logits of c2 per step, the shape where the
     in-batch softmax dominates.  Same timing rules as the headline leg."""
@@ -465,11 +490,7 @@ def c3_leg(model, args, pk, lib, world, rank):
     pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in hb.items()} for hb in host]
     k = max(2, min(args.steps, 10))
     dev = time_device_blocks(lambda i: model.train_step(devb[i % pool]), k, 3, world, args.min_ms / 2)
-    last = [0.0]
-
-    def e2e_step(i):
-        last[0] = float(model.train_step(pinned[i % pool])["loss"])
-
+    e2e_step, last = pipelined_loss_step(model, pinned)
     hostt = time_host_blocks(e2e_step, k, 2, world, args.min_ms / 2)
     out = {"workload": workload_name(B).replace("c2:", "c3:"), "value": world * B / (dev["ms_per_step"] * 1e-3), "unit": "examples/s",
            "ms_per_step": dev["ms_per_step"], "steps": k, "blocks": dev["blocks"], "timed_region_ms": dev["region_ms"],
@@ -673,38 +694,37 @@ def multi_gpu_parity(world, rank, args):
     return out
 
 
-def dp_phase_times(model, B, dev_batches, n=20):
-    """Device time of the four phases of a data-parallel step (rank-local CUDA events; explains the scaling number).  The phases are
-    replayed as separate CUDA graphs here (the timed step itself is one graph when the ranks synchronise through device barriers), so
-    the barrier phases show how long this rank waited for the slowest one."""
+def dp_phase_times(model, B, dev_batches, n=200):
+    """Device time of the four phases of a data-parallel step measured INSIDE the real step graph: the step is re-captured with
+    tt_stamp kernels (%globaltimer) between the phases and n steps run back to back, like the timed region.  sync_* is what the
+    device barrier costs this rank, including waiting for the slowest one."""
     import torch
 
-    sw = model._step_ws(B)
-    if not isinstance(sw.graph, tuple):
-        return None
-    if len(sw.graph) == 2:
-        phases = [lambda: model._phase_pre(sw), sw.graph[0].replay, lambda: model._phase_mid(sw), sw.graph[1].replay]
-    else:
-        graphs = []
-        for fn in (model._phase_pre, model._phase_a, model._phase_mid, model._phase_b):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fn(sw)
-            graphs.append(g)
-        phases = [g.replay for g in graphs]
-    acc = [0.0] * 4
-    for i in range(n):
-        model._stage(sw, dev_batches[i % len(dev_batches)])
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        for k in range(4):
-            ev[k].record()
-            phases[k]()
-        ev[4].record()
+    ring_len = n
+    ring = torch.zeros(1 + ring_len * 5, dtype=torch.int64, device="cuda")
+    model.phase_stamps = ring
+    saved = model._steps.pop(B, None)      # re-capture this batch shape with the stamps in the graph
+    try:
+        for i in range(4):                 # eager step, capture, two replays
+            model.train_step(dev_batches[i % len(dev_batches)])
         torch.cuda.synchronize()
-        for k in range(4):
-            acc[k] += ev[k].elapsed_time(ev[k + 1]) / n
-    return {"sync_ids": acc[0], "phase_a": acc[1], "sync_grads": acc[2], "phase_b": acc[3],
-            "note": "this rank's CUDA events; sync_* = NCCL all-gather or device barrier incl. waiting for the slowest rank"}
+        ring.zero_()
+        for i in range(n):
+            model.train_step(dev_batches[i % len(dev_batches)])
+        torch.cuda.synchronize()
+        t = ring[1:].view(ring_len, 5).double().cpu().numpy()
+    finally:
+        model.phase_stamps = None
+        model._steps.pop(B, None)
+        if saved is not None:
+            model._steps[B] = saved
+    d = np.diff(t, axis=1) * 1e-6          # ms
+    gap = (t[1:, 0] - t[:-1, 4]) * 1e-6   # end of a step -> start of the next (graph launch gap)
+    med = np.median(d, axis=0)
+    return {"sync_ids": float(med[0]), "phase_a": float(med[1]), "sync_grads": float(med[2]), "phase_b": float(med[3]),
+            "between_steps": float(np.median(gap)), "steps": n,
+            "note": "this rank, medians over back-to-back steps, stamps inside the captured step graph (each stamp kernel adds ~2 us); "
+                    "sync_* = device barrier incl. waiting for the slowest rank"}
 
 
 def softmax_roofline(model, B, pk, lib):

@@ -147,6 +147,31 @@ __global__ void take_i32_kernel(const int32_t* __restrict__ table, const int32_t
     }
 }
 
+struct StageArgs {
+    tt_stage_col col[TT_MAX_STAGE_COLS];
+};
+
+// blockIdx.y = column; 16-byte accesses when both ends allow it (device buffers and pinned host memory alike)
+__global__ void __launch_bounds__(256) stage_columns_kernel(const __grid_constant__ StageArgs a, int64_t rows) {
+    const tt_stage_col c = a.col[blockIdx.y];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c.kind == 0) {
+        const bool vec = ((reinterpret_cast<uintptr_t>(c.src) | reinterpret_cast<uintptr_t>(c.dst)) & 15) == 0;
+        const int64_t n4 = vec ? rows / 4 : 0;
+        const uint4* s4 = reinterpret_cast<const uint4*>(c.src);
+        uint4* d4 = reinterpret_cast<uint4*>(c.dst);
+        for (int64_t j = i; j < n4; j += stride) d4[j] = s4[j];
+        const uint32_t* s1 = reinterpret_cast<const uint32_t*>(c.src);
+        uint32_t* d1 = reinterpret_cast<uint32_t*>(c.dst);
+        for (int64_t j = n4 * 4 + i; j < rows; j += stride) d1[j] = s1[j];
+    } else {
+        const long long* s8 = reinterpret_cast<const long long*>(c.src);
+        int32_t* d1 = reinterpret_cast<int32_t*>(c.dst);
+        for (int64_t j = i; j < rows; j += stride) d1[j] = (int32_t)s8[j];
+    }
+}
+
 // value (global row r, column c) of the table initialiser: a hash of (seed, r * e + c) only, so a shard that holds rows
 // {row0 + i * row_stride} gets exactly the values the whole table would hold there
 __device__ __forceinline__ float unit_hash(uint64_t seed, uint64_t ctr) {
@@ -291,6 +316,23 @@ int tt_take_i32(const int32_t* table, const int32_t* idx, int64_t n, int32_t* ou
     if (n == 0) return TT_OK;
     take_i32_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(table, idx, n, out);
     TT_LAUNCH_OK("take_i32_kernel");
+    return TT_OK;
+}
+
+int tt_stage_columns(const tt_stage_col* cols, int n_cols, int64_t rows, void* stream) {
+    TT_REQUIRE(n_cols >= 0 && n_cols <= TT_MAX_STAGE_COLS && rows >= 0, "tt_stage_columns: at most %d columns", TT_MAX_STAGE_COLS);
+    if (n_cols == 0 || rows == 0) return TT_OK;
+    TT_REQUIRE(cols != nullptr, "tt_stage_columns: null pointer");
+    StageArgs a;
+    for (int i = 0; i < n_cols; ++i) {
+        TT_REQUIRE(cols[i].src && cols[i].dst && (cols[i].kind == 0 || cols[i].kind == 1), "tt_stage_columns: column %d: null pointer or bad kind", i);
+        a.col[i] = cols[i];
+    }
+    int64_t gx = ceil_div(rows, 4 * 256);
+    if (gx > 64) gx = 64;
+    if (gx < 1) gx = 1;
+    stage_columns_kernel<<<dim3((unsigned)gx, (unsigned)n_cols), 256, 0, as_stream(stream)>>>(a, rows);
+    TT_LAUNCH_OK("stage_columns_kernel");
     return TT_OK;
 }
 

@@ -42,6 +42,16 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const unsigned long lo
     if (t == 0) mine[slot] = epoch;
 }
 
+// ring[0] = number of completed steps; ring[1 + (step % ring_len) * nk + k] = %globaltimer (ns) when stamp k of that step ran
+__global__ void __launch_bounds__(32) stamp_kernel(unsigned long long* __restrict__ ring, int ring_len, int k, int nk) {
+    if (threadIdx.x != 0) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long step = ring[0];
+    ring[1 + (step % (unsigned long long)ring_len) * nk + k] = t;
+    if (k == nk - 1) ring[0] = step + 1;
+}
+
 // out[i] = src[0][i] + src[1][i] + ... in rank order (fixed order: every rank computes the same bits)
 __global__ void __launch_bounds__(256) peer_sum_kernel(const unsigned long long* __restrict__ srcs, int world, int64_t n, float* __restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -73,6 +83,13 @@ int tt_peer_barrier(const void* flag_blocks, int rank, int world, int slot, void
     TT_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world && slot >= 0 && slot < TT_PEER_SLOTS, "tt_peer_barrier: bad rank/world/slot");
     peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(flag_blocks), rank, world, slot);
     TT_LAUNCH_OK("peer_barrier_kernel");
+    return TT_OK;
+}
+
+int tt_stamp(uint64_t* ring, int ring_len, int k, int nk, void* stream) {
+    TT_REQUIRE(ring != nullptr && ring_len >= 1 && nk >= 1 && k >= 0 && k < nk, "tt_stamp: bad arguments");
+    stamp_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(ring), ring_len, k, nk);
+    TT_LAUNCH_OK("stamp_kernel");
     return TT_OK;
 }
 

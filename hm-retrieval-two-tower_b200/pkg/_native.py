@@ -26,6 +26,13 @@ class TTFeature(ctypes.Structure):
                 ("shards", c_int32)]
 
 
+class TTStageCol(ctypes.Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("kind", c_int32), ("reserved", c_int32)]
+
+
+TT_MAX_STAGE_COLS = 32
+
+
 class TTSparseJob(ctypes.Structure):
     _fields_ = [("table", c_void_p), ("slot0", c_void_p), ("slot1", c_void_p), ("rows", c_int32), ("e", c_int32),
                 ("nsrc", c_int32), ("n_per_src", c_int32), ("shard_rank", c_int32), ("shard_world", c_int32),
@@ -104,6 +111,8 @@ SIGNATURES = {
     "tt_round_tf32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "tt_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tt_take_i32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "tt_stamp": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tt_stage_columns": (c_int, [ctypes.POINTER(TTStageCol), c_int, c_int64, c_void_p]),
     "tt_fill_uniform": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int64, ctypes.c_uint64, c_float, c_float, c_void_p]),
     "tt_recall_hits": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
 }

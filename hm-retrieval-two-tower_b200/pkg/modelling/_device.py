@@ -152,6 +152,116 @@ def stage_floats(value, out):
     out.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(value).reshape(-1), dtype=np.float32)), non_blocking=True)
 
 
+class PinRing:
+    """A few pinned host blocks of (n_cols, rows) 4-byte cells that host-resident feature columns are packed into before the staging
+    kernel reads them in place.  A block is reused only after the kernel that read it has run (one event per block), so the host
+    packs batch k+1 while the GPU still works on batch k."""
+
+    def __init__(self, rows: int, n_cols: int, depth: int = 3):
+        torch = N.require_cuda()
+        self.rows, self.n_cols = int(rows), int(n_cols)
+        self.blocks = [torch.empty((max(n_cols, 1), max(rows, 1)), dtype=torch.int32).pin_memory() for _ in range(depth)]
+        self.views_i = [b.numpy() for b in self.blocks]
+        self.views_f = [v.view(np.float32) for v in self.views_i]
+        self.events = [None] * depth
+        self.cur = -1
+
+    def next_block(self) -> int:
+        self.cur = (self.cur + 1) % len(self.blocks)
+        ev = self.events[self.cur]
+        if ev is not None:
+            ev.synchronize()
+        return self.cur
+
+    def mark_in_flight(self, k: int) -> None:
+        torch = N.require_cuda()
+        if self.events[k] is None:
+            self.events[k] = torch.cuda.Event()
+        self.events[k].record()
+
+
+class Stager:
+    """Collects the feature columns of one batch and stages them with ONE kernel launch (tt_stage_columns): device tensors and
+    pinned host tensors are read where they are, anything else on the host (numpy arrays, strings after the vocabulary lookup)
+    is packed into a PinRing block first."""
+
+    def __init__(self, rows: int, ring_owner):
+        self.rows = int(rows)
+        self.owner = ring_owner            # any object; the ring is cached on it as ``_pin_ring``
+        self.cols = []                     # (src pointer, dst pointer, kind)
+        self.keep = []
+        self.host = []                     # (numpy array, dst tensor, is_float)
+
+    def _tensor(self, t, out, is_float: bool) -> bool:
+        torch = N.require_cuda()
+        t = t.reshape(-1)
+        if t.numel() != self.rows or not t.is_contiguous():
+            return False
+        if not (t.is_cuda or t.is_pinned()):
+            return False
+        if t.is_cuda and t.device != out.device:
+            return False
+        want = torch.float32 if is_float else torch.int32
+        if t.dtype == want:
+            kind = 0
+        elif not is_float and t.dtype == torch.int64:
+            kind = 1
+        else:
+            return False
+        self.cols.append((t.data_ptr(), out.data_ptr(), kind))
+        self.keep.append(t)
+        return True
+
+    def add_ids(self, value, vocab: "Vocab", out) -> None:
+        torch = N.require_cuda()
+        value = unwrap(value)
+        if isinstance(value, torch.Tensor):
+            if not self._tensor(value, out, False):
+                out.copy_(value.reshape(-1), non_blocking=True)
+            return
+        if is_string_like(value):
+            ids = vocab.encode(value)
+        else:
+            ids = np.asarray(value).reshape(-1)
+        self.host.append((ids, out, False))
+
+    def add_floats(self, value, out) -> None:
+        torch = N.require_cuda()
+        value = unwrap(value)
+        if isinstance(value, torch.Tensor):
+            if not self._tensor(value, out, True):
+                out.copy_(value.reshape(-1), non_blocking=True)
+            return
+        self.host.append((np.asarray(value).reshape(-1), out, True))
+
+    def flush(self) -> None:
+        lib = N.load()
+        ring, blk = None, -1
+        if self.host:
+            ring = getattr(self.owner, "_pin_ring", None)
+            if ring is None or ring.rows != self.rows or ring.n_cols < len(self.host):
+                ring = PinRing(self.rows, max(len(self.host), 8))
+                self.owner._pin_ring = ring
+            blk = ring.next_block()
+            base = ring.blocks[blk].data_ptr()
+            for j, (arr, out, is_float) in enumerate(self.host):
+                if arr.shape[0] != self.rows:
+                    raise ValueError(f"feature column of {arr.shape[0]} rows in a batch of {self.rows}")
+                dst = (ring.views_f if is_float else ring.views_i)[blk][j]
+                np.copyto(dst, arr, casting="unsafe")
+                self.cols.append((base + 4 * j * ring.rows, out.data_ptr(), 0))
+        n = len(self.cols)
+        for lo in range(0, n, N.TT_MAX_STAGE_COLS):
+            part = self.cols[lo:lo + N.TT_MAX_STAGE_COLS]
+            arr = (N.TTStageCol * len(part))()
+            for i, (src, dst, kind) in enumerate(part):
+                arr[i].src, arr[i].dst, arr[i].kind = src, dst, kind
+            N.check(lib.tt_stage_columns(arr, len(part), self.rows, N.stream_ptr()), "tt_stage_columns")
+        if ring is not None:
+            ring.mark_in_flight(blk)
+        self.cols, self.keep, self.host = [], [], []
+
+
 class ParamStore:
     """Flat fp32 buffers for Dense kernels/biases: ``params`` and ``grads`` share one layout."""
 

@@ -155,14 +155,21 @@ class InputLayer:
             bufs.append(torch.zeros(batch, dtype=dt, device="cuda"))
         return bufs
 
-    def stage(self, x: Dict[str, object], bufs) -> None:
+    def stage(self, x: Dict[str, object], bufs, stager=None) -> None:
+        """Stage one batch into ``bufs``: every column in one tt_stage_columns launch.  ``stager``: a caller's Stager that collects
+        the columns of several input layers (the train step stages both towers with one launch) and is flushed by the caller."""
+        own = stager is None
+        if own:
+            stager = D.Stager(int(bufs[0].shape[0]), self)
         for (f, t, _, _), buf in zip(self.blocks, bufs):
             if f.name not in x:
                 raise KeyError(f"input is missing feature {f.name!r}")
             if t is None:
-                D.stage_floats(x[f.name], buf)
+                stager.add_floats(x[f.name], buf)
             else:
-                D.stage_ids(x[f.name], t.vocab, buf)
+                stager.add_ids(x[f.name], t.vocab, buf)
+        if own:
+            stager.flush()
 
     def descriptors(self, bufs):
         return D.feature_array(

@@ -112,6 +112,7 @@ class TwoTowerModel(AbstractKerasModel):
         self.use_cuda_graph = os.environ.get("TT_CUDA_GRAPH", "0") == "1"
         self.dist = None                     # set by pkg.modelling.distributed.DataParallel
         self._steps: Dict[int, _StepWorkspace] = {}
+        self.phase_stamps = None
         self._opt_state = None
         self._loss_sum = 0.0
         self._loss_count = 0
@@ -214,8 +215,10 @@ class TwoTowerModel(AbstractKerasModel):
     def _stage(self, sw: _StepWorkspace, data) -> None:
         qf = {f.name: data[f.name] for f in self.query_features}
         cf = {f.name: data[f.name] for f in self.candidate_features}
-        self.query_tower.input_layer.stage(qf, sw.q.bufs)
-        self.candidate_tower.input_layer.stage(cf, sw.c.bufs)
+        stager = D.Stager(sw.batch, sw)       # both towers' columns: ONE staging launch (and one pinned block for host-resident columns)
+        self.query_tower.input_layer.stage(qf, sw.q.bufs, stager)
+        self.candidate_tower.input_layer.stage(cf, sw.c.bufs, stager)
+        stager.flush()
         if self.logq_correction is not None and D.is_string_like(data[self.candidate_id_col]):
             # exact reference semantics for string ids: probability looked up by the STRING (an id outside
             # the vocabulary may still have a sampling probability); ln taken on the device below
@@ -314,10 +317,19 @@ class TwoTowerModel(AbstractKerasModel):
                                        sw.sp_ws.numel(), st), "tt_sparse_adam")
 
     def _launch_step(self, sw: _StepWorkspace) -> None:
-        self._phase_pre(sw)
-        self._phase_a(sw)
-        self._phase_mid(sw)
-        self._phase_b(sw)
+        ring = self.phase_stamps            # measurement aid: (1 + ring_len * 5,) int64 device tensor, see tt_stamp
+        if ring is None:
+            self._phase_pre(sw)
+            self._phase_a(sw)
+            self._phase_mid(sw)
+            self._phase_b(sw)
+            return
+        lib = N.load()
+        n = (ring.numel() - 1) // 5
+        for k, phase in enumerate((self._phase_pre, self._phase_a, self._phase_mid, self._phase_b)):
+            N.check(lib.tt_stamp(ring.data_ptr(), n, k, 5, N.stream_ptr()), "tt_stamp")
+            phase(sw)
+        N.check(lib.tt_stamp(ring.data_ptr(), n, 4, 5, N.stream_ptr()), "tt_stamp")
 
     def _tc_ok(self) -> bool:
         return bool(N.load().tt_tc_available(0, self.joint_embedding_size))

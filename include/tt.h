@@ -82,6 +82,10 @@ int tt_peer_free(void* ptr);
 #define TT_PEER_SLOTS 4
 #define TT_PEER_FLAG_WORDS(G) (TT_PEER_SLOTS * (1 + (G)))
 int tt_peer_barrier(const void* flag_blocks, int rank, int world, int slot, void* stream);
+/* Phase timestamps INSIDE a (captured) step: stamp k of the current step writes %globaltimer (ns) to
+ * ring[1 + (ring[0] % ring_len) * nk + k]; the last stamp (k == nk - 1) increments the step counter ring[0].  `ring` is
+ * 1 + ring_len * nk zero-initialised uint64 on the device.  Measurement aid of the data-parallel step (bench.py dp_phases_ms). */
+int tt_stamp(uint64_t* ring, int ring_len, int k, int nk, void* stream);
 /* out[i] = sum over ranks r = 0..G-1 (in that order) of src_r[i]; `src_ptrs`: device array of G (peer-mapped) float pointers.
  * Dense-gradient all-reduce of the data-parallel step, read in place. */
 int tt_peer_sum_f32(const void* src_ptrs, int world, int64_t n, float* out, void* stream);
@@ -240,6 +244,20 @@ int tt_topk_merge(const float* scores, const int32_t* idx, int G, int nq, int K,
 /* out[i] = table[max(idx[i], 0)]: row indices -> identifiers on the device (tf.gather(identifiers, indices), brute_force.py:83, for
  * integer identifiers; absent entries (-1) read row 0). */
 int tt_take_i32(const int32_t* table, const int32_t* idx, int64_t n, int32_t* out, void* stream);
+
+/* Stage one batch: copy up to TT_MAX_STAGE_COLS feature columns of `rows` 4-byte elements each (int32 row ids, fp32 values) from
+ * where the caller holds them -- device memory, or PINNED host memory, which the kernel reads in place over PCIe (no separate
+ * cudaMemcpy per feature) -- into the towers' staging buffers, in ONE launch.  kind 0: 4-byte elements copied as they are;
+ * kind 1: int64 source elements narrowed to int32.  Replaces one copy per feature of the reference's per-feature tensors
+ * (input_layer.py:55-66 consumes a dict of (B, 1) columns). */
+#define TT_MAX_STAGE_COLS 32
+typedef struct tt_stage_col {
+    const void* src;
+    void* dst;
+    int32_t kind;
+    int32_t reserved;
+} tt_stage_col;
+int tt_stage_columns(const tt_stage_col* cols, int n_cols, int64_t rows, void* stream);
 
 /* Embedding-table initialiser (tf-keras RandomUniform(lo, hi), reference input_layer.py:33-38 builds Embedding() with the default):
  * out[i, c] = lo + (hi - lo) * u(seed, (row0 + i * row_stride) * e + c), u a counter-based hash -> the value of a table cell depends

@@ -498,3 +498,32 @@ def test_row_sharded_sparse_adam_equals_per_shard_oracle(lib, T):
         np.testing.assert_allclose(dt.cpu().numpy()[:n_r], t_r, rtol=1e-5, atol=1e-6)   # tolerances of the unsharded Adam test
         np.testing.assert_allclose(dm.cpu().numpy()[:n_r], m_r, rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(dv.cpu().numpy()[:n_r], v_r, rtol=1e-5, atol=1e-9)
+
+
+def test_stage_columns_one_launch_device_pinned_and_int64(lib):
+    """tt_stage_columns: device and pinned-host sources, int64 narrowing, unaligned ends and row counts that are not multiples of 4."""
+    import torch
+
+    from pkg import _native as N
+
+    for rows in (1, 7, 1000, 8193):
+        g = torch.Generator().manual_seed(rows)
+        ids_dev = torch.randint(0, 1 << 30, (rows,), generator=g, dtype=torch.int32).cuda()
+        f_pin = torch.rand((rows,), generator=g).pin_memory()
+        i64_pin = torch.randint(0, 1 << 30, (rows,), generator=g, dtype=torch.int64).pin_memory()
+        odd = torch.randint(0, 99, (rows + 1,), generator=g, dtype=torch.int32).cuda()[1:]        # 4-byte aligned only
+        outs = [torch.full((rows + 4,), -7, dtype=torch.int32, device="cuda") for _ in range(4)]
+        fout = torch.full((rows + 4,), -7.0, device="cuda")
+        cols = (N.TTStageCol * 4)()
+        for i, (src, dst, kind) in enumerate(((ids_dev, outs[0], 0), (f_pin, fout, 0), (i64_pin, outs[2], 1), (odd, outs[3][1:], 0))):
+            cols[i].src, cols[i].dst, cols[i].kind = src.data_ptr(), dst.data_ptr(), kind
+        c0 = lib.tt_launch_count()
+        N.check(lib.tt_stage_columns(cols, 4, rows, N.stream_ptr()))
+        assert lib.tt_launch_count() - c0 == 1
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0][:rows], ids_dev) and bool((outs[0][rows:] == -7).all())
+        assert torch.equal(fout[:rows].cpu(), f_pin) and bool((fout[rows:] == -7).all())
+        assert torch.equal(outs[2][:rows].cpu(), i64_pin.to(torch.int32)) and bool((outs[2][rows:] == -7).all())
+        assert torch.equal(outs[3][1:rows + 1], odd) and int(outs[3][0]) == -7 and bool((outs[3][rows + 1:] == -7).all())
+    assert lib.tt_stage_columns(None, 2, 5, None) != 0
+    assert lib.tt_stage_columns(cols, N.TT_MAX_STAGE_COLS + 1, 5, None) != 0
