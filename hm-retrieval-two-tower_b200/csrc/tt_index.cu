@@ -264,13 +264,19 @@ size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl, int h
     return a + b + 256;   // the filter path keeps the exact path's scratch for its (rare) fallback
 }
 
-int tt_index_prepare(const float* corpus, int ldc, int64_t n, int E, float* corpus_prepared, float* corpus_norms, void* stream) {
-    TT_REQUIRE(corpus && corpus_prepared && corpus_norms, "tt_index_prepare: null pointer");
-    TT_REQUIRE(n >= 0 && E >= 1 && ldc >= E, "tt_index_prepare: bad shape");
-    return tc::launch_prepare(corpus, ldc, n, E, corpus_prepared, corpus_norms, (int64_t)TT_INDEX_ROWS_PAD(n), as_stream(stream));
+size_t tt_index_prepared_bytes(int64_t n, int E) {
+    if (n <= 0 || E <= 0) return 16;
+    return (size_t)n * E * (E >= 64 ? 2 : 4);      // fp16 tiles from E = 64 (tt_index_tc.cu idx_half_operands), TF32-rounded fp32 below
 }
 
-int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const float* corpus_prepared, const float* corpus_norms, int nq,
+int tt_index_prepare(const float* corpus, int ldc, int64_t n, int E, void* corpus_prepared, float* corpus_norms, void* stream) {
+    TT_REQUIRE(corpus && corpus_prepared && corpus_norms, "tt_index_prepare: null pointer");
+    TT_REQUIRE(n >= 0 && E >= 1 && ldc >= E, "tt_index_prepare: bad shape");
+    TT_REQUIRE((reinterpret_cast<uintptr_t>(corpus_prepared) & 15) == 0, "tt_index_prepare: corpus_prepared must be 16-byte aligned");
+    return tc::launch_prepare(corpus, ldc, n, E, reinterpret_cast<float*>(corpus_prepared), corpus_norms, (int64_t)TT_INDEX_ROWS_PAD(n), as_stream(stream));
+}
+
+int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const void* corpus_prepared, const float* corpus_norms, int nq,
                   int64_t n, int E, int K, int64_t idx_base, float* out_scores, int32_t* out_idx, void* ws, size_t ws_bytes, int impl,
                   void* stream) {
     TT_REQUIRE(Q && corpus && out_scores && out_idx, "tt_index_topk: null pointer");
@@ -284,7 +290,7 @@ int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const f
         return TT_ERR_UNSUPPORTED;
     }
     if (impl == TT_IMPL_TC || (impl == TT_IMPL_AUTO && tc_ok))
-        return index_tc(Q, ldq, corpus, ldc, corpus_prepared, corpus_norms, nq, n, E, K, idx_base, out_scores, out_idx, ws, ws_bytes, st);
+        return index_tc(Q, ldq, corpus, ldc, reinterpret_cast<const float*>(corpus_prepared), corpus_norms, nq, n, E, K, idx_base, out_scores, out_idx, ws, ws_bytes, st);
     return index_exact(Q, ldq, corpus, ldc, nq, n, E, K, idx_base, out_scores, out_idx, ws, ws_bytes, st, nullptr);
 }
 

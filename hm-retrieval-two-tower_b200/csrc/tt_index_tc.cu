@@ -27,6 +27,8 @@
 // accumulation error of both evaluations, with a 2x margin), so every row with s >= lambda has a + eps >= lambda and is
 // listed.  When at least K listed rows have an exact score >= lambda, the exact K-th best score s_K is >= lambda, every true
 // top-K row (s >= s_K) is among them, and steps 5-6 order them by the exact (score desc, index asc) rule; otherwise step 7.
+#include <cuda_fp16.h>
+
 #include "tt_tc_rowpanel.cuh"
 
 namespace tt {
@@ -89,20 +91,56 @@ static Perm make_perm(int64_t n) {
 }
 __device__ __forceinline__ int64_t perm_orig(const Perm& pm, int64_t pos) { return (int64_t)(((unsigned long long)pos * pm.a_inv) % pm.n); }
 
-// Q32 = tf32_rn(Q); kappa[q] = kEpsCoef * ||q||.  One warp per query row.
-__global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ Q, int ldq, int nq, int E, float* __restrict__ Q32,
-                                                           float* __restrict__ eps) {
+// Operand format of the filter passes.  E >= 64: fp16 tiles (tcgen05 kind::f16, twice the TF32 rate and half the bytes) of
+// power-of-two SCALED operands -- every query row by s_q (its own: only scores of one row are ever compared), the corpus by one
+// s_c -- chosen so the largest magnitude lands in [2^14, 2^15): no overflow, and an element only becomes an fp16 subnormal when it
+// is < 2^-28 of the largest one.  fp16 and TF32 both keep 11 significant bits, so the relative part of the error bound is the same:
+//     |a'_ij - S s_ij| <= kappa'_i ||c_j|| + alpha'_i,   S = s_q s_c,  a' = the fp16 tensor-core score of the scaled operands,
+//     kappa'_i = (2^-9 ||q_i|| s_q + 2^-25 sqrt(E)) s_c      (relative rounding of both operands with a 2x margin for the fp32
+//                                                             accumulation; + query elements that fell into the subnormal range)
+//     alpha'_i = 2^-25 sqrt(E) ||q_i|| s_q                   (corpus elements that fell into the subnormal range: |delta| <= 2^-25)
+// The passes work on scaled scores throughout (group bounds, lambda', hit logs); only the exact rescoring compares unscaled scores
+// and takes lambda = (lambda' - alpha') / S.  E = 32 keeps TF32 tiles of the unscaled operands (alpha' = 0, S = 1).
+__device__ __forceinline__ float pow2_scale_for(float amax) {   // s = 2^k with amax * s in [2^14, 2^15); 1 for zero / non-finite input
+    if (!(amax > 0.f) || !(amax < CUDART_INF_F)) return 1.f;
+    int k = 14 - ilogbf(amax);
+    k = k > 60 ? 60 : (k < -60 ? -60 : k);
+    return exp2f((float)k);
+}
+__host__ __device__ inline bool idx_half_operands(int E) { return E >= 64; }
+
+// prepared queries; kappa[q], alpha[q], inv_s[q] as above.  One warp per query row.
+template <bool H>
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ Q, int ldq, int nq, int E, void* __restrict__ Qp,
+                                                           float* __restrict__ eps, float* __restrict__ alpha, float* __restrict__ inv_s,
+                                                           const float* __restrict__ corpus_scale) {
     const int lane = threadIdx.x & 31;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq) return;
-    float s = 0.f;
+    float s = 0.f, amax = 0.f;
     for (int k = lane; k < E; k += 32) {
-        float v = Q[(int64_t)q * ldq + k];
-        Q32[(int64_t)q * E + k] = tf32_rn(v);
+        const float v = Q[(int64_t)q * ldq + k];
+        if (!H) reinterpret_cast<float*>(Qp)[(int64_t)q * E + k] = tf32_rn(v);
         s = fmaf(v, v, s);
+        amax = fmaxf(amax, fabsf(v));
     }
     s = warp_sum(s);
-    if (lane == 0) eps[q] = kEpsCoef * sqrtf(s) * 1.0001f + 1e-30f;
+    if (!H) {
+        if (lane == 0) { eps[q] = kEpsCoef * sqrtf(s) * 1.0001f + 1e-30f; alpha[q] = 0.f; inv_s[q] = 1.f; }
+        return;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float sq = pow2_scale_for(amax), sc = __ldg(corpus_scale);
+    for (int k = lane; k < E; k += 32)
+        reinterpret_cast<__half*>(Qp)[(int64_t)q * E + k] = __float2half_rn(Q[(int64_t)q * ldq + k] * sq);
+    if (lane == 0) {
+        const float nq2 = sqrtf(s) * 1.0001f * sq;                    // ||q'|| (rounded up a hair)
+        const float sub = 2.98023224e-8f * sqrtf((float)E) * 1.0001f;  // 2^-25 sqrt(E)
+        eps[q] = (kEpsCoef * nq2 + sub) * sc * 1.0001f + 1e-30f;
+        alpha[q] = sub * nq2;
+        inv_s[q] = 1.f / (sq * sc);                                    // a power of two: exact
+    }
 }
 
 // One CTA per query: lambda = a lower bound, tight to 16 significant bits, of the K-th largest of gmax[q][0..ngroups).
@@ -112,9 +150,12 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
 // two 8-bit digits, returning the lower edge of the bin that holds the K-th largest key.
 constexpr int kSelectThreads = 128;
 constexpr int kSelectCache = 8;                        // keys held in registers per thread (rows up to 1024 groups; longer rows are re-read)
+// Writes thr[q] = lambda' - 2 alpha' (what the collect pass and the column test compare scaled tensor-core scores with) and
+// thr_exact[q] = (lambda' - alpha') / S (what the exact rescoring compares unscaled fp32 scores with), both rounded down.
 __global__ void __launch_bounds__(kSelectThreads) select_threshold_kernel(const float* __restrict__ gmax, int ld, int ngroups, int K,
-                                                                          float* __restrict__ thr, int32_t* __restrict__ flags,
-                                                                          int32_t* __restrict__ cand_cnt) {
+                                                                          float* __restrict__ thr, float* __restrict__ thr_exact,
+                                                                          const float* __restrict__ alpha, const float* __restrict__ inv_s,
+                                                                          int32_t* __restrict__ flags, int32_t* __restrict__ cand_cnt) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_remaining, s_red[2 * kSelectThreads / 32];
     const int q = blockIdx.x;
@@ -122,7 +163,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_threshold_kernel(const 
     const float* row = gmax + (int64_t)q * ld;
     if (tid == 0) { flags[q] = 0; cand_cnt[q] = 0; }
     if (ngroups < K) {   // fewer groups than K: everything is a candidate (the list will overflow unless n is tiny)
-        if (tid == 0) thr[q] = -CUDART_INF_F;
+        if (tid == 0) { thr[q] = -CUDART_INF_F; thr_exact[q] = -CUDART_INF_F; }
         return;
     }
     uint32_t cache[kSelectCache];
@@ -207,7 +248,10 @@ __global__ void __launch_bounds__(kSelectThreads) select_threshold_kernel(const 
     }
     if (tid == 0) {
         float v = key_to_float(prefix);                // unresolved low bits are zero: the lower edge of the bin
-        thr[q] = (v == v) ? v : -CUDART_INF_F;
+        if (!(v == v)) v = -CUDART_INF_F;
+        const float a = alpha[q];
+        thr[q] = __fsub_rd(v, 2.0002f * a);
+        thr_exact[q] = __fmul_rd(__fsub_rd(v, a), inv_s[q]) ;
     }
 }
 
@@ -394,19 +438,42 @@ __global__ void __launch_bounds__(32 * kSortWarps) sort_topk_kernel(const unsign
     if (!ok && lane == 0) flags[q] = 1;
 }
 
-// C32p[pos][:] = tf32_rn(C[orig(pos)][:]); norms[pos] = ||C[orig(pos)]|| (rounded up a hair); norms[n..n_pad) = 0.
+// max |C| as float bits (non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256) corpus_amax_kernel(const float* __restrict__ C, int ldc, int64_t n, int E, uint32_t* __restrict__ bits) {
+    float m = 0.f;
+    const int64_t total = n * E;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / E;
+        const float v = fabsf(C[r * ldc + (i - r * E)]);
+        m = (v < CUDART_INF_F) ? fmaxf(m, v) : m;      // non-finite cells do not pick the scale
+    }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16)); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4)); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bits, __float_as_uint(m));
+}
+__global__ void corpus_scale_kernel(float* __restrict__ slot) {   // slot: amax bits in, scale out
+    slot[0] = pow2_scale_for(__uint_as_float(reinterpret_cast<uint32_t*>(slot)[0]));
+}
+
+// Cp[pos][:] = prepared(C[orig(pos)][:]) (H: fp16 of the scaled row; else TF32-rounded fp32); norms[pos] = ||C[orig(pos)]||
+// (unscaled, rounded up a hair); norms[n..n_pad) = 0.
+template <bool H>
 __global__ void __launch_bounds__(256) prepare_corpus_kernel(const float* __restrict__ C, int ldc, int64_t n, int E, Perm pm,
-                                                             float* __restrict__ C32p, float* __restrict__ norms, int32_t* __restrict__ orig_of, int64_t n_pad) {
+                                                             void* __restrict__ Cp, float* __restrict__ norms, int32_t* __restrict__ orig_of, int64_t n_pad,
+                                                             const float* __restrict__ scale) {
     int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float sc = H ? __ldg(scale) : 1.f;
     for (int64_t pos = warp; pos < n_pad; pos += nwarps) {
         float s = 0.f;
         if (pos < n) {
             const int64_t o = perm_orig(pm, pos);
             for (int k = lane; k < E; k += 32) {
                 float v = C[o * ldc + k];
-                C32p[pos * E + k] = tf32_rn(v);
+                if (H) reinterpret_cast<__half*>(Cp)[pos * E + k] = __float2half_rn(v * sc);
+                else reinterpret_cast<float*>(Cp)[pos * E + k] = tf32_rn(v);
                 s = fmaf(v, v, s);
             }
         }
@@ -428,10 +495,25 @@ __global__ void chunk_max_kernel(const float* __restrict__ norms, int64_t nchunk
 }
 
 // norms buffer layout: [n_pad per-row norms][n_pad/32 per-chunk maxima][n_pad int32: original row of every permuted position]
-int launch_prepare(const float* C, int ldc, int64_t n, int E, float* C32p, float* norms, int64_t n_pad, cudaStream_t st) {
+// [32 floats: [0] = the corpus scale s_c (1 for TF32 tiles)]
+static inline int64_t scale_slot(int64_t n_pad) { return n_pad + n_pad / 32 + n_pad; }
+int launch_prepare(const float* C, int ldc, int64_t n, int E, float* Cp, float* norms, int64_t n_pad, cudaStream_t st) {
     int64_t g = ceil_div(n_pad * 32, 256);
     int64_t cap = (int64_t)sm_count() * 16;
-    prepare_corpus_kernel<<<(unsigned)(g > cap ? cap : (g < 1 ? 1 : g)), 256, 0, st>>>(C, ldc, n, E, make_perm(n), C32p, norms, reinterpret_cast<int32_t*>(norms + n_pad + n_pad / 32), n_pad);
+    const unsigned grid = (unsigned)(g > cap ? cap : (g < 1 ? 1 : g));
+    int32_t* orig_of = reinterpret_cast<int32_t*>(norms + n_pad + n_pad / 32);
+    float* slot = norms + scale_slot(n_pad);
+    if (idx_half_operands(E)) {
+        TT_CUDA_OK(cudaMemsetAsync(slot, 0, 32 * sizeof(float), st));
+        int64_t ga = ceil_div(n * E, 256 * 8);
+        corpus_amax_kernel<<<(unsigned)(ga > cap ? cap : (ga < 1 ? 1 : ga)), 256, 0, st>>>(C, ldc, n, E, reinterpret_cast<uint32_t*>(slot));
+        TT_LAUNCH_OK("corpus_amax_kernel");
+        corpus_scale_kernel<<<1, 1, 0, st>>>(slot);
+        TT_LAUNCH_OK("corpus_scale_kernel");
+        prepare_corpus_kernel<true><<<grid, 256, 0, st>>>(C, ldc, n, E, make_perm(n), Cp, norms, orig_of, n_pad, slot);
+    } else {
+        prepare_corpus_kernel<false><<<grid, 256, 0, st>>>(C, ldc, n, E, make_perm(n), Cp, norms, orig_of, n_pad, slot);
+    }
     TT_LAUNCH_OK("prepare_corpus_kernel");
     const int64_t nchunks = n_pad / 32;
     chunk_max_kernel<<<(unsigned)ceil_div(nchunks, 256), 256, 0, st>>>(norms, nchunks, norms + n_pad);
@@ -443,10 +525,11 @@ template <int MODE, int E>
 static int launch_idx(const CUtensorMap& tmQ, const CUtensorMap& tmC, const RowPanelParams& p, int m_tiles, int splits, cudaStream_t st,
                       const char* name) {
     constexpr int BN = (E <= 64) ? 256 : 128;
-    using Cfg = RowPanelCfg<MODE, E, BN>;
-    { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(rowpanel_kernel<MODE, E, BN>, Cfg::kSmemBytes)); }
+    constexpr bool H = (E >= 64);     // idx_half_operands(E)
+    using Cfg = RowPanelCfg<MODE, E, BN, H>;
+    { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(rowpanel_kernel<MODE, E, BN, H>, Cfg::kSmemBytes)); }
     dim3 grid((unsigned)m_tiles, (unsigned)splits);
-    rowpanel_kernel<MODE, E, BN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmQ, tmC, tmC, p);
+    rowpanel_kernel<MODE, E, BN, H><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmQ, tmC, tmC, p);
     TT_LAUNCH_OK(name);
     return TT_OK;
 }
@@ -462,7 +545,7 @@ static int launch_idx_e(int E, const CUtensorMap& tmQ, const CUtensorMap& tmC, c
 }
 
 struct IdxLayout {
-    size_t q32, eps, thr, gmax, cnt, flags, queue, cand, ccnt, keys, c32, norms, exact, total;
+    size_t q32, eps, thr, thr_exact, alpha, inv_s, gmax, cnt, flags, queue, cand, ccnt, keys, c32, norms, exact, total;
     int ngroups, n_tiles, cap;
     int m_tiles, splits, tps, n_logs, cap_log, fine;
     int n_tiles_s, splits_s, tps_s, k_sel, rank;   // threshold pass: tiles of the sample, its launch shape, the order statistic taken, the rank lambda sits near
@@ -502,6 +585,9 @@ static IdxLayout layout(int nq, int64_t n, int E, int K, bool need_corpus_copy) 
     L.q32 = take((size_t)nq * E * 4);
     L.eps = take((size_t)nq * 4);
     L.thr = take((size_t)nq * 4);
+    L.thr_exact = take((size_t)nq * 4);
+    L.alpha = take((size_t)nq * 4);
+    L.inv_s = take((size_t)nq * 4);
     L.gmax = take((size_t)nq * L.ngroups * 4);
     L.cnt = take((size_t)L.n_logs * 4);
     L.flags = take((size_t)nq * 4);
@@ -553,6 +639,9 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
     float* q32 = reinterpret_cast<float*>(base + L.q32);
     float* eps = reinterpret_cast<float*>(base + L.eps);
     float* thr = reinterpret_cast<float*>(base + L.thr);
+    float* thr_exact = reinterpret_cast<float*>(base + L.thr_exact);
+    float* alpha = reinterpret_cast<float*>(base + L.alpha);
+    float* inv_s = reinterpret_cast<float*>(base + L.inv_s);
     float* gmax = reinterpret_cast<float*>(base + L.gmax);
     int32_t* cnt = reinterpret_cast<int32_t*>(base + L.cnt);
     int32_t* flags = reinterpret_cast<int32_t*>(base + L.flags);
@@ -574,13 +663,17 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
     int nev = 0;
     auto mark = [&]() { if (g_stage_ms && nev < 8) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], st); ++nev; } };
     mark();
-    prep_queries_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, st>>>(Q, ldq, nq, E, q32, eps);
+    const bool half_ops = idx_half_operands(E);
+    const float* corpus_scale = norms + scale_slot((int64_t)TT_INDEX_ROWS_PAD(n));
+    const unsigned pgrid = (unsigned)ceil_div((int64_t)nq * 32, 256);
+    if (half_ops) prep_queries_kernel<true><<<pgrid, 256, 0, st>>>(Q, ldq, nq, E, q32, eps, alpha, inv_s, corpus_scale);
+    else prep_queries_kernel<false><<<pgrid, 256, 0, st>>>(Q, ldq, nq, E, q32, eps, alpha, inv_s, corpus_scale);
     TT_LAUNCH_OK("prep_queries_kernel");
 
     CUtensorMap tmQ, tmC;
-    int rc = make_tmap_2d(&tmQ, q32, nq, E, E, 128);
+    int rc = half_ops ? make_tmap_2d_f16(&tmQ, q32, nq, E, E, 128) : make_tmap_2d(&tmQ, q32, nq, E, E, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmC, c32, n, E, E, idx_bn(E));   // the prepared copy is dense (ld = E)
+    rc = half_ops ? make_tmap_2d_f16(&tmC, c32, n, E, E, idx_bn(E)) : make_tmap_2d(&tmC, c32, n, E, E, idx_bn(E));   // the prepared copy is dense (ld = E)
     if (rc) return rc;
     const int m_tiles = L.m_tiles, splits = L.splits, tps = L.tps;
     RowPanelParams p{};
@@ -595,7 +688,7 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
         if (rc) return rc;
     }
     mark();
-    select_threshold_kernel<<<(unsigned)nq, kSelectThreads, 0, st>>>(gmax, L.ngroups, L.ngroups, L.k_sel, thr, flags, ccnt);
+    select_threshold_kernel<<<(unsigned)nq, kSelectThreads, 0, st>>>(gmax, L.ngroups, L.ngroups, L.k_sel, thr, thr_exact, alpha, inv_s, flags, ccnt);
     TT_LAUNCH_OK("select_threshold_kernel");
     mark();
     p.out0 = queue;
@@ -612,7 +705,7 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
         TT_LAUNCH_OK("column_test_kernel");
 #define TT_SCORE(EE)                                                                                                        \
     exact_score_kernel<EE><<<dim3((unsigned)ceil_div(L.cap, ScoreCfg<EE>::kThreads), (unsigned)nq), ScoreCfg<EE>::kThreads, 0, st>>>( \
-        Q, ldq, C, ldc, cand, ccnt, L.cap, thr, orig_of, keys)
+        Q, ldq, C, ldc, cand, ccnt, L.cap, thr_exact, orig_of, keys)
         if (E == 32) TT_SCORE(32); else if (E == 64) TT_SCORE(64); else TT_SCORE(128);
 #undef TT_SCORE
         TT_LAUNCH_OK("exact_score_kernel");

@@ -145,6 +145,7 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 // 2-D fp32 row-major matrix (rows x cols, leading dimension ld elements); box = 32 columns (128 B, one
 // swizzle span) x box_rows rows; SWIZZLE_128B; out-of-bounds elements read as zero.
 int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int cols, int ld, int box_rows);
+int make_tmap_2d_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
 }  // namespace tc
 }  // namespace tt

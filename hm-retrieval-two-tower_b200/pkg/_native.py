@@ -107,6 +107,7 @@ SIGNATURES = {
     "tt_index_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int, c_int, c_int]),
     "tt_index_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int64,
                               c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "tt_index_prepared_bytes": (c_size_t, [c_int64, c_int]),
     "tt_index_prepare": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "tt_round_tf32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "tt_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -86,9 +86,10 @@ class BruteForceIndex(AbstractKerasModel):
         n_loc, e = self._candidates.shape
         self._candidates_tf32, self._max_norm = None, None
         if n_loc > 0 and lib.tt_tc_available(1, e):
-            self._candidates_tf32 = torch.empty_like(self._candidates)
+            # opaque operand tiles (fp16 from E = 64: half the size of the corpus); named for the round-1 TF32 layout
+            self._candidates_tf32 = torch.empty(int(lib.tt_index_prepared_bytes(n_loc, e)), dtype=torch.uint8, device="cuda")
             rows_pad = ((n_loc + 255) // 256 + 1) * 256          # TT_INDEX_ROWS_PAD
-            n_pad = 2 * rows_pad + rows_pad // 32                    # TT_INDEX_NORM_PAD: row norms + per-chunk maxima
+            n_pad = 2 * rows_pad + rows_pad // 32 + 32           # TT_INDEX_NORM_PAD: row norms + per-chunk maxima + row map + scale slot
             self._max_norm = torch.zeros(n_pad, dtype=torch.float32, device="cuda")   # per-row norms, zero padded
             N.check(lib.tt_index_prepare(self._candidates.data_ptr(), e, n_loc, e, self._candidates_tf32.data_ptr(),
                                          self._max_norm.data_ptr(), N.stream_ptr()), "tt_index_prepare")

@@ -219,19 +219,21 @@ int tt_debug_sparse_plan(const tt_sparse_job* jobs, int njobs, void* ws, size_t 
  * ---------------------------------------------------------------------------------------------- */
 /* Operand preparation for the tensor-core filter, done once at index-build time (tt_index_prepare) and passed
  * to every query call:
- *   corpus_prepared  (n, E) dense: TF32-rounded rows stored under a fixed pseudo-random permutation (so that
- *                    neighbouring -- e.g. equally popular -- rows do not share a filter group);
+ *   corpus_prepared  tt_index_prepared_bytes(n, E) bytes, opaque: the rows as tensor-core operand tiles -- fp16 of the rows scaled by
+ *                    one power of two (E >= 64) or TF32-rounded fp32 (E = 32) -- stored under a fixed pseudo-random permutation
+ *                    (so that neighbouring -- e.g. equally popular -- rows do not share a filter group);
  *   corpus_norms     TT_INDEX_NORM_PAD(n) floats: ||row||_2 in the same order, zero padded to TT_INDEX_ROWS_PAD(n),
  *                    followed by the maximum norm of every chunk of 32 rows, followed by TT_INDEX_ROWS_PAD(n) int32: the
- *                    original row of every permuted position.
+ *                    original row of every permuted position, followed by 32 floats ([0] = the operand scale).
  * Pass both or neither; when NULL they are rebuilt in the workspace on every call (size the workspace with
  * have_corpus_prepared = 0).  The exact fp32 `corpus` stays authoritative: results never depend on the copy. */
 #define TT_INDEX_ROWS_PAD(n) ((((n) + 255) / 256 + 1) * 256)
-#define TT_INDEX_NORM_PAD(n) (2 * TT_INDEX_ROWS_PAD(n) + TT_INDEX_ROWS_PAD(n) / 32)
-int tt_index_prepare(const float* corpus, int ldc, int64_t n, int E, float* corpus_prepared, float* corpus_norms,
+#define TT_INDEX_NORM_PAD(n) (2 * TT_INDEX_ROWS_PAD(n) + TT_INDEX_ROWS_PAD(n) / 32 + 32)
+size_t tt_index_prepared_bytes(int64_t n, int E);
+int tt_index_prepare(const float* corpus, int ldc, int64_t n, int E, void* corpus_prepared, float* corpus_norms,
                      void* stream);
 size_t tt_index_workspace_bytes(int nq, int64_t n, int E, int K, int impl, int have_corpus_prepared);
-int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const float* corpus_prepared,
+int tt_index_topk(const float* Q, int ldq, const float* corpus, int ldc, const void* corpus_prepared,
                   const float* corpus_norms, int nq, int64_t n, int E, int K, int64_t idx_base, float* out_scores,
                   int32_t* out_idx, void* ws, size_t ws_bytes, int impl, void* stream);
 /* Round-to-nearest TF32 copy of a matrix (operand preparation for TT_IMPL_TC). */

@@ -15,7 +15,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 C = torch.randn(n, E, device="cuda", generator=g).abs() * 0.1
 Q = torch.relu(torch.randn(nq, E, device="cuda", generator=g) * 0.3)
 rows_pad = ((n + 255) // 256 + 1) * 256
-n_pad = 2 * rows_pad + rows_pad // 32
+n_pad = 2 * rows_pad + rows_pad // 32 + 32
 C32 = torch.empty_like(C); norms = torch.zeros(n_pad, device="cuda")
 st = N.stream_ptr()
 N.check(lib.tt_index_prepare(C.data_ptr(), E, n, E, C32.data_ptr(), norms.data_ptr(), st))

@@ -29,7 +29,7 @@ for a in range(0, n, 1 << 22):
 gq = torch.Generator(device="cuda").manual_seed(7)                       # the same queries on every rank
 Q = torch.relu(torch.randn(nq, E, device="cuda", generator=gq) * 0.3)
 rows_pad = ((n + 255) // 256 + 1) * 256
-C32 = torch.empty_like(C); norms = torch.zeros(2 * rows_pad + rows_pad // 32, device="cuda")
+C32 = torch.empty_like(C); norms = torch.zeros(2 * rows_pad + rows_pad // 32 + 32, device="cuda")
 st = N.stream_ptr()
 N.check(lib.tt_index_prepare(C.data_ptr(), E, n, E, C32.data_ptr(), norms.data_ptr(), st))
 s = torch.empty(nq, K, device="cuda"); i = torch.empty(nq, K, dtype=torch.int32, device="cuda")

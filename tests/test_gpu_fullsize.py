@@ -125,7 +125,7 @@ def _prepare(lib, T, c):
 
     n, E = c.shape
     rows_pad = ((n + 255) // 256 + 1) * 256
-    n_pad = 2 * rows_pad + rows_pad // 32                      # TT_INDEX_NORM_PAD
+    n_pad = 2 * rows_pad + rows_pad // 32 + 32                 # TT_INDEX_NORM_PAD
     c32 = T.empty_like(c); mx = T.empty((n_pad,), dtype=T.float32, device="cuda")
     N.check(lib.tt_index_prepare(c.data_ptr(), E, n, E, c32.data_ptr(), mx.data_ptr(), stream()), "tt_index_prepare")
     return c32, mx

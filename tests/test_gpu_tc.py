@@ -173,7 +173,7 @@ def _index_tc(lib, T, q, c, K, idx_base=0, prepared=False):
     c32 = mx = None
     if prepared:   # what BruteForceIndex does once at build time
         rows_pad = ((n + 255) // 256 + 1) * 256
-        n_pad = 2 * rows_pad + rows_pad // 32                      # TT_INDEX_NORM_PAD
+        n_pad = 2 * rows_pad + rows_pad // 32 + 32                 # TT_INDEX_NORM_PAD
         c32 = T.empty_like(dc); mx = T.full((n_pad,), 9.0, dtype=T.float32, device="cuda")
         N.check(lib.tt_index_prepare(dc.data_ptr(), E, n, E, c32.data_ptr(), mx.data_ptr(), stream()))
     s = T.empty((nq, K), dtype=T.float32, device="cuda"); i = T.empty((nq, K), dtype=T.int32, device="cuda")
