@@ -131,12 +131,14 @@ __global__ void __launch_bounds__(256) index_exact_kernel(const float* __restric
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ s_in, const int32_t* __restrict__ i_in, int G, int nq, int K,
                                                          int P, int64_t idx_add, float* __restrict__ s_out, int32_t* __restrict__ i_out,
                                                          const int32_t* __restrict__ flags) {
-    if (flags && !flags[blockIdx.x]) return;   // fallback mode: leave the rows the filter path already produced
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s = reinterpret_cast<float*>(smem_raw);
     int32_t* id = reinterpret_cast<int32_t*>(s + P);
-    const int q = blockIdx.x;
     const int total = G * K;
+    // fallback mode (flags): a small grid strides over the queries and leaves the rows the filter path already produced alone --
+    // normally none is flagged, and 2 CTAs per SM check all flags in a few microseconds
+    for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+    if (flags && !flags[q]) continue;
     for (int t = threadIdx.x; t < P; t += blockDim.x) {
         if (t < total) {
             int g = t / K, j = t - g * K;
@@ -168,6 +170,8 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
         bool pad = (iv == kIdxPad);
         s_out[(int64_t)q * K + t] = pad ? -CUDART_INF_F : s[t];
         i_out[(int64_t)q * K + t] = pad ? -1 : (int32_t)(iv + idx_add);
+    }
+    __syncthreads();
     }
 }
 
@@ -212,7 +216,8 @@ int merge_launch(const float* s_in, const int32_t* i_in, int G, int nq, int K, i
     if (P > 16384) { set_error("tt_topk_merge: G*K=%d exceeds 16384", G * K); return TT_ERR_UNSUPPORTED; }
     size_t smem = (size_t)P * 8;
     { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(topk_merge_kernel, 16384 * 8)); }
-    topk_merge_kernel<<<(unsigned)nq, 256, smem, st>>>(s_in, i_in, G, nq, K, P, idx_add, s_out, i_out, flags);
+    const int grid = (flags && nq > 2 * sm_count()) ? 2 * sm_count() : nq;
+    topk_merge_kernel<<<(unsigned)grid, 256, smem, st>>>(s_in, i_in, G, nq, K, P, idx_add, s_out, i_out, flags);
     TT_LAUNCH_OK("topk_merge_kernel");
     return TT_OK;
 }

@@ -152,12 +152,13 @@ class BruteForceIndex(AbstractKerasModel):
     def query_indices(self, queries, k: Optional[int] = None):
         return self.search(self._embed_queries(queries), k)
 
-    def call(self, queries, training: bool = False, out=None):
+    def call(self, queries, training: bool = False, out=None, wait: bool = True):
         """{query feature: (B,1)} -> (B, k) array of candidate identifiers.
 
         `out` (optional): a pinned host tensor of shape (B, k) and the identifiers' dtype that receives the result; the returned numpy
         array then views it (no further host copy -- the caller owns the buffer and decides when it is reused).  Without `out` the
-        result is an array of its own."""
+        result is an array of its own.  `wait=False` (needs `out`): do not wait for the device -- returns (view of `out`, CUDA event);
+        the view holds the result once ``event.synchronize()`` returns, so a serving loop can submit batch k+1 before reading batch k."""
         torch = N.require_cuda()
         lib = N.load()
         _, idx = self.query_indices(queries)
@@ -174,8 +175,14 @@ class BruteForceIndex(AbstractKerasModel):
                 if tuple(out.shape) != shape or out.dtype != ids_dev.dtype or not out.is_pinned():
                     raise ValueError(f"out must be a pinned host tensor of shape {shape} and dtype {ids_dev.dtype}")
                 out.copy_(ids_dev, non_blocking=True)
+                if not wait:
+                    done = torch.cuda.Event()
+                    done.record()
+                    return out.numpy(), done
                 torch.cuda.current_stream().synchronize()
                 return out.numpy()
+            if not wait:
+                raise ValueError("wait=False needs a caller-owned pinned `out` buffer")
             stage = self.__dict__.get("_pin_stage")
             if stage is None or tuple(stage.shape) != shape or stage.dtype != ids_dev.dtype:
                 stage = self.__dict__["_pin_stage"] = torch.empty(shape, dtype=ids_dev.dtype).pin_memory()
