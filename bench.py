@@ -419,7 +419,7 @@ def run_ours(args):
     line["dp_phases_ms" if world > 1 else "step_phases_ms"] = dp_phase_times(model, B, dev_batches)
     barrier()
     if rank == 0:
-        line["roofline"] = softmax_roofline(model, B, pk, lib)
+        line["roofline"] = softmax_roofline(model, B, pk, lib, world)
         if not args.no_hbm:
             line["hbm_kernels"] = hbm_rooflines(pk, lib)
     line["index"] = index_bench(model, pk, lib, K, world, args)   # every rank takes part (row-sharded corpus when N > 1)
@@ -737,8 +737,9 @@ def dp_phase_times(model, B, dev_batches, n=200):
                     "sync_* = device barrier incl. waiting for the slowest rank"}
 
 
-def softmax_roofline(model, B, pk, lib):
-    """Dominant kernel group: in-batch softmax fwd + bwd (6.B^2.E algorithmic flop), timed alone with CUDA events."""
+def softmax_roofline(model, B, pk, lib, world=1):
+    """Dominant kernel group: in-batch softmax fwd + bwd (6.B.Bc.E algorithmic flop; Bc = B, or world.B candidate columns with cross-GPU
+    negatives), timed alone with CUDA events."""
     import torch
 
     from pkg import _native as N
@@ -750,33 +751,46 @@ def softmax_roofline(model, B, pk, lib):
     impl = N.TT_IMPL_TC if use_tc else N.TT_IMPL_SIMT
     bias = sw.col_bias.data_ptr() if sw.col_bias is not None else None
     st = N.stream_ptr()
-    ws = torch.empty(int(lib.tt_softmax_workspace_bytes(B, B, e)), dtype=torch.uint8, device="cuda")
+    gn = model.dist is not None and model.dist.global_negatives
+    bc = world * B if gn else B
+    dc, off = sw.dc, 0
+    if gn:      # the shape the step runs: this rank's B rows against the world.B candidates of all ranks (synthetic candidates here)
+        g = torch.Generator(device="cuda").manual_seed(11)
+        c = torch.relu(torch.randn((bc, e), generator=g, device="cuda") * 0.3)
+        bias_t = torch.log(torch.rand(bc, generator=g, device="cuda") * 0.01 + 1e-5)
+        bias = bias_t.data_ptr()
+        dc = torch.empty((bc, e), dtype=torch.float32, device="cuda")
+    ws = torch.empty(int(lib.tt_softmax_workspace_bytes(B, bc, e)), dtype=torch.uint8, device="cuda")
 
-    def once():   # the call the train step makes: shared operand prep, forward, combine, dQ+dC passes in one launch, reduction
-        N.check(lib.tt_inbatch_softmax_step(q.data_ptr(), e, c.data_ptr(), e, bias, B, B, e, 0, sw.lse.data_ptr(), sw.loss.data_ptr(),
-                                            sw.dq.data_ptr(), e, sw.dc.data_ptr(), e, ws.data_ptr(), ws.numel(), impl, st))
+    def once():   # the call the train step makes: operand prep, pass 1 (forward + dQ), combine, pass 2 (dC), combine
+        N.check(lib.tt_inbatch_softmax_step(q.data_ptr(), e, c.data_ptr(), e, bias, B, bc, e, off, sw.lse.data_ptr(), sw.loss.data_ptr(),
+                                            sw.dq.data_ptr(), e, dc.data_ptr(), e, ws.data_ptr(), ws.numel(), impl, st))
 
     t = time_device_blocks(lambda i: once(), 10, 3, 1, 300.0)      # rank 0 alone: no collective in the timing helper
     sec = t["ms_per_step"] * 1e-3
-    flops = 6.0 * B * B * e
+    flops = 6.0 * B * bc * e
     achieved = flops / sec / 1e12
-    return {"bound": "tensor", "kernel": "in-batch softmax fwd+bwd (%s)" % ("tcgen05, fp16 operand tiles" if use_tc else "fp32 CUDA cores"),
+    return {"bound": "tensor", "kernel": "in-batch softmax fwd+bwd, %d x %d logits (%s)" % (B, bc, "tcgen05, fp16 operand tiles" if use_tc else "fp32 CUDA cores"),
             "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_burst"],
             "traffic": NCU_SOFTMAX_DRAM_BYTES if (use_tc and B == 8192 and e == 64 and NCU_SOFTMAX_DRAM_BYTES) else None, "traffic_source": NCU_SOFTMAX_SOURCE,
             "ms": sec * 1e3, "algorithmic_flop": flops, "peak_source": pk["source"] + ", dense bf16 burst (kernel timed alone)"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the two stream-K launches (forward 2.17 MB, backward 4.37 MB) from the
-# `ncu --set full` capture of this workload (B = 8192, E = 64); the operands are 2 x 1 MB of fp16 tiles + 2 x 2 MB fp32 outputs
-NCU_SOFTMAX_DRAM_BYTES = None
-NCU_SOFTMAX_SOURCE = "profiles/r01c_softmax_streamk_ncu_full.md (ncu --set full, per launch, fwd + bwd)"
+# dram__bytes_read.sum + dram__bytes_write.sum of the six launches of one softmax call (amax 4.20, convert 4.24, pass 1 2.79 + 0.06,
+# combine1 25.95, pass 2 2.21, combine2 25.21 MB) from the round-2 `ncu --set full` capture at B = 8192, E = 64.  ncu replays every
+# kernel cold: the two combine kernels' ~25 MB are the per-CTA partial accumulators the passes just wrote, L2 hits in the running
+# step.  Algorithmic bytes: 4 MB of fp32 operands in, 4 MB of gradients out.  A constant from that capture, NOT measured in this run.
+NCU_SOFTMAX_DRAM_BYTES = 4204032 + 4235776 + 2787840 + 62976 + 25946368 + 2207744 + 256 + 25209600
+NCU_SOFTMAX_SOURCE = ("profiles/r02_flash_b8192_ncu_full.md (ncu --set full, one call = 6 launches, cold-cache replay; constant from that capture, "
+                      "not measured in this run)")
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default size of hbm_rooflines (2^20 ids, 1.37 M x 64 table):
 # gather 245.1 + 222.6 MB (duplicate ids hit L2, part of the output is still in L2 when the kernel ends); segmented reduce
 # 655.0 + 344.9 MB plus the combine kernel's 14.4 MB, for 1.02 GB of algorithmic bytes
 NCU_HBM_DRAM_BYTES = {"gather": 245108480 + 222646272, "update": 655021568 + 344898048 + 14365696}
-NCU_HBM_SOURCE = "profiles/r01d_hbm_kernels_ncu_full.md (gather), profiles/r01e_sparse_block_ncu_full.md (update); ncu --set full, per launch"
+NCU_HBM_SOURCE = ("profiles/r01d_hbm_kernels_ncu_full.md (gather), profiles/r01e_sparse_block_ncu_full.md (update); ncu --set full, per launch; "
+                  "constants from those captures, not measured in this run")
 
 HBM_TIMING = None     # (warm-up launches, timed launches) override used by scripts/hbm_microbench.py --once under ncu
 
