@@ -187,7 +187,10 @@ struct ExactPlan {
     size_t smem;
 };
 
-static int plan_exact(int nq, int64_t n, int K, ExactPlan* pl) {
+// `fallback`: the kernel redoes the few queries the filter path flagged, so only a few query tiles do any work; the corpus is then cut
+// into as many splits as the merge allows, so that even ONE flagged tile spreads over the chip (10 splits made a flagged tile cost
+// 3.9 ms at 105 k rows: ten CTAs of work on 148 SMs)
+static int plan_exact(int nq, int64_t n, int K, ExactPlan* pl, bool fallback = false) {
     if (K <= 128) { pl->bq = 64; pl->cap = 256; pl->smem = sizeof(IndexSmem<64, 256>); }
     else if (K <= 1536) { pl->bq = 8; pl->cap = 2048; pl->smem = sizeof(IndexSmem<8, 2048>); }
     else { set_error("tt_index_topk (exact): K=%d > 1536 unsupported", K); return TT_ERR_UNSUPPORTED; }
@@ -195,7 +198,7 @@ static int plan_exact(int nq, int64_t n, int K, ExactPlan* pl) {
     int64_t want = ceil_div(2 * (int64_t)sm_count(), qtiles);
     int64_t by_work = ceil_div(n, 2048);             // at least 2048 candidates per split
     int64_t by_merge = 16384 / next_pow2(K);         // merge sorts nsplit*K entries in shared memory
-    int64_t ns = want;
+    int64_t ns = fallback ? 64 : want;
     if (ns > by_work) ns = by_work;
     if (ns > by_merge) ns = by_merge;
     if (ns > 64) ns = 64;
@@ -223,15 +226,16 @@ int merge_launch(const float* s_in, const int32_t* i_in, int G, int nq, int K, i
 }
 
 size_t index_exact_workspace(int nq, int64_t n, int K) {
-    ExactPlan pl;
-    if (plan_exact(nq, n, K, &pl)) return 0;
-    return align_up((size_t)pl.nsplit * nq * K * sizeof(float), 256) + align_up((size_t)pl.nsplit * nq * K * sizeof(int32_t), 256) + 256;
+    ExactPlan pl, pf;
+    if (plan_exact(nq, n, K, &pl) || plan_exact(nq, n, K, &pf, true)) return 0;
+    const size_t ns = (size_t)(pl.nsplit > pf.nsplit ? pl.nsplit : pf.nsplit);      // sized for either use
+    return align_up(ns * nq * K * sizeof(float), 256) + align_up(ns * nq * K * sizeof(int32_t), 256) + 256;
 }
 
 int index_exact(const float* Q, int ldq, const float* C, int ldc, int nq, int64_t n, int E, int K, int64_t idx_base, float* out_s,
                 int32_t* out_i, void* ws, size_t ws_bytes, cudaStream_t st, const int32_t* flags) {
     ExactPlan pl;
-    int rc = plan_exact(nq, n, K, &pl);
+    int rc = plan_exact(nq, n, K, &pl, flags != nullptr);
     if (rc) return rc;
     TT_REQUIRE(ws && ws_bytes >= index_exact_workspace(nq, n, K), "tt_index_topk: workspace too small");
     Carver cv(ws);

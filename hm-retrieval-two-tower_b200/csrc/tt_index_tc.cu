@@ -48,8 +48,10 @@ constexpr float kEpsCoef = 1.0f / 512.0f;   // 2^-9
 static int g_cap_override = 0;              // tests: force tiny candidate lists to exercise the fallback
 
 static inline int cand_cap(int rank) {   // listed columns per query for a threshold near `rank` (a power of two: it is also the largest sort size)
+    // 2x the rank plus slack: a trained, popularity-dominated corpus packs ~1.4-1.9 K rows within the filter's error bound of the
+    // K-th best score (measured), and one overflowing query costs a trip through the exact path
     int c = 128;
-    while (c < rank + rank / 2 + 32) c <<= 1;
+    while (c < 2 * rank + 64) c <<= 1;
     return c < 1024 ? c : 1024;
 }
 
@@ -428,13 +430,12 @@ __global__ void __launch_bounds__(32 * kSortWarps) sort_topk_kernel(const unsign
     int32_t* oi = out_i + (int64_t)q * K;
     const int need = m1 > K ? m1 : K;
     bool ok;
-    if constexpr (!BIG) {
-        if (need <= 128) ok = sort_write<4>(src, m1, K, need_k, idx_base, os, oi, lane);
-        else ok = sort_write<8>(src, m1, K, need_k, idx_base, os, oi, lane);
-    } else {
+    if (need <= 128) ok = sort_write<4>(src, m1, K, need_k, idx_base, os, oi, lane);        // the network is sized per query, at run time
+    else if (need <= 256) ok = sort_write<8>(src, m1, K, need_k, idx_base, os, oi, lane);
+    else if constexpr (BIG) {
         if (need <= 512) ok = sort_write<16>(src, m1, K, need_k, idx_base, os, oi, lane);
         else ok = sort_write<32>(src, m1, K, need_k, idx_base, os, oi, lane);
-    }
+    } else ok = false;
     if (!ok && lane == 0) flags[q] = 1;
 }
 
@@ -579,7 +580,7 @@ static IdxLayout layout(int nq, int64_t n, int E, int K, bool need_corpus_copy) 
     choose_splits(L.m_tiles, L.n_tiles_s, 2, 64, &L.splits_s, &L.tps_s);
     // hit logs of the collect pass: a warp's 32 rows each see ~1.25 K / (splits * halves) qualifying chunks; generous slack because an overflow costs a trip through the exact CUDA-core fallback
     L.n_logs = L.m_tiles * L.splits * 4 * idx_halves(E);   // one log per epilogue warp (32 rows x its share of the columns)
-    L.cap_log = g_cap_override > 0 ? 32 * (1 + g_cap_override / (4 * L.splits)) : 32 * (int)ceil_div(5 * (int64_t)L.rank, 2 * L.splits * idx_halves(E)) + 128;
+    L.cap_log = g_cap_override > 0 ? 32 * (1 + g_cap_override / (4 * L.splits)) : 32 * (int)ceil_div(8 * (int64_t)L.rank, 2 * L.splits * idx_halves(E)) + 128;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     L.q32 = take((size_t)nq * E * 4);
@@ -732,3 +733,12 @@ int index_tc(const float* Q, int ldq, const float* C, int ldc, const float* C32_
 }
 
 }  // namespace tt
+
+extern "C" int tt_debug_index_layout(int nq, int64_t n, int E, int K, int have_corpus_prepared, int64_t* out8) {
+    if (!out8 || nq <= 0 || n <= 0 || K <= 0) return TT_ERR_ARG;
+    const tt::tc::IdxLayout L = tt::tc::layout(nq, n, E, K, !have_corpus_prepared);
+    out8[0] = (int64_t)L.flags; out8[1] = (int64_t)L.ccnt; out8[2] = (int64_t)L.cnt; out8[3] = L.cap;
+    out8[4] = L.cap_log; out8[5] = L.n_logs; out8[6] = L.rank; out8[7] = L.ngroups;
+    return TT_OK;
+}
+

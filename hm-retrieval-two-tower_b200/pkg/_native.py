@@ -59,6 +59,7 @@ SIGNATURES = {
     "tt_peer_gather_f32": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "tt_debug_index_cap": (c_int, [c_int]),
     "tt_debug_index_stages": (c_int, [c_void_p]),
+    "tt_debug_index_layout": (c_int, [c_int, c_int64, c_int, c_int, c_int, ctypes.POINTER(c_int64)]),
     # host-side helpers (csrc/tt_host.cu)
     "tt_vocab_create": (c_void_p, [c_void_p, c_void_p, c_int64]),
     "tt_vocab_destroy": (None, [c_void_p]),

@@ -62,6 +62,10 @@ int tt_debug_index_cap(int cap);
 /* Profiling knob: while `host_ms8` (8 host floats, or NULL to stop) is set, every tensor-core tt_index_topk call adds
  * the device time of its stages (prep, filter, select, collect, rescore, fallback) to it and synchronises. */
 int tt_debug_index_stages(float* host_ms8);
+/* Where a tensor-core tt_index_topk call keeps its per-query diagnostics inside the caller's workspace: out8 = {byte offset of the
+ * int32 fallback flags [nq], of the int32 listed-column counts [nq], of the int32 hit-log fill counts [n_logs], list capacity, log
+ * capacity, n_logs, the rank the threshold sits near, filter groups per query}.  Read after the call (diagnostics only). */
+int tt_debug_index_layout(int nq, int64_t n, int E, int K, int have_corpus_prepared, int64_t* out8);
 /* ------------------------------------------------------------------------------------------------
  * Peer-shareable device memory (one process per GPU): row-sharded embedding tables and the towers' dX
  * blocks are read by the other GPUs' kernels directly over NVLink.  tt_peer_alloc: cudaMalloc (zero-filled) on the

@@ -28,6 +28,6 @@ for leg in ix.get("row_sharded_large", []):
     print(f" index {leg['rows']:.0e}: {leg['value'] / 1e3:.0f}k q/s {leg['ms_per_batch']:.3f} ms e2e {leg['e2e']['value'] / 1e3:.0f}k frac {leg['roofline']['frac']:.3f} parity {leg.get('parity_ok')} build {leg['shard_build_s']:.2f}s")
     print("   stages", {k: round(v, 4) for k, v in (leg.get("stage_ms") or {}).items()})
 if "parity" in l:
-    print(" parity_ok", l.get("parity_ok"), {k: (v.get("ok"), v.get("max_update_err_rel_to_max_update"), v.get("error")) for k, v in l["parity"].items()})
+    print(" parity_ok", l.get("parity_ok"), {k: (v.get("ok"), v.get("max_update_err_rel_to_max_update", v.get("dense_gradient_l2_rel_err")), v.get("error")) for k, v in l["parity"].items()})
 if "cpu_baseline" in l:
     print(" cpu", l["cpu_baseline"]["value"], "index cpu", ix.get("cpu_baseline", {}).get("value"))
