@@ -242,15 +242,38 @@ __global__ void __launch_bounds__(256) fl_combine1_kernel(const Comb1Args a) {
         const int parts = (sk_owner(first + a.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1) * a.ksplit;
         const float zd = a.zd2[r];
         float M = zd;                                            // the positive takes part in the maximum
-        for (int s = 0; s < parts; ++s) M = fmaxf(M, a.pm[(int64_t)s * a.rows_pad + r]);
+        // The partials are read kCB at a time with every load of a batch issued before the first use (a plain loop over a
+        // run-time part count serialises one L2 round trip per part); the merge order -- part 0, 1, 2, ... -- is unchanged.
+        constexpr int kCB = 6;
+        const float* pm_r = a.pm + r;
+        const float* pl_r = a.pl + r;
+        const float4* pg_r = a.pg + (int64_t)c4 * a.rows_pad + r;
+        for (int s0 = 0; s0 < parts; s0 += kCB) {
+            float v[kCB];
+#pragma unroll
+            for (int j = 0; j < kCB; ++j) v[j] = (s0 + j < parts) ? pm_r[(int64_t)(s0 + j) * a.rows_pad] : -CUDART_INF_F;
+#pragma unroll
+            for (int j = 0; j < kCB; ++j) M = fmaxf(M, v[j]);
+        }
         float Loff = 0.f;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < parts; ++s) {
-            const float w = exp2f(a.pm[(int64_t)s * a.rows_pad + r] - M);
-            Loff = fmaf(a.pl[(int64_t)s * a.rows_pad + r], w, Loff);
-            if (a.dQ) {
-                const float4 g = a.pg[((int64_t)s * e4 + c4) * a.rows_pad + r];
-                acc.x = fmaf(g.x, w, acc.x); acc.y = fmaf(g.y, w, acc.y); acc.z = fmaf(g.z, w, acc.z); acc.w = fmaf(g.w, w, acc.w);
+        for (int s0 = 0; s0 < parts; s0 += kCB) {
+            float vm[kCB], vl[kCB];
+            float4 vg[kCB];
+#pragma unroll
+            for (int j = 0; j < kCB; ++j) {
+                const bool on = s0 + j < parts;
+                vm[j] = on ? pm_r[(int64_t)(s0 + j) * a.rows_pad] : -CUDART_INF_F;
+                vl[j] = on ? pl_r[(int64_t)(s0 + j) * a.rows_pad] : 0.f;
+                vg[j] = (on && a.dQ) ? pg_r[(int64_t)(s0 + j) * e4 * a.rows_pad] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < kCB; ++j) {
+                if (s0 + j < parts) {
+                    const float w = exp2f(vm[j] - M);
+                    Loff = fmaf(vl[j], w, Loff);
+                    acc.x = fmaf(vg[j].x, w, acc.x); acc.y = fmaf(vg[j].y, w, acc.y); acc.z = fmaf(vg[j].z, w, acc.z); acc.w = fmaf(vg[j].w, w, acc.w);
+                }
             }
         }
         const float pd = exp2f(zd - M);
@@ -326,9 +349,18 @@ __global__ void __launch_bounds__(256) fl_combine2_kernel(const Comb2Args a) {
             const int first = sd.unit0 + (r >> 8) * sd.n_tiles;
             const int parts = (sk_owner(first + sd.n_tiles - 1, a.units, a.grid) - sk_owner(first, a.units, a.grid) + 1) * a.ksplit;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z = 0; z < parts; ++z) {
-                const float4 v = sd.part[((int64_t)z * e4 + c4) * sd.rows_pad + r];
-                acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+            constexpr int kCB = 8;                                // loads batched as in combine 1; the sum order (part 0, 1, ...) is unchanged
+            const float4* pg_r = sd.part + (int64_t)c4 * sd.rows_pad + r;
+            for (int z0 = 0; z0 < parts; z0 += kCB) {
+                float4 v[kCB];
+#pragma unroll
+                for (int j = 0; j < kCB; ++j) v[j] = (z0 + j < parts) ? pg_r[(int64_t)(z0 + j) * e4 * sd.rows_pad] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < kCB; ++j) {
+                    if (z0 + j < parts) {
+                        acc.x = __fadd_rn(acc.x, v[j].x); acc.y = __fadd_rn(acc.y, v[j].y); acc.z = __fadd_rn(acc.z, v[j].z); acc.w = __fadd_rn(acc.w, v[j].w);
+                    }
+                }
             }
             const int tr = r + sd.d;
             float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -88,57 +88,38 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const __grid_co
     pl.hist[(size_t)threadIdx.x * pl.ntiles + blockIdx.x] = s_hist[threadIdx.x];
 }
 
-// exclusive scan of hist viewed as one array of kRadix*ntiles entries (digit-major): one CTA per job.  Each warp owns a
-// contiguous segment and walks it 128 entries at a time (one 16-byte load per lane, fully coalesced); two sweeps: segment
-// totals, then the scan proper with the carried prefix.
-__global__ void __launch_bounds__(1024) sort_scan_kernel(const __grid_constant__ PlanArr plans, int pass) {
-    const SortPlan& pl = plans.p[blockIdx.x];
-    if (pass >= pl.npass) return;
-    __shared__ uint32_t s_warp[32];
+// Exclusive scan of hist viewed as one array of kRadix*ntiles entries (digit-major), in two levels so that it is not one CTA's
+// serial walk (round 1: 21 us per pass at 2^20 ids, as long as the scatter): CTA (digit, job) scans ITS row of ntiles counts in
+// place and leaves the row total in hist[kRadix * ntiles + digit]; the scatter kernel adds the exclusive prefix of the 256 row
+// totals (a 256-thread scan in its prologue).
+__global__ void __launch_bounds__(256) sort_scan_kernel(const __grid_constant__ PlanArr plans, int pass) {
+    const SortPlan& pl = plans.p[blockIdx.y];
+    if (pass >= pl.npass || pl.ntiles == 0) return;
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_run;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total = kRadix * pl.ntiles;                       // multiple of 256
-    const int seg = ((total + 32 * 128 - 1) / (32 * 128)) * 128;  // entries per warp, multiple of 128
-    const int b = min(total, warp * seg), e = min(total, b + seg);
-    uint4* h4 = reinterpret_cast<uint4*>(pl.hist);             // workspace slices are 256-byte aligned
-    uint32_t sum = 0;
-    for (int i = b + lane * 4; i < e; i += 128) {
-        uint4 v = h4[i >> 2];
-        sum += v.x + v.y + v.z + v.w;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) s_warp[warp] = sum;
+    uint32_t* row = pl.hist + (size_t)blockIdx.x * pl.ntiles;
+    if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t v = s_warp[lane], inc = v;
+    for (int t0 = 0; t0 < pl.ntiles; t0 += 256) {
+        const int t = t0 + threadIdx.x;
+        const uint32_t v = t < pl.ntiles ? row[t] : 0u;
+        uint32_t inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
         }
-        s_warp[lane] = inc - v;                                 // exclusive prefix of the warp segments
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t before = s_run;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (t < pl.ntiles) row[t] = before + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 255) s_run = before + inc;
+        __syncthreads();
     }
-    __syncthreads();
-    uint32_t run = s_warp[warp];
-    for (int i0 = b; i0 < e; i0 += 128) {
-        const int i = i0 + lane * 4;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (i < e) v = h4[i >> 2];
-        const uint32_t mine = v.x + v.y + v.z + v.w;
-        uint32_t inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        uint32_t base = run + inc - mine;
-        if (i < e) {
-            uint4 w;
-            w.x = base; w.y = base + v.x; w.z = w.y + v.y; w.w = w.z + v.z;
-            h4[i >> 2] = w;
-        }
-        run += __shfl_sync(0xffffffffu, inc, 31);
-    }
+    if (threadIdx.x == 0) pl.hist[(size_t)kRadix * pl.ntiles + blockIdx.x] = s_run;
 }
 
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans,
@@ -180,10 +161,23 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const __grid
         __syncwarp();
     }
     __syncthreads();
-    // per digit: exclusive prefix over warps, plus the global base of (digit, tile)
+    // per digit: exclusive prefix over warps, plus the global base of (digit, tile) = the exclusive prefix of the digit totals
+    // (scanned here: 256 values, one per thread) + the tile's offset inside the digit's row
     {
         const int d = threadIdx.x;  // kSortThreads == kRadix
-        uint32_t run = pl.hist[(size_t)d * pl.ntiles + blockIdx.x];
+        __shared__ uint32_t s_dw[kSortWarps];
+        const uint32_t tot = pl.hist[(size_t)kRadix * pl.ntiles + d];
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_dw[warp] = inc;
+        __syncthreads();
+        uint32_t dbase = inc - tot;
+        for (int w = 0; w < warp; ++w) dbase += s_dw[w];
+        uint32_t run = dbase + pl.hist[(size_t)d * pl.ntiles + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
             uint32_t c = s_wcount[w][d];
@@ -613,7 +607,7 @@ static size_t stage_bytes(int max_n, int max_e) {
 static size_t per_job_bytes(int max_n, int max_e) {
     size_t n = (size_t)(max_n > 0 ? max_n : 1);
     size_t ntiles = (n + kTile - 1) / kTile;
-    return 4 * align_up(n * 4, 256) + align_up(ntiles * kRadix * 4, 256) + 2 * part_bytes(max_n, max_e) + stage_bytes(max_n, max_e);
+    return 4 * align_up(n * 4, 256) + align_up((ntiles + 1) * kRadix * 4, 256) + 2 * part_bytes(max_n, max_e) + stage_bytes(max_n, max_e);
 }
 
 static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, JobArr* ja, PlanArr* pa, int* max_tiles,
@@ -649,7 +643,7 @@ static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_
         p.vals[0] = reinterpret_cast<int32_t*>(base + 2 * seg);
         p.vals[1] = reinterpret_cast<int32_t*>(base + 3 * seg);
         p.hist = reinterpret_cast<uint32_t*>(base + 4 * seg);
-        size_t hist_bytes = align_up((size_t)ceil_div(max_n > 0 ? max_n : 1, kTile) * kRadix * 4, 256);
+        size_t hist_bytes = align_up(((size_t)ceil_div(max_n > 0 ? max_n : 1, kTile) + 1) * kRadix * 4, 256);   // + the 256 digit totals
         p.partL = reinterpret_cast<float*>(base + 4 * seg + hist_bytes);
         p.partR = reinterpret_cast<float*>(base + 4 * seg + hist_bytes + part_bytes(max_n, max_e));
         p.stage = jobs[j].shard_world > 1 ? reinterpret_cast<float*>(base + 4 * seg + hist_bytes + 2 * part_bytes(max_n, max_e)) : nullptr;
@@ -723,7 +717,7 @@ int tt_sparse_sort(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_byt
         dim3 grid((unsigned)max_tiles, (unsigned)njobs);
         sort_hist_kernel<<<grid, kSortThreads, 0, st>>>(ja, pa, pass);
         TT_LAUNCH_OK("sort_hist_kernel");
-        sort_scan_kernel<<<(unsigned)njobs, 1024, 0, st>>>(pa, pass);
+        sort_scan_kernel<<<dim3(kRadix, (unsigned)njobs), 256, 0, st>>>(pa, pass);
         TT_LAUNCH_OK("sort_scan_kernel");
         sort_scatter_kernel<<<grid, kSortThreads, 0, st>>>(ja, pa, pass);
         TT_LAUNCH_OK("sort_scatter_kernel");
