@@ -51,6 +51,7 @@ class _StepWorkspace:
         self.col_prob = torch.ones(batch, **f32) if model.logq_correction else None
         self.lse = torch.zeros(batch, **f32)
         self.loss = torch.zeros(1, **f32)
+        self.bias_ready = torch.cuda.Event()
         self.dq = torch.zeros((batch, e), **f32)
         self.dc = torch.zeros((batch, e), **f32)
         self.sm_ws = torch.empty(int(lib.tt_softmax_workspace_bytes(batch, batch, e)), dtype=torch.uint8, device="cuda")
@@ -243,25 +244,28 @@ class TwoTowerModel(AbstractKerasModel):
         lib = N.load()
         b, e = sw.batch, self.joint_embedding_size
         main = torch.cuda.current_stream()
-        # fork: the id sort depends on the (gathered) ids only
+        # fork: the ln p(candidate) gather and the id sort depend on the (gathered) ids only -- both leave the critical path
         sw.side.wait_stream(main)
+        bias = None
         with torch.cuda.stream(sw.side):
-            N.check(lib.tt_sparse_sort(sw.jobs, sw.njobs, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), N.stream_ptr()), "tt_sparse_sort")
+            sts = N.stream_ptr()
+            if self.logq_correction is not None:
+                if sw.bias_from_strings:
+                    N.check(lib.tt_log_f32(sw.col_prob.data_ptr(), sw.col_bias.data_ptr(), b, sts), "tt_log_f32")
+                else:
+                    N.check(lib.tt_gather_concat(sw.bias_feat, 1, b, 1, sw.col_bias.data_ptr(), 1, sts), "tt_gather_concat(logq)")
+                bias = sw.col_bias.data_ptr()
+                sw.bias_ready.record(sw.side)
+            N.check(lib.tt_sparse_sort(sw.jobs, sw.njobs, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), sts), "tt_sparse_sort")
         st = N.stream_ptr()
         # the two towers are independent until the logits: candidate side on its own stream
         sw.cand.wait_stream(main)
         q, q32 = self.query_tower.forward_ws(sw.q)
-        bias = None
         with torch.cuda.stream(sw.cand):
-            stc = N.stream_ptr()
             c, c32 = self.candidate_tower.forward_ws(sw.c)
-            if self.logq_correction is not None:
-                if sw.bias_from_strings:
-                    N.check(lib.tt_log_f32(sw.col_prob.data_ptr(), sw.col_bias.data_ptr(), b, stc), "tt_log_f32")
-                else:
-                    N.check(lib.tt_gather_concat(sw.bias_feat, 1, b, 1, sw.col_bias.data_ptr(), 1, stc), "tt_gather_concat(logq)")
-                bias = sw.col_bias.data_ptr()
         main.wait_stream(sw.cand)
+        if bias is not None:
+            main.wait_event(sw.bias_ready)
         use_tc = self.impl != N.TT_IMPL_SIMT and self._tc_ok()
         qa, ca = (q32, c32) if use_tc else (q, c)
         impl = N.TT_IMPL_TC if use_tc else N.TT_IMPL_SIMT
