@@ -37,6 +37,7 @@ struct SortPlan {  // per-job workspace pointers
     int32_t npass;
     int32_t vec;     // floats per lane access in the segmented reduce (1, 2 or 4): widest that divides e and the alignment of every row base
     int32_t gvec;    // 1: the gradient sources are aligned for `vec`-wide loads too (a feature's dX slice may start at any column)
+    int32_t svec;    // 1: staging copies 16-byte pieces (sources, staging rows and e allow it), else 4-byte pieces
 };
 struct PlanArr {
     SortPlan p[TT_MAX_JOBS];
@@ -424,24 +425,29 @@ __device__ __forceinline__ void block_body_vec(const tt_sparse_job& job, int kMo
     }
 }
 
-// Row-sharded tables: one warp per sorted entry copies the gradient row of an OWNED entry from wherever it was produced (the dX
-// block of another GPU, peer-mapped over NVLink) into the local staging array, in sorted order.  Every load is independent, so the
-// NVLink latency is paid once; the segmented reduce then streams contiguous local rows.
+// Row-sharded tables: the gradient row of every OWNED entry is copied from wherever it was produced (the dX block of another GPU,
+// peer-mapped over NVLink) into the local staging array, in sorted order; the segmented reduce then streams contiguous local rows.
+// One THREAD per piece of a row (16 bytes when the sources allow it, else 4): every thread walks the same short dependent chain
+// (key, position, piece) and all of them are in flight at once, so the NVLink latency is paid once per launch, not once per row
+// of a warp (the round-1 warp-per-entry form took 17 us for 8192 owned rows; a warp-per-32-entries form 37 us).
+template <typename T>
 __global__ void __launch_bounds__(256) sparse_stage_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans) {
     const SortPlan& pl = plans.p[blockIdx.y];
     const tt_sparse_job& job = jobs.j[blockIdx.y];
     if (pl.stage == nullptr) return;
-    const int lane = threadIdx.x & 31;
-    const int nw = (gridDim.x * blockDim.x) >> 5;
+    constexpr int W = (int)(sizeof(T) / sizeof(float));
+    if ((pl.svec != 0) != (W == 4)) return;          // this job is served by the other instantiation
+    const int per_row = job.e / W;
     const uint32_t* ks = pl.keys[pl.npass & 1];
     const int32_t* vs = pl.vals[pl.npass & 1];
     const uint32_t skip = skip_key(job);
-    // the owned entries are a prefix of the sorted array (the skip key sorts last): grid-stride over it, stop at the first foreign entry
-    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < pl.n; j += nw) {
+    const int64_t total = (int64_t)pl.n * per_row;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // the owned entries are a prefix of the sorted array (the skip key sorts last): a thread that meets a foreign entry is done
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += stride) {
+        const int j = (int)(p / per_row), c = (int)(p - (int64_t)j * per_row);
         if (ks[j] == skip) break;
-        const float* src = grad_row(job, vs[j]);
-        float* dst = pl.stage + (int64_t)j * job.e;
-        for (int c = lane; c < job.e; c += 32) dst[c] = __ldg(src + c);
+        reinterpret_cast<T*>(pl.stage + (int64_t)j * job.e)[c] = __ldg(reinterpret_cast<const T*>(grad_row(job, vs[j])) + c);
     }
 }
 
@@ -661,6 +667,7 @@ static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_
             for (int s = 0; s < jb.nsrc; ++s) gbits |= (uintptr_t)jb.grad[s] | ((uintptr_t)(uint32_t)jb.grad_ld[s] * sizeof(float));
             p.vec = want;
             p.gvec = (p.stage != nullptr || (gbits % (want * sizeof(float))) == 0) ? 1 : 0;   // staged rows are read from the workspace
+            p.svec = (p.stage != nullptr && jb.e % 4 == 0 && (gbits % 16) == 0 && ((uintptr_t)p.stage % 16) == 0) ? 1 : 0;
         }
         if (p.ntiles > *max_tiles) *max_tiles = p.ntiles;
         if (p.npass > *max_pass) *max_pass = p.npass;
@@ -681,10 +688,19 @@ static int launch_apply(const JobArr& ja, const PlanArr& pa, int njobs, int mode
     int max_n = 0;
     for (int j = 0; j < pa.n; ++j) { staged |= pa.p[j].stage != nullptr; max_n = pa.p[j].n > max_n ? pa.p[j].n : max_n; }
     if (staged) {
-        int64_t sg = ceil_div(max_n > 0 ? max_n : 1, 8);
-        if (sg > 4 * (int64_t)sm_count()) sg = 4 * (int64_t)sm_count();
-        sparse_stage_kernel<<<dim3((unsigned)sg, (unsigned)njobs), 256, 0, st>>>(ja, pa);
-        TT_LAUNCH_OK("sparse_stage_kernel");
+        int max_e = 1;
+        bool any4 = false, any1 = false;
+        for (int j = 0; j < pa.n; ++j) {
+            if (pa.p[j].stage == nullptr) continue;
+            max_e = ja.j[j].e > max_e ? ja.j[j].e : max_e;
+            (pa.p[j].svec ? any4 : any1) = true;
+        }
+        // a thread per 16-byte (4-byte) piece of the entries the rank can own: about 1 / world of the sorted array, grid-stride beyond
+        int64_t sg = ceil_div((int64_t)(max_n > 0 ? max_n : 1) * max_e / 4, 256);
+        if (sg > 16 * (int64_t)sm_count()) sg = 16 * (int64_t)sm_count();
+        if (sg < 1) sg = 1;
+        if (any4) { sparse_stage_kernel<float4><<<dim3((unsigned)sg, (unsigned)njobs), 256, 0, st>>>(ja, pa); TT_LAUNCH_OK("sparse_stage_kernel<16B>"); }
+        if (any1) { sparse_stage_kernel<float><<<dim3((unsigned)(4 * sg > 16 * (int64_t)sm_count() ? 16 * (int64_t)sm_count() : 4 * sg), (unsigned)njobs), 256, 0, st>>>(ja, pa); TT_LAUNCH_OK("sparse_stage_kernel<4B>"); }
     }
     if (max_n <= (1 << 17)) sparse_block_kernel<true><<<grid, 256, 0, st>>>(ja, pa, mode, lr, eps, omb1, omb2);
     else sparse_block_kernel<false><<<grid, 256, 0, st>>>(ja, pa, mode, lr, eps, omb1, omb2);

@@ -176,25 +176,44 @@ __global__ void __launch_bounds__(256) dense_fwd_fused64_kernel(const __grid_con
         __syncthreads();
         const int np = s_np;
         const bool write_x = Xout != nullptr;
-        for (int q = tid; q < kFwdPM * np; q += 256) {   // consecutive threads -> consecutive pieces of one row
-            const int r = q / np, pc = q - r * np;
-            const int row = m0 + r;
-            const int f = s_pf[pc], off = s_po[pc];
-            const tt_feature& ft = fa.f[f];
-            float* xs = Xs + r * kFwdXs + ft.col + off;
-            if (ft.table == nullptr) {
-                const float v = row < B ? __ldg(reinterpret_cast<const float*>(ft.src) + row) : 0.f;
-                xs[0] = v;
-                if (write_x && row < B) Xout[(int64_t)row * ldx + ft.col] = v;
-            } else {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < B) v = __ldg(reinterpret_cast<const float4*>(feature_row(ft, s_ids[r * TT_MAX_FEATURES + f]) + off));
-                if (((ft.col + off) & 3) == 0) *reinterpret_cast<float4*>(xs) = v;
-                else { xs[0] = v.x; xs[1] = v.y; xs[2] = v.z; xs[3] = v.w; }
-                if (write_x && row < B) {
-                    float* xo = Xout + (int64_t)row * ldx + ft.col + off;
-                    if (((ft.col + off) & 3) == 0) *reinterpret_cast<float4*>(xo) = v;
-                    else { xo[0] = v.x; xo[1] = v.y; xo[2] = v.z; xo[3] = v.w; }
+        // consecutive threads -> consecutive pieces of one row.  Four pieces per thread and round: all their loads are issued before
+        // the first store, so a row that lives in another GPU's HBM (row-sharded tables) costs one NVLink round trip per round
+        constexpr int kGB = 4;
+        for (int q0 = tid; q0 < kFwdPM * np; q0 += 256 * kGB) {
+            float4 v[kGB];
+            int rr[kGB], ff[kGB], oo[kGB];
+#pragma unroll
+            for (int u = 0; u < kGB; ++u) {
+                const int q = q0 + 256 * u;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                rr[u] = -1;
+                if (q < kFwdPM * np) {
+                    const int r = q / np, pc = q - r * np;
+                    rr[u] = r; ff[u] = s_pf[pc]; oo[u] = s_po[pc];
+                    const tt_feature& ft = fa.f[ff[u]];
+                    if (m0 + r < B) {
+                        if (ft.table == nullptr) v[u].x = __ldg(reinterpret_cast<const float*>(ft.src) + m0 + r);
+                        else v[u] = __ldg(reinterpret_cast<const float4*>(feature_row(ft, s_ids[r * TT_MAX_FEATURES + ff[u]]) + oo[u]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kGB; ++u) {
+                if (rr[u] < 0) continue;
+                const tt_feature& ft = fa.f[ff[u]];
+                const int row = m0 + rr[u], col = ft.col + oo[u];
+                float* xs = Xs + rr[u] * kFwdXs + col;
+                float* xo = Xout + (int64_t)row * ldx + col;
+                const bool wx = write_x && row < B;
+                if (ft.table == nullptr) {
+                    xs[0] = v[u].x;
+                    if (wx) xo[0] = v[u].x;
+                } else if ((col & 3) == 0) {
+                    *reinterpret_cast<float4*>(xs) = v[u];
+                    if (wx) *reinterpret_cast<float4*>(xo) = v[u];
+                } else {
+                    xs[0] = v[u].x; xs[1] = v[u].y; xs[2] = v[u].z; xs[3] = v[u].w;
+                    if (wx) { xo[0] = v[u].x; xo[1] = v[u].y; xo[2] = v[u].z; xo[3] = v[u].w; }
                 }
             }
         }

@@ -106,7 +106,10 @@ class Tower(AbstractKerasModel):
         il = self.input_layer
         last = len(self.layer_units) - 1
         n0 = self.layer_units[0]
-        if il.sharded():
+        # the 64-unit first layer has a fused gather + Dense kernel whose gather issues all loads of a round before the first store
+        # (csrc/tt_tower_panel.cu dense_fwd_fused64_kernel): one NVLink round trip per round also for rows in other GPUs' HBM
+        fused64 = n0 == 64 and il.output_dim <= 96 and all(t is None or t.e % 4 == 0 for _, t, _, _ in il.blocks)
+        if il.sharded() and not fused64:
             # row-sharded tables: most rows live in other GPUs' HBM.  A dedicated gather with every 16-byte load independent pays
             # the NVLink latency once; the first Dense then reads the local copy (bit-identical to the fused kernel).
             N.check(lib.tt_gather_concat(ws.feats, len(il.blocks), ws.batch, il.output_dim, ws.x.data_ptr(), il.ld, st), "tt_gather_concat")

@@ -298,27 +298,38 @@ class TwoTowerModel(AbstractKerasModel):
             self.dist.gather_rows(self, sw)
 
     def _phase_b(self, sw: _StepWorkspace) -> None:
+        torch = N.require_cuda()
         lib = N.load()
         opt = self.optimizer
-        st = N.stream_ptr()
         n_dense = self._store.used
-        if self.dist is not None:
-            self.dist.sum_dense(self, sw)
-        if n_dense:
-            ds = self._opt_state["dense"]
-            if isinstance(opt, Adagrad):
-                N.check(lib.tt_dense_adagrad(self._store.params.data_ptr(), ds[0].data_ptr(), self._store.grads.data_ptr(), n_dense,
-                                             opt.learning_rate, opt.epsilon, st), "tt_dense_adagrad")
-            else:
-                N.check(lib.tt_dense_adam(self._store.params.data_ptr(), ds[0].data_ptr(), ds[1].data_ptr(),
-                                          self._store.grads.data_ptr(), n_dense, sw.lr_t, opt.beta_1, opt.beta_2, opt.epsilon, st),
-                        "tt_dense_adam")
+        # the dense half (sum over ranks + Dense-layer update) and the sparse half (embedding rows) touch different memory: two streams
+        # when data parallel (on one GPU the dense half is one 2 us kernel: the fork / join costs more than it hides, measured)
+        main = torch.cuda.current_stream()
+        dense_stream = sw.cand if self.dist is not None else main
+        if dense_stream is not main:
+            dense_stream.wait_stream(main)
+        with torch.cuda.stream(dense_stream):
+            stc = N.stream_ptr()
+            if self.dist is not None:
+                self.dist.sum_dense(self, sw)
+            if n_dense:
+                ds = self._opt_state["dense"]
+                if isinstance(opt, Adagrad):
+                    N.check(lib.tt_dense_adagrad(self._store.params.data_ptr(), ds[0].data_ptr(), self._store.grads.data_ptr(), n_dense,
+                                                 opt.learning_rate, opt.epsilon, stc), "tt_dense_adagrad")
+                else:
+                    N.check(lib.tt_dense_adam(self._store.params.data_ptr(), ds[0].data_ptr(), ds[1].data_ptr(),
+                                              self._store.grads.data_ptr(), n_dense, sw.lr_t, opt.beta_1, opt.beta_2, opt.epsilon, stc),
+                            "tt_dense_adam")
+        st = N.stream_ptr()
         if isinstance(opt, Adagrad):
             N.check(lib.tt_sparse_adagrad(sw.jobs, sw.njobs, opt.learning_rate, opt.epsilon, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), st),
                     "tt_sparse_adagrad")
         else:
             N.check(lib.tt_sparse_adam(sw.jobs, sw.njobs, sw.lr_t, opt.beta_1, opt.beta_2, opt.epsilon, sw.sp_ws.data_ptr(),
                                        sw.sp_ws.numel(), st), "tt_sparse_adam")
+        if dense_stream is not main:
+            main.wait_stream(dense_stream)
 
     def _launch_step(self, sw: _StepWorkspace) -> None:
         ring = self.phase_stamps            # measurement aid: (1 + ring_len * 5,) int64 device tensor, see tt_stamp
