@@ -60,20 +60,25 @@ struct IndexSmem {
     float thr[BQ];
 };
 
-// grid: (query tiles, corpus splits).  Partial results (split, nq, K), best first, padded (-inf, kIdxPad).
+// Work items (query tile, corpus split), item w = split * n_qtiles + tile; a CTA strides over them (the fallback launches a small
+// grid: normally no tile is flagged and a CTA only reads a few flag words).  Partial results (split, nq, K), best first, padded
+// (-inf, kIdxPad).
 template <int BQ, int CAP>
 __global__ void __launch_bounds__(256) index_exact_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ C, int ldc, int nq,
                                                           int64_t n, int E, int K, int64_t per_split, float* __restrict__ ps,
-                                                          int32_t* __restrict__ pi, const int32_t* __restrict__ flags) {
+                                                          int32_t* __restrict__ pi, const int32_t* __restrict__ flags, int n_qtiles, int n_items) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IndexSmem<BQ, CAP>& sm = *reinterpret_cast<IndexSmem<BQ, CAP>*>(smem_raw);
-    const int q0 = blockIdx.x * BQ;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int bx = item % n_qtiles, by = item / n_qtiles;
+    const int q0 = bx * BQ;
+    __syncthreads();   // the previous item's lists are done with
     if (flags) {   // fallback mode: only query tiles holding a flagged query do any work
         int mine = 0;
         for (int q = threadIdx.x; q < BQ; q += 256) mine |= (q0 + q < nq) ? flags[q0 + q] : 0;
-        if (!__syncthreads_or(mine)) return;
+        if (!__syncthreads_or(mine)) continue;
     }
-    const int64_t c_begin = (int64_t)blockIdx.y * per_split;
+    const int64_t c_begin = (int64_t)by * per_split;
     const int64_t c_end = min(n, c_begin + per_split);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ty = tid >> 4, tx = tid & 15;
@@ -122,8 +127,9 @@ __global__ void __launch_bounds__(256) index_exact_kernel(const float* __restric
         for (int t = m + lane; t < CAP; t += 32) { sm.bs[ql][t] = -CUDART_INF_F; sm.bi[ql][t] = kIdxPad; }
         __syncwarp();
         warp_bitonic_sort<CAP>(sm.bs[ql], sm.bi[ql], lane);
-        int64_t o = ((int64_t)blockIdx.y * nq + (q0 + ql)) * K;
+        int64_t o = ((int64_t)by * nq + (q0 + ql)) * K;
         for (int t = lane; t < K; t += 32) { ps[o + t] = sm.bs[ql][t]; pi[o + t] = sm.bi[ql][t]; }
+    }
     }
 }
 
@@ -241,13 +247,17 @@ int index_exact(const float* Q, int ldq, const float* C, int ldc, int nq, int64_
     Carver cv(ws);
     float* ps = cv.take<float>((size_t)pl.nsplit * nq * K);
     int32_t* pi = cv.take<int32_t>((size_t)pl.nsplit * nq * K);
-    dim3 grid((unsigned)ceil_div(nq, pl.bq), (unsigned)pl.nsplit);
+    const int n_qtiles = (int)ceil_div(nq, pl.bq);
+    const int64_t items = (int64_t)n_qtiles * pl.nsplit;
+    TT_REQUIRE(items < (1ll << 31), "tt_index_topk (exact): too many work items");
+    const int64_t cap = flags ? 2 * (int64_t)sm_count() : items;      // fallback: a small grid strides over the (mostly unflagged) items
+    const unsigned grid = (unsigned)(items < cap ? items : cap);
     if (pl.bq == 64) {
-                { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(index_exact_kernel<64, 256>, (int)sizeof(IndexSmem<64, 256>))); }
-        index_exact_kernel<64, 256><<<grid, 256, pl.smem, st>>>(Q, ldq, C, ldc, nq, n, E, K, pl.per_split, ps, pi, flags);
+        { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(index_exact_kernel<64, 256>, (int)sizeof(IndexSmem<64, 256>))); }
+        index_exact_kernel<64, 256><<<grid, 256, pl.smem, st>>>(Q, ldq, C, ldc, nq, n, E, K, pl.per_split, ps, pi, flags, n_qtiles, (int)items);
     } else {
-                { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(index_exact_kernel<8, 2048>, (int)sizeof(IndexSmem<8, 2048>))); }
-        index_exact_kernel<8, 2048><<<grid, 256, pl.smem, st>>>(Q, ldq, C, ldc, nq, n, E, K, pl.per_split, ps, pi, flags);
+        { static SmemAttr smem_attr; TT_CUDA_OK(smem_attr.ensure(index_exact_kernel<8, 2048>, (int)sizeof(IndexSmem<8, 2048>))); }
+        index_exact_kernel<8, 2048><<<grid, 256, pl.smem, st>>>(Q, ldq, C, ldc, nq, n, E, K, pl.per_split, ps, pi, flags, n_qtiles, (int)items);
     }
     TT_LAUNCH_OK("index_exact_kernel");
     return merge_launch(ps, pi, pl.nsplit, nq, K, idx_base, out_s, out_i, st, flags);
