@@ -18,7 +18,13 @@ constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kItems = 8;                          // keys per thread
 constexpr int kTile = kSortThreads * kItems;       // 2048 keys per CTA
-constexpr int kRadix = 256;
+constexpr int kRadix = 256;                        // 8-bit digits: the bandwidth regime (hundreds of thousands of ids)
+// Training batches (<= 2^17 ids per table) are launch- and latency-bound instead: three kernels per pass, ~16 us per pass at 8192 ids
+// however few the keys.  They use 11-bit digits: a 1.37 M-row table sorts in TWO passes instead of three, and each pass fits one of
+// the two windows of a train step in which no persistent softmax kernel runs (under the tower forward / under the tower backward).
+constexpr int kWideBits = 11;
+constexpr int kWideMaxN = 1 << 17;
+constexpr int kRadixMax = 1 << kWideBits;
 
 struct JobArr {
     tt_sparse_job j[TT_MAX_JOBS];
@@ -35,6 +41,7 @@ struct SortPlan {  // per-job workspace pointers
     int32_t n;       // elements
     int32_t ntiles;
     int32_t npass;
+    int32_t bits;    // digit width of this call: 8, or 11 for small batches (then the scan is flat: hist holds global offsets)
     int32_t vec;     // floats per lane access in the segmented reduce (1, 2 or 4): widest that divides e and the alignment of every row base
     int32_t gvec;    // 1: the gradient sources are aligned for `vec`-wide loads too (a feature's dX slice may start at any column)
     int32_t svec;    // 1: staging copies 16-byte pieces (sources, staging rows and e allow it), else 4-byte pieces
@@ -44,10 +51,10 @@ struct PlanArr {
     int n;
 };
 
-static int passes_for_rows(int rows) {
+static int passes_for_rows(int rows, int digit_bits) {
     int bits = 1;
     while (bits < 31 && (1ll << bits) < (long long)rows) ++bits;
-    return (bits + 7) / 8;
+    return (bits + digit_bits - 1) / digit_bits;
 }
 
 // row-sharded tables: number of local rows of every shard; also the key given to entries this rank does not own
@@ -67,26 +74,75 @@ __device__ __forceinline__ uint32_t load_key(const tt_sparse_job& job, int i) {
 }
 
 // ---- pass kernels (blockIdx.y = job, blockIdx.x = tile) ---------------------------------------------
+template <int BITS>
 __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans,
                                                                  int pass) {
+    constexpr int RADIX = 1 << BITS;
     const SortPlan& pl = plans.p[blockIdx.y];
     if (pass >= pl.npass || (int)blockIdx.x >= pl.ntiles) return;
-    __shared__ uint32_t s_hist[kRadix];
-    s_hist[threadIdx.x] = 0;
+    __shared__ uint32_t s_hist[RADIX];
+    for (int d = threadIdx.x; d < RADIX; d += kSortThreads) s_hist[d] = 0;
     __syncthreads();
     const int base = blockIdx.x * kTile;
     const uint32_t* kin = pl.keys[pass & 1];
-    const int shift = pass * 8;
+    const int shift = pass * BITS;
 #pragma unroll
     for (int it = 0; it < kItems; ++it) {
         int i = base + it * kSortThreads + threadIdx.x;
         if (i < pl.n) {
             uint32_t key = pass == 0 ? load_key(jobs.j[blockIdx.y], i) : kin[i];
-            atomicAdd(&s_hist[(key >> shift) & 0xff], 1u);  // integer: order-independent
+            atomicAdd(&s_hist[(key >> shift) & (RADIX - 1)], 1u);  // integer: order-independent
         }
     }
     __syncthreads();
-    pl.hist[(size_t)threadIdx.x * pl.ntiles + blockIdx.x] = s_hist[threadIdx.x];
+    for (int d = threadIdx.x; d < RADIX; d += kSortThreads) pl.hist[(size_t)d * pl.ntiles + blockIdx.x] = s_hist[d];
+}
+
+// Flat exclusive scan of hist viewed as one array of radix*ntiles entries (digit-major) by ONE CTA per job: small batches only
+// (radix * ntiles <= 2^17 entries; 8192 at a batch of 8192 ids).  hist then holds global offsets: the scatter adds nothing.
+__global__ void __launch_bounds__(1024) sort_scan_flat_kernel(const __grid_constant__ PlanArr plans, int pass, int radix) {
+    const SortPlan& pl = plans.p[blockIdx.x];
+    if (pass >= pl.npass || pl.ntiles == 0) return;
+    __shared__ uint32_t s_warp[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = radix * pl.ntiles;                       // a multiple of 2048: 16-byte pieces, workspace slices are 256-byte aligned
+    const int per = ((total + 1023) / 1024 + 3) / 4 * 4;       // entries per thread, a multiple of 4
+    const int b = min(total, (int)threadIdx.x * per), e = min(total, b + per);
+    uint4* h4 = reinterpret_cast<uint4*>(pl.hist);
+    uint32_t sum = 0;
+#pragma unroll 4
+    for (int i = b; i < e; i += 4) {                           // independent loads: they pipeline
+        const uint4 v = h4[i >> 2];
+        sum += v.x + v.y + v.z + v.w;
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t v = s_warp[lane];
+        uint32_t w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        s_warp[lane] = w - v;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + inc - sum;
+#pragma unroll 4
+    for (int i = b; i < e; i += 4) {
+        const uint4 v = h4[i >> 2];
+        uint4 w;
+        w.x = run; w.y = run + v.x; w.z = w.y + v.y; w.w = w.z + v.z;
+        h4[i >> 2] = w;
+        run = w.w + v.w;
+    }
 }
 
 // Exclusive scan of hist viewed as one array of kRadix*ntiles entries (digit-major), in two levels so that it is not one CTA's
@@ -123,12 +179,15 @@ __global__ void __launch_bounds__(256) sort_scan_kernel(const __grid_constant__ 
     if (threadIdx.x == 0) pl.hist[(size_t)kRadix * pl.ntiles + blockIdx.x] = s_run;
 }
 
+template <int BITS>
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const __grid_constant__ JobArr jobs, const __grid_constant__ PlanArr plans,
                                                                     int pass) {
+    constexpr int RADIX = 1 << BITS;
     const SortPlan& pl = plans.p[blockIdx.y];
     if (pass >= pl.npass || (int)blockIdx.x >= pl.ntiles) return;
-    __shared__ uint32_t s_wcount[kSortWarps][kRadix];
-    for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&s_wcount[0][0])[i] = 0;
+    __shared__ uint16_t s_wcount[kSortWarps][RADIX];   // per warp: keys of each digit (<= 256 per warp), then the exclusive prefix over warps
+    __shared__ uint32_t s_base[RADIX];                 // global position of the tile's first key of each digit
+    for (int i = threadIdx.x; i < kSortWarps * RADIX; i += kSortThreads) (&s_wcount[0][0])[i] = 0;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int base = blockIdx.x * kTile + warp * (kTile / kSortWarps);  // each warp owns 256 consecutive keys
@@ -136,7 +195,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const __grid
     const int32_t* vin = pl.vals[pass & 1];
     uint32_t* kout = pl.keys[(pass + 1) & 1];
     int32_t* vout = pl.vals[(pass + 1) & 1];
-    const int shift = pass * 8;
+    const int shift = pass * BITS;
     uint32_t key[kItems];
     int32_t val[kItems];
     uint32_t rank[kItems];
@@ -151,38 +210,42 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const __grid
             if (pass == 0) { key[it] = load_key(jobs.j[blockIdx.y], i); val[it] = i; }
             else { key[it] = kin[i]; val[it] = vin[i]; }
         }
-        uint32_t digit = ok ? ((key[it] >> shift) & 0xff) : 0xffffffffu;  // invalid lanes group together
+        uint32_t digit = ok ? ((key[it] >> shift) & (RADIX - 1)) : 0xffffffffu;  // invalid lanes group together
         uint32_t peers = __match_any_sync(0xffffffffu, digit);
         int leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (ok && lane == leader) old = s_wcount[warp][digit];
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[it] = old + __popc(peers & lt);
-        if (ok && lane == leader) s_wcount[warp][digit] = old + __popc(peers);
+        if (ok && lane == leader) s_wcount[warp][digit] = (uint16_t)(old + __popc(peers));
         __syncwarp();
     }
     __syncthreads();
-    // per digit: exclusive prefix over warps, plus the global base of (digit, tile) = the exclusive prefix of the digit totals
-    // (scanned here: 256 values, one per thread) + the tile's offset inside the digit's row
-    {
-        const int d = threadIdx.x;  // kSortThreads == kRadix
-        __shared__ uint32_t s_dw[kSortWarps];
-        const uint32_t tot = pl.hist[(size_t)kRadix * pl.ntiles + d];
-        uint32_t inc = tot;
+    // per digit: exclusive prefix over warps, and the global base of (digit, tile)
+    uint32_t dbase = 0;
+    if constexpr (BITS == 8) {
+        if (pl.bits == 8) {   // two-level scan: the exclusive prefix of the digit totals is formed here (256 values, one per thread)
+            __shared__ uint32_t s_dw[kSortWarps];
+            const uint32_t tot = pl.hist[(size_t)RADIX * pl.ntiles + threadIdx.x];
+            uint32_t inc = tot;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            if (lane == 31) s_dw[warp] = inc;
+            __syncthreads();
+            dbase = inc - tot;
+            for (int w = 0; w < warp; ++w) dbase += s_dw[w];
         }
-        if (lane == 31) s_dw[warp] = inc;
-        __syncthreads();
-        uint32_t dbase = inc - tot;
-        for (int w = 0; w < warp; ++w) dbase += s_dw[w];
-        uint32_t run = dbase + pl.hist[(size_t)d * pl.ntiles + blockIdx.x];
+    }
+    for (int d = threadIdx.x; d < RADIX; d += kSortThreads) {
+        s_base[d] = dbase + pl.hist[(size_t)d * pl.ntiles + blockIdx.x];
+        uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
-            uint32_t c = s_wcount[w][d];
-            s_wcount[w][d] = run;
+            const uint32_t c = s_wcount[w][d];
+            s_wcount[w][d] = (uint16_t)run;
             run += c;
         }
     }
@@ -191,7 +254,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const __grid
     for (int it = 0; it < kItems; ++it) {
         int i = base + it * 32 + lane;
         if (i < pl.n) {
-            uint32_t pos = s_wcount[warp][(key[it] >> shift) & 0xff] + rank[it];
+            const uint32_t d = (key[it] >> shift) & (RADIX - 1);
+            uint32_t pos = s_base[d] + s_wcount[warp][d] + rank[it];
             kout[pos] = key[it];
             vout[pos] = val[it];
         }
@@ -613,7 +677,8 @@ static size_t stage_bytes(int max_n, int max_e) {
 static size_t per_job_bytes(int max_n, int max_e) {
     size_t n = (size_t)(max_n > 0 ? max_n : 1);
     size_t ntiles = (n + kTile - 1) / kTile;
-    return 4 * align_up(n * 4, 256) + align_up((ntiles + 1) * kRadix * 4, 256) + 2 * part_bytes(max_n, max_e) + stage_bytes(max_n, max_e);
+    const size_t radix = max_n <= kWideMaxN ? kRadixMax : kRadix;
+    return 4 * align_up(n * 4, 256) + align_up((ntiles + 1) * radix * 4, 256) + 2 * part_bytes(max_n, max_e) + stage_bytes(max_n, max_e);
 }
 
 static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, JobArr* ja, PlanArr* pa, int* max_tiles,
@@ -649,13 +714,15 @@ static int make_plans(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_
         p.vals[0] = reinterpret_cast<int32_t*>(base + 2 * seg);
         p.vals[1] = reinterpret_cast<int32_t*>(base + 3 * seg);
         p.hist = reinterpret_cast<uint32_t*>(base + 4 * seg);
-        size_t hist_bytes = align_up(((size_t)ceil_div(max_n > 0 ? max_n : 1, kTile) + 1) * kRadix * 4, 256);   // + the 256 digit totals
+        const int bits = max_n <= kWideMaxN ? kWideBits : 8;
+        size_t hist_bytes = align_up(((size_t)ceil_div(max_n > 0 ? max_n : 1, kTile) + 1) * (size_t)(1 << bits) * 4, 256);   // + the digit totals
         p.partL = reinterpret_cast<float*>(base + 4 * seg + hist_bytes);
         p.partR = reinterpret_cast<float*>(base + 4 * seg + hist_bytes + part_bytes(max_n, max_e));
         p.stage = jobs[j].shard_world > 1 ? reinterpret_cast<float*>(base + 4 * seg + hist_bytes + 2 * part_bytes(max_n, max_e)) : nullptr;
         p.n = jobs[j].nsrc * jobs[j].n_per_src;
         p.ntiles = (int)ceil_div(p.n, kTile);
-        p.npass = passes_for_rows(jobs[j].shard_world > 1 ? (int)skip_key(jobs[j]) + 1 : jobs[j].rows);
+        p.bits = bits;
+        p.npass = passes_for_rows(jobs[j].shard_world > 1 ? (int)skip_key(jobs[j]) + 1 : jobs[j].rows, bits);
         {   // access width of the segmented reduce: e <= 32 -> 1 float per lane, <= 64 -> 2, wider -> 4, narrowed until it divides e
             // and the alignment of every base pointer the kernels add `row * e + column` to
             const tt_sparse_job& jb = jobs[j];
@@ -722,21 +789,37 @@ size_t tt_sparse_workspace_bytes(int njobs, int max_n, int max_e) {
 }
 
 int tt_sparse_sort(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, void* stream) {
+    return tt_sparse_sort_passes(jobs, njobs, ws, ws_bytes, 0, 1 << 30, stream);
+}
+
+int tt_sparse_sort_passes(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, int first_pass, int end_pass, void* stream) {
     JobArr ja;
     PlanArr pa;
     int max_tiles = 0, max_pass = 0;
     int rc = make_plans(jobs, njobs, ws, ws_bytes, &ja, &pa, &max_tiles, &max_pass, "tt_sparse_sort");
     if (rc) return rc;
+    TT_REQUIRE(first_pass >= 0 && end_pass >= first_pass, "tt_sparse_sort_passes: bad pass range");
     if (max_tiles == 0) return TT_OK;
     cudaStream_t st = as_stream(stream);
-    for (int pass = 0; pass < max_pass; ++pass) {
+    if (end_pass < max_pass) max_pass = end_pass;
+    const bool wide = pa.p[0].bits == kWideBits;
+    for (int pass = first_pass; pass < max_pass; ++pass) {
         dim3 grid((unsigned)max_tiles, (unsigned)njobs);
-        sort_hist_kernel<<<grid, kSortThreads, 0, st>>>(ja, pa, pass);
-        TT_LAUNCH_OK("sort_hist_kernel");
-        sort_scan_kernel<<<dim3(kRadix, (unsigned)njobs), 256, 0, st>>>(pa, pass);
-        TT_LAUNCH_OK("sort_scan_kernel");
-        sort_scatter_kernel<<<grid, kSortThreads, 0, st>>>(ja, pa, pass);
-        TT_LAUNCH_OK("sort_scatter_kernel");
+        if (wide) {
+            sort_hist_kernel<kWideBits><<<grid, kSortThreads, 0, st>>>(ja, pa, pass);
+            TT_LAUNCH_OK("sort_hist_kernel");
+            sort_scan_flat_kernel<<<(unsigned)njobs, 1024, 0, st>>>(pa, pass, kRadixMax);
+            TT_LAUNCH_OK("sort_scan_flat_kernel");
+            sort_scatter_kernel<kWideBits><<<grid, kSortThreads, 0, st>>>(ja, pa, pass);
+            TT_LAUNCH_OK("sort_scatter_kernel");
+        } else {
+            sort_hist_kernel<8><<<grid, kSortThreads, 0, st>>>(ja, pa, pass);
+            TT_LAUNCH_OK("sort_hist_kernel");
+            sort_scan_kernel<<<dim3(kRadix, (unsigned)njobs), 256, 0, st>>>(pa, pass);
+            TT_LAUNCH_OK("sort_scan_kernel");
+            sort_scatter_kernel<8><<<grid, kSortThreads, 0, st>>>(ja, pa, pass);
+            TT_LAUNCH_OK("sort_scatter_kernel");
+        }
     }
     return TT_OK;
 }

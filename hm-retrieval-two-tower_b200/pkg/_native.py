@@ -101,6 +101,7 @@ SIGNATURES = {
     "tt_fill_f32": (c_int, [c_void_p, c_float, c_int64, c_void_p]),
     "tt_sparse_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "tt_sparse_sort": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_void_p, c_size_t, c_void_p]),
+    "tt_sparse_sort_passes": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "tt_sparse_adagrad": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "tt_sparse_adam": (c_int, [ctypes.POINTER(TTSparseJob), c_int, c_float, c_float, c_float, c_float, c_void_p, c_size_t,
                                c_void_p]),

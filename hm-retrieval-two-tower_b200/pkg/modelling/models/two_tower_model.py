@@ -256,7 +256,15 @@ class TwoTowerModel(AbstractKerasModel):
                     N.check(lib.tt_gather_concat(sw.bias_feat, 1, b, 1, sw.col_bias.data_ptr(), 1, sts), "tt_gather_concat(logq)")
                 bias = sw.col_bias.data_ptr()
                 sw.bias_ready.record(sw.side)
-            N.check(lib.tt_sparse_sort(sw.jobs, sw.njobs, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), sts), "tt_sparse_sort")
+            # The persistent softmax passes hold every SM and are statically partitioned: a kernel running beside them slows a few
+            # SMs and with them the whole pass (measured: the id sort beside the softmax cost 25 us of a 206 us step).  A training
+            # batch sorts in two radix passes (11-bit digits): pass 0 runs now, under the tower forward; the second one is queued
+            # behind the softmax (below) and runs under the tower backward.
+            # Large batches keep the whole sort here: beside a multi-millisecond softmax the interference is a few per cent, while a
+            # sort pass behind it would be exposed.
+            split_sort = sw.batch * (1 if self.dist is None else self.dist.world) <= int(os.environ.get("TT_SPLIT_SORT_MAX", "32768"))
+            N.check(lib.tt_sparse_sort_passes(sw.jobs, sw.njobs, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), 0, 1 if split_sort else 1 << 30, sts),
+                    "tt_sparse_sort_passes(0)")
         st = N.stream_ptr()
         # the two towers are independent until the logits: candidate side on its own stream
         sw.cand.wait_stream(main)
@@ -285,6 +293,11 @@ class TwoTowerModel(AbstractKerasModel):
                                                 sw.dq.data_ptr(), e, sw.dc.data_ptr(), e, sw.sm_ws.data_ptr(), sw.sm_ws.numel(), impl, st),
                     "tt_inbatch_softmax_step")
         sw.cand.wait_stream(main)
+        if split_sort:
+            sw.side.wait_stream(main)   # the softmax is done (stream order): the rest of the id sort overlaps the tower backward
+            with torch.cuda.stream(sw.side):
+                N.check(lib.tt_sparse_sort_passes(sw.jobs, sw.njobs, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), 1, 1 << 30, N.stream_ptr()),
+                        "tt_sparse_sort_passes(1..)")
         self.query_tower.backward_ws(sw.q, sw.dq)
         with torch.cuda.stream(sw.cand):
             self.candidate_tower.backward_ws(sw.c, sw.dc)

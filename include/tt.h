@@ -204,6 +204,12 @@ size_t tt_sparse_workspace_bytes(int njobs, int max_n, int max_e);
 /* Stable LSD radix sort of (id, position) for every job; depends on ids only, so it can run on a
  * side stream concurrently with forward/backward. */
 int tt_sparse_sort(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, void* stream);
+/* The same sort, radix passes [first_pass, end_pass) only (8 bits per pass, as many passes as the largest table's row count needs;
+ * end_pass beyond that is clipped).  The persistent softmax kernels hold every SM and are statically partitioned: a sort kernel
+ * that runs beside them slows some SMs and with them the whole pass, so the train step runs pass 0 under the tower forward and
+ * the remaining passes under the tower backward (same stream or events in between: the passes must run in order). */
+int tt_sparse_sort_passes(const tt_sparse_job* jobs, int njobs, void* ws, size_t ws_bytes, int first_pass, int end_pass,
+                          void* stream);
 int tt_sparse_adagrad(const tt_sparse_job* jobs, int njobs, float lr, float eps, void* ws, size_t ws_bytes,
                       void* stream);
 /* Non-lazy legacy Adam: whole-table decay + update every step. `touched` is a
