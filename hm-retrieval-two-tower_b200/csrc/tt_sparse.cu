@@ -19,11 +19,11 @@ constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kItems = 8;                          // keys per thread
 constexpr int kTile = kSortThreads * kItems;       // 2048 keys per CTA
 constexpr int kRadix = 256;                        // 8-bit digits: the bandwidth regime (hundreds of thousands of ids)
-// Training batches (<= 2^17 ids per table) are launch- and latency-bound instead: three kernels per pass, ~16 us per pass at 8192 ids
+// Training batches (<= 2^14 ids per table) are launch- and latency-bound instead: three kernels per pass, ~16 us per pass at 8192 ids
 // however few the keys.  They use 11-bit digits: a 1.37 M-row table sorts in TWO passes instead of three, and each pass fits one of
 // the two windows of a train step in which no persistent softmax kernel runs (under the tower forward / under the tower backward).
 constexpr int kWideBits = 11;
-constexpr int kWideMaxN = 1 << 17;
+constexpr int kWideMaxN = 1 << 14;   // beyond, the flat scan and the 2048-bin prologues cost more than the third pass saves (measured at 65536 ids: 0.30 -> 0.375 ms per 8-GPU step)
 constexpr int kRadixMax = 1 << kWideBits;
 
 struct JobArr {

@@ -260,9 +260,10 @@ class TwoTowerModel(AbstractKerasModel):
             # SMs and with them the whole pass (measured: the id sort beside the softmax cost 25 us of a 206 us step).  A training
             # batch sorts in two radix passes (11-bit digits): pass 0 runs now, under the tower forward; the second one is queued
             # behind the softmax (below) and runs under the tower backward.
-            # Large batches keep the whole sort here: beside a multi-millisecond softmax the interference is a few per cent, while a
-            # sort pass behind it would be exposed.
-            split_sort = sw.batch * (1 if self.dist is None else self.dist.world) <= int(os.environ.get("TT_SPLIT_SORT_MAX", "32768"))
+            # Larger sorts (batch x ranks > 16384 ids per table: 8-bit digits, three longer passes) stay here as a whole: beside a
+            # multi-millisecond softmax the interference is a few per cent, and at 8 GPUs x 8192 the split was measured slower
+            # (0.304 vs 0.294 ms per step) because two exposed passes cost more than the interference they avoid.
+            split_sort = sw.batch * (1 if self.dist is None else self.dist.world) <= int(os.environ.get("TT_SPLIT_SORT_MAX", "16384"))
             N.check(lib.tt_sparse_sort_passes(sw.jobs, sw.njobs, sw.sp_ws.data_ptr(), sw.sp_ws.numel(), 0, 1 if split_sort else 1 << 30, sts),
                     "tt_sparse_sort_passes(0)")
         st = N.stream_ptr()
