@@ -19,7 +19,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(32) peer_barrier_kernel(const unsigned long long* __restrict__ blocks, int rank, int world, int slot) {
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const unsigned long long* __restrict__ blocks, int rank, int world, int slot,
+                                                          long long max_cycles) {
     uint32_t* mine = reinterpret_cast<uint32_t*>(blocks[rank]);
     const uint32_t epoch = mine[slot] + 1;          // every lane reads it before lane 0 bumps it (after the __syncwarp below)
     const int t = threadIdx.x;
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const unsigned long lo
         const uint32_t* src = mine + TT_PEER_SLOTS + slot * world + t;                   // wait for peer t's arrival in MY block (local spin)
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(src) - epoch) < 0) {
-            if (clock64() - t0 > (20ll << 30)) {   // ~10 s at 2 GHz: a rank died or the ranks left lockstep -- fail loudly, do not hang
+            if (clock64() - t0 > max_cycles) {     // a rank died or the ranks left lockstep -- fail loudly, do not hang
                 printf("tt_peer_barrier: rank %d timed out waiting for rank %d (slot %d, epoch %u)\n", rank, t, slot, epoch);
                 __trap();
             }
@@ -81,7 +82,15 @@ extern "C" {
 int tt_peer_barrier(const void* flag_blocks, int rank, int world, int slot, void* stream) {
     TT_REQUIRE(flag_blocks != nullptr, "tt_peer_barrier: null pointer");
     TT_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world && slot >= 0 && slot < TT_PEER_SLOTS, "tt_peer_barrier: bad rank/world/slot");
-    peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(flag_blocks), rank, world, slot);
+    // how long a rank may wait for its peers before the kernel traps: TT_PEER_TIMEOUT_S seconds (default 120; a host-side stall of
+    // one rank -- loading a file, a checkpoint, the first eager step -- must stay below it), counted at ~2 GHz
+    static const long long max_cycles = [] {
+        const char* e = getenv("TT_PEER_TIMEOUT_S");
+        double sec = e ? atof(e) : 120.0;
+        if (!(sec >= 1.0)) sec = 1.0;
+        return (long long)(sec * 2.0e9);
+    }();
+    peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(flag_blocks), rank, world, slot, max_cycles);
     TT_LAUNCH_OK("peer_barrier_kernel");
     return TT_OK;
 }

@@ -56,3 +56,25 @@ class PeerBuffer:
             self.ptrs.append(int(p.value))
         # device-side pointer table (what tt_feature.table points at for a row-sharded table)
         self.ptr_table = torch.tensor(self.ptrs, dtype=torch.int64, device="cuda")
+        self._group = group
+        self._closed = False
+
+    def close(self) -> None:
+        """Collective over the group: every rank unmaps the peers' allocations, waits until all ranks have done so, then frees its own
+        (an exporter must not free memory a peer still maps).  The views handed out (``local``, ``ptr_table``) are dead afterwards.
+        Called when a data-parallel step workspace is evicted; process exit releases whatever is still open."""
+        import torch.distributed as dist
+
+        if self._closed:
+            return
+        torch = N.require_cuda()
+        lib = N.load()
+        torch.cuda.synchronize()
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                N.check(lib.tt_peer_close(ctypes.c_void_p(p)), f"tt_peer_close(rank {r})")
+        dist.barrier(group=self._group)
+        N.check(lib.tt_peer_free(ctypes.c_void_p(self._ptr)), "tt_peer_free")
+        self._closed = True
+        self.local = None
+        self.ptr_table = None

@@ -191,6 +191,22 @@ class BruteForceIndex(AbstractKerasModel):
             return stage.numpy().copy()    # the caller's own array: the staging buffer is reused by the next call
         return self._identifiers[idx.cpu().numpy()]
 
+    def canonical_rows(self):
+        """None when every identifier occurs once; else a device int32 array row -> FIRST row holding the same identifier (the row
+        positions_of reports), so that Recall@k on row indices counts every row of a repeated identifier like the reference's
+        comparison of identifiers does (index_recall.py:54-58)."""
+        if "_canon" not in self.__dict__:
+            canon = None
+            if self._identifiers is not None:
+                ids = np.asarray(self._identifiers)
+                keys = ids if ids.dtype.kind in "iu" else np.array([v.decode() if isinstance(v, bytes) else str(v) for v in ids.reshape(-1)])
+                _, first, inverse = np.unique(keys, return_index=True, return_inverse=True)
+                if first.shape[0] < keys.shape[0]:
+                    torch = N.require_cuda()
+                    canon = torch.from_numpy(first[inverse].astype(np.int32)).cuda()
+            self.__dict__["_canon"] = canon
+        return self.__dict__["_canon"]
+
     def positions_of(self, ids) -> np.ndarray:
         """Global row index of each identifier (-1 when absent); used by IndexRecall's device path."""
         flat = np.asarray(ids).reshape(-1)

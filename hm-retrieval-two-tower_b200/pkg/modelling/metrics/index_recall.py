@@ -32,9 +32,14 @@ class IndexRecall:
         self.ks = list(ks)
         if len(self.ks) > N.TT_MAX_KS:
             raise ValueError(f"at most {N.TT_MAX_KS} cut-offs")
+        # hits / seen / metric are what the reference exposes.  This process's own counts live in _local_*: all_reduce() sums THOSE
+        # over the ranks and publishes the totals in hits / seen / metric, so calling it twice (or scoring more batches and
+        # calling it again) never counts anything twice.
         self.hits = {k: np.int32(0) for k in self.ks}
         self.seen = np.int32(0)
         self.metric = {k: np.int32(0) for k in self.ks}
+        self._local_hits = {k: np.int32(0) for k in self.ks}
+        self._local_seen = np.int32(0)
         self._dev_hits = None
         self._dev_ks = None
 
@@ -42,6 +47,9 @@ class IndexRecall:
         torch = N.require_cuda()
         lib = N.load()
         _, idx = self.index.query_indices(queries)
+        canon = self.index.canonical_rows() if hasattr(self.index, "canonical_rows") else None
+        if canon is not None:      # repeated identifiers: the reference compares IDENTIFIERS (tf.equal), so every row of an id counts
+            idx = torch.where(idx >= 0, canon[idx.clamp(min=0).long()], idx).contiguous()
         if isinstance(true_candidate_ids, torch.Tensor) and true_candidate_ids.dtype in (torch.int32, torch.int64) \
                 and getattr(self.index, "identifiers_are_positions", False):
             truth = true_candidate_ids.reshape(-1).to(device="cuda", dtype=torch.int32)
@@ -55,12 +63,12 @@ class IndexRecall:
                                    self._dev_ks.ctypes.data, len(self.ks), self._dev_hits.data_ptr(), N.stream_ptr()), "tt_recall_hits")
         host = self._dev_hits.cpu().numpy()
         for k, h in zip(self.ks, host):
-            self.hits[k] = np.int32(h)
+            self._local_hits[k] = np.int32(h)
 
     def __call__(self, queries, true_candidate_ids) -> Dict[int, float]:
         true_candidate_ids = D.unwrap(true_candidate_ids)      # TF / DLPack tensors -> torch or numpy
         n = int(true_candidate_ids.shape[0])
-        self.seen = np.int32(self.seen + n)
+        self._local_seen = np.int32(self._local_seen + n)
         if hasattr(self.index, "query_indices"):
             self._device_update(queries, true_candidate_ids)
         else:
@@ -78,28 +86,29 @@ class IndexRecall:
                 else:
                     truth = D._as_bytes_array(truth).reshape(-1, 1)
             for k in self.ks:
-                self.hits[k] = np.int32(self.hits[k] + np.int32(np.sum(truth == candidates[:, :k])))
+                self._local_hits[k] = np.int32(self._local_hits[k] + np.int32(np.sum(truth == candidates[:, :k])))
+        self.seen = self._local_seen
         for k in self.ks:
+            self.hits[k] = self._local_hits[k]
             self.metric[k] = np.float64(self.hits[k]) / np.float64(self.seen)
         return self.metric
 
     def all_reduce(self, group=None) -> Dict[int, float]:
         """Multi-GPU evaluation: every rank has scored its own share of the test queries; the int32 hit and seen
-        counters are summed over the ranks (exact) and the ratios recomputed, so every rank ends with the global Recall@k."""
+        counters are summed over the ranks (exact) and the ratios recomputed, so every rank ends with the global Recall@k in
+        hits / seen / metric.  Idempotent: the ranks' own counts are kept apart and are what is summed."""
         import torch
         import torch.distributed as dist
 
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return self.metric
         dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-        t = torch.tensor([int(self.hits[k]) for k in self.ks] + [int(self.seen)], dtype=torch.int32, device=dev)
+        t = torch.tensor([int(self._local_hits[k]) for k in self.ks] + [int(self._local_seen)], dtype=torch.int32, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         vals = t.cpu().numpy()
         for k, h in zip(self.ks, vals[:-1]):
             self.hits[k] = np.int32(h)
         self.seen = np.int32(vals[-1])
-        if self._dev_hits is not None:        # keep the device counters consistent with the merged totals
-            self._dev_hits.copy_(torch.from_numpy(np.asarray(vals[:-1], dtype=np.int32)))
         for k in self.ks:
             self.metric[k] = np.float64(self.hits[k]) / np.float64(self.seen)
         return self.metric

@@ -172,7 +172,10 @@ class TwoTowerModel(AbstractKerasModel):
         sw = self._steps.get(batch)
         if sw is None:
             if len(self._steps) >= 4:
-                self._steps.pop(next(iter(self._steps)))
+                old = self._steps.pop(next(iter(self._steps)))
+                for v in (getattr(old, "dp", None) or {}).values():     # data parallel: peer-shared buffers are released collectively
+                    if hasattr(v, "close") and hasattr(v, "ptr_table"):
+                        v.close()
             sw = self._steps[batch] = _StepWorkspace(self, batch)
             self._build_jobs(sw)
         return sw

@@ -82,7 +82,8 @@ int tt_peer_free(void* ptr);
  * `flag_blocks`: device array of G pointers; entry r = rank r's flag block, TT_PEER_FLAG_WORDS(G) zero-initialised uint32 in
  * peer-shareable memory.  `slot` < TT_PEER_SLOTS names the barrier (each call site of a step uses its own slot).  On return of the
  * kernel every rank's work queued on its stream before its own call is complete and visible to peer reads.  All ranks must call
- * the same slots in the same order; a rank that waits ~10 s traps (the launch fails loudly instead of hanging the GPUs). */
+ * the same slots in the same order; a rank that waits longer than TT_PEER_TIMEOUT_S seconds (environment, default 120) traps:
+ * the launch fails loudly instead of hanging the GPUs. */
 #define TT_PEER_SLOTS 4
 #define TT_PEER_FLAG_WORDS(G) (TT_PEER_SLOTS * (1 + (G)))
 int tt_peer_barrier(const void* flag_blocks, int rank, int world, int slot, void* stream);

@@ -146,6 +146,7 @@ def _recall_worker(rank, world, port, out):
             t = mine[lo:lo + 2]
             metric({"q": np.zeros((len(t), 1))}, t.reshape(-1, 1))
         metric.all_reduce()
+        metric.all_reduce()                                           # idempotent: the ranks' own counts are what is summed
         np.savez(out, hits=np.array([metric.hits[k] for k in (1, 2, 5)]), seen=metric.seen, m=np.array([metric.metric[k] for k in (1, 2, 5)]))
     finally:
         dist.destroy_process_group()

@@ -529,3 +529,37 @@ def test_index_from_local_rows_equals_the_whole_corpus_index(lib):
     assert np.array_equal(one.positions_of([0, 5, n - 1, n, -3]), [0, 5, n - 1, -1, -1])
     with pytest.raises(ValueError):
         BruteForceIndex.from_local_rows(k, ident, corpus[:10], n - 5, n)
+
+
+def test_recall_counts_every_row_of_a_repeated_identifier(lib):
+    """The reference compares identifiers (tf.equal): when an id occurs twice in the corpus, a hit on EITHER row counts (and both
+    count when both are within the cut-off).  The device path compares row indices, so it maps rows to the id's first row."""
+    import torch
+
+    from pkg.modelling.indices.brute_force import BruteForceIndex
+    from pkg.modelling.metrics.index_recall import IndexRecall
+
+    class Ident:
+        def __call__(self, x):
+            return x["q"]
+
+        def get_input_signature(self):
+            return {}
+
+    rng = np.random.default_rng(4)
+    n, e = 300, 16
+    corpus = rng.standard_normal((n, e)).astype(np.float32)
+    ids = np.array([f"id{i}" for i in range(n)], dtype=object)
+    ids[200:220] = ids[0:20]                                   # twenty identifiers occur twice
+    corpus[200:220] = corpus[0:20] * 1.5                       # ... and the SECOND row scores higher for queries along that row
+    index = BruteForceIndex(5, Ident(), [(ids, corpus)])
+    assert index.canonical_rows() is not None
+    q = corpus[:40].copy()                                     # query b is most similar to rows b (and 200 + b for b < 20)
+    truth = ids[:40].reshape(-1, 1)
+    got = IndexRecall(index, ks=[1, 5])({"q": torch.from_numpy(q).cuda()}, truth)
+    cand = index({"q": torch.from_numpy(q).cuda()})            # identifiers, as the reference compares them
+    tb = np.array([t.encode() if isinstance(t, str) else t for t in truth.reshape(-1)]).reshape(-1, 1)
+    cb = np.array([[c.encode() if isinstance(c, str) else c for c in row] for row in cand])
+    want = {k: float(np.sum(tb == cb[:, :k])) / 40 for k in (1, 5)}
+    assert {k: float(v) for k, v in got.items()} == want
+    assert want[5] > 1.0 - 1e-9                                # the twenty duplicated ids are found twice within the top 5

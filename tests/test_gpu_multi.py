@@ -261,6 +261,13 @@ def _worker_owner_init(rank, world, port, out):
         la, lc = float(a.train_step(batches[rank])["loss"]), float(c.train_step(batches[rank])["loss"])
         a.dist.barrier(); c.dist.barrier()
         ta, tc = a.state_arrays(), c.state_arrays()
+        # five batch shapes on one model: the oldest step workspace is evicted and its peer-shared buffers are closed collectively
+        # (PeerBuffer.close); the evicted shape is rebuilt when it comes back
+        for bs in (64, 48, 32, 16):
+            more = float(c.train_step(_batch(rng, bs))["loss"])
+            assert np.isfinite(more)
+        again = float(c.train_step(batches[rank])["loss"])
+        assert np.isfinite(again) and len(c._steps) == 4
         np.savez(out, la=la, lc=lc, **{"a/" + k: v for k, v in sa.items()}, **{"b/" + k: v for k, v in sb.items()},
                  **{"ta/" + k: v for k, v in ta.items()}, **{"tc/" + k: v for k, v in tc.items()})
     finally:
