@@ -128,30 +128,6 @@ def batch_size_of(x) -> int:
     return int(shp[0]) if len(shp) else 1
 
 
-def stage_ids(value, vocab: Vocab, out):
-    """Fill the int32 device buffer ``out`` (B,) with row ids for one categorical feature.
-    Accepts: strings (host lookup), integer numpy arrays / torch tensors / DLPack exporters (already row ids)."""
-    torch = N.require_cuda()
-    value = unwrap(value)
-    if isinstance(value, torch.Tensor):
-        out.copy_(value.reshape(-1), non_blocking=True)
-        return
-    if is_string_like(value):
-        ids = vocab.encode(value)
-    else:
-        ids = np.ascontiguousarray(np.asarray(value).reshape(-1), dtype=np.int32)
-    out.copy_(torch.from_numpy(ids), non_blocking=True)
-
-
-def stage_floats(value, out):
-    torch = N.require_cuda()
-    value = unwrap(value)
-    if isinstance(value, torch.Tensor):
-        out.copy_(value.reshape(-1), non_blocking=True)
-        return
-    out.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(value).reshape(-1), dtype=np.float32)), non_blocking=True)
-
-
 class PinRing:
     """A few pinned host blocks of (n_cols, rows) 4-byte cells that host-resident feature columns are packed into before the staging
     kernel reads them in place.  A block is reused only after the kernel that read it has run (one event per block), so the host
