@@ -49,8 +49,10 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 // ---- scales ---------------------------------------------------------------------------------------------------
-// scal[0] sq  [1] sc  [2],[3] kmul = log2e / (sq*sc)  [4] 1/sq  [5] 1/sc ; bits[8] amax(Q) [9] amax(C) [10] ticket   (64 floats)
+// scal[0] sq  [1] sc  [2],[3] kmul = log2e / (sq*sc)  [4] 1/sq  [5] 1/sc ; [11] ticket of the loss reduction   (64 floats), followed
+// by the per-block maxima of fl_amax_kernel: part[0][kAmaxBlocksMax] for Q, part[1][kAmaxBlocksMax] for C (float bit patterns)
 constexpr int kScalFloats = 64;
+constexpr int kAmaxBlocksMax = 512;
 
 __device__ __forceinline__ float pow2_scale_for(uint32_t amax_bits) {
     const int e = (int)(amax_bits >> 23);                       // biased exponent of the largest magnitude
@@ -61,12 +63,14 @@ __device__ __forceinline__ float pow2_scale_for(uint32_t amax_bits) {
 }
 
 struct AmaxArgs { const float* X[2]; int ld[2]; int n[2]; int E; };
+// Every block leaves the largest magnitudes it saw (as float bit patterns: non-negative floats order like integers) in part[t][block];
+// fl_convert_kernel reduces the <= 512 values per tensor itself.  No atomics, no ticket, nothing to zero beforehand (a memset node
+// and a last-block stage per call in the first version); block 0 also zeroes the loss reduction's ticket.
 __global__ void __launch_bounds__(256) fl_amax_kernel(const AmaxArgs a, float* __restrict__ scal) {
     pdl_trigger();
     pdl_wait();   // (the inputs may come from a kernel launched the same way)
-    uint32_t* bits = reinterpret_cast<uint32_t*>(scal) + 8;
+    uint32_t* part = reinterpret_cast<uint32_t*>(scal) + kScalFloats;
     __shared__ uint32_t s_max[2][8];
-    __shared__ bool s_last;
     uint32_t mx[2] = {0u, 0u};
     const int e4 = a.E >> 2;
     for (int t = 0; t < 2; ++t) {
@@ -84,25 +88,28 @@ __global__ void __launch_bounds__(256) fl_amax_kernel(const AmaxArgs a, float* _
         if ((threadIdx.x & 31) == 0) s_max[t][threadIdx.x >> 5] = mx[t];
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int t = 0; t < 2; ++t) {
-            uint32_t m = 0;
-            for (int w = 0; w < 8; ++w) m = max(m, s_max[t][w]);
-            atomicMax(bits + t, m);                              // integer max: order-independent, deterministic
-        }
-        __threadfence();
-        s_last = (atomicAdd(bits + 2, 1u) == gridDim.x - 1);
+    if (threadIdx.x < 2) {
+        const int t = threadIdx.x;
+        uint32_t m = 0;
+        for (int w = 0; w < 8; ++w) m = max(m, s_max[t][w]);
+        part[t * kAmaxBlocksMax + blockIdx.x] = m;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<uint32_t*>(scal)[11] = 0u;
+}
+
+// the two operand scales from the per-block maxima (every thread of the block returns the same pair)
+__device__ __forceinline__ void fl_block_scales(const float* __restrict__ scal, int nblk, float& sq, float& sc) {
+    __shared__ uint32_t s_red[2][8];
+    const uint32_t* part = reinterpret_cast<const uint32_t*>(scal) + kScalFloats;
+    uint32_t m0 = 0u, m1 = 0u;
+    for (int i = threadIdx.x; i < nblk; i += 256) { m0 = max(m0, part[i]); m1 = max(m1, part[kAmaxBlocksMax + i]); }
+    for (int o = 16; o > 0; o >>= 1) { m0 = max(m0, __shfl_xor_sync(0xffffffffu, m0, o)); m1 = max(m1, __shfl_xor_sync(0xffffffffu, m1, o)); }
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = m0; s_red[1][threadIdx.x >> 5] = m1; }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
-        const float sq = pow2_scale_for(reinterpret_cast<volatile uint32_t*>(bits)[0]);
-        const float sc = pow2_scale_for(reinterpret_cast<volatile uint32_t*>(bits)[1]);
-        scal[0] = sq; scal[1] = sc;
-        const float inv = (1.f / sq) * (1.f / sc);               // exact: powers of two, |exponent| <= 80
-        scal[2] = kLog2e * inv; scal[3] = kLog2e * inv;
-        scal[4] = 1.f / sq; scal[5] = 1.f / sc;
-    }
+    m0 = 0u; m1 = 0u;
+    for (int w = 0; w < 8; ++w) { m0 = max(m0, s_red[0][w]); m1 = max(m1, s_red[1][w]); }
+    sq = pow2_scale_for(m0);
+    sc = pow2_scale_for(m1);
 }
 
 // ---- operand copies, column terms, the positives' logits ------------------------------------------------------------------
@@ -114,12 +121,22 @@ struct CvtItem {
 // z_ii = Q[i] . C[i + off] - bias[i + off] from the fp32 operands (the positive is left out of the tensor-core products):
 // zd2[i] = z_ii * log2e for the pass-1 combine; with lse given (backward entry points) also pm1[i] = exp(z_ii - lse_i) - 1
 struct DiagItem { const float* Q; int ldq; const float* C; int ldc; const float* bias; const float* lse; int Bq, off; float* zd2; float* pm1; int blocks; };
-struct CvtArgs { CvtItem s[2]; int n; int E; DiagItem dg; };
-__global__ void __launch_bounds__(256) fl_convert_kernel(const CvtArgs a, const float* __restrict__ scal) {
+struct CvtArgs { CvtItem s[2]; int n; int E; DiagItem dg; int amax_blocks; };
+__global__ void __launch_bounds__(256) fl_convert_kernel(const CvtArgs a, float* __restrict__ scal) {
     pdl_trigger();
     pdl_wait();
     int b = blockIdx.x;
     const int e8 = a.E >> 3;
+    if (b == 0) {            // block 0 publishes the scales for the kernels that follow (they start after this grid has completed)
+        float sq, sc;
+        fl_block_scales(scal, a.amax_blocks, sq, sc);
+        if (threadIdx.x == 0) {
+            scal[0] = sq; scal[1] = sc;
+            const float inv = (1.f / sq) * (1.f / sc);           // exact: powers of two, |exponent| <= 80
+            scal[2] = kLog2e * inv; scal[3] = kLog2e * inv;
+            scal[4] = 1.f / sq; scal[5] = 1.f / sc;
+        }
+    }
     if (b < a.dg.blocks) {   // e8 consecutive lanes per row
         const int64_t idx = (int64_t)b * 256 + threadIdx.x;
         const int r = (int)(idx / e8), c8 = (int)(idx % e8);
@@ -143,10 +160,12 @@ __global__ void __launch_bounds__(256) fl_convert_kernel(const CvtArgs a, const 
     for (int i = 0; i < a.n; ++i) {
         const CvtItem& it = a.s[i];
         if (b < it.xblocks) {
+            float sq, sc;
+            fl_block_scales(scal, a.amax_blocks, sq, sc);        // (uniform per block; scal[0..1] may not have been written yet)
             const int64_t idx = (int64_t)b * 256 + threadIdx.x;
             if (idx < (int64_t)it.n * e8) {
                 const int r = (int)(idx / e8), c8 = (int)(idx % e8);
-                const float s = scal[it.which];
+                const float s = it.which == 0 ? sq : sc;
                 const float4 v0 = *reinterpret_cast<const float4*>(it.X + (int64_t)r * it.ld + 8 * c8);
                 const float4 v1 = *reinterpret_cast<const float4*>(it.X + (int64_t)r * it.ld + 8 * c8 + 4);
                 uint4 o;
@@ -391,7 +410,7 @@ static FlWs fl_carve(void* ws, int Bq, int Bc, int E) {
     const int bn = fl_bn(E);
     const int pad_c = (int)(ceil_div(Bc, bn) * bn) + 256, pad_q = (int)(ceil_div(Bq, bn) * bn) + 256;
     w.rowloss = cv.take<float>((size_t)(Bq > Bc ? Bq : Bc));      // first: the SIMT path keeps its row losses at the workspace base too
-    w.scal = cv.take<float>(kScalFloats);
+    w.scal = cv.take<float>(kScalFloats + 2 * kAmaxBlocksMax);
     w.Qh = cv.take<__half>((size_t)Bq * E);
     w.Ch = cv.take<__half>((size_t)Bc * E);
     w.c2_bias = cv.take<float>((size_t)pad_c);
@@ -399,7 +418,7 @@ static FlWs fl_carve(void* ws, int Bq, int Bc, int E) {
     w.pm1 = cv.take<float>((size_t)pad_q);
     w.zd2 = cv.take<float>((size_t)pad_q);
     w.block_sums = cv.take<double>((size_t)ceil_div(Bq, 256) + 64);
-    w.counter = reinterpret_cast<unsigned int*>(w.scal) + 11;     // zeroed with the amax words by fl_prepare's memset
+    w.counter = reinterpret_cast<unsigned int*>(w.scal) + 11;     // zeroed by block 0 of fl_amax_kernel
     // pass 1: R = Q, T = C
     int nR1[1] = {Bq}, nT1[1] = {Bc};
     FlPlan p1 = fl_plan(1, nR1, nT1, E);
@@ -424,21 +443,22 @@ size_t softmax_flash_workspace(int Bq, int Bc, int E) { return fl_carve(nullptr,
 static int fl_prepare(const FlWs& w, const float* Q, int ldq, const float* C, int ldc, const float* bias, const float* lse, int Bq, int Bc, int E,
                       int off, cudaStream_t st) {
     const int bn = fl_bn(E);
-    TT_CUDA_OK(cudaMemsetAsync(w.scal + 8, 0, 16, st));          // amax bits, ticket
     AmaxArgs aa{};
     aa.X[0] = Q; aa.ld[0] = ldq; aa.n[0] = Bq; aa.X[1] = C; aa.ld[1] = ldc; aa.n[1] = Bc; aa.E = E;
     int64_t work = ((int64_t)Bq + Bc) * (E / 4);
     int blocks = (int)ceil_div(work, 256 * 4);
     blocks = blocks > 2 * sm_count() ? 2 * sm_count() : (blocks < 1 ? 1 : blocks);
+    blocks = blocks > kAmaxBlocksMax ? kAmaxBlocksMax : blocks;
     TT_CUDA_OK(launch_pdl(fl_amax_kernel, dim3((unsigned)blocks), dim3(256), 0, st, aa, w.scal));
     TT_LAUNCH_OK("fl_amax_kernel");
     CvtArgs ca{};
     ca.E = E;
+    ca.amax_blocks = blocks;
     ca.dg = DiagItem{Q, ldq, C, ldc, bias, lse, Bq, off, w.zd2, w.pm1, (int)ceil_div((int64_t)Bq * (E / 8), 256)};
     int cb = ca.dg.blocks;
     cb += cvt_item(ca.s[ca.n++], Q, ldq, Bq, E, w.Qh, 0, lse, lse ? w.c2_lse : nullptr, Bq, (int)(ceil_div(Bq, bn) * bn), kLog2e);
     cb += cvt_item(ca.s[ca.n++], C, ldc, Bc, E, w.Ch, 1, bias, w.c2_bias, Bc, (int)(ceil_div(Bc, bn) * bn), kLog2e);
-    TT_CUDA_OK(launch_pdl(fl_convert_kernel, dim3((unsigned)cb), dim3(256), 0, st, ca, (const float*)w.scal));
+    TT_CUDA_OK(launch_pdl(fl_convert_kernel, dim3((unsigned)cb), dim3(256), 0, st, ca, w.scal));
     TT_LAUNCH_OK("fl_convert_kernel");
     return TT_OK;
 }
