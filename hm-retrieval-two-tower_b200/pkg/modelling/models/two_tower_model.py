@@ -5,15 +5,18 @@ TwoTowerModel: two Towers, dot-product logits, in-batch sampled softmax with opt
 train_step (reference :94-130) = tape -> logQ -> labels=eye(B) -> CE(from_logits, SUM) -> minimize.
 Here it is a fixed sequence of CUDA launches on pre-allocated buffers (optionally one CUDA graph):
 
-    side stream : radix-sort (id, position) of every embedding feature           tt_sparse_sort
-    main stream : gather + Dense per tower (fp32, + TF32 copy of Q and C)          tt_input_dense_fwd / tt_dense_fwd
-                  ln p(candidate) per column                                       tt_gather_concat on the ln-p row table
-                  S = Q.C^T, Z = S - ln p, LSE, loss   (S never leaves the SM)     tt_inbatch_softmax_fwd
-                  dQ = dZ.C, dC = dZ^T.Q               (S recomputed per tile)     tt_inbatch_softmax_bwd
-                  Dense backward per tower (dW, db, dX)                            tt_dense_bwd
-                  [data parallel: all-reduce dense grads, all-gather (ids, dX)]    torch.distributed / NCCL
-                  Adagrad | Adam on the flat Dense buffer                          tt_dense_adagrad | tt_dense_adam
-                  join side stream; de-duplicated row update of every table        tt_sparse_adagrad | tt_sparse_adam
+    (eager)     : every id / numeric column of the batch into the staging buffers, one launch    tt_stage_columns
+    side stream : ln p(candidate) per column; radix pass 0 of the (id, position) sort          tt_gather_concat, tt_sparse_sort_passes
+    main / cand : gather + Dense per tower, the two towers on two streams (fp32)                tt_input_dense_fwd / tt_dense_fwd
+    main stream : S = Q.C^T, Z = S - ln p, LSE, loss, dQ, dC in ONE call -- two tensor-core      tt_inbatch_softmax_step
+                  passes on power-of-two scaled fp16 operand tiles, S never leaves the SM
+    side stream : the remaining radix pass (training batches sort in two 11-bit passes)          tt_sparse_sort_passes
+    main / cand : Dense backward per tower (dW, db, dX)                                          tt_dense_bwd
+                  [data parallel: device barriers; dense gradients summed, gradient rows         tt_peer_barrier, tt_peer_sum_f32
+                   pulled over NVLink peer memory -- pkg/modelling/distributed.py]
+                  Adagrad | Adam on the flat Dense buffer                                        tt_dense_adagrad | tt_dense_adam
+                  join side stream; de-duplicated row update of every table                      tt_sparse_adagrad | tt_sparse_adam
+The sort passes are placed so that no kernel runs beside the persistent softmax passes.
 """
 from __future__ import annotations
 
